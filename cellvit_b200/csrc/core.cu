@@ -1,0 +1,28 @@
+// core.cu -- error plumbing and device queries shared by every translation unit of libcellvit_b200.so.
+#include <stdarg.h>
+
+#include "common.cuh"
+
+static thread_local char g_err[1024] = "";
+
+void cvb_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int cvb_num_sms() {
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+    }
+    return sms;
+}
+
+extern "C" {
+__attribute__((visibility("default"))) int cvb_version(void) { return 100; }
+__attribute__((visibility("default"))) const char* cvb_last_error(void) { return g_err; }
+}

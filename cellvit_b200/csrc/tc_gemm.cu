@@ -1,0 +1,444 @@
+// tc_gemm.cu -- persistent, warp-specialised tcgen05 + TMA tile engine for sm_100a.
+//
+// One kernel serves every dense contraction of the CellViT forward:
+//   * linear layers (patch-embed, QKV, attn-out, MLP)                 -> GEMM mode
+//   * ConvTranspose2d k2 s2 (= GEMM with N = 4*Cout + scatter epilogue) -> GEMM mode, TC_EPI_CONVT
+//   * Conv3x3 pad 1 over NHWC fp16 (implicit GEMM)                     -> CONV mode: the A tile of tap (dy,dx)
+//     is one 4-D TMA box shifted by (dx-1, dy-1); out-of-image pixels are zero-filled by the TMA unit, so
+//     there is no im2col buffer. torch.cat([skip, x], 1) is a K-split over two tensor maps.
+//
+// CTA = 8 warps: w0 TMA producer (1 lane), w1 MMA issuer (1 lane), w2 TMEM allocator, w4..7 epilogue
+// (TMEM lane quadrant = warp & 3). Tile = 128 x block_n fp32 accumulator in TMEM, double buffered so the
+// epilogue of tile i overlaps the main loop of tile i+1. Operands are fp16 (11-bit mantissa: the reference's
+// own AMP mode, cell_detection.py:314-318), accumulation fp32.
+#include <cudaTypedefs.h>
+
+#include "tc_gemm.h"
+
+namespace {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;                       // 64 fp16 = one 128-byte swizzle atom
+constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;
+constexpr int MAX_STAGES = 8;
+constexpr int NUM_THREADS = 256;
+constexpr int SMEM_BUDGET = 200 * 1024;
+
+struct TcParams {
+    int M, N, K;
+    int block_n, n_tiles_n, n_tiles, num_kb, stages;
+    int conv;
+    int chunks0, chunks_per_tap;  // conv: 64-channel chunks of source 0 / of both sources
+    int H, W, TW;                 // conv geometry: image size, tile width (tile height = 128 / TW)
+    uint32_t tmem_cols;
+    TcEpilogue epi;
+};
+
+__device__ __forceinline__ int map_out_row(const TcEpilogue& e, int m) {
+    if (e.row_map == TC_ROW_IDENTITY) return m;
+    if (e.row_map == TC_ROW_SEQ) return m + (m / e.row_seq) * e.row_pad + e.row_off;
+    // TC_ROW_WINDOW (image_encoder.py:291-318 window_unpartition)
+    const int ws = e.win_size, g = e.win_grid;
+    const int per_img = g * g * ws * ws;
+    const int b = m / per_img;
+    int rem = m - b * per_img;
+    const int win = rem / (ws * ws);
+    const int t = rem - win * ws * ws;
+    const int y = (win / g) * ws + t / ws;
+    const int x = (win % g) * ws + t % ws;
+    if (y >= e.tok_h || x >= e.tok_w) return -1;
+    return (b * e.tok_h + y) * e.tok_w + x;
+}
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+    if (act == TC_ACT_RELU) return fmaxf(v, 0.0f);
+    if (act == TC_ACT_GELU) return gelu_erf(v);
+    return v;
+}
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+          const __grid_constant__ CUtensorMap tmB, const TcParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem_gen = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int stages = p.stages;
+    const uint32_t b_stage_bytes = (uint32_t)p.block_n * BLOCK_K * 2;
+    const uint32_t smem_a = smem_base;
+    const uint32_t smem_b = smem_a + stages * A_STAGE_BYTES;
+    const uint32_t bar_base = smem_b + stages * b_stage_bytes;
+    // barriers: full[s], empty[s], tmem_full[2], tmem_empty[2]
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (MAX_STAGES + s); };
+    auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * MAX_STAGES + s); };
+    auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * MAX_STAGES + 2 + s); };
+    const uint32_t tmem_slot = bar_base + 8u * (2 * MAX_STAGES + 4);
+    const uint32_t aux_off = (bar_base - smem_base) + 8u * (2 * MAX_STAGES + 4) + 16u;
+    float* head_w_s = reinterpret_cast<float*>(smem_gen + aux_off);  // [8*64] + [8]
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tmap(&tmA0);
+        ptx::prefetch_tmap(&tmB);
+        if (p.conv && p.chunks_per_tap > p.chunks0) ptx::prefetch_tmap(&tmA1);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < stages; ++s) {
+            ptx::mbar_init(full_bar(s), 1);
+            ptx::mbar_init(empty_bar(s), 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            ptx::mbar_init(tfull_bar(s), 1);
+            ptx::mbar_init(tempty_bar(s), 128);
+        }
+        ptx::fence_barrier_init();
+    }
+    if (warp == 2) {
+        ptx::tmem_alloc(tmem_slot, p.tmem_cols);
+        ptx::tmem_relinquish();
+    }
+    if (p.epi.kind == TC_EPI_HEAD && warp >= 4) {
+        const int t = threadIdx.x - 128;
+        for (int i = t; i < p.epi.head_nc * 64; i += 128) head_w_s[i] = p.epi.head_w[i];
+        if (t < p.epi.head_nc) head_w_s[8 * 64 + t] = p.epi.head_b[t];
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
+
+    const int num_kb = p.num_kb;
+
+    if (warp == 0 && lane == 0) {
+        // ===================================================== TMA producer
+        int stage = 0;
+        uint32_t phase = 0;
+        const uint32_t tx_bytes = A_STAGE_BYTES + b_stage_bytes;
+        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+            const int mt = tile / p.n_tiles_n, nt = tile - mt * p.n_tiles_n;
+            const int m0 = mt * BLOCK_M, n0 = nt * p.block_n;
+            int img = 0, y0 = 0, x0 = 0;
+            if (p.conv) {
+                const int hw = p.H * p.W;
+                img = m0 / hw;
+                const int rem = m0 - img * hw;
+                y0 = rem / p.W;
+                x0 = rem - y0 * p.W;
+            }
+            for (int kb = 0; kb < num_kb; ++kb) {
+                ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
+                ptx::mbar_expect_tx(full_bar(stage), tx_bytes);
+                const uint32_t dst_a = smem_a + stage * A_STAGE_BYTES;
+                if (!p.conv) {
+                    ptx::tma_load_2d(dst_a, &tmA0, full_bar(stage), kb * BLOCK_K, m0);
+                } else {
+                    const int tap = kb / p.chunks_per_tap;
+                    const int cc = kb - tap * p.chunks_per_tap;
+                    const int dy = tap / 3 - 1, dx = tap - (tap / 3) * 3 - 1;
+                    if (cc < p.chunks0)
+                        ptx::tma_load_4d(dst_a, &tmA0, full_bar(stage), cc * BLOCK_K, x0 + dx, y0 + dy, img);
+                    else
+                        ptx::tma_load_4d(dst_a, &tmA1, full_bar(stage), (cc - p.chunks0) * BLOCK_K, x0 + dx, y0 + dy,
+                                         img);
+                }
+                ptx::tma_load_2d(smem_b + stage * b_stage_bytes, &tmB, full_bar(stage), kb * BLOCK_K, n0);
+                if (++stage == stages) { stage = 0; phase ^= 1u; }
+            }
+        }
+    } else if (warp == 1 && lane == 0) {
+        // ===================================================== MMA issuer
+        // instruction descriptor: D=f32, A=B=f16, both K-major, N>>3 @17, M>>4 @24
+        const uint32_t idesc = (1u << 4) | ((uint32_t)(p.block_n >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+        // smem matrix descriptor: SWIZZLE_128B (2 @61), version 1 @46, SBO = 1024 B (8 rows x 128 B), LBO unused
+        const uint64_t desc_hi = (2ull << 61) | (1ull << 46) | ((uint64_t)(1024 >> 4) << 32);
+        int stage = 0;
+        uint32_t phase = 0;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+            const int as = it & 1;
+            const uint32_t aphase = (it >> 1) & 1;
+            ptx::mbar_wait(tempty_bar(as), aphase ^ 1u);
+            ptx::tc_fence_after();
+            const uint32_t d_tmem = tmem_base + (uint32_t)(as * p.block_n);
+            for (int kb = 0; kb < num_kb; ++kb) {
+                ptx::mbar_wait(full_bar(stage), phase);
+                ptx::tc_fence_after();
+                const uint64_t a_desc = desc_hi | (uint64_t)(((smem_a + stage * A_STAGE_BYTES) >> 4) & 0x3FFF);
+                const uint64_t b_desc = desc_hi | (uint64_t)(((smem_b + stage * b_stage_bytes) >> 4) & 0x3FFF);
+#pragma unroll
+                for (int k = 0; k < BLOCK_K / 16; ++k)  // 16 fp16 = 32 B -> +2 in the (addr >> 4) field
+                    ptx::umma_f16(d_tmem, a_desc + 2u * k, b_desc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                ptx::umma_commit(empty_bar(stage));
+                if (kb == num_kb - 1) ptx::umma_commit(tfull_bar(as));
+                if (++stage == stages) { stage = 0; phase ^= 1u; }
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================================================== epilogue (TMEM -> registers -> global)
+        const TcEpilogue& e = p.epi;
+        const int quad = warp & 3;
+        const int r = quad * 32 + lane;
+        const int n_chunks = p.block_n / 32;  // block_n % 32 == 0 enforced on the host
+        int it = 0;
+        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+            const int as = it & 1;
+            const uint32_t aphase = (it >> 1) & 1;
+            const int mt = tile / p.n_tiles_n, nt = tile - mt * p.n_tiles_n;
+            const int m = mt * BLOCK_M + r, n0 = nt * p.block_n;
+            const bool row_ok = m < p.M;
+            ptx::mbar_wait(tfull_bar(as), aphase);
+            ptx::tc_fence_after();
+            const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * p.block_n);
+
+            if (e.kind == TC_EPI_HEAD) {
+                float v[64];
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    uint32_t acc[32];
+                    ptx::tmem_ld32(t_addr + c * 32, acc);
+                    ptx::tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const int n = c * 32 + j;
+                        v[n] = fmaxf(fmaf(__uint_as_float(acc[j]), __ldg(e.scale + n), __ldg(e.shift + n)), 0.0f);
+                    }
+                }
+                ptx::tc_fence_before();
+                ptx::mbar_arrive(tempty_bar(as));
+                if (row_ok) {
+                    const int img = m / e.head_hw, pix = m - img * e.head_hw;
+                    for (int k = 0; k < e.head_nc; ++k) {
+                        float s = head_w_s[8 * 64 + k];
+#pragma unroll
+                        for (int c = 0; c < 64; ++c) s = fmaf(head_w_s[k * 64 + c], v[c], s);
+                        e.head_out[((size_t)img * e.head_nc + k) * e.head_hw + pix] = s;
+                    }
+                }
+                continue;
+            }
+
+            int orow = -1;
+            size_t out_off = 0;
+            int ct_b = 0, ct_y = 0, ct_x = 0;
+            if (row_ok) {
+                if (e.kind == TC_EPI_CONVT) {
+                    const int hw = e.ct_hin * e.ct_win;
+                    ct_b = m / hw;
+                    const int rem = m - ct_b * hw;
+                    ct_y = rem / e.ct_win;
+                    ct_x = rem - ct_y * e.ct_win;
+                    orow = m;
+                } else {
+                    orow = map_out_row(e, m);
+                    out_off = (size_t)(orow < 0 ? 0 : orow) * (size_t)e.ldc;
+                }
+            }
+            const float* res_row = nullptr;
+            if (e.kind == TC_EPI_RES_F32 && e.res != nullptr && orow >= 0) {
+                const long long rr = e.res_mod > 0 ? (long long)(m % e.res_mod) + e.res_off : (long long)orow;
+                res_row = e.res + rr * e.ldres;
+            }
+
+            for (int c = 0; c < n_chunks; ++c) {
+                uint32_t acc[32];
+                ptx::tmem_ld32(t_addr + c * 32, acc);
+                ptx::tmem_ld_wait();
+                if (c == n_chunks - 1) {
+                    ptx::tc_fence_before();
+                    ptx::mbar_arrive(tempty_bar(as));
+                }
+                if (orow < 0) continue;
+                const int nb = n0 + c * 32;
+                if (e.kind == TC_EPI_F16) {
+                    __half* o = reinterpret_cast<__half*>(e.out) + out_off + nb;
+#pragma unroll
+                    for (int j = 0; j < 32; j += 8) {
+                        uint32_t pk[4];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const int n = nb + j + 2 * q;
+                            float a = __uint_as_float(acc[j + 2 * q]), b = __uint_as_float(acc[j + 2 * q + 1]);
+                            const float s0 = e.scale ? __ldg(e.scale + n) : 1.0f, s1 = e.scale ? __ldg(e.scale + n + 1) : 1.0f;
+                            const float h0 = e.shift ? __ldg(e.shift + n) : 0.0f, h1 = e.shift ? __ldg(e.shift + n + 1) : 0.0f;
+                            a = apply_act(fmaf(a, s0, h0), e.act);
+                            b = apply_act(fmaf(b, s1, h1), e.act);
+                            pk[q] = pack_h2(a, b);
+                        }
+                        *reinterpret_cast<uint4*>(o + j) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                    }
+                } else if (e.kind == TC_EPI_RES_F32) {
+                    float* o = reinterpret_cast<float*>(e.out) + out_off + nb;
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        float4 rv = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (res_row) rv = *reinterpret_cast<const float4*>(res_row + nb + j);
+                        float4 sv = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (e.shift) sv = __ldg(reinterpret_cast<const float4*>(e.shift + nb + j));
+                        float4 ov;
+                        ov.x = __uint_as_float(acc[j + 0]) + sv.x + rv.x;
+                        ov.y = __uint_as_float(acc[j + 1]) + sv.y + rv.y;
+                        ov.z = __uint_as_float(acc[j + 2]) + sv.z + rv.z;
+                        ov.w = __uint_as_float(acc[j + 3]) + sv.w + rv.w;
+                        *reinterpret_cast<float4*>(o + j) = ov;
+                    }
+                } else {  // TC_EPI_CONVT: 32 consecutive n share (dy,dx) because Cout % 32 == 0
+                    const int q = nb / e.ct_cout, co = nb - q * e.ct_cout;
+                    const int dy = q >> 1, dx = q & 1;
+                    const size_t opix = ((size_t)ct_b * (2 * e.ct_hin) + (2 * ct_y + dy)) * (size_t)(2 * e.ct_win) + (2 * ct_x + dx);
+                    __half* o = reinterpret_cast<__half*>(e.out) + opix * (size_t)e.ldc + co;
+#pragma unroll
+                    for (int j = 0; j < 32; j += 8) {
+                        uint32_t pk[4];
+#pragma unroll
+                        for (int t = 0; t < 4; ++t) {
+                            const float h0 = e.shift ? __ldg(e.shift + co + j + 2 * t) : 0.0f;
+                            const float h1 = e.shift ? __ldg(e.shift + co + j + 2 * t + 1) : 0.0f;
+                            pk[t] = pack_h2(__uint_as_float(acc[j + 2 * t]) + h0, __uint_as_float(acc[j + 2 * t + 1]) + h1);
+                        }
+                        *reinterpret_cast<uint4*>(o + j) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                    }
+                }
+            }
+        }
+    }
+
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    if (warp == 2) ptx::tmem_dealloc(tmem_base, p.tmem_cols);
+}
+
+// ------------------------------------------------------------------------------------------- host side
+PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
+    static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+    }
+    return fn;
+}
+
+int make_tmap(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+              const uint32_t* box) {
+    auto fn = get_encode_fn();
+    CVB_CHECK(fn != nullptr, CVB_ECUDA, "cuTensorMapEncodeTiled entry point not available");
+    uint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes,
+                    box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CVB_CHECK(r == CUDA_SUCCESS, CVB_ECUDA, "cuTensorMapEncodeTiled failed with CUresult %d (rank %d, base %p)", (int)r,
+              rank, base);
+    return CVB_OK;
+}
+
+int check_epilogue(const TcEpilogue& e, int N, int block_n) {
+    CVB_CHECK(block_n >= 32 && block_n <= 256 && block_n % 32 == 0 && N % block_n == 0, CVB_ESHAPE,
+              "tc: block_n %d must be a multiple of 32 in [32,256] dividing N=%d", block_n, N);
+    if (e.kind == TC_EPI_F16 || e.kind == TC_EPI_RES_F32)
+        CVB_CHECK(e.out != nullptr && e.ldc % 8 == 0, CVB_EARG, "tc: epilogue needs out and ldc %% 8 == 0");
+    if (e.kind == TC_EPI_CONVT)
+        CVB_CHECK(e.out != nullptr && e.ct_cout % 32 == 0 && N == 4 * e.ct_cout && e.ldc % 8 == 0, CVB_ESHAPE,
+                  "tc: CONVT needs Cout %% 32 == 0 and N == 4*Cout");
+    if (e.kind == TC_EPI_HEAD)
+        CVB_CHECK(N == 64 && block_n == 64 && e.head_nc >= 1 && e.head_nc <= 8 && e.head_out && e.head_w && e.head_b &&
+                      e.scale && e.shift,
+                  CVB_ESHAPE, "tc: HEAD epilogue needs N == 64, 1..8 classes, scale and shift");
+    if (e.row_map == TC_ROW_WINDOW)
+        CVB_CHECK(e.win_size > 0 && e.win_grid > 0 && e.tok_h > 0 && e.tok_w > 0, CVB_EARG, "tc: bad window map");
+    if (e.row_map == TC_ROW_SEQ) CVB_CHECK(e.row_seq > 0, CVB_EARG, "tc: bad seq map");
+    return CVB_OK;
+}
+
+int launch(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, TcParams& p, cudaStream_t stream) {
+    const int b_stage = p.block_n * BLOCK_K * 2;
+    int stages = SMEM_BUDGET / (A_STAGE_BYTES + b_stage);
+    if (stages > MAX_STAGES) stages = MAX_STAGES;
+    p.stages = stages;
+    uint32_t cols = 32;
+    while (cols < (uint32_t)(2 * p.block_n)) cols <<= 1;
+    p.tmem_cols = cols;
+    // 1024 B alignment slack + stages + barriers/tmem slot + head weights; always > half an SM so that
+    // one CTA (and one 512-column TMEM allocation) lives on an SM at a time.
+    size_t smem = 1024 + (size_t)stages * (A_STAGE_BYTES + b_stage) + 8 * (2 * MAX_STAGES + 4) + 16 + (8 * 64 + 8) * 4;
+    if (smem < 120 * 1024) smem = 120 * 1024;
+    static size_t configured = 0;
+    if (smem > configured) {
+        CVB_CUDA(cudaFuncSetAttribute(tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
+        configured = 227 * 1024;
+    }
+    p.n_tiles_n = p.N / p.block_n;
+    p.n_tiles = cdiv(p.M, BLOCK_M) * p.n_tiles_n;
+    int grid = p.n_tiles < cvb_num_sms() ? p.n_tiles : cvb_num_sms();
+    tc_kernel<<<grid, NUM_THREADS, smem, stream>>>(a0, a1, b, p);
+    CVB_CUDA(cudaGetLastError());
+    return CVB_OK;
+}
+
+}  // namespace
+
+int tc_pick_block_n(int n) {
+    for (int bn = 256; bn >= 32; bn -= 32)
+        if (n % bn == 0) return bn;
+    return 0;
+}
+
+int tc_gemm(const __half* A, int M, int K, long long lda, const __half* W, int N, long long ldw, int block_n,
+            const TcEpilogue& epi, cudaStream_t stream) {
+    CVB_CHECK(A && W && M > 0 && N > 0 && K > 0, CVB_EARG, "tc_gemm: null operand or empty shape");
+    CVB_CHECK(K % BLOCK_K == 0 && lda % 8 == 0 && ldw % 8 == 0, CVB_ESHAPE,
+              "tc_gemm: K=%d must be a multiple of 64 and lda/ldw multiples of 8", K);
+    CVB_CHECK(((uintptr_t)A & 15) == 0 && ((uintptr_t)W & 15) == 0, CVB_EARG, "tc_gemm: operands must be 16-byte aligned");
+    CVB_TRY(check_epilogue(epi, N, block_n));
+    CUtensorMap ta, tb;
+    {
+        uint64_t dims[2] = {(uint64_t)K, (uint64_t)M};
+        uint64_t str[1] = {(uint64_t)lda * 2};
+        uint32_t box[2] = {BLOCK_K, BLOCK_M};
+        CVB_TRY(make_tmap(&ta, A, 2, dims, str, box));
+    }
+    {
+        uint64_t dims[2] = {(uint64_t)K, (uint64_t)N};
+        uint64_t str[1] = {(uint64_t)ldw * 2};
+        uint32_t box[2] = {BLOCK_K, (uint32_t)block_n};
+        CVB_TRY(make_tmap(&tb, W, 2, dims, str, box));
+    }
+    TcParams p{};
+    p.M = M; p.N = N; p.K = K; p.block_n = block_n; p.num_kb = K / BLOCK_K; p.conv = 0; p.epi = epi;
+    return launch(ta, ta, tb, p, stream);
+}
+
+int tc_conv3x3(const __half* src0, int C0, const __half* src1, int C1, int NB, int H, int W, const __half* Wp,
+               int N, int block_n, const TcEpilogue& epi, cudaStream_t stream) {
+    CVB_CHECK(src0 && Wp && NB > 0 && H > 0 && W > 0, CVB_EARG, "tc_conv3x3: null operand or empty shape");
+    if (!src1) C1 = 0;
+    CVB_CHECK(C0 > 0 && C0 % 64 == 0 && C1 % 64 == 0, CVB_ESHAPE, "tc_conv3x3: channels (%d,%d) must be multiples of 64", C0, C1);
+    const int TW = W < BLOCK_M ? W : BLOCK_M;
+    CVB_CHECK(BLOCK_M % TW == 0 && W % TW == 0 && H % (BLOCK_M / TW) == 0, CVB_ESHAPE,
+              "tc_conv3x3: image %dx%d does not tile into 128-pixel blocks", H, W);
+    CVB_TRY(check_epilogue(epi, N, block_n));
+    const int TH = BLOCK_M / TW;
+    CUtensorMap t0, t1, tb;
+    auto mk = [&](CUtensorMap* tm, const __half* src, int C) {
+        uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)NB};
+        uint64_t str[3] = {(uint64_t)C * 2, (uint64_t)W * C * 2, (uint64_t)H * W * C * 2};
+        uint32_t box[4] = {BLOCK_K, (uint32_t)TW, (uint32_t)TH, 1};
+        return make_tmap(tm, src, 4, dims, str, box);
+    };
+    CVB_TRY(mk(&t0, src0, C0));
+    if (C1 > 0) CVB_TRY(mk(&t1, src1, C1)); else t1 = t0;
+    const int K = 9 * (C0 + C1);
+    {
+        uint64_t dims[2] = {(uint64_t)K, (uint64_t)N};
+        uint64_t str[1] = {(uint64_t)K * 2};
+        uint32_t box[2] = {BLOCK_K, (uint32_t)block_n};
+        CVB_TRY(make_tmap(&tb, Wp, 2, dims, str, box));
+    }
+    TcParams p{};
+    p.M = NB * H * W; p.N = N; p.K = K; p.block_n = block_n; p.num_kb = K / BLOCK_K; p.conv = 1;
+    p.chunks0 = C0 / 64; p.chunks_per_tap = (C0 + C1) / 64; p.H = H; p.W = W; p.TW = TW; p.epi = epi;
+    return launch(t0, t1, tb, p, stream);
+}
