@@ -1,0 +1,250 @@
+# -*- coding: utf-8 -*-
+"""Drop-in mirrors of the reference model classes for the tile-inference path.
+
+``CellViT`` / ``CellViT256`` / ``CellViTSAM`` keep the reference constructor signatures, public attributes,
+``state_dict`` keys (so reference checkpoints ``load_state_dict(strict=True)``), ``forward`` contract and the
+``calculate_instance_map`` / ``generate_instance_nuclei_map`` helpers
+(models/segmentation/cell_segmentation/cellvit.py:26-151, 153-210, 332-414, 428-494, 496-667).
+
+The forward itself runs entirely in libcellvit_b200.so (``cvb_forward``): there is no PyTorch/CPU fallback --
+calling it without the CUDA library or on CPU tensors raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from collections import OrderedDict
+from typing import List, Tuple
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _lib as L
+from . import packing, weights
+
+
+class ModelDesc(C.Structure):
+    _fields_ = [("sam", C.c_int), ("embed_dim", C.c_int), ("depth", C.c_int), ("num_heads", C.c_int),
+                ("window_size", C.c_int), ("n_global", C.c_int), ("global_idx", C.c_int * 8), ("extract", C.c_int * 4),
+                ("n_np_out", C.c_int), ("n_nt", C.c_int), ("n_tissue", C.c_int), ("skip11", C.c_int), ("skip12", C.c_int),
+                ("bott_pad", C.c_int)]
+
+
+class _Node(nn.Module):
+    """Anonymous container so that dotted reference keys map onto a module tree."""
+
+
+def _build_tree(root: nn.Module, spec, seed: int):
+    for key, (shape, kind) in spec.items():
+        parts = key.split(".")
+        mod = root
+        for p in parts[:-1]:
+            if p not in mod._modules:
+                mod.add_module(p, _Node())
+            mod = mod._modules[p]
+        t = weights.synth_tensor(key, shape, kind, seed)
+        if kind in ("bn_mean", "bn_var", "bn_nbt"):
+            mod.register_buffer(parts[-1], t)
+        else:
+            mod.register_parameter(parts[-1], nn.Parameter(t))
+
+
+class CellViT(nn.Module):
+    """cellvit.py:26-151 -- ViT encoder + three U-Net style decoder branches (NP, HV, NT) + tissue logits."""
+
+    def __init__(self, num_nuclei_classes: int, num_tissue_classes: int, embed_dim: int, input_channels: int,
+                 depth: int, num_heads: int, extract_layers: List, mlp_ratio: float = 4, qkv_bias: bool = True,
+                 drop_rate: float = 0, attn_drop_rate: float = 0, drop_path_rate: float = 0,
+                 regression_loss: bool = False, _arch: str = "ViT256"):
+        super().__init__()
+        assert len(extract_layers) == 4, "Please provide 4 layers for skip connections"
+        if input_channels != 3 or mlp_ratio != 4 or not qkv_bias:
+            raise NotImplementedError("cellvit_b200 supports input_channels=3, mlp_ratio=4, qkv_bias=True")
+        self.patch_size = 16
+        self.num_tissue_classes = num_tissue_classes
+        self.num_nuclei_classes = num_nuclei_classes
+        self.embed_dim = embed_dim
+        self.input_channels = input_channels
+        self.depth = depth
+        self.num_heads = num_heads
+        self.mlp_ratio = mlp_ratio
+        self.qkv_bias = qkv_bias
+        self.extract_layers = extract_layers
+        self.drop_rate = drop_rate
+        self.attn_drop_rate = attn_drop_rate
+        self.drop_path_rate = drop_path_rate
+        self.regression_loss = regression_loss
+        self.skip_dim_11, self.skip_dim_12, self.bottleneck_dim = weights.decoder_dims(embed_dim)
+        self.branches_output = {"nuclei_binary_map": 2 + (2 if regression_loss else 0), "hv_map": 2,
+                                "nuclei_type_maps": num_nuclei_classes}
+        self._arch = _arch
+        self._sam = _arch != "ViT256"
+        self._global_idx = tuple(weights.SAM_CFG[_arch]["global_idx"]) if self._sam else ()
+        spec = weights.state_spec(_arch, num_nuclei_classes, num_tissue_classes, regression_loss,
+                                  embed_dim=embed_dim, depth=depth, num_heads=num_heads)
+        _build_tree(self, spec, seed=int(torch.initial_seed() & 0xFFFF))
+        self._handle = None
+        self._packed = {}        # name -> device tensor (kept alive for the C side)
+        self._packed_key = None  # (device, param versions)
+        self._size_key = None
+        self._ws = None
+
+    # ------------------------------------------------------------------ engine plumbing
+    def _cfg(self):
+        return dict(sam=self._sam, embed_dim=self.embed_dim, depth=self.depth, num_heads=self.num_heads, window=14,
+                    global_idx=self._global_idx, skip11=self.skip_dim_11, skip12=self.skip_dim_12, bott=self.bottleneck_dim)
+
+    def _ensure_handle(self):
+        if self._handle is None:
+            d = ModelDesc(sam=int(self._sam), embed_dim=self.embed_dim, depth=self.depth, num_heads=self.num_heads,
+                          window_size=14 if self._sam else 0, n_global=len(self._global_idx),
+                          n_np_out=self.branches_output["nuclei_binary_map"], n_nt=self.num_nuclei_classes,
+                          n_tissue=self.num_tissue_classes, skip11=self.skip_dim_11, skip12=self.skip_dim_12,
+                          bott_pad=packing.pad64(self.bottleneck_dim))
+            for i, g in enumerate(self._global_idx):
+                d.global_idx[i] = g
+            for i, e in enumerate(self.extract_layers):
+                d.extract[i] = int(e)
+            h = C.c_void_p()
+            L.check(L.lib().cvb_model_create(C.byref(d), C.byref(h)), "cvb_model_create")
+            self._handle = h
+        return self._handle
+
+    def _register(self, tensors):
+        lib = L.lib()
+        for name, t in tensors.items():
+            self._packed[name] = t
+            L.check(lib.cvb_model_set_param(self._handle, name.encode(), C.c_void_p(t.data_ptr())), "cvb_model_set_param")
+
+    def _ensure_packed(self, device, h, w):
+        self._ensure_handle()
+        sd = OrderedDict((k, v) for k, v in self.state_dict().items())
+        key = (str(device), tuple(int(v._version) for v in sd.values()), tuple(v.data_ptr() for v in sd.values()))
+        if key != self._packed_key:
+            sd_dev = {k: v.to(device) for k, v in sd.items()}
+            self._register(packing.pack_static(sd_dev, self._cfg()))
+            self._packed_key, self._size_key = key, None
+        if self._size_key != (h, w):
+            sd_dev = {k: v.to(device) for k, v in sd.items() if k.startswith("encoder.pos_embed") or "rel_pos" in k or "cls_token" in k}
+            self._register(packing.pack_for_size(sd_dev, self._cfg(), h, w))
+            self._size_key = (h, w)
+
+    def __del__(self):
+        try:
+            if self._handle is not None:
+                L.lib().cvb_model_destroy(self._handle)
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ reference API
+    def forward(self, x: torch.Tensor, retrieve_tokens: bool = False) -> dict:
+        """cellvit.py:153-210 / :586-644. Raw logits, fp32, on x.device."""
+        assert x.shape[-2] % self.patch_size == 0, "Input images must be divisible by the patch size"
+        assert x.shape[-1] % self.patch_size == 0, "Input images must be divisible by the patch size"
+        if not x.is_cuda:
+            raise RuntimeError("cellvit_b200 has no CPU path: move the input to a CUDA device")
+        B, Cin, H, W = x.shape
+        assert Cin == 3
+        x = x.contiguous().float()
+        h, w = H // 16, W // 16
+        with torch.cuda.device(x.device):
+            self._ensure_packed(x.device, h, w)
+            lib = L.lib()
+            need = C.c_size_t()
+            L.check(lib.cvb_model_workspace_bytes(self._handle, B, H, W, C.byref(need)), "cvb_model_workspace_bytes")
+            if self._ws is None or self._ws.numel() < need.value or self._ws.device != x.device:
+                self._ws = torch.empty(need.value, dtype=torch.uint8, device=x.device)
+            n_np = self.branches_output["nuclei_binary_map"]
+            o_np = torch.empty(B, n_np, H, W, device=x.device)
+            o_hv = torch.empty(B, 2, H, W, device=x.device)
+            o_nt = torch.empty(B, self.num_nuclei_classes, H, W, device=x.device)
+            o_ti = torch.empty(B, self.num_tissue_classes, device=x.device)
+            o_tok = torch.empty(B, self.embed_dim, h, w, device=x.device) if retrieve_tokens else None
+            L.check(lib.cvb_forward(self._handle, L.ptr(x), B, H, W, L.ptr(o_np), L.ptr(o_hv), L.ptr(o_nt), L.ptr(o_ti),
+                                    L.ptr(o_tok), L.ptr(self._ws), C.c_size_t(self._ws.numel()), L.stream_ptr()), "cvb_forward")
+        out = {"tissue_types": o_ti}
+        if self.regression_loss:
+            out["nuclei_binary_map"], out["regression_map"] = o_np[:, :2], o_np[:, 2:]
+        else:
+            out["nuclei_binary_map"] = o_np
+        out["hv_map"] = o_hv
+        out["nuclei_type_map"] = o_nt
+        if retrieve_tokens:
+            out["tokens"] = o_tok
+        return out
+
+    def calculate_instance_map(self, predictions: OrderedDict, magnification=40) -> Tuple[torch.Tensor, List[dict]]:
+        """cellvit.py:332-383. ``predictions`` hold post-softmax NP/NT maps [B,C,H,W] and the HV map (only the argmax
+        of NP/NT is used). Returns (float32 CPU tensor [B,H,W], list of per-tile instance dicts)."""
+        from .post_proc_cellvit import DetectionCellPostProcessor
+        proc = DetectionCellPostProcessor(nr_types=self.num_nuclei_classes, magnification=magnification, gt=False)
+        labels, dicts = proc.post_process_batch(predictions["nuclei_binary_map"], predictions["hv_map"],
+                                                predictions["nuclei_type_map"])
+        return torch.Tensor(labels.cpu().numpy()).type(torch.float32), dicts
+
+    def generate_instance_nuclei_map(self, instance_maps: torch.Tensor, type_preds: List[dict]) -> torch.Tensor:
+        """cellvit.py:385-414."""
+        batch_size, hh, ww = instance_maps.shape
+        out = torch.zeros((batch_size, hh, ww, self.num_nuclei_classes))
+        for i in range(batch_size):
+            inst = torch.zeros((hh, ww, self.num_nuclei_classes))
+            for nuclei, spec in type_preds[i].items():
+                inst[:, :, spec["type"]][instance_maps[i] == nuclei] = nuclei
+            out[i] = inst
+        return out.permute(0, 3, 1, 2)
+
+    def freeze_encoder(self):
+        """cellvit.py:416-420 (the tissue head stays trainable)."""
+        for name, p in self._modules["encoder"].named_parameters():
+            if name.split(".")[0] != "head":
+                p.requires_grad = False
+
+    def unfreeze_encoder(self):
+        for p in self._modules["encoder"].parameters():
+            p.requires_grad = True
+
+
+class CellViT256(CellViT):
+    """cellvit.py:428-494 -- HIPT ViT-S/16 backbone (embed 384, depth 12, 6 heads, skips after 3/6/9/12)."""
+
+    def __init__(self, model256_path, num_nuclei_classes: int, num_tissue_classes: int, drop_rate: float = 0,
+                 attn_drop_rate: float = 0, drop_path_rate: float = 0, regression_loss: bool = False):
+        self.patch_size = 16
+        self.model256_path = model256_path
+        super().__init__(num_nuclei_classes=num_nuclei_classes, num_tissue_classes=num_tissue_classes, embed_dim=384,
+                         input_channels=3, depth=12, num_heads=6, extract_layers=[3, 6, 9, 12], mlp_ratio=4, qkv_bias=True,
+                         drop_rate=drop_rate, attn_drop_rate=attn_drop_rate, drop_path_rate=drop_path_rate,
+                         regression_loss=regression_loss, _arch="ViT256")
+
+    def load_pretrained_encoder(self, model256_path: str):
+        """cellvit.py:483-494: HIPT checkpoint, key 'teacher', strip 'module.' / 'backbone.' prefixes."""
+        state_dict = torch.load(str(model256_path), map_location="cpu")["teacher"]
+        state_dict = {k.replace("module.", ""): v for k, v in state_dict.items()}
+        state_dict = {k.replace("backbone.", ""): v for k, v in state_dict.items()}
+        own = self._modules["encoder"].state_dict()
+        msg = self._modules["encoder"].load_state_dict({k: v for k, v in state_dict.items() if k in own}, strict=False)
+        print(f"Loading checkpoint: {msg}")
+
+
+class CellViTSAM(CellViT):
+    """cellvit.py:496-667 -- SAM ViTDet backbone (SAM-B / SAM-L / SAM-H)."""
+
+    def __init__(self, model_path, num_nuclei_classes: int, num_tissue_classes: int, vit_structure, drop_rate: float = 0,
+                 regression_loss: bool = False):
+        if vit_structure.upper() not in weights.SAM_CFG:
+            raise NotImplementedError("Unknown ViT-SAM backbone structure")
+        cfg = weights.SAM_CFG[vit_structure.upper()]
+        self.model_path = model_path
+        super().__init__(num_nuclei_classes=num_nuclei_classes, num_tissue_classes=num_tissue_classes,
+                         embed_dim=cfg["embed_dim"], input_channels=3, depth=cfg["depth"], num_heads=cfg["num_heads"],
+                         extract_layers=list(cfg["extract"]), mlp_ratio=4, qkv_bias=True, drop_rate=drop_rate,
+                         attn_drop_rate=0, drop_path_rate=0, regression_loss=regression_loss, _arch=vit_structure.upper())
+        self.prompt_embed_dim = 256
+        self.encoder_global_attn_indexes = list(cfg["global_idx"])
+
+    def load_pretrained_encoder(self, model_path):
+        """cellvit.py:574-584: SAM image-encoder weights, strict=False."""
+        state_dict = torch.load(str(model_path), map_location="cpu")
+        own = self._modules["encoder"].state_dict()
+        msg = self._modules["encoder"].load_state_dict({k: v for k, v in state_dict.items() if k in own}, strict=False)
+        print(f"Loading checkpoint: {msg}")

@@ -20,4 +20,28 @@ CVB_API int cvb_op_conv3x3_f16(const void* src0, int C0, const void* src1, int C
                       (cudaStream_t)stream);
 }
 
+CVB_API int cvb_op_layernorm_f16(const float* x, const float* gamma, const float* beta, float eps, int rows_dst, int D,
+                                 void* out, int map, int B, int tok_h, int tok_w, int ws, int g, void* stream) {
+    return op_layernorm_f16(x, gamma, beta, eps, rows_dst, D, (__half*)out, map, B, tok_h, tok_w, ws, g, (cudaStream_t)stream);
+}
+
+CVB_API int cvb_op_relpos(const void* qkv, int Gb, int heads, int hd, int gh, int gw, const float* Rh, const float* Rw,
+                          float* rel_h, float* rel_w, void* stream) {
+    return op_relpos((const __half*)qkv, Gb, heads, hd, gh, gw, Rh, Rw, rel_h, rel_w, (cudaStream_t)stream);
+}
+
+CVB_API int cvb_op_attention(const void* qkv, int Gb, int S, int heads, int hd, float scale, const float* rel_h,
+                             const float* rel_w, int gh, int gw, void* out, void* stream) {
+    return op_attention((const __half*)qkv, Gb, S, heads, hd, scale, rel_h, rel_w, gh, gw, (__half*)out, (cudaStream_t)stream);
+}
+
+CVB_API int cvb_op_patch_im2col(const float* x, int B, int H, int W, int P, void* out, void* stream) {
+    return op_patch_im2col(x, B, H, W, P, (__half*)out, (cudaStream_t)stream);
+}
+
+CVB_API int cvb_op_stem_conv(const float* x, int B, int H, int W, const float* w, const float* scale, const float* shift,
+                             void* out, int cpad, void* stream) {
+    return op_stem_conv(x, B, H, W, w, scale, shift, (__half*)out, cpad, (cudaStream_t)stream);
+}
+
 CVB_API int cvb_tc_epilogue_bytes(void) { return (int)sizeof(TcEpilogue); }

@@ -1,0 +1,333 @@
+// model.cu -- the CellViT forward (ViT encoder + 3-branch U-Net decoder) sequenced over the tile engine and
+// the helper kernels. One call = one batch of tiles; no allocation, no synchronisation, every launch on the
+// caller's stream, so the whole forward can be captured into a CUDA graph.
+//
+// Reference behaviour followed (file:line in the reference tree):
+//   models/segmentation/cell_segmentation/cellvit.py:153-244   CellViT.forward / _forward_upsample
+//   models/segmentation/cell_segmentation/cellvit.py:586-644   CellViTSAM.forward
+//   models/segmentation/cell_segmentation/utils.py:149-233      encoder wrappers (skip extraction, tissue logits)
+//   models/encoders/VIT/SAM/image_encoder.py:177-392            SAM block / window attention / rel-pos
+//   models/encoders/VIT/vits_histo.py:172-247,404-415           ViT-S block / token preparation
+// The shared skip decoders decoder0..3 are evaluated once per batch (the reference re-evaluates them in each of
+// the three branch calls, cellvit.py:235-241; identical results in eval mode).
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/cellvit_b200.h"
+#include "ops.h"
+#include "tc_gemm.h"
+
+struct cvb_model {
+    cvb_model_desc d;
+    std::unordered_map<std::string, const void*> params;
+};
+
+namespace {
+
+struct Arena {
+    uint8_t* base;
+    size_t off, cap;
+    bool dry;
+    template <class T>
+    T* alloc(size_t n) {
+        off = align_up(off, 256);
+        T* p = reinterpret_cast<T*>(base + off);
+        off += n * sizeof(T);
+        return p;
+    }
+};
+
+struct Fwd {
+    cvb_model& m;
+    Arena& A;
+    cudaStream_t st;
+    int rc = CVB_OK;
+    std::string missing;
+
+    template <class T>
+    const T* P(const std::string& name) {
+        auto it = m.params.find(name);
+        if (it == m.params.end() || it->second == nullptr) {
+            if (!A.dry && rc == CVB_OK) {
+                rc = CVB_EARG;
+                cvb_set_error("cvb_forward: parameter '%s' was not registered", name.c_str());
+            }
+            return nullptr;
+        }
+        return reinterpret_cast<const T*>(it->second);
+    }
+    bool live() const { return !A.dry && rc == CVB_OK; }
+    void chk(int r) { if (rc == CVB_OK && r != CVB_OK) rc = r; }
+
+    static TcEpilogue epi0() { TcEpilogue e; memset(&e, 0, sizeof(e)); return e; }
+
+    void gemm(const __half* a, int M, int K, const std::string& w, int N, const TcEpilogue& e) {
+        const __half* wp = P<__half>(w);
+        if (live()) chk(tc_gemm(a, M, K, K, wp, N, K, tc_pick_block_n(N), e, st));
+    }
+
+    // Conv3x3 + folded BN + ReLU over (src0 || src1), NHWC fp16 -> NHWC fp16 [NB,H,W,N]
+    __half* conv_bn_relu(const __half* s0, int C0, const __half* s1, int C1, int NB, int H, int W, const std::string& name, int N) {
+        __half* out = A.alloc<__half>((size_t)NB * H * W * N);
+        TcEpilogue e = epi0();
+        e.kind = TC_EPI_F16; e.act = TC_ACT_RELU; e.out = out; e.ldc = N;
+        e.scale = P<float>(name + ".scale"); e.shift = P<float>(name + ".shift");
+        const __half* wp = P<__half>(name + ".w");
+        if (live()) chk(tc_conv3x3(s0, C0, s1, C1, NB, H, W, wp, N, tc_pick_block_n(N), e, st));
+        return out;
+    }
+    // ConvTranspose2d k2 s2 (+bias): [NB,hin,win,Cin] -> [NB,2hin,2win,Cout]
+    __half* conv_t(const __half* src, int Cin, int NB, int hin, int win, const std::string& name, int Cout) {
+        __half* out = A.alloc<__half>((size_t)NB * 4 * hin * win * Cout);
+        TcEpilogue e = epi0();
+        e.kind = TC_EPI_CONVT; e.out = out; e.ldc = Cout; e.shift = P<float>(name + ".b");
+        e.ct_cout = Cout; e.ct_hin = hin; e.ct_win = win;
+        const __half* wp = P<__half>(name + ".w");
+        if (live()) chk(tc_gemm(src, NB * hin * win, Cin, Cin, wp, 4 * Cout, Cin, tc_pick_block_n(4 * Cout), e, st));
+        return out;
+    }
+    // Deconv2DBlock (utils.py:46-86): ConvT -> Conv3x3 -> BN -> ReLU
+    __half* deconv_block(const __half* src, int Cin, int NB, int hin, int win, const std::string& name, int Cout) {
+        __half* t = conv_t(src, Cin, NB, hin, win, name + ".ct", Cout);
+        return conv_bn_relu(t, Cout, nullptr, 0, NB, 2 * hin, 2 * win, name + ".conv", Cout);
+    }
+};
+
+int pad64(int c) { return (c + 63) / 64 * 64; }
+
+int forward_impl(cvb_model& m, const float* x, int B, int H, int W, float* o_np, float* o_hv, float* o_nt, float* o_tissue,
+                 float* o_tokens, Arena& A, cudaStream_t st) {
+    const cvb_model_desc& d = m.d;
+    Fwd f{m, A, st};
+    const int h = H / 16, w = W / 16, T = h * w, D = d.embed_dim, heads = d.num_heads, hd = D / heads;
+    const bool sam = d.sam != 0;
+    const int Tx = sam ? T : T + 1;  // ViT-S carries a cls token (vits_histo.py:404-415)
+    const int skip = sam ? 0 : 1;
+    const float scale = 1.0f / sqrtf((float)hd);
+    const bool live = !A.dry;
+
+    // ------------------------------------------------------------------ patch embedding (+bias +pos)
+    __half* a0 = A.alloc<__half>((size_t)B * T * 768);
+    float* xs = A.alloc<float>((size_t)B * Tx * D);
+    if (live) f.chk(op_patch_im2col(x, B, H, W, 16, a0, st));
+    {
+        TcEpilogue e = Fwd::epi0();
+        e.kind = TC_EPI_RES_F32; e.out = xs; e.ldc = D; e.shift = f.P<float>("patch.b");
+        e.res = f.P<float>("pos"); e.ldres = D; e.res_mod = T; e.res_off = skip;
+        if (!sam) { e.row_map = TC_ROW_SEQ; e.row_seq = T; e.row_pad = 1; e.row_off = 1; }
+        f.gemm(a0, B * T, 768, "patch.w", D, e);
+        if (!sam) {
+            const float* cp = f.P<float>("clspos");
+            if (f.live())
+                for (int b = 0; b < B; ++b)
+                    CVB_CUDA(cudaMemcpyAsync(xs + (size_t)b * Tx * D, cp, (size_t)D * 4, cudaMemcpyDeviceToDevice, st));
+        }
+    }
+
+    // ------------------------------------------------------------------ transformer blocks
+    const int ws = sam ? d.window_size : 0;
+    const int g = ws > 0 ? (h + ws - 1) / ws : 0;
+    const int Tw = g * g * ws * ws;
+    const size_t rows_max = (size_t)B * (Tw > Tx ? Tw : Tx);
+    __half* ln = A.alloc<__half>(rows_max * D);
+    __half* qkv = A.alloc<__half>(rows_max * 3 * D);
+    __half* att = A.alloc<__half>(rows_max * D);
+    __half* hid = A.alloc<__half>((size_t)B * Tx * 4 * D);
+    float *relh = nullptr, *relw = nullptr;
+    if (sam) {
+        size_t n_g = (size_t)B * heads * T * (h > w ? h : w);
+        size_t n_w = (size_t)B * g * g * heads * ws * ws * ws;
+        relh = A.alloc<float>(n_g > n_w ? n_g : n_w);
+        relw = A.alloc<float>(n_g > n_w ? n_g : n_w);
+    }
+    __half* z[4];
+    for (int k = 0; k < 4; ++k) z[k] = A.alloc<__half>((size_t)B * T * D);
+
+    for (int i = 0; i < d.depth; ++i) {
+        const std::string p = "b" + std::to_string(i);
+        bool is_global = !sam;
+        for (int k = 0; k < d.n_global; ++k) is_global |= (d.global_idx[k] == i);
+        const bool win = sam && !is_global && ws > 0;
+        const int rows = win ? B * Tw : B * Tx;
+        const float* n1w = f.P<float>(p + ".n1.w");
+        const float* n1b = f.P<float>(p + ".n1.b");
+        if (f.live()) f.chk(op_layernorm_f16(xs, n1w, n1b, 1e-6f, rows, D, ln, win ? 1 : 0, B, h, w, ws, g, st));
+        {
+            TcEpilogue e = Fwd::epi0();
+            e.kind = TC_EPI_F16; e.out = qkv; e.ldc = 3 * D; e.shift = f.P<float>(p + ".qkv.b");
+            f.gemm(ln, rows, D, p + ".qkv.w", 3 * D, e);
+        }
+        const int Gb = win ? B * g * g : B, S = win ? ws * ws : Tx, gh = win ? ws : h, gw = win ? ws : w;
+        if (sam) {
+            const float* th = f.P<float>(p + ".relh");
+            const float* tw = f.P<float>(p + ".relw");
+            if (f.live()) f.chk(op_relpos(qkv, Gb, heads, hd, gh, gw, th, tw, relh, relw, st));
+        }
+        if (f.live()) f.chk(op_attention(qkv, Gb, S, heads, hd, scale, sam ? relh : nullptr, sam ? relw : nullptr, gh, gw, att, st));
+        {
+            TcEpilogue e = Fwd::epi0();
+            e.kind = TC_EPI_RES_F32; e.out = xs; e.ldc = D; e.res = xs; e.ldres = D; e.shift = f.P<float>(p + ".proj.b");
+            if (win) { e.row_map = TC_ROW_WINDOW; e.win_size = ws; e.win_grid = g; e.tok_h = h; e.tok_w = w; }
+            f.gemm(att, rows, D, p + ".proj.w", D, e);
+        }
+        const float* n2w = f.P<float>(p + ".n2.w");
+        const float* n2b = f.P<float>(p + ".n2.b");
+        if (f.live()) f.chk(op_layernorm_f16(xs, n2w, n2b, 1e-6f, B * Tx, D, ln, 0, B, h, w, ws, g, st));
+        {
+            TcEpilogue e = Fwd::epi0();
+            e.kind = TC_EPI_F16; e.act = TC_ACT_GELU; e.out = hid; e.ldc = 4 * D; e.shift = f.P<float>(p + ".fc1.b");
+            f.gemm(ln, B * Tx, D, p + ".fc1.w", 4 * D, e);
+        }
+        {
+            TcEpilogue e = Fwd::epi0();
+            e.kind = TC_EPI_RES_F32; e.out = xs; e.ldc = D; e.res = xs; e.ldres = D; e.shift = f.P<float>(p + ".fc2.b");
+            f.gemm(hid, B * Tx, 4 * D, p + ".fc2.w", D, e);
+        }
+        for (int k = 0; k < 4; ++k)
+            if (d.extract[k] == i + 1) {
+                if (f.live()) f.chk(op_cast_rows_f16(xs, B, Tx, skip, D, z[k], st));
+                if (k == 3 && o_tokens && f.live()) f.chk(op_tokens_nchw(xs, B, Tx, skip, D, o_tokens, st));
+            }
+    }
+
+    // ------------------------------------------------------------------ tissue classifier
+    if (sam) {
+        // neck: conv1x1 -> LayerNorm2d -> conv3x3 -> LayerNorm2d -> spatial mean -> Linear (image_encoder.py:97-113)
+        __half* xf = A.alloc<__half>((size_t)B * T * D);
+        float* n0 = A.alloc<float>((size_t)B * T * 256);
+        __half* n1 = A.alloc<__half>((size_t)B * T * 256);
+        float* n2 = A.alloc<float>((size_t)B * T * 256);
+        if (f.live()) f.chk(op_cast_rows_f16(xs, B, Tx, 0, D, xf, st));
+        TcEpilogue e = Fwd::epi0();
+        e.kind = TC_EPI_RES_F32; e.out = n0; e.ldc = 256;
+        f.gemm(xf, B * T, D, "neck.0.w", 256, e);
+        const float* g1 = f.P<float>("neck.1.w");
+        const float* b1 = f.P<float>("neck.1.b");
+        if (f.live()) f.chk(op_layernorm_f16(n0, g1, b1, 1e-6f, B * T, 256, n1, 0, B, h, w, 0, 0, st));
+        e.out = n2;
+        const __half* w2 = f.P<__half>("neck.2.w");
+        if (f.live()) f.chk(tc_conv3x3(n1, 256, nullptr, 0, B, h, w, w2, 256, 256, e, st));
+        const float* g3 = f.P<float>("neck.3.w");
+        const float* b3 = f.P<float>("neck.3.b");
+        const float* cw = f.P<float>("cls.w");
+        const float* cb = f.P<float>("cls.b");
+        if (f.live() && o_tissue) f.chk(op_ln_mean_linear(n2, B, T, 256, g3, b3, 1e-6f, cw, cb, d.n_tissue, o_tissue, st));
+    } else {
+        const float* gw_ = f.P<float>("norm.w");
+        const float* gb_ = f.P<float>("norm.b");
+        const float* hw = f.P<float>("head.w");
+        const float* hb = f.P<float>("head.b");
+        if (f.live() && o_tissue) f.chk(op_cls_head(xs, B, Tx, D, gw_, gb_, 1e-6f, hw, hb, d.n_tissue, o_tissue, st));
+    }
+
+    // ------------------------------------------------------------------ shared skip decoders (cellvit.py:116-131)
+    const int s11 = d.skip11, s12 = d.skip12, bt = d.bott_pad;
+    __half* st0 = A.alloc<__half>((size_t)B * H * W * 64);
+    {
+        const float* sw = f.P<float>("decoder0.0.w");
+        const float* sc = f.P<float>("decoder0.0.scale");
+        const float* sh = f.P<float>("decoder0.0.shift");
+        if (f.live()) f.chk(op_stem_conv(x, B, H, W, sw, sc, sh, st0, 64, st));
+    }
+    __half* s0 = f.conv_bn_relu(st0, 64, nullptr, 0, B, H, W, "decoder0.1", 64);
+    __half* s1 = f.deconv_block(z[0], D, B, h, w, "decoder1.0", s11);
+    s1 = f.deconv_block(s1, s11, B, 2 * h, 2 * w, "decoder1.1", s12);
+    s1 = f.deconv_block(s1, s12, B, 4 * h, 4 * w, "decoder1.2", 128);
+    __half* s2 = f.deconv_block(z[1], D, B, h, w, "decoder2.0", s11);
+    s2 = f.deconv_block(s2, s11, B, 2 * h, 2 * w, "decoder2.1", 256);
+    __half* s3 = f.deconv_block(z[2], D, B, h, w, "decoder3.0", bt);
+
+    // ------------------------------------------------------------------ three upsampling branches (cellvit.py:212-244)
+    struct Br { const char* name; float* out; int nc; };
+    const Br branches[3] = {{"np", o_np, d.n_np_out}, {"hv", o_hv, 2}, {"nt", o_nt, d.n_nt}};
+    const size_t mark = A.off;
+    for (const Br& br : branches) {
+        A.off = mark;  // branch activations reuse the same arena region (stream order serialises the branches)
+        const std::string n = br.name;
+        __half* b = f.conv_t(z[3], D, B, h, w, n + ".bottleneck", bt);
+        b = f.conv_bn_relu(s3, bt, b, bt, B, 2 * h, 2 * w, n + ".d3.0", bt);
+        b = f.conv_bn_relu(b, bt, nullptr, 0, B, 2 * h, 2 * w, n + ".d3.1", bt);
+        b = f.conv_bn_relu(b, bt, nullptr, 0, B, 2 * h, 2 * w, n + ".d3.2", bt);
+        b = f.conv_t(b, bt, B, 2 * h, 2 * w, n + ".d3.ct", 256);
+        b = f.conv_bn_relu(s2, 256, b, 256, B, 4 * h, 4 * w, n + ".d2.0", 256);
+        b = f.conv_bn_relu(b, 256, nullptr, 0, B, 4 * h, 4 * w, n + ".d2.1", 256);
+        b = f.conv_t(b, 256, B, 4 * h, 4 * w, n + ".d2.ct", 128);
+        b = f.conv_bn_relu(s1, 128, b, 128, B, 8 * h, 8 * w, n + ".d1.0", 128);
+        b = f.conv_bn_relu(b, 128, nullptr, 0, B, 8 * h, 8 * w, n + ".d1.1", 128);
+        b = f.conv_t(b, 128, B, 8 * h, 8 * w, n + ".d1.ct", 64);
+        b = f.conv_bn_relu(s0, 64, b, 64, B, H, W, n + ".d0.0", 64);
+        TcEpilogue e = Fwd::epi0();
+        e.kind = TC_EPI_HEAD;
+        e.scale = f.P<float>(n + ".d0.1.scale"); e.shift = f.P<float>(n + ".d0.1.shift");
+        e.head_w = f.P<float>(n + ".head.w"); e.head_b = f.P<float>(n + ".head.b");
+        e.head_nc = br.nc; e.head_hw = H * W; e.head_out = br.out;
+        const __half* wp = f.P<__half>(n + ".d0.1.w");
+        if (f.live() && br.out) f.chk(tc_conv3x3(b, 64, nullptr, 0, B, H, W, wp, 64, 64, e, st));
+    }
+    (void)pad64;
+    return f.rc;
+}
+
+}  // namespace
+
+#define CVB_API extern "C" __attribute__((visibility("default")))
+
+CVB_API int cvb_model_create(const cvb_model_desc* desc, cvb_model** out) {
+    CVB_CHECK(desc && out, CVB_EARG, "cvb_model_create: null argument");
+    CVB_CHECK(desc->embed_dim > 0 && desc->num_heads > 0 && desc->embed_dim % desc->num_heads == 0, CVB_EARG,
+              "cvb_model_create: bad embed_dim/num_heads");
+    const int hd = desc->embed_dim / desc->num_heads;
+    CVB_CHECK(hd == 64 || hd == 80, CVB_ESHAPE, "cvb_model_create: head dim %d not supported (64, 80)", hd);
+    CVB_CHECK(desc->embed_dim % 64 == 0 && desc->skip11 % 64 == 0 && desc->skip12 % 64 == 0 && desc->bott_pad % 64 == 0,
+              CVB_ESHAPE, "cvb_model_create: channel widths must be padded to multiples of 64");
+    CVB_CHECK(desc->n_np_out >= 1 && desc->n_np_out <= 8 && desc->n_nt >= 1 && desc->n_nt <= 8, CVB_ESHAPE,
+              "cvb_model_create: head widths must be in 1..8");
+    CVB_CHECK(desc->n_global >= 0 && desc->n_global <= 8, CVB_EARG, "cvb_model_create: n_global out of range");
+    cvb_model* m = new cvb_model();
+    m->d = *desc;
+    *out = m;
+    return CVB_OK;
+}
+
+CVB_API int cvb_model_set_param(cvb_model* m, const char* name, const void* dev_ptr) {
+    CVB_CHECK(m && name, CVB_EARG, "cvb_model_set_param: null argument");
+    m->params[name] = dev_ptr;
+    return CVB_OK;
+}
+
+static int check_shape(const cvb_model* m, int B, int H, int W) {
+    CVB_CHECK(m != nullptr && B > 0, CVB_EARG, "cvb_forward: null model or empty batch");
+    CVB_CHECK(H % 16 == 0 && W % 16 == 0 && H > 0 && W > 0, CVB_ESHAPE, "Input images must be divisible by the patch size (%dx%d)", H, W);
+    CVB_CHECK(H == W, CVB_ESHAPE, "cvb_forward: only square tiles are supported (%dx%d)", H, W);
+    CVB_CHECK(H == 256 || H == 512 || H == 1024, CVB_ESHAPE,
+              "cvb_forward: tile edge %d not supported by the 128-pixel conv tiling (256, 512 or 1024)", H);
+    return CVB_OK;
+}
+
+CVB_API int cvb_model_workspace_bytes(cvb_model* m, int B, int H, int W, size_t* out) {
+    CVB_CHECK(out != nullptr, CVB_EARG, "cvb_model_workspace_bytes: null out");
+    CVB_TRY(check_shape(m, B, H, W));
+    Arena A{nullptr, 0, 0, true};
+    size_t peak = 0;
+    // the branch loop rewinds the arena; track the peak by running the dry pass and taking the max offset
+    forward_impl(*m, nullptr, B, H, W, nullptr, nullptr, nullptr, nullptr, nullptr, A, nullptr);
+    peak = A.off;
+    // branch region is re-used three times; all three are the same size except the head, so A.off is the peak
+    *out = peak + 4096;
+    return CVB_OK;
+}
+
+CVB_API int cvb_forward(cvb_model* m, const float* x, int B, int H, int W, float* np_logits, float* hv, float* nt_logits,
+                        float* tissue, float* tokens, void* workspace, size_t ws_bytes, void* stream) {
+    CVB_TRY(check_shape(m, B, H, W));
+    CVB_CHECK(x && workspace, CVB_EARG, "cvb_forward: null input or workspace");
+    size_t need = 0;
+    CVB_TRY(cvb_model_workspace_bytes(m, B, H, W, &need));
+    CVB_CHECK(ws_bytes >= need, CVB_EWORKSPACE, "cvb_forward: workspace %zu < required %zu bytes", ws_bytes, need);
+    CVB_CHECK(((uintptr_t)workspace & 255) == 0, CVB_EARG, "cvb_forward: workspace must be 256-byte aligned");
+    Arena A{reinterpret_cast<uint8_t*>(workspace), 0, ws_bytes, false};
+    return forward_impl(*m, x, B, H, W, np_logits, hv, nt_logits, tissue, tokens, A, (cudaStream_t)stream);
+}
+
+CVB_API void cvb_model_destroy(cvb_model* m) { delete m; }

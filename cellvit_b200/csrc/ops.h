@@ -1,3 +1,49 @@
 // ops.h -- host launchers of the non-GEMM kernels (layer norm, attention, layout transforms, stencils).
+// Every launcher is asynchronous on `stream` and returns a CVB_* status.
 #pragma once
 #include "common.cuh"
+
+// --- ops_misc.cu ------------------------------------------------------------------------------------
+// Non-overlapping PxP patches of x [B,3,H,W] fp32 -> A [B*(H/P)*(W/P), 3*P*P] fp16, column = c*P*P + ky*P + kx
+// (the flattening of the reference Conv2d weight, image_encoder.py:418-426 / vits_histo.py:273-280).
+int op_patch_im2col(const float* x, int B, int H, int W, int P, __half* out, cudaStream_t stream);
+
+// LayerNorm over the last dim (biased variance, eps inside the sqrt) fp32 -> fp16.
+//   map 0: dst row r <- src row r;
+//   map 1: window partition (image_encoder.py:263-288): dst rows are [B, g*g windows, ws*ws tokens]; tokens that
+//          fall outside the tok_h x tok_w grid are written as zeros (padding happens AFTER norm1).
+int op_layernorm_f16(const float* x, const float* gamma, const float* beta, float eps, int rows_dst, int D, __half* out,
+                     int map, int B, int tok_h, int tok_w, int ws, int g, cudaStream_t stream);
+
+// fp32 [B, T_src, D] rows (skipping `skip` leading rows per batch item) -> fp16 [B, T_src-skip, D].
+int op_cast_rows_f16(const float* x, int B, int T_src, int skip, int D, __half* out, cudaStream_t stream);
+
+// fp32 token rows [B, T_src(+skip), D] -> fp32 NCHW [B, D, T] (tokens output of the reference forward).
+int op_tokens_nchw(const float* x, int B, int T_src, int skip, int D, float* out, cudaStream_t stream);
+
+// decoder0.0: Conv3x3(3->32)+BN+ReLU on x [B,3,H,W] fp32 -> NHWC fp16 with `cpad` channels (>= 32, rest zero).
+// w [32,3,3,3] fp32, scale/shift [32] (folded BN + bias).
+int op_stem_conv(const float* x, int B, int H, int W, const float* w, const float* scale, const float* shift,
+                 __half* out, int cpad, cudaStream_t stream);
+
+// SAM neck tail (image_encoder.py:110-113, utils.py:230-233, cellvit.py:613): per image LayerNorm2d over C of
+// y [B, T, C] fp32, mean over T, then Linear(C -> n_out). out [B, n_out] fp32.
+int op_ln_mean_linear(const float* y, int B, int T, int C, const float* gamma, const float* beta, float eps,
+                      const float* w, const float* b, int n_out, float* out, cudaStream_t stream);
+
+// ViT-256 tissue head (utils.py:171-172): LayerNorm(x[:,0]) then Linear. x [B, T, D] fp32.
+int op_cls_head(const float* x, int B, int T, int D, const float* gamma, const float* beta, float eps,
+                const float* w, const float* b, int n_out, float* out, cudaStream_t stream);
+
+// --- attention.cu -----------------------------------------------------------------------------------
+// Decomposed relative-position terms (image_encoder.py:354-392), computed from the UNSCALED q:
+//   rel_h[g, q, kh] = q . Rh[qh - kh + gh - 1],  rel_w[g, q, kw] = q . Rw[qw - kw + gw - 1]
+// qkv fp16 [G_b * S, 3*D] (q | k | v, head-major inside each), tables fp32 [2*gh-1, hd] / [2*gw-1, hd].
+// rel_h / rel_w fp32 [G_b*heads, S, gh] / [.., S, gw] with S = gh*gw.
+int op_relpos(const __half* qkv, int Gb, int heads, int hd, int gh, int gw, const float* Rh, const float* Rw,
+              float* rel_h, float* rel_w, cudaStream_t stream);
+
+// softmax(scale * q k^T + bias) v per (group, head); groups are windows or whole images.
+// out fp16 [Gb*S, D] with head h at columns [h*hd, (h+1)*hd). rel_h/rel_w may be null (no bias).
+int op_attention(const __half* qkv, int Gb, int S, int heads, int hd, float scale, const float* rel_h,
+                 const float* rel_w, int gh, int gw, __half* out, cudaStream_t stream);

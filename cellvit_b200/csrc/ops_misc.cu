@@ -1,0 +1,314 @@
+// ops_misc.cu -- HBM-bound helper kernels of the forward: patch im2col, LayerNorm (with window partition),
+// casts / layout transforms, the 3->32 stem stencil and the two tiny tissue-classifier tails.
+#include "ops.h"
+
+namespace {
+
+// ------------------------------------------------------------------------------------------ im2col
+__global__ void patch_im2col_kernel(const float* __restrict__ x, int B, int H, int W, int P, __half* __restrict__ out) {
+    // one thread = one (row, c, ky) run of P contiguous pixels (P == 16: 64 B in, 32 B out)
+    const int gw = W / P, gh = H / P;
+    const long long total = (long long)B * gh * gw * 3 * P;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int px = (int)(i % gw);
+        long long r = i / gw;
+        const int ky = (int)(r % P); r /= P;
+        const int c = (int)(r % 3); r /= 3;
+        const int py = (int)(r % gh);
+        const int b = (int)(r / gh);
+        const float* src = x + (((long long)b * 3 + c) * H + (py * P + ky)) * W + px * P;
+        __half* dst = out + (((long long)b * gh + py) * gw + px) * (3 * P * P) + c * P * P + ky * P;
+        for (int k = 0; k < P; k += 8) {
+            const float4 a = *reinterpret_cast<const float4*>(src + k);
+            const float4 d = *reinterpret_cast<const float4*>(src + k + 4);
+            *reinterpret_cast<uint4*>(dst + k) = make_uint4(pack_h2(a.x, a.y), pack_h2(a.z, a.w), pack_h2(d.x, d.y), pack_h2(d.z, d.w));
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------ LayerNorm
+constexpr int LN_MAXV = 10;  // float4 per lane: D <= 1280
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__global__ void __launch_bounds__(256)
+layernorm_f16_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                     int rows_dst, int D, __half* __restrict__ out, int map, int tok_h, int tok_w, int ws, int g) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= rows_dst) return;
+    long long src = warp;
+    if (map == 1) {
+        const int per_img = g * g * ws * ws;
+        const int b = warp / per_img;
+        const int rem = warp - b * per_img;
+        const int win = rem / (ws * ws), t = rem - win * ws * ws;
+        const int y = (win / g) * ws + t / ws, xq = (win % g) * ws + t % ws;
+        src = (y < tok_h && xq < tok_w) ? ((long long)b * tok_h + y) * tok_w + xq : -1;
+    }
+    __half* o = out + (long long)warp * D;
+    const int nv = D >> 2;  // float4 count
+    if (src < 0) {
+        for (int i = lane; i < (D >> 3); i += 32) reinterpret_cast<uint4*>(o)[i] = make_uint4(0, 0, 0, 0);
+        return;
+    }
+    const float4* xr = reinterpret_cast<const float4*>(x + src * D);
+    float4 v[LN_MAXV];
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < LN_MAXV; ++k) {
+        const int i = lane + 32 * k;
+        if (i < nv) { v[k] = xr[i]; s += (v[k].x + v[k].y) + (v[k].z + v[k].w); }
+    }
+    const float mean = warp_sum(s) / (float)D;
+    float q = 0.f;
+#pragma unroll
+    for (int k = 0; k < LN_MAXV; ++k) {
+        const int i = lane + 32 * k;
+        if (i < nv) {
+            const float a = v[k].x - mean, b = v[k].y - mean, c = v[k].z - mean, d = v[k].w - mean;
+            q += (a * a + b * b) + (c * c + d * d);
+        }
+    }
+    const float rstd = rsqrtf(warp_sum(q) / (float)D + eps);
+#pragma unroll
+    for (int k = 0; k < LN_MAXV; ++k) {
+        const int i = lane + 32 * k;
+        if (i < nv) {
+            const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma) + i);
+            const float4 bt = __ldg(reinterpret_cast<const float4*>(beta) + i);
+            const float a = (v[k].x - mean) * rstd * gm.x + bt.x, b = (v[k].y - mean) * rstd * gm.y + bt.y;
+            const float c = (v[k].z - mean) * rstd * gm.z + bt.z, d = (v[k].w - mean) * rstd * gm.w + bt.w;
+            reinterpret_cast<uint2*>(o)[i] = make_uint2(pack_h2(a, b), pack_h2(c, d));
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------ casts / layouts
+__global__ void cast_rows_f16_kernel(const float* __restrict__ x, int B, int T_src, int skip, int D, __half* __restrict__ out) {
+    const int T = T_src - skip;
+    const long long nv = (long long)B * T * (D >> 2);
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nv; i += (long long)gridDim.x * blockDim.x) {
+        const int dv = (int)(i % (D >> 2));
+        const long long r = i / (D >> 2);
+        const int t = (int)(r % T);
+        const int b = (int)(r / T);
+        const float4 a = reinterpret_cast<const float4*>(x + ((long long)b * T_src + skip + t) * D)[dv];
+        reinterpret_cast<uint2*>(out + r * D)[dv] = make_uint2(pack_h2(a.x, a.y), pack_h2(a.z, a.w));
+    }
+}
+
+__global__ void tokens_nchw_kernel(const float* __restrict__ x, int T_src, int skip, int D, float* __restrict__ out) {
+    __shared__ float tile[32][33];
+    const int T = T_src - skip;
+    const int b = blockIdx.z, t0 = blockIdx.x * 32, d0 = blockIdx.y * 32;
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        const int t = t0 + j, d = d0 + threadIdx.x;
+        tile[j][threadIdx.x] = (t < T && d < D) ? x[((long long)b * T_src + skip + t) * D + d] : 0.f;
+    }
+    __syncthreads();
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        const int d = d0 + j, t = t0 + threadIdx.x;
+        if (t < T && d < D) out[((long long)b * D + d) * T + t] = tile[threadIdx.x][j];
+    }
+}
+
+// ------------------------------------------------------------------------------------------ stem conv 3->32
+__global__ void __launch_bounds__(128)
+stem_conv_kernel(const float* __restrict__ x, int B, int H, int W, const float* __restrict__ w, const float* __restrict__ scale,
+                 const float* __restrict__ shift, __half* __restrict__ out, int cpad) {
+    __shared__ float ws[27 * 32];  // [tap(c,ky,kx)][co]
+    __shared__ float sc[32], sh[32];
+    for (int i = threadIdx.x; i < 27 * 32; i += blockDim.x) {
+        const int co = i & 31, tap = i >> 5;
+        ws[i] = w[co * 27 + tap];
+    }
+    if (threadIdx.x < 32) { sc[threadIdx.x] = scale[threadIdx.x]; sh[threadIdx.x] = shift[threadIdx.x]; }
+    __syncthreads();
+    const long long total = (long long)B * H * W;
+    for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < total; p += (long long)gridDim.x * blockDim.x) {
+        const int xq = (int)(p % W);
+        const int y = (int)((p / W) % H);
+        const int b = (int)(p / ((long long)W * H));
+        float in[27];
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx) {
+                    const int yy = y + ky - 1, xx = xq + kx - 1;
+                    in[c * 9 + ky * 3 + kx] = (yy >= 0 && yy < H && xx >= 0 && xx < W)
+                                                  ? __ldg(x + (((long long)b * 3 + c) * H + yy) * W + xx) : 0.f;
+                }
+        __half* o = out + p * cpad;
+#pragma unroll
+        for (int c8 = 0; c8 < 32; c8 += 8) {
+            float acc[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+#pragma unroll
+            for (int t = 0; t < 27; ++t)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[j] = fmaf(in[t], ws[t * 32 + c8 + j], acc[j]);
+            uint32_t pk[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float a = fmaxf(fmaf(acc[2 * j], sc[c8 + 2 * j], sh[c8 + 2 * j]), 0.f);
+                const float d = fmaxf(fmaf(acc[2 * j + 1], sc[c8 + 2 * j + 1], sh[c8 + 2 * j + 1]), 0.f);
+                pk[j] = pack_h2(a, d);
+            }
+            *reinterpret_cast<uint4*>(o + c8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        }
+        for (int c8 = 32; c8 < cpad; c8 += 8) *reinterpret_cast<uint4*>(o + c8) = make_uint4(0, 0, 0, 0);
+    }
+}
+
+// ------------------------------------------------------------------------------------------ tissue heads
+// one block (1024 threads) per image; warp w handles rows w, w+32, ...; C <= 256
+__global__ void __launch_bounds__(1024)
+ln_mean_linear_kernel(const float* __restrict__ y, int T, int C, const float* __restrict__ gamma, const float* __restrict__ beta,
+                      float eps, const float* __restrict__ w, const float* __restrict__ bias, int n_out, float* __restrict__ out) {
+    __shared__ float part[32][256 + 1];
+    __shared__ float meanv[256];
+    const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int per = C >> 5;  // channels per lane (C % 32 == 0, per <= 8)
+    float acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+    for (int t = warp; t < T; t += 32) {
+        const float* r = y + ((long long)b * T + t) * C;
+        float v[8], s = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            if (k < per) { v[k] = r[lane + 32 * k]; s += v[k]; }
+        const float mean = warp_sum(s) / (float)C;
+        float q = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            if (k < per) { const float d = v[k] - mean; q += d * d; }
+        const float rstd = 1.0f / sqrtf(warp_sum(q) / (float)C + eps);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            if (k < per) acc[k] += (v[k] - mean) * rstd * gamma[lane + 32 * k] + beta[lane + 32 * k];
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+        if (k < per) part[warp][lane + 32 * k] = acc[k];
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float s = 0.f;
+        for (int wq = 0; wq < 32; ++wq) s += part[wq][c];
+        meanv[c] = s / (float)T;
+    }
+    __syncthreads();
+    for (int o = warp; o < n_out; o += 32) {
+        float s = 0.f;
+        for (int c = lane; c < C; c += 32) s += meanv[c] * w[o * C + c];
+        s = warp_sum(s);
+        if (lane == 0) out[b * n_out + o] = s + bias[o];
+    }
+}
+
+__global__ void __launch_bounds__(256)
+cls_head_kernel(const float* __restrict__ x, int T, int D, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                const float* __restrict__ w, const float* __restrict__ bias, int n_out, float* __restrict__ out) {
+    __shared__ float v[2048];
+    __shared__ float red[2][8];
+    const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const float* r = x + (long long)b * T * D;
+    float s = 0.f;
+    for (int i = threadIdx.x; i < D; i += blockDim.x) { v[i] = r[i]; s += v[i]; }
+    s = warp_sum(s);
+    if (lane == 0) red[0][warp] = s;
+    __syncthreads();
+    float tot = 0.f;
+    for (int i = 0; i < 8; ++i) tot += red[0][i];
+    const float mean = tot / (float)D;
+    float q = 0.f;
+    for (int i = threadIdx.x; i < D; i += blockDim.x) { const float d = v[i] - mean; q += d * d; }
+    q = warp_sum(q);
+    if (lane == 0) red[1][warp] = q;
+    __syncthreads();
+    float tq = 0.f;
+    for (int i = 0; i < 8; ++i) tq += red[1][i];
+    const float rstd = 1.0f / sqrtf(tq / (float)D + eps);
+    for (int i = threadIdx.x; i < D; i += blockDim.x) v[i] = (v[i] - mean) * rstd * gamma[i] + beta[i];
+    __syncthreads();
+    for (int o = warp; o < n_out; o += 8) {
+        float a = 0.f;
+        for (int c = lane; c < D; c += 32) a += v[c] * w[o * D + c];
+        a = warp_sum(a);
+        if (lane == 0) out[b * n_out + o] = a + bias[o];
+    }
+}
+
+int grid_for(long long work_items, int block) {
+    long long g = (work_items + block - 1) / block;
+    const long long cap = (long long)cvb_num_sms() * 16;
+    return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+}  // namespace
+
+int op_patch_im2col(const float* x, int B, int H, int W, int P, __half* out, cudaStream_t stream) {
+    CVB_CHECK(x && out && B > 0 && P % 8 == 0 && H % P == 0 && W % P == 0, CVB_ESHAPE, "patch_im2col: bad shape %dx%d P=%d", H, W, P);
+    const long long total = (long long)B * (H / P) * (W / P) * 3 * P;
+    patch_im2col_kernel<<<grid_for(total, 256), 256, 0, stream>>>(x, B, H, W, P, out);
+    CVB_CUDA(cudaGetLastError());
+    return CVB_OK;
+}
+
+int op_layernorm_f16(const float* x, const float* gamma, const float* beta, float eps, int rows_dst, int D, __half* out,
+                     int map, int B, int tok_h, int tok_w, int ws, int g, cudaStream_t stream) {
+    (void)B;
+    CVB_CHECK(x && gamma && beta && out && rows_dst > 0, CVB_EARG, "layernorm: null operand");
+    CVB_CHECK(D % 8 == 0 && D <= LN_MAXV * 128, CVB_ESHAPE, "layernorm: D=%d must be a multiple of 8 and <= %d", D, LN_MAXV * 128);
+    const int blocks = cdiv(rows_dst, 8);
+    layernorm_f16_kernel<<<blocks, 256, 0, stream>>>(x, gamma, beta, eps, rows_dst, D, out, map, tok_h, tok_w, ws, g);
+    CVB_CUDA(cudaGetLastError());
+    return CVB_OK;
+}
+
+int op_cast_rows_f16(const float* x, int B, int T_src, int skip, int D, __half* out, cudaStream_t stream) {
+    CVB_CHECK(x && out && D % 4 == 0 && T_src > skip, CVB_EARG, "cast_rows: bad arguments");
+    cast_rows_f16_kernel<<<grid_for((long long)B * (T_src - skip) * (D / 4), 256), 256, 0, stream>>>(x, B, T_src, skip, D, out);
+    CVB_CUDA(cudaGetLastError());
+    return CVB_OK;
+}
+
+int op_tokens_nchw(const float* x, int B, int T_src, int skip, int D, float* out, cudaStream_t stream) {
+    CVB_CHECK(x && out && T_src > skip, CVB_EARG, "tokens_nchw: bad arguments");
+    dim3 grid(cdiv(T_src - skip, 32), cdiv(D, 32), B), block(32, 8);
+    tokens_nchw_kernel<<<grid, block, 0, stream>>>(x, T_src, skip, D, out);
+    CVB_CUDA(cudaGetLastError());
+    return CVB_OK;
+}
+
+int op_stem_conv(const float* x, int B, int H, int W, const float* w, const float* scale, const float* shift,
+                 __half* out, int cpad, cudaStream_t stream) {
+    CVB_CHECK(x && w && scale && shift && out && cpad >= 32 && cpad % 8 == 0, CVB_EARG, "stem_conv: bad arguments");
+    stem_conv_kernel<<<grid_for((long long)B * H * W, 128), 128, 0, stream>>>(x, B, H, W, w, scale, shift, out, cpad);
+    CVB_CUDA(cudaGetLastError());
+    return CVB_OK;
+}
+
+int op_ln_mean_linear(const float* y, int B, int T, int C, const float* gamma, const float* beta, float eps,
+                      const float* w, const float* b, int n_out, float* out, cudaStream_t stream) {
+    CVB_CHECK(y && gamma && beta && w && b && out, CVB_EARG, "ln_mean_linear: null operand");
+    CVB_CHECK(C % 32 == 0 && C <= 256, CVB_ESHAPE, "ln_mean_linear: C=%d must be a multiple of 32 and <= 256", C);
+    ln_mean_linear_kernel<<<B, 1024, 0, stream>>>(y, T, C, gamma, beta, eps, w, b, n_out, out);
+    CVB_CUDA(cudaGetLastError());
+    return CVB_OK;
+}
+
+int op_cls_head(const float* x, int B, int T, int D, const float* gamma, const float* beta, float eps,
+                const float* w, const float* b, int n_out, float* out, cudaStream_t stream) {
+    CVB_CHECK(x && gamma && beta && w && b && out && D <= 2048, CVB_EARG, "cls_head: bad arguments");
+    cls_head_kernel<<<B, 256, 0, stream>>>(x, T, D, gamma, beta, eps, w, b, n_out, out);
+    CVB_CUDA(cudaGetLastError());
+    return CVB_OK;
+}

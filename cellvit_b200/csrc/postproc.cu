@@ -1,0 +1,938 @@
+// postproc.cu -- HoVer-Net post-processing of CellViT head maps on the device, bit-exact with the CPU oracle
+// (oracle/postproc_oracle.c), which is itself pinned to the reference's cv2 / scipy code path
+// (cell_segmentation/utils/post_proc_cellvit.py:155-249 stages P1-P7, :95-151 instance table).
+//
+// Stage -> kernel map (all HBM-bound integer / fp64 work on [B, H, W] planes, no tensor cores):
+//   P1/P2  4-connected components of the NP mask + size filter (<10 px)        ccl_* , count, blb
+//   P3     per-tile min-max normalisation of the HV maps (fp32 fma)            minmax_f32 (+ fused into sobel)
+//   P4     Sobel k=21/11, fp64, OpenCV's exact operation order (no FMA)        sobel_kernel
+//   P5     second normalisation, energy map, 3x3 Gaussian                      energy_kernel, blur_kernel
+//   P6     marker mask, hole filling (background CCL), 5x5 ellipse opening,
+//          CCL with scipy's raster-order numbering, size filter                fill/erode/dilate/ccl/scan/marker
+//   P7     marker-controlled watershed: strict total order (value, age, index); every blob of the NP mask is an
+//          independent flood -> one warp per blob, binary heap in shared memory    watershed_kernel
+//   P8/P9  per-instance bbox / centroid / class histogram by atomics, compaction in id order   table_*
+#include <float.h>
+
+#include "../../include/cellvit_b200.h"
+#include "common.cuh"
+
+namespace {
+
+// ------------------------------------------------------------------------------------------ helpers
+__device__ __forceinline__ uint32_t f32_ordered(float f) {
+    const uint32_t u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float f32_unordered(uint32_t u) {
+    return __uint_as_float((u & 0x80000000u) ? (u & 0x7FFFFFFFu) : ~u);
+}
+__device__ __forceinline__ unsigned long long f64_ordered(double d) {
+    const unsigned long long u = (unsigned long long)__double_as_longlong(d);
+    return (u >> 63) ? ~u : (u | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double f64_unordered(unsigned long long u) {
+    return __longlong_as_double((long long)((u >> 63) ? (u & 0x7FFFFFFFFFFFFFFFull) : ~u));
+}
+__device__ __forceinline__ int reflect101(int p, int len) {
+    if (len == 1) return 0;
+    while (p < 0 || p >= len) p = p < 0 ? -p : 2 * len - 2 - p;
+    return p;
+}
+// cv2.normalize(NORM_MINMAX, 0..1, CV_32F) parameters (oracle minmax_params)
+__device__ __forceinline__ void minmax_params(double mn, double mx, float* scale, float* shift) {
+    const double d = __dsub_rn(mx, mn);
+    const double sc = d > DBL_EPSILON ? __ddiv_rn(1.0, d) : 0.0;
+    *scale = __double2float_rn(sc);
+    *shift = __fsub_rn(0.0f, __double2float_rn(__dmul_rn(mn, (double)*scale)));
+}
+
+struct Dims { int B, H, W, N; };
+
+// ------------------------------------------------------------------------------------------ input preparation
+__global__ void prep_float_kernel(const float* __restrict__ np_map, const float* __restrict__ nt_map, int n_types, Dims d,
+                                  uint8_t* __restrict__ npbin, uint8_t* __restrict__ tmap) {
+    const long long total = (long long)d.B * d.N;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int b = (int)(i / d.N), p = (int)(i - (long long)b * d.N);
+        const float* q = np_map + (long long)b * 2 * d.N + p;
+        npbin[i] = q[d.N] > q[0];  // torch.argmax: first maximum wins
+        if (nt_map) {
+            const float* t = nt_map + (long long)b * n_types * d.N + p;
+            int best = 0;
+            float bv = t[0];
+            for (int c = 1; c < n_types; ++c) {
+                const float v = t[(long long)c * d.N];
+                if (v > bv) { bv = v; best = c; }
+            }
+            tmap[i] = (uint8_t)best;
+        }
+    }
+}
+
+__global__ void prep_maps_kernel(const int32_t* __restrict__ type_map, long long total, uint8_t* __restrict__ tmap) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int t = type_map[i];
+        tmap[i] = (uint8_t)(t < 0 ? 255 : (t > 254 ? 255 : t));
+    }
+}
+
+// per (tile, plane) min / max of a float plane -> ordered-u32 atomics; mm[(b*2+plane)*2 + {0,1}]
+__global__ void minmax_f32_kernel(const float* __restrict__ hv, Dims d, uint32_t* __restrict__ mm) {
+    const int plane = blockIdx.y;  // b*2 + c
+    const float* src = hv + (long long)plane * d.N;
+    float mn = INFINITY, mx = -INFINITY;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < d.N; i += gridDim.x * blockDim.x) {
+        const float v = src[i];
+        mn = fminf(mn, v);
+        mx = fmaxf(mx, v);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMin(&mm[plane * 2 + 0], f32_ordered(mn));
+        atomicMax(&mm[plane * 2 + 1], f32_ordered(mx));
+    }
+}
+
+// ------------------------------------------------------------------------------------------ connected components
+__device__ __forceinline__ int uf_find(volatile int* L, int a) {
+    int p = L[a];
+    while (p != a) { a = p; p = L[a]; }
+    return a;
+}
+__device__ __forceinline__ void uf_unite(int* L, int a, int b) {
+    bool done;
+    do {
+        a = uf_find(L, a);
+        b = uf_find(L, b);
+        if (a < b) { const int old = atomicMin(&L[b], a); done = (old == b); b = old; }
+        else if (b < a) { const int old = atomicMin(&L[a], b); done = (old == a); a = old; }
+        else done = true;
+    } while (!done);
+}
+
+// One warp per 32-pixel row segment. Labels start as the index of the first pixel of the horizontal run inside
+// the segment (tile-local pixel index); -1 outside the mask.
+__global__ void ccl_init_kernel(const uint8_t* __restrict__ mask, int want, Dims d, int* __restrict__ L) {
+    const int segs = (d.W + 31) >> 5;
+    const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    const long long total = (long long)d.B * d.H * segs;
+    if (warp >= total) return;
+    const int seg = (int)(warp % segs);
+    const long long row = warp / segs;  // b*H + y
+    const int x = seg * 32 + lane;
+    const bool in = x < d.W;
+    const long long gi = row * d.W + x;
+    const bool fg = in && (mask[gi] != 0) == (want != 0);
+    const uint32_t bits = __ballot_sync(0xffffffffu, fg);
+    if (!in) return;
+    int lab = -1;
+    if (fg) {
+        const uint32_t inv = ~bits & ((1u << lane) - 1u);
+        const int start = inv ? 32 - __clz(inv) : 0;
+        const int y = (int)(row % d.H);
+        lab = y * d.W + seg * 32 + start;
+    }
+    L[gi] = lab;
+}
+
+__global__ void ccl_merge_kernel(const uint8_t* __restrict__ mask, int want, Dims d, int* __restrict__ L) {
+    const long long total = (long long)d.B * d.N;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int b = (int)(i / d.N), p = (int)(i - (long long)b * d.N);
+        int* Lt = L + (long long)b * d.N;
+        if (Lt[p] < 0) continue;
+        const uint8_t* mt = mask + (long long)b * d.N;
+        const int y = p / d.W, x = p - y * d.W;
+        auto is = [&](int q) { return (mt[q] != 0) == (want != 0); };
+        // horizontal: only the first pixel of a 32-segment can continue a run from the previous segment
+        if ((x & 31) == 0 && x > 0 && is(p - 1)) uf_unite(Lt, p, p - 1);
+        // vertical: skip when the pair to the left already joins the same two runs
+        if (y > 0 && is(p - d.W)) {
+            const bool dup = x > 0 && (x & 31) != 0 && is(p - 1) && is(p - d.W - 1);
+            if (!dup) uf_unite(Lt, p, p - d.W);
+        }
+    }
+}
+
+__global__ void ccl_compress_kernel(Dims d, int* __restrict__ L) {
+    const long long total = (long long)d.B * d.N;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int b = (int)(i / d.N);
+        int* Lt = L + (long long)b * d.N;
+        const int p = (int)(i - (long long)b * d.N);
+        if (Lt[p] >= 0) Lt[p] = uf_find(Lt, p);
+    }
+}
+
+__global__ void count_kernel(const int* __restrict__ L, Dims d, int* __restrict__ cnt) {
+    const long long total = (long long)d.B * d.N;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int r = L[i];
+        if (r >= 0) atomicAdd(&cnt[(i / d.N) * d.N + r], 1);
+    }
+}
+
+__global__ void blb_kernel(const int* __restrict__ L, const int* __restrict__ cnt, Dims d, int min_size, uint8_t* __restrict__ blb) {
+    const long long total = (long long)d.B * d.N;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int r = L[i];
+        blb[i] = (r >= 0 && cnt[(i / d.N) * d.N + r] >= min_size) ? 1 : 0;
+    }
+}
+
+// ------------------------------------------------------------------------------------------ exclusive scan (per tile)
+constexpr int SCAN_BLOCK = 1024;  // elements per block (256 threads x 4)
+
+__device__ __forceinline__ int block_excl_scan_256(int v, int* total_out) {
+    __shared__ int wsum[8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int inc = v;
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) wsum[warp] = inc;
+    __syncthreads();
+    int base = 0, tot = 0;
+    for (int k = 0; k < 8; ++k) {
+        if (k < warp) base += wsum[k];
+        tot += wsum[k];
+    }
+    __syncthreads();
+    if (total_out) *total_out = tot;
+    return base + inc - v;
+}
+
+// in: values (flag != 0 -> 1 when `as_flag`), bsum[b*nb + blk]
+__global__ void __launch_bounds__(256) scan_reduce_kernel(const int* __restrict__ in, int as_flag, int n, int nb, int* __restrict__ bsum) {
+    const int b = blockIdx.y, blk = blockIdx.x;
+    const int* src = in + (long long)b * n;
+    int s = 0;
+    for (int k = 0; k < 4; ++k) {
+        const int i = blk * SCAN_BLOCK + k * 256 + threadIdx.x;
+        if (i < n) s += as_flag ? (src[i] != 0) : src[i];
+    }
+    int tot;
+    block_excl_scan_256(s, &tot);
+    if (threadIdx.x == 0) bsum[b * nb + blk] = tot;
+}
+__global__ void __launch_bounds__(256) scan_bsums_kernel(int nb, int* __restrict__ bsum) {
+    int* s = bsum + (long long)blockIdx.x * nb;
+    int carry = 0;
+    for (int base = 0; base < nb; base += 256) {
+        const int i = base + threadIdx.x;
+        const int v = i < nb ? s[i] : 0;
+        int tot;
+        const int ex = block_excl_scan_256(v, &tot);
+        if (i < nb) s[i] = carry + ex;
+        carry += tot;
+        __syncthreads();
+    }
+}
+__global__ void __launch_bounds__(256) scan_apply_kernel(const int* __restrict__ in, int as_flag, int n, int nb, const int* __restrict__ bsum,
+                                                         int* __restrict__ out) {
+    const int b = blockIdx.y, blk = blockIdx.x;
+    const int* src = in + (long long)b * n;
+    int* dst = out + (long long)b * n;
+    int v[4], s = 0;
+    const int i0 = blk * SCAN_BLOCK + threadIdx.x * 4;
+    for (int k = 0; k < 4; ++k) {
+        const int i = i0 + k;
+        v[k] = i < n ? (as_flag ? (src[i] != 0) : src[i]) : 0;
+        s += v[k];
+    }
+    int ex = block_excl_scan_256(s, nullptr) + bsum[b * nb + blk];
+    for (int k = 0; k < 4; ++k) {
+        const int i = i0 + k;
+        if (i < n) dst[i] = ex;
+        ex += v[k];
+    }
+}
+
+// ------------------------------------------------------------------------------------------ Sobel (P3 + P4)
+struct SobelTaps { double kd[32]; double ks[32]; int ksize; };
+constexpr int SB_TW = 64, SB_TH = 32, SB_MAXR = 15;
+
+// blockIdx.z = b*2 + plane. plane 0: h map, row kernel = derivative, column kernel = smoothing (symmetric);
+// plane 1: v map, row kernel = smoothing, column kernel = derivative (anti-symmetric).
+__global__ void __launch_bounds__(256)
+sobel_kernel(const float* __restrict__ hv, Dims d, const uint32_t* __restrict__ mm, const SobelTaps taps,
+             double* __restrict__ sob, unsigned long long* __restrict__ mm64) {
+    extern __shared__ __align__(16) uint8_t sb_smem[];
+    const int r = taps.ksize >> 1, ks = taps.ksize;
+    const int in_w = SB_TW + 2 * r, in_h = SB_TH + 2 * r;
+    float* s_in = reinterpret_cast<float*>(sb_smem);                                    // [in_h][in_w]
+    double* s_tmp = reinterpret_cast<double*>(sb_smem + (((size_t)in_h * in_w * 4 + 15) & ~(size_t)15));  // [in_h][SB_TW]
+    __shared__ double s_k[2][32];
+    __shared__ unsigned long long s_mm[2];
+    const int plane = blockIdx.z & 1, pl = blockIdx.z;
+    const float* src = hv + (long long)pl * d.N;
+    double* dst = sob + (long long)pl * d.N;
+    const int x0 = blockIdx.x * SB_TW, y0 = blockIdx.y * SB_TH;
+    float a, bsh;
+    minmax_params((double)f32_unordered(mm[pl * 2]), (double)f32_unordered(mm[pl * 2 + 1]), &a, &bsh);
+    if (threadIdx.x < 32) {
+        s_k[0][threadIdx.x] = plane == 0 ? taps.kd[threadIdx.x] : taps.ks[threadIdx.x];  // row (x) kernel
+        s_k[1][threadIdx.x] = plane == 0 ? taps.ks[threadIdx.x] : taps.kd[threadIdx.x];  // column (y) kernel
+    }
+    if (threadIdx.x == 0) { s_mm[0] = ~0ull; s_mm[1] = 0ull; }
+    for (int i = threadIdx.x; i < in_h * in_w; i += 256) {
+        const int yy = i / in_w, xx = i - yy * in_w;
+        const int gy = reflect101(y0 - r + yy, d.H), gx = reflect101(x0 - r + xx, d.W);
+        s_in[i] = __fmaf_rn(src[(long long)gy * d.W + gx], a, bsh);  // P3: one fused multiply-add in float
+    }
+    __syncthreads();
+    // row pass: acc = k[0]*s[0]; acc += k[j]*s[j] (ascending j, product and sum rounded separately)
+    for (int i = threadIdx.x; i < in_h * SB_TW; i += 256) {
+        const int yy = i / SB_TW, xx = i - yy * SB_TW;
+        const float* row = s_in + yy * in_w + xx;
+        double acc = __dmul_rn(s_k[0][0], (double)row[0]);
+        for (int j = 1; j < ks; ++j) acc = __dadd_rn(acc, __dmul_rn(s_k[0][j], (double)row[j]));
+        s_tmp[i] = acc;
+    }
+    __syncthreads();
+    double mn = INFINITY, mx = -INFINITY;
+    for (int i = threadIdx.x; i < SB_TH * SB_TW; i += 256) {
+        const int yy = i / SB_TW, xx = i - yy * SB_TW;
+        const int gy = y0 + yy, gx = x0 + xx;
+        if (gy >= d.H || gx >= d.W) continue;
+        const double* col = s_tmp + (yy + r) * SB_TW + xx;
+        double acc;
+        if (plane == 0) {
+            acc = __dmul_rn(s_k[1][r], col[0]);
+            for (int j = 1; j <= r; ++j)
+                acc = __dadd_rn(acc, __dmul_rn(s_k[1][r + j], __dadd_rn(col[j * SB_TW], col[-j * SB_TW])));
+        } else {
+            acc = 0.0;
+            for (int j = 1; j <= r; ++j)
+                acc = __dadd_rn(acc, __dmul_rn(s_k[1][r + j], __dsub_rn(col[j * SB_TW], col[-j * SB_TW])));
+        }
+        dst[(long long)gy * d.W + gx] = acc;
+        mn = fmin(mn, acc);
+        mx = fmax(mx, acc);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMin(&s_mm[0], f64_ordered(mn));
+        atomicMax(&s_mm[1], f64_ordered(mx));
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        atomicMin(&mm64[pl * 2 + 0], s_mm[0]);
+        atomicMax(&mm64[pl * 2 + 1], s_mm[1]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------ energy map (P5) + marker mask (P6 head)
+__global__ void energy_kernel(const double* __restrict__ sob, const unsigned long long* __restrict__ mm64, const uint8_t* __restrict__ blb,
+                              Dims d, double* __restrict__ dist0, uint8_t* __restrict__ mk) {
+    const long long total = (long long)d.B * d.N;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int b = (int)(i / d.N), p = (int)(i - (long long)b * d.N);
+        float m = 0.f;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            const int pl = b * 2 + c;
+            float af, bf;
+            minmax_params(f64_unordered(mm64[pl * 2]), f64_unordered(mm64[pl * 2 + 1]), &af, &bf);
+            // f64 -> f32 convertTo: (float)(src*(double)scale + (double)shift), product and sum rounded separately
+            const float nrm = __double2float_rn(__dadd_rn(__dmul_rn(sob[(long long)pl * d.N + p], (double)af), (double)bf));
+            const float one_minus = __fsub_rn(1.0f, nrm);
+            m = c == 0 ? one_minus : (one_minus > m ? one_minus : m);  // np.maximum(sobelh, sobelv)
+        }
+        const int bl = blb[i];
+        double o = __dsub_rn((double)m, (double)(1 - bl));
+        if (o < 0) o = 0.0;
+        dist0[i] = __dmul_rn(__dsub_rn(1.0, o), (double)bl);
+        mk[i] = (bl - (o >= 0.4 ? 1 : 0)) > 0 ? 1 : 0;
+    }
+}
+
+// dist = -GaussianBlur(dist0, (3,3), 0): kernel [.25,.5,.25], REFLECT_101, row pass ascending taps, column pass centre + pair
+__global__ void blur_kernel(const double* __restrict__ dist0, Dims d, double* __restrict__ dist) {
+    const long long total = (long long)d.B * d.N;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int b = (int)(i / d.N), p = (int)(i - (long long)b * d.N);
+        const int y = p / d.W, x = p - y * d.W;
+        const double* src = dist0 + (long long)b * d.N;
+        const int xm = reflect101(x - 1, d.W), xp = reflect101(x + 1, d.W);
+        double t[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const int yy = reflect101(y + k - 1, d.H);
+            const double* row = src + (long long)yy * d.W;
+            double acc = __dmul_rn(0.25, row[xm]);
+            acc = __dadd_rn(acc, __dmul_rn(0.5, row[x]));
+            acc = __dadd_rn(acc, __dmul_rn(0.25, row[xp]));
+            t[k] = acc;
+        }
+        double acc = __dmul_rn(0.5, t[1]);
+        acc = __dadd_rn(acc, __dmul_rn(0.25, __dadd_rn(t[2], t[0])));
+        dist[i] = -acc;
+    }
+}
+
+// ------------------------------------------------------------------------------------------ hole filling + opening (P6 a,b)
+__global__ void border_flag_kernel(const int* __restrict__ Lbg, Dims d, int* __restrict__ flag) {
+    const int per = 2 * d.W + 2 * d.H;
+    const long long total = (long long)d.B * per;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int b = (int)(i / per);
+        int k = (int)(i - (long long)b * per), p;
+        if (k < d.W) p = k;
+        else if (k < 2 * d.W) p = (d.H - 1) * d.W + (k - d.W);
+        else if (k < 2 * d.W + d.H) p = (k - 2 * d.W) * d.W;
+        else p = (k - 2 * d.W - d.H) * d.W + d.W - 1;
+        const int r = Lbg[(long long)b * d.N + p];
+        if (r >= 0) flag[(long long)b * d.N + r] = 1;
+    }
+}
+__global__ void fill_kernel(const uint8_t* __restrict__ mk, const int* __restrict__ Lbg, const int* __restrict__ flag, Dims d,
+                            uint8_t* __restrict__ out) {
+    const long long total = (long long)d.B * d.N;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int r = Lbg[i];
+        out[i] = (mk[i] || (r >= 0 && flag[(i / d.N) * d.N + r] == 0)) ? 1 : 0;
+    }
+}
+// 5x5 MORPH_ELLIPSE: rows {0,0,1,0,0},{1,1,1,1,1}x3,{0,0,1,0,0}; taps outside the image are ignored
+__global__ void morph5_kernel(const uint8_t* __restrict__ src, Dims d, int dilate, uint8_t* __restrict__ dst) {
+    const long long total = (long long)d.B * d.N;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int b = (int)(i / d.N), p = (int)(i - (long long)b * d.N);
+        const int y = p / d.W, x = p - y * d.W;
+        const uint8_t* s = src + (long long)b * d.N;
+        int v = dilate ? 0 : 1;
+#pragma unroll
+        for (int dy = -2; dy <= 2; ++dy) {
+            const int yy = y + dy;
+            if (yy < 0 || yy >= d.H) continue;
+            const int half = (dy == -2 || dy == 2) ? 0 : 2;
+            for (int dx = -half; dx <= half; ++dx) {
+                const int xx = x + dx;
+                if (xx < 0 || xx >= d.W) continue;
+                const int q = s[yy * d.W + xx];
+                if (dilate) v |= q; else v &= q;
+            }
+        }
+        dst[i] = (uint8_t)v;
+    }
+}
+
+// ------------------------------------------------------------------------------------------ marker ids (P6 c,d)
+__global__ void root_flag_kernel(const int* __restrict__ L, Dims d, int* __restrict__ flag) {
+    const long long total = (long long)d.B * d.N;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x)
+        flag[i] = (L[i] == (int)(i % d.N)) ? 1 : 0;
+}
+// marker id = 1 + raster rank of the component's first pixel (scipy.ndimage.label), 0 if smaller than object_size.
+// Also initialises the flood output: labels = marker inside blb, 0 elsewhere (skimage: markers * mask).
+__global__ void marker_kernel(const int* __restrict__ L, const int* __restrict__ cnt, const int* __restrict__ rank, const uint8_t* __restrict__ blb,
+                              Dims d, int object_size, int* __restrict__ marker, int* __restrict__ labels) {
+    const long long total = (long long)d.B * d.N;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int r = L[i];
+        int id = 0;
+        if (r >= 0) {
+            const long long base = (i / d.N) * d.N;
+            if (cnt[base + r] >= object_size) id = rank[base + r] + 1;
+        }
+        marker[i] = id;
+        labels[i] = blb[i] ? id : 0;
+    }
+}
+
+// ------------------------------------------------------------------------------------------ blob work lists (P7 setup)
+// blobpix[b*N + off[root] + k] = tile-local pixel index of the k-th pixel of the blob (order irrelevant)
+__global__ void blob_scatter_kernel(const int* __restrict__ L1, const uint8_t* __restrict__ blb, const int* __restrict__ off, Dims d,
+                                    int* __restrict__ fill, int* __restrict__ blobpix) {
+    const long long total = (long long)d.B * d.N;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        if (!blb[i]) continue;
+        const long long base = (i / d.N) * d.N;
+        const int r = L1[i];
+        const int k = atomicAdd(&fill[base + r], 1);
+        blobpix[base + off[base + r] + k] = (int)(i - base);
+    }
+}
+// queue[0]: blobs with <= small_cap pixels, queue[1]: the rest. qcount[2]. entries are global indices b*N + root.
+__global__ void blob_queue_kernel(const int* __restrict__ L1, const int* __restrict__ cnt, Dims d, int min_size, int small_cap,
+                                  int* __restrict__ qcount, int* __restrict__ queue_s, int* __restrict__ queue_l) {
+    const long long total = (long long)d.B * d.N;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int p = (int)(i % d.N);
+        if (L1[i] != p) continue;
+        const int n = cnt[i];
+        if (n < min_size) continue;
+        if (n <= small_cap) queue_s[atomicAdd(&qcount[0], 1)] = (int)i;
+        else queue_l[atomicAdd(&qcount[1], 1)] = (int)i;
+    }
+}
+
+// ------------------------------------------------------------------------------------------ watershed (P7)
+struct HeapItem { double v; int age; int idx; };
+__device__ __forceinline__ bool h_less(double va, int aa, int ia, double vb, int ab, int ib) {
+    if (va != vb) return va < vb;
+    if (aa != ab) return aa < ab;
+    return ia < ib;
+}
+struct Heap {
+    double* key;
+    int2* pay;  // (age, idx)
+    int n;
+    __device__ __forceinline__ void sift_down(int i, double v, int age, int idx) {
+        for (;;) {
+            int c = 2 * i + 1;
+            if (c >= n) break;
+            double cv = key[c];
+            int2 cp = pay[c];
+            if (c + 1 < n) {
+                const double rv = key[c + 1];
+                const int2 rp = pay[c + 1];
+                if (h_less(rv, rp.x, rp.y, cv, cp.x, cp.y)) { ++c; cv = rv; cp = rp; }
+            }
+            if (!h_less(cv, cp.x, cp.y, v, age, idx)) break;
+            key[i] = cv; pay[i] = cp;
+            i = c;
+        }
+        key[i] = v; pay[i] = make_int2(age, idx);
+    }
+    __device__ __forceinline__ void push(double v, int age, int idx) {
+        int i = n++;
+        while (i > 0) {
+            const int par = (i - 1) >> 1;
+            const double pv = key[par];
+            const int2 pp = pay[par];
+            if (!h_less(v, age, idx, pv, pp.x, pp.y)) break;
+            key[i] = pv; pay[i] = pp;
+            i = par;
+        }
+        key[i] = v; pay[i] = make_int2(age, idx);
+    }
+    __device__ __forceinline__ int pop() {  // returns idx of the minimum
+        const int top = pay[0].y;
+        --n;
+        if (n > 0) sift_down(0, key[n], pay[n].x, pay[n].y);
+        return top;
+    }
+};
+
+// One warp per blob. Seeds = marker pixels that still have an unlabelled mask neighbour (interior seeds pop as
+// no-ops and never change `age`, so leaving them out does not change the result). Heap in shared memory when
+// the blob fits (cap_entries), else in the blob's slice of the global scratch arrays.
+__global__ void __launch_bounds__(32)
+watershed_kernel(const int* __restrict__ queue, const int* __restrict__ qcount_ptr, int* __restrict__ qhead, const int* __restrict__ cnt,
+                 const int* __restrict__ off, const int* __restrict__ blobpix, const uint8_t* __restrict__ blb, const int* __restrict__ marker,
+                 const double* __restrict__ dist, Dims d, int cap_entries, double* __restrict__ gkey, int2* __restrict__ gpay,
+                 int* labels_) {
+    extern __shared__ __align__(16) uint8_t ws_smem[];
+    volatile int* labels = labels_;
+    double* skey = reinterpret_cast<double*>(ws_smem);
+    int2* spay = reinterpret_cast<int2*>(ws_smem + (size_t)cap_entries * 8);
+    const int lane = threadIdx.x;
+    const int qn = *qcount_ptr;
+    for (;;) {
+        int item = 0;
+        if (lane == 0) item = atomicAdd(qhead, 1);
+        item = __shfl_sync(0xffffffffu, item, 0);
+        if (item >= qn) break;
+        const int gi = queue[item];
+        const long long base = ((long long)gi / d.N) * d.N;
+        const int root = (int)(gi - base);
+        const int n = cnt[base + root];
+        const int* list = blobpix + base + off[base + root];
+        const uint8_t* m = blb + base;
+        const int* mk = marker + base;
+        const double* ds = dist + base;
+        volatile int* out = labels + base;
+        Heap hp;
+        if (n <= cap_entries) { hp.key = skey; hp.pay = spay; }
+        else { hp.key = gkey + base + off[base + root]; hp.pay = gpay + base + off[base + root]; }
+        hp.n = 0;
+        // ---- collect boundary seeds (any order: the heap order is a strict total order)
+        int n_seed = 0;
+        for (int i0 = 0; i0 < n; i0 += 32) {
+            const int i = i0 + lane;
+            bool is_seed = false;
+            int p = 0;
+            if (i < n) {
+                p = list[i];
+                if (mk[p] > 0) {
+                    const int y = p / d.W, x = p - y * d.W;
+                    is_seed = (y > 0 && m[p - d.W] && mk[p - d.W] == 0) || (x > 0 && m[p - 1] && mk[p - 1] == 0) ||
+                              (x < d.W - 1 && m[p + 1] && mk[p + 1] == 0) || (y < d.H - 1 && m[p + d.W] && mk[p + d.W] == 0);
+                }
+            }
+            const uint32_t bits = __ballot_sync(0xffffffffu, is_seed);
+            if (is_seed) {
+                const int slot = n_seed + __popc(bits & ((1u << lane) - 1u));
+                hp.key[slot] = ds[p];
+                hp.pay[slot] = make_int2(0, p);
+            }
+            n_seed += __popc(bits);
+        }
+        __syncwarp();
+        hp.n = n_seed;
+        if (lane == 0) {
+            // Floyd heapify
+            for (int i = n_seed / 2 - 1; i >= 0; --i) hp.sift_down(i, hp.key[i], hp.pay[i].x, hp.pay[i].y);
+        }
+        __syncwarp();
+        // ---- flood: pop min; neighbours up, left, right, down; label at push time
+        int age = 0;
+        int hn = __shfl_sync(0xffffffffu, hp.n, 0);
+        while (hn > 0) {
+            int p = 0;
+            if (lane == 0) p = hp.pop();
+            p = __shfl_sync(0xffffffffu, p, 0);
+            const int y = p / d.W, x = p - y * d.W;
+            int q = -1;
+            if (lane == 0 && y > 0) q = p - d.W;
+            else if (lane == 1 && x > 0) q = p - 1;
+            else if (lane == 2 && x < d.W - 1) q = p + 1;
+            else if (lane == 3 && y < d.H - 1) q = p + d.W;
+            bool take = false;
+            double qv = 0.0;
+            if (q >= 0 && m[q] && out[q] == 0) { take = true; qv = ds[q]; }
+            const uint32_t bits = __ballot_sync(0xffffffffu, take) & 0xFu;
+            const int lab = out[p];
+            for (int k = 0; k < 4; ++k) {
+                if (!(bits >> k & 1u)) continue;
+                const int qq = __shfl_sync(0xffffffffu, q, k);
+                const double vv = __shfl_sync(0xffffffffu, qv, k);
+                if (lane == 0) {
+                    ++age;
+                    out[qq] = lab;
+                    hp.push(vv, age, qq);
+                }
+            }
+            __syncwarp();
+            hn = __shfl_sync(0xffffffffu, hp.n, 0);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------ instance table (P8/P9)
+struct Acc {  // 64 bytes per id
+    int area;
+    int rmin, rmax, cmin, cmax;
+    int pad;
+    unsigned long long sx, sy;
+    int hist[8];
+};
+__global__ void table_init_kernel(Acc* acc, long long n, int H, int W) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        Acc a;
+        a.area = 0; a.rmin = H; a.rmax = -1; a.cmin = W; a.cmax = -1; a.pad = 0; a.sx = 0; a.sy = 0;
+        for (int k = 0; k < 8; ++k) a.hist[k] = 0;
+        acc[i] = a;
+    }
+}
+__global__ void table_accum_kernel(const int* __restrict__ labels, const uint8_t* __restrict__ tmap, Dims d, int cap, Acc* __restrict__ acc,
+                                   int* __restrict__ status) {
+    const long long total = (long long)d.B * d.N;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int l = labels[i];
+        const int b = (int)(i / d.N), p = (int)(i - (long long)b * d.N);
+        if (l == 0) {  // only "is there any background" matters (the np.unique(...)[1:] quirk)
+            if (acc[(long long)b * cap].area == 0) acc[(long long)b * cap].area = 1;
+            continue;
+        }
+        if (l >= cap) { atomicOr(&status[b], 1); continue; }
+        Acc* a = acc + (long long)b * cap + l;
+        const int y = p / d.W, x = p - y * d.W;
+        atomicAdd(&a->area, 1);
+        atomicAdd(&a->sx, (unsigned long long)x);
+        atomicAdd(&a->sy, (unsigned long long)y);
+        if (y < a->rmin) atomicMin(&a->rmin, y);
+        if (y > a->rmax) atomicMax(&a->rmax, y);
+        if (x < a->cmin) atomicMin(&a->cmin, x);
+        if (x > a->cmax) atomicMax(&a->cmax, x);
+        if (tmap) {
+            const int t = tmap[i];
+            if (t < 8) atomicAdd(&a->hist[t], 1);
+        }
+    }
+}
+// one block per tile: compact present ids in ascending order into rows
+__global__ void __launch_bounds__(256)
+table_finalize_kernel(const Acc* __restrict__ acc, int cap, int n_types, int max_rows, cvb_inst_row* __restrict__ table, int* __restrict__ counts) {
+    const int b = blockIdx.x;
+    const Acc* A = acc + (long long)b * cap;
+    cvb_inst_row* rows = table + (long long)b * max_rows;
+    __shared__ int s_base, s_first;
+    if (threadIdx.x == 0) { s_base = 0; s_first = (A[0].area > 0) ? 0 : 1; }  // no background -> drop the smallest id
+    __syncthreads();
+    for (int c0 = 1; c0 < cap; c0 += 256) {
+        const int id = c0 + threadIdx.x;
+        const bool present = id < cap && A[id].area > 0;
+        int tot;
+        const int ex = block_excl_scan_256(present ? 1 : 0, &tot);
+        const int base = s_base, drop = s_first;
+        __syncthreads();
+        if (present) {
+            const int pos = base + ex - drop;  // position among present ids, minus the dropped first one
+            if (pos >= 0 && pos < max_rows) {
+                const Acc a = A[id];
+                cvb_inst_row r;
+                r.id = id;
+                r.rmin = a.rmin; r.cmin = a.cmin; r.rmax = a.rmax + 1; r.cmax = a.cmax + 1;
+                r.area = a.area;
+                const double m00 = (double)a.area;
+                r.cx = __dadd_rn(__ddiv_rn((double)((long long)a.sx - (long long)a.cmin * a.area), m00), (double)a.cmin);
+                r.cy = __dadd_rn(__ddiv_rn((double)((long long)a.sy - (long long)a.rmin * a.area), m00), (double)a.rmin);
+                int best = -1, second = -1;
+                for (int t = 0; t < n_types && t < 8; ++t) {
+                    r.hist[t] = a.hist[t];
+                    if (a.hist[t] == 0) continue;
+                    if (best < 0 || a.hist[t] > a.hist[best]) { second = best; best = t; }
+                    else if (second < 0 || a.hist[t] > a.hist[second]) second = t;
+                }
+                for (int t = (n_types < 8 ? (n_types < 0 ? 0 : n_types) : 8); t < 8; ++t) r.hist[t] = 0;
+                int ty = best;
+                if (ty == 0 && second >= 0) ty = second;
+                r.type = ty;
+                r.type_prob = ty >= 0 ? __ddiv_rn((double)a.hist[ty], __dadd_rn((double)a.area, 1.0e-6)) : 0.0;
+                r.type_prob_f = (float)r.type_prob;
+                rows[pos] = r;
+            }
+        }
+        if (threadIdx.x == 0) s_base = base + tot;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const int n = s_base - s_first;
+        counts[b] = n < 0 ? 0 : n;
+    }
+}
+
+// ------------------------------------------------------------------------------------------ host orchestration
+void sobel_taps_host(int ksize, SobelTaps* t) {
+    // cv::getSobelKernels for ksize > 7 (integer recurrences), orders 1 and 0
+    for (int order = 0; order < 2; ++order) {
+        long long ker[64] = {0};
+        ker[0] = 1;
+        for (int i = 0; i < ksize - order - 1; ++i) {
+            long long oldv = ker[0];
+            for (int j = 1; j <= ksize; ++j) { const long long nv = ker[j] + ker[j - 1]; ker[j - 1] = oldv; oldv = nv; }
+        }
+        for (int i = 0; i < order; ++i) {
+            long long oldv = -ker[0];
+            for (int j = 1; j <= ksize; ++j) { const long long nv = ker[j - 1] - ker[j]; ker[j - 1] = oldv; oldv = nv; }
+        }
+        for (int j = 0; j < 32; ++j) (order ? t->kd : t->ks)[j] = j < ksize ? (double)ker[j] : 0.0;
+    }
+    t->ksize = ksize;
+}
+
+struct Carve {
+    uint8_t* base; size_t off;
+    template <class T> T* take(size_t n) { off = align_up(off, 256); T* p = base ? reinterpret_cast<T*>(base + off) : nullptr; off += n * sizeof(T); return p; }
+};
+struct Ws {
+    uint8_t *npbin, *tmap, *blb, *mk, *mk2;
+    int *L1, *cnt1, *off1, *fill1, *blobpix, *Lx, *cntx, *flagx, *rankx, *marker, *bsum, *queue_s, *queue_l, *qmeta, *status;
+    uint32_t* mm;
+    unsigned long long* mm64;
+    double *sob, *dist0, *dist, *gkey;
+    int2* gpay;
+    Acc* acc;
+    int cap;
+    size_t bytes;
+};
+constexpr int SMALL_CAP = 1024;   // heap entries (16 B each) of the many-CTAs-per-SM flood kernel
+constexpr int LARGE_CAP = 12288;  // 192 KB of shared memory
+
+Ws carve(void* base, int B, int H, int W) {
+    Ws w{};
+    Carve c{reinterpret_cast<uint8_t*>(base), 0};
+    const size_t BN = (size_t)B * H * W;
+    const int nb = ((H * W) + SCAN_BLOCK - 1) / SCAN_BLOCK;
+    w.cap = H * W / 8 + 16;
+    w.npbin = c.take<uint8_t>(BN); w.tmap = c.take<uint8_t>(BN); w.blb = c.take<uint8_t>(BN);
+    w.mk = c.take<uint8_t>(BN); w.mk2 = c.take<uint8_t>(BN);
+    w.L1 = c.take<int>(BN); w.cnt1 = c.take<int>(BN); w.off1 = c.take<int>(BN); w.fill1 = c.take<int>(BN); w.blobpix = c.take<int>(BN);
+    w.Lx = c.take<int>(BN); w.cntx = c.take<int>(BN); w.flagx = c.take<int>(BN); w.rankx = c.take<int>(BN); w.marker = c.take<int>(BN);
+    w.bsum = c.take<int>((size_t)B * nb + 256);
+    w.queue_s = c.take<int>(BN / 8 + 64); w.queue_l = c.take<int>(BN / 8 + 64);
+    w.qmeta = c.take<int>(16); w.status = c.take<int>(B + 16);
+    w.mm = c.take<uint32_t>((size_t)B * 4 + 16); w.mm64 = c.take<unsigned long long>((size_t)B * 4 + 16);
+    w.sob = c.take<double>(BN * 2); w.dist0 = c.take<double>(BN); w.dist = c.take<double>(BN);
+    w.gkey = c.take<double>(BN); w.gpay = c.take<int2>(BN);
+    w.acc = c.take<Acc>((size_t)B * w.cap);
+    w.bytes = c.off + 4096;
+    return w;
+}
+
+int grid1d(long long n, int block = 256) {
+    long long g = (n + block - 1) / block;
+    const long long cap = (long long)cvb_num_sms() * 32;
+    return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+int scan_i32(const int* in, int as_flag, Dims d, int* bsum, int* out, cudaStream_t st) {
+    const int nb = (d.N + SCAN_BLOCK - 1) / SCAN_BLOCK;
+    scan_reduce_kernel<<<dim3(nb, d.B), 256, 0, st>>>(in, as_flag, d.N, nb, bsum);
+    scan_bsums_kernel<<<d.B, 256, 0, st>>>(nb, bsum);
+    scan_apply_kernel<<<dim3(nb, d.B), 256, 0, st>>>(in, as_flag, d.N, nb, bsum, out);
+    CVB_CUDA(cudaGetLastError());
+    return CVB_OK;
+}
+
+int ccl(const uint8_t* mask, int want, Dims d, int* L, cudaStream_t st) {
+    const long long warps = (long long)d.B * d.H * ((d.W + 31) / 32);
+    ccl_init_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(mask, want, d, L);
+    ccl_merge_kernel<<<grid1d((long long)d.B * d.N), 256, 0, st>>>(mask, want, d, L);
+    ccl_compress_kernel<<<grid1d((long long)d.B * d.N), 256, 0, st>>>(d, L);
+    CVB_CUDA(cudaGetLastError());
+    return CVB_OK;
+}
+
+int run_pipeline(const Ws& w, const float* hv, Dims d, int n_types, int object_size, int ksize, bool have_types, int32_t* labels,
+                 cvb_inst_row* table, int32_t* counts, int max_rows, uint8_t* dbg_blb, double* dbg_dist, int32_t* dbg_marker,
+                 cudaStream_t st) {
+    const size_t BN = (size_t)d.B * d.N;
+    const int g = grid1d((long long)BN);
+    // ---- P1/P2
+    CVB_TRY(ccl(w.npbin, 1, d, w.L1, st));
+    CVB_CUDA(cudaMemsetAsync(w.cnt1, 0, BN * 4, st));
+    count_kernel<<<g, 256, 0, st>>>(w.L1, d, w.cnt1);
+    blb_kernel<<<g, 256, 0, st>>>(w.L1, w.cnt1, d, 10, w.blb);
+    // ---- P3/P4
+    CVB_CUDA(cudaMemsetAsync(w.mm, 0, (size_t)d.B * 4 * 4, st));
+    {
+        // min slots start at 0xFFFFFFFF, max slots at 0: set min slots with a strided memset2D
+        CVB_CUDA(cudaMemset2DAsync(w.mm, 8, 0xFF, 4, (size_t)d.B * 2, st));
+        CVB_CUDA(cudaMemsetAsync(w.mm64, 0, (size_t)d.B * 4 * 8, st));
+        CVB_CUDA(cudaMemset2DAsync(w.mm64, 16, 0xFF, 8, (size_t)d.B * 2, st));
+    }
+    minmax_f32_kernel<<<dim3(32, d.B * 2), 256, 0, st>>>(hv, d, w.mm);
+    SobelTaps taps;
+    sobel_taps_host(ksize, &taps);
+    {
+        const int r = ksize / 2;
+        const size_t in_bytes = (((size_t)(SB_TH + 2 * r) * (SB_TW + 2 * r) * 4) + 15) & ~(size_t)15;
+        const size_t smem = in_bytes + (size_t)(SB_TH + 2 * r) * SB_TW * 8;
+        static bool configured = false;
+        if (!configured) {
+            CVB_CUDA(cudaFuncSetAttribute(sobel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+            configured = true;
+        }
+        dim3 grid((d.W + SB_TW - 1) / SB_TW, (d.H + SB_TH - 1) / SB_TH, d.B * 2);
+        sobel_kernel<<<grid, 256, smem, st>>>(hv, d, w.mm, taps, w.sob, w.mm64);
+    }
+    // ---- P5
+    energy_kernel<<<g, 256, 0, st>>>(w.sob, w.mm64, w.blb, d, w.dist0, w.mk);
+    blur_kernel<<<g, 256, 0, st>>>(w.dist0, d, w.dist);
+    // ---- P6a: fill holes = background components that do not touch the border
+    CVB_TRY(ccl(w.mk, 0, d, w.Lx, st));
+    CVB_CUDA(cudaMemsetAsync(w.flagx, 0, BN * 4, st));
+    border_flag_kernel<<<grid1d((long long)d.B * (2 * d.W + 2 * d.H)), 256, 0, st>>>(w.Lx, d, w.flagx);
+    fill_kernel<<<g, 256, 0, st>>>(w.mk, w.Lx, w.flagx, d, w.mk2);
+    // ---- P6b: opening
+    morph5_kernel<<<g, 256, 0, st>>>(w.mk2, d, 0, w.mk);
+    morph5_kernel<<<g, 256, 0, st>>>(w.mk, d, 1, w.mk2);
+    // ---- P6c/d: label markers in raster order, drop small ones
+    CVB_TRY(ccl(w.mk2, 1, d, w.Lx, st));
+    CVB_CUDA(cudaMemsetAsync(w.cntx, 0, BN * 4, st));
+    count_kernel<<<g, 256, 0, st>>>(w.Lx, d, w.cntx);
+    root_flag_kernel<<<g, 256, 0, st>>>(w.Lx, d, w.flagx);
+    CVB_TRY(scan_i32(w.flagx, 1, d, w.bsum, w.rankx, st));
+    marker_kernel<<<g, 256, 0, st>>>(w.Lx, w.cntx, w.rankx, w.blb, d, object_size, w.marker, labels);
+    // ---- P7: per-blob floods
+    CVB_TRY(scan_i32(w.cnt1, 0, d, w.bsum, w.off1, st));
+    CVB_CUDA(cudaMemsetAsync(w.fill1, 0, BN * 4, st));
+    CVB_CUDA(cudaMemsetAsync(w.qmeta, 0, 16 * 4, st));
+    blob_scatter_kernel<<<g, 256, 0, st>>>(w.L1, w.blb, w.off1, d, w.fill1, w.blobpix);
+    blob_queue_kernel<<<g, 256, 0, st>>>(w.L1, w.cnt1, d, 10, SMALL_CAP, w.qmeta, w.queue_s, w.queue_l);
+    {
+        static bool configured = false;
+        if (!configured) {
+            CVB_CUDA(cudaFuncSetAttribute(watershed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LARGE_CAP * 16));
+            configured = true;
+        }
+        const int sms = cvb_num_sms();
+        watershed_kernel<<<sms * 12, 32, SMALL_CAP * 16, st>>>(w.queue_s, w.qmeta + 0, w.qmeta + 2, w.cnt1, w.off1, w.blobpix, w.blb,
+                                                               w.marker, w.dist, d, SMALL_CAP, w.gkey, w.gpay, labels);
+        watershed_kernel<<<sms, 32, LARGE_CAP * 16, st>>>(w.queue_l, w.qmeta + 1, w.qmeta + 3, w.cnt1, w.off1, w.blobpix, w.blb,
+                                                          w.marker, w.dist, d, LARGE_CAP, w.gkey, w.gpay, labels);
+    }
+    // ---- P8/P9
+    if (table && counts) {
+        CVB_CUDA(cudaMemsetAsync(w.status, 0, (size_t)d.B * 4, st));
+        table_init_kernel<<<grid1d((long long)d.B * w.cap), 256, 0, st>>>(w.acc, (long long)d.B * w.cap, d.H, d.W);
+        table_accum_kernel<<<g, 256, 0, st>>>(labels, have_types ? w.tmap : nullptr, d, w.cap, w.acc, w.status);
+        table_finalize_kernel<<<d.B, 256, 0, st>>>(w.acc, w.cap, have_types ? n_types : 0, max_rows, table, counts);
+    }
+    if (dbg_blb) CVB_CUDA(cudaMemcpyAsync(dbg_blb, w.blb, BN, cudaMemcpyDeviceToDevice, st));
+    if (dbg_dist) CVB_CUDA(cudaMemcpyAsync(dbg_dist, w.dist, BN * 8, cudaMemcpyDeviceToDevice, st));
+    if (dbg_marker) CVB_CUDA(cudaMemcpyAsync(dbg_marker, w.marker, BN * 4, cudaMemcpyDeviceToDevice, st));
+    CVB_CUDA(cudaGetLastError());
+    return CVB_OK;
+}
+
+int check_common(int B, int H, int W, int ksize, int max_rows, const void* ws, size_t ws_bytes, size_t need) {
+    CVB_CHECK(B > 0 && H > 0 && W > 0, CVB_EARG, "cvb_postproc: empty shape");
+    CVB_CHECK((long long)B * H * W < (1ll << 31), CVB_ESHAPE, "cvb_postproc: batch too large for 32-bit pixel indices");
+    CVB_CHECK(ksize % 2 == 1 && ksize >= 3 && ksize <= 2 * SB_MAXR + 1, CVB_ESHAPE, "cvb_postproc: Sobel ksize %d not supported", ksize);
+    CVB_CHECK(max_rows >= 0, CVB_EARG, "cvb_postproc: negative max_rows");
+    CVB_CHECK(ws != nullptr && ((uintptr_t)ws & 255) == 0, CVB_EARG, "cvb_postproc: workspace must be non-null and 256-byte aligned");
+    CVB_CHECK(ws_bytes >= need, CVB_EWORKSPACE, "cvb_postproc: workspace %zu < required %zu bytes", ws_bytes, need);
+    return CVB_OK;
+}
+
+}  // namespace
+
+#define CVB_API extern "C" __attribute__((visibility("default")))
+
+CVB_API int cvb_postproc_workspace_bytes(int B, int H, int W, size_t* out) {
+    CVB_CHECK(out && B > 0 && H > 0 && W > 0, CVB_EARG, "cvb_postproc_workspace_bytes: bad arguments");
+    *out = carve(nullptr, B, H, W).bytes;
+    return CVB_OK;
+}
+
+CVB_API int cvb_postproc(const float* np_map, const float* hv, const float* nt_map, int B, int H, int W, int n_types,
+                         int magnification, int32_t* labels, cvb_inst_row* table, int32_t* counts, int max_rows,
+                         void* workspace, size_t ws_bytes, void* stream) {
+    CVB_CHECK(np_map && hv && labels, CVB_EARG, "cvb_postproc: null map");
+    int object_size, ksize;
+    if (magnification == 40) { object_size = 10; ksize = 21; }
+    else if (magnification == 20) { object_size = 3; ksize = 11; }
+    else { cvb_set_error("Unknown magnification"); return CVB_EARG; }
+    CVB_CHECK(nt_map == nullptr || (n_types >= 1 && n_types <= 8), CVB_ESHAPE, "cvb_postproc: n_types must be in 1..8");
+    size_t need = 0;
+    CVB_TRY(cvb_postproc_workspace_bytes(B, H, W, &need));
+    CVB_TRY(check_common(B, H, W, ksize, max_rows, workspace, ws_bytes, need));
+    const Ws w = carve(workspace, B, H, W);
+    const Dims d{B, H, W, H * W};
+    cudaStream_t st = (cudaStream_t)stream;
+    prep_float_kernel<<<grid1d((long long)B * d.N), 256, 0, st>>>(np_map, nt_map, n_types, d, w.npbin, w.tmap);
+    return run_pipeline(w, hv, d, n_types, object_size, ksize, nt_map != nullptr, labels, table, counts, max_rows, nullptr, nullptr,
+                        nullptr, st);
+}
+
+CVB_API int cvb_postproc_maps(const uint8_t* np_bin, const float* hv, const int32_t* type_map, int B, int H, int W, int n_types,
+                              int object_size, int ksize, int32_t* labels, cvb_inst_row* table, int32_t* counts, int max_rows,
+                              uint8_t* dbg_blb, double* dbg_dist, int32_t* dbg_marker, void* workspace, size_t ws_bytes,
+                              void* stream) {
+    CVB_CHECK(np_bin && hv && labels, CVB_EARG, "cvb_postproc_maps: null map");
+    CVB_CHECK(type_map == nullptr || (n_types >= 1 && n_types <= 8), CVB_ESHAPE, "cvb_postproc_maps: n_types must be in 1..8");
+    size_t need = 0;
+    CVB_TRY(cvb_postproc_workspace_bytes(B, H, W, &need));
+    CVB_TRY(check_common(B, H, W, ksize, max_rows, workspace, ws_bytes, need));
+    const Ws w = carve(workspace, B, H, W);
+    const Dims d{B, H, W, H * W};
+    cudaStream_t st = (cudaStream_t)stream;
+    CVB_CUDA(cudaMemcpyAsync(w.npbin, np_bin, (size_t)B * d.N, cudaMemcpyDeviceToDevice, st));
+    if (type_map) prep_maps_kernel<<<grid1d((long long)B * d.N), 256, 0, st>>>(type_map, (long long)B * d.N, w.tmap);
+    return run_pipeline(w, hv, d, n_types, object_size, ksize, type_map != nullptr, labels, table, counts, max_rows, dbg_blb, dbg_dist,
+                        dbg_marker, st);
+}

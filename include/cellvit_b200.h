@@ -1,0 +1,130 @@
+/*
+ * cellvit_b200.h -- C ABI of libcellvit_b200.so: the B200-native CellViT tile-inference hot path
+ * (network forward + HoVer-Net post-processing).
+ *
+ * The reference (TIO-IKIM/CellViT) is pure Python with no FFI layer; the boundary it exposes for this path is the
+ * Python API cited next to each entry point below. A binding only needs ctypes: every
+ * argument is a plain pointer or integer, there are no torch types, no exceptions cross the boundary.
+ *
+ * Conventions
+ *   - return value: 0 = OK, <0 = error class (below); cvb_last_error() gives the thread-local message.
+ *   - all data pointers are DEVICE pointers unless the name says host; buffers are caller-allocated.
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*) and performs no allocation and no
+ *     synchronisation, so sequences of calls can be captured into a CUDA graph.
+ *   - one cvb_model per device; a handle is not thread-safe, different handles are independent.
+ */
+#ifndef CELLVIT_B200_H
+#define CELLVIT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CVB_OK 0
+#define CVB_EARG -1        /* bad argument (null pointer, missing parameter, ...)                           */
+#define CVB_ESHAPE -2      /* unsupported shape (e.g. H or W not divisible by 16: cellvit.py:170-175)       */
+#define CVB_ECUDA -3       /* CUDA runtime / driver error                                                   */
+#define CVB_EWORKSPACE -4  /* workspace too small                                                           */
+#define CVB_EOVERFLOW -5   /* instance table overflow: counts[] holds the number of rows that were needed  */
+
+int cvb_version(void);
+const char* cvb_last_error(void);
+
+/* ------------------------------------------------------------------------------------------------ forward
+ * Replaces  CellViT.forward / CellViT256.forward / CellViTSAM.forward
+ *   models/segmentation/cell_segmentation/cellvit.py:153-210, :586-644  (+ encoder wrappers utils.py:149-233)
+ */
+typedef struct cvb_model cvb_model;
+
+typedef struct {
+    int sam;            /* 1: SAM ViTDet encoder (windowed + global attention, rel-pos); 0: ViT-S/16 with cls token */
+    int embed_dim;      /* 1280 / 1024 / 768 (SAM-H/L/B), 384 (ViT-256)                   cellvit.py:660-665   */
+    int depth;
+    int num_heads;
+    int window_size;    /* 14 for SAM (cellvit.py:563), ignored when sam == 0                                 */
+    int n_global;       /* number of entries used in global_idx                                               */
+    int global_idx[8];  /* blocks with global attention (cellvit.py:664)                                      */
+    int extract[4];     /* 1-based block indices after which skips z1..z4 are taken (cellvit.py:665)          */
+    int n_np_out;       /* 2, or 4 with regression_loss (cellvit.py:134-141)                                  */
+    int n_nt;           /* num_nuclei_classes                                                                 */
+    int n_tissue;       /* num_tissue_classes                                                                 */
+    int skip11, skip12; /* decoder widths (cellvit.py:106-113)                                                */
+    int bott_pad;       /* bottleneck width padded to a multiple of 64 (312 -> 320 for ViT-256)               */
+} cvb_model_desc;
+
+int cvb_model_create(const cvb_model_desc* desc, cvb_model** out);
+void cvb_model_destroy(cvb_model* m);
+
+/* Registers one packed parameter tensor (device pointer; the caller keeps it alive). Names and layouts are
+ * listed in DESIGN.md ("packed parameter table"); cellvit_b200/packing.py produces them from a reference
+ * state_dict (what nn.Module.load_state_dict consumes, cell_detection.py:131-138). */
+int cvb_model_set_param(cvb_model* m, const char* name, const void* dev_ptr);
+
+int cvb_model_workspace_bytes(cvb_model* m, int B, int H, int W, size_t* out);
+
+/* x [B,3,H,W] fp32 (already normalised, cell_detection.py:214-227). Outputs are raw logits, fp32 NCHW:
+ * np_logits [B,n_np_out,H,W], hv [B,2,H,W], nt_logits [B,n_nt,H,W], tissue [B,n_tissue],
+ * tokens [B,embed_dim,H/16,W/16] (nullable; the z4 skip, retrieve_tokens=True). H == W in {256, 512, 1024}. */
+int cvb_forward(cvb_model* m, const float* x, int B, int H, int W, float* np_logits, float* hv, float* nt_logits,
+                float* tissue, float* tokens, void* workspace, size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------ post-processing
+ * Replaces  DetectionCellPostProcessor.post_process_cell_segmentation  (cell_segmentation/utils/post_proc_cellvit.py:67-249)
+ * as driven per tile by  CellViT.calculate_instance_map  (cellvit.py:332-383).
+ */
+typedef struct {
+    int32_t id;                      /* instance id = marker label (non-contiguous)                            */
+    int32_t rmin, cmin, rmax, cmax;  /* bbox, max exclusive (tools.py:24-34)                                   */
+    int32_t area;
+    int32_t type;                    /* majority vote with the "0 yields to runner-up" rule (:141-147)         */
+    float type_prob_f;
+    double cx, cy;                   /* centroid x,y (:117-125)                                                */
+    double type_prob;                /* count / (area + 1e-6) (:149)                                           */
+    int32_t hist[8];                 /* per-class pixel counts                                                 */
+} cvb_inst_row;
+
+int cvb_postproc_workspace_bytes(int B, int H, int W, size_t* out);
+
+/* np_map [B,2,H,W] and nt_map [B,n_types,H,W] fp32 (probabilities or logits -- only the argmax is used,
+ * cellvit.py:369-375; first maximum wins like torch.argmax), hv [B,2,H,W] fp32.
+ * magnification 40 or 20 (post_proc_cellvit.py:55-62). Outputs: labels int32 [B,H,W]; table [B,max_rows];
+ * counts int32 [B]. nt_map may be null (nr_types=None). */
+int cvb_postproc(const float* np_map, const float* hv, const float* nt_map, int B, int H, int W, int n_types,
+                 int magnification, int32_t* labels, cvb_inst_row* table, int32_t* counts, int max_rows,
+                 void* workspace, size_t ws_bytes, void* stream);
+
+/* Same, from already arg-maxed maps: np_bin uint8 [B,H,W] (0/1), type_map int32 [B,H,W] (nullable). Optional
+ * debug outputs (nullable) expose the stage results the parity tests compare with the oracle:
+ * blb uint8, dist float64, marker int32, all [B,H,W]. object_size / ksize are the resolved magnification
+ * parameters (10,21 @x40; 3,11 @x20; 100,21 for gt). */
+int cvb_postproc_maps(const uint8_t* np_bin, const float* hv, const int32_t* type_map, int B, int H, int W, int n_types,
+                      int object_size, int ksize, int32_t* labels, cvb_inst_row* table, int32_t* counts, int max_rows,
+                      uint8_t* dbg_blb, double* dbg_dist, int32_t* dbg_marker, void* workspace, size_t ws_bytes,
+                      void* stream);
+
+/* ------------------------------------------------------------------------------------------------ operator level
+ * The individual device operators, exposed for unit parity tests and for callers that want to compose them.
+ * cvb_tc_epilogue mirrors TcEpilogue in cellvit_b200/csrc/tc_gemm.h (see that header for field semantics). */
+struct TcEpilogue;
+int cvb_tc_epilogue_bytes(void);
+int cvb_op_gemm_f16(const void* A, int M, int K, long long lda, const void* W, int N, long long ldw, int block_n,
+                    const struct TcEpilogue* epi, void* stream);
+int cvb_op_conv3x3_f16(const void* src0, int C0, const void* src1, int C1, int NB, int H, int W, const void* Wp, int N,
+                       int block_n, const struct TcEpilogue* epi, void* stream);
+int cvb_op_layernorm_f16(const float* x, const float* gamma, const float* beta, float eps, int rows_dst, int D, void* out,
+                         int map, int B, int tok_h, int tok_w, int ws, int g, void* stream);
+int cvb_op_relpos(const void* qkv, int Gb, int heads, int hd, int gh, int gw, const float* Rh, const float* Rw,
+                  float* rel_h, float* rel_w, void* stream);
+int cvb_op_attention(const void* qkv, int Gb, int S, int heads, int hd, float scale, const float* rel_h,
+                     const float* rel_w, int gh, int gw, void* out, void* stream);
+int cvb_op_patch_im2col(const float* x, int B, int H, int W, int P, void* out, void* stream);
+int cvb_op_stem_conv(const float* x, int B, int H, int W, const float* w, const float* scale, const float* shift,
+                     void* out, int cpad, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CELLVIT_B200_H */

@@ -1,0 +1,106 @@
+"""GPU parity of the encoder helper kernels and of the whole forward against the fp32 oracle
+(oracle/forward_oracle.py, pinned to the reference modules). Tolerance on NP/HV/NT head maps: 1e-3 abs
+(BASELINE.json north_star)."""
+import ctypes as C
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from cellvit_b200 import _lib as L
+from cellvit_b200 import synth, weights
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-3
+
+
+@pytest.fixture(autouse=True)
+def _no_tf32():
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    yield
+
+
+def test_layernorm_identity_and_window_partition():
+    g = torch.Generator(device="cuda").manual_seed(0)
+    B, h, D, ws = 2, 16, 1280, 14
+    x = torch.randn(B, h, h, D, device="cuda", generator=g) * 2 + 0.3
+    gamma = torch.rand(D, device="cuda", generator=g) + 0.5
+    beta = torch.randn(D, device="cuda", generator=g) * 0.1
+    ref = F.layer_norm(x, (D,), gamma, beta, 1e-6)
+    out = torch.empty(B * h * h, D, device="cuda", dtype=torch.half)
+    L.check(L.lib().cvb_op_layernorm_f16(L.ptr(x), L.ptr(gamma), L.ptr(beta), C.c_float(1e-6), B * h * h, D, L.ptr(out), 0, B, h, h, 0, 0,
+                                         L.stream_ptr()), "ln")
+    assert (out.float().view_as(ref) - ref).abs().max().item() < 5e-3
+    gw = (h + ws - 1) // ws
+    outw = torch.full((B * gw * gw * ws * ws, D), float("nan"), device="cuda", dtype=torch.half)
+    L.check(L.lib().cvb_op_layernorm_f16(L.ptr(x), L.ptr(gamma), L.ptr(beta), C.c_float(1e-6), outw.shape[0], D, L.ptr(outw), 1, B, h, h, ws,
+                                         gw, L.stream_ptr()), "ln-win")
+    pad = gw * ws - h
+    refw = F.pad(ref, (0, 0, 0, pad, 0, pad)).view(B, gw, ws, gw, ws, D).permute(0, 1, 3, 2, 4, 5).reshape(-1, D)
+    assert (outw.float() - refw).abs().max().item() < 5e-3
+
+
+def _ref_attention(qkv, Gb, S, heads, hd, scale, Rh=None, Rw=None, gh=0, gw=0):
+    D = heads * hd
+    q, k, v = qkv.float().view(Gb, S, 3, heads, hd).permute(2, 0, 3, 1, 4)
+    attn = (q * scale) @ k.transpose(-2, -1)
+    if Rh is not None:
+        idx_h = (torch.arange(gh, device=qkv.device)[:, None] - torch.arange(gh, device=qkv.device)[None, :]) + gh - 1
+        idx_w = (torch.arange(gw, device=qkv.device)[:, None] - torch.arange(gw, device=qkv.device)[None, :]) + gw - 1
+        rq = q.reshape(Gb, heads, gh, gw, hd)
+        rel_h = torch.einsum("bnhwc,hkc->bnhwk", rq, Rh[idx_h])
+        rel_w = torch.einsum("bnhwc,wkc->bnhwk", rq, Rw[idx_w])
+        attn = (attn.view(Gb, heads, gh, gw, gh, gw) + rel_h[..., :, None] + rel_w[..., None, :]).view(Gb, heads, S, S)
+    o = attn.softmax(-1) @ v
+    return o.permute(0, 2, 1, 3).reshape(Gb * S, D)
+
+
+@pytest.mark.parametrize("Gb,gh,gw,heads,hd,bias", [(2, 1, 257, 6, 64, False), (2, 16, 16, 16, 80, True), (18, 14, 14, 12, 64, True),
+                                                    (1, 64, 64, 4, 80, True), (50, 14, 14, 16, 80, True)])
+def test_attention_matches_torch(Gb, gh, gw, heads, hd, bias):
+    g = torch.Generator(device="cuda").manual_seed(7)
+    S, D = gh * gw, heads * hd
+    qkv = (torch.randn(Gb * S, 3 * D, device="cuda", generator=g)).half()
+    out = torch.full((Gb * S, D), float("nan"), device="cuda", dtype=torch.half)
+    scale = hd ** -0.5
+    Rh = Rw = rel_h = rel_w = None
+    if bias:
+        Rh = torch.randn(2 * gh - 1, hd, device="cuda", generator=g) * 0.2
+        Rw = torch.randn(2 * gw - 1, hd, device="cuda", generator=g) * 0.2
+        rel_h = torch.empty(Gb * heads, S, gh, device="cuda")
+        rel_w = torch.empty(Gb * heads, S, gw, device="cuda")
+        L.check(L.lib().cvb_op_relpos(L.ptr(qkv), Gb, heads, hd, gh, gw, L.ptr(Rh), L.ptr(Rw), L.ptr(rel_h), L.ptr(rel_w), L.stream_ptr()), "relpos")
+    L.check(L.lib().cvb_op_attention(L.ptr(qkv), Gb, S, heads, hd, C.c_float(scale), L.ptr(rel_h), L.ptr(rel_w), gh, gw, L.ptr(out),
+                                     L.stream_ptr()), "attention")
+    torch.cuda.synchronize()
+    ref = _ref_attention(qkv, Gb, S, heads, hd, scale, Rh, Rw, gh, gw)
+    err = (out.float() - ref).abs().max().item()
+    assert err < 4e-3, err
+
+
+def _oracle(arch, size, B, wseed=3, xseed=5):
+    from oracle import forward_oracle
+    sd = weights.synth_state_dict(arch, 6, 19, seed=wseed)
+    x = torch.from_numpy(synth.synthetic_tiles(B, size, seed=xseed))
+    return sd, x, forward_oracle.cellvit_forward(sd, x, arch, retrieve_tokens=True)
+
+
+@pytest.mark.parametrize("arch,size,B", [("ViT256", 256, 2), ("SAM-B", 256, 1), ("SAM-H", 256, 1), ("ViT256", 512, 1)])
+def test_forward_matches_oracle(arch, size, B):
+    from cellvit_b200.cellvit import CellViT256, CellViTSAM
+    sd, x, ref = _oracle(arch, size, B)
+    m = CellViT256(None, 6, 19) if arch == "ViT256" else CellViTSAM(None, 6, 19, arch)
+    m.load_state_dict(sd, strict=True)
+    m = m.cuda().eval()
+    with torch.no_grad():
+        out = m(x.cuda(), retrieve_tokens=True)
+    torch.cuda.synchronize()
+    errs = {k: (out[k].cpu() - ref[k]).abs().max().item() for k in ref}
+    print(arch, size, errs)
+    for k in ("nuclei_binary_map", "hv_map", "nuclei_type_map"):
+        assert out[k].shape == ref[k].shape and out[k].dtype == torch.float32
+        assert errs[k] <= TOL, errs
+    assert errs["tissue_types"] <= 5e-3, errs
+    assert errs["tokens"] <= 2e-2 * max(1.0, ref["tokens"].abs().max().item()), errs
