@@ -254,6 +254,7 @@ int launch_flash(const __half* qkv, int Gb, int S, int heads, float scale, const
     }
     dim3 grid(cdiv(S, FA_BQ), Gb * heads);
     flash_kernel<HD><<<grid, FA_THREADS, smem, stream>>>(qkv, S, heads, scale, rel_h, rel_w, gh, gw, out);
+    cvb_note_launches(1);
     CVB_CUDA(cudaGetLastError());
     return CVB_OK;
 }
@@ -275,6 +276,7 @@ int op_relpos(const __half* qkv, int Gb, int heads, int hd, int gh, int gw, cons
     CVB_CHECK(smem <= 200 * 1024, CVB_ESHAPE, "relpos: shared memory %zu too large", smem);
     dim3 grid(gh / rows_per_cta, Gb * heads);
     relpos_kernel<<<grid, RP_THREADS, smem, stream>>>(qkv, heads, hd, gh, gw, rows_per_cta, Rh, Rw, rel_h, rel_w);
+    cvb_note_launches(1);
     CVB_CUDA(cudaGetLastError());
     return CVB_OK;
 }

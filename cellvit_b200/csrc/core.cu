@@ -22,7 +22,16 @@ int cvb_num_sms() {
     return sms;
 }
 
+static long long g_launches = 0;
+void cvb_note_launches(int n) { g_launches += n; }
+
 extern "C" {
+// Number of kernels this library has launched since the last reset (bench.py reports it as gpu_launches).
+__attribute__((visibility("default"))) long long cvb_launch_count(int reset) {
+    const long long v = g_launches;
+    if (reset) g_launches = 0;
+    return v;
+}
 __attribute__((visibility("default"))) int cvb_version(void) { return 100; }
 __attribute__((visibility("default"))) const char* cvb_last_error(void) { return g_err; }
 }

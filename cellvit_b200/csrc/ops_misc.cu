@@ -258,6 +258,7 @@ int op_patch_im2col(const float* x, int B, int H, int W, int P, __half* out, cud
     CVB_CHECK(x && out && B > 0 && P % 8 == 0 && H % P == 0 && W % P == 0, CVB_ESHAPE, "patch_im2col: bad shape %dx%d P=%d", H, W, P);
     const long long total = (long long)B * (H / P) * (W / P) * 3 * P;
     patch_im2col_kernel<<<grid_for(total, 256), 256, 0, stream>>>(x, B, H, W, P, out);
+    cvb_note_launches(1);
     CVB_CUDA(cudaGetLastError());
     return CVB_OK;
 }
@@ -269,6 +270,7 @@ int op_layernorm_f16(const float* x, const float* gamma, const float* beta, floa
     CVB_CHECK(D % 8 == 0 && D <= LN_MAXV * 128, CVB_ESHAPE, "layernorm: D=%d must be a multiple of 8 and <= %d", D, LN_MAXV * 128);
     const int blocks = cdiv(rows_dst, 8);
     layernorm_f16_kernel<<<blocks, 256, 0, stream>>>(x, gamma, beta, eps, rows_dst, D, out, map, tok_h, tok_w, ws, g);
+    cvb_note_launches(1);
     CVB_CUDA(cudaGetLastError());
     return CVB_OK;
 }
@@ -276,6 +278,7 @@ int op_layernorm_f16(const float* x, const float* gamma, const float* beta, floa
 int op_cast_rows_f16(const float* x, int B, int T_src, int skip, int D, __half* out, cudaStream_t stream) {
     CVB_CHECK(x && out && D % 4 == 0 && T_src > skip, CVB_EARG, "cast_rows: bad arguments");
     cast_rows_f16_kernel<<<grid_for((long long)B * (T_src - skip) * (D / 4), 256), 256, 0, stream>>>(x, B, T_src, skip, D, out);
+    cvb_note_launches(1);
     CVB_CUDA(cudaGetLastError());
     return CVB_OK;
 }
@@ -284,6 +287,7 @@ int op_tokens_nchw(const float* x, int B, int T_src, int skip, int D, float* out
     CVB_CHECK(x && out && T_src > skip, CVB_EARG, "tokens_nchw: bad arguments");
     dim3 grid(cdiv(T_src - skip, 32), cdiv(D, 32), B), block(32, 8);
     tokens_nchw_kernel<<<grid, block, 0, stream>>>(x, T_src, skip, D, out);
+    cvb_note_launches(1);
     CVB_CUDA(cudaGetLastError());
     return CVB_OK;
 }
@@ -292,6 +296,7 @@ int op_stem_conv(const float* x, int B, int H, int W, const float* w, const floa
                  __half* out, int cpad, cudaStream_t stream) {
     CVB_CHECK(x && w && scale && shift && out && cpad >= 32 && cpad % 8 == 0, CVB_EARG, "stem_conv: bad arguments");
     stem_conv_kernel<<<grid_for((long long)B * H * W, 128), 128, 0, stream>>>(x, B, H, W, w, scale, shift, out, cpad);
+    cvb_note_launches(1);
     CVB_CUDA(cudaGetLastError());
     return CVB_OK;
 }
@@ -301,6 +306,7 @@ int op_ln_mean_linear(const float* y, int B, int T, int C, const float* gamma, c
     CVB_CHECK(y && gamma && beta && w && b && out, CVB_EARG, "ln_mean_linear: null operand");
     CVB_CHECK(C % 32 == 0 && C <= 256, CVB_ESHAPE, "ln_mean_linear: C=%d must be a multiple of 32 and <= 256", C);
     ln_mean_linear_kernel<<<B, 1024, 0, stream>>>(y, T, C, gamma, beta, eps, w, b, n_out, out);
+    cvb_note_launches(1);
     CVB_CUDA(cudaGetLastError());
     return CVB_OK;
 }
@@ -309,6 +315,7 @@ int op_cls_head(const float* x, int B, int T, int D, const float* gamma, const f
                 const float* w, const float* b, int n_out, float* out, cudaStream_t stream) {
     CVB_CHECK(x && gamma && beta && w && b && out && D <= 2048, CVB_EARG, "cls_head: bad arguments");
     cls_head_kernel<<<B, 256, 0, stream>>>(x, T, D, gamma, beta, eps, w, b, n_out, out);
+    cvb_note_launches(1);
     CVB_CUDA(cudaGetLastError());
     return CVB_OK;
 }

@@ -783,6 +783,7 @@ int scan_i32(const int* in, int as_flag, Dims d, int* bsum, int* out, cudaStream
     scan_reduce_kernel<<<dim3(nb, d.B), 256, 0, st>>>(in, as_flag, d.N, nb, bsum);
     scan_bsums_kernel<<<d.B, 256, 0, st>>>(nb, bsum);
     scan_apply_kernel<<<dim3(nb, d.B), 256, 0, st>>>(in, as_flag, d.N, nb, bsum, out);
+    cvb_note_launches(3);
     CVB_CUDA(cudaGetLastError());
     return CVB_OK;
 }
@@ -792,6 +793,7 @@ int ccl(const uint8_t* mask, int want, Dims d, int* L, cudaStream_t st) {
     ccl_init_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(mask, want, d, L);
     ccl_merge_kernel<<<grid1d((long long)d.B * d.N), 256, 0, st>>>(mask, want, d, L);
     ccl_compress_kernel<<<grid1d((long long)d.B * d.N), 256, 0, st>>>(d, L);
+    cvb_note_launches(3);
     CVB_CUDA(cudaGetLastError());
     return CVB_OK;
 }
@@ -872,6 +874,7 @@ int run_pipeline(const Ws& w, const float* hv, Dims d, int n_types, int object_s
         table_accum_kernel<<<g, 256, 0, st>>>(labels, have_types ? w.tmap : nullptr, d, w.cap, w.acc, w.status);
         table_finalize_kernel<<<d.B, 256, 0, st>>>(w.acc, w.cap, have_types ? n_types : 0, max_rows, table, counts);
     }
+    cvb_note_launches(17 + ((table && counts) ? 3 : 0));
     if (dbg_blb) CVB_CUDA(cudaMemcpyAsync(dbg_blb, w.blb, BN, cudaMemcpyDeviceToDevice, st));
     if (dbg_dist) CVB_CUDA(cudaMemcpyAsync(dbg_dist, w.dist, BN * 8, cudaMemcpyDeviceToDevice, st));
     if (dbg_marker) CVB_CUDA(cudaMemcpyAsync(dbg_marker, w.marker, BN * 4, cudaMemcpyDeviceToDevice, st));
@@ -915,6 +918,7 @@ CVB_API int cvb_postproc(const float* np_map, const float* hv, const float* nt_m
     const Dims d{B, H, W, H * W};
     cudaStream_t st = (cudaStream_t)stream;
     prep_float_kernel<<<grid1d((long long)B * d.N), 256, 0, st>>>(np_map, nt_map, n_types, d, w.npbin, w.tmap);
+    cvb_note_launches(1);
     return run_pipeline(w, hv, d, n_types, object_size, ksize, nt_map != nullptr, labels, table, counts, max_rows, nullptr, nullptr,
                         nullptr, st);
 }

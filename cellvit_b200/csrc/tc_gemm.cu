@@ -13,6 +13,8 @@
 // own AMP mode, cell_detection.py:314-318), accumulation fp32.
 #include <cudaTypedefs.h>
 
+#include <vector>
+
 #include "tc_gemm.h"
 
 namespace {
@@ -353,6 +355,15 @@ int check_epilogue(const TcEpilogue& e, int N, int block_n) {
     return CVB_OK;
 }
 
+// Optional per-launch timing of the tile engine (bench.py roofline leg): event pairs around every launch on the
+// launching stream; read back with cvb_tc_profile_end.
+struct TcProfile {
+    bool on = false;
+    std::vector<cudaEvent_t> ev;
+    size_t used = 0;
+    double flops = 0.0;
+} g_prof;
+
 int launch(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, TcParams& p, cudaStream_t stream) {
     const int b_stage = p.block_n * BLOCK_K * 2;
     int stages = SMEM_BUDGET / (A_STAGE_BYTES + b_stage);
@@ -373,8 +384,16 @@ int launch(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, T
     p.n_tiles_n = p.N / p.block_n;
     p.n_tiles = cdiv(p.M, BLOCK_M) * p.n_tiles_n;
     int grid = p.n_tiles < cvb_num_sms() ? p.n_tiles : cvb_num_sms();
+    const bool prof = g_prof.on && g_prof.used + 2 <= g_prof.ev.size();
+    if (prof) CVB_CUDA(cudaEventRecord(g_prof.ev[g_prof.used], stream));
     tc_kernel<<<grid, NUM_THREADS, smem, stream>>>(a0, a1, b, p);
+    if (prof) {
+        CVB_CUDA(cudaEventRecord(g_prof.ev[g_prof.used + 1], stream));
+        g_prof.used += 2;
+        g_prof.flops += 2.0 * (double)p.M * (double)p.N * (double)p.K;
+    }
     CVB_CUDA(cudaGetLastError());
+    cvb_note_launches(1);
     return CVB_OK;
 }
 
@@ -441,4 +460,33 @@ int tc_conv3x3(const __half* src0, int C0, const __half* src1, int C1, int NB, i
     p.M = NB * H * W; p.N = N; p.K = K; p.block_n = block_n; p.num_kb = K / BLOCK_K; p.conv = 1;
     p.chunks0 = C0 / 64; p.chunks_per_tap = (C0 + C1) / 64; p.H = H; p.W = W; p.TW = TW; p.epi = epi;
     return launch(t0, t1, tb, p, stream);
+}
+
+extern "C" __attribute__((visibility("default"))) int cvb_tc_profile_begin(int max_launches) {
+    CVB_CHECK(max_launches > 0, CVB_EARG, "cvb_tc_profile_begin: max_launches must be positive");
+    while (g_prof.ev.size() < (size_t)max_launches * 2) {
+        cudaEvent_t e;
+        CVB_CUDA(cudaEventCreate(&e));
+        g_prof.ev.push_back(e);
+    }
+    g_prof.used = 0;
+    g_prof.flops = 0.0;
+    g_prof.on = true;
+    return CVB_OK;
+}
+
+// Synchronises the recorded events. total_ms = sum of per-launch durations, flops = executed 2*M*N*K summed.
+extern "C" __attribute__((visibility("default"))) int cvb_tc_profile_end(double* total_ms, int* n_launches, double* flops) {
+    g_prof.on = false;
+    double ms = 0.0;
+    for (size_t i = 0; i + 1 < g_prof.used; i += 2) {
+        CVB_CUDA(cudaEventSynchronize(g_prof.ev[i + 1]));
+        float t = 0.f;
+        CVB_CUDA(cudaEventElapsedTime(&t, g_prof.ev[i], g_prof.ev[i + 1]));
+        ms += t;
+    }
+    if (total_ms) *total_ms = ms;
+    if (n_launches) *n_launches = (int)(g_prof.used / 2);
+    if (flops) *flops = g_prof.flops;
+    return CVB_OK;
 }
