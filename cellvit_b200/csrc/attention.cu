@@ -1,70 +1,37 @@
 // attention.cu -- multi-head self-attention of the ViT encoders (windowed and global, SAM and ViT-S).
 //
-//  * relpos_kernel: the decomposed relative-position terms of SAM (image_encoder.py:354-392). They depend on the
-//    UNSCALED query, so they are two small per-query tables  rel_h[q, kh], rel_w[q, kw]  computed once per block
-//    with CUDA cores (2 * (gh + gw) * hd MACs per query -- 3 % of the attention FLOPs).
-//  * flash_kernel<HD>: S = scale * q k^T + rel_h[q, k / gw] + rel_w[q, k % gw]; online softmax; O = P v.
-//    Scores never leave the SM (the reference materialises a 4.3 GB fp32 score tensor at B=4, image_encoder.py:244-251).
-//    Tensor-core path: mma.sync m16n8k16 fp16 -> fp32 with ldmatrix-fed fragments, cp.async double-buffered K/V.
-//    TODO(round 2): move QK^T / PV to tcgen05 with S and O in TMEM; attention is 6 % of the forward FLOPs.
+// flash_kernel<HD, BIAS>: S = scale * q k^T (+ rel_h[q, k / gw] + rel_w[q, k % gw]); online softmax; O = P v.
+// Scores never leave the SM (the reference materialises a 4.3 GB fp32 score tensor at B=4,
+// image_encoder.py:244-251). Tensor-core path: mma.sync m16n8k16 fp16 -> fp32 with ldmatrix-fed fragments and
+// cp.async double-buffered K/V tiles.
+//
+// Decomposed relative position (image_encoder.py:354-392): rel_h[q, kh] = q . Rh[qh - kh + gh - 1] with the
+// UNSCALED q. The kernel computes G = Q Rh^T for all 2*gh-1 table rows with the same MMA path as Q K^T (the table
+// is just another K-major operand tile) and scatters G[q, j] to rel_h[q, kh = qh + gh - 1 - j] in shared memory;
+// same for rel_w. No separate rel-pos kernel, no HBM round trip of the bias tables.
+//
+// TODO(round 2): move QK^T / PV to tcgen05 with S and O in TMEM; attention is 5 % of the forward FLOPs.
 #include "ops.h"
 
 namespace {
 
-constexpr int RP_THREADS = 128;
-constexpr int RP_MAXQ = 256;
-
-__global__ void __launch_bounds__(RP_THREADS)
-relpos_kernel(const __half* __restrict__ qkv, int heads, int hd, int gh, int gw, int rows_per_cta,
-              const float* __restrict__ Rh, const float* __restrict__ Rw, float* __restrict__ rel_h, float* __restrict__ rel_w) {
-    extern __shared__ float rp_smem[];
-    const int ld = hd + 1;
-    float* q_s = rp_smem;                               // [nq][ld]
-    const int nq = rows_per_cta * gw;
-    float* th_s = q_s + nq * ld;                        // [2gh-1][ld]
-    float* tw_s = th_s + (2 * gh - 1) * ld;             // [2gw-1][ld]
-    const int g = blockIdx.y, bp = g / heads, head = g - bp * heads;
-    const int S = gh * gw, D3 = 3 * heads * hd;
-    const int qh0 = blockIdx.x * rows_per_cta;
-    const int t0 = qh0 * gw;
-    for (int i = threadIdx.x; i < nq * hd; i += RP_THREADS) {
-        const int ql = i / hd, c = i - ql * hd;
-        q_s[ql * ld + c] = __half2float(qkv[((long long)bp * S + t0 + ql) * D3 + head * hd + c]);
-    }
-    for (int i = threadIdx.x; i < (2 * gh - 1) * hd; i += RP_THREADS) th_s[(i / hd) * ld + i % hd] = Rh[i];
-    for (int i = threadIdx.x; i < (2 * gw - 1) * hd; i += RP_THREADS) tw_s[(i / hd) * ld + i % hd] = Rw[i];
-    __syncthreads();
-    const int per_q = gh + gw;
-    for (int o = threadIdx.x; o < nq * per_q; o += RP_THREADS) {
-        const int ql = o / per_q, k = o - ql * per_q;
-        const int qh = qh0 + ql / gw, qw = ql % gw;
-        const float* qv = q_s + ql * ld;
-        const float* tv = k < gh ? th_s + (qh - k + gh - 1) * ld : tw_s + (qw - (k - gh) + gw - 1) * ld;
-        float acc = 0.f;
-        for (int c = 0; c < hd; ++c) acc = fmaf(qv[c], tv[c], acc);
-        const long long row = (long long)g * S + t0 + ql;
-        if (k < gh) rel_h[row * gh + k] = acc;
-        else rel_w[row * gw + (k - gh)] = acc;
-    }
-}
-
-// ------------------------------------------------------------------------------------------ flash attention
 constexpr int FA_BQ = 64, FA_BK = 64, FA_THREADS = 128;
+constexpr int REL_LD = 65;  // row stride of the bias tables: rows land in different banks
 
-template <int HD>
+template <int HD, bool BIAS>
 struct FaSmem {
     static constexpr int LD = HD + 8;  // halves per smem row: (HD+8)*2 B is an odd multiple of 16 B -> conflict-free ldmatrix
     __half q[FA_BQ * LD];
     __half k[2][FA_BK * LD];
     __half v[2][FA_BK * LD];
-    float rel_h[FA_BQ * 64];
-    float rel_w[FA_BQ * 64];
+    float rel_h[BIAS ? FA_BQ * REL_LD : 1];
+    float rel_w[BIAS ? FA_BQ * REL_LD : 1];
 };
 
 template <int HD>
 __device__ __forceinline__ void fa_load_tile(__half* dst, const __half* src_base, long long row_stride, int row0, int n_rows,
                                              int tid) {
-    constexpr int LD = FaSmem<HD>::LD;
+    constexpr int LD = HD + 8;
     constexpr int CH = HD / 8;  // 16-byte chunks per row
     for (int i = tid; i < FA_BK * CH; i += FA_THREADS) {
         const int r = i / CH, c = i - r * CH;
@@ -75,13 +42,37 @@ __device__ __forceinline__ void fa_load_tile(__half* dst, const __half* src_base
     }
 }
 
+// s_acc[16 x 64 per warp] = Q_frag (16 x HD) * tile^T, tile = [64 rows][HD] K-major in shared memory
 template <int HD>
+__device__ __forceinline__ void fa_qk(const __half* tile, const uint32_t (&q_frag)[HD / 16][4], float (&s_acc)[8][4], int lane,
+                                      int n_pairs) {
+    constexpr int LD = HD + 8;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { s_acc[i][0] = s_acc[i][1] = s_acc[i][2] = s_acc[i][3] = 0.f; }
+#pragma unroll
+    for (int ks = 0; ks < HD / 16; ++ks) {
+#pragma unroll
+        for (int np = 0; np < 4; ++np) {  // pairs of 8-row n-tiles
+            if (np < n_pairs) {
+                uint32_t b0, b1, b2, b3;
+                const int row = np * 16 + (lane & 7) + ((lane >> 4) << 3);
+                const int col = ks * 16 + ((lane >> 3) & 1) * 8;
+                ptx::ldmatrix_x4(ptx::smem_u32(tile + row * LD + col), b0, b1, b2, b3);
+                ptx::mma_16816(s_acc[2 * np], q_frag[ks], b0, b1);
+                ptx::mma_16816(s_acc[2 * np + 1], q_frag[ks], b2, b3);
+            }
+        }
+    }
+}
+
+template <int HD, bool BIAS>
 __global__ void __launch_bounds__(FA_THREADS)
-flash_kernel(const __half* __restrict__ qkv, int S, int heads, float scale, const float* __restrict__ rel_h,
-             const float* __restrict__ rel_w, int gh, int gw, __half* __restrict__ out) {
+flash_kernel(const __half* __restrict__ qkv, int S, int heads, float scale, const __half* __restrict__ Rh,
+             const __half* __restrict__ Rw, int gh, int gw, __half* __restrict__ out) {
     extern __shared__ __align__(16) uint8_t fa_smem_raw[];
-    FaSmem<HD>& sm = *reinterpret_cast<FaSmem<HD>*>(fa_smem_raw);
-    constexpr int LD = FaSmem<HD>::LD;
+    using Smem = FaSmem<HD, BIAS>;
+    Smem& sm = *reinterpret_cast<Smem*>(fa_smem_raw);
+    constexpr int LD = Smem::LD;
     constexpr int KSTEPS = HD / 16;   // k-steps of QK^T
     constexpr int NT_O = HD / 8;      // n-tiles of O
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -92,34 +83,101 @@ flash_kernel(const __half* __restrict__ qkv, int S, int heads, float scale, cons
     const __half* q_base = qkv + (long long)bp * S * row_stride + head * HD;
     const __half* k_base = q_base + D;
     const __half* v_base = q_base + 2 * D;
-    const bool has_bias = rel_h != nullptr;
     const int n_kt = (S + FA_BK - 1) / FA_BK;
+    const bool warp_active = q0 + warp * 16 < S;  // tail q-tiles: idle warps only help loading
+    const int r_lo = warp * 16 + (lane >> 2);     // local query row of c0/c1; c2/c3 are r_lo + 8
 
     fa_load_tile<HD>(sm.q, q_base, row_stride, q0, S, tid);
+    ptx::cp_async_commit();
     fa_load_tile<HD>(sm.k[0], k_base, row_stride, 0, S, tid);
     fa_load_tile<HD>(sm.v[0], v_base, row_stride, 0, S, tid);
     ptx::cp_async_commit();
-    if (has_bias) {
-        for (int i = tid; i < FA_BQ * gh; i += FA_THREADS) {
-            const int ql = i / gh, kk = i - ql * gh;
-            const int qrow = min(q0 + ql, S - 1);
-            sm.rel_h[ql * 64 + kk] = rel_h[((long long)g * S + qrow) * gh + kk];
+
+    uint32_t q_frag[KSTEPS][4];
+    float s_acc[8][4];
+
+    if (BIAS) {
+        // ---- rel-pos tables through the MMA path; table tiles double-buffer through k[1] / v[1]
+        const int Lh = 2 * gh - 1, Lw = 2 * gw - 1;
+        const int ph = (Lh + 63) / 64, pw = (Lw + 63) / 64;
+        const int n_pass = ph + pw;
+        auto issue = [&](int pass) {
+            const bool is_h = pass < ph;
+            const int p = is_h ? pass : pass - ph;
+            fa_load_tile<HD>((pass & 1) ? sm.v[1] : sm.k[1], is_h ? Rh : Rw, HD, p * 64, is_h ? Lh : Lw, tid);
+            ptx::cp_async_commit();
+        };
+        issue(0);
+        for (int pass = 0; pass < n_pass; ++pass) {
+            if (pass + 1 < n_pass) { issue(pass + 1); ptx::cp_async_wait<1>(); }
+            else ptx::cp_async_wait<0>();
+            __syncthreads();
+            if (pass == 0) {
+#pragma unroll
+                for (int ks = 0; ks < KSTEPS; ++ks) {
+                    const int row = warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+                    const int col = ks * 16 + (lane >> 4) * 8;
+                    ptx::ldmatrix_x4(ptx::smem_u32(sm.q + row * LD + col), q_frag[ks][0], q_frag[ks][1], q_frag[ks][2], q_frag[ks][3]);
+                }
+            }
+            const bool is_h = pass < ph;
+            const int p = is_h ? pass : pass - ph;
+            const int L = is_h ? Lh : Lw, gdim = is_h ? gh : gw;
+            const int rows_here = min(64, L - p * 64);
+            if (warp_active) {
+                fa_qk<HD>((pass & 1) ? sm.v[1] : sm.k[1], q_frag, s_acc, lane, (rows_here + 15) >> 4);
+                float* dst = is_h ? sm.rel_h : sm.rel_w;
+#pragma unroll
+                for (int hrow = 0; hrow < 2; ++hrow) {
+                    const int row = r_lo + 8 * hrow;
+                    const int t = q0 + row;
+                    if (t < S) {
+                        const int qh = t / gw;
+                        const int qpos = is_h ? qh : t - qh * gw;
+#pragma unroll
+                        for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+                            for (int e = 0; e < 2; ++e) {
+                                const int j = p * 64 + nt * 8 + 2 * (lane & 3) + e;
+                                const int kk = qpos + gdim - 1 - j;
+                                if (kk >= 0 && kk < gdim && j < L) dst[row * REL_LD + kk] = s_acc[nt][2 * hrow + e];
+                            }
+                    }
+                }
+            }
+            __syncthreads();
         }
-        for (int i = tid; i < FA_BQ * gw; i += FA_THREADS) {
-            const int ql = i / gw, kk = i - ql * gw;
-            const int qrow = min(q0 + ql, S - 1);
-            sm.rel_w[ql * 64 + kk] = rel_w[((long long)g * S + qrow) * gw + kk];
+    } else {
+        ptx::cp_async_wait<0>();
+        __syncthreads();
+#pragma unroll
+        for (int ks = 0; ks < KSTEPS; ++ks) {
+            const int row = warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+            const int col = ks * 16 + (lane >> 4) * 8;
+            ptx::ldmatrix_x4(ptx::smem_u32(sm.q + row * LD + col), q_frag[ks][0], q_frag[ks][1], q_frag[ks][2], q_frag[ks][3]);
         }
     }
+
+    constexpr float L2E = 1.4426950408889634f;
+    const float sl2 = scale * L2E;
+    const bool fast_bias = BIAS && gw == FA_BK;  // one key tile == one key row: rel_h is a per-row scalar, rel_w loop-invariant
+    float rw[BIAS ? 32 : 1];
+    if (BIAS && fast_bias && warp_active) {
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int c = nt * 8 + 2 * (lane & 3) + e;
+                rw[nt * 4 + e] = sm.rel_w[r_lo * REL_LD + c] * L2E;
+                rw[nt * 4 + 2 + e] = sm.rel_w[(r_lo + 8) * REL_LD + c] * L2E;
+            }
+    }
+    const float inv_gw = 1.0f / (float)gw;
 
     float o_acc[NT_O][4];
 #pragma unroll
     for (int i = 0; i < NT_O; ++i) { o_acc[i][0] = o_acc[i][1] = o_acc[i][2] = o_acc[i][3] = 0.f; }
     float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
-    uint32_t q_frag[KSTEPS][4];
-    const int r_lo = warp * 16 + (lane >> 2);  // local query row of c0/c1; c2/c3 are r_lo + 8
-    const float sl2 = scale * 1.4426950408889634f;
-    constexpr float L2E = 1.4426950408889634f;
 
     for (int kt = 0; kt < n_kt; ++kt) {
         const int buf = kt & 1;
@@ -132,100 +190,88 @@ flash_kernel(const __half* __restrict__ qkv, int S, int heads, float scale, cons
             ptx::cp_async_wait<0>();
         }
         __syncthreads();
-        if (kt == 0) {
+        if (warp_active) {
+            fa_qk<HD>(sm.k[buf], q_frag, s_acc, lane, 4);
+            // ---- scale, bias, mask (log2 domain)
+            const int kbase = kt * FA_BK;
+            if (BIAS && fast_bias) {
+                const float bh0 = sm.rel_h[r_lo * REL_LD + kt] * L2E, bh1 = sm.rel_h[(r_lo + 8) * REL_LD + kt] * L2E;
 #pragma unroll
-            for (int ks = 0; ks < KSTEPS; ++ks) {
-                const int row = warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
-                const int col = ks * 16 + (lane >> 4) * 8;
-                ptx::ldmatrix_x4(ptx::smem_u32(sm.q + row * LD + col), q_frag[ks][0], q_frag[ks][1], q_frag[ks][2], q_frag[ks][3]);
-            }
-        }
-        // ---- S = Q K^T (16 x 64 per warp)
-        float s_acc[8][4];
+                for (int nt = 0; nt < 8; ++nt)
 #pragma unroll
-        for (int i = 0; i < 8; ++i) { s_acc[i][0] = s_acc[i][1] = s_acc[i][2] = s_acc[i][3] = 0.f; }
-#pragma unroll
-        for (int ks = 0; ks < KSTEPS; ++ks) {
-#pragma unroll
-            for (int np = 0; np < 4; ++np) {  // pairs of 8-key n-tiles
-                uint32_t b0, b1, b2, b3;
-                const int row = np * 16 + (lane & 7) + ((lane >> 4) << 3);
-                const int col = ks * 16 + ((lane >> 3) & 1) * 8;
-                ptx::ldmatrix_x4(ptx::smem_u32(sm.k[buf] + row * LD + col), b0, b1, b2, b3);
-                ptx::mma_16816(s_acc[2 * np], q_frag[ks], b0, b1);
-                ptx::mma_16816(s_acc[2 * np + 1], q_frag[ks], b2, b3);
-            }
-        }
-        // ---- scale, bias, mask (log2 domain)
-        const int kbase = kt * FA_BK;
-#pragma unroll
-        for (int nt = 0; nt < 8; ++nt) {
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                const int kcol = kbase + nt * 8 + 2 * (lane & 3) + e;
-                float b_lo = 0.f, b_hi = 0.f;
-                if (has_bias) {
-                    const int kh = kcol / gw, kw = kcol - kh * gw;
-                    if (kcol < S) {
-                        b_lo = sm.rel_h[r_lo * 64 + kh] + sm.rel_w[r_lo * 64 + kw];
-                        b_hi = sm.rel_h[(r_lo + 8) * 64 + kh] + sm.rel_w[(r_lo + 8) * 64 + kw];
+                    for (int e = 0; e < 2; ++e) {
+                        s_acc[nt][e] = fmaf(s_acc[nt][e], sl2, bh0 + rw[nt * 4 + e]);
+                        s_acc[nt][2 + e] = fmaf(s_acc[nt][2 + e], sl2, bh1 + rw[nt * 4 + 2 + e]);
                     }
-                }
-                const bool valid = kcol < S;
-                s_acc[nt][e] = valid ? fmaf(s_acc[nt][e], sl2, b_lo * L2E) : -INFINITY;
-                s_acc[nt][2 + e] = valid ? fmaf(s_acc[nt][2 + e], sl2, b_hi * L2E) : -INFINITY;
+            } else {
+#pragma unroll
+                for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int kcol = kbase + nt * 8 + 2 * (lane & 3) + e;
+                        const bool valid = kcol < S;
+                        float b_lo = 0.f, b_hi = 0.f;
+                        if (BIAS && valid) {
+                            const int kh = (int)(((float)kcol + 0.5f) * inv_gw), kw = kcol - kh * gw;
+                            b_lo = (sm.rel_h[r_lo * REL_LD + kh] + sm.rel_w[r_lo * REL_LD + kw]) * L2E;
+                            b_hi = (sm.rel_h[(r_lo + 8) * REL_LD + kh] + sm.rel_w[(r_lo + 8) * REL_LD + kw]) * L2E;
+                        }
+                        s_acc[nt][e] = valid ? fmaf(s_acc[nt][e], sl2, b_lo) : -INFINITY;
+                        s_acc[nt][2 + e] = valid ? fmaf(s_acc[nt][2 + e], sl2, b_hi) : -INFINITY;
+                    }
             }
-        }
-        // ---- online softmax
-        float mx[2] = {m_run[0], m_run[1]};
+            // ---- online softmax
+            float mx[2] = {m_run[0], m_run[1]};
 #pragma unroll
-        for (int nt = 0; nt < 8; ++nt) {
-            mx[0] = fmaxf(mx[0], fmaxf(s_acc[nt][0], s_acc[nt][1]));
-            mx[1] = fmaxf(mx[1], fmaxf(s_acc[nt][2], s_acc[nt][3]));
-        }
+            for (int nt = 0; nt < 8; ++nt) {
+                mx[0] = fmaxf(mx[0], fmaxf(s_acc[nt][0], s_acc[nt][1]));
+                mx[1] = fmaxf(mx[1], fmaxf(s_acc[nt][2], s_acc[nt][3]));
+            }
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            mx[h] = fmaxf(mx[h], __shfl_xor_sync(0xffffffffu, mx[h], 1));
-            mx[h] = fmaxf(mx[h], __shfl_xor_sync(0xffffffffu, mx[h], 2));
-        }
-        float alpha[2], rs[2] = {0.f, 0.f};
+            for (int h = 0; h < 2; ++h) {
+                mx[h] = fmaxf(mx[h], __shfl_xor_sync(0xffffffffu, mx[h], 1));
+                mx[h] = fmaxf(mx[h], __shfl_xor_sync(0xffffffffu, mx[h], 2));
+            }
+            float alpha[2], rs[2] = {0.f, 0.f};
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            alpha[h] = exp2f(m_run[h] - mx[h]);
-            m_run[h] = mx[h];
-        }
-        uint32_t p_frag[4][4];
+            for (int h = 0; h < 2; ++h) {
+                alpha[h] = exp2f(m_run[h] - mx[h]);
+                m_run[h] = mx[h];
+            }
+            uint32_t p_frag[4][4];
 #pragma unroll
-        for (int nt = 0; nt < 8; ++nt) {
-            const float p0 = exp2f(s_acc[nt][0] - mx[0]), p1 = exp2f(s_acc[nt][1] - mx[0]);
-            const float p2 = exp2f(s_acc[nt][2] - mx[1]), p3 = exp2f(s_acc[nt][3] - mx[1]);
-            rs[0] += p0 + p1;
-            rs[1] += p2 + p3;
-            p_frag[nt >> 1][(nt & 1) * 2 + 0] = pack_h2(p0, p1);
-            p_frag[nt >> 1][(nt & 1) * 2 + 1] = pack_h2(p2, p3);
-        }
+            for (int nt = 0; nt < 8; ++nt) {
+                const float p0 = exp2f(s_acc[nt][0] - mx[0]), p1 = exp2f(s_acc[nt][1] - mx[0]);
+                const float p2 = exp2f(s_acc[nt][2] - mx[1]), p3 = exp2f(s_acc[nt][3] - mx[1]);
+                rs[0] += p0 + p1;
+                rs[1] += p2 + p3;
+                p_frag[nt >> 1][(nt & 1) * 2 + 0] = pack_h2(p0, p1);
+                p_frag[nt >> 1][(nt & 1) * 2 + 1] = pack_h2(p2, p3);
+            }
 #pragma unroll
-        for (int h = 0; h < 2; ++h) l_run[h] = l_run[h] * alpha[h] + rs[h];
+            for (int h = 0; h < 2; ++h) l_run[h] = l_run[h] * alpha[h] + rs[h];
 #pragma unroll
-        for (int i = 0; i < NT_O; ++i) {
-            o_acc[i][0] *= alpha[0]; o_acc[i][1] *= alpha[0];
-            o_acc[i][2] *= alpha[1]; o_acc[i][3] *= alpha[1];
-        }
-        // ---- O += P V
+            for (int i = 0; i < NT_O; ++i) {
+                o_acc[i][0] *= alpha[0]; o_acc[i][1] *= alpha[0];
+                o_acc[i][2] *= alpha[1]; o_acc[i][3] *= alpha[1];
+            }
+            // ---- O += P V
 #pragma unroll
-        for (int kk = 0; kk < 4; ++kk) {  // 16 keys per step
+            for (int kk = 0; kk < 4; ++kk) {  // 16 keys per step
 #pragma unroll
-            for (int dp = 0; dp < NT_O / 2; ++dp) {
-                uint32_t b0, b1, b2, b3;
-                const int row = kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
-                const int col = dp * 16 + (lane >> 4) * 8;
-                ptx::ldmatrix_x4_trans(ptx::smem_u32(sm.v[buf] + row * LD + col), b0, b1, b2, b3);
-                ptx::mma_16816(o_acc[2 * dp], p_frag[kk], b0, b1);
-                ptx::mma_16816(o_acc[2 * dp + 1], p_frag[kk], b2, b3);
+                for (int dp = 0; dp < NT_O / 2; ++dp) {
+                    uint32_t b0, b1, b2, b3;
+                    const int row = kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+                    const int col = dp * 16 + (lane >> 4) * 8;
+                    ptx::ldmatrix_x4_trans(ptx::smem_u32(sm.v[buf] + row * LD + col), b0, b1, b2, b3);
+                    ptx::mma_16816(o_acc[2 * dp], p_frag[kk], b0, b1);
+                    ptx::mma_16816(o_acc[2 * dp + 1], p_frag[kk], b2, b3);
+                }
             }
         }
         __syncthreads();
     }
+    if (!warp_active) return;
     // ---- finalize
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
@@ -243,17 +289,17 @@ flash_kernel(const __half* __restrict__ qkv, int S, int heads, float scale, cons
     }
 }
 
-template <int HD>
-int launch_flash(const __half* qkv, int Gb, int S, int heads, float scale, const float* rel_h, const float* rel_w,
+template <int HD, bool BIAS>
+int launch_flash(const __half* qkv, int Gb, int S, int heads, float scale, const __half* Rh, const __half* Rw,
                  int gh, int gw, __half* out, cudaStream_t stream) {
     static bool configured = false;
-    const int smem = (int)sizeof(FaSmem<HD>);
+    const int smem = (int)sizeof(FaSmem<HD, BIAS>);
     if (!configured) {
-        CVB_CUDA(cudaFuncSetAttribute(flash_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        CVB_CUDA(cudaFuncSetAttribute(flash_kernel<HD, BIAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         configured = true;
     }
     dim3 grid(cdiv(S, FA_BQ), Gb * heads);
-    flash_kernel<HD><<<grid, FA_THREADS, smem, stream>>>(qkv, S, heads, scale, rel_h, rel_w, gh, gw, out);
+    flash_kernel<HD, BIAS><<<grid, FA_THREADS, smem, stream>>>(qkv, S, heads, scale, Rh, Rw, gh, gw, out);
     cvb_note_launches(1);
     CVB_CUDA(cudaGetLastError());
     return CVB_OK;
@@ -261,34 +307,16 @@ int launch_flash(const __half* qkv, int Gb, int S, int heads, float scale, const
 
 }  // namespace
 
-int op_relpos(const __half* qkv, int Gb, int heads, int hd, int gh, int gw, const float* Rh, const float* Rw,
-              float* rel_h, float* rel_w, cudaStream_t stream) {
-    CVB_CHECK(qkv && Rh && Rw && rel_h && rel_w, CVB_EARG, "relpos: null operand");
-    CVB_CHECK(gh <= 64 && gw <= 64, CVB_ESHAPE, "relpos: token grid %dx%d exceeds 64x64", gh, gw);
-    const int rows_per_cta = gw >= 32 ? 1 : (gh * gw <= RP_MAXQ ? gh : 1);
-    const int nq = rows_per_cta * gw;
-    const size_t smem = (size_t)(nq + 2 * gh - 1 + 2 * gw - 1) * (hd + 1) * sizeof(float);
-    static size_t configured = 0;
-    if (smem > configured) {
-        CVB_CUDA(cudaFuncSetAttribute(relpos_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        configured = 200 * 1024;
-    }
-    CVB_CHECK(smem <= 200 * 1024, CVB_ESHAPE, "relpos: shared memory %zu too large", smem);
-    dim3 grid(gh / rows_per_cta, Gb * heads);
-    relpos_kernel<<<grid, RP_THREADS, smem, stream>>>(qkv, heads, hd, gh, gw, rows_per_cta, Rh, Rw, rel_h, rel_w);
-    cvb_note_launches(1);
-    CVB_CUDA(cudaGetLastError());
-    return CVB_OK;
-}
-
-int op_attention(const __half* qkv, int Gb, int S, int heads, int hd, float scale, const float* rel_h,
-                 const float* rel_w, int gh, int gw, __half* out, cudaStream_t stream) {
+int op_attention(const __half* qkv, int Gb, int S, int heads, int hd, float scale, const __half* Rh, const __half* Rw,
+                 int gh, int gw, __half* out, cudaStream_t stream) {
     CVB_CHECK(qkv && out && Gb > 0 && S > 0, CVB_EARG, "attention: null operand or empty shape");
-    CVB_CHECK((rel_h == nullptr) == (rel_w == nullptr), CVB_EARG, "attention: rel_h and rel_w must both be set or both null");
-    if (rel_h) CVB_CHECK(gh * gw == S && gh <= 64 && gw <= 64, CVB_ESHAPE, "attention: bias grid %dx%d does not match S=%d", gh, gw, S);
-    if (!rel_h) { gh = 1; gw = S; }
-    if (hd == 80) return launch_flash<80>(qkv, Gb, S, heads, scale, rel_h, rel_w, gh, gw, out, stream);
-    if (hd == 64) return launch_flash<64>(qkv, Gb, S, heads, scale, rel_h, rel_w, gh, gw, out, stream);
+    CVB_CHECK((Rh == nullptr) == (Rw == nullptr), CVB_EARG, "attention: Rh and Rw must both be set or both null");
+    if (Rh) CVB_CHECK(gh * gw == S && gh <= 64 && gw <= 64, CVB_ESHAPE, "attention: bias grid %dx%d does not match S=%d", gh, gw, S);
+    if (!Rh) { gh = 1; gw = S; }
+    if (hd == 80) return Rh ? launch_flash<80, true>(qkv, Gb, S, heads, scale, Rh, Rw, gh, gw, out, stream)
+                            : launch_flash<80, false>(qkv, Gb, S, heads, scale, Rh, Rw, gh, gw, out, stream);
+    if (hd == 64) return Rh ? launch_flash<64, true>(qkv, Gb, S, heads, scale, Rh, Rw, gh, gw, out, stream)
+                            : launch_flash<64, false>(qkv, Gb, S, heads, scale, Rh, Rw, gh, gw, out, stream);
     cvb_set_error("attention: head dim %d not supported (64 or 80)", hd);
     return CVB_ESHAPE;
 }

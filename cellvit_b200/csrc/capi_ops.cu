@@ -25,14 +25,10 @@ CVB_API int cvb_op_layernorm_f16(const float* x, const float* gamma, const float
     return op_layernorm_f16(x, gamma, beta, eps, rows_dst, D, (__half*)out, map, B, tok_h, tok_w, ws, g, (cudaStream_t)stream);
 }
 
-CVB_API int cvb_op_relpos(const void* qkv, int Gb, int heads, int hd, int gh, int gw, const float* Rh, const float* Rw,
-                          float* rel_h, float* rel_w, void* stream) {
-    return op_relpos((const __half*)qkv, Gb, heads, hd, gh, gw, Rh, Rw, rel_h, rel_w, (cudaStream_t)stream);
-}
-
-CVB_API int cvb_op_attention(const void* qkv, int Gb, int S, int heads, int hd, float scale, const float* rel_h,
-                             const float* rel_w, int gh, int gw, void* out, void* stream) {
-    return op_attention((const __half*)qkv, Gb, S, heads, hd, scale, rel_h, rel_w, gh, gw, (__half*)out, (cudaStream_t)stream);
+CVB_API int cvb_op_attention(const void* qkv, int Gb, int S, int heads, int hd, float scale, const void* Rh,
+                             const void* Rw, int gh, int gw, void* out, void* stream) {
+    return op_attention((const __half*)qkv, Gb, S, heads, hd, scale, (const __half*)Rh, (const __half*)Rw, gh, gw, (__half*)out,
+                        (cudaStream_t)stream);
 }
 
 CVB_API int cvb_op_patch_im2col(const float* x, int B, int H, int W, int P, void* out, void* stream) {

@@ -134,13 +134,6 @@ int forward_impl(cvb_model& m, const float* x, int B, int H, int W, float* o_np,
     __half* qkv = A.alloc<__half>(rows_max * 3 * D);
     __half* att = A.alloc<__half>(rows_max * D);
     __half* hid = A.alloc<__half>((size_t)B * Tx * 4 * D);
-    float *relh = nullptr, *relw = nullptr;
-    if (sam) {
-        size_t n_g = (size_t)B * heads * T * (h > w ? h : w);
-        size_t n_w = (size_t)B * g * g * heads * ws * ws * ws;
-        relh = A.alloc<float>(n_g > n_w ? n_g : n_w);
-        relw = A.alloc<float>(n_g > n_w ? n_g : n_w);
-    }
     __half* z[4];
     for (int k = 0; k < 4; ++k) z[k] = A.alloc<__half>((size_t)B * T * D);
 
@@ -159,12 +152,9 @@ int forward_impl(cvb_model& m, const float* x, int B, int H, int W, float* o_np,
             f.gemm(ln, rows, D, p + ".qkv.w", 3 * D, e);
         }
         const int Gb = win ? B * g * g : B, S = win ? ws * ws : Tx, gh = win ? ws : h, gw = win ? ws : w;
-        if (sam) {
-            const float* th = f.P<float>(p + ".relh");
-            const float* tw = f.P<float>(p + ".relw");
-            if (f.live()) f.chk(op_relpos(qkv, Gb, heads, hd, gh, gw, th, tw, relh, relw, st));
-        }
-        if (f.live()) f.chk(op_attention(qkv, Gb, S, heads, hd, scale, sam ? relh : nullptr, sam ? relw : nullptr, gh, gw, att, st));
+        const __half* th = sam ? f.P<__half>(p + ".relh") : nullptr;
+        const __half* tw = sam ? f.P<__half>(p + ".relw") : nullptr;
+        if (f.live()) f.chk(op_attention(qkv, Gb, S, heads, hd, scale, th, tw, gh, gw, att, st));
         {
             TcEpilogue e = Fwd::epi0();
             e.kind = TC_EPI_RES_F32; e.out = xs; e.ldc = D; e.res = xs; e.ldres = D; e.shift = f.P<float>(p + ".proj.b");

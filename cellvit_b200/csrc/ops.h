@@ -36,14 +36,9 @@ int op_cls_head(const float* x, int B, int T, int D, const float* gamma, const f
                 const float* w, const float* b, int n_out, float* out, cudaStream_t stream);
 
 // --- attention.cu -----------------------------------------------------------------------------------
-// Decomposed relative-position terms (image_encoder.py:354-392), computed from the UNSCALED q:
-//   rel_h[g, q, kh] = q . Rh[qh - kh + gh - 1],  rel_w[g, q, kw] = q . Rw[qw - kw + gw - 1]
-// qkv fp16 [G_b * S, 3*D] (q | k | v, head-major inside each), tables fp32 [2*gh-1, hd] / [2*gw-1, hd].
-// rel_h / rel_w fp32 [G_b*heads, S, gh] / [.., S, gw] with S = gh*gw.
-int op_relpos(const __half* qkv, int Gb, int heads, int hd, int gh, int gw, const float* Rh, const float* Rw,
-              float* rel_h, float* rel_w, cudaStream_t stream);
-
 // softmax(scale * q k^T + bias) v per (group, head); groups are windows or whole images.
-// out fp16 [Gb*S, D] with head h at columns [h*hd, (h+1)*hd). rel_h/rel_w may be null (no bias).
-int op_attention(const __half* qkv, int Gb, int S, int heads, int hd, float scale, const float* rel_h,
-                 const float* rel_w, int gh, int gw, __half* out, cudaStream_t stream);
+// qkv fp16 [Gb*S, 3*D] (q | k | v, head-major inside each); out fp16 [Gb*S, D], head h at columns [h*hd, (h+1)*hd).
+// Decomposed relative position (image_encoder.py:354-392): Rh / Rw fp16 tables [2*gh-1, hd] / [2*gw-1, hd]
+// (row = q - k + g - 1), applied to the UNSCALED q inside the kernel; both null = no bias (ViT-S).
+int op_attention(const __half* qkv, int Gb, int S, int heads, int hd, float scale, const __half* Rh, const __half* Rw,
+                 int gh, int gw, __half* out, cudaStream_t stream);

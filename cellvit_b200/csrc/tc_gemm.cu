@@ -7,8 +7,8 @@
 //     is one 4-D TMA box shifted by (dx-1, dy-1); out-of-image pixels are zero-filled by the TMA unit, so
 //     there is no im2col buffer. torch.cat([skip, x], 1) is a K-split over two tensor maps.
 //
-// CTA = 8 warps: w0 TMA producer (1 lane), w1 MMA issuer (1 lane), w2 TMEM allocator, w4..7 epilogue
-// (TMEM lane quadrant = warp & 3). Tile = 128 x block_n fp32 accumulator in TMEM, double buffered so the
+// CTA = 12 warps: w0 TMA producer (1 lane), w1 MMA issuer (1 lane), w2 TMEM allocator, w4..11 epilogue
+// (TMEM lane quadrant = warp & 3; the two warps of a quadrant take alternating 32-column chunks). Tile = 128 x block_n fp32 accumulator in TMEM, double buffered so the
 // epilogue of tile i overlaps the main loop of tile i+1. Operands are fp16 (11-bit mantissa: the reference's
 // own AMP mode, cell_detection.py:314-318), accumulation fp32.
 #include <cudaTypedefs.h>
@@ -23,7 +23,7 @@ constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;                       // 64 fp16 = one 128-byte swizzle atom
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;
 constexpr int MAX_STAGES = 8;
-constexpr int NUM_THREADS = 256;
+constexpr int NUM_THREADS = 384;  // 4 control warps + 8 epilogue warps
 constexpr int SMEM_BUDGET = 200 * 1024;
 
 struct TcParams {
@@ -92,7 +92,7 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUte
         }
         for (int s = 0; s < 2; ++s) {
             ptx::mbar_init(tfull_bar(s), 1);
-            ptx::mbar_init(tempty_bar(s), 128);
+            ptx::mbar_init(tempty_bar(s), NUM_THREADS - 128);
         }
         ptx::fence_barrier_init();
     }
@@ -102,7 +102,7 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUte
     }
     if (p.epi.kind == TC_EPI_HEAD && warp >= 4) {
         const int t = threadIdx.x - 128;
-        for (int i = t; i < p.epi.head_nc * 64; i += 128) head_w_s[i] = p.epi.head_w[i];
+        for (int i = t; i < p.epi.head_nc * 64; i += NUM_THREADS - 128) head_w_s[i] = p.epi.head_w[i];
         if (t < p.epi.head_nc) head_w_s[8 * 64 + t] = p.epi.head_b[t];
     }
     ptx::tc_fence_before();
@@ -178,10 +178,13 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUte
         }
     } else if (warp >= 4) {
         // ===================================================== epilogue (TMEM -> registers -> global)
+        // 8 warps: TMEM lane quadrant = warp & 3 (hardware restriction), and the two warps that share a quadrant
+        // take alternating 32-column chunks, so a 128 x 256 tile drains in 4 chunk-steps per warp.
         const TcEpilogue& e = p.epi;
-        const int quad = warp & 3;
+        const int quad = warp & 3, half = (warp - 4) >> 2;
         const int r = quad * 32 + lane;
         const int n_chunks = p.block_n / 32;  // block_n % 32 == 0 enforced on the host
+        const int last_c = n_chunks - 1 - (((n_chunks - 1) & 1) != half ? 1 : 0);  // last chunk of this warp (may be < 0)
         int it = 0;
         for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
             const int as = it & 1;
@@ -194,28 +197,37 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUte
             const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * p.block_n);
 
             if (e.kind == TC_EPI_HEAD) {
-                float v[64];
+                if (half != 0) {  // the fused 1x1 head needs all 64 channels of a pixel in one thread
+                    ptx::tc_fence_before();
+                    ptx::mbar_arrive(tempty_bar(as));
+                    continue;
+                }
+                float hs[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) hs[k] = head_w_s[8 * 64 + k];
 #pragma unroll
                 for (int c = 0; c < 2; ++c) {
                     uint32_t acc[32];
                     ptx::tmem_ld32(t_addr + c * 32, acc);
                     ptx::tmem_ld_wait();
+                    if (c == 1) {
+                        ptx::tc_fence_before();
+                        ptx::mbar_arrive(tempty_bar(as));
+                    }
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
                         const int n = c * 32 + j;
-                        v[n] = fmaxf(fmaf(__uint_as_float(acc[j]), __ldg(e.scale + n), __ldg(e.shift + n)), 0.0f);
+                        const float v = fmaxf(fmaf(__uint_as_float(acc[j]), __ldg(e.scale + n), __ldg(e.shift + n)), 0.0f);
+#pragma unroll
+                        for (int k = 0; k < 8; ++k)
+                            if (k < e.head_nc) hs[k] = fmaf(head_w_s[k * 64 + n], v, hs[k]);
                     }
                 }
-                ptx::tc_fence_before();
-                ptx::mbar_arrive(tempty_bar(as));
                 if (row_ok) {
                     const int img = m / e.head_hw, pix = m - img * e.head_hw;
-                    for (int k = 0; k < e.head_nc; ++k) {
-                        float s = head_w_s[8 * 64 + k];
 #pragma unroll
-                        for (int c = 0; c < 64; ++c) s = fmaf(head_w_s[k * 64 + c], v[c], s);
-                        e.head_out[((size_t)img * e.head_nc + k) * e.head_hw + pix] = s;
-                    }
+                    for (int k = 0; k < 8; ++k)
+                        if (k < e.head_nc) e.head_out[((size_t)img * e.head_nc + k) * e.head_hw + pix] = hs[k];
                 }
                 continue;
             }
@@ -241,12 +253,16 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUte
                 const long long rr = e.res_mod > 0 ? (long long)(m % e.res_mod) + e.res_off : (long long)orow;
                 res_row = e.res + rr * e.ldres;
             }
+            if (last_c < 0) {
+                ptx::tc_fence_before();
+                ptx::mbar_arrive(tempty_bar(as));
+            }
 
-            for (int c = 0; c < n_chunks; ++c) {
+            for (int c = half; c < n_chunks; c += 2) {
                 uint32_t acc[32];
                 ptx::tmem_ld32(t_addr + c * 32, acc);
                 ptx::tmem_ld_wait();
-                if (c == n_chunks - 1) {
+                if (c == last_c) {
                     ptx::tc_fence_before();
                     ptx::mbar_arrive(tempty_bar(as));
                 }
@@ -256,18 +272,25 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUte
                     __half* o = reinterpret_cast<__half*>(e.out) + out_off + nb;
 #pragma unroll
                     for (int j = 0; j < 32; j += 8) {
-                        uint32_t pk[4];
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            const int n = nb + j + 2 * q;
-                            float a = __uint_as_float(acc[j + 2 * q]), b = __uint_as_float(acc[j + 2 * q + 1]);
-                            const float s0 = e.scale ? __ldg(e.scale + n) : 1.0f, s1 = e.scale ? __ldg(e.scale + n + 1) : 1.0f;
-                            const float h0 = e.shift ? __ldg(e.shift + n) : 0.0f, h1 = e.shift ? __ldg(e.shift + n + 1) : 0.0f;
-                            a = apply_act(fmaf(a, s0, h0), e.act);
-                            b = apply_act(fmaf(b, s1, h1), e.act);
-                            pk[q] = pack_h2(a, b);
+                        float4 s0 = make_float4(1.f, 1.f, 1.f, 1.f), s1 = s0;
+                        float4 h0 = make_float4(0.f, 0.f, 0.f, 0.f), h1 = h0;
+                        if (e.scale) {
+                            s0 = __ldg(reinterpret_cast<const float4*>(e.scale + nb + j));
+                            s1 = __ldg(reinterpret_cast<const float4*>(e.scale + nb + j + 4));
                         }
-                        *reinterpret_cast<uint4*>(o + j) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                        if (e.shift) {
+                            h0 = __ldg(reinterpret_cast<const float4*>(e.shift + nb + j));
+                            h1 = __ldg(reinterpret_cast<const float4*>(e.shift + nb + j + 4));
+                        }
+                        const float v0 = apply_act(fmaf(__uint_as_float(acc[j + 0]), s0.x, h0.x), e.act);
+                        const float v1 = apply_act(fmaf(__uint_as_float(acc[j + 1]), s0.y, h0.y), e.act);
+                        const float v2 = apply_act(fmaf(__uint_as_float(acc[j + 2]), s0.z, h0.z), e.act);
+                        const float v3 = apply_act(fmaf(__uint_as_float(acc[j + 3]), s0.w, h0.w), e.act);
+                        const float v4 = apply_act(fmaf(__uint_as_float(acc[j + 4]), s1.x, h1.x), e.act);
+                        const float v5 = apply_act(fmaf(__uint_as_float(acc[j + 5]), s1.y, h1.y), e.act);
+                        const float v6 = apply_act(fmaf(__uint_as_float(acc[j + 6]), s1.z, h1.z), e.act);
+                        const float v7 = apply_act(fmaf(__uint_as_float(acc[j + 7]), s1.w, h1.w), e.act);
+                        *reinterpret_cast<uint4*>(o + j) = make_uint4(pack_h2(v0, v1), pack_h2(v2, v3), pack_h2(v4, v5), pack_h2(v6, v7));
                     }
                 } else if (e.kind == TC_EPI_RES_F32) {
                     float* o = reinterpret_cast<float*>(e.out) + out_off + nb;
@@ -291,14 +314,16 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUte
                     __half* o = reinterpret_cast<__half*>(e.out) + opix * (size_t)e.ldc + co;
 #pragma unroll
                     for (int j = 0; j < 32; j += 8) {
-                        uint32_t pk[4];
-#pragma unroll
-                        for (int t = 0; t < 4; ++t) {
-                            const float h0 = e.shift ? __ldg(e.shift + co + j + 2 * t) : 0.0f;
-                            const float h1 = e.shift ? __ldg(e.shift + co + j + 2 * t + 1) : 0.0f;
-                            pk[t] = pack_h2(__uint_as_float(acc[j + 2 * t]) + h0, __uint_as_float(acc[j + 2 * t + 1]) + h1);
+                        float4 h0 = make_float4(0.f, 0.f, 0.f, 0.f), h1 = h0;
+                        if (e.shift) {
+                            h0 = __ldg(reinterpret_cast<const float4*>(e.shift + co + j));
+                            h1 = __ldg(reinterpret_cast<const float4*>(e.shift + co + j + 4));
                         }
-                        *reinterpret_cast<uint4*>(o + j) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                        *reinterpret_cast<uint4*>(o + j) =
+                            make_uint4(pack_h2(__uint_as_float(acc[j + 0]) + h0.x, __uint_as_float(acc[j + 1]) + h0.y),
+                                       pack_h2(__uint_as_float(acc[j + 2]) + h0.z, __uint_as_float(acc[j + 3]) + h0.w),
+                                       pack_h2(__uint_as_float(acc[j + 4]) + h1.x, __uint_as_float(acc[j + 5]) + h1.y),
+                                       pack_h2(__uint_as_float(acc[j + 6]) + h1.z, __uint_as_float(acc[j + 7]) + h1.w));
                     }
                 }
             }

@@ -66,12 +66,12 @@ def fold_bn(sd, conv_prefix, bn_prefix, n_pad, eps=1e-5):
 
 
 def rel_table(rel_pos, size):
-    """image_encoder.py:321-351 for q_size == k_size == size -> fp32 [2*size-1, hd] (row = q - k + size - 1)."""
+    """image_encoder.py:321-351 for q_size == k_size == size -> fp16 [2*size-1, hd] (row = q - k + size - 1)."""
     L = 2 * size - 1
     if rel_pos.shape[0] != L:
         r = F.interpolate(rel_pos.float().reshape(1, rel_pos.shape[0], -1).permute(0, 2, 1), size=L, mode="linear")
-        return r.reshape(-1, L).permute(1, 0).contiguous()
-    return _f(rel_pos)
+        return _h(r.reshape(-1, L).permute(1, 0))
+    return _h(rel_pos)
 
 
 def vit_pos(pos_embed, h, w, dim):

@@ -116,10 +116,9 @@ int cvb_op_conv3x3_f16(const void* src0, int C0, const void* src1, int C1, int N
                        int block_n, const struct TcEpilogue* epi, void* stream);
 int cvb_op_layernorm_f16(const float* x, const float* gamma, const float* beta, float eps, int rows_dst, int D, void* out,
                          int map, int B, int tok_h, int tok_w, int ws, int g, void* stream);
-int cvb_op_relpos(const void* qkv, int Gb, int heads, int hd, int gh, int gw, const float* Rh, const float* Rw,
-                  float* rel_h, float* rel_w, void* stream);
-int cvb_op_attention(const void* qkv, int Gb, int S, int heads, int hd, float scale, const float* rel_h,
-                     const float* rel_w, int gh, int gw, void* out, void* stream);
+/* Rh / Rw: fp16 rel-pos tables [2*gh-1, hd] / [2*gw-1, hd] (both null: no bias). */
+int cvb_op_attention(const void* qkv, int Gb, int S, int heads, int hd, float scale, const void* Rh, const void* Rw,
+                     int gh, int gw, void* out, void* stream);
 int cvb_op_patch_im2col(const float* x, int B, int H, int W, int P, void* out, void* stream);
 int cvb_op_stem_conv(const float* x, int B, int H, int W, const float* w, const float* scale, const float* shift,
                      void* out, int cpad, void* stream);

@@ -58,24 +58,21 @@ def _ref_attention(qkv, Gb, S, heads, hd, scale, Rh=None, Rw=None, gh=0, gw=0):
 
 
 @pytest.mark.parametrize("Gb,gh,gw,heads,hd,bias", [(2, 1, 257, 6, 64, False), (2, 16, 16, 16, 80, True), (18, 14, 14, 12, 64, True),
-                                                    (1, 64, 64, 4, 80, True), (50, 14, 14, 16, 80, True)])
+                                                    (1, 64, 64, 4, 80, True), (50, 14, 14, 16, 80, True), (2, 32, 32, 12, 64, True)])
 def test_attention_matches_torch(Gb, gh, gw, heads, hd, bias):
     g = torch.Generator(device="cuda").manual_seed(7)
     S, D = gh * gw, heads * hd
     qkv = (torch.randn(Gb * S, 3 * D, device="cuda", generator=g)).half()
     out = torch.full((Gb * S, D), float("nan"), device="cuda", dtype=torch.half)
     scale = hd ** -0.5
-    Rh = Rw = rel_h = rel_w = None
+    Rh = Rw = None
     if bias:
-        Rh = torch.randn(2 * gh - 1, hd, device="cuda", generator=g) * 0.2
-        Rw = torch.randn(2 * gw - 1, hd, device="cuda", generator=g) * 0.2
-        rel_h = torch.empty(Gb * heads, S, gh, device="cuda")
-        rel_w = torch.empty(Gb * heads, S, gw, device="cuda")
-        L.check(L.lib().cvb_op_relpos(L.ptr(qkv), Gb, heads, hd, gh, gw, L.ptr(Rh), L.ptr(Rw), L.ptr(rel_h), L.ptr(rel_w), L.stream_ptr()), "relpos")
-    L.check(L.lib().cvb_op_attention(L.ptr(qkv), Gb, S, heads, hd, C.c_float(scale), L.ptr(rel_h), L.ptr(rel_w), gh, gw, L.ptr(out),
+        Rh = (torch.randn(2 * gh - 1, hd, device="cuda", generator=g) * 0.2).half()
+        Rw = (torch.randn(2 * gw - 1, hd, device="cuda", generator=g) * 0.2).half()
+    L.check(L.lib().cvb_op_attention(L.ptr(qkv), Gb, S, heads, hd, C.c_float(scale), L.ptr(Rh), L.ptr(Rw), gh, gw, L.ptr(out),
                                      L.stream_ptr()), "attention")
     torch.cuda.synchronize()
-    ref = _ref_attention(qkv, Gb, S, heads, hd, scale, Rh, Rw, gh, gw)
+    ref = _ref_attention(qkv, Gb, S, heads, hd, scale, None if Rh is None else Rh.float(), None if Rw is None else Rw.float(), gh, gw)
     err = (out.float() - ref).abs().max().item()
     assert err < 4e-3, err
 
