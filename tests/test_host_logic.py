@@ -1,0 +1,160 @@
+"""CPU-side checks: the C-ABI library exports every declared symbol, the module mirrors keep the reference
+state_dict surface and error behaviour, packing shapes, sharding logic (incl. a world-size-2 gloo run)."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib_path():
+    from cellvit_b200 import build
+    return build.build()
+
+
+def test_c_abi_exports_every_declared_symbol(lib_path):
+    hdr = open(os.path.join(ROOT, "include", "cellvit_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    names = sorted(set(re.findall(r"\b(cvb_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(names) >= 14
+    L = ctypes.CDLL(lib_path)
+    missing = [n for n in names if not hasattr(L, n)]
+    assert not missing, missing
+    assert L.cvb_version() >= 100
+    # argument validation that needs no GPU
+    L.cvb_last_error.restype = ctypes.c_char_p
+    need = ctypes.c_size_t()
+    assert L.cvb_postproc_workspace_bytes(2, 1024, 1024, ctypes.byref(need)) == 0 and need.value > 2 * 1024 * 1024 * 44
+    assert L.cvb_postproc_workspace_bytes(0, 1024, 1024, ctypes.byref(need)) == -1
+    assert L.cvb_model_create(None, None) == -1 and b"null" in L.cvb_last_error()
+
+
+def test_model_desc_validation_and_shape_errors(lib_path):
+    from cellvit_b200.cellvit import CellViT256, ModelDesc
+    L = ctypes.CDLL(lib_path)
+    L.cvb_last_error.restype = ctypes.c_char_p
+    m = CellViT256(None, 6, 19)
+    h = m._ensure_handle()
+    need = ctypes.c_size_t()
+    assert L.cvb_model_workspace_bytes(h, 1, 256, 256, ctypes.byref(need)) == 0 and need.value > 0
+    assert L.cvb_model_workspace_bytes(h, 1, 250, 250, ctypes.byref(need)) == -2     # not divisible by 16
+    assert b"divisible by the patch size" in L.cvb_last_error()
+    assert L.cvb_model_workspace_bytes(h, 1, 320, 320, ctypes.byref(need)) == -2     # unsupported tile edge
+    bad = ModelDesc(sam=0, embed_dim=100, depth=1, num_heads=3)
+    out = ctypes.c_void_p()
+    assert L.cvb_model_create(ctypes.byref(bad), ctypes.byref(out)) != 0
+
+
+@pytest.mark.parametrize("arch", ["ViT256", "SAM-B", "SAM-H"])
+def test_state_dict_surface_matches_reference_spec(arch):
+    from cellvit_b200 import weights
+    from cellvit_b200.cellvit import CellViT256, CellViTSAM
+    m = CellViT256(None, 6, 19) if arch == "ViT256" else CellViTSAM(None, 6, 19, arch)
+    sd = weights.synth_state_dict(arch, 6, 19, seed=1)
+    own = m.state_dict()
+    assert list(own.keys()) == list(sd.keys())
+    assert all(tuple(own[k].shape) == tuple(sd[k].shape) for k in sd)
+    m.load_state_dict(sd, strict=True)
+    assert m.patch_size == 16 and m.num_nuclei_classes == 6 and m.embed_dim == (384 if arch == "ViT256" else weights.SAM_CFG[arch]["embed_dim"])
+    n_params = sum(p.numel() for p in m.parameters())
+    if arch == "ViT256":
+        assert n_params == 46_750_349   # logs_paper/PanNuke/CellViTHV/ViT256/Best-Setting/Fold-1/logs.log:718
+    if arch == "SAM-H":
+        assert n_params == 699_741_149  # logs_paper/PanNuke/CellViTHV/SAM-H/Fold-1/logs.log:957
+
+
+def test_forward_contract_errors_without_gpu():
+    from cellvit_b200.cellvit import CellViT256, CellViTSAM
+    m = CellViT256(None, 6, 19)
+    with pytest.raises(AssertionError, match="divisible by the patch size"):
+        m(torch.zeros(1, 3, 250, 256))
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        m(torch.zeros(1, 3, 256, 256))
+    with pytest.raises(NotImplementedError, match="Unknown ViT-SAM backbone structure"):
+        CellViTSAM(None, 6, 19, "SAM-X")
+    from cellvit_b200.post_proc_cellvit import DetectionCellPostProcessor
+    with pytest.raises(NotImplementedError, match="Unknown magnification"):
+        DetectionCellPostProcessor(6, magnification=30)
+    assert (DetectionCellPostProcessor(6, 40).object_size, DetectionCellPostProcessor(6, 20).k_size) == (10, 11)
+    assert (DetectionCellPostProcessor(6, 40, gt=True).object_size, DetectionCellPostProcessor(6, 40, gt=True).k_size) == (100, 21)
+
+
+def test_packing_layouts():
+    from cellvit_b200 import packing, weights
+    from cellvit_b200.cellvit import CellViT256
+    sd = weights.synth_state_dict("ViT256", 6, 19, seed=2)
+    cfg = CellViT256(None, 6, 19)._cfg()
+    P = packing.pack_static(sd, cfg)
+    P.update(packing.pack_for_size(sd, cfg, 16, 16))
+    # conv weight: k = tap * Cpad + c, concat split (312 -> 320 twice)
+    w = sd["hv_map_decoder.decoder3_upsampler.0.block.0.weight"]
+    pk = P["hv.d3.0.w"].float().view(320, 3, 3, 640)
+    assert torch.equal(pk[:312, :, :, :312], w[:, :312].permute(0, 2, 3, 1).half().float())
+    assert torch.equal(pk[:312, :, :, 320:632], w[:, 312:].permute(0, 2, 3, 1).half().float())
+    assert pk[312:].abs().sum() == 0 and pk[:, :, :, 312:320].abs().sum() == 0 and pk[:, :, :, 632:].abs().sum() == 0
+    # folded BN: relu(scale * conv + shift) == relu(bn(conv + bias))
+    p = "decoder2.1.block"
+    s, sh = P["decoder2.1.conv.scale"], P["decoder2.1.conv.shift"]
+    y = torch.randn(256)
+    bn = (y + sd[p + ".1.bias"] - sd[p + ".2.running_mean"]) / torch.sqrt(sd[p + ".2.running_var"] + 1e-5) * sd[p + ".2.weight"] + sd[p + ".2.bias"]
+    assert torch.allclose(y * s + sh, bn, atol=1e-5)
+    # ConvTranspose: rows ordered (dy, dx, co)
+    wt = sd["decoder1.0.block.0.weight"]
+    pt = P["decoder1.0.ct.w"].float().view(2, 2, 256, 384)
+    assert torch.equal(pt[1, 0], wt[:, :, 1, 0].t().half().float())
+    assert P["pos"].shape == (257, 384) and P["clspos"].shape == (384,)
+
+
+def test_shard_indices_cover_all_tiles_once():
+    from cellvit_b200.cell_detection import shard_indices, unflatten_dict
+    for n, world in [(10, 1), (10, 3), (7, 8), (10000, 8)]:
+        got = sorted(i for r in range(world) for i in shard_indices(n, r, world))
+        assert got == list(range(n))
+    assert unflatten_dict({"data.num_nuclei_classes": 6, "model.backbone": "SAM-H"}) == {"data": {"num_nuclei_classes": 6}, "model": {"backbone": "SAM-H"}}
+
+
+_GLOO = r'''
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from cellvit_b200.cell_detection import broadcast_weights, shard_indices
+from cellvit_b200.cellvit import CellViT256
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+torch.manual_seed(100 + rank)                    # different weights per rank before the broadcast
+m = CellViT256(None, 6, 19)
+with torch.no_grad():
+    for p in m.parameters():
+        p.add_(float(rank))
+broadcast_weights(m, 0)
+chk = torch.cat([p.detach().reshape(-1)[:4] for p in m.parameters()]).double().sum()
+allc = [torch.zeros_like(chk) for _ in range(world)]
+dist.all_gather(allc, chk)
+assert all(torch.equal(allc[0], c) for c in allc), allc
+# tile sharding + all-gather of per-tile "instance counts" gives the same table on every rank, in tile order
+n_tiles = 11
+mine = shard_indices(n_tiles, rank, world)
+counts = torch.zeros(n_tiles, dtype=torch.int64)
+for i in mine:
+    counts[i] = 100 + i
+dist.all_reduce(counts)
+assert counts.tolist() == [100 + i for i in range(n_tiles)]
+dist.destroy_process_group()
+print("ok", rank)
+'''
+
+
+def test_world_size_2_gloo_broadcast_and_sharding(tmp_path):
+    script = tmp_path / "gloo_job.py"
+    script.write_text(_GLOO)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29611", str(script), ROOT], capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert r.stdout.count("ok") == 2

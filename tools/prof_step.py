@@ -1,0 +1,16 @@
+import torch, sys, numpy as np
+sys.path.insert(0, ".")
+from cellvit_b200.cellvit import CellViTSAM
+from cellvit_b200.post_proc_cellvit import DetectionCellPostProcessor
+from cellvit_b200 import synth
+torch.manual_seed(0)
+m = CellViTSAM(None, 6, 19, "SAM-H").eval().cuda()
+x = torch.from_numpy(synth.synthetic_tiles(4, 1024, seed=1)).cuda()
+nuc = [synth.synthetic_nuclei(1024, 700, seed=i) for i in range(4)]
+lg = [synth.head_logits_from_maps(n["np_bin"], n["nt"], 6) for n in nuc]
+npd = torch.from_numpy(np.stack([l[0] for l in lg])).cuda(); ntd = torch.from_numpy(np.stack([l[1] for l in lg])).cuda()
+hvd = torch.from_numpy(np.stack([n["hv"] for n in nuc])).cuda()
+p = DetectionCellPostProcessor(6, 40)
+with torch.no_grad():
+    m(x, retrieve_tokens=True); p.run_float(npd, hvd, ntd)
+torch.cuda.synchronize()
