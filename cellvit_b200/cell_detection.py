@@ -88,6 +88,16 @@ class CellSegmentationInference:
         # the tile engine always computes fp16 operands / fp32 accumulate (the reference's AMP mode, :314-318)
         self.mixed_precision = True if enforce_mixed_precision else self.run_conf.get("training", {}).get("mixed_precision", False)
 
+    @classmethod
+    def from_model(cls, model: CellViT, gpu: int) -> "CellSegmentationInference":
+        """Wrap an already constructed (and loaded) model instead of reading a checkpoint file."""
+        self = cls.__new__(cls)
+        self.device = f"cuda:{gpu}"
+        self.model, self.run_conf = model.eval().to(self.device), {}
+        self.mean = self.std = (0.5, 0.5, 0.5)
+        self.mixed_precision = True
+        return self
+
     def get_cell_predictions_with_tokens(self, predictions: dict, magnification: int = 40) -> Tuple[List[dict], torch.Tensor]:
         """cell_detection.py:485-514."""
         predictions["nuclei_binary_map"] = F.softmax(predictions["nuclei_binary_map"], dim=1)
@@ -104,14 +114,34 @@ class CellSegmentationInference:
         return (x - mean) / std
 
     @torch.no_grad()
-    def process_tiles(self, batches: Iterable[torch.Tensor], magnification: int = 40) -> List[List[dict]]:
-        """Hot loop of process_wsi (:306-323) over already normalised batches [B,3,H,W] (host or device)."""
-        results = []
-        for patches in batches:
-            patches = patches.to(self.device, non_blocking=True)
-            predictions = self.model.forward(patches, retrieve_tokens=True)
-            instance_types, _ = self.get_cell_predictions_with_tokens(predictions, magnification=magnification)
-            results.append(instance_types)
+    def process_tiles(self, batches: Iterable[torch.Tensor], magnification: int = 40, head_override: dict = None,
+                      host_threads: int = 0) -> List[List[dict]]:
+        """Hot loop of process_wsi (:306-323) over already normalised batches [B,3,H,W] (pinned host or device
+        tensors). Per batch: H2D, forward, softmax (:500-505), device post-processing, D2H of label maps and instance
+        tables; the host part (contours + dict building, post_proc_cellvit.py:96-151) of batch k overlaps the device
+        work of batch k+1. ``head_override`` replaces head maps before post-processing (bench/test hook: random-init
+        networks emit constant maps). Returns one list of per-tile instance dicts per batch."""
+        from concurrent.futures import ThreadPoolExecutor
+        from .post_proc_cellvit import DetectionCellPostProcessor
+        proc = DetectionCellPostProcessor(nr_types=self.model.num_nuclei_classes, magnification=magnification, gt=False)
+        results, pending = [], None
+        # host_threads > 0 spreads the per-tile dict building over a thread pool; with CPython's GIL this only pays
+        # when cv2.findContours dominates, so the default (0) keeps it on the calling thread.
+        with ThreadPoolExecutor(max_workers=max(1, host_threads)) as pool_:
+            pool = pool_ if host_threads > 0 else None
+            for k, patches in enumerate(batches):
+                patches = patches.to(self.device, non_blocking=True)
+                predictions = self.model.forward(patches, retrieve_tokens=True)
+                if head_override:
+                    predictions.update(head_override)
+                np_map = F.softmax(predictions["nuclei_binary_map"], dim=1)
+                nt_map = F.softmax(predictions["nuclei_type_map"], dim=1)
+                proc.launch_float(np_map, predictions["hv_map"], nt_map, slot=k & 1)
+                if pending is not None:
+                    results.append(proc.collect(pending, pool)[1])
+                pending = k & 1
+            if pending is not None:
+                results.append(proc.collect(pending, pool)[1])
         return results
 
     def process_wsi(self, *args, **kwargs):

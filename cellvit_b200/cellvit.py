@@ -118,14 +118,21 @@ class CellViT(nn.Module):
 
     def _ensure_packed(self, device, h, w):
         self._ensure_handle()
-        sd = OrderedDict((k, v) for k, v in self.state_dict().items())
-        key = (str(device), tuple(int(v._version) for v in sd.values()), tuple(v.data_ptr() for v in sd.values()))
-        if key != self._packed_key:
-            sd_dev = {k: v.to(device) for k, v in sd.items()}
+        ver = ptr = 0
+        for t in self.parameters():
+            ver += t._version
+            ptr ^= t.data_ptr()
+        for t in self.buffers():
+            ver += t._version
+            ptr ^= t.data_ptr()
+        key = (str(device), ver, ptr)
+        if key != self._packed_key:  # weights were (re)loaded, updated in place or moved: repack once
+            sd_dev = {k: v.to(device) for k, v in self.state_dict().items()}
             self._register(packing.pack_static(sd_dev, self._cfg()))
             self._packed_key, self._size_key = key, None
         if self._size_key != (h, w):
-            sd_dev = {k: v.to(device) for k, v in sd.items() if k.startswith("encoder.pos_embed") or "rel_pos" in k or "cls_token" in k}
+            sd_dev = {k: v.to(device) for k, v in self.state_dict().items()
+                      if k.startswith("encoder.pos_embed") or "rel_pos" in k or "cls_token" in k}
             self._register(packing.pack_for_size(sd_dev, self._cfg(), h, w))
             self._size_key = (h, w)
 

@@ -289,6 +289,212 @@ flash_kernel(const __half* __restrict__ qkv, int S, int heads, float scale, cons
     }
 }
 
+// ------------------------------------------------------------------------------------------ windowed attention
+// One CTA per (window, head): the whole K and V of the window (S <= 208 keys, 14 x 14 = 196 for SAM) stay in shared
+// memory, so the seven warps run their 16-query m-tiles without any block-level synchronisation after the load.
+// Q fragments are read straight from global memory in the MMA A-fragment layout (31 KB per CTA, L1-resident).
+constexpr int WA_WARPS = 7, WA_THREADS = WA_WARPS * 32, WA_MAXS = 208, WA_REL_LD = 15;
+
+template <int HD>
+struct WaSmem {
+    static constexpr int LD = HD + 8;
+    __half k[WA_MAXS * LD];
+    __half v[WA_MAXS * LD];
+    __half th[32 * LD];  // rel-pos tables (L = 2g-1 <= 29 rows for g <= 15), zero-padded to 32 rows
+    __half tw[32 * LD];
+    float bias_h[WA_WARPS][16 * WA_REL_LD];
+    float bias_w[WA_WARPS][16 * WA_REL_LD];
+};
+
+template <int HD>
+__global__ void __launch_bounds__(WA_THREADS, 2)
+window_attn_kernel(const __half* __restrict__ qkv, int S, int heads, float scale, const __half* __restrict__ Rh,
+                   const __half* __restrict__ Rw, int gh, int gw, __half* __restrict__ out) {
+    extern __shared__ __align__(16) uint8_t wa_smem_raw[];
+    using Smem = WaSmem<HD>;
+    Smem& sm = *reinterpret_cast<Smem*>(wa_smem_raw);
+    constexpr int LD = Smem::LD, KSTEPS = HD / 16, NT_O = HD / 8, CH = HD / 8;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = blockIdx.x, bp = g / heads, head = g - bp * heads;
+    const int D = heads * HD;
+    const long long row_stride = 3LL * D;
+    const __half* q_base = qkv + (long long)bp * S * row_stride + head * HD;
+    const __half* k_base = q_base + D;
+    const __half* v_base = q_base + 2 * D;
+    const int Lh = 2 * gh - 1, Lw = 2 * gw - 1;
+    const int s_pad = (S + 15) & ~15;
+
+    for (int i = tid; i < s_pad * CH; i += WA_THREADS) {
+        const int r = i / CH, c = i - r * CH;
+        const bool ok = r < S;
+        const long long off = (long long)(ok ? r : 0) * row_stride + c * 8;
+        ptx::cp_async16(ptx::smem_u32(sm.k + r * LD + c * 8), k_base + off, ok);
+        ptx::cp_async16(ptx::smem_u32(sm.v + r * LD + c * 8), v_base + off, ok);
+    }
+    for (int i = tid; i < 32 * CH; i += WA_THREADS) {
+        const int r = i / CH, c = i - r * CH;
+        ptx::cp_async16(ptx::smem_u32(sm.th + r * LD + c * 8), Rh + (long long)(r < Lh ? r : 0) * HD + c * 8, r < Lh);
+        ptx::cp_async16(ptx::smem_u32(sm.tw + r * LD + c * 8), Rw + (long long)(r < Lw ? r : 0) * HD + c * 8, r < Lw);
+    }
+    ptx::cp_async_commit();
+    ptx::cp_async_wait<0>();
+    __syncthreads();
+
+    constexpr float L2E = 1.4426950408889634f;
+    const float sl2 = scale * L2E;
+    const float inv_gw = 1.0f / (float)gw;
+    const int n_mt = s_pad >> 4, n_kt = (S + 63) >> 6;
+    float* bh = sm.bias_h[warp];
+    float* bw = sm.bias_w[warp];
+    const int rl = lane >> 2;  // local row of c0/c1; c2/c3 are rl + 8
+
+    for (int mt = warp; mt < n_mt; mt += WA_WARPS) {
+        const int q0 = mt * 16;
+        // ---- Q fragments from global: a0=(rl, 2*(lane&3)), a1=(rl+8, .), a2=(rl, .+8), a3=(rl+8, .+8)
+        uint32_t q_frag[KSTEPS][4];
+        {
+            const int r0 = q0 + rl, r1 = r0 + 8;
+            const __half* p0 = q_base + (long long)min(r0, S - 1) * row_stride + 2 * (lane & 3);
+            const __half* p1 = q_base + (long long)min(r1, S - 1) * row_stride + 2 * (lane & 3);
+#pragma unroll
+            for (int ks = 0; ks < KSTEPS; ++ks) {
+                q_frag[ks][0] = r0 < S ? *reinterpret_cast<const uint32_t*>(p0 + ks * 16) : 0u;
+                q_frag[ks][1] = r1 < S ? *reinterpret_cast<const uint32_t*>(p1 + ks * 16) : 0u;
+                q_frag[ks][2] = r0 < S ? *reinterpret_cast<const uint32_t*>(p0 + ks * 16 + 8) : 0u;
+                q_frag[ks][3] = r1 < S ? *reinterpret_cast<const uint32_t*>(p1 + ks * 16 + 8) : 0u;
+            }
+        }
+        float s_acc[8][4];
+        // ---- rel-pos: G = Q T^T, scattered to bias[row][k = qpos + g - 1 - j]
+#pragma unroll
+        for (int tbl = 0; tbl < 2; ++tbl) {
+            const int L = tbl == 0 ? Lh : Lw, gdim = tbl == 0 ? gh : gw;
+            fa_qk<HD>(tbl == 0 ? sm.th : sm.tw, q_frag, s_acc, lane, (L + 15) >> 4);
+            float* dst = tbl == 0 ? bh : bw;
+#pragma unroll
+            for (int hrow = 0; hrow < 2; ++hrow) {
+                const int t = q0 + rl + 8 * hrow;
+                if (t < S) {
+                    const int qh = (int)(((float)t + 0.5f) * inv_gw);
+                    const int qpos = tbl == 0 ? qh : t - qh * gw;
+#pragma unroll
+                    for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            const int j = nt * 8 + 2 * (lane & 3) + e;
+                            const int kk = qpos + gdim - 1 - j;
+                            if (kk >= 0 && kk < gdim && j < L) dst[(rl + 8 * hrow) * WA_REL_LD + kk] = s_acc[nt][2 * hrow + e];
+                        }
+                }
+            }
+        }
+        __syncwarp();
+
+        float o_acc[NT_O][4];
+#pragma unroll
+        for (int i = 0; i < NT_O; ++i) { o_acc[i][0] = o_acc[i][1] = o_acc[i][2] = o_acc[i][3] = 0.f; }
+        float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
+        for (int kt = 0; kt < n_kt; ++kt) {
+            const int kbase = kt * 64;
+            const int keys_here = min(64, s_pad - kbase);        // multiple of 16
+            fa_qk<HD>(sm.k + kbase * LD, q_frag, s_acc, lane, keys_here >> 4);
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int kcol = kbase + nt * 8 + 2 * (lane & 3) + e;
+                    const bool valid = kcol < S;
+                    float b_lo = 0.f, b_hi = 0.f;
+                    if (valid) {
+                        const int kh = (int)(((float)kcol + 0.5f) * inv_gw), kw = kcol - kh * gw;
+                        b_lo = (bh[rl * WA_REL_LD + kh] + bw[rl * WA_REL_LD + kw]) * L2E;
+                        b_hi = (bh[(rl + 8) * WA_REL_LD + kh] + bw[(rl + 8) * WA_REL_LD + kw]) * L2E;
+                    }
+                    s_acc[nt][e] = valid ? fmaf(s_acc[nt][e], sl2, b_lo) : -INFINITY;
+                    s_acc[nt][2 + e] = valid ? fmaf(s_acc[nt][2 + e], sl2, b_hi) : -INFINITY;
+                }
+            float mx[2] = {m_run[0], m_run[1]};
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) {
+                mx[0] = fmaxf(mx[0], fmaxf(s_acc[nt][0], s_acc[nt][1]));
+                mx[1] = fmaxf(mx[1], fmaxf(s_acc[nt][2], s_acc[nt][3]));
+            }
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                mx[h] = fmaxf(mx[h], __shfl_xor_sync(0xffffffffu, mx[h], 1));
+                mx[h] = fmaxf(mx[h], __shfl_xor_sync(0xffffffffu, mx[h], 2));
+            }
+            float alpha[2], rs[2] = {0.f, 0.f};
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                alpha[h] = exp2f(m_run[h] - mx[h]);
+                m_run[h] = mx[h];
+            }
+            uint32_t p_frag[4][4];
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) {
+                const float p0 = exp2f(s_acc[nt][0] - mx[0]), p1 = exp2f(s_acc[nt][1] - mx[0]);
+                const float p2 = exp2f(s_acc[nt][2] - mx[1]), p3 = exp2f(s_acc[nt][3] - mx[1]);
+                rs[0] += p0 + p1;
+                rs[1] += p2 + p3;
+                p_frag[nt >> 1][(nt & 1) * 2 + 0] = pack_h2(p0, p1);
+                p_frag[nt >> 1][(nt & 1) * 2 + 1] = pack_h2(p2, p3);
+            }
+#pragma unroll
+            for (int h = 0; h < 2; ++h) l_run[h] = l_run[h] * alpha[h] + rs[h];
+#pragma unroll
+            for (int i = 0; i < NT_O; ++i) {
+                o_acc[i][0] *= alpha[0]; o_acc[i][1] *= alpha[0];
+                o_acc[i][2] *= alpha[1]; o_acc[i][3] *= alpha[1];
+            }
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+                if (kk * 16 < keys_here) {
+#pragma unroll
+                    for (int dp = 0; dp < NT_O / 2; ++dp) {
+                        uint32_t b0, b1, b2, b3;
+                        const int row = kbase + kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+                        const int col = dp * 16 + (lane >> 4) * 8;
+                        ptx::ldmatrix_x4_trans(ptx::smem_u32(sm.v + row * LD + col), b0, b1, b2, b3);
+                        ptx::mma_16816(o_acc[2 * dp], p_frag[kk], b0, b1);
+                        ptx::mma_16816(o_acc[2 * dp + 1], p_frag[kk], b2, b3);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            l_run[h] += __shfl_xor_sync(0xffffffffu, l_run[h], 1);
+            l_run[h] += __shfl_xor_sync(0xffffffffu, l_run[h], 2);
+        }
+        const float inv0 = 1.0f / l_run[0], inv1 = 1.0f / l_run[1];
+        const int qr0 = q0 + rl, qr1 = qr0 + 8;
+        __half* o0 = out + ((long long)bp * S + qr0) * D + head * HD + 2 * (lane & 3);
+        __half* o1 = out + ((long long)bp * S + qr1) * D + head * HD + 2 * (lane & 3);
+#pragma unroll
+        for (int i = 0; i < NT_O; ++i) {
+            if (qr0 < S) *reinterpret_cast<uint32_t*>(o0 + i * 8) = pack_h2(o_acc[i][0] * inv0, o_acc[i][1] * inv0);
+            if (qr1 < S) *reinterpret_cast<uint32_t*>(o1 + i * 8) = pack_h2(o_acc[i][2] * inv1, o_acc[i][3] * inv1);
+        }
+        __syncwarp();  // bias tables are reused by the warp's next m-tile
+    }
+}
+
+template <int HD>
+int launch_window(const __half* qkv, int Gb, int S, int heads, float scale, const __half* Rh, const __half* Rw, int gh, int gw,
+                  __half* out, cudaStream_t stream) {
+    static bool configured = false;
+    const int smem = (int)sizeof(WaSmem<HD>);
+    if (!configured) {
+        CVB_CUDA(cudaFuncSetAttribute(window_attn_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        configured = true;
+    }
+    window_attn_kernel<HD><<<Gb * heads, WA_THREADS, smem, stream>>>(qkv, S, heads, scale, Rh, Rw, gh, gw, out);
+    cvb_note_launches(1);
+    CVB_CUDA(cudaGetLastError());
+    return CVB_OK;
+}
+
 template <int HD, bool BIAS>
 int launch_flash(const __half* qkv, int Gb, int S, int heads, float scale, const __half* Rh, const __half* Rw,
                  int gh, int gw, __half* out, cudaStream_t stream) {
@@ -313,6 +519,10 @@ int op_attention(const __half* qkv, int Gb, int S, int heads, int hd, float scal
     CVB_CHECK((Rh == nullptr) == (Rw == nullptr), CVB_EARG, "attention: Rh and Rw must both be set or both null");
     if (Rh) CVB_CHECK(gh * gw == S && gh <= 64 && gw <= 64, CVB_ESHAPE, "attention: bias grid %dx%d does not match S=%d", gh, gw, S);
     if (!Rh) { gh = 1; gw = S; }
+    if (Rh && S <= WA_MAXS && gh <= 15 && gw <= 15) {  // SAM windows: whole K/V resident in shared memory
+        if (hd == 80) return launch_window<80>(qkv, Gb, S, heads, scale, Rh, Rw, gh, gw, out, stream);
+        if (hd == 64) return launch_window<64>(qkv, Gb, S, heads, scale, Rh, Rw, gh, gw, out, stream);
+    }
     if (hd == 80) return Rh ? launch_flash<80, true>(qkv, Gb, S, heads, scale, Rh, Rw, gh, gw, out, stream)
                             : launch_flash<80, false>(qkv, Gb, S, heads, scale, Rh, Rw, gh, gw, out, stream);
     if (hd == 64) return Rh ? launch_flash<64, true>(qkv, Gb, S, heads, scale, Rh, Rw, gh, gw, out, stream)

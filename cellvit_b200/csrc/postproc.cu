@@ -714,6 +714,98 @@ table_finalize_kernel(const Acc* __restrict__ acc, int cap, int n_types, int max
     }
 }
 
+// ------------------------------------------------------------------------------------------ contours
+// cv2.findContours(crop, RETR_TREE, CHAIN_APPROX_SIMPLE)[0][0] of every instance (post_proc_cellvit.py:106-125) =
+// the Suzuki-Abe outer border of the instance, started at its raster-first pixel, 8-neighbour search order
+// right, up-right, up, up-left, left, down-left, down, down-right, a point emitted whenever the step direction
+// changes. Exact for instances with one 8-connected component (cv2 lists the LAST component first otherwise):
+// an 8-connectivity CCL of the label map counts the components of every id, and ids with more than one are
+// flagged (npts = -1) for the host to resolve with cv2 itself.
+__global__ void lab8_init_kernel(const int* __restrict__ labels, Dims d, int* __restrict__ L) {
+    const long long total = (long long)d.B * d.N;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x)
+        L[i] = labels[i] > 0 ? (int)(i % d.N) : -1;
+}
+__global__ void lab8_merge_kernel(const int* __restrict__ labels, Dims d, int* __restrict__ L) {
+    const long long total = (long long)d.B * d.N;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int b = (int)(i / d.N), p = (int)(i - (long long)b * d.N);
+        const int* lt = labels + (long long)b * d.N;
+        const int id = lt[p];
+        if (id <= 0) continue;
+        int* Lt = L + (long long)b * d.N;
+        const int y = p / d.W, x = p - y * d.W;
+        if (x > 0 && lt[p - 1] == id) uf_unite(Lt, p, p - 1);
+        if (y > 0) {
+            if (lt[p - d.W] == id) uf_unite(Lt, p, p - d.W);
+            else {  // diagonals only matter when the pixel above does not already join them
+                if (x > 0 && lt[p - d.W - 1] == id && lt[p - 1] != id) uf_unite(Lt, p, p - d.W - 1);
+                if (x < d.W - 1 && lt[p - d.W + 1] == id) uf_unite(Lt, p, p - d.W + 1);
+            }
+        }
+    }
+}
+__global__ void lab8_count_kernel(const int* __restrict__ labels, const int* __restrict__ L, Dims d, int cap, int* __restrict__ ncomp) {
+    const long long total = (long long)d.B * d.N;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int p = (int)(i % d.N);
+        if (L[i] != p) continue;
+        const int id = labels[i];
+        if (id > 0 && id < cap) atomicAdd(&ncomp[(i / d.N) * cap + id], 1);
+    }
+}
+// one thread per table row
+__global__ void contour_kernel(const int* __restrict__ labels, const cvb_inst_row* __restrict__ table, const int* __restrict__ counts,
+                               const int* __restrict__ ncomp, Dims d, int cap, int max_rows, int max_pts, short2* __restrict__ pts,
+                               int* __restrict__ npts) {
+    const int b = blockIdx.y;
+    const int row = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n = min(counts[b], max_rows);
+    if (row >= n) return;
+    const cvb_inst_row r = table[(long long)b * max_rows + row];
+    int* out_n = npts + (long long)b * max_rows + row;
+    if (r.id >= cap || ncomp[(long long)b * cap + r.id] != 1) { *out_n = -1; return; }
+    const int* lt = labels + (long long)b * d.N;
+    short2* out = pts + ((long long)b * max_rows + row) * max_pts;
+    const int id = r.id, W = d.W, H = d.H;
+    auto in = [&](int y, int x) { return y >= 0 && y < H && x >= 0 && x < W && lt[y * W + x] == id; };
+    const int dx[8] = {1, 1, 0, -1, -1, -1, 0, 1}, dy[8] = {0, -1, -1, -1, 0, 1, 1, 1};
+    int y0 = r.rmin, x0 = r.cmin;
+    while (x0 < r.cmax && !in(y0, x0)) ++x0;  // raster-first pixel: left-most pixel of the top bbox row
+    int s = 4, s_end = 4;
+    bool found = false;
+    do {
+        s = (s - 1) & 7;
+        if (in(y0 + dy[s], x0 + dx[s])) { found = true; break; }
+    } while (s != s_end);
+    if (!found) {  // isolated pixel
+        out[0] = make_short2((short)x0, (short)y0);
+        *out_n = 1;
+        return;
+    }
+    const int y1 = y0 + dy[s], x1 = x0 + dx[s];
+    int y3 = y0, x3 = x0, prev_s = s ^ 4, k = 0;
+    for (int guard = 0; guard < 4 * (H + W) * 8; ++guard) {
+        int y4, x4;
+        for (;;) {
+            ++s;
+            y4 = y3 + dy[s & 7];
+            x4 = x3 + dx[s & 7];
+            if (in(y4, x4)) break;
+        }
+        s &= 7;
+        if (s != prev_s) {
+            if (k < max_pts) out[k] = make_short2((short)x3, (short)y3);
+            ++k;
+        }
+        prev_s = s;
+        if (y4 == y0 && x4 == x0 && y3 == y1 && x3 == x1) break;
+        y3 = y4; x3 = x4;
+        s = (s + 4) & 7;
+    }
+    *out_n = k <= max_pts ? k : -1;
+}
+
 // ------------------------------------------------------------------------------------------ host orchestration
 void sobel_taps_host(int ksize, SobelTaps* t) {
     // cv::getSobelKernels for ksize > 7 (integer recurrences), orders 1 and 0
@@ -939,4 +1031,38 @@ CVB_API int cvb_postproc_maps(const uint8_t* np_bin, const float* hv, const int3
     if (type_map) prep_maps_kernel<<<grid1d((long long)B * d.N), 256, 0, st>>>(type_map, (long long)B * d.N, w.tmap);
     return run_pipeline(w, hv, d, n_types, object_size, ksize, type_map != nullptr, labels, table, counts, max_rows, dbg_blb, dbg_dist,
                         dbg_marker, st);
+}
+
+CVB_API int cvb_contours_workspace_bytes(int B, int H, int W, size_t* out) {
+    CVB_CHECK(out && B > 0 && H > 0 && W > 0, CVB_EARG, "cvb_contours_workspace_bytes: bad arguments");
+    *out = align_up((size_t)B * H * W * 4, 256) + align_up((size_t)B * (H * W / 8 + 16) * 4, 256) + 4096;
+    return CVB_OK;
+}
+
+// Contours of the instances listed in table[b, :counts[b]] traced on the device label maps.
+// pts int16 (x,y) pairs [B, max_rows, max_pts]; npts int32 [B, max_rows]: number of points, or -1 when the instance
+// must be resolved on the host (several 8-connected components, or more than max_pts points).
+CVB_API int cvb_contours(const int32_t* labels, const cvb_inst_row* table, const int32_t* counts, int B, int H, int W, int max_rows,
+                         int max_pts, int16_t* pts, int32_t* npts, void* workspace, size_t ws_bytes, void* stream) {
+    CVB_CHECK(labels && table && counts && pts && npts && workspace, CVB_EARG, "cvb_contours: null argument");
+    CVB_CHECK(H < 32768 && W < 32768 && max_rows > 0 && max_pts > 0, CVB_ESHAPE, "cvb_contours: bad shape");
+    size_t need = 0;
+    CVB_TRY(cvb_contours_workspace_bytes(B, H, W, &need));
+    CVB_CHECK(ws_bytes >= need && ((uintptr_t)workspace & 255) == 0, CVB_EWORKSPACE, "cvb_contours: workspace %zu < %zu or unaligned", ws_bytes, need);
+    const Dims d{B, H, W, H * W};
+    const int cap = H * W / 8 + 16;
+    int* L = reinterpret_cast<int*>(workspace);
+    int* ncomp = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(workspace) + align_up((size_t)B * d.N * 4, 256));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int g = grid1d((long long)B * d.N);
+    CVB_CUDA(cudaMemsetAsync(ncomp, 0, (size_t)B * cap * 4, st));
+    lab8_init_kernel<<<g, 256, 0, st>>>(labels, d, L);
+    lab8_merge_kernel<<<g, 256, 0, st>>>(labels, d, L);
+    ccl_compress_kernel<<<g, 256, 0, st>>>(d, L);
+    lab8_count_kernel<<<g, 256, 0, st>>>(labels, L, d, cap, ncomp);
+    contour_kernel<<<dim3((max_rows + 63) / 64, B), 64, 0, st>>>(labels, table, counts, ncomp, d, cap, max_rows, max_pts,
+                                                               reinterpret_cast<short2*>(pts), npts);
+    cvb_note_launches(5);
+    CVB_CUDA(cudaGetLastError());
+    return CVB_OK;
 }

@@ -54,7 +54,7 @@ __device__ __forceinline__ int map_out_row(const TcEpilogue& e, int m) {
 
 __device__ __forceinline__ float apply_act(float v, int act) {
     if (act == TC_ACT_RELU) return fmaxf(v, 0.0f);
-    if (act == TC_ACT_GELU) return gelu_erf(v);
+    if (act == TC_ACT_GELU) return gelu_erf_fast(v);
     return v;
 }
 
@@ -294,18 +294,22 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUte
                     }
                 } else if (e.kind == TC_EPI_RES_F32) {
                     float* o = reinterpret_cast<float*>(e.out) + out_off + nb;
+                    // all residual loads first: `res` may alias `out`, so the compiler cannot hoist them over the
+                    // stores itself and the chunk would pay eight dependent memory round trips instead of one
+                    float4 rv[8];
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        float4 rv = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (res_row) rv = *reinterpret_cast<const float4*>(res_row + nb + j);
+                    for (int j = 0; j < 8; ++j)
+                        rv[j] = res_row ? *reinterpret_cast<const float4*>(res_row + nb + 4 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
                         float4 sv = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (e.shift) sv = __ldg(reinterpret_cast<const float4*>(e.shift + nb + j));
+                        if (e.shift) sv = __ldg(reinterpret_cast<const float4*>(e.shift + nb + 4 * j));
                         float4 ov;
-                        ov.x = __uint_as_float(acc[j + 0]) + sv.x + rv.x;
-                        ov.y = __uint_as_float(acc[j + 1]) + sv.y + rv.y;
-                        ov.z = __uint_as_float(acc[j + 2]) + sv.z + rv.z;
-                        ov.w = __uint_as_float(acc[j + 3]) + sv.w + rv.w;
-                        *reinterpret_cast<float4*>(o + j) = ov;
+                        ov.x = __uint_as_float(acc[4 * j + 0]) + sv.x + rv[j].x;
+                        ov.y = __uint_as_float(acc[4 * j + 1]) + sv.y + rv[j].y;
+                        ov.z = __uint_as_float(acc[4 * j + 2]) + sv.z + rv[j].z;
+                        ov.w = __uint_as_float(acc[4 * j + 3]) + sv.w + rv[j].w;
+                        *reinterpret_cast<float4*>(o + 4 * j) = ov;
                     }
                 } else {  // TC_EPI_CONVT: 32 consecutive n share (dy,dx) because Cout % 32 == 0
                     const int q = nb / e.ct_cout, co = nb - q * e.ct_cout;

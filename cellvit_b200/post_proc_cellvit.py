@@ -2,9 +2,11 @@
 """Drop-in mirror of the reference post-processor (cell_segmentation/utils/post_proc_cellvit.py:33-153) whose
 stages P1-P9 run on the GPU through ``cvb_postproc`` / ``cvb_postproc_maps`` (csrc/postproc.cu).
 
-Only the contour of each instance (``cv2.findContours`` on the bbox crop, post_proc_cellvit.py:106-125) is still
-computed on the host from the device label map -- SURVEY.md section 8f row N1. There is no CPU fallback for the
-map stages: without libcellvit_b200.so or a CUDA device the calls raise.
+Instance contours (``cv2.findContours(crop, RETR_TREE, CHAIN_APPROX_SIMPLE)[0][0]``, post_proc_cellvit.py:106-125)
+are traced on the device as well (``cvb_contours``); the host only assembles the
+per-tile dicts, and calls cv2 itself for the rare instance the device flags (several 8-connected components, or
+more than MAX_PTS points). There is no CPU fallback for the map stages: without libcellvit_b200.so or a CUDA device
+the calls raise.
 """
 from __future__ import annotations
 
@@ -20,6 +22,8 @@ ROW_DTYPE = np.dtype([("id", "<i4"), ("rmin", "<i4"), ("cmin", "<i4"), ("rmax", 
                       ("area", "<i4"), ("type", "<i4"), ("type_prob_f", "<f4"), ("cx", "<f8"), ("cy", "<f8"),
                       ("type_prob", "<f8"), ("hist", "<i4", (8,))])
 assert ROW_DTYPE.itemsize == 88
+MAX_PTS = 128       # contour points kept per instance on the device (longer contours fall back to cv2)
+ROWS_COPIED = 2048  # table / contour rows copied to the host eagerly per tile (more instances: second copy)
 
 
 def magnification_params(magnification, gt: bool = False):
@@ -46,6 +50,33 @@ class _Workspace:
         self.labels = torch.empty(B, H, W, dtype=torch.int32, device=device)
         self.table = torch.empty(B, max_rows, ROW_DTYPE.itemsize, dtype=torch.uint8, device=device)
         self.counts = torch.empty(B, dtype=torch.int32, device=device)
+        L.check(L.lib().cvb_contours_workspace_bytes(B, H, W, C.byref(need)), "cvb_contours_workspace_bytes")
+        self.cws = torch.empty(need.value, dtype=torch.uint8, device=device)
+        self.pts = torch.empty(B, max_rows, MAX_PTS, 2, dtype=torch.int16, device=device)
+        self.npts = torch.empty(B, max_rows, dtype=torch.int32, device=device)
+        # two pinned host slots so that the host can finish batch k while the device runs batch k+1
+        self.host = [dict(labels=torch.empty(B, H, W, dtype=torch.int32).pin_memory(),
+                          table=torch.empty(B, max_rows, ROW_DTYPE.itemsize, dtype=torch.uint8).pin_memory(),
+                          pts=torch.empty(B, max_rows, MAX_PTS, 2, dtype=torch.int16).pin_memory(),
+                          npts=torch.empty(B, max_rows, dtype=torch.int32).pin_memory(),
+                          counts=torch.empty(B, dtype=torch.int32).pin_memory(), event=None) for _ in range(2)]
+
+    def launch_contours(self, B, H, W, max_rows):
+        L.check(L.lib().cvb_contours(L.ptr(self.labels), L.ptr(self.table), L.ptr(self.counts), B, H, W, max_rows, MAX_PTS,
+                                     L.ptr(self.pts), L.ptr(self.npts), L.ptr(self.cws), C.c_size_t(self.cws.numel()), L.stream_ptr()),
+                "cvb_contours")
+
+    def copy_to_host(self, slot, n_rows):
+        h = self.host[slot]
+        h["labels"].copy_(self.labels, non_blocking=True)
+        h["counts"].copy_(self.counts, non_blocking=True)
+        h["table"][:, :n_rows].copy_(self.table[:, :n_rows], non_blocking=True)
+        h["pts"][:, :n_rows].copy_(self.pts[:, :n_rows], non_blocking=True)
+        h["npts"][:, :n_rows].copy_(self.npts[:, :n_rows], non_blocking=True)
+        h["rows_copied"] = n_rows
+        h["event"] = torch.cuda.Event()
+        h["event"].record()
+        return h
 
 
 class DetectionCellPostProcessor:
@@ -101,6 +132,41 @@ class DetectionCellPostProcessor:
                                          L.ptr(w.ws), C.c_size_t(w.ws.numel()), L.stream_ptr()), "cvb_postproc")
             return w.labels, self._rows(w)
 
+    # ------------------------------------------------------------------ asynchronous (pipelined) use
+    def launch_float(self, np_map: torch.Tensor, hv: torch.Tensor, nt_map: torch.Tensor, slot: int, table_rows: int = ROWS_COPIED):
+        """Enqueue cvb_postproc and the D2H copies of its results into pinned host slot ``slot`` (0/1) on the current
+        stream; returns immediately. ``collect(slot)`` waits for that slot and builds the per-tile dicts."""
+        B, _, H, W = np_map.shape
+        with torch.cuda.device(np_map.device):
+            w = self._workspace(B, H, W, np_map.device)
+            nt = nt_map if self.nr_types is not None else None
+            L.check(L.lib().cvb_postproc(L.ptr(np_map), L.ptr(hv), L.ptr(nt), B, H, W, 0 if nt is None else nt.shape[1],
+                                         int(self.magnification), L.ptr(w.labels), L.ptr(w.table), L.ptr(w.counts), self.max_rows,
+                                         L.ptr(w.ws), C.c_size_t(w.ws.numel()), L.stream_ptr()), "cvb_postproc")
+            w.launch_contours(B, H, W, self.max_rows)
+            w.copy_to_host(slot, min(table_rows, self.max_rows))
+
+    def collect(self, slot: int, pool=None) -> Tuple[np.ndarray, List[dict]]:
+        """Wait for host slot ``slot`` and assemble the per-tile instance dicts (reference layout)."""
+        w = self._wsp
+        h = w.host[slot]
+        h["event"].synchronize()
+        counts = h["counts"].numpy()
+        if (counts > self.max_rows).any():
+            raise L.CvbError(f"instance table overflow: {int(counts.max())} rows needed, max_rows={self.max_rows}")
+        if (counts > h["rows_copied"]).any():  # rare: more instances than the eagerly copied prefix
+            h["table"].copy_(w.table); h["pts"].copy_(w.pts); h["npts"].copy_(w.npts)
+        lab, tab, pts, npts = h["labels"].numpy(), h["table"].numpy(), h["pts"].numpy(), h["npts"].numpy()
+        with_types = self.nr_types is not None
+
+        def one(b):
+            n = int(counts[b])
+            rows = np.frombuffer(tab[b, :n].tobytes(), dtype=ROW_DTYPE)
+            return self.rows_to_dict(lab[b], rows, with_types, pts[b, :n], npts[b, :n])
+
+        dicts = [one(b) for b in range(len(counts))] if pool is None else list(pool.map(one, range(len(counts))))
+        return lab, dicts
+
     def _rows(self, w: _Workspace) -> List[np.ndarray]:
         counts = w.counts.cpu().numpy()  # synchronises the stream
         if (counts > self.max_rows).any():
@@ -111,34 +177,47 @@ class DetectionCellPostProcessor:
 
     # ------------------------------------------------------------------ host glue (contours, dict format)
     @staticmethod
-    def rows_to_dict(labels: np.ndarray, rows: np.ndarray, with_types: bool = True) -> dict:
-        """Instance table -> the reference's per-tile dict (post_proc_cellvit.py:96-151)."""
-        import cv2
+    def rows_to_dict(labels: np.ndarray, rows: np.ndarray, with_types: bool = True, pts: np.ndarray = None,
+                     npts: np.ndarray = None) -> dict:
+        """Instance table (+ device contours) -> the reference's per-tile dict (post_proc_cellvit.py:96-151).
+        Without device contours, or for instances the device flagged (npts < 0), the contour comes from cv2."""
         out = {}
-        for r in rows:
-            rmin, cmin, rmax, cmax = int(r["rmin"]), int(r["cmin"]), int(r["rmax"]), int(r["cmax"])
-            crop = (labels[rmin:rmax, cmin:cmax] == r["id"]).astype(np.uint8)
-            cnts = cv2.findContours(crop, cv2.RETR_TREE, cv2.CHAIN_APPROX_SIMPLE)
-            contour = np.squeeze(cnts[0][0].astype("int32"))
-            if contour.shape[0] < 3 or contour.ndim != 2:
-                continue
-            contour[:, 0] += cmin
-            contour[:, 1] += rmin
-            out[np.int32(r["id"])] = {
+        ids, rmin_, cmin_, rmax_, cmax_ = (rows[k].tolist() for k in ("id", "rmin", "cmin", "rmax", "cmax"))
+        cx, cy, tp, ty = rows["cx"].tolist(), rows["cy"].tolist(), rows["type_prob"].tolist(), rows["type"].tolist()
+        nn = npts.tolist() if npts is not None else None
+        pts32 = pts.astype(np.int32) if pts is not None else None
+        for i, inst_id in enumerate(ids):
+            rmin, cmin, rmax, cmax = rmin_[i], cmin_[i], rmax_[i], cmax_[i]
+            if nn is not None and nn[i] >= 0:
+                if nn[i] < 3:
+                    continue  # "< 3 points dont make a contour" (post_proc_cellvit.py:110-113)
+                contour = pts32[i, :nn[i]].copy()
+            else:
+                import cv2
+                crop = (labels[rmin:rmax, cmin:cmax] == inst_id).astype(np.uint8)
+                cnts = cv2.findContours(crop, cv2.RETR_TREE, cv2.CHAIN_APPROX_SIMPLE)
+                contour = np.squeeze(cnts[0][0].astype("int32"))
+                if contour.shape[0] < 3 or contour.ndim != 2:
+                    continue
+                contour[:, 0] += cmin
+                contour[:, 1] += rmin
+            out[np.int32(inst_id)] = {
                 "bbox": np.array([[rmin, cmin], [rmax, cmax]]),
-                "centroid": np.array([r["cx"], r["cy"]]),
+                "centroid": np.array([cx[i], cy[i]]),
                 "contour": contour,
-                "type_prob": float(r["type_prob"]) if with_types else None,
-                "type": int(r["type"]) if with_types else None,
+                "type_prob": tp[i] if with_types else None,
+                "type": ty[i] if with_types else None,
             }
         return out
 
     def post_process_batch(self, np_map: torch.Tensor, hv_map: torch.Tensor, nt_map: torch.Tensor) -> Tuple[torch.Tensor, List[dict]]:
         """Batched device path used by ``CellViT.calculate_instance_map`` (cellvit.py:360-381)."""
-        labels, rows = self.run_float(np_map, hv_map, nt_map if self.nr_types is not None else None)
-        lab_host = labels.cpu().numpy()
-        dicts = [self.rows_to_dict(lab_host[b], rows[b], self.nr_types is not None) for b in range(lab_host.shape[0])]
-        return labels, dicts
+        if not np_map.is_cuda:
+            raise RuntimeError("cellvit_b200 has no CPU path: post-processing inputs must be CUDA tensors")
+        self.launch_float(np_map.contiguous().float(), hv_map.contiguous().float(),
+                          None if nt_map is None else nt_map.contiguous().float(), slot=0)
+        _, dicts = self.collect(0)
+        return self._wsp.labels, dicts
 
     def post_process_cell_segmentation(self, pred_map: np.ndarray) -> Tuple[np.ndarray, dict]:
         """Reference signature (post_proc_cellvit.py:67-153): pred_map [H,W,4] = (type, np, h, v) or [H,W,3]."""
@@ -152,5 +231,10 @@ class DetectionCellPostProcessor:
         np_bin = torch.from_numpy(np.ascontiguousarray((pred[..., 0] >= 0.5).astype(np.uint8)))[None].cuda()
         hv = torch.from_numpy(np.ascontiguousarray(pred[..., 1:3].transpose(2, 0, 1)))[None].cuda()
         labels, rows, _ = self.run_maps(np_bin, hv, pred_type)
+        w = self._wsp
+        H, W = np_bin.shape[-2:]
+        w.launch_contours(1, H, W, self.max_rows)
+        n = len(rows[0])
         lab = labels[0].cpu().numpy()
-        return lab, self.rows_to_dict(lab, rows[0], self.nr_types is not None)
+        return lab.copy(), self.rows_to_dict(lab, rows[0], self.nr_types is not None, w.pts[0, :max(n, 1)].cpu().numpy()[:n],
+                                             w.npts[0, :max(n, 1)].cpu().numpy()[:n])

@@ -139,3 +139,70 @@ def test_against_reference_golden(path):
 def test_unknown_magnification_raises():
     with pytest.raises(NotImplementedError, match="Unknown magnification"):
         DetectionCellPostProcessor(nr_types=6, magnification=10)
+
+
+def _device_contours(lab, type_map=None):
+    """cvb_contours on a hand-made label map, with the table built by the oracle (same row layout)."""
+    import ctypes as C
+    import cv2
+    from cellvit_b200 import _lib as L
+    from cellvit_b200.post_proc_cellvit import MAX_PTS
+    H, W = lab.shape
+    rows = po.instance_table(lab, type_map, 0)
+    n = len(rows)
+    max_rows = max(n, 1)
+    labels = torch.from_numpy(lab.astype(np.int32))[None].cuda()
+    table = torch.from_numpy(np.frombuffer(rows.tobytes(), np.uint8).copy()).cuda().view(1, max_rows if n else 0, 88) if n else torch.zeros(1, 1, 88, dtype=torch.uint8).cuda()
+    counts = torch.tensor([n], dtype=torch.int32).cuda()
+    pts = torch.full((1, max_rows, MAX_PTS, 2), -7, dtype=torch.int16).cuda()
+    npts = torch.full((1, max_rows), -9, dtype=torch.int32).cuda()
+    need = C.c_size_t()
+    L.check(L.lib().cvb_contours_workspace_bytes(1, H, W, C.byref(need)), "ws")
+    ws = torch.empty(need.value, dtype=torch.uint8).cuda()
+    L.check(L.lib().cvb_contours(L.ptr(labels), L.ptr(table), L.ptr(counts), 1, H, W, max_rows, MAX_PTS, L.ptr(pts), L.ptr(npts), L.ptr(ws),
+                                 C.c_size_t(ws.numel()), L.stream_ptr()), "cvb_contours")
+    torch.cuda.synchronize()
+    ref = {}
+    for r in rows:
+        crop = (lab[r["rmin"]:r["rmax"], r["cmin"]:r["cmax"]] == r["id"]).astype(np.uint8)
+        c = cv2.findContours(crop, cv2.RETR_TREE, cv2.CHAIN_APPROX_SIMPLE)[0][0].reshape(-1, 2).astype(np.int32)
+        ref[int(r["id"])] = c + np.array([r["cmin"], r["rmin"]], np.int32)
+    return rows, pts[0].cpu().numpy().astype(np.int32), npts[0].cpu().numpy(), ref
+
+
+def test_device_contours_match_cv2_and_flag_what_they_cannot_do():
+    from scipy import ndimage
+    rng = np.random.default_rng(3)
+    H = W = 160
+    lab = np.zeros((H, W), np.int32)
+    lab[0, 0] = 0
+    nid = 1  # id 1 is the dropped "first unique value" only when there is no background; here background exists
+    expect_flag = set()
+    # random single-component blobs with holes, lines, single pixels on a 16-px grid
+    for gy in range(0, H - 16, 16):
+        for gx in range(0, W - 16, 16):
+            h, w = rng.integers(1, 14, 2)
+            m = rng.random((h, w)) < rng.uniform(0.4, 0.95)
+            cc, nc = ndimage.label(m, structure=np.ones((3, 3)))
+            if nc == 0:
+                continue
+            keep = cc == 1 + int(np.argmax(ndimage.sum(m, cc, range(1, nc + 1))))
+            if rng.random() < 0.15 and nc > 1:      # sometimes keep two components under one id -> must be flagged
+                keep = cc > 0
+                if ndimage.label(keep, structure=np.ones((3, 3)))[1] > 1:
+                    expect_flag.add(nid)
+            lab[gy + 1:gy + 1 + h, gx + 1:gx + 1 + w][keep] = nid
+            nid += 1
+    # one contour longer than MAX_PTS: a comb
+    comb = np.zeros((12, 150), bool); comb[0] = True; comb[:, ::2] = True
+    lab2 = np.zeros((H, W), np.int32); lab2[20:32, 5:155][comb] = 1; lab2[60:63, 60:64] = 2
+    for L_, flags in ((lab, expect_flag), (lab2, {1})):
+        rows, pts, npts, ref = _device_contours(L_)
+        assert len(rows) > 1
+        for i, r in enumerate(rows):
+            rid = int(r["id"])
+            if rid in flags:
+                assert npts[i] == -1, rid
+            else:
+                assert npts[i] == len(ref[rid]), (rid, npts[i], len(ref[rid]))
+                assert np.array_equal(pts[i, :npts[i]], ref[rid]), rid
