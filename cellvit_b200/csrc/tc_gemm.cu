@@ -58,6 +58,11 @@ __device__ __forceinline__ float apply_act(float v, int act) {
     return v;
 }
 
+// PAIR: the two CTAs of a cluster (one TPC) run one 256 x block_n tile with tcgen05.mma.cta_group::2 -- each CTA
+// stages its own 128 rows of A and HALF of the B tile, so the L2 -> SM operand traffic per FLOP drops by a third
+// (the tile engine is bound by that feed, ~53 B/clk/SM, not by the tensor pipe). Only the leader CTA issues MMAs;
+// TMA completions of both CTAs land on the leader's full barrier; tcgen05.commit multicasts to both CTAs.
+template <bool PAIR>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
           const __grid_constant__ CUtensorMap tmB, const TcParams p) {
@@ -67,7 +72,12 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUte
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int stages = p.stages;
-    const uint32_t b_stage_bytes = (uint32_t)p.block_n * BLOCK_K * 2;
+    const uint32_t rank = PAIR ? ptx::cluster_ctarank() : 0u;
+    const int tile0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int tile_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    constexpr int TILE_M = PAIR ? 2 * BLOCK_M : BLOCK_M;
+    const int b_rows = PAIR ? p.block_n / 2 : p.block_n;  // B rows staged by this CTA
+    const uint32_t b_stage_bytes = (uint32_t)b_rows * BLOCK_K * 2;
     const uint32_t smem_a = smem_base;
     const uint32_t smem_b = smem_a + stages * A_STAGE_BYTES;
     const uint32_t bar_base = smem_b + stages * b_stage_bytes;
@@ -87,18 +97,18 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUte
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < stages; ++s) {
-            ptx::mbar_init(full_bar(s), 1);
+            ptx::mbar_init(full_bar(s), PAIR ? 2 : 1);
             ptx::mbar_init(empty_bar(s), 1);
         }
         for (int s = 0; s < 2; ++s) {
             ptx::mbar_init(tfull_bar(s), 1);
-            ptx::mbar_init(tempty_bar(s), NUM_THREADS - 128);
+            ptx::mbar_init(tempty_bar(s), (PAIR ? 2 : 1) * (NUM_THREADS - 128));
         }
         ptx::fence_barrier_init();
     }
     if (warp == 2) {
-        ptx::tmem_alloc(tmem_slot, p.tmem_cols);
-        ptx::tmem_relinquish();
+        if (PAIR) { ptx::tmem_alloc_pair(tmem_slot, p.tmem_cols); ptx::tmem_relinquish_pair(); }
+        else { ptx::tmem_alloc(tmem_slot, p.tmem_cols); ptx::tmem_relinquish(); }
     }
     if (p.epi.kind == TC_EPI_HEAD && warp >= 4) {
         const int t = threadIdx.x - 128;
@@ -106,7 +116,7 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUte
         if (t < p.epi.head_nc) head_w_s[8 * 64 + t] = p.epi.head_b[t];
     }
     ptx::tc_fence_before();
-    __syncthreads();
+    if (PAIR) ptx::cluster_sync(); else __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
 
@@ -116,10 +126,10 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUte
         // ===================================================== TMA producer
         int stage = 0;
         uint32_t phase = 0;
-        const uint32_t tx_bytes = A_STAGE_BYTES + b_stage_bytes;
-        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        const uint32_t tx_bytes = (PAIR ? 2u : 1u) * (A_STAGE_BYTES + b_stage_bytes);
+        for (int tile = tile0; tile < p.n_tiles; tile += tile_step) {
             const int mt = tile / p.n_tiles_n, nt = tile - mt * p.n_tiles_n;
-            const int m0 = mt * BLOCK_M, n0 = nt * p.block_n;
+            const int m0 = mt * TILE_M + (int)rank * BLOCK_M, n0 = nt * p.block_n + (int)rank * b_rows;
             int img = 0, y0 = 0, x0 = 0;
             if (p.conv) {
                 const int hw = p.H * p.W;
@@ -130,34 +140,41 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUte
             }
             for (int kb = 0; kb < num_kb; ++kb) {
                 ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
-                ptx::mbar_expect_tx(full_bar(stage), tx_bytes);
+                if (!PAIR || rank == 0) ptx::mbar_expect_tx(full_bar(stage), tx_bytes);
                 const uint32_t dst_a = smem_a + stage * A_STAGE_BYTES;
-                if (!p.conv) {
-                    ptx::tma_load_2d(dst_a, &tmA0, full_bar(stage), kb * BLOCK_K, m0);
-                } else {
+                const CUtensorMap* ta = &tmA0;
+                int c0 = kb * BLOCK_K, dx = 0, dy = 0;
+                if (p.conv) {
                     const int tap = kb / p.chunks_per_tap;
                     const int cc = kb - tap * p.chunks_per_tap;
-                    const int dy = tap / 3 - 1, dx = tap - (tap / 3) * 3 - 1;
-                    if (cc < p.chunks0)
-                        ptx::tma_load_4d(dst_a, &tmA0, full_bar(stage), cc * BLOCK_K, x0 + dx, y0 + dy, img);
-                    else
-                        ptx::tma_load_4d(dst_a, &tmA1, full_bar(stage), (cc - p.chunks0) * BLOCK_K, x0 + dx, y0 + dy,
-                                         img);
+                    dy = tap / 3 - 1;
+                    dx = tap - (tap / 3) * 3 - 1;
+                    if (cc < p.chunks0) c0 = cc * BLOCK_K;
+                    else { ta = &tmA1; c0 = (cc - p.chunks0) * BLOCK_K; }
                 }
-                ptx::tma_load_2d(smem_b + stage * b_stage_bytes, &tmB, full_bar(stage), kb * BLOCK_K, n0);
+                if (PAIR) {
+                    if (!p.conv) ptx::tma_load_2d_pair(dst_a, ta, full_bar(stage), c0, m0);
+                    else ptx::tma_load_4d_pair(dst_a, ta, full_bar(stage), c0, x0 + dx, y0 + dy, img);
+                    ptx::tma_load_2d_pair(smem_b + stage * b_stage_bytes, &tmB, full_bar(stage), kb * BLOCK_K, n0);
+                    if (rank != 0) ptx::mbar_arrive_cluster(full_bar(stage), 0);
+                } else {
+                    if (!p.conv) ptx::tma_load_2d(dst_a, ta, full_bar(stage), c0, m0);
+                    else ptx::tma_load_4d(dst_a, ta, full_bar(stage), c0, x0 + dx, y0 + dy, img);
+                    ptx::tma_load_2d(smem_b + stage * b_stage_bytes, &tmB, full_bar(stage), kb * BLOCK_K, n0);
+                }
                 if (++stage == stages) { stage = 0; phase ^= 1u; }
             }
         }
-    } else if (warp == 1 && lane == 0) {
-        // ===================================================== MMA issuer
+    } else if (warp == 1 && lane == 0 && rank == 0) {
+        // ===================================================== MMA issuer (leader CTA only in PAIR mode)
         // instruction descriptor: D=f32, A=B=f16, both K-major, N>>3 @17, M>>4 @24
-        const uint32_t idesc = (1u << 4) | ((uint32_t)(p.block_n >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+        const uint32_t idesc = (1u << 4) | ((uint32_t)(p.block_n >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
         // smem matrix descriptor: SWIZZLE_128B (2 @61), version 1 @46, SBO = 1024 B (8 rows x 128 B), LBO unused
         const uint64_t desc_hi = (2ull << 61) | (1ull << 46) | ((uint64_t)(1024 >> 4) << 32);
         int stage = 0;
         uint32_t phase = 0;
         int it = 0;
-        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+        for (int tile = tile0; tile < p.n_tiles; tile += tile_step, ++it) {
             const int as = it & 1;
             const uint32_t aphase = (it >> 1) & 1;
             ptx::mbar_wait(tempty_bar(as), aphase ^ 1u);
@@ -169,10 +186,17 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUte
                 const uint64_t a_desc = desc_hi | (uint64_t)(((smem_a + stage * A_STAGE_BYTES) >> 4) & 0x3FFF);
                 const uint64_t b_desc = desc_hi | (uint64_t)(((smem_b + stage * b_stage_bytes) >> 4) & 0x3FFF);
 #pragma unroll
-                for (int k = 0; k < BLOCK_K / 16; ++k)  // 16 fp16 = 32 B -> +2 in the (addr >> 4) field
-                    ptx::umma_f16(d_tmem, a_desc + 2u * k, b_desc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
-                ptx::umma_commit(empty_bar(stage));
-                if (kb == num_kb - 1) ptx::umma_commit(tfull_bar(as));
+                for (int k = 0; k < BLOCK_K / 16; ++k) {  // 16 fp16 = 32 B -> +2 in the (addr >> 4) field
+                    if (PAIR) ptx::umma_f16_pair(d_tmem, a_desc + 2u * k, b_desc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                    else ptx::umma_f16(d_tmem, a_desc + 2u * k, b_desc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                }
+                if (PAIR) {
+                    ptx::umma_commit_pair(empty_bar(stage), 3);
+                    if (kb == num_kb - 1) ptx::umma_commit_pair(tfull_bar(as), 3);
+                } else {
+                    ptx::umma_commit(empty_bar(stage));
+                    if (kb == num_kb - 1) ptx::umma_commit(tfull_bar(as));
+                }
                 if (++stage == stages) { stage = 0; phase ^= 1u; }
             }
         }
@@ -186,11 +210,16 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUte
         const int n_chunks = p.block_n / 32;  // block_n % 32 == 0 enforced on the host
         const int last_c = n_chunks - 1 - (((n_chunks - 1) & 1) != half ? 1 : 0);  // last chunk of this warp (may be < 0)
         int it = 0;
-        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+        auto release_tmem = [&](int as_) {
+            ptx::tc_fence_before();
+            if (PAIR) ptx::mbar_arrive_cluster(tempty_bar(as_), 0);
+            else ptx::mbar_arrive(tempty_bar(as_));
+        };
+        for (int tile = tile0; tile < p.n_tiles; tile += tile_step, ++it) {
             const int as = it & 1;
             const uint32_t aphase = (it >> 1) & 1;
             const int mt = tile / p.n_tiles_n, nt = tile - mt * p.n_tiles_n;
-            const int m = mt * BLOCK_M + r, n0 = nt * p.block_n;
+            const int m = mt * TILE_M + (int)rank * BLOCK_M + r, n0 = nt * p.block_n;
             const bool row_ok = m < p.M;
             ptx::mbar_wait(tfull_bar(as), aphase);
             ptx::tc_fence_after();
@@ -198,8 +227,7 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUte
 
             if (e.kind == TC_EPI_HEAD) {
                 if (half != 0) {  // the fused 1x1 head needs all 64 channels of a pixel in one thread
-                    ptx::tc_fence_before();
-                    ptx::mbar_arrive(tempty_bar(as));
+                    release_tmem(as);
                     continue;
                 }
                 float hs[8];
@@ -210,10 +238,7 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUte
                     uint32_t acc[32];
                     ptx::tmem_ld32(t_addr + c * 32, acc);
                     ptx::tmem_ld_wait();
-                    if (c == 1) {
-                        ptx::tc_fence_before();
-                        ptx::mbar_arrive(tempty_bar(as));
-                    }
+                    if (c == 1) release_tmem(as);
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
                         const int n = c * 32 + j;
@@ -253,19 +278,13 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUte
                 const long long rr = e.res_mod > 0 ? (long long)(m % e.res_mod) + e.res_off : (long long)orow;
                 res_row = e.res + rr * e.ldres;
             }
-            if (last_c < 0) {
-                ptx::tc_fence_before();
-                ptx::mbar_arrive(tempty_bar(as));
-            }
+            if (last_c < 0) release_tmem(as);
 
             for (int c = half; c < n_chunks; c += 2) {
                 uint32_t acc[32];
                 ptx::tmem_ld32(t_addr + c * 32, acc);
                 ptx::tmem_ld_wait();
-                if (c == last_c) {
-                    ptx::tc_fence_before();
-                    ptx::mbar_arrive(tempty_bar(as));
-                }
+                if (c == last_c) release_tmem(as);
                 if (orow < 0) continue;
                 const int nb = n0 + c * 32;
                 if (e.kind == TC_EPI_F16) {
@@ -335,9 +354,12 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUte
     }
 
     ptx::tc_fence_before();
-    __syncthreads();
+    if (PAIR) ptx::cluster_sync(); else __syncthreads();
     ptx::tc_fence_after();
-    if (warp == 2) ptx::tmem_dealloc(tmem_base, p.tmem_cols);
+    if (warp == 2) {
+        if (PAIR) ptx::tmem_dealloc_pair(tmem_base, p.tmem_cols);
+        else ptx::tmem_dealloc(tmem_base, p.tmem_cols);
+    }
 }
 
 // ------------------------------------------------------------------------------------------- host side
@@ -393,8 +415,17 @@ struct TcProfile {
     double flops = 0.0;
 } g_prof;
 
-int launch(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, TcParams& p, cudaStream_t stream) {
-    const int b_stage = p.block_n * BLOCK_K * 2;
+bool g_pair_enabled = true;
+
+// pair mode needs at least two 256-row tiles per pair-CTA to pay off and an even B split in 16-row units
+bool use_pair(int M, int N, int block_n) {
+    if (!g_pair_enabled || block_n % 32 != 0) return false;
+    const long long pair_tiles = (long long)((M + 2 * BLOCK_M - 1) / (2 * BLOCK_M)) * (N / block_n);
+    return pair_tiles >= cvb_num_sms() / 2;
+}
+
+int launch(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, TcParams& p, bool pair, cudaStream_t stream) {
+    const int b_stage = (pair ? p.block_n / 2 : p.block_n) * BLOCK_K * 2;
     int stages = SMEM_BUDGET / (A_STAGE_BYTES + b_stage);
     if (stages > MAX_STAGES) stages = MAX_STAGES;
     p.stages = stages;
@@ -405,17 +436,33 @@ int launch(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, T
     // one CTA (and one 512-column TMEM allocation) lives on an SM at a time.
     size_t smem = 1024 + (size_t)stages * (A_STAGE_BYTES + b_stage) + 8 * (2 * MAX_STAGES + 4) + 16 + (8 * 64 + 8) * 4;
     if (smem < 120 * 1024) smem = 120 * 1024;
-    static size_t configured = 0;
-    if (smem > configured) {
-        CVB_CUDA(cudaFuncSetAttribute(tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
-        configured = 227 * 1024;
+    static bool configured = false;
+    if (!configured) {
+        CVB_CUDA(cudaFuncSetAttribute(tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
+        CVB_CUDA(cudaFuncSetAttribute(tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
+        configured = true;
     }
     p.n_tiles_n = p.N / p.block_n;
-    p.n_tiles = cdiv(p.M, BLOCK_M) * p.n_tiles_n;
-    int grid = p.n_tiles < cvb_num_sms() ? p.n_tiles : cvb_num_sms();
+    p.n_tiles = cdiv(p.M, pair ? 2 * BLOCK_M : BLOCK_M) * p.n_tiles_n;
+    const int sms = cvb_num_sms();
+    int grid = pair ? 2 * (p.n_tiles < sms / 2 ? p.n_tiles : sms / 2) : (p.n_tiles < sms ? p.n_tiles : sms);
     const bool prof = g_prof.on && g_prof.used + 2 <= g_prof.ev.size();
     if (prof) CVB_CUDA(cudaEventRecord(g_prof.ev[g_prof.used], stream));
-    tc_kernel<<<grid, NUM_THREADS, smem, stream>>>(a0, a1, b, p);
+    if (pair) {
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(grid);
+        cfg.blockDim = dim3(NUM_THREADS);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        CVB_CUDA(cudaLaunchKernelEx(&cfg, tc_kernel<true>, a0, a1, b, p));
+    } else {
+        tc_kernel<false><<<grid, NUM_THREADS, smem, stream>>>(a0, a1, b, p);
+    }
     if (prof) {
         CVB_CUDA(cudaEventRecord(g_prof.ev[g_prof.used + 1], stream));
         g_prof.used += 2;
@@ -441,6 +488,7 @@ int tc_gemm(const __half* A, int M, int K, long long lda, const __half* W, int N
               "tc_gemm: K=%d must be a multiple of 64 and lda/ldw multiples of 8", K);
     CVB_CHECK(((uintptr_t)A & 15) == 0 && ((uintptr_t)W & 15) == 0, CVB_EARG, "tc_gemm: operands must be 16-byte aligned");
     CVB_TRY(check_epilogue(epi, N, block_n));
+    const bool pair = use_pair(M, N, block_n) && epi.kind != TC_EPI_HEAD;
     CUtensorMap ta, tb;
     {
         uint64_t dims[2] = {(uint64_t)K, (uint64_t)M};
@@ -451,12 +499,12 @@ int tc_gemm(const __half* A, int M, int K, long long lda, const __half* W, int N
     {
         uint64_t dims[2] = {(uint64_t)K, (uint64_t)N};
         uint64_t str[1] = {(uint64_t)ldw * 2};
-        uint32_t box[2] = {BLOCK_K, (uint32_t)block_n};
+        uint32_t box[2] = {BLOCK_K, (uint32_t)(pair ? block_n / 2 : block_n)};
         CVB_TRY(make_tmap(&tb, W, 2, dims, str, box));
     }
     TcParams p{};
     p.M = M; p.N = N; p.K = K; p.block_n = block_n; p.num_kb = K / BLOCK_K; p.conv = 0; p.epi = epi;
-    return launch(ta, ta, tb, p, stream);
+    return launch(ta, ta, tb, p, pair, stream);
 }
 
 int tc_conv3x3(const __half* src0, int C0, const __half* src1, int C1, int NB, int H, int W, const __half* Wp,
@@ -479,16 +527,17 @@ int tc_conv3x3(const __half* src0, int C0, const __half* src1, int C1, int NB, i
     CVB_TRY(mk(&t0, src0, C0));
     if (C1 > 0) CVB_TRY(mk(&t1, src1, C1)); else t1 = t0;
     const int K = 9 * (C0 + C1);
+    const bool pair = use_pair(NB * H * W, N, block_n) && (NB * H * W) % (2 * BLOCK_M) == 0;
     {
         uint64_t dims[2] = {(uint64_t)K, (uint64_t)N};
         uint64_t str[1] = {(uint64_t)K * 2};
-        uint32_t box[2] = {BLOCK_K, (uint32_t)block_n};
+        uint32_t box[2] = {BLOCK_K, (uint32_t)(pair ? block_n / 2 : block_n)};
         CVB_TRY(make_tmap(&tb, Wp, 2, dims, str, box));
     }
     TcParams p{};
     p.M = NB * H * W; p.N = N; p.K = K; p.block_n = block_n; p.num_kb = K / BLOCK_K; p.conv = 1;
     p.chunks0 = C0 / 64; p.chunks_per_tap = (C0 + C1) / 64; p.H = H; p.W = W; p.TW = TW; p.epi = epi;
-    return launch(t0, t1, tb, p, stream);
+    return launch(t0, t1, tb, p, pair, stream);
 }
 
 extern "C" __attribute__((visibility("default"))) int cvb_tc_profile_begin(int max_launches) {
@@ -519,3 +568,6 @@ extern "C" __attribute__((visibility("default"))) int cvb_tc_profile_end(double*
     if (flops) *flops = g_prof.flops;
     return CVB_OK;
 }
+
+// Test / ablation hook: 0 disables the CTA-pair (cta_group::2) path, 1 enables it (default).
+extern "C" __attribute__((visibility("default"))) void cvb_tc_set_pair_mode(int on) { g_pair_enabled = on != 0; }

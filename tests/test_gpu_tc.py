@@ -140,3 +140,54 @@ def test_conv3x3_fused_head():
     ref = F.relu(ref * scale[None, :, None, None] + shift[None, :, None, None])
     ref = F.conv2d(ref, hw[:, :, None, None], hb)
     assert (out - ref).abs().max().item() < 1e-3
+
+
+@pytest.mark.parametrize("M,K,N,bn", [(16384, 1280, 3840, 256), (19600, 1280, 1280, 256), (19000, 256, 512, 128), (37888, 128, 64, 64)])
+def test_cta_pair_mode_is_bit_identical_to_single_cta(M, K, N, bn):
+    g = torch.Generator(device="cuda").manual_seed(11)
+    A = (torch.randn(M, K, device="cuda", generator=g) * 0.5).half()
+    W = (torch.randn(N, K, device="cuda", generator=g) * 0.05).half()
+    shift = torch.randn(N, device="cuda", generator=g) * 0.1
+    outs = []
+    try:
+        for mode in (0, 1):
+            L.lib().cvb_tc_set_pair_mode(mode)
+            out = torch.full((M, N), float("nan"), device="cuda", dtype=torch.half)
+            epi = L.TcEpilogue(kind=L.EPI_F16, act=L.ACT_GELU, shift=shift.data_ptr(), out=out.data_ptr(), ldc=N)
+            _gemm(A, W, epi, bn)
+            outs.append(out)
+    finally:
+        L.lib().cvb_tc_set_pair_mode(1)
+    assert torch.isfinite(outs[1].float()).all()
+    assert torch.equal(outs[0], outs[1])
+    ref = F.gelu(A[:2048].float() @ W.float().t() + shift)
+    assert (outs[1][:2048].float() - ref).abs().max().item() <= 2e-3 * max(1.0, ref.abs().max().item())
+
+
+def test_cta_pair_mode_conv_and_head():
+    g = torch.Generator(device="cuda").manual_seed(12)
+    B, H, W, Cc, nc = 2, 256, 256, 64, 6
+    s0 = (torch.randn(B, H, W, Cc, device="cuda", generator=g) * 0.5).half()
+    s1 = (torch.randn(B, H, W, Cc, device="cuda", generator=g) * 0.5).half()
+    w = torch.randn(64, 2 * Cc, 3, 3, device="cuda", generator=g) * 0.03
+    Wp = _pack_conv_w(w)
+    scale = torch.rand(64, device="cuda", generator=g) + 0.5
+    shift = torch.randn(64, device="cuda", generator=g) * 0.1
+    hw = torch.randn(nc, 64, device="cuda", generator=g) * 0.1
+    hb = torch.randn(nc, device="cuda", generator=g) * 0.1
+    res = []
+    try:
+        for mode in (0, 1):
+            L.lib().cvb_tc_set_pair_mode(mode)
+            out = torch.full((B, nc, H, W), float("nan"), device="cuda")
+            epi = L.TcEpilogue(kind=L.EPI_HEAD, scale=scale.data_ptr(), shift=shift.data_ptr(), head_w=hw.data_ptr(), head_b=hb.data_ptr(),
+                               head_nc=nc, head_hw=H * W, head_out=out.data_ptr())
+            L.check(L.lib().cvb_op_conv3x3_f16(L.ptr(s0), Cc, L.ptr(s1), Cc, B, H, W, L.ptr(Wp), 64, 64, C.byref(epi), L.stream_ptr()), "conv-head")
+            torch.cuda.synchronize()
+            res.append(out)
+    finally:
+        L.lib().cvb_tc_set_pair_mode(1)
+    assert torch.equal(res[0], res[1])
+    ref = F.conv2d(torch.cat([s0, s1], -1).permute(0, 3, 1, 2).float(), Wp.view(64, 3, 3, 2 * Cc).permute(0, 3, 1, 2).float(), padding=1)
+    ref = F.conv2d(F.relu(ref * scale[None, :, None, None] + shift[None, :, None, None]), hw[:, :, None, None], hb)
+    assert (res[1] - ref).abs().max().item() < 1e-3
