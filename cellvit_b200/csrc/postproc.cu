@@ -586,7 +586,9 @@ watershed_kernel(const int* __restrict__ queue, const int* __restrict__ qcount_p
             for (int i = n_seed / 2 - 1; i >= 0; --i) hp.sift_down(i, hp.key[i], hp.pay[i].x, hp.pay[i].y);
         }
         __syncwarp();
-        // ---- flood: pop min; neighbours up, left, right, down; label at push time
+        // ---- flood: pop min; neighbours up, left, right, down; label at push time.
+        // One global round trip per pop: lanes 0..3 fetch mask / label / dist of their neighbour and lane 4 the
+        // label of the popped pixel, all in flight together.
         int age = 0;
         int hn = __shfl_sync(0xffffffffu, hp.n, 0);
         while (hn > 0) {
@@ -599,11 +601,13 @@ watershed_kernel(const int* __restrict__ queue, const int* __restrict__ qcount_p
             else if (lane == 1 && x > 0) q = p - 1;
             else if (lane == 2 && x < d.W - 1) q = p + 1;
             else if (lane == 3 && y < d.H - 1) q = p + d.W;
-            bool take = false;
+            int mq = 0, oq = 1;
             double qv = 0.0;
-            if (q >= 0 && m[q] && out[q] == 0) { take = true; qv = ds[q]; }
+            if (q >= 0) { mq = m[q]; oq = out[q]; qv = ds[q]; }
+            int lab = lane == 4 ? out[p] : 0;
+            const bool take = q >= 0 && mq != 0 && oq == 0;
             const uint32_t bits = __ballot_sync(0xffffffffu, take) & 0xFu;
-            const int lab = out[p];
+            lab = __shfl_sync(0xffffffffu, lab, 4);
             for (int k = 0; k < 4; ++k) {
                 if (!(bits >> k & 1u)) continue;
                 const int qq = __shfl_sync(0xffffffffu, q, k);

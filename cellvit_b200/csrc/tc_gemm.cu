@@ -7,7 +7,7 @@
 //     is one 4-D TMA box shifted by (dx-1, dy-1); out-of-image pixels are zero-filled by the TMA unit, so
 //     there is no im2col buffer. torch.cat([skip, x], 1) is a K-split over two tensor maps.
 //
-// CTA = 12 warps: w0 TMA producer (1 lane), w1 MMA issuer (1 lane), w2 TMEM allocator, w4..11 epilogue
+// CTA = 12 warps: w0 / w3 TMA producers for A / B (1 lane each), w1 MMA issuer (1 lane), w2 TMEM allocator, w4..11 epilogue
 // (TMEM lane quadrant = warp & 3; the two warps of a quadrant take alternating 32-column chunks). Tile = 128 x block_n fp32 accumulator in TMEM, double buffered so the
 // epilogue of tile i overlaps the main loop of tile i+1. Operands are fp16 (11-bit mantissa: the reference's
 // own AMP mode, cell_detection.py:314-318), accumulation fp32.
@@ -97,7 +97,7 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUte
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < stages; ++s) {
-            ptx::mbar_init(full_bar(s), PAIR ? 2 : 1);
+            ptx::mbar_init(full_bar(s), PAIR ? 4 : 2);  // one arrival per producer thread (A and B, per CTA)
             ptx::mbar_init(empty_bar(s), 1);
         }
         for (int s = 0; s < 2; ++s) {
@@ -122,11 +122,14 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUte
 
     const int num_kb = p.num_kb;
 
-    if (warp == 0 && lane == 0) {
-        // ===================================================== TMA producer
+    if ((warp == 0 || warp == 3) && lane == 0) {
+        // ===================================================== TMA producers: warp 0 streams A, warp 3 streams B.
+        // Two issuing threads because one thread's wait + expect_tx + 2 x UTMALDG chain (~700 clk per k-block) is
+        // slower than a k-block of MMA for narrow tiles (128 clk at N = 64).
+        const bool is_a = warp == 0;
         int stage = 0;
         uint32_t phase = 0;
-        const uint32_t tx_bytes = (PAIR ? 2u : 1u) * (A_STAGE_BYTES + b_stage_bytes);
+        const uint32_t tx_bytes = (PAIR ? 2u : 1u) * (is_a ? (uint32_t)A_STAGE_BYTES : b_stage_bytes);
         for (int tile = tile0; tile < p.n_tiles; tile += tile_step) {
             const int mt = tile / p.n_tiles_n, nt = tile - mt * p.n_tiles_n;
             const int m0 = mt * TILE_M + (int)rank * BLOCK_M, n0 = nt * p.block_n + (int)rank * b_rows;
@@ -138,30 +141,33 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUte
                 y0 = rem / p.W;
                 x0 = rem - y0 * p.W;
             }
+            int tap = 0, cc = 0;  // conv: k-block = (tap, 64-channel chunk), chunk fastest
             for (int kb = 0; kb < num_kb; ++kb) {
                 ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
                 if (!PAIR || rank == 0) ptx::mbar_expect_tx(full_bar(stage), tx_bytes);
-                const uint32_t dst_a = smem_a + stage * A_STAGE_BYTES;
-                const CUtensorMap* ta = &tmA0;
-                int c0 = kb * BLOCK_K, dx = 0, dy = 0;
-                if (p.conv) {
-                    const int tap = kb / p.chunks_per_tap;
-                    const int cc = kb - tap * p.chunks_per_tap;
-                    dy = tap / 3 - 1;
-                    dx = tap - (tap / 3) * 3 - 1;
-                    if (cc < p.chunks0) c0 = cc * BLOCK_K;
-                    else { ta = &tmA1; c0 = (cc - p.chunks0) * BLOCK_K; }
-                }
-                if (PAIR) {
-                    if (!p.conv) ptx::tma_load_2d_pair(dst_a, ta, full_bar(stage), c0, m0);
-                    else ptx::tma_load_4d_pair(dst_a, ta, full_bar(stage), c0, x0 + dx, y0 + dy, img);
-                    ptx::tma_load_2d_pair(smem_b + stage * b_stage_bytes, &tmB, full_bar(stage), kb * BLOCK_K, n0);
-                    if (rank != 0) ptx::mbar_arrive_cluster(full_bar(stage), 0);
+                if (is_a) {
+                    const uint32_t dst_a = smem_a + stage * A_STAGE_BYTES;
+                    const CUtensorMap* ta = &tmA0;
+                    int c0 = kb * BLOCK_K, dx = 0, dy = 0;
+                    if (p.conv) {
+                        dy = tap / 3 - 1;
+                        dx = tap - (tap / 3) * 3 - 1;
+                        if (cc < p.chunks0) c0 = cc * BLOCK_K;
+                        else { ta = &tmA1; c0 = (cc - p.chunks0) * BLOCK_K; }
+                        if (++cc == p.chunks_per_tap) { cc = 0; ++tap; }
+                    }
+                    if (PAIR) {
+                        if (!p.conv) ptx::tma_load_2d_pair(dst_a, ta, full_bar(stage), c0, m0);
+                        else ptx::tma_load_4d_pair(dst_a, ta, full_bar(stage), c0, x0 + dx, y0 + dy, img);
+                    } else {
+                        if (!p.conv) ptx::tma_load_2d(dst_a, ta, full_bar(stage), c0, m0);
+                        else ptx::tma_load_4d(dst_a, ta, full_bar(stage), c0, x0 + dx, y0 + dy, img);
+                    }
                 } else {
-                    if (!p.conv) ptx::tma_load_2d(dst_a, ta, full_bar(stage), c0, m0);
-                    else ptx::tma_load_4d(dst_a, ta, full_bar(stage), c0, x0 + dx, y0 + dy, img);
-                    ptx::tma_load_2d(smem_b + stage * b_stage_bytes, &tmB, full_bar(stage), kb * BLOCK_K, n0);
+                    if (PAIR) ptx::tma_load_2d_pair(smem_b + stage * b_stage_bytes, &tmB, full_bar(stage), kb * BLOCK_K, n0);
+                    else ptx::tma_load_2d(smem_b + stage * b_stage_bytes, &tmB, full_bar(stage), kb * BLOCK_K, n0);
                 }
+                if (PAIR && rank != 0) ptx::mbar_arrive_cluster(full_bar(stage), 0);
                 if (++stage == stages) { stage = 0; phase ^= 1u; }
             }
         }
