@@ -58,6 +58,139 @@ __device__ __forceinline__ float apply_act(float v, int act) {
     return v;
 }
 
+// Drains one 128 x (32 * n_chunks) fp32 accumulator (TMEM address t_addr already carries the lane quadrant) through
+// the fused epilogue. `m` is the global output row of this thread; `release()` hands the TMEM buffer back to the MMA
+// issuer and is called right after this thread's last tcgen05.ld when `do_release` is set.
+template <class Release>
+__device__ __forceinline__ void epilogue_tile(const TcEpilogue& e, uint32_t t_addr, int m, bool row_ok, int n0, int n_chunks,
+                                              int half, int last_c, const float* head_w_s, bool do_release, Release release) {
+    if (e.kind == TC_EPI_HEAD) {
+        if (half != 0) {  // the fused 1x1 head needs all 64 channels of a pixel in one thread
+            if (do_release) release();
+            return;
+        }
+        float hs[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) hs[k] = head_w_s[8 * 64 + k];
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            uint32_t acc[32];
+            ptx::tmem_ld32(t_addr + c * 32, acc);
+            ptx::tmem_ld_wait();
+            if (c == 1) if (do_release) release();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const int n = c * 32 + j;
+                const float v = fmaxf(fmaf(__uint_as_float(acc[j]), __ldg(e.scale + n), __ldg(e.shift + n)), 0.0f);
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                    if (k < e.head_nc) hs[k] = fmaf(head_w_s[k * 64 + n], v, hs[k]);
+            }
+        }
+        if (row_ok) {
+            const int img = m / e.head_hw, pix = m - img * e.head_hw;
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                if (k < e.head_nc) e.head_out[((size_t)img * e.head_nc + k) * e.head_hw + pix] = hs[k];
+        }
+        return;
+    }
+
+    int orow = -1;
+    size_t out_off = 0;
+    int ct_b = 0, ct_y = 0, ct_x = 0;
+    if (row_ok) {
+        if (e.kind == TC_EPI_CONVT) {
+            const int hw = e.ct_hin * e.ct_win;
+            ct_b = m / hw;
+            const int rem = m - ct_b * hw;
+            ct_y = rem / e.ct_win;
+            ct_x = rem - ct_y * e.ct_win;
+            orow = m;
+        } else {
+            orow = map_out_row(e, m);
+            out_off = (size_t)(orow < 0 ? 0 : orow) * (size_t)e.ldc;
+        }
+    }
+    const float* res_row = nullptr;
+    if (e.kind == TC_EPI_RES_F32 && e.res != nullptr && orow >= 0) {
+        const long long rr = e.res_mod > 0 ? (long long)(m % e.res_mod) + e.res_off : (long long)orow;
+        res_row = e.res + rr * e.ldres;
+    }
+    if (last_c < 0) if (do_release) release();
+
+    for (int c = half; c < n_chunks; c += 2) {
+        uint32_t acc[32];
+        ptx::tmem_ld32(t_addr + c * 32, acc);
+        ptx::tmem_ld_wait();
+        if (c == last_c) if (do_release) release();
+        if (orow < 0) continue;
+        const int nb = n0 + c * 32;
+        if (e.kind == TC_EPI_F16) {
+            __half* o = reinterpret_cast<__half*>(e.out) + out_off + nb;
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+                float4 s0 = make_float4(1.f, 1.f, 1.f, 1.f), s1 = s0;
+                float4 h0 = make_float4(0.f, 0.f, 0.f, 0.f), h1 = h0;
+                if (e.scale) {
+                    s0 = __ldg(reinterpret_cast<const float4*>(e.scale + nb + j));
+                    s1 = __ldg(reinterpret_cast<const float4*>(e.scale + nb + j + 4));
+                }
+                if (e.shift) {
+                    h0 = __ldg(reinterpret_cast<const float4*>(e.shift + nb + j));
+                    h1 = __ldg(reinterpret_cast<const float4*>(e.shift + nb + j + 4));
+                }
+                const float v0 = apply_act(fmaf(__uint_as_float(acc[j + 0]), s0.x, h0.x), e.act);
+                const float v1 = apply_act(fmaf(__uint_as_float(acc[j + 1]), s0.y, h0.y), e.act);
+                const float v2 = apply_act(fmaf(__uint_as_float(acc[j + 2]), s0.z, h0.z), e.act);
+                const float v3 = apply_act(fmaf(__uint_as_float(acc[j + 3]), s0.w, h0.w), e.act);
+                const float v4 = apply_act(fmaf(__uint_as_float(acc[j + 4]), s1.x, h1.x), e.act);
+                const float v5 = apply_act(fmaf(__uint_as_float(acc[j + 5]), s1.y, h1.y), e.act);
+                const float v6 = apply_act(fmaf(__uint_as_float(acc[j + 6]), s1.z, h1.z), e.act);
+                const float v7 = apply_act(fmaf(__uint_as_float(acc[j + 7]), s1.w, h1.w), e.act);
+                *reinterpret_cast<uint4*>(o + j) = make_uint4(pack_h2(v0, v1), pack_h2(v2, v3), pack_h2(v4, v5), pack_h2(v6, v7));
+            }
+        } else if (e.kind == TC_EPI_RES_F32) {
+            float* o = reinterpret_cast<float*>(e.out) + out_off + nb;
+            // all residual loads first: `res` may alias `out`, so the compiler cannot hoist them over the
+            // stores itself and the chunk would pay eight dependent memory round trips instead of one
+            float4 rv[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                rv[j] = res_row ? *reinterpret_cast<const float4*>(res_row + nb + 4 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                float4 sv = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (e.shift) sv = __ldg(reinterpret_cast<const float4*>(e.shift + nb + 4 * j));
+                float4 ov;
+                ov.x = __uint_as_float(acc[4 * j + 0]) + sv.x + rv[j].x;
+                ov.y = __uint_as_float(acc[4 * j + 1]) + sv.y + rv[j].y;
+                ov.z = __uint_as_float(acc[4 * j + 2]) + sv.z + rv[j].z;
+                ov.w = __uint_as_float(acc[4 * j + 3]) + sv.w + rv[j].w;
+                *reinterpret_cast<float4*>(o + 4 * j) = ov;
+            }
+        } else {  // TC_EPI_CONVT: 32 consecutive n share (dy,dx) because Cout % 32 == 0
+            const int q = nb / e.ct_cout, co = nb - q * e.ct_cout;
+            const int dy = q >> 1, dx = q & 1;
+            const size_t opix = ((size_t)ct_b * (2 * e.ct_hin) + (2 * ct_y + dy)) * (size_t)(2 * e.ct_win) + (2 * ct_x + dx);
+            __half* o = reinterpret_cast<__half*>(e.out) + opix * (size_t)e.ldc + co;
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+                float4 h0 = make_float4(0.f, 0.f, 0.f, 0.f), h1 = h0;
+                if (e.shift) {
+                    h0 = __ldg(reinterpret_cast<const float4*>(e.shift + co + j));
+                    h1 = __ldg(reinterpret_cast<const float4*>(e.shift + co + j + 4));
+                }
+                *reinterpret_cast<uint4*>(o + j) =
+                    make_uint4(pack_h2(__uint_as_float(acc[j + 0]) + h0.x, __uint_as_float(acc[j + 1]) + h0.y),
+                               pack_h2(__uint_as_float(acc[j + 2]) + h0.z, __uint_as_float(acc[j + 3]) + h0.w),
+                               pack_h2(__uint_as_float(acc[j + 4]) + h1.x, __uint_as_float(acc[j + 5]) + h1.y),
+                               pack_h2(__uint_as_float(acc[j + 6]) + h1.z, __uint_as_float(acc[j + 7]) + h1.w));
+            }
+        }
+    }
+}
+
 // PAIR: the two CTAs of a cluster (one TPC) run one 256 x block_n tile with tcgen05.mma.cta_group::2 -- each CTA
 // stages its own 128 rows of A and HALF of the B tile, so the L2 -> SM operand traffic per FLOP drops by a third
 // (the tile engine is bound by that feed, ~53 B/clk/SM, not by the tensor pipe). Only the leader CTA issues MMAs;
@@ -231,131 +364,7 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUte
             ptx::tc_fence_after();
             const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * p.block_n);
 
-            if (e.kind == TC_EPI_HEAD) {
-                if (half != 0) {  // the fused 1x1 head needs all 64 channels of a pixel in one thread
-                    release_tmem(as);
-                    continue;
-                }
-                float hs[8];
-#pragma unroll
-                for (int k = 0; k < 8; ++k) hs[k] = head_w_s[8 * 64 + k];
-#pragma unroll
-                for (int c = 0; c < 2; ++c) {
-                    uint32_t acc[32];
-                    ptx::tmem_ld32(t_addr + c * 32, acc);
-                    ptx::tmem_ld_wait();
-                    if (c == 1) release_tmem(as);
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const int n = c * 32 + j;
-                        const float v = fmaxf(fmaf(__uint_as_float(acc[j]), __ldg(e.scale + n), __ldg(e.shift + n)), 0.0f);
-#pragma unroll
-                        for (int k = 0; k < 8; ++k)
-                            if (k < e.head_nc) hs[k] = fmaf(head_w_s[k * 64 + n], v, hs[k]);
-                    }
-                }
-                if (row_ok) {
-                    const int img = m / e.head_hw, pix = m - img * e.head_hw;
-#pragma unroll
-                    for (int k = 0; k < 8; ++k)
-                        if (k < e.head_nc) e.head_out[((size_t)img * e.head_nc + k) * e.head_hw + pix] = hs[k];
-                }
-                continue;
-            }
-
-            int orow = -1;
-            size_t out_off = 0;
-            int ct_b = 0, ct_y = 0, ct_x = 0;
-            if (row_ok) {
-                if (e.kind == TC_EPI_CONVT) {
-                    const int hw = e.ct_hin * e.ct_win;
-                    ct_b = m / hw;
-                    const int rem = m - ct_b * hw;
-                    ct_y = rem / e.ct_win;
-                    ct_x = rem - ct_y * e.ct_win;
-                    orow = m;
-                } else {
-                    orow = map_out_row(e, m);
-                    out_off = (size_t)(orow < 0 ? 0 : orow) * (size_t)e.ldc;
-                }
-            }
-            const float* res_row = nullptr;
-            if (e.kind == TC_EPI_RES_F32 && e.res != nullptr && orow >= 0) {
-                const long long rr = e.res_mod > 0 ? (long long)(m % e.res_mod) + e.res_off : (long long)orow;
-                res_row = e.res + rr * e.ldres;
-            }
-            if (last_c < 0) release_tmem(as);
-
-            for (int c = half; c < n_chunks; c += 2) {
-                uint32_t acc[32];
-                ptx::tmem_ld32(t_addr + c * 32, acc);
-                ptx::tmem_ld_wait();
-                if (c == last_c) release_tmem(as);
-                if (orow < 0) continue;
-                const int nb = n0 + c * 32;
-                if (e.kind == TC_EPI_F16) {
-                    __half* o = reinterpret_cast<__half*>(e.out) + out_off + nb;
-#pragma unroll
-                    for (int j = 0; j < 32; j += 8) {
-                        float4 s0 = make_float4(1.f, 1.f, 1.f, 1.f), s1 = s0;
-                        float4 h0 = make_float4(0.f, 0.f, 0.f, 0.f), h1 = h0;
-                        if (e.scale) {
-                            s0 = __ldg(reinterpret_cast<const float4*>(e.scale + nb + j));
-                            s1 = __ldg(reinterpret_cast<const float4*>(e.scale + nb + j + 4));
-                        }
-                        if (e.shift) {
-                            h0 = __ldg(reinterpret_cast<const float4*>(e.shift + nb + j));
-                            h1 = __ldg(reinterpret_cast<const float4*>(e.shift + nb + j + 4));
-                        }
-                        const float v0 = apply_act(fmaf(__uint_as_float(acc[j + 0]), s0.x, h0.x), e.act);
-                        const float v1 = apply_act(fmaf(__uint_as_float(acc[j + 1]), s0.y, h0.y), e.act);
-                        const float v2 = apply_act(fmaf(__uint_as_float(acc[j + 2]), s0.z, h0.z), e.act);
-                        const float v3 = apply_act(fmaf(__uint_as_float(acc[j + 3]), s0.w, h0.w), e.act);
-                        const float v4 = apply_act(fmaf(__uint_as_float(acc[j + 4]), s1.x, h1.x), e.act);
-                        const float v5 = apply_act(fmaf(__uint_as_float(acc[j + 5]), s1.y, h1.y), e.act);
-                        const float v6 = apply_act(fmaf(__uint_as_float(acc[j + 6]), s1.z, h1.z), e.act);
-                        const float v7 = apply_act(fmaf(__uint_as_float(acc[j + 7]), s1.w, h1.w), e.act);
-                        *reinterpret_cast<uint4*>(o + j) = make_uint4(pack_h2(v0, v1), pack_h2(v2, v3), pack_h2(v4, v5), pack_h2(v6, v7));
-                    }
-                } else if (e.kind == TC_EPI_RES_F32) {
-                    float* o = reinterpret_cast<float*>(e.out) + out_off + nb;
-                    // all residual loads first: `res` may alias `out`, so the compiler cannot hoist them over the
-                    // stores itself and the chunk would pay eight dependent memory round trips instead of one
-                    float4 rv[8];
-#pragma unroll
-                    for (int j = 0; j < 8; ++j)
-                        rv[j] = res_row ? *reinterpret_cast<const float4*>(res_row + nb + 4 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        float4 sv = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (e.shift) sv = __ldg(reinterpret_cast<const float4*>(e.shift + nb + 4 * j));
-                        float4 ov;
-                        ov.x = __uint_as_float(acc[4 * j + 0]) + sv.x + rv[j].x;
-                        ov.y = __uint_as_float(acc[4 * j + 1]) + sv.y + rv[j].y;
-                        ov.z = __uint_as_float(acc[4 * j + 2]) + sv.z + rv[j].z;
-                        ov.w = __uint_as_float(acc[4 * j + 3]) + sv.w + rv[j].w;
-                        *reinterpret_cast<float4*>(o + 4 * j) = ov;
-                    }
-                } else {  // TC_EPI_CONVT: 32 consecutive n share (dy,dx) because Cout % 32 == 0
-                    const int q = nb / e.ct_cout, co = nb - q * e.ct_cout;
-                    const int dy = q >> 1, dx = q & 1;
-                    const size_t opix = ((size_t)ct_b * (2 * e.ct_hin) + (2 * ct_y + dy)) * (size_t)(2 * e.ct_win) + (2 * ct_x + dx);
-                    __half* o = reinterpret_cast<__half*>(e.out) + opix * (size_t)e.ldc + co;
-#pragma unroll
-                    for (int j = 0; j < 32; j += 8) {
-                        float4 h0 = make_float4(0.f, 0.f, 0.f, 0.f), h1 = h0;
-                        if (e.shift) {
-                            h0 = __ldg(reinterpret_cast<const float4*>(e.shift + co + j));
-                            h1 = __ldg(reinterpret_cast<const float4*>(e.shift + co + j + 4));
-                        }
-                        *reinterpret_cast<uint4*>(o + j) =
-                            make_uint4(pack_h2(__uint_as_float(acc[j + 0]) + h0.x, __uint_as_float(acc[j + 1]) + h0.y),
-                                       pack_h2(__uint_as_float(acc[j + 2]) + h0.z, __uint_as_float(acc[j + 3]) + h0.w),
-                                       pack_h2(__uint_as_float(acc[j + 4]) + h1.x, __uint_as_float(acc[j + 5]) + h1.y),
-                                       pack_h2(__uint_as_float(acc[j + 6]) + h1.z, __uint_as_float(acc[j + 7]) + h1.w));
-                    }
-                }
-            }
+            epilogue_tile(e, t_addr, m, row_ok, n0, n_chunks, half, last_c, head_w_s, true, [&]() { release_tmem(as); });
         }
     }
 
@@ -366,6 +375,193 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUte
         if (PAIR) ptx::tmem_dealloc_pair(tmem_base, p.tmem_cols);
         else ptx::tmem_dealloc(tmem_base, p.tmem_cols);
     }
+}
+
+// ------------------------------------------------------------------------------------------- patch-resident 3x3 conv
+// The k-block conv above re-reads every input pixel nine times through the L2 -> SM fabric, which is what bounds it
+// (the wide, shallow layers at 512^2 / 1024^2 run at ~0.2 of the tensor peak). This variant stages, per 64-channel
+// chunk, the (R+2) x 130-pixel input patch of an R-row x 128-pixel output tile ONCE (one 4-D TMA box, zero-filled
+// halo) and forms the A operand of tap (dy,dx) and output row r by pointing the UMMA shared-memory descriptor at
+// patch row (r+dy)*130 + dx: 128 consecutive 128-byte rows, the canonical K-major SWIZZLE_128B layout. The start
+// address is then not 1024-byte aligned; measured on B200 (tools/probe_conv_patch.py): the 128B swizzle is a pure
+// function of the absolute shared-memory address for both TMA and UMMA, so the descriptor needs NO base offset
+// (setting (addr >> 7) & 7 there gives wrong results). Weights go through their own ring, one [N x 64] tile per
+// (chunk, tap), shared by the R accumulators; when the whole weight set fits (Cin = 64, N = 64: 72 KB) it is
+// loaded once per CTA and stays resident. Input bytes per output pixel drop 9x -> (R+2)/R * 130/128 = 2.03x.
+constexpr int CP_R = 2;
+constexpr int CP_PW = 130;                                 // patch width: 128 + 2 halo pixels
+constexpr int CP_PATCH_BYTES = (CP_R + 2) * CP_PW * 128;   // 66,560 B = 65 KiB
+constexpr int CP_MAX_BSTAGES = 12;
+
+struct CpParams {
+    int NB, H, W, N;
+    int chunks0, chunks;  // 64-channel chunks of source 0 / of both sources
+    int n_tiles, tiles_x, tiles_y;
+    int b_stages, resident;  // resident: b_stages == 9 * chunks, every weight tile loaded once per CTA
+    uint32_t tmem_cols;
+    TcEpilogue epi;
+};
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+conv_patch_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+                  const __grid_constant__ CUtensorMap tmB, const CpParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem_gen = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t b_stage_bytes = (uint32_t)p.N * BLOCK_K * 2;
+    const uint32_t smem_patch = smem_base;
+    const uint32_t smem_b = smem_patch + 2 * CP_PATCH_BYTES;
+    const uint32_t bar_base = smem_b + p.b_stages * b_stage_bytes;
+    auto pfull = [&](int s) { return bar_base + 8u * s; };
+    auto pempty = [&](int s) { return bar_base + 8u * (2 + s); };
+    auto bfull = [&](int s) { return bar_base + 8u * (4 + s); };
+    auto bempty = [&](int s) { return bar_base + 8u * (4 + CP_MAX_BSTAGES + s); };
+    auto tfull = [&](int s) { return bar_base + 8u * (4 + 2 * CP_MAX_BSTAGES + s); };
+    auto tempty = [&](int s) { return bar_base + 8u * (6 + 2 * CP_MAX_BSTAGES + s); };
+    const uint32_t tmem_slot = bar_base + 8u * (8 + 2 * CP_MAX_BSTAGES);
+    const uint32_t aux_off = (tmem_slot - smem_base) + 16u;
+    float* head_w_s = reinterpret_cast<float*>(smem_gen + aux_off);
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tmap(&tmA0);
+        ptx::prefetch_tmap(&tmB);
+        if (p.chunks > p.chunks0) ptx::prefetch_tmap(&tmA1);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < 2; ++s) {
+            ptx::mbar_init(pfull(s), 1);
+            ptx::mbar_init(pempty(s), 1);
+            ptx::mbar_init(tfull(s), 1);
+            ptx::mbar_init(tempty(s), NUM_THREADS - 128);
+        }
+        for (int s = 0; s < p.b_stages; ++s) {
+            ptx::mbar_init(bfull(s), 1);
+            ptx::mbar_init(bempty(s), 1);
+        }
+        ptx::fence_barrier_init();
+    }
+    if (warp == 2) {
+        ptx::tmem_alloc(tmem_slot, p.tmem_cols);
+        ptx::tmem_relinquish();
+    }
+    if (p.epi.kind == TC_EPI_HEAD && warp >= 4) {
+        const int t = threadIdx.x - 128;
+        for (int i = t; i < p.epi.head_nc * 64; i += NUM_THREADS - 128) head_w_s[i] = p.epi.head_w[i];
+        if (t < p.epi.head_nc) head_w_s[8 * 64 + t] = p.epi.head_b[t];
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
+
+    auto tile_origin = [&](int tile, int& img, int& y0, int& x0) {
+        const int xb = tile % p.tiles_x;
+        const int t2 = tile / p.tiles_x;
+        const int yb = t2 % p.tiles_y;
+        img = t2 / p.tiles_y;
+        y0 = yb * CP_R;
+        x0 = xb * BLOCK_M;
+    };
+
+    if (warp == 0 && lane == 0) {
+        // ===================================================== patch producer
+        int ps = 0;
+        uint32_t pphase = 0;
+        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+            int img, y0, x0;
+            tile_origin(tile, img, y0, x0);
+            for (int c = 0; c < p.chunks; ++c) {
+                ptx::mbar_wait(pempty(ps), pphase ^ 1u);
+                ptx::mbar_expect_tx(pfull(ps), CP_PATCH_BYTES);
+                const bool first = c < p.chunks0;
+                // one TMA per patch row: a single large box is serviced at ~14 GB/s, concurrent boxes overlap
+#pragma unroll
+                for (int pr = 0; pr < CP_R + 2; ++pr)
+                    ptx::tma_load_4d(smem_patch + ps * CP_PATCH_BYTES + pr * (CP_PW * 128), first ? &tmA0 : &tmA1, pfull(ps),
+                                     (first ? c : c - p.chunks0) * BLOCK_K, x0 - 1, y0 - 1 + pr, img);
+                if (++ps == 2) { ps = 0; pphase ^= 1u; }
+            }
+        }
+    } else if (warp == 3 && lane == 0) {
+        // ===================================================== weight producer: one [N x 64] tile per (chunk, tap)
+        int bs = 0;
+        uint32_t bphase = 0;
+        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+            if (p.resident && tile != (int)blockIdx.x) break;  // resident weights: one pass fills every slot for good
+            for (int c = 0; c < p.chunks; ++c) {
+                for (int tap = 0; tap < 9; ++tap) {
+                    ptx::mbar_wait(bempty(bs), bphase ^ 1u);
+                    ptx::mbar_expect_tx(bfull(bs), b_stage_bytes);
+                    ptx::tma_load_2d(smem_b + bs * b_stage_bytes, &tmB, bfull(bs), (tap * p.chunks + c) * BLOCK_K, 0);
+                    if (++bs == p.b_stages) { bs = 0; bphase ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1 && lane == 0) {
+        // ===================================================== MMA issuer
+        const uint32_t idesc = (1u << 4) | ((uint32_t)(p.N >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+        const uint64_t desc_hi = (2ull << 61) | (1ull << 46) | ((uint64_t)(1024 >> 4) << 32);
+        int ps = 0, bs = 0, it = 0;
+        uint32_t pphase = 0, bphase = 0;
+        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+            const int as = it & 1;
+            ptx::mbar_wait(tempty(as), ((it >> 1) & 1) ^ 1u);
+            ptx::tc_fence_after();
+            for (int c = 0; c < p.chunks; ++c) {
+                ptx::mbar_wait(pfull(ps), pphase);
+                ptx::tc_fence_after();
+                const uint32_t patch = smem_patch + ps * CP_PATCH_BYTES;
+                for (int tap = 0; tap < 9; ++tap) {
+                    ptx::mbar_wait(bfull(bs), p.resident ? 0u : bphase);  // resident: phase 0 completes once, stays complete
+                    ptx::tc_fence_after();
+                    const int dy = tap / 3, dx = tap - dy * 3;
+                    const uint64_t b_desc = desc_hi | (uint64_t)(((smem_b + bs * b_stage_bytes) >> 4) & 0x3FFF);
+#pragma unroll
+                    for (int r = 0; r < CP_R; ++r) {
+                        const uint32_t a_addr = patch + (uint32_t)((r + dy) * CP_PW + dx) * 128u;
+                        const uint64_t a_desc = desc_hi | (uint64_t)((a_addr >> 4) & 0x3FFF);
+                        const uint32_t d_tmem = tmem_base + (uint32_t)((as * CP_R + r) * p.N);
+#pragma unroll
+                        for (int k = 0; k < BLOCK_K / 16; ++k)
+                            ptx::umma_f16(d_tmem, a_desc + 2u * k, b_desc + 2u * k, idesc, (c | tap | k) != 0 ? 1u : 0u);
+                    }
+                    if (!p.resident) ptx::umma_commit(bempty(bs));
+                    if (++bs == p.b_stages) { bs = 0; bphase ^= 1u; }
+                }
+                ptx::umma_commit(pempty(ps));
+                if (++ps == 2) { ps = 0; pphase ^= 1u; }
+            }
+            ptx::umma_commit(tfull(as));
+        }
+    } else if (warp >= 4) {
+        // ===================================================== epilogue: R accumulators of 128 pixels each
+        const TcEpilogue& e = p.epi;
+        const int quad = warp & 3, half = (warp - 4) >> 2;
+        const int n_chunks = p.N / 32;
+        const int last_c = n_chunks - 1 - (((n_chunks - 1) & 1) != half ? 1 : 0);
+        int it = 0;
+        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+            const int as = it & 1;
+            int img, y0, x0;
+            tile_origin(tile, img, y0, x0);
+            ptx::mbar_wait(tfull(as), (it >> 1) & 1);
+            ptx::tc_fence_after();
+#pragma unroll
+            for (int r = 0; r < CP_R; ++r) {
+                const int m = (img * p.H + y0 + r) * p.W + x0 + quad * 32 + lane;
+                const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)((as * CP_R + r) * p.N);
+                epilogue_tile(e, t_addr, m, true, 0, n_chunks, half, last_c, head_w_s, r == CP_R - 1, [&]() {
+                    ptx::tc_fence_before();
+                    ptx::mbar_arrive(tempty(as));
+                });
+            }
+        }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    if (warp == 2) ptx::tmem_dealloc(tmem_base, p.tmem_cols);
 }
 
 // ------------------------------------------------------------------------------------------- host side
@@ -513,11 +709,71 @@ int tc_gemm(const __half* A, int M, int K, long long lda, const __half* W, int N
     return launch(ta, ta, tb, p, pair, stream);
 }
 
+static int g_patch_mode = 1;  // 0: k-block conv only, 1: patch-resident conv where the shape allows it
+
+static int conv_patch_launch(const __half* src0, int C0, const __half* src1, int C1, int NB, int H, int W, const __half* Wp, int N,
+                             const TcEpilogue& epi, cudaStream_t stream) {
+    CUtensorMap t0, t1, tb;
+    auto mk = [&](CUtensorMap* tm, const __half* src, int C) {
+        uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)NB};
+        uint64_t str[3] = {(uint64_t)C * 2, (uint64_t)W * C * 2, (uint64_t)H * W * C * 2};
+        uint32_t box[4] = {BLOCK_K, (uint32_t)CP_PW, 1, 1};
+        return make_tmap(tm, src, 4, dims, str, box);
+    };
+    CVB_TRY(mk(&t0, src0, C0));
+    if (C1 > 0) CVB_TRY(mk(&t1, src1, C1)); else t1 = t0;
+    const int K = 9 * (C0 + C1);
+    {
+        uint64_t dims[2] = {(uint64_t)K, (uint64_t)N};
+        uint64_t str[1] = {(uint64_t)K * 2};
+        uint32_t box[2] = {BLOCK_K, (uint32_t)N};
+        CVB_TRY(make_tmap(&tb, Wp, 2, dims, str, box));
+    }
+    CpParams p{};
+    p.NB = NB; p.H = H; p.W = W; p.N = N; p.chunks0 = C0 / 64; p.chunks = (C0 + C1) / 64;
+    p.tiles_x = W / BLOCK_M; p.tiles_y = H / CP_R; p.n_tiles = NB * p.tiles_x * p.tiles_y;
+    p.epi = epi;
+    const int b_stage = N * BLOCK_K * 2;
+    const int fixed = 1024 + 2 * CP_PATCH_BYTES + 8 * (8 + 2 * CP_MAX_BSTAGES) + 16 + (8 * 64 + 8) * 4;
+    int bst = (226 * 1024 - fixed) / b_stage;
+    if (bst > CP_MAX_BSTAGES) bst = CP_MAX_BSTAGES;
+    CVB_CHECK(bst >= 3, CVB_ESHAPE, "conv_patch: not enough shared memory for the weight ring (N=%d)", N);
+    p.resident = 9 * p.chunks <= bst ? 1 : 0;
+    if (p.resident) bst = 9 * p.chunks;
+    p.b_stages = bst;
+    uint32_t cols = 32;
+    while (cols < (uint32_t)(2 * CP_R * N)) cols <<= 1;
+    p.tmem_cols = cols;
+    const size_t smem = (size_t)fixed + (size_t)bst * b_stage;
+    static bool configured = false;
+    if (!configured) {
+        CVB_CUDA(cudaFuncSetAttribute(conv_patch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
+        configured = true;
+    }
+    const int grid = p.n_tiles < cvb_num_sms() ? p.n_tiles : cvb_num_sms();
+    const bool prof = g_prof.on && g_prof.used + 2 <= g_prof.ev.size();
+    if (prof) CVB_CUDA(cudaEventRecord(g_prof.ev[g_prof.used], stream));
+    conv_patch_kernel<<<grid, NUM_THREADS, smem, stream>>>(t0, t1, tb, p);
+    if (prof) {
+        CVB_CUDA(cudaEventRecord(g_prof.ev[g_prof.used + 1], stream));
+        g_prof.used += 2;
+        g_prof.flops += 2.0 * (double)NB * H * W * (double)N * (double)K;
+    }
+    CVB_CUDA(cudaGetLastError());
+    cvb_note_launches(1);
+    return CVB_OK;
+}
+
 int tc_conv3x3(const __half* src0, int C0, const __half* src1, int C1, int NB, int H, int W, const __half* Wp,
                int N, int block_n, const TcEpilogue& epi, cudaStream_t stream) {
     CVB_CHECK(src0 && Wp && NB > 0 && H > 0 && W > 0, CVB_EARG, "tc_conv3x3: null operand or empty shape");
     if (!src1) C1 = 0;
     CVB_CHECK(C0 > 0 && C0 % 64 == 0 && C1 % 64 == 0, CVB_ESHAPE, "tc_conv3x3: channels (%d,%d) must be multiples of 64", C0, C1);
+    if (g_patch_mode != 0 && W % BLOCK_M == 0 && H % CP_R == 0 && (N == 64 || N == 128) && block_n == N &&
+        (epi.kind == TC_EPI_F16 || epi.kind == TC_EPI_HEAD) && epi.row_map == TC_ROW_IDENTITY) {
+        CVB_TRY(check_epilogue(epi, N, block_n));
+        return conv_patch_launch(src0, C0, src1, C1, NB, H, W, Wp, N, epi, stream);
+    }
     const int TW = W < BLOCK_M ? W : BLOCK_M;
     CVB_CHECK(BLOCK_M % TW == 0 && W % TW == 0 && H % (BLOCK_M / TW) == 0, CVB_ESHAPE,
               "tc_conv3x3: image %dx%d does not tile into 128-pixel blocks", H, W);
@@ -577,3 +833,6 @@ extern "C" __attribute__((visibility("default"))) int cvb_tc_profile_end(double*
 
 // Test / ablation hook: 0 disables the CTA-pair (cta_group::2) path, 1 enables it (default).
 extern "C" __attribute__((visibility("default"))) void cvb_tc_set_pair_mode(int on) { g_pair_enabled = on != 0; }
+
+// Test / ablation hook: 0 = k-block conv only, 1 = patch-resident conv where the shape allows it (default).
+extern "C" __attribute__((visibility("default"))) void cvb_tc_set_conv_patch_mode(int mode) { g_patch_mode = mode; }

@@ -191,3 +191,34 @@ def test_cta_pair_mode_conv_and_head():
     ref = F.conv2d(torch.cat([s0, s1], -1).permute(0, 3, 1, 2).float(), Wp.view(64, 3, 3, 2 * Cc).permute(0, 3, 1, 2).float(), padding=1)
     ref = F.conv2d(F.relu(ref * scale[None, :, None, None] + shift[None, :, None, None]), hw[:, :, None, None], hb)
     assert (res[1] - ref).abs().max().item() < 1e-3
+
+
+@pytest.mark.parametrize("C0,C1,N,H,W", [(64, 0, 64, 4, 128), (64, 64, 64, 64, 256), (128, 128, 128, 32, 128), (128, 0, 128, 16, 384)])
+def test_patch_resident_conv_matches_kblock_conv_and_reference(C0, C1, N, H, W):
+    """csrc/tc_gemm.cu conv_patch_kernel (UMMA descriptors pointing into a halo patch) vs the k-block conv and fp32."""
+    g = torch.Generator(device="cuda").manual_seed(21)
+    B = 2
+    s0 = (torch.randn(B, H, W, C0, device="cuda", generator=g) * 0.5).half()
+    s1 = (torch.randn(B, H, W, C1, device="cuda", generator=g) * 0.5).half() if C1 else None
+    w = torch.randn(N, C0 + C1, 3, 3, device="cuda", generator=g) * 0.03
+    Wp = _pack_conv_w(w)
+    scale = torch.rand(N, device="cuda", generator=g) + 0.5
+    shift = torch.randn(N, device="cuda", generator=g) * 0.1
+    outs = []
+    try:
+        for mode in (0, 1):
+            L.lib().cvb_tc_set_conv_patch_mode(mode)
+            out = torch.full((B, H, W, N), float("nan"), device="cuda", dtype=torch.half)
+            epi = L.TcEpilogue(kind=L.EPI_F16, act=L.ACT_RELU, scale=scale.data_ptr(), shift=shift.data_ptr(), out=out.data_ptr(), ldc=N)
+            L.check(L.lib().cvb_op_conv3x3_f16(L.ptr(s0), C0, L.ptr(s1), C1, B, H, W, L.ptr(Wp), N, N, C.byref(epi), L.stream_ptr()), "conv")
+            torch.cuda.synchronize()
+            outs.append(out)
+    finally:
+        L.lib().cvb_tc_set_conv_patch_mode(1)
+    xin = torch.cat([s0, s1], -1) if C1 else s0
+    ref = F.conv2d(xin.permute(0, 3, 1, 2).float(), Wp.view(N, 3, 3, C0 + C1).permute(0, 3, 1, 2).float(), padding=1)
+    ref = F.relu(ref * scale[None, :, None, None] + shift[None, :, None, None])
+    tol = 2e-3 * max(1.0, ref.abs().max().item())
+    for o in outs:
+        assert (o.permute(0, 3, 1, 2).float() - ref).abs().max().item() < tol
+    assert (outs[0].float() - outs[1].float()).abs().max().item() < 2 * tol
