@@ -28,19 +28,37 @@ struct FaSmem {
     float rel_w[BIAS ? FA_BQ * REL_LD : 1];
 };
 
+// 64-row x HD tile loader. Every thread owns the same NJ 16-byte chunks of every tile, so the (row, chunk) split and the
+// source / destination offsets are computed once (the naive per-tile div/mod + 64-bit address math was 43 % of the
+// global-attention kernel's instructions).
 template <int HD>
-__device__ __forceinline__ void fa_load_tile(__half* dst, const __half* src_base, long long row_stride, int row0, int n_rows,
-                                             int tid) {
-    constexpr int LD = HD + 8;
-    constexpr int CH = HD / 8;  // 16-byte chunks per row
-    for (int i = tid; i < FA_BK * CH; i += FA_THREADS) {
-        const int r = i / CH, c = i - r * CH;
-        const int row = row0 + r;
-        const bool ok = row < n_rows;
-        const __half* src = src_base + (long long)(ok ? row : 0) * row_stride + c * 8;
-        ptx::cp_async16(ptx::smem_u32(dst + r * LD + c * 8), src, ok);
+struct TileLoader {
+    static constexpr int LD = HD + 8;
+    static constexpr int CH = HD / 8;                                      // 16-byte chunks per row
+    static constexpr int NJ = (FA_BK * CH + FA_THREADS - 1) / FA_THREADS;  // chunks per thread (5 for HD=80, 4 for 64)
+    int row[NJ];
+    int src_off[NJ];       // in halves, relative to the tile's first row
+    uint32_t dst_off[NJ];  // in bytes
+    __device__ __forceinline__ void init(int tid, int row_stride) {
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+            const int i = tid + j * FA_THREADS;
+            const int r = i / CH, c = i - r * CH;
+            row[j] = i < FA_BK * CH ? r : (1 << 30);
+            src_off[j] = r * row_stride + c * 8;
+            dst_off[j] = (uint32_t)(r * LD + c * 8) * 2u;
+        }
     }
-}
+    // rows >= n_rows (or chunks past the tile) are zero-filled
+    __device__ __forceinline__ void load(uint32_t dst_smem, const __half* tile_src, int row0, int n_rows) const {
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+            if ((FA_BK * CH) % FA_THREADS != 0 && row[j] >= FA_BK) continue;
+            const bool ok = row0 + row[j] < n_rows;
+            ptx::cp_async16(dst_smem + dst_off[j], tile_src + (ok ? src_off[j] : 0), ok);
+        }
+    }
+};
 
 // s_acc[16 x 64 per warp] = Q_frag (16 x HD) * tile^T, tile = [64 rows][HD] K-major in shared memory
 template <int HD>
@@ -87,10 +105,14 @@ flash_kernel(const __half* __restrict__ qkv, int S, int heads, float scale, cons
     const bool warp_active = q0 + warp * 16 < S;  // tail q-tiles: idle warps only help loading
     const int r_lo = warp * 16 + (lane >> 2);     // local query row of c0/c1; c2/c3 are r_lo + 8
 
-    fa_load_tile<HD>(sm.q, q_base, row_stride, q0, S, tid);
+    TileLoader<HD> ld;
+    ld.init(tid, (int)row_stride);
+    constexpr uint32_t KV_BYTES = FA_BK * LD * 2;
+    const uint32_t sq = ptx::smem_u32(sm.q), sk0 = ptx::smem_u32(sm.k[0]), sv0 = ptx::smem_u32(sm.v[0]);
+    ld.load(sq, q_base + (long long)q0 * row_stride, q0, S);
     ptx::cp_async_commit();
-    fa_load_tile<HD>(sm.k[0], k_base, row_stride, 0, S, tid);
-    fa_load_tile<HD>(sm.v[0], v_base, row_stride, 0, S, tid);
+    ld.load(sk0, k_base, 0, S);
+    ld.load(sv0, v_base, 0, S);
     ptx::cp_async_commit();
 
     uint32_t q_frag[KSTEPS][4];
@@ -101,10 +123,12 @@ flash_kernel(const __half* __restrict__ qkv, int S, int heads, float scale, cons
         const int Lh = 2 * gh - 1, Lw = 2 * gw - 1;
         const int ph = (Lh + 63) / 64, pw = (Lw + 63) / 64;
         const int n_pass = ph + pw;
+        TileLoader<HD> ldt;
+        ldt.init(tid, HD);
         auto issue = [&](int pass) {
             const bool is_h = pass < ph;
             const int p = is_h ? pass : pass - ph;
-            fa_load_tile<HD>((pass & 1) ? sm.v[1] : sm.k[1], is_h ? Rh : Rw, HD, p * 64, is_h ? Lh : Lw, tid);
+            ldt.load(((pass & 1) ? sv0 : sk0) + KV_BYTES, (is_h ? Rh : Rw) + (long long)p * 64 * HD, p * 64, is_h ? Lh : Lw);
             ptx::cp_async_commit();
         };
         issue(0);
@@ -182,8 +206,9 @@ flash_kernel(const __half* __restrict__ qkv, int S, int heads, float scale, cons
     for (int kt = 0; kt < n_kt; ++kt) {
         const int buf = kt & 1;
         if (kt + 1 < n_kt) {
-            fa_load_tile<HD>(sm.k[buf ^ 1], k_base, row_stride, (kt + 1) * FA_BK, S, tid);
-            fa_load_tile<HD>(sm.v[buf ^ 1], v_base, row_stride, (kt + 1) * FA_BK, S, tid);
+            const long long toff = (long long)(kt + 1) * FA_BK * row_stride;
+            ld.load(sk0 + (buf ^ 1) * KV_BYTES, k_base + toff, (kt + 1) * FA_BK, S);
+            ld.load(sv0 + (buf ^ 1) * KV_BYTES, v_base + toff, (kt + 1) * FA_BK, S);
             ptx::cp_async_commit();
             ptx::cp_async_wait<1>();
         } else {
@@ -192,16 +217,20 @@ flash_kernel(const __half* __restrict__ qkv, int S, int heads, float scale, cons
         __syncthreads();
         if (warp_active) {
             fa_qk<HD>(sm.k[buf], q_frag, s_acc, lane, 4);
-            // ---- scale, bias, mask (log2 domain)
+            // ---- scale, bias, mask (log2 domain). Fast path: the key tile is one key row, so rel_h is a per-row scalar
+            // bh for the whole tile: it is folded into the softmax reference (p = 2^(s' - (m - bh))) instead of being
+            // added to all 64 scores.
             const int kbase = kt * FA_BK;
+            float bh[2] = {0.f, 0.f};
             if (BIAS && fast_bias) {
-                const float bh0 = sm.rel_h[r_lo * REL_LD + kt] * L2E, bh1 = sm.rel_h[(r_lo + 8) * REL_LD + kt] * L2E;
+                bh[0] = sm.rel_h[r_lo * REL_LD + kt] * L2E;
+                bh[1] = sm.rel_h[(r_lo + 8) * REL_LD + kt] * L2E;
 #pragma unroll
                 for (int nt = 0; nt < 8; ++nt)
 #pragma unroll
                     for (int e = 0; e < 2; ++e) {
-                        s_acc[nt][e] = fmaf(s_acc[nt][e], sl2, bh0 + rw[nt * 4 + e]);
-                        s_acc[nt][2 + e] = fmaf(s_acc[nt][2 + e], sl2, bh1 + rw[nt * 4 + 2 + e]);
+                        s_acc[nt][e] = fmaf(s_acc[nt][e], sl2, rw[nt * 4 + e]);
+                        s_acc[nt][2 + e] = fmaf(s_acc[nt][2 + e], sl2, rw[nt * 4 + 2 + e]);
                     }
             } else {
 #pragma unroll
@@ -221,28 +250,27 @@ flash_kernel(const __half* __restrict__ qkv, int S, int heads, float scale, cons
                     }
             }
             // ---- online softmax
-            float mx[2] = {m_run[0], m_run[1]};
+            float mx[2] = {-INFINITY, -INFINITY};
 #pragma unroll
             for (int nt = 0; nt < 8; ++nt) {
                 mx[0] = fmaxf(mx[0], fmaxf(s_acc[nt][0], s_acc[nt][1]));
                 mx[1] = fmaxf(mx[1], fmaxf(s_acc[nt][2], s_acc[nt][3]));
             }
+            float alpha[2], mref[2], rs[2] = {0.f, 0.f};
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 mx[h] = fmaxf(mx[h], __shfl_xor_sync(0xffffffffu, mx[h], 1));
                 mx[h] = fmaxf(mx[h], __shfl_xor_sync(0xffffffffu, mx[h], 2));
-            }
-            float alpha[2], rs[2] = {0.f, 0.f};
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                alpha[h] = exp2f(m_run[h] - mx[h]);
-                m_run[h] = mx[h];
+                const float m_new = fmaxf(m_run[h], mx[h] + bh[h]);
+                alpha[h] = ptx::ex2(m_run[h] - m_new);
+                m_run[h] = m_new;
+                mref[h] = m_new - bh[h];
             }
             uint32_t p_frag[4][4];
 #pragma unroll
             for (int nt = 0; nt < 8; ++nt) {
-                const float p0 = exp2f(s_acc[nt][0] - mx[0]), p1 = exp2f(s_acc[nt][1] - mx[0]);
-                const float p2 = exp2f(s_acc[nt][2] - mx[1]), p3 = exp2f(s_acc[nt][3] - mx[1]);
+                const float p0 = ptx::ex2(s_acc[nt][0] - mref[0]), p1 = ptx::ex2(s_acc[nt][1] - mref[0]);
+                const float p2 = ptx::ex2(s_acc[nt][2] - mref[1]), p3 = ptx::ex2(s_acc[nt][3] - mref[1]);
                 rs[0] += p0 + p1;
                 rs[1] += p2 + p3;
                 p_frag[nt >> 1][(nt & 1) * 2 + 0] = pack_h2(p0, p1);
@@ -250,10 +278,12 @@ flash_kernel(const __half* __restrict__ qkv, int S, int heads, float scale, cons
             }
 #pragma unroll
             for (int h = 0; h < 2; ++h) l_run[h] = l_run[h] * alpha[h] + rs[h];
+            if (__any_sync(0xffffffffu, alpha[0] != 1.0f || alpha[1] != 1.0f)) {  // the running max moves rarely after the first tiles
 #pragma unroll
-            for (int i = 0; i < NT_O; ++i) {
-                o_acc[i][0] *= alpha[0]; o_acc[i][1] *= alpha[0];
-                o_acc[i][2] *= alpha[1]; o_acc[i][3] *= alpha[1];
+                for (int i = 0; i < NT_O; ++i) {
+                    o_acc[i][0] *= alpha[0]; o_acc[i][1] *= alpha[0];
+                    o_acc[i][2] *= alpha[1]; o_acc[i][3] *= alpha[1];
+                }
             }
             // ---- O += P V
 #pragma unroll
@@ -302,8 +332,9 @@ struct WaSmem {
     __half v[WA_MAXS * LD];
     __half th[32 * LD];  // rel-pos tables (L = 2g-1 <= 29 rows for g <= 15), zero-padded to 32 rows
     __half tw[32 * LD];
-    float bias_h[WA_WARPS][16 * WA_REL_LD];
+    float bias_h[WA_WARPS][16 * WA_REL_LD];  // pre-multiplied by log2(e)
     float bias_w[WA_WARPS][16 * WA_REL_LD];
+    uint16_t colmap[256];                    // key index -> kh | kw << 8 (padded to whole 64-key tiles)
 };
 
 template <int HD>
@@ -337,6 +368,10 @@ window_attn_kernel(const __half* __restrict__ qkv, int S, int heads, float scale
         ptx::cp_async16(ptx::smem_u32(sm.tw + r * LD + c * 8), Rw + (long long)(r < Lw ? r : 0) * HD + c * 8, r < Lw);
     }
     ptx::cp_async_commit();
+    for (int k = tid; k < 256; k += WA_THREADS) {
+        const int kh = min(k / gw, gh - 1);
+        sm.colmap[k] = (uint16_t)(kh | (min(k - kh * gw, gw - 1) << 8));
+    }
     ptx::cp_async_wait<0>();
     __syncthreads();
 
@@ -383,7 +418,7 @@ window_attn_kernel(const __half* __restrict__ qkv, int S, int heads, float scale
                         for (int e = 0; e < 2; ++e) {
                             const int j = nt * 8 + 2 * (lane & 3) + e;
                             const int kk = qpos + gdim - 1 - j;
-                            if (kk >= 0 && kk < gdim && j < L) dst[(rl + 8 * hrow) * WA_REL_LD + kk] = s_acc[nt][2 * hrow + e];
+                            if (kk >= 0 && kk < gdim && j < L) dst[(rl + 8 * hrow) * WA_REL_LD + kk] = s_acc[nt][2 * hrow + e] * L2E;
                         }
                 }
             }
@@ -399,20 +434,23 @@ window_attn_kernel(const __half* __restrict__ qkv, int S, int heads, float scale
             const int keys_here = min(64, s_pad - kbase);        // multiple of 16
             fa_qk<HD>(sm.k + kbase * LD, q_frag, s_acc, lane, keys_here >> 4);
 #pragma unroll
-            for (int nt = 0; nt < 8; ++nt)
+            for (int nt = 0; nt < 8; ++nt) {
+                const uint32_t cm2 = *reinterpret_cast<const uint32_t*>(&sm.colmap[kbase + nt * 8 + 2 * (lane & 3)]);  // two columns
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
-                    const int kcol = kbase + nt * 8 + 2 * (lane & 3) + e;
-                    const bool valid = kcol < S;
-                    float b_lo = 0.f, b_hi = 0.f;
-                    if (valid) {
-                        const int kh = (int)(((float)kcol + 0.5f) * inv_gw), kw = kcol - kh * gw;
-                        b_lo = (bh[rl * WA_REL_LD + kh] + bw[rl * WA_REL_LD + kw]) * L2E;
-                        b_hi = (bh[(rl + 8) * WA_REL_LD + kh] + bw[(rl + 8) * WA_REL_LD + kw]) * L2E;
-                    }
-                    s_acc[nt][e] = valid ? fmaf(s_acc[nt][e], sl2, b_lo) : -INFINITY;
-                    s_acc[nt][2 + e] = valid ? fmaf(s_acc[nt][2 + e], sl2, b_hi) : -INFINITY;
+                    const uint32_t cm = e ? (cm2 >> 16) : (cm2 & 0xffffu);
+                    const int kh = cm & 0xff, kw = cm >> 8;
+                    s_acc[nt][e] = fmaf(s_acc[nt][e], sl2, bh[rl * WA_REL_LD + kh] + bw[rl * WA_REL_LD + kw]);
+                    s_acc[nt][2 + e] = fmaf(s_acc[nt][2 + e], sl2, bh[(rl + 8) * WA_REL_LD + kh] + bw[(rl + 8) * WA_REL_LD + kw]);
                 }
+            }
+            if (kbase + 64 > S) {  // only the last key tile has columns past S
+#pragma unroll
+                for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e)
+                        if (kbase + nt * 8 + 2 * (lane & 3) + e >= S) { s_acc[nt][e] = -INFINITY; s_acc[nt][2 + e] = -INFINITY; }
+            }
             float mx[2] = {m_run[0], m_run[1]};
 #pragma unroll
             for (int nt = 0; nt < 8; ++nt) {
@@ -427,14 +465,14 @@ window_attn_kernel(const __half* __restrict__ qkv, int S, int heads, float scale
             float alpha[2], rs[2] = {0.f, 0.f};
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
-                alpha[h] = exp2f(m_run[h] - mx[h]);
+                alpha[h] = ptx::ex2(m_run[h] - mx[h]);
                 m_run[h] = mx[h];
             }
             uint32_t p_frag[4][4];
 #pragma unroll
             for (int nt = 0; nt < 8; ++nt) {
-                const float p0 = exp2f(s_acc[nt][0] - mx[0]), p1 = exp2f(s_acc[nt][1] - mx[0]);
-                const float p2 = exp2f(s_acc[nt][2] - mx[1]), p3 = exp2f(s_acc[nt][3] - mx[1]);
+                const float p0 = ptx::ex2(s_acc[nt][0] - mx[0]), p1 = ptx::ex2(s_acc[nt][1] - mx[0]);
+                const float p2 = ptx::ex2(s_acc[nt][2] - mx[1]), p3 = ptx::ex2(s_acc[nt][3] - mx[1]);
                 rs[0] += p0 + p1;
                 rs[1] += p2 + p3;
                 p_frag[nt >> 1][(nt & 1) * 2 + 0] = pack_h2(p0, p1);

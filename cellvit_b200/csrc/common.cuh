@@ -107,6 +107,15 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const void* tmap, uint
         : "memory");
 }
 
+// L2 prefetch of a tile (no shared-memory destination, no barrier): warms the line fill ahead of the real load
+__device__ __forceinline__ void tma_prefetch_2d(const void* tmap, int c0, int c1) {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"((uint64_t)tmap), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_4d(const void* tmap, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global [%0, {%1, %2, %3, %4}];"
+                 ::"l"((uint64_t)tmap), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+
 // ---- tcgen05 / TMEM
 __device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols)
@@ -219,6 +228,12 @@ __device__ __forceinline__ void umma_commit_pair(uint32_t bar, uint16_t cta_mask
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool pred) {
     int sz = pred ? 16 : 0;
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+}
+// 2^x, single MUFU (exp2f without -use_fast_math adds range/denormal handling: ~8 instructions)
+__device__ __forceinline__ float ex2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>

@@ -137,6 +137,7 @@ int forward_impl(cvb_model& m, const float* x, int B, int H, int W, float* o_np,
     __half* z[4];
     for (int k = 0; k < 4; ++k) z[k] = A.alloc<__half>((size_t)B * T * D);
 
+    __half* ybuf = A.alloc<__half>(rows_max * D);
     for (int i = 0; i < d.depth; ++i) {
         const std::string p = "b" + std::to_string(i);
         bool is_global = !sam;
@@ -156,14 +157,19 @@ int forward_impl(cvb_model& m, const float* x, int B, int H, int W, float* o_np,
         const __half* tw = sam ? f.P<__half>(p + ".relw") : nullptr;
         if (f.live()) f.chk(op_attention(qkv, Gb, S, heads, hd, scale, th, tw, gh, gw, att, st));
         {
+            // attn-out projection writes fp16 y (+bias) in window order; the residual add x += unpartition(y) is fused
+            // into norm2 below (coalesced) -- with K = 1280 a scattered fp32 read-modify-write epilogue is slower than
+            // the main loop (131 -> 69 us per launch), unlike lin2 (K = 5120) which keeps the fp32 residual epilogue.
             TcEpilogue e = Fwd::epi0();
-            e.kind = TC_EPI_RES_F32; e.out = xs; e.ldc = D; e.res = xs; e.ldres = D; e.shift = f.P<float>(p + ".proj.b");
-            if (win) { e.row_map = TC_ROW_WINDOW; e.win_size = ws; e.win_grid = g; e.tok_h = h; e.tok_w = w; }
+            e.kind = TC_EPI_F16; e.out = ybuf; e.ldc = D; e.shift = f.P<float>(p + ".proj.b");
             f.gemm(att, rows, D, p + ".proj.w", D, e);
         }
         const float* n2w = f.P<float>(p + ".n2.w");
         const float* n2b = f.P<float>(p + ".n2.b");
-        if (f.live()) f.chk(op_layernorm_f16(xs, n2w, n2b, 1e-6f, B * Tx, D, ln, 0, B, h, w, ws, g, st));
+        {
+            LnFuse lf{ybuf, win ? 1 : 0, xs, nullptr, 0, Tx, 1};
+            if (f.live()) f.chk(op_residual_ln(xs, lf, n2w, n2b, 1e-6f, B * Tx, D, ln, 0, B, h, w, ws, g, st));
+        }
         {
             TcEpilogue e = Fwd::epi0();
             e.kind = TC_EPI_F16; e.act = TC_ACT_GELU; e.out = hid; e.ldc = 4 * D; e.shift = f.P<float>(p + ".fc1.b");

@@ -15,6 +15,24 @@ int op_patch_im2col(const float* x, int B, int H, int W, int P, __half* out, cud
 int op_layernorm_f16(const float* x, const float* gamma, const float* beta, float eps, int rows_dst, int D, __half* out,
                      int map, int B, int tok_h, int tok_w, int ws, int g, cudaStream_t stream);
 
+// Residual-fused LayerNorm for the encoder blocks. Per destination row (mapping as in op_layernorm_f16):
+//   v = x[src] (+ add[add_row])            add fp16: the previous GEMM's output (attn-out proj or MLP lin2 + bias)
+//   x_out[src] = v      (fp32, if set)     -- the residual update  x = x + f(x)  happens here, fully coalesced,
+//   cast_out[..] = v    (fp16, if set)        instead of as a scattered fp32 read-modify-write in the GEMM epilogue
+//   out[dst] = LayerNorm(v)  (if norm != 0)
+// add_map 0: add row = src token row; 1: add rows are window-partitioned [B, g*g, ws*ws] (image_encoder.py:291-318).
+// cast_out drops the first `cast_skip` rows of every batch item of `tok_per_item` rows (ViT-S cls token).
+struct LnFuse {
+    const __half* add;
+    int add_map;
+    float* x_out;
+    __half* cast_out;
+    int cast_skip, tok_per_item;
+    int norm;
+};
+int op_residual_ln(const float* x, const LnFuse& f, const float* gamma, const float* beta, float eps, int rows_dst, int D,
+                   __half* out, int map, int B, int tok_h, int tok_w, int ws, int g, cudaStream_t stream);
+
 // fp32 [B, T_src, D] rows (skipping `skip` leading rows per batch item) -> fp16 [B, T_src-skip, D].
 int op_cast_rows_f16(const float* x, int B, int T_src, int skip, int D, __half* out, cudaStream_t stream);
 

@@ -87,6 +87,103 @@ layernorm_f16_kernel(const float* __restrict__ x, const float* __restrict__ gamm
     }
 }
 
+__global__ void __launch_bounds__(256)
+residual_ln_kernel(const float* __restrict__ x, LnFuse f, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                   int rows_dst, int D, __half* __restrict__ out, int map, int tok_h, int tok_w, int ws, int g) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= rows_dst) return;
+    long long src = warp;
+    if (map == 1) {
+        const int per_img = g * g * ws * ws;
+        const int b = warp / per_img;
+        const int rem = warp - b * per_img;
+        const int win = rem / (ws * ws), t = rem - win * ws * ws;
+        const int y = (win / g) * ws + t / ws, xq = (win % g) * ws + t % ws;
+        src = (y < tok_h && xq < tok_w) ? ((long long)b * tok_h + y) * tok_w + xq : -1;
+    }
+    const int nv = D >> 2;
+    if (src < 0) {
+        if (f.norm) {
+            __half* o = out + (long long)warp * D;
+            for (int i = lane; i < (D >> 3); i += 32) reinterpret_cast<uint4*>(o)[i] = make_uint4(0, 0, 0, 0);
+        }
+        return;
+    }
+    const float4* xr = reinterpret_cast<const float4*>(x + src * D);
+    const uint2* ar = nullptr;
+    if (f.add) {
+        long long arow = src;
+        if (f.add_map == 1) {
+            const int per_tok = tok_h * tok_w;
+            const int b = (int)(src / per_tok);
+            const int rem = (int)(src - (long long)b * per_tok);
+            const int y = rem / tok_w, xq = rem - y * tok_w;
+            arow = ((long long)(b * g * g + (y / ws) * g + xq / ws) * ws + (y % ws)) * ws + xq % ws;
+        }
+        ar = reinterpret_cast<const uint2*>(f.add + arow * D);
+    }
+    float4 v[LN_MAXV];
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < LN_MAXV; ++k) {
+        const int i = lane + 32 * k;
+        if (i < nv) {
+            v[k] = xr[i];
+            if (ar) {
+                const uint2 h = ar[i];
+                const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&h.x));
+                const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&h.y));
+                v[k].x += a.x; v[k].y += a.y; v[k].z += b.x; v[k].w += b.y;
+            }
+            s += (v[k].x + v[k].y) + (v[k].z + v[k].w);
+        }
+    }
+    if (f.x_out) {
+        float4* xo = reinterpret_cast<float4*>(f.x_out + src * D);
+#pragma unroll
+        for (int k = 0; k < LN_MAXV; ++k) {
+            const int i = lane + 32 * k;
+            if (i < nv) xo[i] = v[k];
+        }
+    }
+    if (f.cast_out) {
+        const int b = (int)(src / f.tok_per_item);
+        const int t = (int)(src - (long long)b * f.tok_per_item);
+        if (t >= f.cast_skip) {
+            uint2* co = reinterpret_cast<uint2*>(f.cast_out + ((long long)b * (f.tok_per_item - f.cast_skip) + t - f.cast_skip) * D);
+#pragma unroll
+            for (int k = 0; k < LN_MAXV; ++k) {
+                const int i = lane + 32 * k;
+                if (i < nv) co[i] = make_uint2(pack_h2(v[k].x, v[k].y), pack_h2(v[k].z, v[k].w));
+            }
+        }
+    }
+    if (!f.norm) return;
+    const float mean = warp_sum(s) / (float)D;
+    float q = 0.f;
+#pragma unroll
+    for (int k = 0; k < LN_MAXV; ++k) {
+        const int i = lane + 32 * k;
+        if (i < nv) {
+            const float a = v[k].x - mean, b = v[k].y - mean, c = v[k].z - mean, d = v[k].w - mean;
+            q += (a * a + b * b) + (c * c + d * d);
+        }
+    }
+    const float rstd = rsqrtf(warp_sum(q) / (float)D + eps);
+    __half* o = out + (long long)warp * D;
+#pragma unroll
+    for (int k = 0; k < LN_MAXV; ++k) {
+        const int i = lane + 32 * k;
+        if (i < nv) {
+            const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma) + i);
+            const float4 bt = __ldg(reinterpret_cast<const float4*>(beta) + i);
+            const float a = (v[k].x - mean) * rstd * gm.x + bt.x, b = (v[k].y - mean) * rstd * gm.y + bt.y;
+            const float c = (v[k].z - mean) * rstd * gm.z + bt.z, d = (v[k].w - mean) * rstd * gm.w + bt.w;
+            reinterpret_cast<uint2*>(o)[i] = make_uint2(pack_h2(a, b), pack_h2(c, d));
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------ casts / layouts
 __global__ void cast_rows_f16_kernel(const float* __restrict__ x, int B, int T_src, int skip, int D, __half* __restrict__ out) {
     const int T = T_src - skip;
@@ -270,6 +367,19 @@ int op_layernorm_f16(const float* x, const float* gamma, const float* beta, floa
     CVB_CHECK(D % 8 == 0 && D <= LN_MAXV * 128, CVB_ESHAPE, "layernorm: D=%d must be a multiple of 8 and <= %d", D, LN_MAXV * 128);
     const int blocks = cdiv(rows_dst, 8);
     layernorm_f16_kernel<<<blocks, 256, 0, stream>>>(x, gamma, beta, eps, rows_dst, D, out, map, tok_h, tok_w, ws, g);
+    cvb_note_launches(1);
+    CVB_CUDA(cudaGetLastError());
+    return CVB_OK;
+}
+
+int op_residual_ln(const float* x, const LnFuse& f, const float* gamma, const float* beta, float eps, int rows_dst, int D,
+                   __half* out, int map, int B, int tok_h, int tok_w, int ws, int g, cudaStream_t stream) {
+    (void)B;
+    CVB_CHECK(x && rows_dst > 0, CVB_EARG, "residual_ln: null operand");
+    CVB_CHECK(!f.norm || (gamma && beta && out), CVB_EARG, "residual_ln: norm requested without gamma/beta/out");
+    CVB_CHECK(D % 8 == 0 && D <= LN_MAXV * 128, CVB_ESHAPE, "residual_ln: D=%d must be a multiple of 8 and <= %d", D, LN_MAXV * 128);
+    CVB_CHECK(!f.cast_out || f.tok_per_item > f.cast_skip, CVB_EARG, "residual_ln: bad cast geometry");
+    residual_ln_kernel<<<cdiv(rows_dst, 8), 256, 0, stream>>>(x, f, gamma, beta, eps, rows_dst, D, out, map, tok_h, tok_w, ws, g);
     cvb_note_launches(1);
     CVB_CUDA(cudaGetLastError());
     return CVB_OK;

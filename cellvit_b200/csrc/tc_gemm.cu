@@ -32,6 +32,7 @@ struct TcParams {
     int conv;
     int chunks0, chunks_per_tap;  // conv: 64-channel chunks of source 0 / of both sources
     int H, W, TW;                 // conv geometry: image size, tile width (tile height = 128 / TW)
+    int l2_prefetch;              // GEMM mode: A k-blocks prefetched into L2 ahead of the smem ring (0 = off)
     uint32_t tmem_cols;
     TcEpilogue epi;
 };
@@ -279,6 +280,14 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUte
                 ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
                 if (!PAIR || rank == 0) ptx::mbar_expect_tx(full_bar(stage), tx_bytes);
                 if (is_a) {
+                    if (!p.conv && p.l2_prefetch > 0) {
+                        // A rows are touched for the first time by all n-tiles of an m-block at once: without this the
+                        // ring waits on a cold DRAM line fill (~3 us under load) for every k-block
+                        int pk = kb + p.l2_prefetch, pm = m0;
+                        if (pk >= num_kb) { pk -= num_kb; pm = -1; const int t2 = tile + tile_step;
+                            if (t2 < p.n_tiles) pm = (t2 / p.n_tiles_n) * TILE_M + (int)rank * BLOCK_M; }
+                        if (pm >= 0 && pk < num_kb && (nt == 0 || pm != m0)) ptx::tma_prefetch_2d(&tmA0, pk * BLOCK_K, pm);
+                    }
                     const uint32_t dst_a = smem_a + stage * A_STAGE_BYTES;
                     const CUtensorMap* ta = &tmA0;
                     int c0 = kb * BLOCK_K, dx = 0, dy = 0;
@@ -618,6 +627,7 @@ struct TcProfile {
 } g_prof;
 
 bool g_pair_enabled = true;
+int g_l2_prefetch = 0;  // measured on B200: no effect on the encoder GEMMs (the A stream is not cold-miss bound); kept as a hook
 
 // pair mode needs at least two 256-row tiles per pair-CTA to pay off and an even B split in 16-row units
 bool use_pair(int M, int N, int block_n) {
@@ -706,6 +716,7 @@ int tc_gemm(const __half* A, int M, int K, long long lda, const __half* W, int N
     }
     TcParams p{};
     p.M = M; p.N = N; p.K = K; p.block_n = block_n; p.num_kb = K / BLOCK_K; p.conv = 0; p.epi = epi;
+    p.l2_prefetch = g_l2_prefetch;
     return launch(ta, ta, tb, p, pair, stream);
 }
 
@@ -836,3 +847,6 @@ extern "C" __attribute__((visibility("default"))) void cvb_tc_set_pair_mode(int 
 
 // Test / ablation hook: 0 = k-block conv only, 1 = patch-resident conv where the shape allows it (default).
 extern "C" __attribute__((visibility("default"))) void cvb_tc_set_conv_patch_mode(int mode) { g_patch_mode = mode; }
+
+// Test / ablation hook: number of A k-blocks prefetched into L2 ahead of the ring in GEMM mode (0 disables).
+extern "C" __attribute__((visibility("default"))) void cvb_tc_set_l2_prefetch(int k) { g_l2_prefetch = k < 0 ? 0 : k; }

@@ -5,7 +5,7 @@ hdr = rows[hi]; ki = hdr.index("Kernel Name"); vi = hdr.index("Metric Value")
 agg = collections.defaultdict(lambda:[0,0.0]); seq=[]
 for r in rows[hi+1:]:
     if len(r) <= vi: continue
-    name = re.sub(r"\(.*","",r[ki]).replace("<unnamed>::","").replace("void ",""); t = float(r[vi].replace(",",""))
+    name = re.sub(r"\(.*","",r[ki]).replace("<unnamed>::","").replace("void ",""); t = float(r[vi].replace(",","") or 0)
     agg[name][0]+=1; agg[name][1]+=t; seq.append((name,t/1e3))
 tot = sum(v[1] for v in agg.values())
 for k,v in sorted(agg.items(), key=lambda kv:-kv[1][1])[:int(sys.argv[2]) if len(sys.argv)>2 else 10]:
