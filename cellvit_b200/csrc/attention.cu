@@ -323,20 +323,24 @@ flash_kernel(const __half* __restrict__ qkv, int S, int heads, float scale, cons
 // One CTA per (window, head): the whole K and V of the window (S <= 208 keys, 14 x 14 = 196 for SAM) stay in shared
 // memory, so the seven warps run their 16-query m-tiles without any block-level synchronisation after the load.
 // Q fragments are read straight from global memory in the MMA A-fragment layout (31 KB per CTA, L1-resident).
-constexpr int WA_WARPS = 7, WA_THREADS = WA_WARPS * 32, WA_MAXS = 208, WA_REL_LD = 15;
+constexpr int WA_WARPS = 7, WA_THREADS = WA_WARPS * 32, WA_MAXS = 208;
 
 template <int HD>
 struct WaSmem {
     static constexpr int LD = HD + 8;
+    static constexpr int GLD = 40;           // row stride (halves) of the 32-column bias operands: 80 B, conflict-free ldmatrix
     __half k[WA_MAXS * LD];
     __half v[WA_MAXS * LD];
-    __half th[32 * LD];  // rel-pos tables (L = 2g-1 <= 29 rows for g <= 15), zero-padded to 32 rows
+    __half th[32 * LD];                      // rel-pos tables (L = 2g-1 <= 29 rows for g <= 15), zero-padded to 32 rows
     __half tw[32 * LD];
-    float bias_h[WA_WARPS][16 * WA_REL_LD];  // pre-multiplied by log2(e)
-    float bias_w[WA_WARPS][16 * WA_REL_LD];
-    uint16_t colmap[256];                    // key index -> kh | kw << 8 (padded to whole 64-key tiles)
+    __half sel[WA_MAXS * GLD];               // Sel[k][j] = 1 where j == kh(k) or j == gh + kw(k): bias = Gsel * Sel^T
+    __half gsel[WA_WARPS][16 * GLD];         // per m-tile: [rel_h(q, 0..gh-1) | rel_w(q, 0..gw-1)] / scale
 };
 
+// The decomposed rel-pos bias is added by the tensor cores: bias[q,k] = rel_h[q, kh(k)] + rel_w[q, kw(k)] is the product
+// of the per-query row Gsel[q, :] = [rel_h | rel_w] (gh + gw <= 30 values) with a constant 0/1 selection matrix, i.e.
+// two extra k-steps of the QK^T MMA instead of ~20 scalar instructions per score. Gsel is stored divided by `scale`
+// so that one factor scale*log2(e) applies to the whole accumulator, FlashAttention-2 style: p = 2^(acc*c - m*c).
 template <int HD>
 __global__ void __launch_bounds__(WA_THREADS, 2)
 window_attn_kernel(const __half* __restrict__ qkv, int S, int heads, float scale, const __half* __restrict__ Rh,
@@ -344,7 +348,7 @@ window_attn_kernel(const __half* __restrict__ qkv, int S, int heads, float scale
     extern __shared__ __align__(16) uint8_t wa_smem_raw[];
     using Smem = WaSmem<HD>;
     Smem& sm = *reinterpret_cast<Smem*>(wa_smem_raw);
-    constexpr int LD = Smem::LD, KSTEPS = HD / 16, NT_O = HD / 8, CH = HD / 8;
+    constexpr int LD = Smem::LD, GLD = Smem::GLD, KSTEPS = HD / 16, NT_O = HD / 8, CH = HD / 8;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = blockIdx.x, bp = g / heads, head = g - bp * heads;
     const int D = heads * HD;
@@ -368,19 +372,25 @@ window_attn_kernel(const __half* __restrict__ qkv, int S, int heads, float scale
         ptx::cp_async16(ptx::smem_u32(sm.tw + r * LD + c * 8), Rw + (long long)(r < Lw ? r : 0) * HD + c * 8, r < Lw);
     }
     ptx::cp_async_commit();
-    for (int k = tid; k < 256; k += WA_THREADS) {
-        const int kh = min(k / gw, gh - 1);
-        sm.colmap[k] = (uint16_t)(kh | (min(k - kh * gw, gw - 1) << 8));
+    // selection matrix and zeroed Gsel tiles (columns gh+gw..31 stay zero)
+    for (int k = tid; k < s_pad; k += WA_THREADS) {  // one key row per thread: zero 32 columns, then set its two ones
+        uint4* row = reinterpret_cast<uint4*>(sm.sel + k * GLD);
+        row[0] = row[1] = row[2] = row[3] = make_uint4(0, 0, 0, 0);
+        if (k < S) {
+            const int kh = k / gw, kw = k - kh * gw;
+            sm.sel[k * GLD + kh] = __float2half(1.0f);
+            sm.sel[k * GLD + gh + kw] = __float2half(1.0f);
+        }
     }
+    for (int i = tid; i < WA_WARPS * 16 * GLD; i += WA_THREADS) (&sm.gsel[0][0])[i] = __float2half(0.0f);
     ptx::cp_async_wait<0>();
     __syncthreads();
 
     constexpr float L2E = 1.4426950408889634f;
-    const float sl2 = scale * L2E;
+    const float sl2 = scale * L2E, inv_scale = 1.0f / scale;
     const float inv_gw = 1.0f / (float)gw;
     const int n_mt = s_pad >> 4, n_kt = (S + 63) >> 6;
-    float* bh = sm.bias_h[warp];
-    float* bw = sm.bias_w[warp];
+    __half* gs = sm.gsel[warp];
     const int rl = lane >> 2;  // local row of c0/c1; c2/c3 are rl + 8
 
     for (int mt = warp; mt < n_mt; mt += WA_WARPS) {
@@ -400,12 +410,11 @@ window_attn_kernel(const __half* __restrict__ qkv, int S, int heads, float scale
             }
         }
         float s_acc[8][4];
-        // ---- rel-pos: G = Q T^T, scattered to bias[row][k = qpos + g - 1 - j]
+        // ---- rel-pos: G = Q T^T (unscaled q), scattered to Gsel[row][kk] with kk = qpos + g - 1 - j
 #pragma unroll
         for (int tbl = 0; tbl < 2; ++tbl) {
-            const int L = tbl == 0 ? Lh : Lw, gdim = tbl == 0 ? gh : gw;
+            const int L = tbl == 0 ? Lh : Lw, gdim = tbl == 0 ? gh : gw, col0 = tbl == 0 ? 0 : gh;
             fa_qk<HD>(tbl == 0 ? sm.th : sm.tw, q_frag, s_acc, lane, (L + 15) >> 4);
-            float* dst = tbl == 0 ? bh : bw;
 #pragma unroll
             for (int hrow = 0; hrow < 2; ++hrow) {
                 const int t = q0 + rl + 8 * hrow;
@@ -413,35 +422,48 @@ window_attn_kernel(const __half* __restrict__ qkv, int S, int heads, float scale
                     const int qh = (int)(((float)t + 0.5f) * inv_gw);
                     const int qpos = tbl == 0 ? qh : t - qh * gw;
 #pragma unroll
-                    for (int nt = 0; nt < 8; ++nt)
+                    for (int nt = 0; nt < 4; ++nt)  // L <= 29: only the first 32 table rows exist
 #pragma unroll
                         for (int e = 0; e < 2; ++e) {
                             const int j = nt * 8 + 2 * (lane & 3) + e;
                             const int kk = qpos + gdim - 1 - j;
-                            if (kk >= 0 && kk < gdim && j < L) dst[(rl + 8 * hrow) * WA_REL_LD + kk] = s_acc[nt][2 * hrow + e] * L2E;
+                            if (kk >= 0 && kk < gdim && j < L)
+                                gs[(rl + 8 * hrow) * GLD + col0 + kk] = __float2half(s_acc[nt][2 * hrow + e] * inv_scale);
                         }
                 }
             }
         }
         __syncwarp();
+        uint32_t g_frag[2][4];
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+            const int row = (lane & 7) + ((lane >> 3) & 1) * 8;
+            const int col = ks * 16 + (lane >> 4) * 8;
+            ptx::ldmatrix_x4(ptx::smem_u32(gs + row * GLD + col), g_frag[ks][0], g_frag[ks][1], g_frag[ks][2], g_frag[ks][3]);
+        }
 
         float o_acc[NT_O][4];
 #pragma unroll
         for (int i = 0; i < NT_O; ++i) { o_acc[i][0] = o_acc[i][1] = o_acc[i][2] = o_acc[i][3] = 0.f; }
-        float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
+        float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};  // m_run in raw accumulator units
         for (int kt = 0; kt < n_kt; ++kt) {
             const int kbase = kt * 64;
             const int keys_here = min(64, s_pad - kbase);        // multiple of 16
-            fa_qk<HD>(sm.k + kbase * LD, q_frag, s_acc, lane, keys_here >> 4);
+            const int n_pairs = keys_here >> 4;
+            fa_qk<HD>(sm.k + kbase * LD, q_frag, s_acc, lane, n_pairs);
+            // ---- + Gsel * Sel^T (two k-steps over the 32 bias columns)
 #pragma unroll
-            for (int nt = 0; nt < 8; ++nt) {
-                const uint32_t cm2 = *reinterpret_cast<const uint32_t*>(&sm.colmap[kbase + nt * 8 + 2 * (lane & 3)]);  // two columns
+            for (int ks = 0; ks < 2; ++ks) {
 #pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    const uint32_t cm = e ? (cm2 >> 16) : (cm2 & 0xffffu);
-                    const int kh = cm & 0xff, kw = cm >> 8;
-                    s_acc[nt][e] = fmaf(s_acc[nt][e], sl2, bh[rl * WA_REL_LD + kh] + bw[rl * WA_REL_LD + kw]);
-                    s_acc[nt][2 + e] = fmaf(s_acc[nt][2 + e], sl2, bh[(rl + 8) * WA_REL_LD + kh] + bw[(rl + 8) * WA_REL_LD + kw]);
+                for (int np = 0; np < 4; ++np) {
+                    if (np < n_pairs) {
+                        uint32_t b0, b1, b2, b3;
+                        const int row = kbase + np * 16 + (lane & 7) + ((lane >> 4) << 3);
+                        const int col = ks * 16 + ((lane >> 3) & 1) * 8;
+                        ptx::ldmatrix_x4(ptx::smem_u32(sm.sel + row * GLD + col), b0, b1, b2, b3);
+                        ptx::mma_16816(s_acc[2 * np], g_frag[ks], b0, b1);
+                        ptx::mma_16816(s_acc[2 * np + 1], g_frag[ks], b2, b3);
+                    }
                 }
             }
             if (kbase + 64 > S) {  // only the last key tile has columns past S
@@ -457,22 +479,20 @@ window_attn_kernel(const __half* __restrict__ qkv, int S, int heads, float scale
                 mx[0] = fmaxf(mx[0], fmaxf(s_acc[nt][0], s_acc[nt][1]));
                 mx[1] = fmaxf(mx[1], fmaxf(s_acc[nt][2], s_acc[nt][3]));
             }
+            float alpha[2], mneg[2], rs[2] = {0.f, 0.f};
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 mx[h] = fmaxf(mx[h], __shfl_xor_sync(0xffffffffu, mx[h], 1));
                 mx[h] = fmaxf(mx[h], __shfl_xor_sync(0xffffffffu, mx[h], 2));
-            }
-            float alpha[2], rs[2] = {0.f, 0.f};
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                alpha[h] = ptx::ex2(m_run[h] - mx[h]);
+                alpha[h] = ptx::ex2((m_run[h] - mx[h]) * sl2);
                 m_run[h] = mx[h];
+                mneg[h] = -mx[h] * sl2;
             }
             uint32_t p_frag[4][4];
 #pragma unroll
             for (int nt = 0; nt < 8; ++nt) {
-                const float p0 = ptx::ex2(s_acc[nt][0] - mx[0]), p1 = ptx::ex2(s_acc[nt][1] - mx[0]);
-                const float p2 = ptx::ex2(s_acc[nt][2] - mx[1]), p3 = ptx::ex2(s_acc[nt][3] - mx[1]);
+                const float p0 = ptx::ex2(fmaf(s_acc[nt][0], sl2, mneg[0])), p1 = ptx::ex2(fmaf(s_acc[nt][1], sl2, mneg[0]));
+                const float p2 = ptx::ex2(fmaf(s_acc[nt][2], sl2, mneg[1])), p3 = ptx::ex2(fmaf(s_acc[nt][3], sl2, mneg[1]));
                 rs[0] += p0 + p1;
                 rs[1] += p2 + p3;
                 p_frag[nt >> 1][(nt & 1) * 2 + 0] = pack_h2(p0, p1);
@@ -514,7 +534,7 @@ window_attn_kernel(const __half* __restrict__ qkv, int S, int heads, float scale
             if (qr0 < S) *reinterpret_cast<uint32_t*>(o0 + i * 8) = pack_h2(o_acc[i][0] * inv0, o_acc[i][1] * inv0);
             if (qr1 < S) *reinterpret_cast<uint32_t*>(o1 + i * 8) = pack_h2(o_acc[i][2] * inv1, o_acc[i][3] * inv1);
         }
-        __syncwarp();  // bias tables are reused by the warp's next m-tile
+        __syncwarp();  // Gsel is rewritten by the warp's next m-tile
     }
 }
 
@@ -557,7 +577,7 @@ int op_attention(const __half* qkv, int Gb, int S, int heads, int hd, float scal
     CVB_CHECK((Rh == nullptr) == (Rw == nullptr), CVB_EARG, "attention: Rh and Rw must both be set or both null");
     if (Rh) CVB_CHECK(gh * gw == S && gh <= 64 && gw <= 64, CVB_ESHAPE, "attention: bias grid %dx%d does not match S=%d", gh, gw, S);
     if (!Rh) { gh = 1; gw = S; }
-    if (Rh && S <= WA_MAXS && gh <= 15 && gw <= 15) {  // SAM windows: whole K/V resident in shared memory
+    if (Rh && S <= WA_MAXS && gh <= 15 && gw <= 15 && gh + gw <= 32) {  // SAM windows: whole K/V resident in shared memory
         if (hd == 80) return launch_window<80>(qkv, Gb, S, heads, scale, Rh, Rw, gh, gw, out, stream);
         if (hd == 64) return launch_window<64>(qkv, Gb, S, heads, scale, Rh, Rw, gh, gw, out, stream);
     }
