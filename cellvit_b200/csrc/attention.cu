@@ -16,7 +16,7 @@
 namespace {
 
 constexpr int FA_BQ = 64, FA_BK = 64, FA_THREADS = 128;
-constexpr int REL_LD = 65;  // row stride of the bias tables: rows land in different banks
+constexpr int REL_LD = 66;  // row stride (halves) of the bias tables: 33 words, rows land in different banks
 
 template <int HD, bool BIAS>
 struct FaSmem {
@@ -24,8 +24,8 @@ struct FaSmem {
     __half q[FA_BQ * LD];
     __half k[2][FA_BK * LD];
     __half v[2][FA_BK * LD];
-    float rel_h[BIAS ? FA_BQ * REL_LD : 1];
-    float rel_w[BIAS ? FA_BQ * REL_LD : 1];
+    __half rel_h[BIAS ? FA_BQ * REL_LD : 2];  // fp16 keeps the CTA at 73 KB -> 3 CTAs (12 warps) per SM
+    __half rel_w[BIAS ? FA_BQ * REL_LD : 2];
 };
 
 // 64-row x HD tile loader. Every thread owns the same NJ 16-byte chunks of every tile, so the (row, chunk) split and the
@@ -84,7 +84,7 @@ __device__ __forceinline__ void fa_qk(const __half* tile, const uint32_t (&q_fra
 }
 
 template <int HD, bool BIAS>
-__global__ void __launch_bounds__(FA_THREADS)
+__global__ void __launch_bounds__(FA_THREADS, 3)
 flash_kernel(const __half* __restrict__ qkv, int S, int heads, float scale, const __half* __restrict__ Rh,
              const __half* __restrict__ Rw, int gh, int gw, __half* __restrict__ out) {
     extern __shared__ __align__(16) uint8_t fa_smem_raw[];
@@ -150,7 +150,7 @@ flash_kernel(const __half* __restrict__ qkv, int S, int heads, float scale, cons
             const int rows_here = min(64, L - p * 64);
             if (warp_active) {
                 fa_qk<HD>((pass & 1) ? sm.v[1] : sm.k[1], q_frag, s_acc, lane, (rows_here + 15) >> 4);
-                float* dst = is_h ? sm.rel_h : sm.rel_w;
+                __half* dst = is_h ? sm.rel_h : sm.rel_w;
 #pragma unroll
                 for (int hrow = 0; hrow < 2; ++hrow) {
                     const int row = r_lo + 8 * hrow;
@@ -164,7 +164,7 @@ flash_kernel(const __half* __restrict__ qkv, int S, int heads, float scale, cons
                             for (int e = 0; e < 2; ++e) {
                                 const int j = p * 64 + nt * 8 + 2 * (lane & 3) + e;
                                 const int kk = qpos + gdim - 1 - j;
-                                if (kk >= 0 && kk < gdim && j < L) dst[row * REL_LD + kk] = s_acc[nt][2 * hrow + e];
+                                if (kk >= 0 && kk < gdim && j < L) dst[row * REL_LD + kk] = __float2half(s_acc[nt][2 * hrow + e]);
                             }
                     }
                 }
@@ -192,8 +192,8 @@ flash_kernel(const __half* __restrict__ qkv, int S, int heads, float scale, cons
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
                 const int c = nt * 8 + 2 * (lane & 3) + e;
-                rw[nt * 4 + e] = sm.rel_w[r_lo * REL_LD + c] * L2E;
-                rw[nt * 4 + 2 + e] = sm.rel_w[(r_lo + 8) * REL_LD + c] * L2E;
+                rw[nt * 4 + e] = __half2float(sm.rel_w[r_lo * REL_LD + c]) * L2E;
+                rw[nt * 4 + 2 + e] = __half2float(sm.rel_w[(r_lo + 8) * REL_LD + c]) * L2E;
             }
     }
     const float inv_gw = 1.0f / (float)gw;
@@ -223,8 +223,8 @@ flash_kernel(const __half* __restrict__ qkv, int S, int heads, float scale, cons
             const int kbase = kt * FA_BK;
             float bh[2] = {0.f, 0.f};
             if (BIAS && fast_bias) {
-                bh[0] = sm.rel_h[r_lo * REL_LD + kt] * L2E;
-                bh[1] = sm.rel_h[(r_lo + 8) * REL_LD + kt] * L2E;
+                bh[0] = __half2float(sm.rel_h[r_lo * REL_LD + kt]) * L2E;
+                bh[1] = __half2float(sm.rel_h[(r_lo + 8) * REL_LD + kt]) * L2E;
 #pragma unroll
                 for (int nt = 0; nt < 8; ++nt)
 #pragma unroll
@@ -242,8 +242,8 @@ flash_kernel(const __half* __restrict__ qkv, int S, int heads, float scale, cons
                         float b_lo = 0.f, b_hi = 0.f;
                         if (BIAS && valid) {
                             const int kh = (int)(((float)kcol + 0.5f) * inv_gw), kw = kcol - kh * gw;
-                            b_lo = (sm.rel_h[r_lo * REL_LD + kh] + sm.rel_w[r_lo * REL_LD + kw]) * L2E;
-                            b_hi = (sm.rel_h[(r_lo + 8) * REL_LD + kh] + sm.rel_w[(r_lo + 8) * REL_LD + kw]) * L2E;
+                            b_lo = (__half2float(sm.rel_h[r_lo * REL_LD + kh]) + __half2float(sm.rel_w[r_lo * REL_LD + kw])) * L2E;
+                            b_hi = (__half2float(sm.rel_h[(r_lo + 8) * REL_LD + kh]) + __half2float(sm.rel_w[(r_lo + 8) * REL_LD + kw])) * L2E;
                         }
                         s_acc[nt][e] = valid ? fmaf(s_acc[nt][e], sl2, b_lo) : -INFINITY;
                         s_acc[nt][2 + e] = valid ? fmaf(s_acc[nt][2 + e], sl2, b_hi) : -INFINITY;
