@@ -265,7 +265,7 @@ def run_gpu(args):
                 "launches_per_step": tot_n // Kp, "kernel_ms_per_step": tot_ms / Kp,
                 "executed_tflop_per_step": tot_fl / Kp / 1e12, "algorithmic_tflop_per_step": GFLOP_TC_PER_TILE * B / 1000.0,
                 "share_of_step": (tot_ms / Kp) / (ms_total / K)}
-        if world == 1:
+        if world == 1 and not args.no_cpu:
             cores = os.cpu_count() or 1
             tf, tp = cpu_tile_seconds(cores, 1)
             cpu_base = {"value": 1.0 / (tf + tp), "unit": "tiles/s", "cores": cores, "kind": "port",
@@ -295,6 +295,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling / quick iteration runs)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":

@@ -87,6 +87,7 @@ class CellSegmentationInference:
         self.std = tuple(norm.get("std", (0.5, 0.5, 0.5)))
         # the tile engine always computes fp16 operands / fp32 accumulate (the reference's AMP mode, :314-318)
         self.mixed_precision = True if enforce_mixed_precision else self.run_conf.get("training", {}).get("mixed_precision", False)
+        self._streams = None
 
     @classmethod
     def from_model(cls, model: CellViT, gpu: int) -> "CellSegmentationInference":
@@ -96,6 +97,7 @@ class CellSegmentationInference:
         self.model, self.run_conf = model.eval().to(self.device), {}
         self.mean = self.std = (0.5, 0.5, 0.5)
         self.mixed_precision = True
+        self._streams = None
         return self
 
     def get_cell_predictions_with_tokens(self, predictions: dict, magnification: int = 40) -> Tuple[List[dict], torch.Tensor]:
@@ -117,31 +119,74 @@ class CellSegmentationInference:
     def process_tiles(self, batches: Iterable[torch.Tensor], magnification: int = 40, head_override: dict = None,
                       host_threads: int = 0) -> List[List[dict]]:
         """Hot loop of process_wsi (:306-323) over already normalised batches [B,3,H,W] (pinned host or device
-        tensors). Per batch: H2D, forward, softmax (:500-505), device post-processing, D2H of label maps and instance
-        tables; the host part (contours + dict building, post_proc_cellvit.py:96-151) of batch k overlaps the device
-        work of batch k+1. ``head_override`` replaces head maps before post-processing (bench/test hook: random-init
-        networks emit constant maps). Returns one list of per-tile instance dicts per batch."""
+        tensors). Three streams keep the device busy: the H2D copy of batch k+1 (copy stream) and the softmax
+        (:500-505) + device post-processing + D2H of batch k (post stream) run beside the forward of batch k+1 (the
+        caller's stream); the host part (dict building, post_proc_cellvit.py:96-151) of batch k overlaps them too.
+        ``head_override`` replaces head maps before post-processing (bench/test hook: random-init networks emit
+        constant maps). Returns one list of per-tile instance dicts per batch."""
         from concurrent.futures import ThreadPoolExecutor
         from .post_proc_cellvit import DetectionCellPostProcessor
         proc = DetectionCellPostProcessor(nr_types=self.model.num_nuclei_classes, magnification=magnification, gt=False)
+        dev = torch.device(self.device)
         results, pending = [], None
-        # host_threads > 0 spreads the per-tile dict building over a thread pool; with CPython's GIL this only pays
-        # when cv2.findContours dominates, so the default (0) keeps it on the calling thread.
-        with ThreadPoolExecutor(max_workers=max(1, host_threads)) as pool_:
+        with torch.cuda.device(dev), ThreadPoolExecutor(max_workers=max(1, host_threads)) as pool_:
+            # host_threads > 0 spreads the per-tile dict building over a thread pool; with CPython's GIL this only
+            # pays when cv2.findContours dominates, so the default (0) keeps it on the calling thread.
             pool = pool_ if host_threads > 0 else None
-            for k, patches in enumerate(batches):
-                patches = patches.to(self.device, non_blocking=True)
-                predictions = self.model.forward(patches, retrieve_tokens=True)
+            main = torch.cuda.current_stream(dev)
+            if getattr(self, "_streams", None) is None:
+                self._streams = (torch.cuda.Stream(dev), torch.cuda.Stream(dev))
+            s_in, s_post = self._streams
+            in_buf, consumed, keep = [None, None], [None, None], [None, None]
+
+            def stage(k, patches):
+                """H2D of batch k into device slot k & 1 on the copy stream; returns (device tensor, ready event)."""
+                if patches.is_cuda:
+                    return patches, None
+                slot = k & 1
+                if in_buf[slot] is None or in_buf[slot].shape != patches.shape or in_buf[slot].dtype != patches.dtype:
+                    in_buf[slot] = torch.empty(patches.shape, dtype=patches.dtype, device=dev)
+                    consumed[slot] = torch.cuda.Event()
+                    consumed[slot].record(main)     # the fresh block may still be in use by earlier work on `main`
+                s_in.wait_event(consumed[slot])     # the forward that last read this slot has finished
+                with torch.cuda.stream(s_in):
+                    in_buf[slot].copy_(patches, non_blocking=True)
+                    ready = torch.cuda.Event()
+                    ready.record(s_in)
+                return in_buf[slot], ready
+
+            it = iter(batches)
+            nxt = next(it, None)
+            staged = stage(0, nxt) if nxt is not None else None
+            k = 0
+            while staged is not None:
+                x, ready = staged
+                slot = k & 1
+                if ready is not None:
+                    main.wait_event(ready)
+                predictions = self.model.forward(x, retrieve_tokens=True)
+                fwd_done = torch.cuda.Event()
+                fwd_done.record(main)
+                consumed[slot] = fwd_done
+                nxt = next(it, None)
+                staged = stage(k + 1, nxt) if nxt is not None else None  # overlaps this forward
                 if head_override:
                     predictions.update(head_override)
-                np_map = F.softmax(predictions["nuclei_binary_map"], dim=1)
-                nt_map = F.softmax(predictions["nuclei_type_map"], dim=1)
-                proc.launch_float(np_map, predictions["hv_map"], nt_map, slot=k & 1)
+                s_post.wait_event(fwd_done)
+                with torch.cuda.stream(s_post):
+                    np_map = F.softmax(predictions["nuclei_binary_map"], dim=1)
+                    nt_map = F.softmax(predictions["nuclei_type_map"], dim=1)
+                    proc.launch_float(np_map, predictions["hv_map"], nt_map, slot=slot)
+                keep[slot] = (predictions, np_map, nt_map)  # alive until the D2H event of this batch has completed
                 if pending is not None:
                     results.append(proc.collect(pending, pool)[1])
-                pending = k & 1
+                    keep[pending] = None
+                pending = slot
+                k += 1
             if pending is not None:
                 results.append(proc.collect(pending, pool)[1])
+                keep[pending] = None
+            main.wait_stream(s_post)
         return results
 
     def process_wsi(self, *args, **kwargs):

@@ -525,18 +525,65 @@ struct Heap {
     }
 };
 
+// 4-ary heap of packed 16-byte entries in shared memory (one LDS.128 per entry, four independent child loads per
+// level, depth log4 n). Any correct priority queue gives the same flood because (value, age, index) is a strict
+// total order; the array has 4 slack entries so that the child loads never need a bounds check.
+struct __align__(16) HItem { double v; int age; int idx; };
+__device__ __forceinline__ bool it_less(const HItem& a, const HItem& b) { return h_less(a.v, a.age, a.idx, b.v, b.age, b.idx); }
+struct Heap4 {
+    HItem* a;
+    int n;
+    __device__ __forceinline__ void sift_down(int i, HItem x) {
+        for (;;) {
+            const int c = 4 * i + 1;
+            if (c >= n) break;
+            HItem best = a[c];
+            const HItem t1 = a[c + 1], t2 = a[c + 2], t3 = a[c + 3];
+            int bi = c;
+            if (c + 1 < n && it_less(t1, best)) { best = t1; bi = c + 1; }
+            if (c + 2 < n && it_less(t2, best)) { best = t2; bi = c + 2; }
+            if (c + 3 < n && it_less(t3, best)) { best = t3; bi = c + 3; }
+            if (!it_less(best, x)) break;
+            a[i] = best;
+            i = bi;
+        }
+        a[i] = x;
+    }
+    __device__ __forceinline__ void push(HItem x) {
+        int i = n++;
+        while (i > 0) {
+            const int par = (i - 1) >> 2;
+            const HItem pv = a[par];
+            if (!it_less(x, pv)) break;
+            a[i] = pv;
+            i = par;
+        }
+        a[i] = x;
+    }
+    __device__ __forceinline__ HItem pop() {
+        const HItem top = a[0];
+        --n;
+        if (n > 0) sift_down(0, a[n]);
+        return top;
+    }
+};
+
 // One warp per blob. Seeds = marker pixels that still have an unlabelled mask neighbour (interior seeds pop as
 // no-ops and never change `age`, so leaving them out does not change the result). Heap in shared memory when
 // the blob fits (cap_entries), else in the blob's slice of the global scratch arrays.
 __global__ void __launch_bounds__(32)
 watershed_kernel(const int* __restrict__ queue, const int* __restrict__ qcount_ptr, int* __restrict__ qhead, const int* __restrict__ cnt,
                  const int* __restrict__ off, const int* __restrict__ blobpix, const uint8_t* __restrict__ blb, const int* __restrict__ marker,
-                 const double* __restrict__ dist, Dims d, int cap_entries, double* __restrict__ gkey, int2* __restrict__ gpay,
+                 const double* __restrict__ dist, Dims d, int cap_entries, int rcap, double* __restrict__ gkey, int2* __restrict__ gpay,
                  int* labels_) {
+    // shared memory: [heap: (cap_entries + 4) x 16 B][region dist: rcap x 8 B][region labels: rcap x 4 B]
     extern __shared__ __align__(16) uint8_t ws_smem[];
     volatile int* labels = labels_;
     double* skey = reinterpret_cast<double*>(ws_smem);
     int2* spay = reinterpret_cast<int2*>(ws_smem + (size_t)cap_entries * 8);
+    HItem* sheap = reinterpret_cast<HItem*>(ws_smem);
+    double* sdist = reinterpret_cast<double*>(ws_smem + (size_t)(cap_entries + 4) * 16);
+    int* slab = reinterpret_cast<int*>(ws_smem + (size_t)(cap_entries + 4) * 16 + (size_t)rcap * 8);
     const int lane = threadIdx.x;
     const int qn = *qcount_ptr;
     for (;;) {
@@ -553,6 +600,91 @@ watershed_kernel(const int* __restrict__ queue, const int* __restrict__ qcount_p
         const int* mk = marker + base;
         const double* ds = dist + base;
         volatile int* out = labels + base;
+        // ---- fast path: the blob's bounding box (+1 pixel apron) is staged into shared memory -- mask and label
+        // folded into one int (-1 = outside the mask), dist as fp64 -- and lane 0 runs the serial priority flood
+        // entirely out of shared memory (~0.3 us per pop instead of ~2 us through L2). Local raster indices order
+        // like the global ones, so the (value, age, index) total order is unchanged.
+        {
+            int y0 = d.H, y1 = -1, x0 = d.W, x1 = -1;
+            for (int i = lane; i < n; i += 32) {
+                const int p = list[i];
+                const int y = p / d.W, x = p - y * d.W;
+                y0 = min(y0, y); y1 = max(y1, y); x0 = min(x0, x); x1 = max(x1, x);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                y0 = min(y0, __shfl_xor_sync(0xffffffffu, y0, o));
+                y1 = max(y1, __shfl_xor_sync(0xffffffffu, y1, o));
+                x0 = min(x0, __shfl_xor_sync(0xffffffffu, x0, o));
+                x1 = max(x1, __shfl_xor_sync(0xffffffffu, x1, o));
+            }
+            const int rw = x1 - x0 + 3, rh = y1 - y0 + 3;
+            const long long cells_ll = (long long)rw * rh;
+            if (n <= cap_entries && cells_ll <= (long long)rcap) {
+                const int cells = (int)cells_ll;
+                int* gout = labels_ + base;
+                // only this blob's pixels enter the region (via its pixel list): everything else, including pixels of
+                // other blobs inside the bounding box and the whole apron, is "outside the mask"
+                for (int c = lane; c < cells; c += 32) slab[c] = -1;
+                __syncwarp();
+                for (int i = lane; i < n; i += 32) {
+                    const int p = list[i];
+                    const int y = p / d.W, x = p - y * d.W;
+                    const int c = (y - y0 + 1) * rw + (x - x0 + 1);
+                    slab[c] = gout[p];
+                    sdist[c] = ds[p];
+                }
+                __syncwarp();
+                Heap4 hq;
+                hq.a = sheap;
+                int n_seed = 0;
+                for (int c0 = 0; c0 < cells; c0 += 32) {
+                    const int c = c0 + lane;
+                    bool is_seed = false;
+                    if (c < cells && slab[c] > 0)  // labelled cells are never on the apron, so the four neighbours exist
+                        is_seed = slab[c - rw] == 0 || slab[c - 1] == 0 || slab[c + 1] == 0 || slab[c + rw] == 0;
+                    const uint32_t bits = __ballot_sync(0xffffffffu, is_seed);
+                    if (is_seed) {
+                        HItem it;
+                        it.v = sdist[c]; it.age = 0; it.idx = c;
+                        sheap[n_seed + __popc(bits & ((1u << lane) - 1u))] = it;
+                    }
+                    n_seed += __popc(bits);
+                }
+                __syncwarp();
+                if (lane == 0) {
+                    hq.n = n_seed;
+                    for (int i = (n_seed - 2) / 4; i >= 0 && n_seed > 1; --i) hq.sift_down(i, sheap[i]);  // Floyd heapify
+                    int age = 0;
+                    while (hq.n > 0) {
+                        const HItem t = hq.pop();
+                        const int c = t.idx;
+                        const int lab = slab[c];
+                        const int qs[4] = {c - rw, c - 1, c + 1, c + rw};  // up, left, right, down
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const int q = qs[k];
+                            if (slab[q] == 0) {
+                                ++age;
+                                slab[q] = lab;  // labelled at push time
+                                HItem it;
+                                it.v = sdist[q]; it.age = age; it.idx = q;
+                                hq.push(it);
+                            }
+                        }
+                    }
+                }
+                __syncwarp();
+                for (int i = lane; i < n; i += 32) {
+                    const int p = list[i];
+                    const int y = p / d.W, x = p - y * d.W;
+                    const int lab = slab[(y - y0 + 1) * rw + (x - x0 + 1)];
+                    if (lab > 0 && gout[p] == 0) gout[p] = lab;  // pixels this flood labelled
+                }
+                __syncwarp();
+                continue;
+            }
+        }
         Heap hp;
         if (n <= cap_entries) { hp.key = skey; hp.pay = spay; }
         else { hp.key = gkey + base + off[base + root]; hp.pay = gpay + base + off[base + root]; }
@@ -844,8 +976,10 @@ struct Ws {
     int cap;
     size_t bytes;
 };
-constexpr int SMALL_CAP = 1024;   // heap entries (16 B each) of the many-CTAs-per-SM flood kernel
-constexpr int LARGE_CAP = 12288;  // 192 KB of shared memory
+// Flood kernel shared-memory budgets: heap entries (16 B each) + staged bounding-box cells (12 B each). Blobs that exceed
+// either fall back to the global-memory path of the same kernel.
+constexpr int SMALL_CAP = 1024, SMALL_RCAP = 2304;    // 44 KB -> 5 CTAs per SM
+constexpr int LARGE_CAP = 4096, LARGE_RCAP = 10240;   // 186 KB -> 1 CTA per SM
 
 Ws carve(void* base, int B, int H, int W) {
     Ws w{};
@@ -954,14 +1088,16 @@ int run_pipeline(const Ws& w, const float* hv, Dims d, int n_types, int object_s
     {
         static bool configured = false;
         if (!configured) {
-            CVB_CUDA(cudaFuncSetAttribute(watershed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LARGE_CAP * 16));
+            CVB_CUDA(cudaFuncSetAttribute(watershed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (LARGE_CAP + 4) * 16 + LARGE_RCAP * 12));
             configured = true;
         }
         const int sms = cvb_num_sms();
-        watershed_kernel<<<sms * 12, 32, SMALL_CAP * 16, st>>>(w.queue_s, w.qmeta + 0, w.qmeta + 2, w.cnt1, w.off1, w.blobpix, w.blb,
-                                                               w.marker, w.dist, d, SMALL_CAP, w.gkey, w.gpay, labels);
-        watershed_kernel<<<sms, 32, LARGE_CAP * 16, st>>>(w.queue_l, w.qmeta + 1, w.qmeta + 3, w.cnt1, w.off1, w.blobpix, w.blb,
-                                                          w.marker, w.dist, d, LARGE_CAP, w.gkey, w.gpay, labels);
+        const size_t smem_s = (size_t)(SMALL_CAP + 4) * 16 + (size_t)SMALL_RCAP * 12;
+        const size_t smem_l = (size_t)(LARGE_CAP + 4) * 16 + (size_t)LARGE_RCAP * 12;
+        watershed_kernel<<<sms * 5, 32, smem_s, st>>>(w.queue_s, w.qmeta + 0, w.qmeta + 2, w.cnt1, w.off1, w.blobpix, w.blb,
+                                                      w.marker, w.dist, d, SMALL_CAP, SMALL_RCAP, w.gkey, w.gpay, labels);
+        watershed_kernel<<<sms, 32, smem_l, st>>>(w.queue_l, w.qmeta + 1, w.qmeta + 3, w.cnt1, w.off1, w.blobpix, w.blb,
+                                                  w.marker, w.dist, d, LARGE_CAP, LARGE_RCAP, w.gkey, w.gpay, labels);
     }
     // ---- P8/P9
     if (table && counts) {

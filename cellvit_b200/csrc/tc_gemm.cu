@@ -37,6 +37,26 @@ struct TcParams {
     TcEpilogue epi;
 };
 
+// shared-memory block of the fused 1x1 head (floats): weights transposed to [channel][8 classes], bias, BN
+// (scale, shift) pairs, and the partial-sum exchange buffer of the two epilogue warp groups
+constexpr int HEAD_S_BIAS = 64 * 8;
+constexpr int HEAD_S_SS = HEAD_S_BIAS + 8;
+constexpr int HEAD_S_PART = HEAD_S_SS + 128;
+constexpr int HEAD_S_FLOATS = HEAD_S_PART + 8 * 128;
+constexpr int HEAD_S_BYTES = HEAD_S_FLOATS * 4;
+
+__device__ __forceinline__ void head_smem_fill(float* hs, const TcEpilogue& e, int t, int nthreads) {
+    for (int i = t; i < 64 * 8; i += nthreads) {
+        const int n = i >> 3, k = i & 7;
+        hs[i] = k < e.head_nc ? e.head_w[k * 64 + n] : 0.0f;
+    }
+    if (t < 8) hs[HEAD_S_BIAS + t] = t < e.head_nc ? e.head_b[t] : 0.0f;
+    for (int i = t; i < 64; i += nthreads) {
+        hs[HEAD_S_SS + 2 * i] = e.scale[i];
+        hs[HEAD_S_SS + 2 * i + 1] = e.shift[i];
+    }
+}
+
 __device__ __forceinline__ int map_out_row(const TcEpilogue& e, int m) {
     if (e.row_map == TC_ROW_IDENTITY) return m;
     if (e.row_map == TC_ROW_SEQ) return m + (m / e.row_seq) * e.row_pad + e.row_off;
@@ -64,36 +84,67 @@ __device__ __forceinline__ float apply_act(float v, int act) {
 // issuer and is called right after this thread's last tcgen05.ld when `do_release` is set.
 template <class Release>
 __device__ __forceinline__ void epilogue_tile(const TcEpilogue& e, uint32_t t_addr, int m, bool row_ok, int n0, int n_chunks,
-                                              int half, int last_c, const float* head_w_s, bool do_release, Release release) {
+                                              int half, int last_c, float* head_w_s, bool do_release, Release release) {
     if (e.kind == TC_EPI_HEAD) {
-        if (half != 0) {  // the fused 1x1 head needs all 64 channels of a pixel in one thread
-            if (do_release) release();
-            return;
-        }
+        // Fused BN + ReLU + 1x1 head: the two warps of a lane quadrant each reduce 32 of the 64 channels of their
+        // pixel, exchange the partial class sums through shared memory and the lower warp stores fp32 NCHW.
+        // head_s: hw[64][8] | hb[8] | (scale, shift)[64] | part[8][128]   (filled by head_smem_fill)
+        const float4* hw4 = reinterpret_cast<const float4*>(head_w_s);
+        const float* hb = head_w_s + HEAD_S_BIAS;
+        const float2* ss = reinterpret_cast<const float2*>(head_w_s + HEAD_S_SS);
+        float* part = head_w_s + HEAD_S_PART;
+        uint32_t acc[32];
+        ptx::tmem_ld32(t_addr + half * 32, acc);
+        ptx::tmem_ld_wait();
+        if (do_release) release();
         float hs[8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) hs[k] = head_w_s[8 * 64 + k];
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-            uint32_t acc[32];
-            ptx::tmem_ld32(t_addr + c * 32, acc);
-            ptx::tmem_ld_wait();
-            if (c == 1) if (do_release) release();
+        for (int k = 0; k < 8; ++k) hs[k] = 0.0f;
+        const int nc = e.head_nc;
+        if (nc <= 2) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-                const int n = c * 32 + j;
-                const float v = fmaxf(fmaf(__uint_as_float(acc[j]), __ldg(e.scale + n), __ldg(e.shift + n)), 0.0f);
+                const int n = half * 32 + j;
+                const float2 sc = ss[n];
+                const float v = fmaxf(fmaf(__uint_as_float(acc[j]), sc.x, sc.y), 0.0f);
+                const float4 w0 = hw4[2 * n];
+                hs[0] = fmaf(w0.x, v, hs[0]); hs[1] = fmaf(w0.y, v, hs[1]);
+            }
+        } else if (nc <= 4) {
 #pragma unroll
-                for (int k = 0; k < 8; ++k)
-                    if (k < e.head_nc) hs[k] = fmaf(head_w_s[k * 64 + n], v, hs[k]);
+            for (int j = 0; j < 32; ++j) {
+                const int n = half * 32 + j;
+                const float2 sc = ss[n];
+                const float v = fmaxf(fmaf(__uint_as_float(acc[j]), sc.x, sc.y), 0.0f);
+                const float4 w0 = hw4[2 * n];
+                hs[0] = fmaf(w0.x, v, hs[0]); hs[1] = fmaf(w0.y, v, hs[1]); hs[2] = fmaf(w0.z, v, hs[2]); hs[3] = fmaf(w0.w, v, hs[3]);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const int n = half * 32 + j;
+                const float2 sc = ss[n];
+                const float v = fmaxf(fmaf(__uint_as_float(acc[j]), sc.x, sc.y), 0.0f);
+                const float4 w0 = hw4[2 * n], w1 = hw4[2 * n + 1];
+                hs[0] = fmaf(w0.x, v, hs[0]); hs[1] = fmaf(w0.y, v, hs[1]); hs[2] = fmaf(w0.z, v, hs[2]); hs[3] = fmaf(w0.w, v, hs[3]);
+                hs[4] = fmaf(w1.x, v, hs[4]); hs[5] = fmaf(w1.y, v, hs[5]); hs[6] = fmaf(w1.z, v, hs[6]); hs[7] = fmaf(w1.w, v, hs[7]);
             }
         }
-        if (row_ok) {
+        const int prow = (int)(threadIdx.x & 127);  // quadrant * 32 + lane
+        const int bar_id = 1 + (prow >> 5);
+        if (half == 1) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                if (k < nc) part[k * 128 + prow] = hs[k];
+        }
+        ptx::named_bar_sync(bar_id, 64);
+        if (half == 0 && row_ok) {
             const int img = m / e.head_hw, pix = m - img * e.head_hw;
 #pragma unroll
             for (int k = 0; k < 8; ++k)
-                if (k < e.head_nc) e.head_out[((size_t)img * e.head_nc + k) * e.head_hw + pix] = hs[k];
+                if (k < nc) e.head_out[((size_t)img * nc + k) * e.head_hw + pix] = hs[k] + part[k * 128 + prow] + hb[k];
         }
+        ptx::named_bar_sync(bar_id, 64);  // part[] may be overwritten by the next tile only after it was read
         return;
     }
 
@@ -245,9 +296,7 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUte
         else { ptx::tmem_alloc(tmem_slot, p.tmem_cols); ptx::tmem_relinquish(); }
     }
     if (p.epi.kind == TC_EPI_HEAD && warp >= 4) {
-        const int t = threadIdx.x - 128;
-        for (int i = t; i < p.epi.head_nc * 64; i += NUM_THREADS - 128) head_w_s[i] = p.epi.head_w[i];
-        if (t < p.epi.head_nc) head_w_s[8 * 64 + t] = p.epi.head_b[t];
+        head_smem_fill(head_w_s, p.epi, threadIdx.x - 128, NUM_THREADS - 128);
     }
     ptx::tc_fence_before();
     if (PAIR) ptx::cluster_sync(); else __syncthreads();
@@ -455,9 +504,7 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
         ptx::tmem_relinquish();
     }
     if (p.epi.kind == TC_EPI_HEAD && warp >= 4) {
-        const int t = threadIdx.x - 128;
-        for (int i = t; i < p.epi.head_nc * 64; i += NUM_THREADS - 128) head_w_s[i] = p.epi.head_w[i];
-        if (t < p.epi.head_nc) head_w_s[8 * 64 + t] = p.epi.head_b[t];
+        head_smem_fill(head_w_s, p.epi, threadIdx.x - 128, NUM_THREADS - 128);
     }
     ptx::tc_fence_before();
     __syncthreads();
@@ -646,7 +693,7 @@ int launch(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, T
     p.tmem_cols = cols;
     // 1024 B alignment slack + stages + barriers/tmem slot + head weights; always > half an SM so that
     // one CTA (and one 512-column TMEM allocation) lives on an SM at a time.
-    size_t smem = 1024 + (size_t)stages * (A_STAGE_BYTES + b_stage) + 8 * (2 * MAX_STAGES + 4) + 16 + (8 * 64 + 8) * 4;
+    size_t smem = 1024 + (size_t)stages * (A_STAGE_BYTES + b_stage) + 8 * (2 * MAX_STAGES + 4) + 16 + HEAD_S_BYTES;
     if (smem < 120 * 1024) smem = 120 * 1024;
     static bool configured = false;
     if (!configured) {
@@ -745,7 +792,7 @@ static int conv_patch_launch(const __half* src0, int C0, const __half* src1, int
     p.tiles_x = W / BLOCK_M; p.tiles_y = H / CP_R; p.n_tiles = NB * p.tiles_x * p.tiles_y;
     p.epi = epi;
     const int b_stage = N * BLOCK_K * 2;
-    const int fixed = 1024 + 2 * CP_PATCH_BYTES + 8 * (8 + 2 * CP_MAX_BSTAGES) + 16 + (8 * 64 + 8) * 4;
+    const int fixed = 1024 + 2 * CP_PATCH_BYTES + 8 * (8 + 2 * CP_MAX_BSTAGES) + 16 + HEAD_S_BYTES;
     int bst = (226 * 1024 - fixed) / b_stage;
     if (bst > CP_MAX_BSTAGES) bst = CP_MAX_BSTAGES;
     CVB_CHECK(bst >= 3, CVB_ESHAPE, "conv_patch: not enough shared memory for the weight ring (N=%d)", N);

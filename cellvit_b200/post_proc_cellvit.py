@@ -40,40 +40,52 @@ def magnification_params(magnification, gt: bool = False):
 
 
 class _Workspace:
-    """Device scratch + output buffers for one (B, H, W); reused across calls."""
+    """Device scratch + output buffers for one (B, H, W); reused across calls. Outputs (label maps, instance tables,
+    contours) exist once per pipeline slot, so batch k's results stay intact on the device while batch k+1 runs."""
+
+    N_SLOTS = 2
 
     def __init__(self, B, H, W, device, max_rows):
         need = C.c_size_t()
         L.check(L.lib().cvb_postproc_workspace_bytes(B, H, W, C.byref(need)), "cvb_postproc_workspace_bytes")
         self.key = (B, H, W, str(device), max_rows)
         self.ws = torch.empty(need.value, dtype=torch.uint8, device=device)
-        self.labels = torch.empty(B, H, W, dtype=torch.int32, device=device)
-        self.table = torch.empty(B, max_rows, ROW_DTYPE.itemsize, dtype=torch.uint8, device=device)
-        self.counts = torch.empty(B, dtype=torch.int32, device=device)
         L.check(L.lib().cvb_contours_workspace_bytes(B, H, W, C.byref(need)), "cvb_contours_workspace_bytes")
         self.cws = torch.empty(need.value, dtype=torch.uint8, device=device)
-        self.pts = torch.empty(B, max_rows, MAX_PTS, 2, dtype=torch.int16, device=device)
-        self.npts = torch.empty(B, max_rows, dtype=torch.int32, device=device)
-        # two pinned host slots so that the host can finish batch k while the device runs batch k+1
+        self.dev = [dict(labels=torch.empty(B, H, W, dtype=torch.int32, device=device),
+                         table=torch.empty(B, max_rows, ROW_DTYPE.itemsize, dtype=torch.uint8, device=device),
+                         counts=torch.empty(B, dtype=torch.int32, device=device),
+                         pts=torch.empty(B, max_rows, MAX_PTS, 2, dtype=torch.int16, device=device),
+                         npts=torch.empty(B, max_rows, dtype=torch.int32, device=device)) for _ in range(self.N_SLOTS)]
+        # the synchronous entry points use slot 0
+        d0 = self.dev[0]
+        self.labels, self.table, self.counts, self.pts, self.npts = d0["labels"], d0["table"], d0["counts"], d0["pts"], d0["npts"]
+        # pinned host slots so that the host can finish batch k while the device runs batch k+1
         self.host = [dict(labels=torch.empty(B, H, W, dtype=torch.int32).pin_memory(),
                           table=torch.empty(B, max_rows, ROW_DTYPE.itemsize, dtype=torch.uint8).pin_memory(),
                           pts=torch.empty(B, max_rows, MAX_PTS, 2, dtype=torch.int16).pin_memory(),
                           npts=torch.empty(B, max_rows, dtype=torch.int32).pin_memory(),
-                          counts=torch.empty(B, dtype=torch.int32).pin_memory(), event=None) for _ in range(2)]
+                          counts=torch.empty(B, dtype=torch.int32).pin_memory(), event=None) for _ in range(self.N_SLOTS)]
 
-    def launch_contours(self, B, H, W, max_rows):
-        L.check(L.lib().cvb_contours(L.ptr(self.labels), L.ptr(self.table), L.ptr(self.counts), B, H, W, max_rows, MAX_PTS,
-                                     L.ptr(self.pts), L.ptr(self.npts), L.ptr(self.cws), C.c_size_t(self.cws.numel()), L.stream_ptr()),
+    def launch_contours(self, B, H, W, max_rows, slot=0):
+        d = self.dev[slot]
+        L.check(L.lib().cvb_contours(L.ptr(d["labels"]), L.ptr(d["table"]), L.ptr(d["counts"]), B, H, W, max_rows, MAX_PTS,
+                                     L.ptr(d["pts"]), L.ptr(d["npts"]), L.ptr(self.cws), C.c_size_t(self.cws.numel()), L.stream_ptr()),
                 "cvb_contours")
 
     def copy_to_host(self, slot, n_rows):
-        h = self.host[slot]
-        h["labels"].copy_(self.labels, non_blocking=True)
-        h["counts"].copy_(self.counts, non_blocking=True)
-        h["table"][:, :n_rows].copy_(self.table[:, :n_rows], non_blocking=True)
-        h["pts"][:, :n_rows].copy_(self.pts[:, :n_rows], non_blocking=True)
-        h["npts"][:, :n_rows].copy_(self.npts[:, :n_rows], non_blocking=True)
+        """Enqueue the D2H copies of one batch on the current stream. Every copy is a CONTIGUOUS block: a strided
+        slice such as ``table[:, :n_rows]`` would make torch stage it through a temporary and block the host until
+        the device has drained (which serialises the host dict building with the next batch's device work)."""
+        h, d = self.host[slot], self.dev[slot]
+        h["labels"].copy_(d["labels"], non_blocking=True)
+        h["counts"].copy_(d["counts"], non_blocking=True)
+        for b in range(d["labels"].shape[0]):
+            h["table"][b, :n_rows].copy_(d["table"][b, :n_rows], non_blocking=True)
+            h["pts"][b, :n_rows].copy_(d["pts"][b, :n_rows], non_blocking=True)
+            h["npts"][b, :n_rows].copy_(d["npts"][b, :n_rows], non_blocking=True)
         h["rows_copied"] = n_rows
+        h["stream"] = torch.cuda.current_stream()
         h["event"] = torch.cuda.Event()
         h["event"].record()
         return h
@@ -139,11 +151,12 @@ class DetectionCellPostProcessor:
         B, _, H, W = np_map.shape
         with torch.cuda.device(np_map.device):
             w = self._workspace(B, H, W, np_map.device)
+            d = w.dev[slot]
             nt = nt_map if self.nr_types is not None else None
             L.check(L.lib().cvb_postproc(L.ptr(np_map), L.ptr(hv), L.ptr(nt), B, H, W, 0 if nt is None else nt.shape[1],
-                                         int(self.magnification), L.ptr(w.labels), L.ptr(w.table), L.ptr(w.counts), self.max_rows,
-                                         L.ptr(w.ws), C.c_size_t(w.ws.numel()), L.stream_ptr()), "cvb_postproc")
-            w.launch_contours(B, H, W, self.max_rows)
+                                         int(self.magnification), L.ptr(d["labels"]), L.ptr(d["table"]), L.ptr(d["counts"]),
+                                         self.max_rows, L.ptr(w.ws), C.c_size_t(w.ws.numel()), L.stream_ptr()), "cvb_postproc")
+            w.launch_contours(B, H, W, self.max_rows, slot)
             w.copy_to_host(slot, min(table_rows, self.max_rows))
 
     def collect(self, slot: int, pool=None) -> Tuple[np.ndarray, List[dict]]:
@@ -155,7 +168,10 @@ class DetectionCellPostProcessor:
         if (counts > self.max_rows).any():
             raise L.CvbError(f"instance table overflow: {int(counts.max())} rows needed, max_rows={self.max_rows}")
         if (counts > h["rows_copied"]).any():  # rare: more instances than the eagerly copied prefix
-            h["table"].copy_(w.table); h["pts"].copy_(w.pts); h["npts"].copy_(w.npts)
+            d = w.dev[slot]
+            with torch.cuda.stream(h["stream"]):  # the slot's device buffers are intact until its next launch
+                h["table"].copy_(d["table"]); h["pts"].copy_(d["pts"]); h["npts"].copy_(d["npts"])
+                torch.cuda.current_stream().synchronize()
         lab, tab, pts, npts = h["labels"].numpy(), h["table"].numpy(), h["pts"].numpy(), h["npts"].numpy()
         with_types = self.nr_types is not None
 
@@ -217,7 +233,7 @@ class DetectionCellPostProcessor:
         self.launch_float(np_map.contiguous().float(), hv_map.contiguous().float(),
                           None if nt_map is None else nt_map.contiguous().float(), slot=0)
         _, dicts = self.collect(0)
-        return self._wsp.labels, dicts
+        return self._wsp.dev[0]["labels"], dicts
 
     def post_process_cell_segmentation(self, pred_map: np.ndarray) -> Tuple[np.ndarray, dict]:
         """Reference signature (post_proc_cellvit.py:67-153): pred_map [H,W,4] = (type, np, h, v) or [H,W,3]."""
