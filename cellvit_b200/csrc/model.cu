@@ -208,7 +208,8 @@ int forward_impl(cvb_model& m, const float* x, int B, int H, int W, float* o_np,
         const float* b3 = f.P<float>("neck.3.b");
         const float* cw = f.P<float>("cls.w");
         const float* cb = f.P<float>("cls.b");
-        if (f.live() && o_tissue) f.chk(op_ln_mean_linear(n2, B, T, 256, g3, b3, 1e-6f, cw, cb, d.n_tissue, o_tissue, st));
+        float* lnm = A.alloc<float>(op_ln_mean_linear_scratch_floats(B, T, 256));
+        if (f.live() && o_tissue) f.chk(op_ln_mean_linear(n2, B, T, 256, g3, b3, 1e-6f, cw, cb, d.n_tissue, o_tissue, lnm, st));
     } else {
         const float* gw_ = f.P<float>("norm.w");
         const float* gb_ = f.P<float>("norm.b");

@@ -47,7 +47,8 @@ int op_stem_conv(const float* x, int B, int H, int W, const float* w, const floa
 // SAM neck tail (image_encoder.py:110-113, utils.py:230-233, cellvit.py:613): per image LayerNorm2d over C of
 // y [B, T, C] fp32, mean over T, then Linear(C -> n_out). out [B, n_out] fp32.
 int op_ln_mean_linear(const float* y, int B, int T, int C, const float* gamma, const float* beta, float eps,
-                      const float* w, const float* b, int n_out, float* out, cudaStream_t stream);
+                      const float* w, const float* b, int n_out, float* out, float* scratch, cudaStream_t stream);
+size_t op_ln_mean_linear_scratch_floats(int B, int T, int C);  // size of `scratch` (per-chunk partial sums)
 
 // ViT-256 tissue head (utils.py:171-172): LayerNorm(x[:,0]) then Linear. x [B, T, D] fp32.
 int op_cls_head(const float* x, int B, int T, int D, const float* gamma, const float* beta, float eps,

@@ -265,18 +265,25 @@ stem_conv_kernel(const float* __restrict__ x, int B, int H, int W, const float* 
 }
 
 // ------------------------------------------------------------------------------------------ tissue heads
-// one block (1024 threads) per image; warp w handles rows w, w+32, ...; C <= 256
-__global__ void __launch_bounds__(1024)
-ln_mean_linear_kernel(const float* __restrict__ y, int T, int C, const float* __restrict__ gamma, const float* __restrict__ beta,
-                      float eps, const float* __restrict__ w, const float* __restrict__ bias, int n_out, float* __restrict__ out) {
-    __shared__ float part[32][256 + 1];
-    __shared__ float meanv[256];
-    const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int per = C >> 5;  // channels per lane (C % 32 == 0, per <= 8)
-    float acc[8];
+// Stage 1: grid (chunks, B), 8 warps; each block LayerNorms LNM_ROWS token rows (one warp per row at a time) and writes the
+// per-channel sum of its rows to part[b][chunk][C]. Stage 2: one block per image adds the chunk partials in a fixed
+// order (deterministic), divides by T and applies the linear layer. C <= 256, C % 32 == 0.
+constexpr int LNM_ROWS = 64;
+__global__ void __launch_bounds__(256)
+ln_mean_partial_kernel(const float* __restrict__ y, int T, int C, const float* __restrict__ gamma, const float* __restrict__ beta,
+                       float eps, float* __restrict__ part) {
+    __shared__ float sp[8][256 + 1];
+    const int b = blockIdx.y, chunk = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int per = C >> 5;  // channels per lane (per <= 8)
+    float acc[8], gm[8], bt[8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) acc[k] = 0.f;
-    for (int t = warp; t < T; t += 32) {
+    for (int k = 0; k < 8; ++k) {
+        acc[k] = 0.f;
+        gm[k] = k < per ? gamma[lane + 32 * k] : 0.f;
+        bt[k] = k < per ? beta[lane + 32 * k] : 0.f;
+    }
+    const int t_end = min(T, (chunk + 1) * LNM_ROWS);
+    for (int t = chunk * LNM_ROWS + warp; t < t_end; t += 8) {
         const float* r = y + ((long long)b * T + t) * C;
         float v[8], s = 0.f;
 #pragma unroll
@@ -290,19 +297,31 @@ ln_mean_linear_kernel(const float* __restrict__ y, int T, int C, const float* __
         const float rstd = 1.0f / sqrtf(warp_sum(q) / (float)C + eps);
 #pragma unroll
         for (int k = 0; k < 8; ++k)
-            if (k < per) acc[k] += (v[k] - mean) * rstd * gamma[lane + 32 * k] + beta[lane + 32 * k];
+            if (k < per) acc[k] += (v[k] - mean) * rstd * gm[k] + bt[k];
     }
 #pragma unroll
     for (int k = 0; k < 8; ++k)
-        if (k < per) part[warp][lane + 32 * k] = acc[k];
+        if (k < per) sp[warp][lane + 32 * k] = acc[k];
     __syncthreads();
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
         float s = 0.f;
-        for (int wq = 0; wq < 32; ++wq) s += part[wq][c];
+#pragma unroll
+        for (int wq = 0; wq < 8; ++wq) s += sp[wq][c];
+        part[((long long)b * gridDim.x + chunk) * C + c] = s;
+    }
+}
+__global__ void __launch_bounds__(256)
+mean_linear_kernel(const float* __restrict__ part, int chunks, int T, int C, const float* __restrict__ w, const float* __restrict__ bias,
+                   int n_out, float* __restrict__ out) {
+    __shared__ float meanv[256];
+    const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float s = 0.f;
+        for (int k = 0; k < chunks; ++k) s += part[((long long)b * chunks + k) * C + c];
         meanv[c] = s / (float)T;
     }
     __syncthreads();
-    for (int o = warp; o < n_out; o += 32) {
+    for (int o = warp; o < n_out; o += 8) {
         float s = 0.f;
         for (int c = lane; c < C; c += 32) s += meanv[c] * w[o * C + c];
         s = warp_sum(s);
@@ -411,12 +430,16 @@ int op_stem_conv(const float* x, int B, int H, int W, const float* w, const floa
     return CVB_OK;
 }
 
+size_t op_ln_mean_linear_scratch_floats(int B, int T, int C) { return (size_t)B * ((T + LNM_ROWS - 1) / LNM_ROWS) * C; }
+
 int op_ln_mean_linear(const float* y, int B, int T, int C, const float* gamma, const float* beta, float eps,
-                      const float* w, const float* b, int n_out, float* out, cudaStream_t stream) {
-    CVB_CHECK(y && gamma && beta && w && b && out, CVB_EARG, "ln_mean_linear: null operand");
+                      const float* w, const float* b, int n_out, float* out, float* scratch, cudaStream_t stream) {
+    CVB_CHECK(y && gamma && beta && w && b && out && scratch, CVB_EARG, "ln_mean_linear: null operand");
     CVB_CHECK(C % 32 == 0 && C <= 256, CVB_ESHAPE, "ln_mean_linear: C=%d must be a multiple of 32 and <= 256", C);
-    ln_mean_linear_kernel<<<B, 1024, 0, stream>>>(y, T, C, gamma, beta, eps, w, b, n_out, out);
-    cvb_note_launches(1);
+    const int chunks = (T + LNM_ROWS - 1) / LNM_ROWS;
+    ln_mean_partial_kernel<<<dim3(chunks, B), 256, 0, stream>>>(y, T, C, gamma, beta, eps, scratch);
+    mean_linear_kernel<<<B, 256, 0, stream>>>(scratch, chunks, T, C, w, b, n_out, out);
+    cvb_note_launches(2);
     CVB_CUDA(cudaGetLastError());
     return CVB_OK;
 }

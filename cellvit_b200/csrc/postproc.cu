@@ -14,6 +14,8 @@
 //   P8/P9  per-instance bbox / centroid / class histogram by atomics, compaction in id order   table_*
 #include <float.h>
 
+#include <vector>
+
 #include "../../include/cellvit_b200.h"
 #include "common.cuh"
 
@@ -463,17 +465,26 @@ __global__ void blob_scatter_kernel(const int* __restrict__ L1, const uint8_t* _
         blobpix[base + off[base + r] + k] = (int)(i - base);
     }
 }
-// queue[0]: blobs with <= small_cap pixels, queue[1]: the rest. qcount[2]. entries are global indices b*N + root.
+// Work queues by blob size class (largest first, so that the flood kernels run longest-job-first and end without a
+// long tail): class 0 = more than small_cap pixels (LARGE launch), classes 1..5 = (small_cap/2, small_cap], ... halving,
+// class 5 = everything smaller. qmeta[c] = count of class c, qmeta[8 + c] = its pop cursor. Entries are b*N + root.
+constexpr int NQ_CLASSES = 6;
+__device__ __forceinline__ int blob_size_class(int n, int small_cap) {
+    if (n > small_cap) return 0;
+    int c = 1, lim = small_cap >> 1;
+    while (c < NQ_CLASSES - 1 && n <= lim) { ++c; lim >>= 1; }
+    return c;
+}
 __global__ void blob_queue_kernel(const int* __restrict__ L1, const int* __restrict__ cnt, Dims d, int min_size, int small_cap,
-                                  int* __restrict__ qcount, int* __restrict__ queue_s, int* __restrict__ queue_l) {
+                                  int* __restrict__ qmeta, int* __restrict__ queue, int qstride) {
     const long long total = (long long)d.B * d.N;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const int p = (int)(i % d.N);
         if (L1[i] != p) continue;
         const int n = cnt[i];
         if (n < min_size) continue;
-        if (n <= small_cap) queue_s[atomicAdd(&qcount[0], 1)] = (int)i;
-        else queue_l[atomicAdd(&qcount[1], 1)] = (int)i;
+        const int c = blob_size_class(n, small_cap);
+        queue[(long long)c * qstride + atomicAdd(&qmeta[c], 1)] = (int)i;
     }
 }
 
@@ -528,8 +539,21 @@ struct Heap {
 // 4-ary heap of packed 16-byte entries in shared memory (one LDS.128 per entry, four independent child loads per
 // level, depth log4 n). Any correct priority queue gives the same flood because (value, age, index) is a strict
 // total order; the array has 4 slack entries so that the child loads never need a bounds check.
-struct __align__(16) HItem { double v; int age; int idx; };
-__device__ __forceinline__ bool it_less(const HItem& a, const HItem& b) { return h_less(a.v, a.age, a.idx, b.v, b.age, b.idx); }
+// Entries are two 64-bit integers: k = order-preserving image of the fp64 value (with -0.0 folded onto +0.0, as the
+// floating-point comparison does), ai = age << 32 | index -- so "less" is two integer compares instead of a chain of
+// fp64 ones.
+struct __align__(16) HItem { unsigned long long k, ai; };
+__device__ __forceinline__ unsigned long long f64_order_key(double v) {
+    const long long b = __double_as_longlong(v + 0.0);
+    return b < 0 ? ~(unsigned long long)b : ((unsigned long long)b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ HItem make_item(double v, int age, int idx) {
+    HItem it;
+    it.k = f64_order_key(v);
+    it.ai = ((unsigned long long)(unsigned)age << 32) | (unsigned)idx;
+    return it;
+}
+__device__ __forceinline__ bool it_less(const HItem& a, const HItem& b) { return a.k < b.k || (a.k == b.k && a.ai < b.ai); }
 struct Heap4 {
     HItem* a;
     int n;
@@ -572,7 +596,7 @@ struct Heap4 {
 // no-ops and never change `age`, so leaving them out does not change the result). Heap in shared memory when
 // the blob fits (cap_entries), else in the blob's slice of the global scratch arrays.
 __global__ void __launch_bounds__(32)
-watershed_kernel(const int* __restrict__ queue, const int* __restrict__ qcount_ptr, int* __restrict__ qhead, const int* __restrict__ cnt,
+watershed_kernel(const int* __restrict__ queue_base, int qstride, int* __restrict__ qmeta, int cls_begin, int cls_end, const int* __restrict__ cnt,
                  const int* __restrict__ off, const int* __restrict__ blobpix, const uint8_t* __restrict__ blb, const int* __restrict__ marker,
                  const double* __restrict__ dist, Dims d, int cap_entries, int rcap, double* __restrict__ gkey, int2* __restrict__ gpay,
                  int* labels_) {
@@ -585,7 +609,10 @@ watershed_kernel(const int* __restrict__ queue, const int* __restrict__ qcount_p
     double* sdist = reinterpret_cast<double*>(ws_smem + (size_t)(cap_entries + 4) * 16);
     int* slab = reinterpret_cast<int*>(ws_smem + (size_t)(cap_entries + 4) * 16 + (size_t)rcap * 8);
     const int lane = threadIdx.x;
-    const int qn = *qcount_ptr;
+    for (int cls = cls_begin; cls < cls_end; ++cls) {
+    const int qn = qmeta[cls];
+    const int* queue = queue_base + (long long)cls * qstride;
+    int* qhead = qmeta + 8 + cls;
     for (;;) {
         int item = 0;
         if (lane == 0) item = atomicAdd(qhead, 1);
@@ -644,11 +671,7 @@ watershed_kernel(const int* __restrict__ queue, const int* __restrict__ qcount_p
                     if (c < cells && slab[c] > 0)  // labelled cells are never on the apron, so the four neighbours exist
                         is_seed = slab[c - rw] == 0 || slab[c - 1] == 0 || slab[c + 1] == 0 || slab[c + rw] == 0;
                     const uint32_t bits = __ballot_sync(0xffffffffu, is_seed);
-                    if (is_seed) {
-                        HItem it;
-                        it.v = sdist[c]; it.age = 0; it.idx = c;
-                        sheap[n_seed + __popc(bits & ((1u << lane) - 1u))] = it;
-                    }
+                    if (is_seed) sheap[n_seed + __popc(bits & ((1u << lane) - 1u))] = make_item(sdist[c], 0, c);
                     n_seed += __popc(bits);
                 }
                 __syncwarp();
@@ -658,7 +681,7 @@ watershed_kernel(const int* __restrict__ queue, const int* __restrict__ qcount_p
                     int age = 0;
                     while (hq.n > 0) {
                         const HItem t = hq.pop();
-                        const int c = t.idx;
+                        const int c = (int)(unsigned)t.ai;
                         const int lab = slab[c];
                         const int qs[4] = {c - rw, c - 1, c + 1, c + rw};  // up, left, right, down
 #pragma unroll
@@ -667,9 +690,7 @@ watershed_kernel(const int* __restrict__ queue, const int* __restrict__ qcount_p
                             if (slab[q] == 0) {
                                 ++age;
                                 slab[q] = lab;  // labelled at push time
-                                HItem it;
-                                it.v = sdist[q]; it.age = age; it.idx = q;
-                                hq.push(it);
+                                hq.push(make_item(sdist[q], age, q));
                             }
                         }
                     }
@@ -754,6 +775,7 @@ watershed_kernel(const int* __restrict__ queue, const int* __restrict__ qcount_p
             hn = __shfl_sync(0xffffffffu, hp.n, 0);
         }
     }
+    }  // size classes
 }
 
 // ------------------------------------------------------------------------------------------ instance table (P8/P9)
@@ -773,7 +795,7 @@ __global__ void table_init_kernel(Acc* acc, long long n, int H, int W) {
     }
 }
 __global__ void table_accum_kernel(const int* __restrict__ labels, const uint8_t* __restrict__ tmap, Dims d, int cap, Acc* __restrict__ acc,
-                                   int* __restrict__ status) {
+                                   int* __restrict__ status, int* __restrict__ maxid) {
     const long long total = (long long)d.B * d.N;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const int l = labels[i];
@@ -783,6 +805,7 @@ __global__ void table_accum_kernel(const int* __restrict__ labels, const uint8_t
             continue;
         }
         if (l >= cap) { atomicOr(&status[b], 1); continue; }
+        if (l > maxid[b]) atomicMax(&maxid[b], l);  // bounds the id range table_finalize_kernel scans
         Acc* a = acc + (long long)b * cap + l;
         const int y = p / d.W, x = p - y * d.W;
         atomicAdd(&a->area, 1);
@@ -800,9 +823,11 @@ __global__ void table_accum_kernel(const int* __restrict__ labels, const uint8_t
 }
 // one block per tile: compact present ids in ascending order into rows
 __global__ void __launch_bounds__(256)
-table_finalize_kernel(const Acc* __restrict__ acc, int cap, int n_types, int max_rows, cvb_inst_row* __restrict__ table, int* __restrict__ counts) {
+table_finalize_kernel(const Acc* __restrict__ acc, int cap_, const int* __restrict__ maxid, int n_types, int max_rows,
+                      cvb_inst_row* __restrict__ table, int* __restrict__ counts) {
     const int b = blockIdx.x;
-    const Acc* A = acc + (long long)b * cap;
+    const int cap = min(cap_, maxid[b] + 1);  // ids above the largest label of the tile are absent
+    const Acc* A = acc + (long long)b * cap_;
     cvb_inst_row* rows = table + (long long)b * max_rows;
     __shared__ int s_base, s_first;
     if (threadIdx.x == 0) { s_base = 0; s_first = (A[0].area > 0) ? 0 : 1; }  // no background -> drop the smallest id
@@ -967,7 +992,8 @@ struct Carve {
 };
 struct Ws {
     uint8_t *npbin, *tmap, *blb, *mk, *mk2;
-    int *L1, *cnt1, *off1, *fill1, *blobpix, *Lx, *cntx, *flagx, *rankx, *marker, *bsum, *queue_s, *queue_l, *qmeta, *status;
+    int *L1, *cnt1, *off1, *fill1, *blobpix, *Lx, *cntx, *flagx, *rankx, *marker, *bsum, *queue, *qmeta, *status;
+    int qstride;
     uint32_t* mm;
     unsigned long long* mm64;
     double *sob, *dist0, *dist, *gkey;
@@ -979,7 +1005,23 @@ struct Ws {
 // Flood kernel shared-memory budgets: heap entries (16 B each) + staged bounding-box cells (12 B each). Blobs that exceed
 // either fall back to the global-memory path of the same kernel.
 constexpr int SMALL_CAP = 1024, SMALL_RCAP = 2304;    // 44 KB -> 5 CTAs per SM
-constexpr int LARGE_CAP = 4096, LARGE_RCAP = 10240;   // 186 KB -> 1 CTA per SM
+constexpr int LARGE_CAP = 2560, LARGE_RCAP = 7168;    // 127 KB -> leaves room for two SMALL CTAs beside it
+
+// side stream + events for the forked LARGE flood launch (one set per host thread and device)
+struct Fork { cudaStream_t side; cudaEvent_t fork, join; int dev; };
+Fork* get_fork() {
+    thread_local std::vector<Fork> forks;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+    for (Fork& f : forks) if (f.dev == dev) return &f;
+    Fork f{};
+    f.dev = dev;
+    if (cudaStreamCreateWithFlags(&f.side, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&f.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&f.join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    forks.push_back(f);
+    return &forks.back();
+}
 
 Ws carve(void* base, int B, int H, int W) {
     Ws w{};
@@ -992,8 +1034,9 @@ Ws carve(void* base, int B, int H, int W) {
     w.L1 = c.take<int>(BN); w.cnt1 = c.take<int>(BN); w.off1 = c.take<int>(BN); w.fill1 = c.take<int>(BN); w.blobpix = c.take<int>(BN);
     w.Lx = c.take<int>(BN); w.cntx = c.take<int>(BN); w.flagx = c.take<int>(BN); w.rankx = c.take<int>(BN); w.marker = c.take<int>(BN);
     w.bsum = c.take<int>((size_t)B * nb + 256);
-    w.queue_s = c.take<int>(BN / 8 + 64); w.queue_l = c.take<int>(BN / 8 + 64);
-    w.qmeta = c.take<int>(16); w.status = c.take<int>(B + 16);
+    w.qstride = (int)(BN / 8 + 64);
+    w.queue = c.take<int>((size_t)NQ_CLASSES * w.qstride);
+    w.qmeta = c.take<int>(16); w.status = c.take<int>(2 * B + 32);  // status[B + 16] | maxid[B]
     w.mm = c.take<uint32_t>((size_t)B * 4 + 16); w.mm64 = c.take<unsigned long long>((size_t)B * 4 + 16);
     w.sob = c.take<double>(BN * 2); w.dist0 = c.take<double>(BN); w.dist = c.take<double>(BN);
     w.gkey = c.take<double>(BN); w.gpay = c.take<int2>(BN);
@@ -1084,7 +1127,7 @@ int run_pipeline(const Ws& w, const float* hv, Dims d, int n_types, int object_s
     CVB_CUDA(cudaMemsetAsync(w.fill1, 0, BN * 4, st));
     CVB_CUDA(cudaMemsetAsync(w.qmeta, 0, 16 * 4, st));
     blob_scatter_kernel<<<g, 256, 0, st>>>(w.L1, w.blb, w.off1, d, w.fill1, w.blobpix);
-    blob_queue_kernel<<<g, 256, 0, st>>>(w.L1, w.cnt1, d, 10, SMALL_CAP, w.qmeta, w.queue_s, w.queue_l);
+    blob_queue_kernel<<<g, 256, 0, st>>>(w.L1, w.cnt1, d, 10, SMALL_CAP, w.qmeta, w.queue, w.qstride);
     {
         static bool configured = false;
         if (!configured) {
@@ -1094,17 +1137,26 @@ int run_pipeline(const Ws& w, const float* hv, Dims d, int n_types, int object_s
         const int sms = cvb_num_sms();
         const size_t smem_s = (size_t)(SMALL_CAP + 4) * 16 + (size_t)SMALL_RCAP * 12;
         const size_t smem_l = (size_t)(LARGE_CAP + 4) * 16 + (size_t)LARGE_RCAP * 12;
-        watershed_kernel<<<sms * 5, 32, smem_s, st>>>(w.queue_s, w.qmeta + 0, w.qmeta + 2, w.cnt1, w.off1, w.blobpix, w.blb,
+        // The two launches are independent (disjoint blobs): the LARGE one (few long floods, one CTA per SM) runs on a
+        // forked side stream while the SMALL one fills the rest of the chip. Fork/join with events, so the sequence
+        // stays capturable and the caller's stream sees one ordered unit of work.
+        Fork* fk = get_fork();
+        CVB_CHECK(fk != nullptr, CVB_ECUDA, "cvb_postproc: could not create the side stream");
+        CVB_CUDA(cudaEventRecord(fk->fork, st));
+        CVB_CUDA(cudaStreamWaitEvent(fk->side, fk->fork, 0));
+        watershed_kernel<<<sms, 32, smem_l, fk->side>>>(w.queue, w.qstride, w.qmeta, 0, 1, w.cnt1, w.off1, w.blobpix, w.blb, w.marker,
+                                                        w.dist, d, LARGE_CAP, LARGE_RCAP, w.gkey, w.gpay, labels);
+        CVB_CUDA(cudaEventRecord(fk->join, fk->side));
+        watershed_kernel<<<sms * 5, 32, smem_s, st>>>(w.queue, w.qstride, w.qmeta, 1, NQ_CLASSES, w.cnt1, w.off1, w.blobpix, w.blb,
                                                       w.marker, w.dist, d, SMALL_CAP, SMALL_RCAP, w.gkey, w.gpay, labels);
-        watershed_kernel<<<sms, 32, smem_l, st>>>(w.queue_l, w.qmeta + 1, w.qmeta + 3, w.cnt1, w.off1, w.blobpix, w.blb,
-                                                  w.marker, w.dist, d, LARGE_CAP, LARGE_RCAP, w.gkey, w.gpay, labels);
+        CVB_CUDA(cudaStreamWaitEvent(st, fk->join, 0));
     }
     // ---- P8/P9
     if (table && counts) {
-        CVB_CUDA(cudaMemsetAsync(w.status, 0, (size_t)d.B * 4, st));
+        CVB_CUDA(cudaMemsetAsync(w.status, 0, (size_t)(2 * d.B + 16) * 4, st));  // status[B+16] and maxid[B]
         table_init_kernel<<<grid1d((long long)d.B * w.cap), 256, 0, st>>>(w.acc, (long long)d.B * w.cap, d.H, d.W);
-        table_accum_kernel<<<g, 256, 0, st>>>(labels, have_types ? w.tmap : nullptr, d, w.cap, w.acc, w.status);
-        table_finalize_kernel<<<d.B, 256, 0, st>>>(w.acc, w.cap, have_types ? n_types : 0, max_rows, table, counts);
+        table_accum_kernel<<<g, 256, 0, st>>>(labels, have_types ? w.tmap : nullptr, d, w.cap, w.acc, w.status, w.status + d.B + 16);
+        table_finalize_kernel<<<d.B, 256, 0, st>>>(w.acc, w.cap, w.status + d.B + 16, have_types ? n_types : 0, max_rows, table, counts);
     }
     cvb_note_launches(17 + ((table && counts) ? 3 : 0));
     if (dbg_blb) CVB_CUDA(cudaMemcpyAsync(dbg_blb, w.blb, BN, cudaMemcpyDeviceToDevice, st));

@@ -674,6 +674,7 @@ struct TcProfile {
 } g_prof;
 
 bool g_pair_enabled = true;
+int g_max_ctas = 1 << 30;  // debug knob (cvb_tc_set_max_ctas): restrict the persistent grid, for feed-bandwidth probes
 int g_l2_prefetch = 0;  // measured on B200: no effect on the encoder GEMMs (the A stream is not cold-miss bound); kept as a hook
 
 // pair mode needs at least two 256-row tiles per pair-CTA to pay off and an even B split in 16-row units
@@ -703,7 +704,7 @@ int launch(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, T
     }
     p.n_tiles_n = p.N / p.block_n;
     p.n_tiles = cdiv(p.M, pair ? 2 * BLOCK_M : BLOCK_M) * p.n_tiles_n;
-    const int sms = cvb_num_sms();
+    const int sms = cvb_num_sms() < g_max_ctas ? cvb_num_sms() : g_max_ctas;
     int grid = pair ? 2 * (p.n_tiles < sms / 2 ? p.n_tiles : sms / 2) : (p.n_tiles < sms ? p.n_tiles : sms);
     const bool prof = g_prof.on && g_prof.used + 2 <= g_prof.ev.size();
     if (prof) CVB_CUDA(cudaEventRecord(g_prof.ev[g_prof.used], stream));
@@ -890,6 +891,7 @@ extern "C" __attribute__((visibility("default"))) int cvb_tc_profile_end(double*
 }
 
 // Test / ablation hook: 0 disables the CTA-pair (cta_group::2) path, 1 enables it (default).
+extern "C" __attribute__((visibility("default"))) void cvb_tc_set_max_ctas(int n) { g_max_ctas = n > 0 ? n : (1 << 30); }
 extern "C" __attribute__((visibility("default"))) void cvb_tc_set_pair_mode(int on) { g_pair_enabled = on != 0; }
 
 // Test / ablation hook: 0 = k-block conv only, 1 = patch-resident conv where the shape allows it (default).
