@@ -5,7 +5,9 @@ Mirrored: ``CellSegmentationInference.__init__`` / checkpoint loading (cell_dete
 ``get_cell_predictions_with_tokens`` (:485-514). New for the B200 deployment: ``process_tiles`` -- the per-batch hot
 loop of ``process_wsi`` (:306-323) over an in-memory tile stream, sharded round-robin over ``torch.distributed``
 ranks with one NCCL weight broadcast and an optional all-gather of the per-tile instance tables.
-WSI file IO, edge-cell merging and JSON/GeoJSON export (:244-304, :424-483, :516-902) are "next" rows.
+``process_wsi`` (:244-483) ingests a preprocessed WSI folder (wsi_datamodel.py), pools the cell tokens on the device,
+removes cells detected twice by overlapping tiles (wsi_merge.py) and writes the reference's JSON / GeoJSON / graph files
+(SURVEY 8f rows N2-N4).
 """
 from __future__ import annotations
 
@@ -17,6 +19,12 @@ import torch
 import torch.nn.functional as F
 
 from .cellvit import CellViT, CellViT256, CellViTSAM
+
+
+# cell_detection.py:75-90 (QuPath colours / names of the PanNuke classes)
+COLOR_DICT = {1: [255, 0, 0], 2: [34, 221, 77], 3: [35, 92, 236], 4: [254, 255, 0], 5: [255, 159, 68]}
+TYPE_NUCLEI_DICT = {1: "Neoplastic", 2: "Inflammatory", 3: "Connective", 4: "Dead", 5: "Epithelial"}
+DEFAULT_NUCLEI_TYPES = {"Background": 0, "Neoplastic": 1, "Inflammatory": 2, "Connective": 3, "Dead": 4, "Epithelial": 5}
 
 
 def unflatten_dict(d: dict, sep: str = ".") -> dict:
@@ -116,19 +124,20 @@ class CellSegmentationInference:
         return (x - mean) / std
 
     @torch.no_grad()
-    def process_tiles(self, batches: Iterable[torch.Tensor], magnification: int = 40, head_override: dict = None,
-                      host_threads: int = 0) -> List[List[dict]]:
-        """Hot loop of process_wsi (:306-323) over already normalised batches [B,3,H,W] (pinned host or device
-        tensors). Three streams keep the device busy: the H2D copy of batch k+1 (copy stream) and the softmax
-        (:500-505) + device post-processing + D2H of batch k (post stream) run beside the forward of batch k+1 (the
-        caller's stream); the host part (dict building, post_proc_cellvit.py:96-151) of batch k overlaps them too.
-        ``head_override`` replaces head maps before post-processing (bench/test hook: random-init networks emit
-        constant maps). Returns one list of per-tile instance dicts per batch."""
+    def _pipeline(self, items, magnification: int = 40, head_override=None, with_tokens: bool = False, host_threads: int = 0):
+        """Generator over ``items`` = iterable of (batch [B,3,H,W] pinned-host or device tensor, payload); yields
+        ``(payload, dicts, cell_tokens)`` per batch, in order, where ``dicts`` are the per-tile instance dicts and
+        ``cell_tokens`` (``with_tokens``) one float32 array [n_cells, D] per tile, rows aligned with the dict order.
+
+        Three streams keep the device busy: the H2D copy of batch k+1 (copy stream) and the softmax (:500-505) +
+        device post-processing (+ cell-token pooling) + D2H of batch k (post stream) run beside the forward of batch
+        k+1 (the caller's stream); the host part (dict building, post_proc_cellvit.py:96-151) of batch k overlaps
+        them too. ``head_override`` (dict, or callable(payload) -> dict) replaces head maps before post-processing
+        (bench/test hook: random-init networks emit constant maps)."""
         from concurrent.futures import ThreadPoolExecutor
         from .post_proc_cellvit import DetectionCellPostProcessor
         proc = DetectionCellPostProcessor(nr_types=self.model.num_nuclei_classes, magnification=magnification, gt=False)
         dev = torch.device(self.device)
-        results, pending = [], None
         with torch.cuda.device(dev), ThreadPoolExecutor(max_workers=max(1, host_threads)) as pool_:
             # host_threads > 0 spreads the per-tile dict building over a thread pool; with CPython's GIL this only
             # pays when cv2.findContours dominates, so the default (0) keeps it on the calling thread.
@@ -155,12 +164,19 @@ class CellSegmentationInference:
                     ready.record(s_in)
                 return in_buf[slot], ready
 
-            it = iter(batches)
+            def finish(slot):
+                payload = keep[slot][0]
+                res = proc.collect(slot, pool, with_tokens=with_tokens)
+                dicts, toks = res[1], (res[2] if with_tokens else None)
+                keep[slot] = None
+                return payload, dicts, toks
+
+            it = iter(items)
             nxt = next(it, None)
-            staged = stage(0, nxt) if nxt is not None else None
-            k = 0
+            staged = (stage(0, nxt[0]), nxt[1]) if nxt is not None else None
+            k, pending = 0, None
             while staged is not None:
-                x, ready = staged
+                (x, ready), payload = staged
                 slot = k & 1
                 if ready is not None:
                     main.wait_event(ready)
@@ -169,26 +185,138 @@ class CellSegmentationInference:
                 fwd_done.record(main)
                 consumed[slot] = fwd_done
                 nxt = next(it, None)
-                staged = stage(k + 1, nxt) if nxt is not None else None  # overlaps this forward
-                if head_override:
-                    predictions.update(head_override)
+                staged = (stage(k + 1, nxt[0]), nxt[1]) if nxt is not None else None  # overlaps this forward
+                ov = head_override(payload) if callable(head_override) else head_override
+                if ov:
+                    predictions.update(ov)
                 s_post.wait_event(fwd_done)
                 with torch.cuda.stream(s_post):
                     np_map = F.softmax(predictions["nuclei_binary_map"], dim=1)
                     nt_map = F.softmax(predictions["nuclei_type_map"], dim=1)
-                    proc.launch_float(np_map, predictions["hv_map"], nt_map, slot=slot)
-                keep[slot] = (predictions, np_map, nt_map)  # alive until the D2H event of this batch has completed
+                    proc.launch_float(np_map, predictions["hv_map"], nt_map, slot=slot,
+                                      tokens=predictions["tokens"] if with_tokens else None, patch_size=self.model.patch_size)
+                keep[slot] = (payload, predictions, np_map, nt_map)  # alive until the D2H event of this batch has completed
                 if pending is not None:
-                    results.append(proc.collect(pending, pool)[1])
-                    keep[pending] = None
+                    yield finish(pending)
                 pending = slot
                 k += 1
             if pending is not None:
-                results.append(proc.collect(pending, pool)[1])
-                keep[pending] = None
+                yield finish(pending)
             main.wait_stream(s_post)
-        return results
 
-    def process_wsi(self, *args, **kwargs):
-        raise NotImplementedError("WSI ingest/export is outside the tile hot path (SURVEY.md section 8f, rows N3/N4); "
-                                  "feed tiles through process_tiles")
+    def process_tiles(self, batches: Iterable[torch.Tensor], magnification: int = 40, head_override: dict = None,
+                      host_threads: int = 0) -> List[List[dict]]:
+        """Hot loop of process_wsi (:306-323) over already normalised batches [B,3,H,W] (pinned host or device
+        tensors), see ``_pipeline``. Returns one list of per-tile instance dicts per batch."""
+        return [d for _, d, _ in self._pipeline(((b, None) for b in batches), magnification, head_override, False, host_threads)]
+
+    # ------------------------------------------------------------------ WSI level (SURVEY.md section 8f, rows N2-N4)
+    def process_wsi(self, wsi, subdir_name: str = None, patch_size: int = 1024, overlap: int = 64, batch_size: int = 8,
+                    geojson: bool = False, num_workers: int = None, head_override=None) -> dict:
+        """cell_detection.py:244-483 -- all tiles of one preprocessed WSI -> ``cells.json``, ``cell_detection.json``
+        (+ ``.geojson``) and ``cells.pt`` under ``<patched_slide_path>/cell_detection[/subdir_name]``.
+
+        Same per-cell records as the reference (global bbox / centroid / contour, ``cell_status``, edge information,
+        mean cell token). The forward, post-processing, contour tracing and token pooling run on the GPU through
+        ``_pipeline``; the duplicate removal of overlapping tiles uses the GPU polygon-overlap kernel (wsi_merge.py).
+        Returns the ``cells.json`` dictionary. ``head_override`` is the bench/test hook of ``_pipeline``."""
+        import json
+        import os
+        from torch.utils.data import DataLoader
+        from .wsi_datamodel import CellGraphDataWSI, InferenceTransform, PatchedWSIInference
+        from .wsi_merge import cell_status_batch, get_cell_position, get_edge_patch
+
+        dataset = PatchedWSIInference(wsi, transform=InferenceTransform(self.mean, self.std))
+        if num_workers is None:
+            num_workers = int(np.clip(int(3 / 4 * (os.cpu_count() or 16)), 1, 2 * batch_size))
+        loader = DataLoader(dataset, batch_size=batch_size, num_workers=num_workers, shuffle=False,
+                            collate_fn=dataset.collate_batch, pin_memory=True)
+        nuclei_types = self.run_conf.get("dataset_config", {}).get("nuclei_types", DEFAULT_NUCLEI_TYPES)
+        background = nuclei_types.get("Background", 0)
+        outdir = Path(wsi.patched_slide_path) / "cell_detection"
+        if subdir_name is not None:
+            outdir = outdir / subdir_name
+        outdir.mkdir(exist_ok=True, parents=True)
+
+        cell_dict_wsi, cell_dict_detection, processed_patches = [], [], []
+        tokens_all, positions_all, contours_all = [], [], []
+        scale, psize = wsi.metadata["downsampling"], wsi.metadata["patch_size"]
+        for metadata, dicts, toks in self._pipeline(loader, wsi.metadata["magnification"], head_override, with_tokens=True):
+            for meta, cells, tok in zip(metadata, dicts, toks):
+                row, col = meta["row"], meta["col"]
+                processed_patches.append(f"{row}_{col}")
+                x_global = int(row * psize * scale - (row + 0.5) * overlap)      # :343-350 (x follows the tile ROW)
+                y_global = int(col * psize * scale - (col + 0.5) * overlap)
+                offset_global = np.array([x_global, y_global])
+                keep = [k for k, c in enumerate(cells.values()) if c["type"] != background]
+                if not keep:
+                    continue
+                all_vals = list(cells.values())
+                vals = [all_vals[k] for k in keep]
+                bboxes = np.stack([v["bbox"] for v in vals])
+                status = cell_status_batch(bboxes, 1024, 64)                      # :372-374 (constants as in the reference)
+                on_edge = (bboxes.reshape(len(vals), -1).max(1) == 1024) | (bboxes.reshape(len(vals), -1).min(1) == 0)
+                for n, cell in enumerate(vals):
+                    centroid_global = cell["centroid"] + np.flip(offset_global)
+                    contour_global = cell["contour"] + np.flip(offset_global)
+                    bbox_global = cell["bbox"] + offset_global
+                    cell_dict = {"bbox": bbox_global.tolist(), "centroid": centroid_global.tolist(), "contour": contour_global.tolist(),
+                                 "type_prob": cell["type_prob"], "type": cell["type"], "patch_coordinates": [row, col],
+                                 "cell_status": int(status[n]), "offset_global": offset_global.tolist()}
+                    if on_edge[n]:
+                        position = get_cell_position(cell["bbox"], 1024)
+                        cell_dict["edge_position"] = True
+                        cell_dict["edge_information"] = {"position": position, "edge_patches": get_edge_patch(position, row, col)}
+                    else:
+                        cell_dict["edge_position"] = False
+                    cell_dict_wsi.append(cell_dict)
+                    cell_dict_detection.append({"bbox": cell_dict["bbox"], "centroid": cell_dict["centroid"], "type": cell["type"]})
+                    positions_all.append(torch.Tensor(centroid_global))
+                    contours_all.append(torch.Tensor(contour_global))
+                tokens_all.append(torch.from_numpy(tok[keep]))
+
+        keep_idx = self.post_process_edge_cells(cell_dict_wsi)
+        cell_dict_wsi = [cell_dict_wsi[i] for i in keep_idx]
+        cell_dict_detection = [cell_dict_detection[i] for i in keep_idx]
+        tokens_cat = torch.cat(tokens_all) if tokens_all else torch.zeros(0, self.model.embed_dim)
+        graph = CellGraphDataWSI(x=tokens_cat[keep_idx], positions=torch.stack([positions_all[i] for i in keep_idx]) if keep_idx
+                                 else torch.zeros(0, 2), contours=[contours_all[i] for i in keep_idx],
+                                 metadata={"wsi_metadata": wsi.metadata, "nuclei_types": nuclei_types})
+
+        out_wsi = {"wsi_metadata": wsi.metadata, "processed_patches": processed_patches, "type_map": nuclei_types, "cells": cell_dict_wsi}
+        out_det = {"wsi_metadata": wsi.metadata, "processed_patches": processed_patches, "type_map": nuclei_types, "cells": cell_dict_detection}
+        with open(outdir / "cells.json", "w") as f:
+            json.dump(out_wsi, f, indent=2)
+        with open(outdir / "cell_detection.json", "w") as f:
+            json.dump(out_det, f, indent=2)
+        if geojson:
+            with open(outdir / "cells.geojson", "w") as f:
+                json.dump(self.convert_geojson(cell_dict_wsi, True), f, indent=2)
+            with open(outdir / "cell_detection.geojson", "w") as f:
+                json.dump(self.convert_geojson(cell_dict_wsi, False), f, indent=2)
+        torch.save(graph, outdir / "cells.pt")
+        return out_wsi
+
+    def post_process_edge_cells(self, cell_list: List[dict]) -> List[int]:
+        """cell_detection.py:516-536 -- indices of the cells to keep after the overlap clean-up."""
+        from .wsi_merge import CellPostProcessor
+        return CellPostProcessor(cell_list, None, torch.device(self.device)).post_process_cells()
+
+    @staticmethod
+    def convert_geojson(cell_list: List[dict], polygons: bool = False) -> List[dict]:
+        """cell_detection.py:538-597 -- one MultiPolygon (segmentation) or MultiPoint (detection) feature per type."""
+        import uuid
+        features = []
+        for cell_type in sorted({c["type"] for c in cell_list}):
+            cells = [c for c in cell_list if c["type"] == cell_type]
+            if polygons:
+                coords = [[list(c["contour"]) + [c["contour"][0]]] for c in cells]  # closed rings
+            else:
+                coords = [c["centroid"] for c in cells]
+            features.append({
+                "type": "Feature", "id": str(uuid.uuid4()),
+                "geometry": {"type": "MultiPolygon" if polygons else "MultiPoint", "coordinates": coords},
+                "properties": {"objectType": "annotation",
+                               "classification": {"name": TYPE_NUCLEI_DICT[cell_type], "color": COLOR_DICT[cell_type]}},
+            })
+        return features

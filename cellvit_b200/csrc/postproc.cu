@@ -1166,6 +1166,31 @@ int run_pipeline(const Ws& w, const float* hv, Dims d, int n_types, int object_s
     return CVB_OK;
 }
 
+// ------------------------------------------------------------------------------------------ cell tokens
+// cell_detection.py:397-409: every cell's embedding is the mean of the z4 tokens under its bounding box,
+// tokens[b, :, floor(rmin/P):ceil(rmax/P), floor(cmin/P):ceil(cmax/P)] averaged over the window. One block per cell row,
+// threads over the embedding dimension (reads are strided by h*w in the reference NCHW token layout, but a window is
+// only a handful of tokens; the write is coalesced).
+__global__ void __launch_bounds__(256)
+cell_tokens_kernel(const float* __restrict__ tokens, const cvb_inst_row* __restrict__ table, const int* __restrict__ counts, int D,
+                   int th, int tw, int patch, int max_rows, float* __restrict__ out) {
+    const int b = blockIdx.y;
+    const int n = min(counts[b], max_rows);
+    for (int i = blockIdx.x; i < n; i += gridDim.x) {
+        const cvb_inst_row r = table[(long long)b * max_rows + i];
+        const int r0 = r.rmin / patch, r1 = min(th, (r.rmax + patch - 1) / patch);
+        const int c0 = r.cmin / patch, c1 = min(tw, (r.cmax + patch - 1) / patch);
+        const float inv = 1.0f / (float)((r1 - r0) * (c1 - c0));
+        for (int dch = threadIdx.x; dch < D; dch += blockDim.x) {
+            const float* t = tokens + ((long long)b * D + dch) * th * tw;
+            float s = 0.0f;
+            for (int y = r0; y < r1; ++y)
+                for (int x = c0; x < c1; ++x) s += t[y * tw + x];
+            out[((long long)b * max_rows + i) * D + dch] = s * inv;
+        }
+    }
+}
+
 int check_common(int B, int H, int W, int ksize, int max_rows, const void* ws, size_t ws_bytes, size_t need) {
     CVB_CHECK(B > 0 && H > 0 && W > 0, CVB_EARG, "cvb_postproc: empty shape");
     CVB_CHECK((long long)B * H * W < (1ll << 31), CVB_ESHAPE, "cvb_postproc: batch too large for 32-bit pixel indices");
@@ -1255,6 +1280,17 @@ CVB_API int cvb_contours(const int32_t* labels, const cvb_inst_row* table, const
     contour_kernel<<<dim3((max_rows + 63) / 64, B), 64, 0, st>>>(labels, table, counts, ncomp, d, cap, max_rows, max_pts,
                                                                reinterpret_cast<short2*>(pts), npts);
     cvb_note_launches(5);
+    CVB_CUDA(cudaGetLastError());
+    return CVB_OK;
+}
+
+CVB_API int cvb_cell_tokens(const float* tokens, const cvb_inst_row* table, const int32_t* counts, int B, int D, int th, int tw,
+                            int patch, int max_rows, float* out, void* stream) {
+    CVB_CHECK(tokens && table && counts && out, CVB_EARG, "cvb_cell_tokens: null argument");
+    CVB_CHECK(B > 0 && D > 0 && th > 0 && tw > 0 && patch > 0 && max_rows > 0, CVB_EARG, "cvb_cell_tokens: empty shape");
+    const int gx = max_rows < 4096 ? max_rows : 4096;
+    cell_tokens_kernel<<<dim3(gx, B), 256, 0, (cudaStream_t)stream>>>(tokens, table, counts, D, th, tw, patch, max_rows, out);
+    cvb_note_launches(1);
     CVB_CUDA(cudaGetLastError());
     return CVB_OK;
 }

@@ -145,9 +145,11 @@ class DetectionCellPostProcessor:
             return w.labels, self._rows(w)
 
     # ------------------------------------------------------------------ asynchronous (pipelined) use
-    def launch_float(self, np_map: torch.Tensor, hv: torch.Tensor, nt_map: torch.Tensor, slot: int, table_rows: int = ROWS_COPIED):
+    def launch_float(self, np_map: torch.Tensor, hv: torch.Tensor, nt_map: torch.Tensor, slot: int, table_rows: int = ROWS_COPIED,
+                     tokens: torch.Tensor = None, patch_size: int = 16):
         """Enqueue cvb_postproc and the D2H copies of its results into pinned host slot ``slot`` (0/1) on the current
-        stream; returns immediately. ``collect(slot)`` waits for that slot and builds the per-tile dicts."""
+        stream; returns immediately. ``collect(slot)`` waits for that slot and builds the per-tile dicts. With
+        ``tokens`` [B,D,h,w] the per-cell mean tokens (cell_detection.py:397-409) are pooled on the device too."""
         B, _, H, W = np_map.shape
         with torch.cuda.device(np_map.device):
             w = self._workspace(B, H, W, np_map.device)
@@ -157,31 +159,47 @@ class DetectionCellPostProcessor:
                                          int(self.magnification), L.ptr(d["labels"]), L.ptr(d["table"]), L.ptr(d["counts"]),
                                          self.max_rows, L.ptr(w.ws), C.c_size_t(w.ws.numel()), L.stream_ptr()), "cvb_postproc")
             w.launch_contours(B, H, W, self.max_rows, slot)
+            if tokens is not None:
+                tokens = tokens.contiguous().float()
+                D, th, tw = tokens.shape[1:]
+                if d.get("cell_tokens") is None or d["cell_tokens"].shape[-1] != D:
+                    d["cell_tokens"] = torch.empty(B, self.max_rows, D, dtype=torch.float32, device=np_map.device)
+                L.check(L.lib().cvb_cell_tokens(L.ptr(tokens), L.ptr(d["table"]), L.ptr(d["counts"]), B, D, th, tw, int(patch_size),
+                                                self.max_rows, L.ptr(d["cell_tokens"]), L.stream_ptr()), "cvb_cell_tokens")
             w.copy_to_host(slot, min(table_rows, self.max_rows))
 
-    def collect(self, slot: int, pool=None) -> Tuple[np.ndarray, List[dict]]:
-        """Wait for host slot ``slot`` and assemble the per-tile instance dicts (reference layout)."""
+    def collect(self, slot: int, pool=None, with_tokens: bool = False):
+        """Wait for host slot ``slot`` and assemble the per-tile instance dicts (reference layout). Returns
+        (label maps, dicts) -- or (label maps, dicts, cell tokens per tile) when ``with_tokens``."""
         w = self._wsp
         h = w.host[slot]
         h["event"].synchronize()
         counts = h["counts"].numpy()
         if (counts > self.max_rows).any():
             raise L.CvbError(f"instance table overflow: {int(counts.max())} rows needed, max_rows={self.max_rows}")
+        d = w.dev[slot]
         if (counts > h["rows_copied"]).any():  # rare: more instances than the eagerly copied prefix
-            d = w.dev[slot]
             with torch.cuda.stream(h["stream"]):  # the slot's device buffers are intact until its next launch
                 h["table"].copy_(d["table"]); h["pts"].copy_(d["pts"]); h["npts"].copy_(d["npts"])
                 torch.cuda.current_stream().synchronize()
         lab, tab, pts, npts = h["labels"].numpy(), h["table"].numpy(), h["pts"].numpy(), h["npts"].numpy()
         with_types = self.nr_types is not None
+        kept = [[] for _ in range(len(counts))]
 
         def one(b):
             n = int(counts[b])
             rows = np.frombuffer(tab[b, :n].tobytes(), dtype=ROW_DTYPE)
-            return self.rows_to_dict(lab[b], rows, with_types, pts[b, :n], npts[b, :n])
+            return self.rows_to_dict(lab[b], rows, with_types, pts[b, :n], npts[b, :n], kept[b])
 
         dicts = [one(b) for b in range(len(counts))] if pool is None else list(pool.map(one, range(len(counts))))
-        return lab, dicts
+        if not with_tokens:
+            return lab, dicts
+        toks = []
+        with torch.cuda.stream(h["stream"]):
+            for b in range(len(counts)):
+                t = d["cell_tokens"][b, :int(counts[b])].cpu().numpy()  # exact row count, known only now
+                toks.append(t[kept[b]] if len(kept[b]) else np.zeros((0, t.shape[-1]), np.float32))
+        return lab, dicts, toks
 
     def _rows(self, w: _Workspace) -> List[np.ndarray]:
         counts = w.counts.cpu().numpy()  # synchronises the stream
@@ -194,9 +212,10 @@ class DetectionCellPostProcessor:
     # ------------------------------------------------------------------ host glue (contours, dict format)
     @staticmethod
     def rows_to_dict(labels: np.ndarray, rows: np.ndarray, with_types: bool = True, pts: np.ndarray = None,
-                     npts: np.ndarray = None) -> dict:
+                     npts: np.ndarray = None, kept: list = None) -> dict:
         """Instance table (+ device contours) -> the reference's per-tile dict (post_proc_cellvit.py:96-151).
-        Without device contours, or for instances the device flagged (npts < 0), the contour comes from cv2."""
+        Without device contours, or for instances the device flagged (npts < 0), the contour comes from cv2.
+        ``kept`` (optional list) receives the table row index of every instance that made it into the dict."""
         out = {}
         ids, rmin_, cmin_, rmax_, cmax_ = (rows[k].tolist() for k in ("id", "rmin", "cmin", "rmax", "cmax"))
         cx, cy, tp, ty = rows["cx"].tolist(), rows["cy"].tolist(), rows["type_prob"].tolist(), rows["type"].tolist()
@@ -217,6 +236,8 @@ class DetectionCellPostProcessor:
                     continue
                 contour[:, 0] += cmin
                 contour[:, 1] += rmin
+            if kept is not None:
+                kept.append(i)
             out[np.int32(inst_id)] = {
                 "bbox": np.array([[rmin, cmin], [rmax, cmax]]),
                 "centroid": np.array([cx[i], cy[i]]),

@@ -113,6 +113,23 @@ int cvb_contours_workspace_bytes(int B, int H, int W, size_t* out);
 int cvb_contours(const int32_t* labels, const cvb_inst_row* table, const int32_t* counts, int B, int H, int W, int max_rows,
                  int max_pts, int16_t* pts, int32_t* npts, void* workspace, size_t ws_bytes, void* stream);
 
+/* Cell tokens: replaces the per-cell loop  tokens[idx, :, floor(rmin/P):ceil(rmax/P), floor(cmin/P):ceil(cmax/P)]
+ * -> mean over the window  (cell_segmentation/inference/cell_detection.py:397-409) for the instances in
+ * table[b, :counts[b]]. tokens fp32 [B,D,th,tw] (the forward's `tokens` output), patch = 16 (model.patch_size);
+ * out fp32 [B,max_rows,D]; rows >= counts[b] are left untouched. */
+int cvb_cell_tokens(const float* tokens, const cvb_inst_row* table, const int32_t* counts, int B, int D, int th, int tw,
+                    int patch, int max_rows, float* out, void* stream);
+
+/* Polygon overlap for the WSI-level duplicate removal: replaces the shapely calls of
+ * CellPostProcessor._remove_overlap (cell_segmentation/inference/cell_detection.py:687-767) --
+ * Polygon(contour).area and query.intersection(other).area -- for a list of candidate pairs (envelope hits).
+ * pts_xy fp64 [n_points,2] (all contours concatenated, global WSI coordinates), poly_off int32 [n_poly+1],
+ * pairs int32 [n_pairs,2]. Outputs (device): poly_area fp64 [n_poly] (nullable), inter_area fp64 [n_pairs]; -1 marks
+ * a pair the kernel cannot handle (a contour with more than 128 points or pathological crossing counts): the host
+ * resolves it with the same algorithm. */
+int cvb_polygon_overlap(const double* pts_xy, const int32_t* poly_off, int n_poly, const int32_t* pairs, int n_pairs,
+                        double* poly_area, double* inter_area, void* stream);
+
 /* ------------------------------------------------------------------------------------------------ operator level
  * The individual device operators, exposed for unit parity tests and for callers that want to compose them.
  * cvb_tc_epilogue mirrors TcEpilogue in cellvit_b200/csrc/tc_gemm.h (see that header for field semantics). */

@@ -1,0 +1,196 @@
+"""CPU checks of the WSI-level host logic: position codes against the reference's own
+functions, polygon overlap against analytic and rasterised areas, envelope pairing, the duplicate-removal loop and the
+on-disk WSI layout."""
+import ast
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from cellvit_b200 import wsi_merge as wm
+
+REF = "/root/reference/cell_segmentation/inference/cell_detection.py"
+
+
+def _reference_functions():
+    """The three pure position helpers of the reference, compiled from its source in place (nothing is copied)."""
+    tree = ast.parse(open(REF).read())
+    wanted = {"get_cell_position", "get_cell_position_marging", "get_edge_patch"}
+    mod = ast.Module([n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name in wanted], [])
+    ns = {"np": np, "List": list}
+    exec(compile(mod, REF, "exec"), ns)
+    return ns
+
+
+@pytest.mark.skipif(not os.path.exists(REF), reason="reference tree not present")
+def test_position_codes_match_reference():
+    ref = _reference_functions()
+    rng = np.random.default_rng(0)
+    specials = [0, 1, 63, 64, 65, 959, 960, 961, 1023, 1024]
+    boxes = []
+    for _ in range(4000):
+        r0, c0 = (int(rng.choice(specials)) if rng.random() < 0.5 else int(rng.integers(0, 1000)) for _ in range(2))
+        r1 = int(rng.choice(specials)) if rng.random() < 0.3 else r0 + int(rng.integers(1, 60))
+        c1 = int(rng.choice(specials)) if rng.random() < 0.3 else c0 + int(rng.integers(1, 60))
+        r1, c1 = max(r1, r0 + 1), max(c1, c0 + 1)
+        boxes.append([[r0, c0], [min(r1, 1024), min(c1, 1024)]])
+    boxes = np.array(boxes)
+    status = wm.cell_status_batch(boxes, 1024, 64)
+    for b, s in zip(boxes, status):
+        assert ref["get_cell_position_marging"](b, 1024, 64) == s == wm.get_cell_position_marging(b, 1024, 64)
+        pos = ref["get_cell_position"](b, 1024)
+        assert pos == wm.get_cell_position(b, 1024)
+        assert ref["get_edge_patch"](pos, 5, 7) == wm.get_edge_patch(pos, 5, 7)
+
+
+def _raster_area(polys, ss=8):
+    """Even-odd area of the intersection of polygons by supersampled point sampling (independent of the slab method)."""
+    allp = np.concatenate(polys)
+    x0, y0, x1, y1 = allp[:, 0].min(), allp[:, 1].min(), allp[:, 0].max(), allp[:, 1].max()
+    xs = x0 + (np.arange(int((x1 - x0) * ss)) + 0.5) / ss
+    ys = y0 + (np.arange(int((y1 - y0) * ss)) + 0.5) / ss
+    X, Y = np.meshgrid(xs, ys)
+    inside = np.ones(X.shape, bool)
+    for p in polys:
+        q = np.roll(p, -1, axis=0)
+        ins = np.zeros(X.shape, bool)
+        for (ax, ay), (bx, by) in zip(p, q):
+            if ay == by:
+                continue
+            cond = (ay > Y) != (by > Y)
+            xi = ax + (Y - ay) * (bx - ax) / (by - ay)
+            ins ^= cond & (X < xi)
+        inside &= ins
+    return inside.sum() / ss ** 2
+
+
+def test_polygon_intersection_area_exact_cases():
+    sq = lambda x, y, s: np.array([[x, y], [x + s, y], [x + s, y + s], [x, y + s]], float)
+    assert wm.polygon_area(sq(3, 4, 10)) == 100.0
+    assert wm.polygon_intersection_area(sq(0, 0, 10), sq(5, 5, 10)) == pytest.approx(25.0, abs=1e-12)
+    assert wm.polygon_intersection_area(sq(0, 0, 10), sq(10, 0, 10)) == 0.0           # touching edge
+    assert wm.polygon_intersection_area(sq(0, 0, 10), sq(20, 20, 5)) == 0.0
+    assert wm.polygon_intersection_area(sq(0, 0, 10), sq(2, 2, 3)) == pytest.approx(9.0, abs=1e-12)  # containment
+    tri = np.array([[0, 0], [10, 0], [0, 10]], float)
+    assert wm.polygon_intersection_area(tri, sq(0, 0, 5)) == pytest.approx(25.0, abs=1e-12)
+    assert wm.polygon_intersection_area(tri, sq(0, 0, 10)[::-1]) == pytest.approx(50.0, abs=1e-12)  # orientation-free
+    # non-convex: a U shape against a bar crossing both prongs, far from the origin (global WSI coordinates)
+    u = np.array([[0, 0], [9, 0], [9, 9], [6, 9], [6, 3], [3, 3], [3, 9], [0, 9]], float) + 150000
+    bar = np.array([[-1, 5], [10, 5], [10, 7], [-1, 7]], float) + 150000
+    assert wm.polygon_intersection_area(u, bar) == pytest.approx(12.0, abs=1e-9)
+
+
+def test_polygon_intersection_area_random_contours_vs_raster():
+    import cv2
+    rng = np.random.default_rng(1)
+    for _ in range(12):
+        polys = []
+        for k in range(2):
+            img = np.zeros((64, 64), np.uint8)
+            for _ in range(3):
+                cv2.ellipse(img, (int(rng.integers(20, 44)), int(rng.integers(20, 44))), (int(rng.integers(5, 14)), int(rng.integers(4, 10))),
+                            float(rng.integers(0, 180)), 0, 360, 1, -1)
+            c = cv2.findContours(img, cv2.RETR_TREE, cv2.CHAIN_APPROX_SIMPLE)[0][0].reshape(-1, 2).astype(float)
+            polys.append(c + rng.integers(0, 5, 2))
+        got = wm.polygon_intersection_area(polys[0], polys[1])
+        want = _raster_area(polys)
+        assert abs(got - want) <= 0.02 * max(want, 1.0) + 2.0, (got, want)
+        assert wm.polygon_area(polys[0]) == pytest.approx(_raster_area(polys[:1]), rel=0.03, abs=2.0)
+
+
+def test_envelope_pairs_matches_brute_force():
+    rng = np.random.default_rng(2)
+    lo = rng.uniform(0, 3000, (400, 2))
+    boxes = np.concatenate([lo, lo + rng.uniform(1, 90, (400, 2))], 1)
+    boxes[10] = [100, 100, 128, 128]; boxes[11] = [128, 128, 140, 140]   # touching corners count
+    got = {tuple(p) for p in wm.envelope_pairs(boxes).tolist()}
+    want = set()
+    for i in range(400):
+        for j in range(i + 1, 400):
+            a, b = boxes[i], boxes[j]
+            if a[0] <= b[2] and b[0] <= a[2] and a[1] <= b[3] and b[1] <= a[3]:
+                want.add((i, j))
+    assert got == want and (10, 11) in got
+
+
+def _host_overlap(contours, pairs):
+    area = np.array([wm.polygon_area(c) for c in contours])
+    inter = np.array([wm.polygon_intersection_area(contours[i], contours[j]) for i, j in pairs]) if len(pairs) else np.zeros(0)
+    return area, inter
+
+
+def _cell(contour, status, patch, edge=None):
+    c = {"contour": contour, "cell_status": status, "patch_coordinates": list(patch), "edge_position": edge is not None}
+    if edge is not None:
+        c["edge_information"] = {"position": None, "edge_patches": [list(e) for e in edge]}
+    return c
+
+
+def test_cell_post_processor_removes_duplicates():
+    sq = lambda x, y, s: [[x, y], [x + s, y], [x + s, y + s], [x, y + s]]
+    cells = [
+        _cell(sq(500, 500, 20), 0, (0, 0)),                          # 0 mid cell: always kept
+        _cell(sq(1000, 300, 20), 4, (0, 0)),                         # 1 margin cell of tile (0,0) ...
+        _cell(sq(1002, 301, 24), 8, (0, 1)),                         # 2 ... the same nucleus seen by tile (0,1), larger
+        _cell(sq(1010, 600, 14), 4, (0, 0), edge=[(0, 1)]),          # 3 touches the border, neighbour exists -> dropped
+        _cell(sq(300, 1010, 14), 6, (0, 0), edge=[(1, 0)]),          # 4 touches the border, neighbour (1,0) absent -> kept
+        _cell(sq(1000, 800, 20), 4, (0, 0)),                         # 5 margin cell barely touching 6 (< 1 % overlap)
+        _cell(sq(1019.9, 800, 20), 8, (0, 1)),                       # 6
+        _cell(sq(2000, 50, 30), 2, (0, 1)),                          # 7 chain a-b-c: 7 overlaps 8, 8 overlaps 9
+        _cell(sq(2020, 50, 40), 2, (0, 1)),                          # 8
+        _cell(sq(2050, 50, 30), 2, (0, 1)),                          # 9
+    ]
+    proc = wm.CellPostProcessor(cells, overlap_fn=_host_overlap)
+    assert proc._clean_edge_cells() == [1, 2, 4, 5, 6, 7, 8, 9]
+    keep = proc.post_process_cells()
+    # 1 is replaced by its larger twin 2; 5/6 overlap by 0.1*20/400 = 0.5 % and both stay. Chain, as the reference's loop
+    # runs it (:722-765): round 1 visits 7 -> its partner 8 is selected and consumed, 9 stays; round 2 visits 8 -> its
+    # partner 9 is selected (the query itself is never a candidate, even when it is the larger one); round 3 is clean
+    assert keep == [0, 2, 4, 5, 6, 9]
+
+
+def test_wsi_layout_and_dataset(tmp_path):
+    import yaml
+    from PIL import Image
+    from cellvit_b200.wsi_datamodel import InferenceTransform, PatchedWSIInference, WSI
+    root = tmp_path / "slideA"
+    (root / "patches").mkdir(parents=True)
+    (root / "metadata").mkdir()
+    meta = {"magnification": 40, "base_magnification": 40, "downsampling": 1, "patch_size": 32, "patch_overlap": 4,
+            "label_map": {"background": 0, "tumor": 1}}
+    yaml.safe_dump(meta, open(root / "metadata.yaml", "w"))
+    rng = np.random.default_rng(0)
+    entries, imgs = [], {}
+    for r in range(2):
+        for c in range(2):
+            name = f"slideA_{r}_{c}.png"
+            imgs[name] = rng.integers(0, 256, (32, 32, 3), dtype=np.uint8)
+            Image.fromarray(imgs[name]).save(root / "patches" / name)
+            yaml.safe_dump({"row": r, "col": c, "background_ratio": 0.1}, open(root / "metadata" / f"slideA_{r}_{c}.yaml", "w"))
+            entries.append({name: {"row": r, "col": c, "metadata_path": f"./metadata/slideA_{r}_{c}.yaml"}})
+    json.dump(entries, open(root / "patch_metadata.json", "w"))
+    wsi = WSI(name="slideA", patient="p", slide_path=root, patched_slide_path=root)
+    assert wsi.get_number_patches() == 4 and wsi.metadata["label_map_inverse"] == {0: "background", 1: "tumor"}
+    ds = PatchedWSIInference(wsi, InferenceTransform())
+    x, m = ds[3]
+    assert m["row"] == 1 and m["col"] == 1 and m["name"] == "slideA_1_1.png"
+    want = (torch.from_numpy(imgs["slideA_1_1.png"]).permute(2, 0, 1).float() / 255 - 0.5) / 0.5
+    assert torch.equal(x, want)
+    xb, mb = ds.collate_batch([ds[0], ds[1]])
+    assert tuple(xb.shape) == (2, 3, 32, 32) and [q["col"] for q in mb] == [0, 1]
+
+
+def test_convert_geojson_layout():
+    from cellvit_b200.cell_detection import CellSegmentationInference
+    cells = [{"type": 2, "contour": [[0, 0], [4, 0], [4, 4]], "centroid": [2.5, 1.5]},
+             {"type": 1, "contour": [[9, 9], [12, 9], [12, 12]], "centroid": [11.0, 10.0]},
+             {"type": 2, "contour": [[20, 20], [24, 20], [24, 24]], "centroid": [22.5, 21.5]}]
+    seg = CellSegmentationInference.convert_geojson(cells, True)
+    assert [f["properties"]["classification"]["name"] for f in seg] == ["Neoplastic", "Inflammatory"]
+    assert seg[1]["geometry"]["type"] == "MultiPolygon" and len(seg[1]["geometry"]["coordinates"]) == 2
+    assert seg[1]["geometry"]["coordinates"][0][0] == [[0, 0], [4, 0], [4, 4], [0, 0]]
+    det = CellSegmentationInference.convert_geojson(cells, False)
+    assert det[0]["geometry"] == {"type": "MultiPoint", "coordinates": [[11.0, 10.0]]}
+    assert det[1]["properties"]["classification"]["color"] == [34, 221, 77]
