@@ -272,8 +272,14 @@ def run_gpu(args):
             tot_ms += tc_ms.value; tot_n += tc_n.value; tot_fl += tc_fl.value
         peak, _, how = _peaks()
         achieved = GFLOP_TC_PER_TILE * B * Kp / (tot_ms / 1000.0) / 1000.0  # TFLOP/s
+        traffic, traffic_src = None, None
+        tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
+        if os.path.exists(tpath):  # DRAM bytes per tile-engine launch from the committed ncu pass of this same step
+            tj = json.load(open(tpath))
+            traffic, traffic_src = tj.get("dram_bytes_per_launch"), "profiles/r1_traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum, mean over the step's tile-engine launches)"
         roof = {"bound": "tensor", "kernel": "tc_kernel (tcgen05 GEMM / implicit-GEMM conv)", "achieved": achieved, "peak": peak,
-                "unit": "TFLOP/s", "frac": achieved / peak, "peak_source": how, "traffic": None,
+                "unit": "TFLOP/s", "frac": achieved / peak, "peak_source": how, "traffic": traffic, "traffic_unit": "bytes/launch",
+                "traffic_source": traffic_src,
                 "launches_per_step": tot_n // Kp, "kernel_ms_per_step": tot_ms / Kp,
                 "executed_tflop_per_step": tot_fl / Kp / 1e12, "algorithmic_tflop_per_step": GFLOP_TC_PER_TILE * B / 1000.0,
                 "share_of_step": (tot_ms / Kp) / (ms_total / K)}

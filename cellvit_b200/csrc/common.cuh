@@ -56,6 +56,14 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
+// One lane of the (fully active) warp: lets a whole warp run a producer / MMA-issue loop in uniform control flow -- so
+// that descriptors and coordinates live in uniform registers -- while a single thread issues the asynchronous op.
+// (A loop entered by one lane only makes ptxas wrap every UTCHMMA / UTMALDG in an ELECT + R2UR "waterfall".)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }

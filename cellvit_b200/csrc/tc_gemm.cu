@@ -315,7 +315,7 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUte
     const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem_gen = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;  // provably warp-uniform
     const int stages = p.stages;
     const uint32_t rank = PAIR ? ptx::cluster_ctarank() : 0u;
     const int tile0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
@@ -365,7 +365,7 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUte
 
     const int num_kb = p.num_kb;
 
-    if ((warp == 0 || warp == 3) && lane == 0) {
+    if (warp == 0 || warp == 3) {
         // ===================================================== TMA producers: warp 0 streams A, warp 3 streams B.
         // Two issuing threads because one thread's wait + expect_tx + 2 x UTMALDG chain (~700 clk per k-block) is
         // slower than a k-block of MMA for narrow tiles (128 clk at N = 64).
@@ -387,7 +387,8 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUte
             int tap = 0, cc = 0;  // conv: k-block = (tap, 64-channel chunk), chunk fastest
             for (int kb = 0; kb < num_kb; ++kb) {
                 ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
-                if (!PAIR || rank == 0) ptx::mbar_expect_tx(full_bar(stage), tx_bytes);
+                const bool issue = ptx::elect_one();  // the whole warp walks the loop, one lane issues
+                if (issue && (!PAIR || rank == 0)) ptx::mbar_expect_tx(full_bar(stage), tx_bytes);
                 if (is_a) {
                     if (!p.conv && p.l2_prefetch > 0) {
                         // A rows are touched for the first time by all n-tiles of an m-block at once: without this the
@@ -395,7 +396,7 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUte
                         int pk = kb + p.l2_prefetch, pm = m0;
                         if (pk >= num_kb) { pk -= num_kb; pm = -1; const int t2 = tile + tile_step;
                             if (t2 < p.n_tiles) pm = (t2 / p.n_tiles_n) * TILE_M + (int)rank * BLOCK_M; }
-                        if (pm >= 0 && pk < num_kb && (nt == 0 || pm != m0)) ptx::tma_prefetch_2d(&tmA0, pk * BLOCK_K, pm);
+                        if (issue && pm >= 0 && pk < num_kb && (nt == 0 || pm != m0)) ptx::tma_prefetch_2d(&tmA0, pk * BLOCK_K, pm);
                     }
                     const uint32_t dst_a = smem_a + stage * A_STAGE_BYTES;
                     const CUtensorMap* ta = &tmA0;
@@ -407,22 +408,24 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUte
                         else { ta = &tmA1; c0 = (cc - p.chunks0) * BLOCK_K; }
                         if (++cc == p.chunks_per_tap) { cc = 0; ++tap; }
                     }
-                    if (PAIR) {
-                        if (!p.conv) ptx::tma_load_2d_pair(dst_a, ta, full_bar(stage), c0, m0);
-                        else ptx::tma_load_4d_pair(dst_a, ta, full_bar(stage), c0, x0 + dx, y0 + dy, img);
-                    } else {
-                        if (!p.conv) ptx::tma_load_2d(dst_a, ta, full_bar(stage), c0, m0);
-                        else ptx::tma_load_4d(dst_a, ta, full_bar(stage), c0, x0 + dx, y0 + dy, img);
+                    if (issue) {
+                        if (PAIR) {
+                            if (!p.conv) ptx::tma_load_2d_pair(dst_a, ta, full_bar(stage), c0, m0);
+                            else ptx::tma_load_4d_pair(dst_a, ta, full_bar(stage), c0, x0 + dx, y0 + dy, img);
+                        } else {
+                            if (!p.conv) ptx::tma_load_2d(dst_a, ta, full_bar(stage), c0, m0);
+                            else ptx::tma_load_4d(dst_a, ta, full_bar(stage), c0, x0 + dx, y0 + dy, img);
+                        }
                     }
-                } else {
+                } else if (issue) {
                     if (PAIR) ptx::tma_load_2d_pair(smem_b + stage * b_stage_bytes, &tmB, full_bar(stage), kb * BLOCK_K, n0);
                     else ptx::tma_load_2d(smem_b + stage * b_stage_bytes, &tmB, full_bar(stage), kb * BLOCK_K, n0);
                 }
-                if (PAIR && rank != 0) ptx::mbar_arrive_cluster(full_bar(stage), 0);
+                if (issue && PAIR && rank != 0) ptx::mbar_arrive_cluster(full_bar(stage), 0);
                 if (++stage == stages) { stage = 0; phase ^= 1u; }
             }
         }
-    } else if (warp == 1 && lane == 0 && rank == 0) {
+    } else if (warp == 1 && rank == 0) {
         // ===================================================== MMA issuer (leader CTA only in PAIR mode)
         // instruction descriptor: D=f32, A=B=f16, both K-major, N>>3 @17, M>>4 @24
         const uint32_t idesc = (1u << 4) | ((uint32_t)(p.block_n >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
@@ -442,18 +445,21 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUte
                 ptx::tc_fence_after();
                 const uint64_t a_desc = desc_hi | (uint64_t)(((smem_a + stage * A_STAGE_BYTES) >> 4) & 0x3FFF);
                 const uint64_t b_desc = desc_hi | (uint64_t)(((smem_b + stage * b_stage_bytes) >> 4) & 0x3FFF);
+                if (ptx::elect_one()) {  // always lane 0 of the full warp, so tcgen05.commit tracks this thread's MMAs
 #pragma unroll
-                for (int k = 0; k < BLOCK_K / 16; ++k) {  // 16 fp16 = 32 B -> +2 in the (addr >> 4) field
-                    if (PAIR) ptx::umma_f16_pair(d_tmem, a_desc + 2u * k, b_desc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
-                    else ptx::umma_f16(d_tmem, a_desc + 2u * k, b_desc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                    for (int k = 0; k < BLOCK_K / 16; ++k) {  // 16 fp16 = 32 B -> +2 in the (addr >> 4) field
+                        if (PAIR) ptx::umma_f16_pair(d_tmem, a_desc + 2u * k, b_desc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                        else ptx::umma_f16(d_tmem, a_desc + 2u * k, b_desc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                    }
+                    if (PAIR) {
+                        ptx::umma_commit_pair(empty_bar(stage), 3);
+                        if (kb == num_kb - 1) ptx::umma_commit_pair(tfull_bar(as), 3);
+                    } else {
+                        ptx::umma_commit(empty_bar(stage));
+                        if (kb == num_kb - 1) ptx::umma_commit(tfull_bar(as));
+                    }
                 }
-                if (PAIR) {
-                    ptx::umma_commit_pair(empty_bar(stage), 3);
-                    if (kb == num_kb - 1) ptx::umma_commit_pair(tfull_bar(as), 3);
-                } else {
-                    ptx::umma_commit(empty_bar(stage));
-                    if (kb == num_kb - 1) ptx::umma_commit(tfull_bar(as));
-                }
+                __syncwarp();
                 if (++stage == stages) { stage = 0; phase ^= 1u; }
             }
         }
@@ -526,7 +532,7 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem_gen = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;  // provably warp-uniform
     const uint32_t b_stage_bytes = (uint32_t)p.N * BLOCK_K * 2;
     const uint32_t smem_patch = smem_base;
     const uint32_t smem_b = smem_patch + 2 * CP_PATCH_BYTES;
@@ -580,8 +586,8 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
         x0 = xb * BLOCK_M;
     };
 
-    if (warp == 0 && lane == 0) {
-        // ===================================================== patch producer
+    if (warp == 0) {
+        // ===================================================== patch producer (whole warp in the loop, one lane issues)
         int ps = 0;
         uint32_t pphase = 0;
         for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
@@ -589,17 +595,19 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
             tile_origin(tile, img, y0, x0);
             for (int c = 0; c < p.chunks; ++c) {
                 ptx::mbar_wait(pempty(ps), pphase ^ 1u);
-                ptx::mbar_expect_tx(pfull(ps), CP_PATCH_BYTES);
                 const bool first = c < p.chunks0;
-                // one TMA per patch row: a single large box is serviced at ~14 GB/s, concurrent boxes overlap
+                if (ptx::elect_one()) {
+                    ptx::mbar_expect_tx(pfull(ps), CP_PATCH_BYTES);
+                    // one TMA per patch row: a single large box is serviced at ~14 GB/s, concurrent boxes overlap
 #pragma unroll
-                for (int pr = 0; pr < CP_R + 2; ++pr)
-                    ptx::tma_load_4d(smem_patch + ps * CP_PATCH_BYTES + pr * (CP_PW * 128), first ? &tmA0 : &tmA1, pfull(ps),
-                                     (first ? c : c - p.chunks0) * BLOCK_K, x0 - 1, y0 - 1 + pr, img);
+                    for (int pr = 0; pr < CP_R + 2; ++pr)
+                        ptx::tma_load_4d(smem_patch + ps * CP_PATCH_BYTES + pr * (CP_PW * 128), first ? &tmA0 : &tmA1, pfull(ps),
+                                         (first ? c : c - p.chunks0) * BLOCK_K, x0 - 1, y0 - 1 + pr, img);
+                }
                 if (++ps == 2) { ps = 0; pphase ^= 1u; }
             }
         }
-    } else if (warp == 3 && lane == 0) {
+    } else if (warp == 3) {
         // ===================================================== weight producer: one [N x 64] tile per (chunk, tap)
         int bs = 0;
         uint32_t bphase = 0;
@@ -608,14 +616,16 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
             for (int c = 0; c < p.chunks; ++c) {
                 for (int tap = 0; tap < 9; ++tap) {
                     ptx::mbar_wait(bempty(bs), bphase ^ 1u);
-                    ptx::mbar_expect_tx(bfull(bs), b_stage_bytes);
-                    ptx::tma_load_2d(smem_b + bs * b_stage_bytes, &tmB, bfull(bs), (tap * p.chunks + c) * BLOCK_K, 0);
+                    if (ptx::elect_one()) {
+                        ptx::mbar_expect_tx(bfull(bs), b_stage_bytes);
+                        ptx::tma_load_2d(smem_b + bs * b_stage_bytes, &tmB, bfull(bs), (tap * p.chunks + c) * BLOCK_K, 0);
+                    }
                     if (++bs == p.b_stages) { bs = 0; bphase ^= 1u; }
                 }
             }
         }
-    } else if (warp == 1 && lane == 0) {
-        // ===================================================== MMA issuer
+    } else if (warp == 1) {
+        // ===================================================== MMA issuer (whole warp in the loop, one lane issues)
         const uint32_t idesc = (1u << 4) | ((uint32_t)(p.N >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
         const uint64_t desc_hi = (2ull << 61) | (1ull << 46) | ((uint64_t)(1024 >> 4) << 32);
         int ps = 0, bs = 0, it = 0;
@@ -633,22 +643,25 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
                     ptx::tc_fence_after();
                     const int dy = tap / 3, dx = tap - dy * 3;
                     const uint64_t b_desc = desc_hi | (uint64_t)(((smem_b + bs * b_stage_bytes) >> 4) & 0x3FFF);
+                    if (ptx::elect_one()) {
 #pragma unroll
-                    for (int r = 0; r < CP_R; ++r) {
-                        const uint32_t a_addr = patch + (uint32_t)((r + dy) * CP_PW + dx) * 128u;
-                        const uint64_t a_desc = desc_hi | (uint64_t)((a_addr >> 4) & 0x3FFF);
-                        const uint32_t d_tmem = tmem_base + (uint32_t)((as * CP_R + r) * p.N);
+                        for (int r = 0; r < CP_R; ++r) {
+                            const uint32_t a_addr = patch + (uint32_t)((r + dy) * CP_PW + dx) * 128u;
+                            const uint64_t a_desc = desc_hi | (uint64_t)((a_addr >> 4) & 0x3FFF);
+                            const uint32_t d_tmem = tmem_base + (uint32_t)((as * CP_R + r) * p.N);
 #pragma unroll
-                        for (int k = 0; k < BLOCK_K / 16; ++k)
-                            ptx::umma_f16(d_tmem, a_desc + 2u * k, b_desc + 2u * k, idesc, (c | tap | k) != 0 ? 1u : 0u);
+                            for (int k = 0; k < BLOCK_K / 16; ++k)
+                                ptx::umma_f16(d_tmem, a_desc + 2u * k, b_desc + 2u * k, idesc, (c | tap | k) != 0 ? 1u : 0u);
+                        }
+                        if (!p.resident) ptx::umma_commit(bempty(bs));
+                        if (tap == 8) ptx::umma_commit(pempty(ps));
+                        if (tap == 8 && c == p.chunks - 1) ptx::umma_commit(tfull(as));
                     }
-                    if (!p.resident) ptx::umma_commit(bempty(bs));
+                    __syncwarp();
                     if (++bs == p.b_stages) { bs = 0; bphase ^= 1u; }
                 }
-                ptx::umma_commit(pempty(ps));
                 if (++ps == 2) { ps = 0; pphase ^= 1u; }
             }
-            ptx::umma_commit(tfull(as));
         }
     } else if (warp >= 4) {
         // ===================================================== epilogue: R accumulators of 128 pixels each
