@@ -284,8 +284,7 @@ __device__ __forceinline__ void epilogue_tile(const TcEpilogue& e, uint32_t t_ad
         } else {  // TC_EPI_CONVT: 32 consecutive n share (dy,dx) because Cout % 32 == 0
             const int q = nb / e.ct_cout, co = nb - q * e.ct_cout;
             const int dy = q >> 1, dx = q & 1;
-            const size_t opix = ((size_t)ct_b * (2 * e.ct_hin) + (2 * ct_y + dy)) * (size_t)(2 * e.ct_win) + (2 * ct_x + dx);
-            __half* o = reinterpret_cast<__half*>(e.out) + opix * (size_t)e.ldc + co;
+            uint4 pk[4];
 #pragma unroll
             for (int j = 0; j < 32; j += 8) {
                 float4 h0 = make_float4(0.f, 0.f, 0.f, 0.f), h1 = h0;
@@ -293,12 +292,38 @@ __device__ __forceinline__ void epilogue_tile(const TcEpilogue& e, uint32_t t_ad
                     h0 = __ldg(reinterpret_cast<const float4*>(e.shift + co + j));
                     h1 = __ldg(reinterpret_cast<const float4*>(e.shift + co + j + 4));
                 }
-                *reinterpret_cast<uint4*>(o + j) =
-                    make_uint4(pack_h2(__uint_as_float(acc[j + 0]) + h0.x, __uint_as_float(acc[j + 1]) + h0.y),
-                               pack_h2(__uint_as_float(acc[j + 2]) + h0.z, __uint_as_float(acc[j + 3]) + h0.w),
-                               pack_h2(__uint_as_float(acc[j + 4]) + h1.x, __uint_as_float(acc[j + 5]) + h1.y),
-                               pack_h2(__uint_as_float(acc[j + 6]) + h1.z, __uint_as_float(acc[j + 7]) + h1.w));
+                pk[j >> 3] = make_uint4(pack_h2(__uint_as_float(acc[j + 0]) + h0.x, __uint_as_float(acc[j + 1]) + h0.y),
+                                        pack_h2(__uint_as_float(acc[j + 2]) + h0.z, __uint_as_float(acc[j + 3]) + h0.w),
+                                        pack_h2(__uint_as_float(acc[j + 4]) + h1.x, __uint_as_float(acc[j + 5]) + h1.y),
+                                        pack_h2(__uint_as_float(acc[j + 6]) + h1.z, __uint_as_float(acc[j + 7]) + h1.w));
             }
+            // A lane owns one input pixel: its four 16-byte pieces would go to four different 128-byte lines per store
+            // instruction (32 lines per warp instruction). A 4x4 transpose inside each group of four lanes (two shuffle
+            // rounds) makes lane j hold piece j of the group's four pixels, so every instruction writes 64 contiguous
+            // bytes per lane group -- 8 lines instead of 32.
+            const int l4 = (int)(threadIdx.x & 3);
+            {
+                const bool odd = l4 & 1;
+                uint4 s0 = odd ? pk[0] : pk[1], s1 = odd ? pk[2] : pk[3];
+                s0.x = __shfl_xor_sync(0xffffffffu, s0.x, 1); s0.y = __shfl_xor_sync(0xffffffffu, s0.y, 1);
+                s0.z = __shfl_xor_sync(0xffffffffu, s0.z, 1); s0.w = __shfl_xor_sync(0xffffffffu, s0.w, 1);
+                s1.x = __shfl_xor_sync(0xffffffffu, s1.x, 1); s1.y = __shfl_xor_sync(0xffffffffu, s1.y, 1);
+                s1.z = __shfl_xor_sync(0xffffffffu, s1.z, 1); s1.w = __shfl_xor_sync(0xffffffffu, s1.w, 1);
+                if (odd) { pk[0] = s0; pk[2] = s1; } else { pk[1] = s0; pk[3] = s1; }
+                const bool hi = l4 & 2;
+                uint4 t0 = hi ? pk[0] : pk[2], t1 = hi ? pk[1] : pk[3];
+                t0.x = __shfl_xor_sync(0xffffffffu, t0.x, 2); t0.y = __shfl_xor_sync(0xffffffffu, t0.y, 2);
+                t0.z = __shfl_xor_sync(0xffffffffu, t0.z, 2); t0.w = __shfl_xor_sync(0xffffffffu, t0.w, 2);
+                t1.x = __shfl_xor_sync(0xffffffffu, t1.x, 2); t1.y = __shfl_xor_sync(0xffffffffu, t1.y, 2);
+                t1.z = __shfl_xor_sync(0xffffffffu, t1.z, 2); t1.w = __shfl_xor_sync(0xffffffffu, t1.w, 2);
+                if (hi) { pk[0] = t0; pk[1] = t1; } else { pk[2] = t0; pk[3] = t1; }
+            }
+            // pk[k] = piece l4 of the pixel of lane (lane & ~3) + k; the four pixels are consecutive in x (win % 4 == 0)
+            const int x_base = ct_x - l4;
+            const size_t opix = ((size_t)ct_b * (2 * e.ct_hin) + (2 * ct_y + dy)) * (size_t)(2 * e.ct_win) + (2 * x_base + dx);
+            __half* o = reinterpret_cast<__half*>(e.out) + opix * (size_t)e.ldc + co + 8 * l4;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) *reinterpret_cast<uint4*>(o + (size_t)(2 * k) * (size_t)e.ldc) = pk[k];
         }
     }
 }
@@ -725,8 +750,8 @@ int check_epilogue(const TcEpilogue& e, int N, int block_n) {
     if (e.kind == TC_EPI_F16 || e.kind == TC_EPI_RES_F32)
         CVB_CHECK(e.out != nullptr && e.ldc % 8 == 0, CVB_EARG, "tc: epilogue needs out and ldc %% 8 == 0");
     if (e.kind == TC_EPI_CONVT)
-        CVB_CHECK(e.out != nullptr && e.ct_cout % 32 == 0 && N == 4 * e.ct_cout && e.ldc % 8 == 0, CVB_ESHAPE,
-                  "tc: CONVT needs Cout %% 32 == 0 and N == 4*Cout");
+        CVB_CHECK(e.out != nullptr && e.ct_cout % 32 == 0 && N == 4 * e.ct_cout && e.ldc % 8 == 0 && e.ct_win % 4 == 0, CVB_ESHAPE,
+                  "tc: CONVT needs Cout %% 32 == 0, N == 4*Cout and an input width that is a multiple of 4");
     if (e.kind == TC_EPI_HEAD)
         CVB_CHECK(N == 64 && block_n == 64 && e.head_nc >= 1 && e.head_nc <= 8 && e.head_out && e.head_w && e.head_b &&
                       e.scale && e.shift,
@@ -821,6 +846,9 @@ int tc_gemm(const __half* A, int M, int K, long long lda, const __half* W, int N
               "tc_gemm: K=%d must be a multiple of 64 and lda/ldw multiples of 8", K);
     CVB_CHECK(((uintptr_t)A & 15) == 0 && ((uintptr_t)W & 15) == 0, CVB_EARG, "tc_gemm: operands must be 16-byte aligned");
     CVB_TRY(check_epilogue(epi, N, block_n));
+    if (epi.kind == TC_EPI_CONVT)  // the scatter epilogue transposes inside lane groups: no partially valid warps
+        CVB_CHECK(M % BLOCK_M == 0 && M == (M / (epi.ct_hin * epi.ct_win)) * epi.ct_hin * epi.ct_win, CVB_ESHAPE,
+                  "tc_gemm: CONVT needs M = NB*hin*win to be a multiple of %d (M=%d)", BLOCK_M, M);
     const bool pair = use_pair(M, N, block_n) && epi.kind != TC_EPI_HEAD;
     CUtensorMap ta, tb;
     {
