@@ -319,6 +319,102 @@ flash_kernel(const __half* __restrict__ qkv, int S, int heads, float scale, cons
     }
 }
 
+// ------------------------------------------------------------------------------------------ rel-pos tables only
+// The bias prologue of flash_kernel as a kernel of its own, for the tcgen05 attention (flash_tc.cu): per 64 queries of one
+// (image, head), G = Q R^T through the MMA path, scattered to rel[q, k] = G[q, qpos + g - 1 - k], then written out
+// (times log2 e, fp16) as bias_h / bias_w [(g*heads + head)*S + q][64].
+template <int HD>
+struct RtSmem {
+    static constexpr int LD = HD + 8;
+    __half q[FA_BQ * LD];
+    __half t[2][FA_BK * LD];
+    __half rel_h[FA_BQ * REL_LD];
+    __half rel_w[FA_BQ * REL_LD];
+};
+
+template <int HD>
+__global__ void __launch_bounds__(FA_THREADS)
+relpos_tables_kernel(const __half* __restrict__ qkv, int S, int heads, const __half* __restrict__ Rh, const __half* __restrict__ Rw,
+                     int gh, int gw, __half* __restrict__ bias_h, __half* __restrict__ bias_w) {
+    extern __shared__ __align__(16) uint8_t rt_smem_raw[];
+    using Smem = RtSmem<HD>;
+    Smem& sm = *reinterpret_cast<Smem*>(rt_smem_raw);
+    constexpr int LD = Smem::LD;
+    constexpr int KSTEPS = HD / 16;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = blockIdx.y, bp = g / heads, head = g - bp * heads;
+    const int D = heads * HD;
+    const long long row_stride = 3LL * D;
+    const int q0 = blockIdx.x * FA_BQ;
+    const __half* q_base = qkv + (long long)bp * S * row_stride + head * HD;
+    const int r_lo = warp * 16 + (lane >> 2);
+    for (int i = tid; i < FA_BQ * REL_LD; i += FA_THREADS) { sm.rel_h[i] = __float2half(0.f); sm.rel_w[i] = __float2half(0.f); }
+    TileLoader<HD> ld, ldt;
+    ld.init(tid, (int)row_stride);
+    ldt.init(tid, HD);
+    constexpr uint32_t T_BYTES = FA_BK * LD * 2;
+    const uint32_t sq = ptx::smem_u32(sm.q), st0 = ptx::smem_u32(sm.t[0]);
+    ld.load(sq, q_base + (long long)q0 * row_stride, q0, S);
+    ptx::cp_async_commit();
+    const int Lh = 2 * gh - 1, Lw = 2 * gw - 1;
+    const int ph = (Lh + 63) / 64, pw = (Lw + 63) / 64;
+    const int n_pass = ph + pw;
+    auto issue = [&](int pass) {
+        const bool is_h = pass < ph;
+        const int p = is_h ? pass : pass - ph;
+        ldt.load(st0 + (pass & 1) * T_BYTES, (is_h ? Rh : Rw) + (long long)p * 64 * HD, p * 64, is_h ? Lh : Lw);
+        ptx::cp_async_commit();
+    };
+    issue(0);
+    uint32_t q_frag[KSTEPS][4];
+    float s_acc[8][4];
+    for (int pass = 0; pass < n_pass; ++pass) {
+        if (pass + 1 < n_pass) { issue(pass + 1); ptx::cp_async_wait<1>(); }
+        else ptx::cp_async_wait<0>();
+        __syncthreads();
+        if (pass == 0) {
+#pragma unroll
+            for (int ks = 0; ks < KSTEPS; ++ks) {
+                const int row = warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+                const int col = ks * 16 + (lane >> 4) * 8;
+                ptx::ldmatrix_x4(ptx::smem_u32(sm.q + row * LD + col), q_frag[ks][0], q_frag[ks][1], q_frag[ks][2], q_frag[ks][3]);
+            }
+        }
+        const bool is_h = pass < ph;
+        const int p = is_h ? pass : pass - ph;
+        const int L = is_h ? Lh : Lw, gdim = is_h ? gh : gw;
+        const int rows_here = min(64, L - p * 64);
+        fa_qk<HD>(sm.t[pass & 1], q_frag, s_acc, lane, (rows_here + 15) >> 4);
+        __half* dst = is_h ? sm.rel_h : sm.rel_w;
+#pragma unroll
+        for (int hrow = 0; hrow < 2; ++hrow) {
+            const int row = r_lo + 8 * hrow;
+            const int t = q0 + row;
+            if (t < S) {
+                const int qh = t / gw;
+                const int qpos = is_h ? qh : t - qh * gw;
+#pragma unroll
+                for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int j = p * 64 + nt * 8 + 2 * (lane & 3) + e;
+                        const int kk = qpos + gdim - 1 - j;
+                        if (kk >= 0 && kk < gdim && j < L) dst[row * REL_LD + kk] = __float2half(s_acc[nt][2 * hrow + e] * 1.4426950408889634f);
+                    }
+            }
+        }
+        __syncthreads();
+    }
+    // coalesced write-out: 64 rows x 64 halves per table
+    for (int i = tid; i < FA_BQ * 32; i += FA_THREADS) {
+        const int r = i >> 5, c = (i & 31) * 2;
+        if (q0 + r >= S) continue;
+        const long long o = ((long long)g * S + q0 + r) * 64 + c;
+        *reinterpret_cast<__half2*>(bias_h + o) = *reinterpret_cast<const __half2*>(sm.rel_h + r * REL_LD + c);
+        *reinterpret_cast<__half2*>(bias_w + o) = *reinterpret_cast<const __half2*>(sm.rel_w + r * REL_LD + c);
+    }
+}
+
 // ------------------------------------------------------------------------------------------ windowed attention
 // One CTA per (window, head): the whole K and V of the window (S <= 208 keys, 14 x 14 = 196 for SAM) stay in shared
 // memory, so the seven warps run their 16-query m-tiles without any block-level synchronisation after the load.
@@ -570,6 +666,22 @@ int launch_flash(const __half* qkv, int Gb, int S, int heads, float scale, const
 }
 
 }  // namespace
+
+int op_relpos_tables(const __half* qkv, int Gb, int S, int heads, int hd, const __half* Rh, const __half* Rw, int gh, int gw,
+                     __half* bias_h, __half* bias_w, cudaStream_t stream) {
+    CVB_CHECK(qkv && Rh && Rw && bias_h && bias_w && hd == 80 && gh <= 64 && gw <= 64 && gh * gw == S, CVB_ESHAPE,
+              "relpos_tables: needs head dim 80 and a token grid of at most 64 x 64");
+    static bool configured = false;
+    const int smem = (int)sizeof(RtSmem<80>);
+    if (!configured) {
+        CVB_CUDA(cudaFuncSetAttribute(relpos_tables_kernel<80>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        configured = true;
+    }
+    relpos_tables_kernel<80><<<dim3(cdiv(S, FA_BQ), Gb * heads), FA_THREADS, smem, stream>>>(qkv, S, heads, Rh, Rw, gh, gw, bias_h, bias_w);
+    cvb_note_launches(1);
+    CVB_CUDA(cudaGetLastError());
+    return CVB_OK;
+}
 
 int op_attention(const __half* qkv, int Gb, int S, int heads, int hd, float scale, const __half* Rh, const __half* Rw,
                  int gh, int gw, __half* out, cudaStream_t stream) {

@@ -31,6 +31,17 @@ CVB_API int cvb_op_attention(const void* qkv, int Gb, int S, int heads, int hd, 
                         (cudaStream_t)stream);
 }
 
+CVB_API int cvb_op_attention_tc_workspace_bytes(int Gb, int S, int heads, size_t* out) {
+    CVB_CHECK(out != nullptr && Gb > 0 && S > 0 && heads > 0, CVB_EARG, "cvb_op_attention_tc_workspace_bytes: bad arguments");
+    *out = op_attention_tc_workspace_bytes(Gb, S, heads);
+    return CVB_OK;
+}
+CVB_API int cvb_op_attention_tc(const void* qkv, int Gb, int S, int heads, int hd, float scale, const void* Rh, const void* Rw,
+                                int gh, int gw, void* out, void* workspace, size_t ws_bytes, void* stream) {
+    return op_attention_tc((const __half*)qkv, Gb, S, heads, hd, scale, (const __half*)Rh, (const __half*)Rw, gh, gw, (__half*)out,
+                           workspace, ws_bytes, (cudaStream_t)stream);
+}
+
 CVB_API int cvb_op_patch_im2col(const float* x, int B, int H, int W, int P, void* out, void* stream) {
     return op_patch_im2col(x, B, H, W, P, (__half*)out, (cudaStream_t)stream);
 }

@@ -1,0 +1,387 @@
+// flash_tc.cu -- global (non-windowed) attention of the SAM encoder on the tcgen05 tensor cores.
+//
+//   out = softmax(scale * q k^T + rel_h[q, kh(k)] + rel_w[q, kw(k)]) v     (image_encoder.py:235-260, 354-392)
+//
+// per (image, head): S = 4096 keys (64 x 64 token grid), head dim 80. Replaces the mma.sync flash kernel for this
+// shape (246 TFLOP/s, 44 % of the legacy-HMMA ceiling) with a warp-specialised kernel in the style of the tile engine:
+//
+//   CTA = 128 queries of one (image, head); key tiles of 64 keys = ONE key row of the token grid, so rel_h is a per-query
+//   scalar for the whole tile and rel_w[q, 0..63] is the same vector for every tile (kept in registers).
+//   warp 0   TMA producer: Q once (two 64-column boxes: hd columns 0-63 and 16-79 -- the fifth k-step reads columns
+//            64-79 out of the second box, so only the proven 128B-swizzle K-major layout is used), then per key
+//            tile K (same two boxes) and V^T (80 x 64 keys, K-major) through a 3-stage ring.
+//   warp 1   MMA issuer: S[t&1] = Q K_t^T (5 x UMMA 128x64x16, fp32 in TMEM), then O[t&1] = P_t V_t (4 x UMMA 128x80x16)
+//            once the softmax warps have published P_t; QK of tile t+1 is issued before PV of tile t so the tensor
+//            pipe works while tile t is in the softmax.
+//   warp 2   TMEM allocator.   warps 4-7  softmax: one query row per thread (TMEM lane), exact online softmax in
+//            the log2 domain, P written to shared memory as the fp16 K-major A operand of PV (128B swizzle), the
+//            per-tile partial output read back from TMEM and accumulated in registers (rescaled when the running
+//            max moves).
+// V must be K-major for the B operand of P V, i.e. transposed to [hd, keys]: v_transpose_kernel does that once per
+// block (42 MB). The decomposed rel-pos bias tables rel_h / rel_w [q, 64] come from relpos_tables_kernel (attention.cu:
+// G = Q R^T through the MMA path, UNSCALED q, pre-multiplied by log2(e), fp16 as in the mma.sync kernel).
+#include <cudaTypedefs.h>
+
+#include "ops.h"
+
+namespace {
+
+constexpr int FT_BQ = 128, FT_BK = 64, FT_HD = 80, FT_STAGES = 3;
+constexpr int FT_THREADS = 256;
+constexpr uint32_t FT_Q_BYTES = 2 * FT_BQ * 128;          // two boxes of 128 rows x 128 B
+constexpr uint32_t FT_K_BYTES = 2 * FT_BK * 128;          // two boxes of 64 rows x 128 B
+constexpr uint32_t FT_V_BYTES = FT_HD * 128;              // 80 rows (hd) x 64 keys
+constexpr uint32_t FT_P_BYTES = FT_BQ * 128;              // 128 rows x 64 keys fp16
+constexpr uint32_t FT_SMEM = 1024 + FT_Q_BYTES + FT_STAGES * (FT_K_BYTES + FT_V_BYTES) + 2 * FT_P_BYTES + 256;
+constexpr float FT_L2E = 1.4426950408889634f;
+
+// ------------------------------------------------------------------------------------------ V^T
+// v rows [Gb*S, 3*D] (columns 2*D + head*hd + d) -> vt [(g*heads + head)*hd + d][S]
+__global__ void __launch_bounds__(256)
+v_transpose_kernel(const __half* __restrict__ qkv, int S, int heads, __half* __restrict__ vt) {
+    __shared__ __half tile[64][FT_HD + 2];
+    const int gh = blockIdx.y, g = gh / heads, head = gh - g * heads;
+    const int D = heads * FT_HD, k0 = blockIdx.x * 64;
+    const __half* src = qkv + ((long long)g * S + k0) * 3 * D + 2 * D + head * FT_HD;
+    for (int i = threadIdx.x; i < 64 * (FT_HD / 8); i += 256) {
+        const int r = i / (FT_HD / 8), c = i - r * (FT_HD / 8);
+        const uint4 v = *reinterpret_cast<const uint4*>(src + (long long)r * 3 * D + c * 8);
+        const __half* h = reinterpret_cast<const __half*>(&v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) tile[r][c * 8 + j] = h[j];
+    }
+    __syncthreads();
+    __half* dst = vt + (long long)gh * FT_HD * S + k0;
+    for (int i = threadIdx.x; i < FT_HD * 32; i += 256) {
+        const int d = i >> 5, kp = i & 31;
+        const __half2 v = __halves2half2(tile[2 * kp][d], tile[2 * kp + 1][d]);
+        *reinterpret_cast<__half2*>(dst + (long long)d * S + 2 * kp) = v;
+    }
+}
+
+// ------------------------------------------------------------------------------------------ main kernel
+__global__ void __launch_bounds__(FT_THREADS, 1)
+flash_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                const __grid_constant__ CUtensorMap tmV, const __half* __restrict__ bias_h, const __half* __restrict__ bias_w,
+                int S, int heads, float scale, __half* __restrict__ out) {
+    extern __shared__ uint8_t ft_smem_raw[];
+    const uint32_t smem_base = (ptx::smem_u32(ft_smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem_gen = ft_smem_raw + (smem_base - ptx::smem_u32(ft_smem_raw));
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
+    const int ghd = blockIdx.y, g = ghd / heads, head = ghd - g * heads;
+    const int q0 = blockIdx.x * FT_BQ;
+    const int D = heads * FT_HD;
+    const int n_t = S / FT_BK;
+
+    const uint32_t sQ = smem_base;
+    const uint32_t sK = sQ + FT_Q_BYTES;
+    const uint32_t sV = sK + FT_STAGES * FT_K_BYTES;
+    const uint32_t sP = sV + FT_STAGES * FT_V_BYTES;
+    const uint32_t bar = sP + 2 * FT_P_BYTES;
+    // barriers (8 B each)
+    const uint32_t q_full = bar;
+    auto kv_full = [&](int s) { return bar + 8u * (1 + s); };
+    auto kv_empty = [&](int s) { return bar + 8u * (4 + s); };
+    auto s_full = [&](int b) { return bar + 8u * (7 + b); };
+    auto s_empty = [&](int b) { return bar + 8u * (9 + b); };
+    auto p_full = [&](int b) { return bar + 8u * (11 + b); };
+    auto o_full = [&](int b) { return bar + 8u * (13 + b); };
+    auto o_empty = [&](int b) { return bar + 8u * (15 + b); };
+    const uint32_t tmem_slot = bar + 8u * 17;
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tmap(&tmQ);
+        ptx::prefetch_tmap(&tmK);
+        ptx::prefetch_tmap(&tmV);
+    }
+    if (warp == 1 && lane == 0) {
+        ptx::mbar_init(q_full, 1);
+        for (int s = 0; s < FT_STAGES; ++s) { ptx::mbar_init(kv_full(s), 1); ptx::mbar_init(kv_empty(s), 1); }
+        for (int b = 0; b < 2; ++b) {
+            ptx::mbar_init(s_full(b), 1);
+            ptx::mbar_init(s_empty(b), 128);
+            ptx::mbar_init(p_full(b), 128);
+            ptx::mbar_init(o_full(b), 1);
+            ptx::mbar_init(o_empty(b), 128);
+        }
+        ptx::fence_barrier_init();
+    }
+    if (warp == 2) {
+        ptx::tmem_alloc(tmem_slot, 512);
+        ptx::tmem_relinquish();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
+    // TMEM columns: S buffers at 0 / 64, O buffers at 128 / 224 (80 used of 96)
+    auto tS = [&](int b) { return tmem_base + (uint32_t)(b * 64); };
+    auto tO = [&](int b) { return tmem_base + 128u + (uint32_t)(b * 96); };
+
+    if (warp == 0) {
+        // ===================================================== TMA producer
+        const int row_q = g * S + q0;
+        if (ptx::elect_one()) {
+            ptx::mbar_expect_tx(q_full, FT_Q_BYTES);
+            ptx::tma_load_2d(sQ, &tmQ, q_full, head * FT_HD, row_q);
+            ptx::tma_load_2d(sQ + FT_BQ * 128, &tmQ, q_full, head * FT_HD + 16, row_q);
+        }
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int t = 0; t < n_t; ++t) {
+            ptx::mbar_wait(kv_empty(stage), phase ^ 1u);
+            if (ptx::elect_one()) {
+                ptx::mbar_expect_tx(kv_full(stage), FT_K_BYTES + FT_V_BYTES);
+                const int row_k = g * S + t * FT_BK;
+                ptx::tma_load_2d(sK + stage * FT_K_BYTES, &tmK, kv_full(stage), D + head * FT_HD, row_k);
+                ptx::tma_load_2d(sK + stage * FT_K_BYTES + FT_BK * 128, &tmK, kv_full(stage), D + head * FT_HD + 16, row_k);
+                ptx::tma_load_2d(sV + stage * FT_V_BYTES, &tmV, kv_full(stage), t * FT_BK, ghd * FT_HD);
+            }
+            if (++stage == FT_STAGES) { stage = 0; phase ^= 1u; }
+        }
+    } else if (warp == 1) {
+        // ===================================================== MMA issuer
+        // instruction descriptors: D=f32, A=B=f16, both K-major; N>>3 @17, M>>4 @24
+        const uint32_t idesc_qk = (1u << 4) | ((uint32_t)(FT_BK >> 3) << 17) | ((uint32_t)(FT_BQ >> 4) << 24);
+        const uint32_t idesc_pv = (1u << 4) | ((uint32_t)(FT_HD >> 3) << 17) | ((uint32_t)(FT_BQ >> 4) << 24);
+        const uint64_t desc_hi = (2ull << 61) | (1ull << 46) | ((uint64_t)(1024 >> 4) << 32);  // SWIZZLE_128B, SBO 1024
+        auto desc = [&](uint32_t addr) { return desc_hi | (uint64_t)((addr >> 4) & 0x3FFF); };
+        ptx::mbar_wait(q_full, 0);
+        ptx::tc_fence_after();
+        auto issue_qk = [&](int t) {
+            const int stage = t % FT_STAGES, b = t & 1;
+            ptx::mbar_wait(kv_full(stage), (uint32_t)((t / FT_STAGES) & 1));
+            ptx::mbar_wait(s_empty(b), (uint32_t)(((t >> 1) & 1) ^ 1));
+            ptx::tc_fence_after();
+            if (ptx::elect_one()) {
+                const uint64_t a0 = desc(sQ), a1 = desc(sQ + FT_BQ * 128);
+                const uint64_t b0 = desc(sK + stage * FT_K_BYTES), b1 = desc(sK + stage * FT_K_BYTES + FT_BK * 128);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) ptx::umma_f16(tS(b), a0 + 2u * k, b0 + 2u * k, idesc_qk, k != 0 ? 1u : 0u);
+                ptx::umma_f16(tS(b), a1 + 6u, b1 + 6u, idesc_qk, 1u);  // hd columns 64-79 = columns 48-63 of the second box
+                ptx::umma_commit(s_full(b));
+            }
+            __syncwarp();
+        };
+        auto issue_pv = [&](int t) {
+            const int stage = t % FT_STAGES, b = t & 1;
+            ptx::mbar_wait(p_full(b), (uint32_t)((t >> 1) & 1));
+            ptx::mbar_wait(o_empty(b), (uint32_t)(((t >> 1) & 1) ^ 1));
+            ptx::tc_fence_after();
+            if (ptx::elect_one()) {
+                const uint64_t a0 = desc(sP + b * FT_P_BYTES), b0 = desc(sV + stage * FT_V_BYTES);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) ptx::umma_f16(tO(b), a0 + 2u * k, b0 + 2u * k, idesc_pv, k != 0 ? 1u : 0u);
+                ptx::umma_commit(o_full(b));
+                ptx::umma_commit(kv_empty(stage));
+            }
+            __syncwarp();
+        };
+        issue_qk(0);
+        for (int t = 0; t < n_t; ++t) {
+            if (t + 1 < n_t) issue_qk(t + 1);
+            issue_pv(t);
+        }
+    } else if (warp >= 4) {
+        // ===================================================== softmax / output: one query row per thread
+        const int quad = warp & 3, r = quad * 32 + lane;
+        const long long row = (long long)ghd * S + q0 + r;
+        const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
+        const float sl2 = scale * FT_L2E;
+        // rel_w[q, 0..63] (log2 domain) packed as 32 half2 registers
+        uint32_t bw[32];
+        {
+            const uint4* p = reinterpret_cast<const uint4*>(bias_w + row * 64);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const uint4 v = __ldg(p + i);
+                bw[4 * i] = v.x; bw[4 * i + 1] = v.y; bw[4 * i + 2] = v.z; bw[4 * i + 3] = v.w;
+            }
+        }
+        const __half* bh_row = bias_h + row * 64;
+        float o[FT_HD];
+#pragma unroll
+        for (int i = 0; i < FT_HD; ++i) o[i] = 0.f;
+        float m_run = -INFINITY, l_run = 0.f;
+        float bh_next = __half2float(__ldg(bh_row));
+        const uint32_t p_row = (uint32_t)r * 128u;
+        const uint32_t sw = (uint32_t)(r & 7);
+        for (int t = 0; t < n_t; ++t) {
+            const int b = t & 1;
+            const float bh = bh_next;
+            if (t + 1 < n_t) bh_next = __half2float(__ldg(bh_row + t + 1));
+            ptx::mbar_wait(s_full(b), (uint32_t)((t >> 1) & 1));
+            ptx::tc_fence_after();
+            uint32_t v0[32], v1[32];
+            ptx::tmem_ld32(tS(b) + lane_off, v0);
+            ptx::tmem_ld32(tS(b) + lane_off + 32u, v1);
+            ptx::tmem_ld_wait();
+            ptx::tc_fence_before();
+            ptx::mbar_arrive(s_empty(b));
+            // scores in the log2 domain (without the per-tile scalar bh), and their maximum
+            float mx = -INFINITY;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const float2 w0 = __half22float2(*reinterpret_cast<const __half2*>(&bw[j]));
+                const float2 w1 = __half22float2(*reinterpret_cast<const __half2*>(&bw[16 + j]));
+                const float a0 = fmaf(__uint_as_float(v0[2 * j]), sl2, w0.x), a1 = fmaf(__uint_as_float(v0[2 * j + 1]), sl2, w0.y);
+                const float c0 = fmaf(__uint_as_float(v1[2 * j]), sl2, w1.x), c1 = fmaf(__uint_as_float(v1[2 * j + 1]), sl2, w1.y);
+                v0[2 * j] = __float_as_uint(a0); v0[2 * j + 1] = __float_as_uint(a1);
+                v1[2 * j] = __float_as_uint(c0); v1[2 * j + 1] = __float_as_uint(c1);
+                mx = fmaxf(mx, fmaxf(fmaxf(a0, a1), fmaxf(c0, c1)));
+            }
+            const float m_new = fmaxf(m_run, mx + bh);
+            const float alpha = ptx::ex2(m_run - m_new);  // 0 on the first tile (m_run = -inf)
+            m_run = m_new;
+            const float mref = m_new - bh;
+            float rs = 0.f;
+            uint32_t pk[32];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const float p0 = ptx::ex2(__uint_as_float(v0[2 * j]) - mref), p1 = ptx::ex2(__uint_as_float(v0[2 * j + 1]) - mref);
+                const float p2 = ptx::ex2(__uint_as_float(v1[2 * j]) - mref), p3 = ptx::ex2(__uint_as_float(v1[2 * j + 1]) - mref);
+                rs += (p0 + p1) + (p2 + p3);
+                pk[j] = pack_h2(p0, p1);
+                pk[16 + j] = pack_h2(p2, p3);
+            }
+            l_run = l_run * alpha + rs;
+            // P row (64 keys fp16 = 8 chunks of 16 B) into the K-major SWIZZLE_128B A operand: chunk c -> c ^ (row & 7)
+            {
+                const uint32_t base = sP + b * FT_P_BYTES + p_row;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const uint32_t addr = base + (((uint32_t)c ^ sw) << 4);
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[4 * c]), "r"(pk[4 * c + 1]),
+                                 "r"(pk[4 * c + 2]), "r"(pk[4 * c + 3]) : "memory");
+                }
+            }
+            ptx::fence_proxy_async();  // generic-proxy writes -> visible to the tensor core (async proxy)
+            ptx::mbar_arrive(p_full(b));
+            // previous tile's partial output: o = (o + O_{t-1}) * alpha  (both terms are in the scale of m_{t-1})
+            if (t > 0) {
+                const int pb = b ^ 1;
+                ptx::mbar_wait(o_full(pb), (uint32_t)(((t - 1) >> 1) & 1));
+                ptx::tc_fence_after();
+                uint32_t a[32], c[32], d[16];
+                ptx::tmem_ld32(tO(pb) + lane_off, a);
+                ptx::tmem_ld32(tO(pb) + lane_off + 32u, c);
+                ptx::tmem_ld16(tO(pb) + lane_off + 64u, d);
+                ptx::tmem_ld_wait();
+                ptx::tc_fence_before();
+                ptx::mbar_arrive(o_empty(pb));
+#pragma unroll
+                for (int i = 0; i < 32; ++i) { o[i] = (o[i] + __uint_as_float(a[i])) * alpha; o[32 + i] = (o[32 + i] + __uint_as_float(c[i])) * alpha; }
+#pragma unroll
+                for (int i = 0; i < 16; ++i) o[64 + i] = (o[64 + i] + __uint_as_float(d[i])) * alpha;
+            }
+        }
+        {   // last tile's partial output
+            const int pb = (n_t - 1) & 1;
+            ptx::mbar_wait(o_full(pb), (uint32_t)(((n_t - 1) >> 1) & 1));
+            ptx::tc_fence_after();
+            uint32_t a[32], c[32], d[16];
+            ptx::tmem_ld32(tO(pb) + lane_off, a);
+            ptx::tmem_ld32(tO(pb) + lane_off + 32u, c);
+            ptx::tmem_ld16(tO(pb) + lane_off + 64u, d);
+            ptx::tmem_ld_wait();
+            const float inv = 1.0f / l_run;
+            __half* dst = out + ((long long)g * S + q0 + r) * D + head * FT_HD;
+#pragma unroll
+            for (int i = 0; i < 32; i += 8) {
+                *reinterpret_cast<uint4*>(dst + i) =
+                    make_uint4(pack_h2((o[i] + __uint_as_float(a[i])) * inv, (o[i + 1] + __uint_as_float(a[i + 1])) * inv),
+                               pack_h2((o[i + 2] + __uint_as_float(a[i + 2])) * inv, (o[i + 3] + __uint_as_float(a[i + 3])) * inv),
+                               pack_h2((o[i + 4] + __uint_as_float(a[i + 4])) * inv, (o[i + 5] + __uint_as_float(a[i + 5])) * inv),
+                               pack_h2((o[i + 6] + __uint_as_float(a[i + 6])) * inv, (o[i + 7] + __uint_as_float(a[i + 7])) * inv));
+                *reinterpret_cast<uint4*>(dst + 32 + i) =
+                    make_uint4(pack_h2((o[32 + i] + __uint_as_float(c[i])) * inv, (o[33 + i] + __uint_as_float(c[i + 1])) * inv),
+                               pack_h2((o[34 + i] + __uint_as_float(c[i + 2])) * inv, (o[35 + i] + __uint_as_float(c[i + 3])) * inv),
+                               pack_h2((o[36 + i] + __uint_as_float(c[i + 4])) * inv, (o[37 + i] + __uint_as_float(c[i + 5])) * inv),
+                               pack_h2((o[38 + i] + __uint_as_float(c[i + 6])) * inv, (o[39 + i] + __uint_as_float(c[i + 7])) * inv));
+            }
+#pragma unroll
+            for (int i = 0; i < 16; i += 8)
+                *reinterpret_cast<uint4*>(dst + 64 + i) =
+                    make_uint4(pack_h2((o[64 + i] + __uint_as_float(d[i])) * inv, (o[65 + i] + __uint_as_float(d[i + 1])) * inv),
+                               pack_h2((o[66 + i] + __uint_as_float(d[i + 2])) * inv, (o[67 + i] + __uint_as_float(d[i + 3])) * inv),
+                               pack_h2((o[68 + i] + __uint_as_float(d[i + 4])) * inv, (o[69 + i] + __uint_as_float(d[i + 5])) * inv),
+                               pack_h2((o[70 + i] + __uint_as_float(d[i + 6])) * inv, (o[71 + i] + __uint_as_float(d[i + 7])) * inv));
+        }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    if (warp == 2) ptx::tmem_dealloc(tmem_base, 512);
+}
+
+PFN_cuTensorMapEncodeTiled_v12000 ft_encode_fn() {
+    static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+    }
+    return fn;
+}
+
+int ft_tmap_2d(CUtensorMap* tm, const void* base, uint64_t cols, uint64_t rows, uint64_t row_stride_bytes, uint32_t box_cols,
+               uint32_t box_rows) {
+    auto fn = ft_encode_fn();
+    CVB_CHECK(fn != nullptr, CVB_ECUDA, "cuTensorMapEncodeTiled entry point not available");
+    uint64_t dims[2] = {cols, rows};
+    uint64_t str[1] = {row_stride_bytes};
+    uint32_t box[2] = {box_cols, box_rows};
+    uint32_t estr[2] = {1, 1};
+    CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, str, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CVB_CHECK(r == CUDA_SUCCESS, CVB_ECUDA, "flash_tc: cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return CVB_OK;
+}
+
+}  // namespace
+
+bool op_attention_tc_supported(int S, int hd, const __half* Rh, int gh, int gw) {
+    return hd == FT_HD && Rh != nullptr && gw == FT_BK && gh <= 64 && gh * gw == S && S % FT_BQ == 0;
+}
+
+size_t op_attention_tc_workspace_bytes(int Gb, int S, int heads) {
+    const size_t vt = align_up((size_t)Gb * heads * FT_HD * S * 2, 1024);
+    const size_t bias = align_up((size_t)Gb * heads * S * 64 * 2, 1024);
+    return vt + 2 * bias + 1024;
+}
+
+int op_attention_tc(const __half* qkv, int Gb, int S, int heads, int hd, float scale, const __half* Rh, const __half* Rw, int gh,
+                    int gw, __half* out, void* workspace, size_t ws_bytes, cudaStream_t stream) {
+    CVB_CHECK(qkv && out && workspace, CVB_EARG, "attention_tc: null operand");
+    CVB_CHECK(op_attention_tc_supported(S, hd, Rh, gh, gw) && Rw != nullptr, CVB_ESHAPE,
+              "attention_tc: needs head dim 80, a 64-wide token grid and S %% 128 == 0 (S=%d hd=%d grid %dx%d)", S, hd, gh, gw);
+    CVB_CHECK(ws_bytes >= op_attention_tc_workspace_bytes(Gb, S, heads), CVB_EWORKSPACE, "attention_tc: workspace too small");
+    CVB_CHECK(((uintptr_t)workspace & 1023) == 0, CVB_EARG, "attention_tc: workspace must be 1024-byte aligned");
+    const int D = heads * hd;
+    uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+    __half* vt = reinterpret_cast<__half*>(ws);
+    const size_t vt_b = align_up((size_t)Gb * heads * FT_HD * S * 2, 1024);
+    const size_t bias_b = align_up((size_t)Gb * heads * S * 64 * 2, 1024);
+    __half* bias_h = reinterpret_cast<__half*>(ws + vt_b);
+    __half* bias_w = reinterpret_cast<__half*>(ws + vt_b + bias_b);
+
+    static bool configured = false;
+    if (!configured) {
+        CVB_CUDA(cudaFuncSetAttribute(flash_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FT_SMEM));
+        configured = true;
+    }
+    const dim3 grid64(S / 64, Gb * heads);
+    v_transpose_kernel<<<grid64, 256, 0, stream>>>(qkv, S, heads, vt);
+    CVB_TRY(op_relpos_tables(qkv, Gb, S, heads, hd, Rh, Rw, gh, gw, bias_h, bias_w, stream));
+    CUtensorMap tq, tk, tv;
+    CVB_TRY(ft_tmap_2d(&tq, qkv, (uint64_t)3 * D, (uint64_t)Gb * S, (uint64_t)3 * D * 2, 64, FT_BQ));
+    CVB_TRY(ft_tmap_2d(&tk, qkv, (uint64_t)3 * D, (uint64_t)Gb * S, (uint64_t)3 * D * 2, 64, FT_BK));
+    CVB_TRY(ft_tmap_2d(&tv, vt, (uint64_t)S, (uint64_t)Gb * heads * FT_HD, (uint64_t)S * 2, 64, FT_HD));
+    flash_tc_kernel<<<dim3(S / FT_BQ, Gb * heads), FT_THREADS, FT_SMEM, stream>>>(tq, tk, tv, bias_h, bias_w, S, heads, scale, out);
+    cvb_note_launches(2);
+    CVB_CUDA(cudaGetLastError());
+    return CVB_OK;
+}

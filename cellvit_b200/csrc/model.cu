@@ -23,6 +23,8 @@ struct cvb_model {
     std::unordered_map<std::string, const void*> params;
 };
 
+static bool g_attn_tc_enabled = true;  // cvb_set_attention_tc(0) selects the mma.sync flash kernel for the global blocks
+
 namespace {
 
 struct Arena {
@@ -138,6 +140,14 @@ int forward_impl(cvb_model& m, const float* x, int B, int H, int W, float* o_np,
     for (int k = 0; k < 4; ++k) z[k] = A.alloc<__half>((size_t)B * T * D);
 
     __half* ybuf = A.alloc<__half>(rows_max * D);
+    // global-attention blocks of SAM-H run on the tcgen05 attention kernel (needs V^T + bias tables scratch)
+    const bool attn_tc = sam && g_attn_tc_enabled && op_attention_tc_supported(Tx, hd, reinterpret_cast<const __half*>(1), h, w);
+    const size_t attn_ws_bytes = attn_tc ? op_attention_tc_workspace_bytes(B, Tx, heads) : 0;
+    uint8_t* attn_ws = nullptr;
+    if (attn_tc) {
+        attn_ws = A.alloc<uint8_t>(attn_ws_bytes + 1024);
+        attn_ws = reinterpret_cast<uint8_t*>(((uintptr_t)attn_ws + 1023) & ~(uintptr_t)1023);
+    }
     for (int i = 0; i < d.depth; ++i) {
         const std::string p = "b" + std::to_string(i);
         bool is_global = !sam;
@@ -155,7 +165,10 @@ int forward_impl(cvb_model& m, const float* x, int B, int H, int W, float* o_np,
         const int Gb = win ? B * g * g : B, S = win ? ws * ws : Tx, gh = win ? ws : h, gw = win ? ws : w;
         const __half* th = sam ? f.P<__half>(p + ".relh") : nullptr;
         const __half* tw = sam ? f.P<__half>(p + ".relw") : nullptr;
-        if (f.live()) f.chk(op_attention(qkv, Gb, S, heads, hd, scale, th, tw, gh, gw, att, st));
+        if (f.live()) {
+            if (attn_tc && !win) f.chk(op_attention_tc(qkv, Gb, S, heads, hd, scale, th, tw, gh, gw, att, attn_ws, attn_ws_bytes, st));
+            else f.chk(op_attention(qkv, Gb, S, heads, hd, scale, th, tw, gh, gw, att, st));
+        }
         {
             // attn-out projection writes fp16 y (+bias) in window order; the residual add x += unpartition(y) is fused
             // into norm2 below (coalesced) -- with K = 1280 a scattered fp32 read-modify-write epilogue is slower than
@@ -328,3 +341,5 @@ CVB_API int cvb_forward(cvb_model* m, const float* x, int B, int H, int W, float
 }
 
 CVB_API void cvb_model_destroy(cvb_model* m) { delete m; }
+
+CVB_API void cvb_set_attention_tc(int on) { g_attn_tc_enabled = on != 0; }

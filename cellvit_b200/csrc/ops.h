@@ -61,3 +61,17 @@ int op_cls_head(const float* x, int B, int T, int D, const float* gamma, const f
 // (row = q - k + g - 1), applied to the UNSCALED q inside the kernel; both null = no bias (ViT-S).
 int op_attention(const __half* qkv, int Gb, int S, int heads, int hd, float scale, const __half* Rh, const __half* Rw,
                  int gh, int gw, __half* out, cudaStream_t stream);
+
+// Decomposed rel-pos bias tables of a global-attention call (attention.cu, MMA path): bias_h / bias_w fp16
+// [(g*heads + head)*S + q][64] = log2(e) * <q, R[qpos - k + g - 1]> for k < gh / gw (other entries zero).
+int op_relpos_tables(const __half* qkv, int Gb, int S, int heads, int hd, const __half* Rh, const __half* Rw, int gh, int gw,
+                     __half* bias_h, __half* bias_w, cudaStream_t stream);
+
+// --- flash_tc.cu ------------------------------------------------------------------------------------
+// tcgen05 version of op_attention for the SAM global-attention shape (head dim 80, 64-wide token grid, S % 128 == 0,
+// rel-pos tables present). `workspace` (1024-byte aligned, op_attention_tc_workspace_bytes) holds V^T and the two
+// decomposed rel-pos bias tables of the call.
+bool op_attention_tc_supported(int S, int hd, const __half* Rh, int gh, int gw);
+size_t op_attention_tc_workspace_bytes(int Gb, int S, int heads);
+int op_attention_tc(const __half* qkv, int Gb, int S, int heads, int hd, float scale, const __half* Rh, const __half* Rw, int gh,
+                    int gw, __half* out, void* workspace, size_t ws_bytes, cudaStream_t stream);

@@ -144,6 +144,11 @@ int cvb_op_layernorm_f16(const float* x, const float* gamma, const float* beta, 
 /* Rh / Rw: fp16 rel-pos tables [2*gh-1, hd] / [2*gw-1, hd] (both null: no bias). */
 int cvb_op_attention(const void* qkv, int Gb, int S, int heads, int hd, float scale, const void* Rh, const void* Rw,
                      int gh, int gw, void* out, void* stream);
+/* tcgen05 attention for the SAM global-attention shape (head dim 80, 64-wide token grid, S % 128 == 0, rel-pos tables
+ * required); workspace (1024-byte aligned) holds V^T and the rel-pos bias tables of the call. */
+int cvb_op_attention_tc_workspace_bytes(int Gb, int S, int heads, size_t* out);
+int cvb_op_attention_tc(const void* qkv, int Gb, int S, int heads, int hd, float scale, const void* Rh, const void* Rw,
+                        int gh, int gw, void* out, void* workspace, size_t ws_bytes, void* stream);
 int cvb_op_patch_im2col(const float* x, int B, int H, int W, int P, void* out, void* stream);
 int cvb_op_stem_conv(const float* x, int B, int H, int W, const float* w, const float* scale, const float* shift,
                      void* out, int cpad, void* stream);

@@ -133,3 +133,52 @@ def test_forward_full_size_1024_matches_oracle_on_device(arch, B):
             assert err <= 5e-3, (k, err)
         else:
             assert err <= 2e-2 * max(1.0, ref.abs().max().item()), (k, err)
+
+
+@pytest.mark.parametrize("Gb,heads", [(1, 2), (2, 3)])
+def test_attention_tc_matches_torch(Gb, heads):
+    """tcgen05 global attention (flash_tc.cu): SAM-H shape -- 64 x 64 tokens, head dim 80, decomposed rel-pos bias."""
+    g = torch.Generator(device="cuda").manual_seed(11)
+    gh = gw = 64
+    hd, S = 80, 4096
+    D = heads * hd
+    qkv = (torch.randn(Gb * S, 3 * D, device="cuda", generator=g)).half()
+    Rh = (torch.randn(2 * gh - 1, hd, device="cuda", generator=g) * 0.2).half()
+    Rw = (torch.randn(2 * gw - 1, hd, device="cuda", generator=g) * 0.2).half()
+    out = torch.full((Gb * S, D), float("nan"), device="cuda", dtype=torch.half)
+    need = C.c_size_t()
+    L.check(L.lib().cvb_op_attention_tc_workspace_bytes(Gb, S, heads, C.byref(need)), "ws")
+    ws = torch.empty(need.value + 1024, dtype=torch.uint8, device="cuda")
+    off = (-ws.data_ptr()) % 1024
+    scale = hd ** -0.5
+    L.check(L.lib().cvb_op_attention_tc(L.ptr(qkv), Gb, S, heads, hd, C.c_float(scale), L.ptr(Rh), L.ptr(Rw), gh, gw, L.ptr(out),
+                                        C.c_void_p(ws.data_ptr() + off), C.c_size_t(need.value), L.stream_ptr()), "attention_tc")
+    torch.cuda.synchronize()
+    ref = _ref_attention(qkv, Gb, S, heads, hd, scale, Rh.float(), Rw.float(), gh, gw)
+    err = (out.float() - ref).abs().max().item()
+    assert err < 4e-3, err
+    # and against the mma.sync kernel on the same inputs
+    out2 = torch.empty_like(out)
+    L.check(L.lib().cvb_op_attention(L.ptr(qkv), Gb, S, heads, hd, C.c_float(scale), L.ptr(Rh), L.ptr(Rw), gh, gw, L.ptr(out2),
+                                     L.stream_ptr()), "attention")
+    assert (out.float() - out2.float()).abs().max().item() < 8e-3  # two fp16-output kernels, each within 4e-3 of the fp32 reference
+
+
+def test_forward_sam_h_1024_attention_tc_vs_mma_sync():
+    """Full SAM-H forward on a 1024^2 tile: the tcgen05 global-attention path against the (oracle-validated) mma.sync path."""
+    from cellvit_b200.cellvit import CellViTSAM
+    sd = weights.synth_state_dict("SAM-H", 6, 19, seed=3)
+    m = CellViTSAM(None, 6, 19, "SAM-H")
+    m.load_state_dict(sd, strict=True)
+    m = m.cuda().eval()
+    x = torch.from_numpy(synth.synthetic_tiles(1, 1024, seed=5)).cuda()
+    outs = []
+    for on in (1, 0):
+        L.lib().cvb_set_attention_tc(on)
+        with torch.no_grad():
+            outs.append({k: v.clone() for k, v in m(x, retrieve_tokens=True).items()})
+    L.lib().cvb_set_attention_tc(1)
+    for k in ("nuclei_binary_map", "hv_map", "nuclei_type_map", "tokens"):
+        err = (outs[0][k] - outs[1][k]).abs().max().item()
+        tol = 2e-4 if k != "tokens" else 1e-3 * max(1.0, outs[1][k].abs().max().item())  # tokens are O(10): relative bar
+        assert err <= tol, (k, err)
