@@ -5,7 +5,7 @@
 // per (image, head): S = 4096 keys (64 x 64 token grid), head dim 80. Replaces the mma.sync flash kernel for this
 // shape (246 TFLOP/s, 44 % of the legacy-HMMA ceiling) with a warp-specialised kernel in the style of the tile engine:
 //
-//   CTA = 128 queries of one (image, head); key tiles of 64 keys = ONE key row of the token grid, so rel_h is a per-query
+//   CTA = 2 x 128 queries of one (image, head) sharing every K / V tile; key tiles of 64 keys = ONE key row of the token grid, so rel_h is a per-query
 //   scalar for the whole tile and rel_w[q, 0..63] is the same vector for every tile (kept in registers).
 //   warp 0   TMA producer: Q once (two 64-column boxes: hd columns 0-63 and 16-79 -- the fifth k-step reads columns
 //            64-79 out of the second box, so only the proven 128B-swizzle K-major layout is used), then per key
@@ -14,9 +14,10 @@
 //            once the softmax warps have published P_t; QK of tile t+1 is issued before PV of tile t so the tensor
 //            pipe works while tile t is in the softmax.
 //   warp 2   TMEM allocator.   warps 4-7  softmax: one query row per thread (TMEM lane), exact online softmax in
-//            the log2 domain, P written to shared memory as the fp16 K-major A operand of PV (128B swizzle), the
-//            per-tile partial output read back from TMEM and accumulated in registers (rescaled when the running
-//            max moves).
+//            the log2 domain, P written to shared memory as the fp16 K-major A operand of PV (128B swizzle). O accumulates
+//            in TMEM across all key tiles; the softmax reference m only moves when a score exceeds it by more than 2^8
+//            (P stays <= 256 in fp16, sums in fp32 -- mathematically the same softmax), and only then is O rescaled in
+//            place (tcgen05.ld / st) -- after the first tile practically never, so the softmax warps never wait for PV.
 // V must be K-major for the B operand of P V, i.e. transposed to [hd, keys]: v_transpose_kernel does that once per
 // block (42 MB). The decomposed rel-pos bias tables rel_h / rel_w [q, 64] come from relpos_tables_kernel (attention.cu:
 // G = Q R^T through the MMA path, UNSCALED q, pre-multiplied by log2(e), fp16 as in the mma.sync kernel).
@@ -27,12 +28,9 @@
 namespace {
 
 constexpr int FT_BQ = 128, FT_BK = 64, FT_HD = 80, FT_STAGES = 3;
-constexpr int FT_THREADS = 256;
-constexpr uint32_t FT_Q_BYTES = 2 * FT_BQ * 128;          // two boxes of 128 rows x 128 B
 constexpr uint32_t FT_K_BYTES = 2 * FT_BK * 128;          // two boxes of 64 rows x 128 B
 constexpr uint32_t FT_V_BYTES = FT_HD * 128;              // 80 rows (hd) x 64 keys
-constexpr uint32_t FT_P_BYTES = FT_BQ * 128;              // 128 rows x 64 keys fp16
-constexpr uint32_t FT_SMEM = 1024 + FT_Q_BYTES + FT_STAGES * (FT_K_BYTES + FT_V_BYTES) + 2 * FT_P_BYTES + 256;
+constexpr int FT_NG = 2;                                  // query groups (of 128 rows) per CTA
 constexpr float FT_L2E = 1.4426950408889634f;
 
 // ------------------------------------------------------------------------------------------ V^T
@@ -60,34 +58,45 @@ v_transpose_kernel(const __half* __restrict__ qkv, int S, int heads, __half* __r
 }
 
 // ------------------------------------------------------------------------------------------ main kernel
-__global__ void __launch_bounds__(FT_THREADS, 1)
+// NG query groups of 128 rows per CTA share every K / V^T tile; each group has its own S double buffer, O accumulator,
+// P double buffer and four softmax warps (NG = 2: 8 softmax warps, two per scheduler).
+template <int NG>
+struct FtCfg {
+    static constexpr int THREADS = 128 + NG * 128;
+    static constexpr uint32_t Q_BYTES = NG * 2 * FT_BQ * 128;
+    static constexpr uint32_t P_BYTES = FT_BQ * 128;
+    static constexpr uint32_t SMEM = 1024 + Q_BYTES + FT_STAGES * (FT_K_BYTES + FT_V_BYTES) + NG * 2 * P_BYTES + 512;
+};
+
+template <int NG>
+__global__ void __launch_bounds__(FtCfg<NG>::THREADS, 1)
 flash_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const __half* __restrict__ bias_h, const __half* __restrict__ bias_w,
                 int S, int heads, float scale, __half* __restrict__ out) {
+    using Cfg = FtCfg<NG>;
     extern __shared__ uint8_t ft_smem_raw[];
     const uint32_t smem_base = (ptx::smem_u32(ft_smem_raw) + 1023u) & ~1023u;
     uint8_t* smem_gen = ft_smem_raw + (smem_base - ptx::smem_u32(ft_smem_raw));
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
     const int ghd = blockIdx.y, g = ghd / heads, head = ghd - g * heads;
-    const int q0 = blockIdx.x * FT_BQ;
+    const int q0 = blockIdx.x * (NG * FT_BQ);
     const int D = heads * FT_HD;
     const int n_t = S / FT_BK;
 
     const uint32_t sQ = smem_base;
-    const uint32_t sK = sQ + FT_Q_BYTES;
+    const uint32_t sK = sQ + Cfg::Q_BYTES;
     const uint32_t sV = sK + FT_STAGES * FT_K_BYTES;
     const uint32_t sP = sV + FT_STAGES * FT_V_BYTES;
-    const uint32_t bar = sP + 2 * FT_P_BYTES;
-    // barriers (8 B each)
+    const uint32_t bar = sP + NG * 2 * Cfg::P_BYTES;
+    // barriers (8 B each); per-group ones are indexed by gb = group * 2 + buffer
     const uint32_t q_full = bar;
-    auto kv_full = [&](int s) { return bar + 8u * (1 + s); };
-    auto kv_empty = [&](int s) { return bar + 8u * (4 + s); };
-    auto s_full = [&](int b) { return bar + 8u * (7 + b); };
-    auto s_empty = [&](int b) { return bar + 8u * (9 + b); };
-    auto p_full = [&](int b) { return bar + 8u * (11 + b); };
-    auto o_full = [&](int b) { return bar + 8u * (13 + b); };
-    auto o_empty = [&](int b) { return bar + 8u * (15 + b); };
-    const uint32_t tmem_slot = bar + 8u * 17;
+    auto kv_full = [&](int st) { return bar + 8u * (1 + st); };
+    auto kv_empty = [&](int st) { return bar + 8u * (4 + st); };
+    auto s_full = [&](int gb) { return bar + 8u * (7 + gb); };
+    auto s_empty = [&](int gb) { return bar + 8u * (7 + 2 * NG + gb); };
+    auto p_full = [&](int gb) { return bar + 8u * (7 + 4 * NG + gb); };
+    auto o_full = [&](int gb) { return bar + 8u * (7 + 6 * NG + gb); };
+    const uint32_t tmem_slot = bar + 8u * (7 + 8 * NG);
 
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tmap(&tmQ);
@@ -96,13 +105,12 @@ flash_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     }
     if (warp == 1 && lane == 0) {
         ptx::mbar_init(q_full, 1);
-        for (int s = 0; s < FT_STAGES; ++s) { ptx::mbar_init(kv_full(s), 1); ptx::mbar_init(kv_empty(s), 1); }
-        for (int b = 0; b < 2; ++b) {
-            ptx::mbar_init(s_full(b), 1);
-            ptx::mbar_init(s_empty(b), 128);
-            ptx::mbar_init(p_full(b), 128);
-            ptx::mbar_init(o_full(b), 1);
-            ptx::mbar_init(o_empty(b), 128);
+        for (int st = 0; st < FT_STAGES; ++st) { ptx::mbar_init(kv_full(st), 1); ptx::mbar_init(kv_empty(st), 1); }
+        for (int gb = 0; gb < 2 * NG; ++gb) {
+            ptx::mbar_init(s_full(gb), 1);
+            ptx::mbar_init(s_empty(gb), 128);
+            ptx::mbar_init(p_full(gb), 128);
+            ptx::mbar_init(o_full(gb), 1);
         }
         ptx::fence_barrier_init();
     }
@@ -114,17 +122,20 @@ flash_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
-    // TMEM columns: S buffers at 0 / 64, O buffers at 128 / 224 (80 used of 96)
-    auto tS = [&](int b) { return tmem_base + (uint32_t)(b * 64); };
-    auto tO = [&](int b) { return tmem_base + 128u + (uint32_t)(b * 96); };
+    // TMEM columns: S[group][buffer] at (group*2 + buffer)*64, O[group] at NG*128 + group*96 (80 used)
+    auto tS = [&](int gb) { return tmem_base + (uint32_t)(gb * 64); };
+    auto tO = [&](int grp) { return tmem_base + (uint32_t)(NG * 128 + grp * 96); };
 
     if (warp == 0) {
         // ===================================================== TMA producer
         const int row_q = g * S + q0;
         if (ptx::elect_one()) {
-            ptx::mbar_expect_tx(q_full, FT_Q_BYTES);
-            ptx::tma_load_2d(sQ, &tmQ, q_full, head * FT_HD, row_q);
-            ptx::tma_load_2d(sQ + FT_BQ * 128, &tmQ, q_full, head * FT_HD + 16, row_q);
+            ptx::mbar_expect_tx(q_full, Cfg::Q_BYTES);
+#pragma unroll
+            for (int grp = 0; grp < NG; ++grp) {
+                ptx::tma_load_2d(sQ + grp * 2 * FT_BQ * 128, &tmQ, q_full, head * FT_HD, row_q + grp * FT_BQ);
+                ptx::tma_load_2d(sQ + grp * 2 * FT_BQ * 128 + FT_BQ * 128, &tmQ, q_full, head * FT_HD + 16, row_q + grp * FT_BQ);
+            }
         }
         int stage = 0;
         uint32_t phase = 0;
@@ -151,31 +162,39 @@ flash_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         auto issue_qk = [&](int t) {
             const int stage = t % FT_STAGES, b = t & 1;
             ptx::mbar_wait(kv_full(stage), (uint32_t)((t / FT_STAGES) & 1));
-            ptx::mbar_wait(s_empty(b), (uint32_t)(((t >> 1) & 1) ^ 1));
-            ptx::tc_fence_after();
-            if (ptx::elect_one()) {
-                const uint64_t a0 = desc(sQ), a1 = desc(sQ + FT_BQ * 128);
-                const uint64_t b0 = desc(sK + stage * FT_K_BYTES), b1 = desc(sK + stage * FT_K_BYTES + FT_BK * 128);
 #pragma unroll
-                for (int k = 0; k < 4; ++k) ptx::umma_f16(tS(b), a0 + 2u * k, b0 + 2u * k, idesc_qk, k != 0 ? 1u : 0u);
-                ptx::umma_f16(tS(b), a1 + 6u, b1 + 6u, idesc_qk, 1u);  // hd columns 64-79 = columns 48-63 of the second box
-                ptx::umma_commit(s_full(b));
+            for (int grp = 0; grp < NG; ++grp) {
+                const int gb = grp * 2 + b;
+                ptx::mbar_wait(s_empty(gb), (uint32_t)(((t >> 1) & 1) ^ 1));
+                ptx::tc_fence_after();
+                if (ptx::elect_one()) {
+                    const uint32_t q = sQ + grp * 2 * FT_BQ * 128;
+                    const uint64_t a0 = desc(q), a1 = desc(q + FT_BQ * 128);
+                    const uint64_t b0 = desc(sK + stage * FT_K_BYTES), b1 = desc(sK + stage * FT_K_BYTES + FT_BK * 128);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) ptx::umma_f16(tS(gb), a0 + 2u * k, b0 + 2u * k, idesc_qk, k != 0 ? 1u : 0u);
+                    ptx::umma_f16(tS(gb), a1 + 6u, b1 + 6u, idesc_qk, 1u);  // hd columns 64-79 = columns 48-63 of the second box
+                    ptx::umma_commit(s_full(gb));
+                }
+                __syncwarp();
             }
-            __syncwarp();
         };
         auto issue_pv = [&](int t) {
             const int stage = t % FT_STAGES, b = t & 1;
-            ptx::mbar_wait(p_full(b), (uint32_t)((t >> 1) & 1));
-            ptx::mbar_wait(o_empty(b), (uint32_t)(((t >> 1) & 1) ^ 1));
-            ptx::tc_fence_after();
-            if (ptx::elect_one()) {
-                const uint64_t a0 = desc(sP + b * FT_P_BYTES), b0 = desc(sV + stage * FT_V_BYTES);
 #pragma unroll
-                for (int k = 0; k < 4; ++k) ptx::umma_f16(tO(b), a0 + 2u * k, b0 + 2u * k, idesc_pv, k != 0 ? 1u : 0u);
-                ptx::umma_commit(o_full(b));
-                ptx::umma_commit(kv_empty(stage));
+            for (int grp = 0; grp < NG; ++grp) {
+                const int gb = grp * 2 + b;
+                ptx::mbar_wait(p_full(gb), (uint32_t)((t >> 1) & 1));
+                ptx::tc_fence_after();
+                if (ptx::elect_one()) {
+                    const uint64_t a0 = desc(sP + gb * Cfg::P_BYTES), b0 = desc(sV + stage * FT_V_BYTES);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) ptx::umma_f16(tO(grp), a0 + 2u * k, b0 + 2u * k, idesc_pv, (t | k) != 0 ? 1u : 0u);
+                    ptx::umma_commit(o_full(gb));
+                    if (grp == NG - 1) ptx::umma_commit(kv_empty(stage));
+                }
+                __syncwarp();
             }
-            __syncwarp();
         };
         issue_qk(0);
         for (int t = 0; t < n_t; ++t) {
@@ -184,8 +203,8 @@ flash_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         }
     } else if (warp >= 4) {
         // ===================================================== softmax / output: one query row per thread
-        const int quad = warp & 3, r = quad * 32 + lane;
-        const long long row = (long long)ghd * S + q0 + r;
+        const int grp = (warp - 4) >> 2, quad = warp & 3, r = quad * 32 + lane;
+        const long long row = (long long)ghd * S + q0 + grp * FT_BQ + r;
         const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
         const float sl2 = scale * FT_L2E;
         // rel_w[q, 0..63] (log2 domain) packed as 32 half2 registers
@@ -199,25 +218,22 @@ flash_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             }
         }
         const __half* bh_row = bias_h + row * 64;
-        float o[FT_HD];
-#pragma unroll
-        for (int i = 0; i < FT_HD; ++i) o[i] = 0.f;
-        float m_run = -INFINITY, l_run = 0.f;
+        float m_ref = -INFINITY, l_run = 0.f;
         float bh_next = __half2float(__ldg(bh_row));
         const uint32_t p_row = (uint32_t)r * 128u;
         const uint32_t sw = (uint32_t)(r & 7);
         for (int t = 0; t < n_t; ++t) {
-            const int b = t & 1;
+            const int gb = grp * 2 + (t & 1);
             const float bh = bh_next;
             if (t + 1 < n_t) bh_next = __half2float(__ldg(bh_row + t + 1));
-            ptx::mbar_wait(s_full(b), (uint32_t)((t >> 1) & 1));
+            ptx::mbar_wait(s_full(gb), (uint32_t)((t >> 1) & 1));
             ptx::tc_fence_after();
             uint32_t v0[32], v1[32];
-            ptx::tmem_ld32(tS(b) + lane_off, v0);
-            ptx::tmem_ld32(tS(b) + lane_off + 32u, v1);
+            ptx::tmem_ld32(tS(gb) + lane_off, v0);
+            ptx::tmem_ld32(tS(gb) + lane_off + 32u, v1);
             ptx::tmem_ld_wait();
             ptx::tc_fence_before();
-            ptx::mbar_arrive(s_empty(b));
+            ptx::mbar_arrive(s_empty(gb));
             // scores in the log2 domain (without the per-tile scalar bh), and their maximum
             float mx = -INFINITY;
 #pragma unroll
@@ -230,10 +246,29 @@ flash_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 v1[2 * j] = __float_as_uint(c0); v1[2 * j + 1] = __float_as_uint(c1);
                 mx = fmaxf(mx, fmaxf(fmaxf(a0, a1), fmaxf(c0, c1)));
             }
-            const float m_new = fmaxf(m_run, mx + bh);
-            const float alpha = ptx::ex2(m_run - m_new);  // 0 on the first tile (m_run = -inf)
-            m_run = m_new;
-            const float mref = m_new - bh;
+            // lazy reference update: move m only when this tile exceeds it by more than 8 (a factor 256)
+            const float cand = mx + bh;
+            const bool move = cand > m_ref + 8.0f;  // always true on the first tile (m_ref = -inf)
+            if (__any_sync(0xffffffffu, move) && t > 0) {
+                // rare: rescale the accumulated O (TMEM) and l of the rows that moved; all PV issued so far must be done
+                const float alpha = move ? ptx::ex2(m_ref - cand) : 1.0f;
+                ptx::mbar_wait(o_full(grp * 2 + ((t - 1) & 1)), (uint32_t)(((t - 1) >> 1) & 1));
+                ptx::tc_fence_after();
+#pragma unroll 1
+                for (int c0 = 0; c0 < FT_HD; c0 += 16) {
+                    uint32_t d[16];
+                    ptx::tmem_ld16(tO(grp) + lane_off + (uint32_t)c0, d);
+                    ptx::tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) d[i] = __float_as_uint(__uint_as_float(d[i]) * alpha);
+                    ptx::tmem_st16(tO(grp) + lane_off + (uint32_t)c0, d);
+                }
+                ptx::tmem_st_wait();
+                ptx::tc_fence_before();
+                l_run *= alpha;
+            }
+            if (move) m_ref = cand;
+            const float mref = m_ref - bh;
             float rs = 0.f;
             uint32_t pk[32];
 #pragma unroll
@@ -244,10 +279,10 @@ flash_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 pk[j] = pack_h2(p0, p1);
                 pk[16 + j] = pack_h2(p2, p3);
             }
-            l_run = l_run * alpha + rs;
+            l_run += rs;
             // P row (64 keys fp16 = 8 chunks of 16 B) into the K-major SWIZZLE_128B A operand: chunk c -> c ^ (row & 7)
             {
-                const uint32_t base = sP + b * FT_P_BYTES + p_row;
+                const uint32_t base = sP + gb * Cfg::P_BYTES + p_row;
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
                     const uint32_t addr = base + (((uint32_t)c ^ sw) << 4);
@@ -256,56 +291,24 @@ flash_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 }
             }
             ptx::fence_proxy_async();  // generic-proxy writes -> visible to the tensor core (async proxy)
-            ptx::mbar_arrive(p_full(b));
-            // previous tile's partial output: o = (o + O_{t-1}) * alpha  (both terms are in the scale of m_{t-1})
-            if (t > 0) {
-                const int pb = b ^ 1;
-                ptx::mbar_wait(o_full(pb), (uint32_t)(((t - 1) >> 1) & 1));
-                ptx::tc_fence_after();
-                uint32_t a[32], c[32], d[16];
-                ptx::tmem_ld32(tO(pb) + lane_off, a);
-                ptx::tmem_ld32(tO(pb) + lane_off + 32u, c);
-                ptx::tmem_ld16(tO(pb) + lane_off + 64u, d);
-                ptx::tmem_ld_wait();
-                ptx::tc_fence_before();
-                ptx::mbar_arrive(o_empty(pb));
-#pragma unroll
-                for (int i = 0; i < 32; ++i) { o[i] = (o[i] + __uint_as_float(a[i])) * alpha; o[32 + i] = (o[32 + i] + __uint_as_float(c[i])) * alpha; }
-#pragma unroll
-                for (int i = 0; i < 16; ++i) o[64 + i] = (o[64 + i] + __uint_as_float(d[i])) * alpha;
-            }
+            ptx::mbar_arrive(p_full(gb));
         }
-        {   // last tile's partial output
-            const int pb = (n_t - 1) & 1;
-            ptx::mbar_wait(o_full(pb), (uint32_t)(((n_t - 1) >> 1) & 1));
+        {   // all key tiles accumulated: O / l
+            ptx::mbar_wait(o_full(grp * 2 + ((n_t - 1) & 1)), (uint32_t)(((n_t - 1) >> 1) & 1));
             ptx::tc_fence_after();
-            uint32_t a[32], c[32], d[16];
-            ptx::tmem_ld32(tO(pb) + lane_off, a);
-            ptx::tmem_ld32(tO(pb) + lane_off + 32u, c);
-            ptx::tmem_ld16(tO(pb) + lane_off + 64u, d);
-            ptx::tmem_ld_wait();
             const float inv = 1.0f / l_run;
-            __half* dst = out + ((long long)g * S + q0 + r) * D + head * FT_HD;
+            __half* dst = out + ((long long)g * S + q0 + grp * FT_BQ + r) * D + head * FT_HD;
+            auto f = [&](uint32_t u) { return __uint_as_float(u) * inv; };
+#pragma unroll 1
+            for (int c0 = 0; c0 < FT_HD; c0 += 16) {
+                uint32_t d[16];
+                ptx::tmem_ld16(tO(grp) + lane_off + (uint32_t)c0, d);
+                ptx::tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 32; i += 8) {
-                *reinterpret_cast<uint4*>(dst + i) =
-                    make_uint4(pack_h2((o[i] + __uint_as_float(a[i])) * inv, (o[i + 1] + __uint_as_float(a[i + 1])) * inv),
-                               pack_h2((o[i + 2] + __uint_as_float(a[i + 2])) * inv, (o[i + 3] + __uint_as_float(a[i + 3])) * inv),
-                               pack_h2((o[i + 4] + __uint_as_float(a[i + 4])) * inv, (o[i + 5] + __uint_as_float(a[i + 5])) * inv),
-                               pack_h2((o[i + 6] + __uint_as_float(a[i + 6])) * inv, (o[i + 7] + __uint_as_float(a[i + 7])) * inv));
-                *reinterpret_cast<uint4*>(dst + 32 + i) =
-                    make_uint4(pack_h2((o[32 + i] + __uint_as_float(c[i])) * inv, (o[33 + i] + __uint_as_float(c[i + 1])) * inv),
-                               pack_h2((o[34 + i] + __uint_as_float(c[i + 2])) * inv, (o[35 + i] + __uint_as_float(c[i + 3])) * inv),
-                               pack_h2((o[36 + i] + __uint_as_float(c[i + 4])) * inv, (o[37 + i] + __uint_as_float(c[i + 5])) * inv),
-                               pack_h2((o[38 + i] + __uint_as_float(c[i + 6])) * inv, (o[39 + i] + __uint_as_float(c[i + 7])) * inv));
+                for (int i = 0; i < 16; i += 8)
+                    *reinterpret_cast<uint4*>(dst + c0 + i) = make_uint4(pack_h2(f(d[i]), f(d[i + 1])), pack_h2(f(d[i + 2]), f(d[i + 3])),
+                                                                         pack_h2(f(d[i + 4]), f(d[i + 5])), pack_h2(f(d[i + 6]), f(d[i + 7])));
             }
-#pragma unroll
-            for (int i = 0; i < 16; i += 8)
-                *reinterpret_cast<uint4*>(dst + 64 + i) =
-                    make_uint4(pack_h2((o[64 + i] + __uint_as_float(d[i])) * inv, (o[65 + i] + __uint_as_float(d[i + 1])) * inv),
-                               pack_h2((o[66 + i] + __uint_as_float(d[i + 2])) * inv, (o[67 + i] + __uint_as_float(d[i + 3])) * inv),
-                               pack_h2((o[68 + i] + __uint_as_float(d[i + 4])) * inv, (o[69 + i] + __uint_as_float(d[i + 5])) * inv),
-                               pack_h2((o[70 + i] + __uint_as_float(d[i + 6])) * inv, (o[71 + i] + __uint_as_float(d[i + 7])) * inv));
         }
     }
     ptx::tc_fence_before();
@@ -344,7 +347,7 @@ int ft_tmap_2d(CUtensorMap* tm, const void* base, uint64_t cols, uint64_t rows, 
 }  // namespace
 
 bool op_attention_tc_supported(int S, int hd, const __half* Rh, int gh, int gw) {
-    return hd == FT_HD && Rh != nullptr && gw == FT_BK && gh <= 64 && gh * gw == S && S % FT_BQ == 0;
+    return hd == FT_HD && Rh != nullptr && gw == FT_BK && gh <= 64 && gh * gw == S && S % (FT_NG * FT_BQ) == 0;
 }
 
 size_t op_attention_tc_workspace_bytes(int Gb, int S, int heads) {
@@ -357,7 +360,7 @@ int op_attention_tc(const __half* qkv, int Gb, int S, int heads, int hd, float s
                     int gw, __half* out, void* workspace, size_t ws_bytes, cudaStream_t stream) {
     CVB_CHECK(qkv && out && workspace, CVB_EARG, "attention_tc: null operand");
     CVB_CHECK(op_attention_tc_supported(S, hd, Rh, gh, gw) && Rw != nullptr, CVB_ESHAPE,
-              "attention_tc: needs head dim 80, a 64-wide token grid and S %% 128 == 0 (S=%d hd=%d grid %dx%d)", S, hd, gh, gw);
+              "attention_tc: needs head dim 80, a 64-wide token grid and S %% 256 == 0 (S=%d hd=%d grid %dx%d)", S, hd, gh, gw);
     CVB_CHECK(ws_bytes >= op_attention_tc_workspace_bytes(Gb, S, heads), CVB_EWORKSPACE, "attention_tc: workspace too small");
     CVB_CHECK(((uintptr_t)workspace & 1023) == 0, CVB_EARG, "attention_tc: workspace must be 1024-byte aligned");
     const int D = heads * hd;
@@ -370,7 +373,7 @@ int op_attention_tc(const __half* qkv, int Gb, int S, int heads, int hd, float s
 
     static bool configured = false;
     if (!configured) {
-        CVB_CUDA(cudaFuncSetAttribute(flash_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FT_SMEM));
+        CVB_CUDA(cudaFuncSetAttribute(flash_tc_kernel<FT_NG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FtCfg<FT_NG>::SMEM));
         configured = true;
     }
     const dim3 grid64(S / 64, Gb * heads);
@@ -380,7 +383,8 @@ int op_attention_tc(const __half* qkv, int Gb, int S, int heads, int hd, float s
     CVB_TRY(ft_tmap_2d(&tq, qkv, (uint64_t)3 * D, (uint64_t)Gb * S, (uint64_t)3 * D * 2, 64, FT_BQ));
     CVB_TRY(ft_tmap_2d(&tk, qkv, (uint64_t)3 * D, (uint64_t)Gb * S, (uint64_t)3 * D * 2, 64, FT_BK));
     CVB_TRY(ft_tmap_2d(&tv, vt, (uint64_t)S, (uint64_t)Gb * heads * FT_HD, (uint64_t)S * 2, 64, FT_HD));
-    flash_tc_kernel<<<dim3(S / FT_BQ, Gb * heads), FT_THREADS, FT_SMEM, stream>>>(tq, tk, tv, bias_h, bias_w, S, heads, scale, out);
+    flash_tc_kernel<FT_NG><<<dim3(S / (FT_NG * FT_BQ), Gb * heads), FtCfg<FT_NG>::THREADS, FtCfg<FT_NG>::SMEM, stream>>>(tq, tk, tv, bias_h, bias_w, S, heads,
+                                                                                                               scale, out);
     cvb_note_launches(2);
     CVB_CUDA(cudaGetLastError());
     return CVB_OK;
