@@ -10,7 +10,8 @@
 // is just another K-major operand tile) and scatters G[q, j] to rel_h[q, kh = qh + gh - 1 - j] in shared memory;
 // same for rel_w. No separate rel-pos kernel, no HBM round trip of the bias tables.
 //
-// TODO(round 2): move QK^T / PV to tcgen05 with S and O in TMEM; attention is 5 % of the forward FLOPs.
+// The SAM global-attention shape (64 x 64 tokens, head dim 80) runs on tcgen05 instead (flash_tc.cu); this file keeps the
+// mma.sync kernels for the windows, ViT-S and the smaller token grids, and the rel-pos table kernel flash_tc.cu uses.
 #include "ops.h"
 
 namespace {
