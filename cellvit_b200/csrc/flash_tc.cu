@@ -317,6 +317,367 @@ flash_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     if (warp == 2) ptx::tmem_dealloc(tmem_base, 512);
 }
 
+// ------------------------------------------------------------------------------------------ windowed attention (14 x 14)
+// Same machinery for the SAM windows: CTA = one (window, head): 196 queries as two groups of 128 rows (rows past 196 are
+// the next window's tokens: computed, never stored), 196 keys as tiles of 64 + 64 + 64 + 16 (the last tile is a
+// 128x16x16 UMMA; keys 196..207 get P = 0). The decomposed rel-pos bias is produced in the kernel: G = Q Rcat^T is one
+// more UMMA (Rcat = [rel_h rows | rel_w rows], 64 x 80, K-major, parked in the O columns of TMEM before P V starts);
+// each thread keeps bh[kh] = G[qh + 13 - kh] and bw[kw] = G[32 + qw + 13 - kw] in registers, and because the key
+// tile loop is fully unrolled (kh, kw) of every score are compile-time constants. V^T comes from
+// v_transpose_win_kernel in a per-window layout padded to 208 keys (16-byte aligned TMA boxes).
+constexpr int WT_S = 196, WT_G = 14, WT_NT = 4, WT_VLD = 208, WT_STAGES = 2;
+constexpr uint32_t WT_Q_BYTES = 2 * 2 * FT_BQ * 128;
+constexpr uint32_t WT_R_BYTES = 2 * 64 * 128;
+constexpr uint32_t WT_P_BYTES = FT_BQ * 128;
+constexpr uint32_t WT_SMEM = 1024 + WT_Q_BYTES + WT_R_BYTES + WT_STAGES * (FT_K_BYTES + FT_V_BYTES) + 4 * WT_P_BYTES + 512;
+constexpr int WT_THREADS = 384;
+
+// v rows of window `item` [196, 3*D] -> vt [(head*hd + d)][item*208 + key], keys 196..207 zero
+__global__ void __launch_bounds__(256)
+v_transpose_win_kernel(const __half* __restrict__ qkv, int heads, int n_items, __half* __restrict__ vt) {
+    __shared__ __half tile[WT_VLD][FT_HD + 2];
+    const int item = blockIdx.x, head = blockIdx.y;
+    const int D = heads * FT_HD;
+    const __half* src = qkv + (long long)item * WT_S * 3 * D + 2 * D + head * FT_HD;
+    for (int i = threadIdx.x; i < WT_VLD * (FT_HD / 8); i += 256) {
+        const int r = i / (FT_HD / 8), c = i - r * (FT_HD / 8);
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (r < WT_S) v = *reinterpret_cast<const uint4*>(src + (long long)r * 3 * D + c * 8);
+        const __half* h = reinterpret_cast<const __half*>(&v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) tile[r][c * 8 + j] = h[j];
+    }
+    __syncthreads();
+    const long long ld = (long long)n_items * WT_VLD;
+    __half* dst = vt + (long long)head * FT_HD * ld + (long long)item * WT_VLD;
+    for (int i = threadIdx.x; i < FT_HD * (WT_VLD / 2); i += 256) {
+        const int d = i / (WT_VLD / 2), kp = i - d * (WT_VLD / 2);
+        *reinterpret_cast<__half2*>(dst + (long long)d * ld + 2 * kp) = __halves2half2(tile[2 * kp][d], tile[2 * kp + 1][d]);
+    }
+}
+
+__global__ void __launch_bounds__(WT_THREADS, 1)
+window_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                 const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmR, int heads, int n_items, float scale,
+                 __half* __restrict__ out) {
+    extern __shared__ uint8_t ft_smem_raw[];
+    const uint32_t smem_base = (ptx::smem_u32(ft_smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem_gen = ft_smem_raw + (smem_base - ptx::smem_u32(ft_smem_raw));
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
+    // persistent: CTA c works on (window, head) pairs c, c + gridDim.x, ... -- TMEM, barriers and the rel-pos operand are set
+    // up once, and the K / V ring runs ahead into the next pair. Every ring / buffer barrier completes an even number
+    // of phases per pair (4 key tiles, 2 buffers), so their parities are functions of the tile index alone; the
+    // once-per-pair barriers (q_full, q_empty, g_full, o_read) use the parity of the pair counter `it`.
+    const int D = heads * FT_HD;
+    const int n_work = n_items * heads;
+
+    const uint32_t sQ = smem_base;
+    const uint32_t sR = sQ + WT_Q_BYTES;
+    const uint32_t sK = sR + WT_R_BYTES;
+    const uint32_t sV = sK + WT_STAGES * FT_K_BYTES;
+    const uint32_t sP = sV + WT_STAGES * FT_V_BYTES;
+    const uint32_t bar = sP + 4 * WT_P_BYTES;
+    const uint32_t q_full = bar;  // Q (both groups) + Rcat
+    auto kv_full = [&](int st) { return bar + 8u * (1 + st); };
+    auto kv_empty = [&](int st) { return bar + 8u * (3 + st); };
+    auto s_full = [&](int gb) { return bar + 8u * (5 + gb); };
+    auto s_empty = [&](int gb) { return bar + 8u * (9 + gb); };
+    auto p_full = [&](int gb) { return bar + 8u * (13 + gb); };
+    auto o_full = [&](int gb) { return bar + 8u * (17 + gb); };
+    auto g_full = [&](int grp) { return bar + 8u * (21 + grp); };
+    auto o_read = [&](int grp) { return bar + 8u * (23 + grp); };
+    const uint32_t q_empty = bar + 8u * 25, r_full = bar + 8u * 26;
+    const uint32_t tmem_slot = bar + 8u * 27;
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tmap(&tmQ);
+        ptx::prefetch_tmap(&tmK);
+        ptx::prefetch_tmap(&tmV);
+        ptx::prefetch_tmap(&tmR);
+    }
+    if (warp == 1 && lane == 0) {
+        ptx::mbar_init(q_full, 1);
+        for (int st = 0; st < WT_STAGES; ++st) { ptx::mbar_init(kv_full(st), 1); ptx::mbar_init(kv_empty(st), 1); }
+        for (int gb = 0; gb < 4; ++gb) {
+            ptx::mbar_init(s_full(gb), 1);
+            ptx::mbar_init(s_empty(gb), 128);
+            ptx::mbar_init(p_full(gb), 128);
+            ptx::mbar_init(o_full(gb), 1);
+        }
+        ptx::mbar_init(g_full(0), 1);
+        ptx::mbar_init(g_full(1), 1);
+        ptx::mbar_init(o_read(0), 128);
+        ptx::mbar_init(o_read(1), 128);
+        ptx::mbar_init(q_empty, 1);
+        ptx::mbar_init(r_full, 1);
+        ptx::fence_barrier_init();
+    }
+    if (warp == 2) {
+        ptx::tmem_alloc(tmem_slot, 512);
+        ptx::tmem_relinquish();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
+    auto tS = [&](int gb) { return tmem_base + (uint32_t)(gb * 64); };
+    auto tO = [&](int grp) { return tmem_base + (uint32_t)(256 + grp * 96); };
+
+    if (warp == 0) {
+        // ===================================================== TMA producer
+        if (ptx::elect_one()) {
+            ptx::mbar_expect_tx(r_full, WT_R_BYTES);
+            ptx::tma_load_2d(sR, &tmR, r_full, 0, 0);
+            ptx::tma_load_2d(sR + 64 * 128, &tmR, r_full, 16, 0);
+        }
+        int stage = 0;
+        uint32_t phase = 0;
+        int it = 0;
+        for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++it) {
+            const int item = w / heads, head = w - item * heads;
+            const int row0 = item * WT_S;
+            ptx::mbar_wait(q_empty, (uint32_t)((it & 1) ^ 1));  // all Q K^T / G MMAs of the previous pair have read Q
+            if (ptx::elect_one()) {
+                ptx::mbar_expect_tx(q_full, WT_Q_BYTES);
+#pragma unroll
+                for (int grp = 0; grp < 2; ++grp) {
+                    ptx::tma_load_2d(sQ + grp * 2 * FT_BQ * 128, &tmQ, q_full, head * FT_HD, row0 + grp * FT_BQ);
+                    ptx::tma_load_2d(sQ + grp * 2 * FT_BQ * 128 + FT_BQ * 128, &tmQ, q_full, head * FT_HD + 16, row0 + grp * FT_BQ);
+                }
+            }
+            for (int t = 0; t < WT_NT; ++t) {
+                ptx::mbar_wait(kv_empty(stage), phase ^ 1u);
+                if (ptx::elect_one()) {
+                    ptx::mbar_expect_tx(kv_full(stage), FT_K_BYTES + FT_V_BYTES);
+                    const int row_k = row0 + t * FT_BK;
+                    ptx::tma_load_2d(sK + stage * FT_K_BYTES, &tmK, kv_full(stage), D + head * FT_HD, row_k);
+                    ptx::tma_load_2d(sK + stage * FT_K_BYTES + FT_BK * 128, &tmK, kv_full(stage), D + head * FT_HD + 16, row_k);
+                    ptx::tma_load_2d(sV + stage * FT_V_BYTES, &tmV, kv_full(stage), item * WT_VLD + t * FT_BK, head * FT_HD);
+                }
+                if (++stage == WT_STAGES) { stage = 0; phase ^= 1u; }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================================================== MMA issuer
+        auto idesc = [](int n) { return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(FT_BQ >> 4) << 24); };
+        const uint64_t desc_hi = (2ull << 61) | (1ull << 46) | ((uint64_t)(1024 >> 4) << 32);
+        auto desc = [&](uint32_t addr) { return desc_hi | (uint64_t)((addr >> 4) & 0x3FFF); };
+        ptx::mbar_wait(r_full, 0);
+        auto issue_qk = [&](int t) {
+            const int stage = t % WT_STAGES, b = t & 1;
+            const int n = t == WT_NT - 1 ? 16 : 64;
+            ptx::mbar_wait(kv_full(stage), (uint32_t)((t / WT_STAGES) & 1));
+#pragma unroll
+            for (int grp = 0; grp < 2; ++grp) {
+                const int gb = grp * 2 + b;
+                ptx::mbar_wait(s_empty(gb), (uint32_t)(((t >> 1) & 1) ^ 1));
+                ptx::tc_fence_after();
+                if (ptx::elect_one()) {
+                    const uint32_t q = sQ + grp * 2 * FT_BQ * 128;
+                    const uint64_t a0 = desc(q), a1 = desc(q + FT_BQ * 128);
+                    const uint64_t b0 = desc(sK + stage * FT_K_BYTES), b1 = desc(sK + stage * FT_K_BYTES + FT_BK * 128);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) ptx::umma_f16(tS(gb), a0 + 2u * k, b0 + 2u * k, idesc(n), k != 0 ? 1u : 0u);
+                    ptx::umma_f16(tS(gb), a1 + 6u, b1 + 6u, idesc(n), 1u);
+                    ptx::umma_commit(s_full(gb));
+                }
+                __syncwarp();
+            }
+        };
+        auto issue_pv = [&](int t) {
+            const int stage = t % WT_STAGES, b = t & 1;
+            const int ksteps = t == WT_NT - 1 ? 1 : 4;
+#pragma unroll
+            for (int grp = 0; grp < 2; ++grp) {
+                const int gb = grp * 2 + b;
+                ptx::mbar_wait(p_full(gb), (uint32_t)((t >> 1) & 1));
+                ptx::tc_fence_after();
+                if (ptx::elect_one()) {
+                    const uint64_t a0 = desc(sP + gb * WT_P_BYTES), b0 = desc(sV + stage * FT_V_BYTES);
+                    for (int k = 0; k < ksteps; ++k) ptx::umma_f16(tO(grp), a0 + 2u * k, b0 + 2u * k, idesc(FT_HD), (t | k) != 0 ? 1u : 0u);
+                    ptx::umma_commit(o_full(gb));
+                    if (grp == 1) ptx::umma_commit(kv_empty(stage));
+                }
+                __syncwarp();
+            }
+        };
+        int it = 0;
+        for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++it) {
+            ptx::mbar_wait(q_full, (uint32_t)(it & 1));
+            // G = Q Rcat^T into the O columns of each group, once the previous pair's output has been read out of them
+            ptx::mbar_wait(o_read(0), (uint32_t)((it & 1) ^ 1));
+            ptx::mbar_wait(o_read(1), (uint32_t)((it & 1) ^ 1));
+            ptx::tc_fence_after();
+            if (ptx::elect_one()) {
+#pragma unroll
+                for (int grp = 0; grp < 2; ++grp) {
+                    const uint32_t q = sQ + grp * 2 * FT_BQ * 128;
+                    const uint64_t a0 = desc(q), a1 = desc(q + FT_BQ * 128), b0 = desc(sR), b1 = desc(sR + 64 * 128);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) ptx::umma_f16(tO(grp), a0 + 2u * k, b0 + 2u * k, idesc(64), k != 0 ? 1u : 0u);
+                    ptx::umma_f16(tO(grp), a1 + 6u, b1 + 6u, idesc(64), 1u);
+                    ptx::umma_commit(g_full(grp));
+                }
+            }
+            __syncwarp();
+            issue_qk(0);
+            for (int t = 0; t < WT_NT; ++t) {
+                if (t + 1 < WT_NT) issue_qk(t + 1);
+                if (t + 1 == WT_NT - 1) {  // the last Q K^T of this pair has been issued: Q may be overwritten once it completes
+                    if (ptx::elect_one()) ptx::umma_commit(q_empty);
+                    __syncwarp();
+                }
+                issue_pv(t);
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================================================== softmax / output: one query row per thread
+        const int grp = (warp - 4) >> 2, quad = warp & 3, r = quad * 32 + lane;
+        const int qi = grp * FT_BQ + r;                 // query index inside the window (rows >= 196: next window, not stored)
+        const int qc = qi < WT_S ? qi : WT_S - 1;
+        const int qh = qc / WT_G, qw = qc - qh * WT_G;
+        const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
+        const float sl2 = scale * FT_L2E;
+        int it = 0;
+        for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++it) {
+        const int item = w / heads, head = w - item * heads;
+        const int row0 = item * WT_S;
+        float bh[WT_G], bw[WT_G];
+        {
+            // this thread's G row: stash it in shared memory (aliasing the group's two P buffers, 256 B per row), then
+            // gather the 14 + 14 values this query needs
+            ptx::mbar_wait(g_full(grp), (uint32_t)(it & 1));
+            ptx::tc_fence_after();
+            uint32_t g0[32], g1[32];
+            ptx::tmem_ld32(tO(grp) + lane_off, g0);
+            ptx::tmem_ld32(tO(grp) + lane_off + 32u, g1);
+            ptx::tmem_ld_wait();
+            ptx::tc_fence_before();
+            float* gs = reinterpret_cast<float*>(smem_gen + (sP - smem_base) + grp * 2 * WT_P_BYTES) + r * 64;
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+                *reinterpret_cast<uint4*>(gs + i) = make_uint4(g0[i], g0[i + 1], g0[i + 2], g0[i + 3]);
+                *reinterpret_cast<uint4*>(gs + 32 + i) = make_uint4(g1[i], g1[i + 1], g1[i + 2], g1[i + 3]);
+            }
+            __syncwarp();
+#pragma unroll
+            for (int k = 0; k < WT_G; ++k) {
+                bh[k] = gs[qh + WT_G - 1 - k] * FT_L2E;
+                bw[k] = gs[32 + qw + WT_G - 1 - k] * FT_L2E;
+            }
+            ptx::named_bar_sync(1 + grp, 128);  // every row of the group is read before the first P row is written
+        }
+        float m_ref = -INFINITY, l_run = 0.f;
+        const uint32_t p_row = (uint32_t)r * 128u;
+        const uint32_t sw = (uint32_t)(r & 7);
+#pragma unroll
+        for (int t = 0; t < WT_NT; ++t) {
+            const int gb = grp * 2 + (t & 1);
+            constexpr int NC_FULL = 64;
+            const int ncol = t == WT_NT - 1 ? 16 : NC_FULL;
+            ptx::mbar_wait(s_full(gb), (uint32_t)((t >> 1) & 1));
+            ptx::tc_fence_after();
+            uint32_t v[64];
+            if (t == WT_NT - 1) {
+                uint32_t d[16];
+                ptx::tmem_ld16(tS(gb) + lane_off, d);
+                ptx::tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = d[j];
+            } else {
+                uint32_t a[32], c[32];
+                ptx::tmem_ld32(tS(gb) + lane_off, a);
+                ptx::tmem_ld32(tS(gb) + lane_off + 32u, c);
+                ptx::tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) { v[j] = a[j]; v[32 + j] = c[j]; }
+            }
+            ptx::tc_fence_before();
+            ptx::mbar_arrive(s_empty(gb));
+            float mx = -INFINITY;
+#pragma unroll
+            for (int j = 0; j < 64; ++j) {
+                const int k = t * 64 + j;
+                if (j < ncol && k < WT_S) {
+                    const float a = fmaf(__uint_as_float(v[j]), sl2, bh[k / WT_G] + bw[k % WT_G]);
+                    v[j] = __float_as_uint(a);
+                    mx = fmaxf(mx, a);
+                }
+            }
+            const bool move = mx > m_ref + 8.0f;
+            if (__any_sync(0xffffffffu, move) && t > 0) {
+                const float alpha = move ? ptx::ex2(m_ref - mx) : 1.0f;
+                ptx::mbar_wait(o_full(grp * 2 + ((t - 1) & 1)), (uint32_t)(((t - 1) >> 1) & 1));
+                ptx::tc_fence_after();
+#pragma unroll 1
+                for (int c0 = 0; c0 < FT_HD; c0 += 16) {
+                    uint32_t d[16];
+                    ptx::tmem_ld16(tO(grp) + lane_off + (uint32_t)c0, d);
+                    ptx::tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) d[i] = __float_as_uint(__uint_as_float(d[i]) * alpha);
+                    ptx::tmem_st16(tO(grp) + lane_off + (uint32_t)c0, d);
+                }
+                ptx::tmem_st_wait();
+                ptx::tc_fence_before();
+                l_run *= alpha;
+            }
+            if (move) m_ref = mx;
+            float rs = 0.f;
+            uint32_t pk[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const int k0 = t * 64 + 2 * j;
+                float p0 = 0.f, p1 = 0.f;
+                if (2 * j < ncol && k0 < WT_S) p0 = ptx::ex2(__uint_as_float(v[2 * j]) - m_ref);
+                if (2 * j + 1 < ncol && k0 + 1 < WT_S) p1 = ptx::ex2(__uint_as_float(v[2 * j + 1]) - m_ref);
+                rs += p0 + p1;
+                pk[j] = pack_h2(p0, p1);
+            }
+            l_run += rs;
+            {
+                const uint32_t base = sP + gb * WT_P_BYTES + p_row;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    if (c * 8 < ncol) {
+                        const uint32_t addr = base + (((uint32_t)c ^ sw) << 4);
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[4 * c]), "r"(pk[4 * c + 1]),
+                                     "r"(pk[4 * c + 2]), "r"(pk[4 * c + 3]) : "memory");
+                    }
+                }
+            }
+            ptx::fence_proxy_async();
+            ptx::mbar_arrive(p_full(gb));
+        }
+        {
+            ptx::mbar_wait(o_full(grp * 2 + ((WT_NT - 1) & 1)), (uint32_t)(((WT_NT - 1) >> 1) & 1));
+            ptx::tc_fence_after();
+            const float inv = 1.0f / l_run;
+            __half* dst = out + ((long long)row0 + qi) * D + head * FT_HD;
+            auto f = [&](uint32_t u) { return __uint_as_float(u) * inv; };
+#pragma unroll 1
+            for (int c0 = 0; c0 < FT_HD; c0 += 16) {
+                uint32_t d[16];
+                ptx::tmem_ld16(tO(grp) + lane_off + (uint32_t)c0, d);
+                ptx::tmem_ld_wait();
+                if (qi < WT_S) {
+#pragma unroll
+                    for (int i = 0; i < 16; i += 8)
+                        *reinterpret_cast<uint4*>(dst + c0 + i) = make_uint4(pack_h2(f(d[i]), f(d[i + 1])), pack_h2(f(d[i + 2]), f(d[i + 3])),
+                                                                             pack_h2(f(d[i + 4]), f(d[i + 5])), pack_h2(f(d[i + 6]), f(d[i + 7])));
+                }
+            }
+            ptx::tc_fence_before();
+            ptx::mbar_arrive(o_read(grp));  // the O columns may take the next pair's G
+        }
+        }  // work items
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    if (warp == 2) ptx::tmem_dealloc(tmem_base, 512);
+}
+
 PFN_cuTensorMapEncodeTiled_v12000 ft_encode_fn() {
     static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
     if (!fn) {
@@ -385,6 +746,41 @@ int op_attention_tc(const __half* qkv, int Gb, int S, int heads, int hd, float s
     CVB_TRY(ft_tmap_2d(&tv, vt, (uint64_t)S, (uint64_t)Gb * heads * FT_HD, (uint64_t)S * 2, 64, FT_HD));
     flash_tc_kernel<FT_NG><<<dim3(S / (FT_NG * FT_BQ), Gb * heads), FtCfg<FT_NG>::THREADS, FtCfg<FT_NG>::SMEM, stream>>>(tq, tk, tv, bias_h, bias_w, S, heads,
                                                                                                                scale, out);
+    cvb_note_launches(2);
+    CVB_CUDA(cudaGetLastError());
+    return CVB_OK;
+}
+
+// ------------------------------------------------------------------------------------------ windows: host side
+bool op_window_attention_tc_supported(int S, int hd, int gh, int gw) { return hd == FT_HD && S == WT_S && gh == WT_G && gw == WT_G; }
+
+size_t op_window_attention_tc_workspace_bytes(int n_items, int heads) {
+    return align_up((size_t)heads * FT_HD * n_items * WT_VLD * 2, 1024) + 1024;
+}
+
+int op_window_attention_tc(const __half* qkv, int n_items, int heads, int hd, float scale, const __half* relcat, __half* out,
+                           void* workspace, size_t ws_bytes, cudaStream_t stream) {
+    CVB_CHECK(qkv && out && relcat && workspace, CVB_EARG, "window_attention_tc: null operand");
+    CVB_CHECK(hd == FT_HD && n_items > 0 && heads > 0, CVB_ESHAPE, "window_attention_tc: needs head dim 80");
+    CVB_CHECK(ws_bytes >= op_window_attention_tc_workspace_bytes(n_items, heads), CVB_EWORKSPACE, "window_attention_tc: workspace too small");
+    CVB_CHECK(((uintptr_t)workspace & 1023) == 0, CVB_EARG, "window_attention_tc: workspace must be 1024-byte aligned");
+    const int D = heads * hd;
+    __half* vt = reinterpret_cast<__half*>(workspace);
+    static bool configured = false;
+    if (!configured) {
+        CVB_CUDA(cudaFuncSetAttribute(window_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WT_SMEM));
+        configured = true;
+    }
+    v_transpose_win_kernel<<<dim3(n_items, heads), 256, 0, stream>>>(qkv, heads, n_items, vt);
+    CUtensorMap tq, tk, tv, tr;
+    const uint64_t rows = (uint64_t)n_items * WT_S;
+    CVB_TRY(ft_tmap_2d(&tq, qkv, (uint64_t)3 * D, rows, (uint64_t)3 * D * 2, 64, FT_BQ));
+    CVB_TRY(ft_tmap_2d(&tk, qkv, (uint64_t)3 * D, rows, (uint64_t)3 * D * 2, 64, FT_BK));
+    CVB_TRY(ft_tmap_2d(&tv, vt, (uint64_t)n_items * WT_VLD, (uint64_t)heads * FT_HD, (uint64_t)n_items * WT_VLD * 2, 64, FT_HD));
+    CVB_TRY(ft_tmap_2d(&tr, relcat, (uint64_t)FT_HD, 64, (uint64_t)FT_HD * 2, 64, 64));
+    const int n_work = n_items * heads;
+    const int grid = n_work < cvb_num_sms() ? n_work : cvb_num_sms();
+    window_tc_kernel<<<grid, WT_THREADS, WT_SMEM, stream>>>(tq, tk, tv, tr, heads, n_items, scale, out);
     cvb_note_launches(2);
     CVB_CUDA(cudaGetLastError());
     return CVB_OK;

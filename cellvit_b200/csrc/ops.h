@@ -75,3 +75,10 @@ bool op_attention_tc_supported(int S, int hd, const __half* Rh, int gh, int gw);
 size_t op_attention_tc_workspace_bytes(int Gb, int S, int heads);
 int op_attention_tc(const __half* qkv, int Gb, int S, int heads, int hd, float scale, const __half* Rh, const __half* Rw, int gh,
                     int gw, __half* out, void* workspace, size_t ws_bytes, cudaStream_t stream);
+
+// tcgen05 attention for the 14 x 14 SAM windows (196 tokens, head dim 80). qkv fp16 [n_items*196, 3*D] in window order,
+// relcat fp16 [64, 80] = rel_h table rows at 0.., rel_w table rows at 32.. (packing.py), out fp16 [n_items*196, D].
+bool op_window_attention_tc_supported(int S, int hd, int gh, int gw);
+size_t op_window_attention_tc_workspace_bytes(int n_items, int heads);
+int op_window_attention_tc(const __half* qkv, int n_items, int heads, int hd, float scale, const __half* relcat, __half* out,
+                           void* workspace, size_t ws_bytes, cudaStream_t stream);

@@ -105,6 +105,11 @@ def pack_static(sd, cfg):
         if sam and i not in cfg["global_idx"]:
             P[f"{p}.relh"] = rel_table(sd[f"{r}.attn.rel_pos_h"], cfg["window"])
             P[f"{p}.relw"] = rel_table(sd[f"{r}.attn.rel_pos_w"], cfg["window"])
+            # both tables as one K-major [64, hd] B operand for the tcgen05 window attention: rows 0.. = rel_h, rows 32.. = rel_w
+            cat = torch.zeros(64, P[f"{p}.relh"].shape[1], dtype=P[f"{p}.relh"].dtype, device=P[f"{p}.relh"].device)
+            cat[:P[f"{p}.relh"].shape[0]] = P[f"{p}.relh"]
+            cat[32:32 + P[f"{p}.relw"].shape[0]] = P[f"{p}.relw"]
+            P[f"{p}.relcat"] = cat.contiguous()
     if sam:
         P["neck.0.w"] = _h(sd["encoder.neck.0.weight"].reshape(256, D))
         P["neck.1.w"], P["neck.1.b"] = _f(sd["encoder.neck.1.weight"]), _f(sd["encoder.neck.1.bias"])

@@ -173,12 +173,41 @@ def test_forward_sam_h_1024_attention_tc_vs_mma_sync():
     m = m.cuda().eval()
     x = torch.from_numpy(synth.synthetic_tiles(1, 1024, seed=5)).cuda()
     outs = []
-    for on in (1, 0):
-        L.lib().cvb_set_attention_tc(on)
+    for mode in (1, 3, 0):  # global blocks on tcgen05 (default) / global + windows on tcgen05 / everything on mma.sync
+        L.lib().cvb_set_attention_tc(mode)
         with torch.no_grad():
             outs.append({k: v.clone() for k, v in m(x, retrieve_tokens=True).items()})
     L.lib().cvb_set_attention_tc(1)
-    for k in ("nuclei_binary_map", "hv_map", "nuclei_type_map", "tokens"):
-        err = (outs[0][k] - outs[1][k]).abs().max().item()
-        tol = 2e-4 if k != "tokens" else 1e-3 * max(1.0, outs[1][k].abs().max().item())  # tokens are O(10): relative bar
-        assert err <= tol, (k, err)
+    for o in outs[:2]:
+        for k in ("nuclei_binary_map", "hv_map", "nuclei_type_map", "tokens"):
+            err = (o[k] - outs[2][k]).abs().max().item()
+            tol = 2e-4 if k != "tokens" else 1e-3 * max(1.0, outs[2][k].abs().max().item())  # tokens are O(10): relative bar
+            assert err <= tol, (k, err)
+
+
+@pytest.mark.parametrize("n_items,heads", [(3, 2), (25, 4)])
+def test_window_attention_tc_matches_torch(n_items, heads):
+    """tcgen05 window attention (flash_tc.cu): 14 x 14 windows, head dim 80, rel-pos bias computed in the kernel."""
+    g = torch.Generator(device="cuda").manual_seed(13)
+    gh = gw = 14
+    hd, S = 80, 196
+    D = heads * hd
+    qkv = (torch.randn(n_items * S, 3 * D, device="cuda", generator=g)).half()
+    Rh = (torch.randn(2 * gh - 1, hd, device="cuda", generator=g) * 0.2).half()
+    Rw = (torch.randn(2 * gw - 1, hd, device="cuda", generator=g) * 0.2).half()
+    relcat = torch.zeros(64, hd, device="cuda", dtype=torch.half)
+    relcat[:27] = Rh
+    relcat[32:59] = Rw
+    out = torch.full((n_items * S, D), float("nan"), device="cuda", dtype=torch.half)
+    need = C.c_size_t()
+    L.check(L.lib().cvb_op_window_attention_tc_workspace_bytes(n_items, heads, C.byref(need)), "ws")
+    ws = torch.empty(need.value + 1024, dtype=torch.uint8, device="cuda")
+    off = (-ws.data_ptr()) % 1024
+    scale = hd ** -0.5
+    L.check(L.lib().cvb_op_window_attention_tc(L.ptr(qkv), n_items, heads, hd, C.c_float(scale), L.ptr(relcat), L.ptr(out),
+                                               C.c_void_p(ws.data_ptr() + off), C.c_size_t(need.value), L.stream_ptr()), "window_tc")
+    torch.cuda.synchronize()
+    ref = _ref_attention(qkv, n_items, S, heads, hd, scale, Rh.float(), Rw.float(), gh, gw)
+    assert torch.isfinite(out.float()).all()
+    err = (out.float() - ref).abs().max().item()
+    assert err < 4e-3, err
