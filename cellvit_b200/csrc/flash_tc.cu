@@ -29,12 +29,15 @@ namespace {
 
 constexpr int FT_BQ = 128, FT_BK = 64, FT_HD = 80, FT_STAGES = 3;
 constexpr uint32_t FT_K_BYTES = 2 * FT_BK * 128;          // two boxes of 64 rows x 128 B
-constexpr uint32_t FT_V_BYTES = FT_HD * 128;              // 80 rows (hd) x 64 keys
+constexpr uint32_t FT_V_BYTES = FT_HD * 128;              // 80 rows (hd) x 64 keys (window kernel)
+constexpr int FT_VR = 96;                                 // global kernel: V^T rows per head = 80 + a row of ones (row sums of P
+                                                          // come out of the P V MMA as output column 80) + 15 zero rows
+constexpr uint32_t FTG_V_BYTES = FT_VR * 128;
 constexpr int FT_NG = 2;                                  // query groups (of 128 rows) per CTA
 constexpr float FT_L2E = 1.4426950408889634f;
 
 // ------------------------------------------------------------------------------------------ V^T
-// v rows [Gb*S, 3*D] (columns 2*D + head*hd + d) -> vt [(g*heads + head)*hd + d][S]
+// v rows [Gb*S, 3*D] (columns 2*D + head*hd + d) -> vt [(g*heads + head)*96 + d][S]; row 80 = ones, rows 81..95 = zeros
 __global__ void __launch_bounds__(256)
 v_transpose_kernel(const __half* __restrict__ qkv, int S, int heads, __half* __restrict__ vt) {
     __shared__ __half tile[64][FT_HD + 2];
@@ -49,10 +52,12 @@ v_transpose_kernel(const __half* __restrict__ qkv, int S, int heads, __half* __r
         for (int j = 0; j < 8; ++j) tile[r][c * 8 + j] = h[j];
     }
     __syncthreads();
-    __half* dst = vt + (long long)gh * FT_HD * S + k0;
-    for (int i = threadIdx.x; i < FT_HD * 32; i += 256) {
+    __half* dst = vt + (long long)gh * FT_VR * S + k0;
+    for (int i = threadIdx.x; i < FT_VR * 32; i += 256) {
         const int d = i >> 5, kp = i & 31;
-        const __half2 v = __halves2half2(tile[2 * kp][d], tile[2 * kp + 1][d]);
+        __half2 v = __floats2half2_rn(0.f, 0.f);
+        if (d < FT_HD) v = __halves2half2(tile[2 * kp][d], tile[2 * kp + 1][d]);
+        else if (d == FT_HD) v = __floats2half2_rn(1.f, 1.f);
         *reinterpret_cast<__half2*>(dst + (long long)d * S + 2 * kp) = v;
     }
 }
@@ -65,7 +70,7 @@ struct FtCfg {
     static constexpr int THREADS = 128 + NG * 128;
     static constexpr uint32_t Q_BYTES = NG * 2 * FT_BQ * 128;
     static constexpr uint32_t P_BYTES = FT_BQ * 128;
-    static constexpr uint32_t SMEM = 1024 + Q_BYTES + FT_STAGES * (FT_K_BYTES + FT_V_BYTES) + NG * 2 * P_BYTES + 512;
+    static constexpr uint32_t SMEM = 1024 + Q_BYTES + FT_STAGES * (FT_K_BYTES + FTG_V_BYTES) + NG * 2 * P_BYTES + 512;
 };
 
 template <int NG>
@@ -86,7 +91,7 @@ flash_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const uint32_t sQ = smem_base;
     const uint32_t sK = sQ + Cfg::Q_BYTES;
     const uint32_t sV = sK + FT_STAGES * FT_K_BYTES;
-    const uint32_t sP = sV + FT_STAGES * FT_V_BYTES;
+    const uint32_t sP = sV + FT_STAGES * FTG_V_BYTES;
     const uint32_t bar = sP + NG * 2 * Cfg::P_BYTES;
     // barriers (8 B each); per-group ones are indexed by gb = group * 2 + buffer
     const uint32_t q_full = bar;
@@ -142,11 +147,11 @@ flash_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         for (int t = 0; t < n_t; ++t) {
             ptx::mbar_wait(kv_empty(stage), phase ^ 1u);
             if (ptx::elect_one()) {
-                ptx::mbar_expect_tx(kv_full(stage), FT_K_BYTES + FT_V_BYTES);
+                ptx::mbar_expect_tx(kv_full(stage), FT_K_BYTES + FTG_V_BYTES);
                 const int row_k = g * S + t * FT_BK;
                 ptx::tma_load_2d(sK + stage * FT_K_BYTES, &tmK, kv_full(stage), D + head * FT_HD, row_k);
                 ptx::tma_load_2d(sK + stage * FT_K_BYTES + FT_BK * 128, &tmK, kv_full(stage), D + head * FT_HD + 16, row_k);
-                ptx::tma_load_2d(sV + stage * FT_V_BYTES, &tmV, kv_full(stage), t * FT_BK, ghd * FT_HD);
+                ptx::tma_load_2d(sV + stage * FTG_V_BYTES, &tmV, kv_full(stage), t * FT_BK, ghd * FT_VR);
             }
             if (++stage == FT_STAGES) { stage = 0; phase ^= 1u; }
         }
@@ -154,7 +159,7 @@ flash_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         // ===================================================== MMA issuer
         // instruction descriptors: D=f32, A=B=f16, both K-major; N>>3 @17, M>>4 @24
         const uint32_t idesc_qk = (1u << 4) | ((uint32_t)(FT_BK >> 3) << 17) | ((uint32_t)(FT_BQ >> 4) << 24);
-        const uint32_t idesc_pv = (1u << 4) | ((uint32_t)(FT_HD >> 3) << 17) | ((uint32_t)(FT_BQ >> 4) << 24);
+        const uint32_t idesc_pv = (1u << 4) | ((uint32_t)(FT_VR >> 3) << 17) | ((uint32_t)(FT_BQ >> 4) << 24);
         const uint64_t desc_hi = (2ull << 61) | (1ull << 46) | ((uint64_t)(1024 >> 4) << 32);  // SWIZZLE_128B, SBO 1024
         auto desc = [&](uint32_t addr) { return desc_hi | (uint64_t)((addr >> 4) & 0x3FFF); };
         ptx::mbar_wait(q_full, 0);
@@ -187,7 +192,7 @@ flash_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 ptx::mbar_wait(p_full(gb), (uint32_t)((t >> 1) & 1));
                 ptx::tc_fence_after();
                 if (ptx::elect_one()) {
-                    const uint64_t a0 = desc(sP + gb * Cfg::P_BYTES), b0 = desc(sV + stage * FT_V_BYTES);
+                    const uint64_t a0 = desc(sP + gb * Cfg::P_BYTES), b0 = desc(sV + stage * FTG_V_BYTES);
 #pragma unroll
                     for (int k = 0; k < 4; ++k) ptx::umma_f16(tO(grp), a0 + 2u * k, b0 + 2u * k, idesc_pv, (t | k) != 0 ? 1u : 0u);
                     ptx::umma_commit(o_full(gb));
@@ -218,14 +223,16 @@ flash_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             }
         }
         const __half* bh_row = bias_h + row * 64;
-        float m_ref = -INFINITY, l_run = 0.f;
-        float bh_next = __half2float(__ldg(bh_row));
+        float m_ref = -INFINITY;
+        // the per-tile rel_h scalar is fetched one tile ahead and left untouched (raw fp16) until the next iteration, so the
+        // L2 round trip never sits on the critical path (converting it right away stalled every tile on the load)
+        unsigned short bh_raw = __ldg(reinterpret_cast<const unsigned short*>(bh_row));
         const uint32_t p_row = (uint32_t)r * 128u;
         const uint32_t sw = (uint32_t)(r & 7);
         for (int t = 0; t < n_t; ++t) {
             const int gb = grp * 2 + (t & 1);
-            const float bh = bh_next;
-            if (t + 1 < n_t) bh_next = __half2float(__ldg(bh_row + t + 1));
+            const float bh = __half2float(__ushort_as_half(bh_raw));
+            if (t + 1 < n_t) bh_raw = __ldg(reinterpret_cast<const unsigned short*>(bh_row) + t + 1);
             ptx::mbar_wait(s_full(gb), (uint32_t)((t >> 1) & 1));
             ptx::tc_fence_after();
             uint32_t v0[32], v1[32];
@@ -255,7 +262,7 @@ flash_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 ptx::mbar_wait(o_full(grp * 2 + ((t - 1) & 1)), (uint32_t)(((t - 1) >> 1) & 1));
                 ptx::tc_fence_after();
 #pragma unroll 1
-                for (int c0 = 0; c0 < FT_HD; c0 += 16) {
+                for (int c0 = 0; c0 < FT_VR; c0 += 16) {  // 80 output columns + the row-sum column
                     uint32_t d[16];
                     ptx::tmem_ld16(tO(grp) + lane_off + (uint32_t)c0, d);
                     ptx::tmem_ld_wait();
@@ -265,21 +272,18 @@ flash_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 }
                 ptx::tmem_st_wait();
                 ptx::tc_fence_before();
-                l_run *= alpha;
             }
             if (move) m_ref = cand;
             const float mref = m_ref - bh;
-            float rs = 0.f;
+            // P = 2^(t - m) straight in fp16 pairs (one MUFU op per two weights; they are rounded to fp16 for the MMA anyway,
+            // and the fp16 rounding of the exponent only matters for weights that are negligible). The row sum is not
+            // accumulated here: the ones row of V^T makes it output column 80 of P V, from exactly these rounded weights.
             uint32_t pk[32];
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
-                const float p0 = ptx::ex2(__uint_as_float(v0[2 * j]) - mref), p1 = ptx::ex2(__uint_as_float(v0[2 * j + 1]) - mref);
-                const float p2 = ptx::ex2(__uint_as_float(v1[2 * j]) - mref), p3 = ptx::ex2(__uint_as_float(v1[2 * j + 1]) - mref);
-                rs += (p0 + p1) + (p2 + p3);
-                pk[j] = pack_h2(p0, p1);
-                pk[16 + j] = pack_h2(p2, p3);
+                pk[j] = ptx::ex2_f16x2(pack_h2(__uint_as_float(v0[2 * j]) - mref, __uint_as_float(v0[2 * j + 1]) - mref));
+                pk[16 + j] = ptx::ex2_f16x2(pack_h2(__uint_as_float(v1[2 * j]) - mref, __uint_as_float(v1[2 * j + 1]) - mref));
             }
-            l_run += rs;
             // P row (64 keys fp16 = 8 chunks of 16 B) into the K-major SWIZZLE_128B A operand: chunk c -> c ^ (row & 7)
             {
                 const uint32_t base = sP + gb * Cfg::P_BYTES + p_row;
@@ -296,7 +300,13 @@ flash_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         {   // all key tiles accumulated: O / l
             ptx::mbar_wait(o_full(grp * 2 + ((n_t - 1) & 1)), (uint32_t)(((n_t - 1) >> 1) & 1));
             ptx::tc_fence_after();
-            const float inv = 1.0f / l_run;
+            float inv;
+            {
+                uint32_t d[16];
+                ptx::tmem_ld16(tO(grp) + lane_off + (uint32_t)FT_HD, d);  // column 80 = sum of the row's weights
+                ptx::tmem_ld_wait();
+                inv = 1.0f / __uint_as_float(d[0]);
+            }
             __half* dst = out + ((long long)g * S + q0 + grp * FT_BQ + r) * D + head * FT_HD;
             auto f = [&](uint32_t u) { return __uint_as_float(u) * inv; };
 #pragma unroll 1
@@ -712,7 +722,7 @@ bool op_attention_tc_supported(int S, int hd, const __half* Rh, int gh, int gw) 
 }
 
 size_t op_attention_tc_workspace_bytes(int Gb, int S, int heads) {
-    const size_t vt = align_up((size_t)Gb * heads * FT_HD * S * 2, 1024);
+    const size_t vt = align_up((size_t)Gb * heads * FT_VR * S * 2, 1024);
     const size_t bias = align_up((size_t)Gb * heads * S * 64 * 2, 1024);
     return vt + 2 * bias + 1024;
 }
@@ -727,7 +737,7 @@ int op_attention_tc(const __half* qkv, int Gb, int S, int heads, int hd, float s
     const int D = heads * hd;
     uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
     __half* vt = reinterpret_cast<__half*>(ws);
-    const size_t vt_b = align_up((size_t)Gb * heads * FT_HD * S * 2, 1024);
+    const size_t vt_b = align_up((size_t)Gb * heads * FT_VR * S * 2, 1024);
     const size_t bias_b = align_up((size_t)Gb * heads * S * 64 * 2, 1024);
     __half* bias_h = reinterpret_cast<__half*>(ws + vt_b);
     __half* bias_w = reinterpret_cast<__half*>(ws + vt_b + bias_b);
@@ -743,7 +753,7 @@ int op_attention_tc(const __half* qkv, int Gb, int S, int heads, int hd, float s
     CUtensorMap tq, tk, tv;
     CVB_TRY(ft_tmap_2d(&tq, qkv, (uint64_t)3 * D, (uint64_t)Gb * S, (uint64_t)3 * D * 2, 64, FT_BQ));
     CVB_TRY(ft_tmap_2d(&tk, qkv, (uint64_t)3 * D, (uint64_t)Gb * S, (uint64_t)3 * D * 2, 64, FT_BK));
-    CVB_TRY(ft_tmap_2d(&tv, vt, (uint64_t)S, (uint64_t)Gb * heads * FT_HD, (uint64_t)S * 2, 64, FT_HD));
+    CVB_TRY(ft_tmap_2d(&tv, vt, (uint64_t)S, (uint64_t)Gb * heads * FT_VR, (uint64_t)S * 2, 64, FT_VR));
     flash_tc_kernel<FT_NG><<<dim3(S / (FT_NG * FT_BQ), Gb * heads), FtCfg<FT_NG>::THREADS, FtCfg<FT_NG>::SMEM, stream>>>(tq, tk, tv, bias_h, bias_w, S, heads,
                                                                                                                scale, out);
     cvb_note_launches(2);
