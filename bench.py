@@ -189,7 +189,10 @@ def run_gpu(args):
         # finished (the dependency of the real pipeline), so it overlaps the forward of batch k+1 -- the same
         # structure as CellSegmentationInference.process_tiles
         with torch.no_grad():
-            model(x_dev, retrieve_tokens=True)
+            if args.graphs:
+                model.forward_graphed(x_dev, retrieve_tokens=True, slot=0)
+            else:
+                model(x_dev, retrieve_tokens=True)
         fwd_done = torch.cuda.Event()
         fwd_done.record(main)
         s_post.wait_event(fwd_done)
@@ -212,7 +215,7 @@ def run_gpu(args):
     def run_e2e(n_batches):
         # public API: pinned-host tiles in, per-tile instance dicts out (H2D, forward, softmax, device post-processing,
         # D2H of label maps + tables, host contours/dicts; host work of batch k overlaps device work of batch k+1)
-        res = inf.process_tiles([tiles_host] * n_batches, magnification=40, head_override=override)
+        res = inf.process_tiles([tiles_host] * n_batches, magnification=40, head_override=override, use_graphs=bool(args.graphs))
         return sum(len(d) for d in res[-1])
 
     def sync_all():
@@ -221,6 +224,11 @@ def run_gpu(args):
             dist.barrier()
             torch.cuda.synchronize()
 
+    # launches of one forward (a graph replay does not pass through the launch counter)
+    lib.cvb_launch_count(1)
+    with torch.no_grad():
+        model(x_dev, retrieve_tokens=True)
+    fwd_launches = int(lib.cvb_launch_count(1))
     sampler = ClockSampler(local) if rank == 0 else None
     for _ in range(Wm):
         step_device()
@@ -234,7 +242,7 @@ def run_gpu(args):
     main.wait_stream(s_post)  # the timed region ends when the last batch's post-processing has finished
     e1.record()
     sync_all()
-    launches = int(lib.cvb_launch_count(1))
+    launches = int(lib.cvb_launch_count(1)) + (K * fwd_launches if args.graphs else 0)
     clocks = sampler.stop() if sampler else None
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
     if world > 1:
@@ -298,6 +306,7 @@ def run_gpu(args):
             "config": {"workload": f"CellViT-{ARCH} inference, batch={B} synthetic {TILE}x{TILE} tiles per GPU per step, on-GPU HV watershed "
                                    f"post-processing on injected synthetic-nuclei head maps ({N_NUCLEI} nuclei/tile); random-init weights",
                        "l2": "per-step working set (1.4 GB fp16 weights + >10 GB activations) exceeds the 126 MB L2; no explicit flush",
+                       "forward_launch": "CUDA graph replay" if args.graphs else "eager",
                        "parallelism": f"tiles sharded over {world} GPU(s), NCCL weight broadcast" + (", per-step all-gather of instance tables" if world > 1 else "")},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "tiles/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke,
@@ -313,6 +322,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--graphs", type=int, default=1, help="1 (default): the forward is replayed from a CUDA graph, as in the product pipeline; 0: eager launches")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling / quick iteration runs)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup

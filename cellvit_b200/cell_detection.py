@@ -124,7 +124,8 @@ class CellSegmentationInference:
         return (x - mean) / std
 
     @torch.no_grad()
-    def _pipeline(self, items, magnification: int = 40, head_override=None, with_tokens: bool = False, host_threads: int = 0):
+    def _pipeline(self, items, magnification: int = 40, head_override=None, with_tokens: bool = False, host_threads: int = 0,
+                  use_graphs: bool = True):
         """Generator over ``items`` = iterable of (batch [B,3,H,W] pinned-host or device tensor, payload); yields
         ``(payload, dicts, cell_tokens)`` per batch, in order, where ``dicts`` are the per-tile instance dicts and
         ``cell_tokens`` (``with_tokens``) one float32 array [n_cells, D] per tile, rows aligned with the dict order.
@@ -133,7 +134,9 @@ class CellSegmentationInference:
         device post-processing (+ cell-token pooling) + D2H of batch k (post stream) run beside the forward of batch
         k+1 (the caller's stream); the host part (dict building, post_proc_cellvit.py:96-151) of batch k overlaps
         them too. ``head_override`` (dict, or callable(payload) -> dict) replaces head maps before post-processing
-        (bench/test hook: random-init networks emit constant maps)."""
+        (bench/test hook: random-init networks emit constant maps). ``use_graphs``: the forward of each pipeline slot
+        is replayed from a CUDA graph (``CellViT.graph_slot``) whose static input buffer the H2D copy writes directly; a
+        slot's static outputs have been consumed (its batch collected) before the slot is replayed."""
         from concurrent.futures import ThreadPoolExecutor
         from .post_proc_cellvit import DetectionCellPostProcessor
         proc = DetectionCellPostProcessor(nr_types=self.model.num_nuclei_classes, magnification=magnification, gt=False)
@@ -149,20 +152,30 @@ class CellSegmentationInference:
             in_buf, consumed, keep = [None, None], [None, None], [None, None]
 
             def stage(k, patches):
-                """H2D of batch k into device slot k & 1 on the copy stream; returns (device tensor, ready event)."""
-                if patches.is_cuda:
-                    return patches, None
+                """Input of batch k into the device buffer of slot k & 1 (H2D on the copy stream); returns
+                (device tensor, ready event, graph slot or None)."""
                 slot = k & 1
-                if in_buf[slot] is None or in_buf[slot].shape != patches.shape or in_buf[slot].dtype != patches.dtype:
-                    in_buf[slot] = torch.empty(patches.shape, dtype=patches.dtype, device=dev)
-                    consumed[slot] = torch.cuda.Event()
-                    consumed[slot].record(main)     # the fresh block may still be in use by earlier work on `main`
-                s_in.wait_event(consumed[slot])     # the forward that last read this slot has finished
+                gs = None
+                if use_graphs:
+                    gs = self.model.graph_slot(tuple(patches.shape), True, slot, dev)
+                    buf = gs[1]
+                    if consumed[slot] is None:
+                        consumed[slot] = torch.cuda.Event()
+                        consumed[slot].record(main)
+                elif patches.is_cuda:
+                    return patches, None, None
+                else:
+                    if in_buf[slot] is None or in_buf[slot].shape != patches.shape or in_buf[slot].dtype != patches.dtype:
+                        in_buf[slot] = torch.empty(patches.shape, dtype=patches.dtype, device=dev)
+                        consumed[slot] = torch.cuda.Event()
+                        consumed[slot].record(main)  # the fresh block may still be in use by earlier work on `main`
+                    buf = in_buf[slot]
+                s_in.wait_event(consumed[slot])      # the forward that last read this slot has finished
                 with torch.cuda.stream(s_in):
-                    in_buf[slot].copy_(patches, non_blocking=True)
+                    buf.copy_(patches, non_blocking=True)
                     ready = torch.cuda.Event()
                     ready.record(s_in)
-                return in_buf[slot], ready
+                return buf, ready, gs
 
             def finish(slot):
                 payload = keep[slot][0]
@@ -176,11 +189,15 @@ class CellSegmentationInference:
             staged = (stage(0, nxt[0]), nxt[1]) if nxt is not None else None
             k, pending = 0, None
             while staged is not None:
-                (x, ready), payload = staged
+                (x, ready, gs), payload = staged
                 slot = k & 1
                 if ready is not None:
                     main.wait_event(ready)
-                predictions = self.model.forward(x, retrieve_tokens=True)
+                if gs is not None:
+                    gs[0].replay()
+                    predictions = dict(gs[2])
+                else:
+                    predictions = self.model.forward(x, retrieve_tokens=True)
                 fwd_done = torch.cuda.Event()
                 fwd_done.record(main)
                 consumed[slot] = fwd_done
@@ -205,10 +222,10 @@ class CellSegmentationInference:
             main.wait_stream(s_post)
 
     def process_tiles(self, batches: Iterable[torch.Tensor], magnification: int = 40, head_override: dict = None,
-                      host_threads: int = 0) -> List[List[dict]]:
+                      host_threads: int = 0, use_graphs: bool = True) -> List[List[dict]]:
         """Hot loop of process_wsi (:306-323) over already normalised batches [B,3,H,W] (pinned host or device
         tensors), see ``_pipeline``. Returns one list of per-tile instance dicts per batch."""
-        return [d for _, d, _ in self._pipeline(((b, None) for b in batches), magnification, head_override, False, host_threads)]
+        return [d for _, d, _ in self._pipeline(((b, None) for b in batches), magnification, head_override, False, host_threads, use_graphs)]
 
     # ------------------------------------------------------------------ WSI level (SURVEY.md section 8f, rows N2-N4)
     def process_wsi(self, wsi, subdir_name: str = None, patch_size: int = 1024, overlap: int = 64, batch_size: int = 8,

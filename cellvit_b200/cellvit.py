@@ -88,6 +88,7 @@ class CellViT(nn.Module):
         self._packed_key = None  # (device, param versions)
         self._size_key = None
         self._ws = None
+        self._graphs = {}        # forward_graphed: (shape, tokens, slot, device) -> (graph, static input, static outputs)
 
     # ------------------------------------------------------------------ engine plumbing
     def _cfg(self):
@@ -130,11 +131,13 @@ class CellViT(nn.Module):
             sd_dev = {k: v.to(device) for k, v in self.state_dict().items()}
             self._register(packing.pack_static(sd_dev, self._cfg()))
             self._packed_key, self._size_key = key, None
+            self._graphs = {}  # captured graphs hold the old tensors' addresses
         if self._size_key != (h, w):
             sd_dev = {k: v.to(device) for k, v in self.state_dict().items()
                       if k.startswith("encoder.pos_embed") or "rel_pos" in k or "cls_token" in k}
             self._register(packing.pack_for_size(sd_dev, self._cfg(), h, w))
             self._size_key = (h, w)
+            self._graphs = {}
 
     def __del__(self):
         try:
@@ -179,6 +182,41 @@ class CellViT(nn.Module):
         if retrieve_tokens:
             out["tokens"] = o_tok
         return out
+
+    def forward_graphed(self, x: torch.Tensor, retrieve_tokens: bool = True, slot: int = 0) -> dict:
+        """``forward`` replayed from a CUDA graph (one per input shape and ``slot``): the ~290 launches of a SAM-H forward
+        become one graph launch, which removes the 2 us of idle time at every kernel boundary. The returned tensors are
+        STATIC: the next call with the same ``slot`` overwrites them (the tile pipeline alternates two slots and has
+        consumed a slot's outputs before it is replayed). ``x`` may be a host tensor (pinned: asynchronous H2D straight
+        into the graph's input buffer)."""
+        assert x.shape[-2] % self.patch_size == 0, "Input images must be divisible by the patch size"
+        assert x.shape[-1] % self.patch_size == 0, "Input images must be divisible by the patch size"
+        dev = x.device if x.is_cuda else next(self.parameters()).device
+        if dev.type != "cuda":
+            raise RuntimeError("cellvit_b200 has no CPU path: move the model to a CUDA device")
+        graph, static_x, out = self.graph_slot(tuple(x.shape), retrieve_tokens, slot, dev)
+        static_x.copy_(x, non_blocking=True)
+        graph.replay()
+        return out
+
+    def graph_slot(self, shape, retrieve_tokens: bool, slot: int, dev):
+        """(CUDA graph, static input tensor, static output dict) of ``forward`` for one input shape and pipeline slot;
+        captured on first use. Repacking the weights (new checkpoint, other tile size) drops all captured graphs."""
+        B, _, H, W = shape
+        with torch.cuda.device(dev):
+            self._ensure_packed(dev, H // 16, W // 16)
+            key = (tuple(shape), bool(retrieve_tokens), int(slot), str(dev))
+            g = self._graphs.get(key)
+            if g is None:
+                static_x = torch.zeros(tuple(shape), dtype=torch.float32, device=dev)
+                with torch.no_grad():
+                    self.forward(static_x, retrieve_tokens)  # eager warm-up: sizes the workspace, sets kernel attributes
+                    torch.cuda.synchronize(dev)
+                    graph = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(graph):
+                        out = self.forward(static_x, retrieve_tokens)
+                g = self._graphs[key] = (graph, static_x, out)
+        return g
 
     def calculate_instance_map(self, predictions: OrderedDict, magnification=40) -> Tuple[torch.Tensor, List[dict]]:
         """cellvit.py:332-383. ``predictions`` hold post-softmax NP/NT maps [B,C,H,W] and the HV map (only the argmax
