@@ -281,6 +281,9 @@ __device__ __forceinline__ void ldmatrix_x4(uint32_t addr, uint32_t& a, uint32_t
     asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
                  : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(addr));
 }
+__device__ __forceinline__ void ldmatrix_x2_trans(uint32_t addr, uint32_t& a, uint32_t& b) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];" : "=r"(a), "=r"(b) : "r"(addr));
+}
 __device__ __forceinline__ void ldmatrix_x4_trans(uint32_t addr, uint32_t& a, uint32_t& b, uint32_t& c, uint32_t& d) {
     asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
                  : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(addr));
