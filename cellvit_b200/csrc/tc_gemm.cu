@@ -83,40 +83,58 @@ __device__ __forceinline__ float act_t(float v) {
 // F16 epilogue of one accumulator, specialised at compile time on the activation and on the presence of a per-column
 // scale (folded BatchNorm): the generic path below re-tests `act` / `scale` per element, which doubled the instruction
 // count of the GELU epilogue (ncu: 32 instead of 16 issue slots per element, making fc1 epilogue-bound).
+// 16 accumulator columns -> (scale,) shift, activation, fp16, two 16-byte stores
+template <int ACT, bool HAS_SCALE>
+__device__ __forceinline__ void epi_f16_store16(const TcEpilogue& e, const uint32_t (&acc)[16], int nb, __half* o) {
+#pragma unroll
+    for (int j = 0; j < 16; j += 8) {
+        float v[8];
+        const float4 h0 = __ldg(reinterpret_cast<const float4*>(e.shift + nb + j));
+        const float4 h1 = __ldg(reinterpret_cast<const float4*>(e.shift + nb + j + 4));
+        if (HAS_SCALE) {
+            const float4 s0 = __ldg(reinterpret_cast<const float4*>(e.scale + nb + j));
+            const float4 s1 = __ldg(reinterpret_cast<const float4*>(e.scale + nb + j + 4));
+            v[0] = fmaf(__uint_as_float(acc[j + 0]), s0.x, h0.x); v[1] = fmaf(__uint_as_float(acc[j + 1]), s0.y, h0.y);
+            v[2] = fmaf(__uint_as_float(acc[j + 2]), s0.z, h0.z); v[3] = fmaf(__uint_as_float(acc[j + 3]), s0.w, h0.w);
+            v[4] = fmaf(__uint_as_float(acc[j + 4]), s1.x, h1.x); v[5] = fmaf(__uint_as_float(acc[j + 5]), s1.y, h1.y);
+            v[6] = fmaf(__uint_as_float(acc[j + 6]), s1.z, h1.z); v[7] = fmaf(__uint_as_float(acc[j + 7]), s1.w, h1.w);
+        } else {
+            v[0] = __uint_as_float(acc[j + 0]) + h0.x; v[1] = __uint_as_float(acc[j + 1]) + h0.y;
+            v[2] = __uint_as_float(acc[j + 2]) + h0.z; v[3] = __uint_as_float(acc[j + 3]) + h0.w;
+            v[4] = __uint_as_float(acc[j + 4]) + h1.x; v[5] = __uint_as_float(acc[j + 5]) + h1.y;
+            v[6] = __uint_as_float(acc[j + 6]) + h1.z; v[7] = __uint_as_float(acc[j + 7]) + h1.w;
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = act_t<ACT>(v[k]);
+        *reinterpret_cast<uint4*>(o + j) = make_uint4(pack_h2(v[0], v[1]), pack_h2(v[2], v[3]), pack_h2(v[4], v[5]), pack_h2(v[6], v[7]));
+    }
+}
+
+// F16 epilogue of one accumulator, specialised at compile time on the activation and on the presence of a per-column
+// scale (folded BatchNorm): the generic path below re-tests `act` / `scale` per element, which doubled the instruction
+// count of the GELU epilogue (ncu: 32 instead of 16 issue slots per element, making fc1 epilogue-bound). The TMEM
+// reads are software-pipelined in 16-column halves: the next half is in flight while the current one is computed
+// (the tcgen05.ld -> first-use stall was 16 % of the epilogue's samples).
 template <int ACT, bool HAS_SCALE, class Release>
 __device__ __forceinline__ void epilogue_f16_fast(const TcEpilogue& e, uint32_t t_addr, size_t out_off, bool store, int n0, int n_chunks,
                                                   int half, int last_c, bool do_release, Release release) {
-    if (last_c < 0) if (do_release) release();
+    if (last_c < 0) {
+        if (do_release) release();
+        return;
+    }
+    __half* obase = reinterpret_cast<__half*>(e.out) + out_off + n0;
+    uint32_t a[16], b[16];
+    ptx::tmem_ld16(t_addr + half * 32, a);
+    ptx::tmem_ld_wait();
     for (int c = half; c < n_chunks; c += 2) {
-        uint32_t acc[32];
-        ptx::tmem_ld32(t_addr + c * 32, acc);
+        ptx::tmem_ld16(t_addr + c * 32 + 16, b);
+        if (store) epi_f16_store16<ACT, HAS_SCALE>(e, a, n0 + c * 32, obase + c * 32);
         ptx::tmem_ld_wait();
-        if (c == last_c) if (do_release) release();
-        if (!store) continue;
-        const int nb = n0 + c * 32;
-        __half* o = reinterpret_cast<__half*>(e.out) + out_off + nb;
-#pragma unroll
-        for (int j = 0; j < 32; j += 8) {
-            float v[8];
-            const float4 h0 = __ldg(reinterpret_cast<const float4*>(e.shift + nb + j));
-            const float4 h1 = __ldg(reinterpret_cast<const float4*>(e.shift + nb + j + 4));
-            if (HAS_SCALE) {
-                const float4 s0 = __ldg(reinterpret_cast<const float4*>(e.scale + nb + j));
-                const float4 s1 = __ldg(reinterpret_cast<const float4*>(e.scale + nb + j + 4));
-                v[0] = fmaf(__uint_as_float(acc[j + 0]), s0.x, h0.x); v[1] = fmaf(__uint_as_float(acc[j + 1]), s0.y, h0.y);
-                v[2] = fmaf(__uint_as_float(acc[j + 2]), s0.z, h0.z); v[3] = fmaf(__uint_as_float(acc[j + 3]), s0.w, h0.w);
-                v[4] = fmaf(__uint_as_float(acc[j + 4]), s1.x, h1.x); v[5] = fmaf(__uint_as_float(acc[j + 5]), s1.y, h1.y);
-                v[6] = fmaf(__uint_as_float(acc[j + 6]), s1.z, h1.z); v[7] = fmaf(__uint_as_float(acc[j + 7]), s1.w, h1.w);
-            } else {
-                v[0] = __uint_as_float(acc[j + 0]) + h0.x; v[1] = __uint_as_float(acc[j + 1]) + h0.y;
-                v[2] = __uint_as_float(acc[j + 2]) + h0.z; v[3] = __uint_as_float(acc[j + 3]) + h0.w;
-                v[4] = __uint_as_float(acc[j + 4]) + h1.x; v[5] = __uint_as_float(acc[j + 5]) + h1.y;
-                v[6] = __uint_as_float(acc[j + 6]) + h1.z; v[7] = __uint_as_float(acc[j + 7]) + h1.w;
-            }
-#pragma unroll
-            for (int k = 0; k < 8; ++k) v[k] = act_t<ACT>(v[k]);
-            *reinterpret_cast<uint4*>(o + j) = make_uint4(pack_h2(v[0], v[1]), pack_h2(v[2], v[3]), pack_h2(v[4], v[5]), pack_h2(v[6], v[7]));
-        }
+        const bool more = c + 2 < n_chunks;
+        if (more) ptx::tmem_ld16(t_addr + (c + 2) * 32, a);
+        else if (do_release) release();  // every TMEM read of this thread has completed
+        if (store) epi_f16_store16<ACT, HAS_SCALE>(e, b, n0 + c * 32 + 16, obase + c * 32 + 16);
+        if (more) ptx::tmem_ld_wait();
     }
 }
 
