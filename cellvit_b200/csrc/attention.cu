@@ -638,11 +638,12 @@ window_attn_kernel(const __half* __restrict__ qkv, int S, int heads, float scale
 template <int HD>
 int launch_window(const __half* qkv, int Gb, int S, int heads, float scale, const __half* Rh, const __half* Rw, int gh, int gw,
                   __half* out, cudaStream_t stream) {
-    static bool configured = false;
+    static unsigned long long configured = 0;  // one bit per device: function attributes are per device
+    const int cfg_dev = cvb_current_device();
     const int smem = (int)sizeof(WaSmem<HD>);
-    if (!configured) {
+    if (!((configured >> cfg_dev) & 1ull)) {
         CVB_CUDA(cudaFuncSetAttribute(window_attn_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        configured = true;
+        configured |= 1ull << cfg_dev;
     }
     window_attn_kernel<HD><<<Gb * heads, WA_THREADS, smem, stream>>>(qkv, S, heads, scale, Rh, Rw, gh, gw, out);
     cvb_note_launches(1);
@@ -653,11 +654,12 @@ int launch_window(const __half* qkv, int Gb, int S, int heads, float scale, cons
 template <int HD, bool BIAS>
 int launch_flash(const __half* qkv, int Gb, int S, int heads, float scale, const __half* Rh, const __half* Rw,
                  int gh, int gw, __half* out, cudaStream_t stream) {
-    static bool configured = false;
+    static unsigned long long configured = 0;  // one bit per device: function attributes are per device
+    const int cfg_dev = cvb_current_device();
     const int smem = (int)sizeof(FaSmem<HD, BIAS>);
-    if (!configured) {
+    if (!((configured >> cfg_dev) & 1ull)) {
         CVB_CUDA(cudaFuncSetAttribute(flash_kernel<HD, BIAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        configured = true;
+        configured |= 1ull << cfg_dev;
     }
     dim3 grid(cdiv(S, FA_BQ), Gb * heads);
     flash_kernel<HD, BIAS><<<grid, FA_THREADS, smem, stream>>>(qkv, S, heads, scale, Rh, Rw, gh, gw, out);
@@ -672,11 +674,12 @@ int op_relpos_tables(const __half* qkv, int Gb, int S, int heads, int hd, const 
                      __half* bias_h, __half* bias_w, cudaStream_t stream) {
     CVB_CHECK(qkv && Rh && Rw && bias_h && bias_w && hd == 80 && gh <= 64 && gw <= 64 && gh * gw == S, CVB_ESHAPE,
               "relpos_tables: needs head dim 80 and a token grid of at most 64 x 64");
-    static bool configured = false;
+    static unsigned long long configured = 0;  // one bit per device: function attributes are per device
+    const int cfg_dev = cvb_current_device();
     const int smem = (int)sizeof(RtSmem<80>);
-    if (!configured) {
+    if (!((configured >> cfg_dev) & 1ull)) {
         CVB_CUDA(cudaFuncSetAttribute(relpos_tables_kernel<80>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        configured = true;
+        configured |= 1ull << cfg_dev;
     }
     relpos_tables_kernel<80><<<dim3(cdiv(S, FA_BQ), Gb * heads), FA_THREADS, smem, stream>>>(qkv, S, heads, Rh, Rw, gh, gw, bias_h, bias_w);
     cvb_note_launches(1);

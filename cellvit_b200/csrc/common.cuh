@@ -45,6 +45,7 @@ static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 int cvb_num_sms();
+int cvb_current_device();
 void cvb_note_launches(int n);
 
 #ifdef __CUDACC__

@@ -12,14 +12,21 @@ void cvb_set_error(const char* fmt, ...) {
     va_end(ap);
 }
 
+int cvb_current_device() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev > 63) return 0;
+    return dev;
+}
+
 int cvb_num_sms() {
-    static int sms = 0;
-    if (sms == 0) {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess) return 148;
-        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+    static int sms[64] = {0};
+    const int dev = cvb_current_device();
+    if (sms[dev] == 0) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        sms[dev] = n;
     }
-    return sms;
+    return sms[dev];
 }
 
 static long long g_launches = 0;

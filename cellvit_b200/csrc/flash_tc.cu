@@ -742,10 +742,11 @@ int op_attention_tc(const __half* qkv, int Gb, int S, int heads, int hd, float s
     __half* bias_h = reinterpret_cast<__half*>(ws + vt_b);
     __half* bias_w = reinterpret_cast<__half*>(ws + vt_b + bias_b);
 
-    static bool configured = false;
-    if (!configured) {
+    static unsigned long long configured = 0;  // one bit per device: function attributes are per device
+    const int cfg_dev = cvb_current_device();
+    if (!((configured >> cfg_dev) & 1ull)) {
         CVB_CUDA(cudaFuncSetAttribute(flash_tc_kernel<FT_NG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FtCfg<FT_NG>::SMEM));
-        configured = true;
+        configured |= 1ull << cfg_dev;
     }
     const dim3 grid64(S / 64, Gb * heads);
     v_transpose_kernel<<<grid64, 256, 0, stream>>>(qkv, S, heads, vt);
@@ -776,10 +777,11 @@ int op_window_attention_tc(const __half* qkv, int n_items, int heads, int hd, fl
     CVB_CHECK(((uintptr_t)workspace & 1023) == 0, CVB_EARG, "window_attention_tc: workspace must be 1024-byte aligned");
     const int D = heads * hd;
     __half* vt = reinterpret_cast<__half*>(workspace);
-    static bool configured = false;
-    if (!configured) {
+    static unsigned long long configured = 0;  // one bit per device: function attributes are per device
+    const int cfg_dev = cvb_current_device();
+    if (!((configured >> cfg_dev) & 1ull)) {
         CVB_CUDA(cudaFuncSetAttribute(window_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WT_SMEM));
-        configured = true;
+        configured |= 1ull << cfg_dev;
     }
     v_transpose_win_kernel<<<dim3(n_items, heads), 256, 0, stream>>>(qkv, heads, n_items, vt);
     CUtensorMap tq, tk, tv, tr;

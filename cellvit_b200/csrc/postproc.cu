@@ -1096,10 +1096,11 @@ int run_pipeline(const Ws& w, const float* hv, Dims d, int n_types, int object_s
         const int r = ksize / 2;
         const size_t in_bytes = (((size_t)(SB_TH + 2 * r) * (SB_TW + 2 * r) * 4) + 15) & ~(size_t)15;
         const size_t smem = in_bytes + (size_t)(SB_TH + 2 * r) * SB_TW * 8;
-        static bool configured = false;
-        if (!configured) {
+        static unsigned long long configured = 0;  // one bit per device: function attributes are per device
+    const int cfg_dev = cvb_current_device();
+        if (!((configured >> cfg_dev) & 1ull)) {
             CVB_CUDA(cudaFuncSetAttribute(sobel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-            configured = true;
+            configured |= 1ull << cfg_dev;
         }
         dim3 grid((d.W + SB_TW - 1) / SB_TW, (d.H + SB_TH - 1) / SB_TH, d.B * 2);
         sobel_kernel<<<grid, 256, smem, st>>>(hv, d, w.mm, taps, w.sob, w.mm64);
@@ -1129,10 +1130,11 @@ int run_pipeline(const Ws& w, const float* hv, Dims d, int n_types, int object_s
     blob_scatter_kernel<<<g, 256, 0, st>>>(w.L1, w.blb, w.off1, d, w.fill1, w.blobpix);
     blob_queue_kernel<<<g, 256, 0, st>>>(w.L1, w.cnt1, d, 10, SMALL_CAP, w.qmeta, w.queue, w.qstride);
     {
-        static bool configured = false;
-        if (!configured) {
+        static unsigned long long configured = 0;  // one bit per device: function attributes are per device
+    const int cfg_dev = cvb_current_device();
+        if (!((configured >> cfg_dev) & 1ull)) {
             CVB_CUDA(cudaFuncSetAttribute(watershed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (LARGE_CAP + 4) * 16 + LARGE_RCAP * 12));
-            configured = true;
+            configured |= 1ull << cfg_dev;
         }
         const int sms = cvb_num_sms();
         const size_t smem_s = (size_t)(SMALL_CAP + 4) * 16 + (size_t)SMALL_RCAP * 12;

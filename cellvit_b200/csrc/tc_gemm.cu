@@ -812,11 +812,12 @@ int launch(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, T
     // one CTA (and one 512-column TMEM allocation) lives on an SM at a time.
     size_t smem = 1024 + (size_t)stages * (A_STAGE_BYTES + b_stage) + 8 * (2 * MAX_STAGES + 4) + 16 + HEAD_S_BYTES;
     if (smem < 120 * 1024) smem = 120 * 1024;
-    static bool configured = false;
-    if (!configured) {
+    static unsigned long long configured = 0;  // one bit per device: function attributes are per device
+    const int cfg_dev = cvb_current_device();
+    if (!((configured >> cfg_dev) & 1ull)) {
         CVB_CUDA(cudaFuncSetAttribute(tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
         CVB_CUDA(cudaFuncSetAttribute(tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
-        configured = true;
+        configured |= 1ull << cfg_dev;
     }
     p.n_tiles_n = p.N / p.block_n;
     p.n_tiles = cdiv(p.M, pair ? 2 * BLOCK_M : BLOCK_M) * p.n_tiles_n;
@@ -923,10 +924,11 @@ static int conv_patch_launch(const __half* src0, int C0, const __half* src1, int
     while (cols < (uint32_t)(2 * CP_R * N)) cols <<= 1;
     p.tmem_cols = cols;
     const size_t smem = (size_t)fixed + (size_t)bst * b_stage;
-    static bool configured = false;
-    if (!configured) {
+    static unsigned long long configured = 0;  // one bit per device: function attributes are per device
+    const int cfg_dev = cvb_current_device();
+    if (!((configured >> cfg_dev) & 1ull)) {
         CVB_CUDA(cudaFuncSetAttribute(conv_patch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
-        configured = true;
+        configured |= 1ull << cfg_dev;
     }
     const int grid = p.n_tiles < cvb_num_sms() ? p.n_tiles : cvb_num_sms();
     const bool prof = g_prof.on && g_prof.used + 2 <= g_prof.ev.size();
