@@ -688,6 +688,338 @@ window_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     if (warp == 2) ptx::tmem_dealloc(tmem_base, 512);
 }
 
+// ------------------------------------------------------------------------------------------ windowed attention, single-shot
+// Second design for the windows: the whole 196-key score row is ONE UMMA per k-step (S = Q K^T with N = 208), so the
+// softmax warps run through the keys without waiting for the tensor pipe between key tiles (the four-tile loop above
+// exposes a ~4.5 k-clock Q K^T -> softmax -> P V latency per tile). Per (window, head) and query group:
+//   G = Q Rcat^T (N = 64) into S columns 0..63 -> threads stash their row, gather bh / bw -> S = Q K^T over them ->
+//   exact row maximum over the 196 biased scores -> key chunks 192..207, 128..191, 64..127, 0..63 (in that order): P
+//   chunk to shared memory (2-buffer ring) -> P V for the chunk. O lives in S columns 128..207, which are dead once
+//   the first two chunks have been read, so S (208) + O fit in 256 TMEM columns per group.
+// K (208 rows, two 64-column boxes) and V^T (4 x 64 keys) stay resident per pair; the next pair's Q / K load as soon as
+// this pair's Q K^T has completed.
+constexpr uint32_t W2_KA_BYTES = WT_VLD * 128;                                  // 208 key rows x 128 B per box
+constexpr uint32_t W2_V_BYTES = 4 * FT_V_BYTES;
+constexpr uint32_t W2_SMEM = 1024 + WT_Q_BYTES + 2 * W2_KA_BYTES + W2_V_BYTES + 4 * WT_P_BYTES + 512;
+
+__global__ void __launch_bounds__(WT_THREADS, 1)
+window_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                  const __grid_constant__ CUtensorMap tmK16, const __grid_constant__ CUtensorMap tmV,
+                  const __grid_constant__ CUtensorMap tmR, int heads, int n_items, float scale, __half* __restrict__ out) {
+    extern __shared__ uint8_t ft_smem_raw[];
+    const uint32_t smem_base = (ptx::smem_u32(ft_smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem_gen = ft_smem_raw + (smem_base - ptx::smem_u32(ft_smem_raw));
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
+    const int D = heads * FT_HD;
+    const int n_work = n_items * heads;
+
+    const uint32_t sQ = smem_base;
+    const uint32_t sKa = sQ + WT_Q_BYTES;
+    const uint32_t sKb = sKa + W2_KA_BYTES;
+    const uint32_t sV = sKb + W2_KA_BYTES;
+    const uint32_t sP = sV + W2_V_BYTES;   // [group][buffer] 16 KB each; the first 16 KB double as the Rcat operand
+    const uint32_t sR = sP;
+    const uint32_t bar = sP + 4 * WT_P_BYTES;
+    // once-per-pair barriers (parity = pair counter & 1)
+    const uint32_t q_full = bar, k_full = bar + 8, v_full = bar + 16, qk_done = bar + 24, v_done = bar + 32, r_full = bar + 40,
+                   r_done = bar + 48;
+    auto g_full = [&](int g) { return bar + 8u * (8 + g); };
+    auto g_read = [&](int g) { return bar + 8u * (10 + g); };
+    auto s_full = [&](int g) { return bar + 8u * (12 + g); };
+    auto o_full = [&](int g) { return bar + 8u * (14 + g); };
+    auto o_read = [&](int g) { return bar + 8u * (16 + g); };
+    auto p_full = [&](int g, int c) { return bar + 8u * (18 + g * 4 + c); };   // chunk c of group g published
+    auto p_free = [&](int g, int b) { return bar + 8u * (26 + g * 2 + b); };   // two completions per pair
+    const uint32_t tmem_slot = bar + 8u * 30;
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tmap(&tmQ); ptx::prefetch_tmap(&tmK); ptx::prefetch_tmap(&tmK16); ptx::prefetch_tmap(&tmV); ptx::prefetch_tmap(&tmR);
+    }
+    if (warp == 1 && lane == 0) {
+        ptx::mbar_init(q_full, 1); ptx::mbar_init(k_full, 1); ptx::mbar_init(v_full, 1); ptx::mbar_init(qk_done, 1);
+        ptx::mbar_init(v_done, 1); ptx::mbar_init(r_full, 1); ptx::mbar_init(r_done, 1);
+        for (int g = 0; g < 2; ++g) {
+            ptx::mbar_init(g_full(g), 1); ptx::mbar_init(g_read(g), 128); ptx::mbar_init(s_full(g), 1);
+            ptx::mbar_init(o_full(g), 1); ptx::mbar_init(o_read(g), 128);
+            for (int c = 0; c < 4; ++c) ptx::mbar_init(p_full(g, c), 128);
+            for (int b = 0; b < 2; ++b) ptx::mbar_init(p_free(g, b), 1);
+        }
+        ptx::fence_barrier_init();
+    }
+    if (warp == 2) {
+        ptx::tmem_alloc(tmem_slot, 512);
+        ptx::tmem_relinquish();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
+    auto tS = [&](int g) { return tmem_base + (uint32_t)(g * 256); };
+    auto tO = [&](int g) { return tmem_base + (uint32_t)(g * 256 + 128); };
+
+    if (warp == 0) {
+        // ===================================================== TMA producer
+        int it = 0;
+        for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++it) {
+            const int item = w / heads, head = w - item * heads;
+            const int row0 = item * WT_S;
+            const uint32_t par = (uint32_t)(it & 1);
+            // Rcat lives in the P region: reload it for every pair once the previous pair's P V has finished with P
+            ptx::mbar_wait(v_done, par ^ 1u);
+            if (ptx::elect_one()) {
+                ptx::mbar_expect_tx(r_full, WT_R_BYTES);
+                ptx::tma_load_2d(sR, &tmR, r_full, 0, 0);
+                ptx::tma_load_2d(sR + 64 * 128, &tmR, r_full, 16, 0);
+                ptx::mbar_expect_tx(v_full, W2_V_BYTES);
+#pragma unroll
+                for (int t = 0; t < 4; ++t) ptx::tma_load_2d(sV + t * FT_V_BYTES, &tmV, v_full, item * WT_VLD + t * FT_BK, head * FT_HD);
+            }
+            ptx::mbar_wait(qk_done, par ^ 1u);  // Q / K of the previous pair are no longer read
+            if (ptx::elect_one()) {
+                ptx::mbar_expect_tx(q_full, WT_Q_BYTES);
+#pragma unroll
+                for (int grp = 0; grp < 2; ++grp) {
+                    ptx::tma_load_2d(sQ + grp * 2 * FT_BQ * 128, &tmQ, q_full, head * FT_HD, row0 + grp * FT_BQ);
+                    ptx::tma_load_2d(sQ + grp * 2 * FT_BQ * 128 + FT_BQ * 128, &tmQ, q_full, head * FT_HD + 16, row0 + grp * FT_BQ);
+                }
+                ptx::mbar_expect_tx(k_full, 2 * W2_KA_BYTES);
+#pragma unroll
+                for (int t = 0; t < 3; ++t) {
+                    ptx::tma_load_2d(sKa + t * 8192, &tmK, k_full, D + head * FT_HD, row0 + t * 64);
+                    ptx::tma_load_2d(sKb + t * 8192, &tmK, k_full, D + head * FT_HD + 16, row0 + t * 64);
+                }
+                ptx::tma_load_2d(sKa + 3 * 8192, &tmK16, k_full, D + head * FT_HD, row0 + 192);
+                ptx::tma_load_2d(sKb + 3 * 8192, &tmK16, k_full, D + head * FT_HD + 16, row0 + 192);
+            }
+        }
+    } else if (warp == 1) {
+        // ===================================================== MMA issuer
+        auto idesc = [](int n) { return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(FT_BQ >> 4) << 24); };
+        const uint64_t desc_hi = (2ull << 61) | (1ull << 46) | ((uint64_t)(1024 >> 4) << 32);
+        auto desc = [&](uint32_t addr) { return desc_hi | (uint64_t)((addr >> 4) & 0x3FFF); };
+        int it = 0;
+        for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++it) {
+            const uint32_t par = (uint32_t)(it & 1);
+            ptx::mbar_wait(q_full, par);
+            ptx::mbar_wait(r_full, par);
+            // G = Q Rcat^T into S columns 0..63 of each group (the previous pair's O, in the same columns region, has been read)
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+                ptx::mbar_wait(o_read(g), par ^ 1u);
+                ptx::tc_fence_after();
+                if (ptx::elect_one()) {
+                    const uint32_t q = sQ + g * 2 * FT_BQ * 128;
+                    const uint64_t a0 = desc(q), a1 = desc(q + FT_BQ * 128), b0 = desc(sR), b1 = desc(sR + 64 * 128);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) ptx::umma_f16(tS(g), a0 + 2u * k, b0 + 2u * k, idesc(64), k != 0 ? 1u : 0u);
+                    ptx::umma_f16(tS(g), a1 + 6u, b1 + 6u, idesc(64), 1u);
+                    ptx::umma_commit(g_full(g));
+                    if (g == 1) ptx::umma_commit(r_done);
+                }
+                __syncwarp();
+            }
+            ptx::mbar_wait(k_full, par);
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+                ptx::mbar_wait(g_read(g), par);  // every thread of the group has its G row
+                ptx::tc_fence_after();
+                if (ptx::elect_one()) {
+                    const uint32_t q = sQ + g * 2 * FT_BQ * 128;
+                    const uint64_t a0 = desc(q), a1 = desc(q + FT_BQ * 128), b0 = desc(sKa), b1 = desc(sKb);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) ptx::umma_f16(tS(g), a0 + 2u * k, b0 + 2u * k, idesc(WT_VLD), k != 0 ? 1u : 0u);
+                    ptx::umma_f16(tS(g), a1 + 6u, b1 + 6u, idesc(WT_VLD), 1u);
+                    ptx::umma_commit(s_full(g));
+                    if (g == 1) ptx::umma_commit(qk_done);
+                }
+                __syncwarp();
+            }
+            ptx::mbar_wait(v_full, par);
+            // P V per key chunk, chunks 3, 2, 1, 0; O (S columns 128..207) may only be written once chunks 3 AND 2 were read
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+                ptx::mbar_wait(p_full(g, 3), par);
+                ptx::mbar_wait(p_full(g, 2), par);
+                ptx::tc_fence_after();
+                if (ptx::elect_one()) {
+                    ptx::umma_f16(tO(g), desc(sP + (g * 2 + 1) * WT_P_BYTES), desc(sV + 3 * FT_V_BYTES), idesc(FT_HD), 0u);  // keys 192..207
+                    ptx::umma_commit(p_free(g, 1));
+                    const uint64_t a0 = desc(sP + (g * 2 + 0) * WT_P_BYTES), b0 = desc(sV + 2 * FT_V_BYTES);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) ptx::umma_f16(tO(g), a0 + 2u * k, b0 + 2u * k, idesc(FT_HD), 1u);
+                    ptx::umma_commit(p_free(g, 0));
+                }
+                __syncwarp();
+            }
+#pragma unroll
+            for (int c = 1; c >= 0; --c) {
+#pragma unroll
+                for (int g = 0; g < 2; ++g) {
+                    ptx::mbar_wait(p_full(g, c), par);
+                    ptx::tc_fence_after();
+                    if (ptx::elect_one()) {
+                        const uint64_t a0 = desc(sP + (g * 2 + (c & 1)) * WT_P_BYTES), b0 = desc(sV + c * FT_V_BYTES);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) ptx::umma_f16(tO(g), a0 + 2u * k, b0 + 2u * k, idesc(FT_HD), 1u);
+                        if (c == 1) ptx::umma_commit(p_free(g, 1));
+                        else { ptx::umma_commit(p_free(g, 0)); ptx::umma_commit(o_full(g)); if (g == 1) ptx::umma_commit(v_done); }
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================================================== softmax / output: one query row per thread
+        const int grp = (warp - 4) >> 2, quad = warp & 3, r = quad * 32 + lane;
+        const int qi = grp * FT_BQ + r;
+        const int qc = qi < WT_S ? qi : WT_S - 1;
+        const int qh = qc / WT_G, qw = qc - qh * WT_G;
+        const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
+        const float sl2 = scale * FT_L2E;
+        const uint32_t p_row = (uint32_t)r * 128u;
+        const uint32_t sw = (uint32_t)(r & 7);
+        int it = 0;
+        for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++it) {
+            const int item = w / heads, head = w - item * heads;
+            const int row0 = item * WT_S;
+            const uint32_t par = (uint32_t)(it & 1);
+            float bh[WT_G], bw[WT_G];
+            {
+                ptx::mbar_wait(g_full(grp), par);
+                ptx::tc_fence_after();
+                uint32_t g0[32], g1[32];
+                ptx::tmem_ld32(tS(grp) + lane_off, g0);
+                ptx::tmem_ld32(tS(grp) + lane_off + 32u, g1);
+                ptx::tmem_ld_wait();
+                ptx::tc_fence_before();
+                ptx::mbar_arrive(g_read(grp));  // S columns 0..63 may take Q K^T now
+                // stash the row (group 1 uses the upper half of the P region; group 0 must not touch the Rcat operand in the
+                // first 16 KB before the G MMAs of BOTH groups have completed)
+                ptx::mbar_wait(r_done, par);
+                float* gs = reinterpret_cast<float*>(smem_gen + (sP - smem_base) + grp * 2 * WT_P_BYTES) + r * 64;
+#pragma unroll
+                for (int i = 0; i < 32; i += 4) {
+                    *reinterpret_cast<uint4*>(gs + i) = make_uint4(g0[i], g0[i + 1], g0[i + 2], g0[i + 3]);
+                    *reinterpret_cast<uint4*>(gs + 32 + i) = make_uint4(g1[i], g1[i + 1], g1[i + 2], g1[i + 3]);
+                }
+                __syncwarp();
+#pragma unroll
+                for (int k = 0; k < WT_G; ++k) {
+                    bh[k] = gs[qh + WT_G - 1 - k] * FT_L2E;
+                    bw[k] = gs[32 + qw + WT_G - 1 - k] * FT_L2E;
+                }
+                ptx::named_bar_sync(1 + grp, 128);  // every row of the group is read before the first P row is written
+            }
+            ptx::mbar_wait(s_full(grp), par);
+            ptx::tc_fence_after();
+            // ---- exact row maximum over the 196 biased scores
+            float mx = -INFINITY;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                if (c < 3) {
+                    uint32_t a[32], b2[32];
+                    ptx::tmem_ld32(tS(grp) + lane_off + (uint32_t)(c * 64), a);
+                    ptx::tmem_ld32(tS(grp) + lane_off + (uint32_t)(c * 64 + 32), b2);
+                    ptx::tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const int k0 = c * 64 + j, k1 = k0 + 32;
+                        mx = fmaxf(mx, fmaf(__uint_as_float(a[j]), sl2, bh[k0 / WT_G] + bw[k0 % WT_G]));
+                        mx = fmaxf(mx, fmaf(__uint_as_float(b2[j]), sl2, bh[k1 / WT_G] + bw[k1 % WT_G]));
+                    }
+                } else {
+                    uint32_t d[16];
+                    ptx::tmem_ld16(tS(grp) + lane_off + 192u, d);
+                    ptx::tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int k0 = 192 + j;
+                        mx = fmaxf(mx, fmaf(__uint_as_float(d[j]), sl2, bh[k0 / WT_G] + bw[k0 % WT_G]));
+                    }
+                }
+            }
+            float l_run = 0.f;
+            // ---- P chunks in the order 3, 2, 1, 0
+#pragma unroll
+            for (int c = 3; c >= 0; --c) {
+                const int buf = c & 1;
+                uint32_t pk[32];
+                if (c == 3) {
+                    uint32_t d[16];
+                    ptx::tmem_ld16(tS(grp) + lane_off + 192u, d);
+                    ptx::tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int k0 = 192 + 2 * j;
+                        float p0 = 0.f, p1 = 0.f;
+                        if (k0 < WT_S) p0 = ptx::ex2(fmaf(__uint_as_float(d[2 * j]), sl2, bh[k0 / WT_G] + bw[k0 % WT_G]) - mx);
+                        if (k0 + 1 < WT_S) p1 = ptx::ex2(fmaf(__uint_as_float(d[2 * j + 1]), sl2, bh[(k0 + 1) / WT_G] + bw[(k0 + 1) % WT_G]) - mx);
+                        l_run += p0 + p1;
+                        pk[j] = pack_h2(p0, p1);
+                    }
+                } else {
+                    uint32_t a[32], b2[32];
+                    ptx::tmem_ld32(tS(grp) + lane_off + (uint32_t)(c * 64), a);
+                    ptx::tmem_ld32(tS(grp) + lane_off + (uint32_t)(c * 64 + 32), b2);
+                    ptx::tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const int k0 = c * 64 + 2 * j, k2 = k0 + 32;
+                        const float p0 = ptx::ex2(fmaf(__uint_as_float(a[2 * j]), sl2, bh[k0 / WT_G] + bw[k0 % WT_G]) - mx);
+                        const float p1 = ptx::ex2(fmaf(__uint_as_float(a[2 * j + 1]), sl2, bh[(k0 + 1) / WT_G] + bw[(k0 + 1) % WT_G]) - mx);
+                        const float p2 = ptx::ex2(fmaf(__uint_as_float(b2[2 * j]), sl2, bh[k2 / WT_G] + bw[k2 % WT_G]) - mx);
+                        const float p3 = ptx::ex2(fmaf(__uint_as_float(b2[2 * j + 1]), sl2, bh[(k2 + 1) / WT_G] + bw[(k2 + 1) % WT_G]) - mx);
+                        l_run += (p0 + p1) + (p2 + p3);
+                        pk[j] = pack_h2(p0, p1);
+                        pk[16 + j] = pack_h2(p2, p3);
+                    }
+                }
+                ptx::tc_fence_before();
+                // the buffer was last read by the P V of: chunk c + 2 of this pair (c = 1, 0) or chunk c - 2 of the previous pair
+                ptx::mbar_wait(p_free(grp, buf), c >= 2 ? 1u : 0u);  // two completions per pair: parity 1 = last P V of the previous pair
+                {
+                    const uint32_t base = sP + (grp * 2 + buf) * WT_P_BYTES + p_row;
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        if (c < 3 || q < 2) {
+                            const uint32_t addr = base + (((uint32_t)q ^ sw) << 4);
+                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[4 * q]), "r"(pk[4 * q + 1]),
+                                         "r"(pk[4 * q + 2]), "r"(pk[4 * q + 3]) : "memory");
+                        }
+                    }
+                }
+                ptx::fence_proxy_async();
+                ptx::mbar_arrive(p_full(grp, c));
+            }
+            {
+                ptx::mbar_wait(o_full(grp), par);
+                ptx::tc_fence_after();
+                const float inv = 1.0f / l_run;
+                __half* dst = out + ((long long)row0 + qi) * D + head * FT_HD;
+                auto f = [&](uint32_t u) { return __uint_as_float(u) * inv; };
+#pragma unroll 1
+                for (int c0 = 0; c0 < FT_HD; c0 += 16) {
+                    uint32_t d[16];
+                    ptx::tmem_ld16(tO(grp) + lane_off + (uint32_t)c0, d);
+                    ptx::tmem_ld_wait();
+                    if (qi < WT_S) {
+#pragma unroll
+                        for (int i = 0; i < 16; i += 8)
+                            *reinterpret_cast<uint4*>(dst + c0 + i) = make_uint4(pack_h2(f(d[i]), f(d[i + 1])), pack_h2(f(d[i + 2]), f(d[i + 3])),
+                                                                                 pack_h2(f(d[i + 4]), f(d[i + 5])), pack_h2(f(d[i + 6]), f(d[i + 7])));
+                    }
+                }
+                ptx::tc_fence_before();
+                ptx::mbar_arrive(o_read(grp));
+            }
+        }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    if (warp == 2) ptx::tmem_dealloc(tmem_base, 512);
+}
+
 PFN_cuTensorMapEncodeTiled_v12000 ft_encode_fn() {
     static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
     if (!fn) {
@@ -769,6 +1101,11 @@ size_t op_window_attention_tc_workspace_bytes(int n_items, int heads) {
     return align_up((size_t)heads * FT_HD * n_items * WT_VLD * 2, 1024) + 1024;
 }
 
+// 1: four-key-tile loop (window_tc_kernel, 128 us per SAM-H block at B = 4), 2: single-shot N = 208 (window_tc2_kernel, 152 us:
+// one thread per 196-score row is ~1,800 serial instructions per pair, and only 8 softmax warps fit beside the TMEM budget)
+static int g_window_tc_variant = 1;
+extern "C" __attribute__((visibility("default"))) void cvb_set_window_tc_variant(int v) { g_window_tc_variant = v == 2 ? 2 : 1; }
+
 int op_window_attention_tc(const __half* qkv, int n_items, int heads, int hd, float scale, const __half* relcat, __half* out,
                            void* workspace, size_t ws_bytes, cudaStream_t stream) {
     CVB_CHECK(qkv && out && relcat && workspace, CVB_EARG, "window_attention_tc: null operand");
@@ -781,6 +1118,7 @@ int op_window_attention_tc(const __half* qkv, int n_items, int heads, int hd, fl
     const int cfg_dev = cvb_current_device();
     if (!((configured >> cfg_dev) & 1ull)) {
         CVB_CUDA(cudaFuncSetAttribute(window_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WT_SMEM));
+        CVB_CUDA(cudaFuncSetAttribute(window_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)W2_SMEM));
         configured |= 1ull << cfg_dev;
     }
     v_transpose_win_kernel<<<dim3(n_items, heads), 256, 0, stream>>>(qkv, heads, n_items, vt);
@@ -792,7 +1130,13 @@ int op_window_attention_tc(const __half* qkv, int n_items, int heads, int hd, fl
     CVB_TRY(ft_tmap_2d(&tr, relcat, (uint64_t)FT_HD, 64, (uint64_t)FT_HD * 2, 64, 64));
     const int n_work = n_items * heads;
     const int grid = n_work < cvb_num_sms() ? n_work : cvb_num_sms();
-    window_tc_kernel<<<grid, WT_THREADS, WT_SMEM, stream>>>(tq, tk, tv, tr, heads, n_items, scale, out);
+    if (g_window_tc_variant == 2) {
+        CUtensorMap tk16;
+        CVB_TRY(ft_tmap_2d(&tk16, qkv, (uint64_t)3 * D, rows, (uint64_t)3 * D * 2, 64, 16));
+        window_tc2_kernel<<<grid, WT_THREADS, W2_SMEM, stream>>>(tq, tk, tk16, tv, tr, heads, n_items, scale, out);
+    } else {
+        window_tc_kernel<<<grid, WT_THREADS, WT_SMEM, stream>>>(tq, tk, tv, tr, heads, n_items, scale, out);
+    }
     cvb_note_launches(2);
     CVB_CUDA(cudaGetLastError());
     return CVB_OK;

@@ -154,6 +154,7 @@ int cvb_op_attention_tc(const void* qkv, int Gb, int S, int heads, int hd, float
 int cvb_op_window_attention_tc_workspace_bytes(int n_items, int heads, size_t* out);
 int cvb_op_window_attention_tc(const void* qkv, int n_items, int heads, int hd, float scale, const void* relcat, void* out,
                                void* workspace, size_t ws_bytes, void* stream);
+void cvb_set_window_tc_variant(int v); /* 1 (default): four-key-tile loop, 2: single-shot N = 208 kernel */
 int cvb_op_patch_im2col(const float* x, int B, int H, int W, int P, void* out, void* stream);
 int cvb_op_stem_conv(const float* x, int B, int H, int W, const float* w, const float* scale, const float* shift,
                      void* out, int cpad, void* stream);

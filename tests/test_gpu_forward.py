@@ -185,9 +185,11 @@ def test_forward_sam_h_1024_attention_tc_vs_mma_sync():
             assert err <= tol, (k, err)
 
 
-@pytest.mark.parametrize("n_items,heads", [(3, 2), (25, 4)])
-def test_window_attention_tc_matches_torch(n_items, heads):
-    """tcgen05 window attention (flash_tc.cu): 14 x 14 windows, head dim 80, rel-pos bias computed in the kernel."""
+@pytest.mark.parametrize("n_items,heads,variant", [(3, 2, 1), (25, 4, 1), (3, 2, 2), (25, 4, 2), (160, 16, 2)])
+def test_window_attention_tc_matches_torch(n_items, heads, variant):
+    """tcgen05 window attention (flash_tc.cu, both kernel designs): 14 x 14 windows, head dim 80, rel-pos bias computed
+    in the kernel; 160 x 16 pairs exercise the persistent loop (several pairs per CTA)."""
+    L.lib().cvb_set_window_tc_variant(variant)
     g = torch.Generator(device="cuda").manual_seed(13)
     gh = gw = 14
     hd, S = 80, 196
@@ -207,6 +209,7 @@ def test_window_attention_tc_matches_torch(n_items, heads):
     L.check(L.lib().cvb_op_window_attention_tc(L.ptr(qkv), n_items, heads, hd, C.c_float(scale), L.ptr(relcat), L.ptr(out),
                                                C.c_void_p(ws.data_ptr() + off), C.c_size_t(need.value), L.stream_ptr()), "window_tc")
     torch.cuda.synchronize()
+    L.lib().cvb_set_window_tc_variant(1)
     ref = _ref_attention(qkv, n_items, S, heads, hd, scale, Rh.float(), Rw.float(), gh, gw)
     assert torch.isfinite(out.float()).all()
     err = (out.float() - ref).abs().max().item()

@@ -3,6 +3,9 @@ sys.path.insert(0, ".")
 from cellvit_b200.cellvit import CellViTSAM
 from cellvit_b200.post_proc_cellvit import DetectionCellPostProcessor
 from cellvit_b200 import synth
+from cellvit_b200 import _lib as _L
+if len(sys.argv) > 1: _L.lib().cvb_set_attention_tc(int(sys.argv[1]))   # attention mode bits (see csrc/model.cu)
+if len(sys.argv) > 2: _L.lib().cvb_set_window_tc_variant(int(sys.argv[2]))
 torch.manual_seed(0)
 m = CellViTSAM(None, 6, 19, "SAM-H").eval().cuda()
 x = torch.from_numpy(synth.synthetic_tiles(4, 1024, seed=1)).cuda()
