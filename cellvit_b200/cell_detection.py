@@ -206,6 +206,9 @@ class CellSegmentationInference:
                 ov = head_override(payload) if callable(head_override) else head_override
                 if ov:
                     predictions.update(ov)
+                if pending is not None and proc.needs_realloc(x.shape[0], x.shape[2], x.shape[3], dev):
+                    yield finish(pending)  # a larger batch / other tile size re-creates the workspace: collect first
+                    pending = None
                 s_post.wait_event(fwd_done)
                 with torch.cuda.stream(s_post):
                     np_map = F.softmax(predictions["nuclei_binary_map"], dim=1)

@@ -73,14 +73,16 @@ class _Workspace:
                                      L.ptr(d["pts"]), L.ptr(d["npts"]), L.ptr(self.cws), C.c_size_t(self.cws.numel()), L.stream_ptr()),
                 "cvb_contours")
 
-    def copy_to_host(self, slot, n_rows):
+    def copy_to_host(self, slot, n_rows, B=None):
         """Enqueue the D2H copies of one batch on the current stream. Every copy is a CONTIGUOUS block: a strided
         slice such as ``table[:, :n_rows]`` would make torch stage it through a temporary and block the host until
         the device has drained (which serialises the host dict building with the next batch's device work)."""
         h, d = self.host[slot], self.dev[slot]
-        h["labels"].copy_(d["labels"], non_blocking=True)
-        h["counts"].copy_(d["counts"], non_blocking=True)
-        for b in range(d["labels"].shape[0]):
+        B = d["labels"].shape[0] if B is None else B
+        h["B"] = B
+        h["labels"][:B].copy_(d["labels"][:B], non_blocking=True)
+        h["counts"][:B].copy_(d["counts"][:B], non_blocking=True)
+        for b in range(B):
             h["table"][b, :n_rows].copy_(d["table"][b, :n_rows], non_blocking=True)
             h["pts"][b, :n_rows].copy_(d["pts"][b, :n_rows], non_blocking=True)
             h["npts"][b, :n_rows].copy_(d["npts"][b, :n_rows], non_blocking=True)
@@ -101,9 +103,15 @@ class DetectionCellPostProcessor:
         self._wsp = None
 
     # ------------------------------------------------------------------ device entry points
+    def needs_realloc(self, B, H, W, device) -> bool:
+        """True if a batch of this shape does not fit the current workspace (a smaller batch of the same tile size does)."""
+        w = self._wsp
+        return w is None or w.key[1:] != (H, W, str(device), self.max_rows) or B > w.key[0]
+
     def _workspace(self, B, H, W, device) -> _Workspace:
-        key = (B, H, W, str(device), self.max_rows)
-        if self._wsp is None or self._wsp.key != key:
+        """Workspace for up to B tiles of H x W; a smaller batch (the ragged tail of a tile stream) reuses the buffers of a
+        larger one -- reallocating would drop the pinned results of a batch that has not been collected yet."""
+        if self.needs_realloc(B, H, W, device):
             self._wsp = _Workspace(B, H, W, device, self.max_rows)
         return self._wsp
 
@@ -126,7 +134,7 @@ class DetectionCellPostProcessor:
                                               self.object_size, self.k_size, L.ptr(w.labels), L.ptr(w.table), L.ptr(w.counts),
                                               self.max_rows, L.ptr(dbg.get("blb")), L.ptr(dbg.get("dist")), L.ptr(dbg.get("marker")),
                                               L.ptr(w.ws), C.c_size_t(w.ws.numel()), L.stream_ptr()), "cvb_postproc_maps")
-            return w.labels, self._rows(w), dbg
+            return w.labels[:B], self._rows(w, B), dbg
 
     def run_float(self, np_map: torch.Tensor, hv: torch.Tensor, nt_map: torch.Tensor = None):
         """np_map [B,2,H,W], hv [B,2,H,W], nt_map [B,C,H,W] float32 CUDA (probabilities or logits; argmax on device)."""
@@ -142,7 +150,7 @@ class DetectionCellPostProcessor:
             L.check(L.lib().cvb_postproc(L.ptr(np_map), L.ptr(hv), L.ptr(nt_map), B, H, W, 0 if nt_map is None else nt_map.shape[1],
                                          int(self.magnification), L.ptr(w.labels), L.ptr(w.table), L.ptr(w.counts), self.max_rows,
                                          L.ptr(w.ws), C.c_size_t(w.ws.numel()), L.stream_ptr()), "cvb_postproc")
-            return w.labels, self._rows(w)
+            return w.labels[:B], self._rows(w, B)
 
     # ------------------------------------------------------------------ asynchronous (pipelined) use
     def launch_float(self, np_map: torch.Tensor, hv: torch.Tensor, nt_map: torch.Tensor, slot: int, table_rows: int = ROWS_COPIED,
@@ -166,7 +174,7 @@ class DetectionCellPostProcessor:
                     d["cell_tokens"] = torch.empty(B, self.max_rows, D, dtype=torch.float32, device=np_map.device)
                 L.check(L.lib().cvb_cell_tokens(L.ptr(tokens), L.ptr(d["table"]), L.ptr(d["counts"]), B, D, th, tw, int(patch_size),
                                                 self.max_rows, L.ptr(d["cell_tokens"]), L.stream_ptr()), "cvb_cell_tokens")
-            w.copy_to_host(slot, min(table_rows, self.max_rows))
+            w.copy_to_host(slot, min(table_rows, self.max_rows), B)
 
     def collect(self, slot: int, pool=None, with_tokens: bool = False):
         """Wait for host slot ``slot`` and assemble the per-tile instance dicts (reference layout). Returns
@@ -174,7 +182,8 @@ class DetectionCellPostProcessor:
         w = self._wsp
         h = w.host[slot]
         h["event"].synchronize()
-        counts = h["counts"].numpy()
+        nb = h.get("B", h["counts"].shape[0])
+        counts = h["counts"].numpy()[:nb]
         if (counts > self.max_rows).any():
             raise L.CvbError(f"instance table overflow: {int(counts.max())} rows needed, max_rows={self.max_rows}")
         d = w.dev[slot]
@@ -182,7 +191,7 @@ class DetectionCellPostProcessor:
             with torch.cuda.stream(h["stream"]):  # the slot's device buffers are intact until its next launch
                 h["table"].copy_(d["table"]); h["pts"].copy_(d["pts"]); h["npts"].copy_(d["npts"])
                 torch.cuda.current_stream().synchronize()
-        lab, tab, pts, npts = h["labels"].numpy(), h["table"].numpy(), h["pts"].numpy(), h["npts"].numpy()
+        lab, tab, pts, npts = h["labels"].numpy()[:nb], h["table"].numpy(), h["pts"].numpy(), h["npts"].numpy()
         with_types = self.nr_types is not None
         kept = [[] for _ in range(len(counts))]
 
@@ -201,12 +210,12 @@ class DetectionCellPostProcessor:
                 toks.append(t[kept[b]] if len(kept[b]) else np.zeros((0, t.shape[-1]), np.float32))
         return lab, dicts, toks
 
-    def _rows(self, w: _Workspace) -> List[np.ndarray]:
-        counts = w.counts.cpu().numpy()  # synchronises the stream
+    def _rows(self, w: _Workspace, B: int) -> List[np.ndarray]:
+        counts = w.counts[:B].cpu().numpy()  # synchronises the stream
         if (counts > self.max_rows).any():
             raise L.CvbError(f"instance table overflow: {int(counts.max())} rows needed, max_rows={self.max_rows}")
         n_max = int(counts.max()) if counts.size else 0
-        tab = w.table[:, :max(n_max, 1)].cpu().numpy()
+        tab = w.table[:B, :max(n_max, 1)].cpu().numpy()
         return [np.frombuffer(tab[b].tobytes(), dtype=ROW_DTYPE, count=int(counts[b])) for b in range(len(counts))]
 
     # ------------------------------------------------------------------ host glue (contours, dict format)
@@ -254,7 +263,7 @@ class DetectionCellPostProcessor:
         self.launch_float(np_map.contiguous().float(), hv_map.contiguous().float(),
                           None if nt_map is None else nt_map.contiguous().float(), slot=0)
         _, dicts = self.collect(0)
-        return self._wsp.dev[0]["labels"], dicts
+        return self._wsp.dev[0]["labels"][:np_map.shape[0]], dicts
 
     def post_process_cell_segmentation(self, pred_map: np.ndarray) -> Tuple[np.ndarray, dict]:
         """Reference signature (post_proc_cellvit.py:67-153): pred_map [H,W,4] = (type, np, h, v) or [H,W,3]."""

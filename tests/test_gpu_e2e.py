@@ -49,3 +49,35 @@ def test_process_tiles_pipeline_matches_oracle():
     assert lab.dtype == torch.float32 and lab.device.type == "cpu" and tuple(lab.shape) == (B, size, size)
     nuc_map = inf.model.generate_instance_nuclei_map(lab, dicts)
     assert tuple(nuc_map.shape) == (B, 6, size, size)
+
+
+def test_pipeline_ragged_last_batch_and_graph_replay():
+    """Batches of 3, 3 and 1 tiles through process_tiles with and without CUDA-graph replay: identical dicts, and the
+    static graph outputs of a slot are not clobbered before its batch has been collected."""
+    from cellvit_b200.cell_detection import CellSegmentationInference
+    ckpt = {"arch": "CellViT256", "config": {"data.num_nuclei_classes": 6, "data.num_tissue_classes": 19, "model.backbone": "default"},
+            "model_state_dict": weights.synth_state_dict("ViT256", 6, 19, seed=3)}
+    inf = CellSegmentationInference(ckpt, gpu=0)
+    size = 256
+    nuc = [synth.synthetic_nuclei(size, 30 + 3 * i, seed=70 + i) for i in range(7)]
+    lg = [synth.head_logits_from_maps(n["np_bin"], n["nt"], 6) for n in nuc]
+    batches = [(0, 3), (3, 6), (6, 7)]
+    tiles = [torch.from_numpy(synth.synthetic_tiles(b - a, size, seed=a)).pin_memory() for a, b in batches]
+
+    def override_for(k):
+        a, b = batches[k]
+        return {"nuclei_binary_map": torch.from_numpy(np.stack([l[0] for l in lg[a:b]])).cuda(),
+                "nuclei_type_map": torch.from_numpy(np.stack([l[1] for l in lg[a:b]])).cuda(),
+                "hv_map": torch.from_numpy(np.stack([n["hv"] for n in nuc[a:b]])).cuda()}
+
+    outs = {}
+    for graphs in (True, False):
+        res = [d for _, d, _ in inf._pipeline(((t, k) for k, t in enumerate(tiles)), 40, head_override=override_for, use_graphs=graphs)]
+        assert [len(r) for r in res] == [3, 3, 1]
+        outs[graphs] = res
+    flat = lambda res: [d for batch in res for d in batch]
+    for i, (g, e) in enumerate(zip(flat(outs[True]), flat(outs[False]))):
+        _same_dict(g, e)
+        pm = np.concatenate([nuc[i]["nt"][..., None], nuc[i]["np_bin"][..., None], nuc[i]["hv"].transpose(1, 2, 0)], -1).astype(np.float64)
+        _, odict = po.DetectionCellPostProcessor(6, 40).post_process_cell_segmentation(pm)
+        _same_dict(g, odict)

@@ -206,3 +206,35 @@ def test_device_contours_match_cv2_and_flag_what_they_cannot_do():
             else:
                 assert npts[i] == len(ref[rid]), (rid, npts[i], len(ref[rid]))
                 assert np.array_equal(pts[i, :npts[i]], ref[rid]), rid
+
+
+def test_flood_paths_thin_and_huge_blobs():
+    """Blobs that do not fit the shared-memory fast path of the flood kernel: thin diagonal bands (few pixels, bounding box
+    far larger than the staged region -> global-memory path of the SMALL launch), a chain of touching nuclei of ~6,000
+    pixels (> LARGE heap -> global heap), next to ordinary nuclei (fast path). All must equal the oracle bit for bit."""
+    size = 512
+    t = synth.synthetic_nuclei(size, 120, seed=21)
+    yy, xx = np.mgrid[0:size, 0:size]
+    np_bin, hv, nt = t["np_bin"].copy(), t["hv"].copy(), t["nt"].copy()
+    rng = np.random.default_rng(5)
+    # two diagonal bands, 4 px thick, 180 px long: ~700 px each, bounding box 180 x 184
+    for (y0, x0, s) in ((20, 30, 1), (300, 480, -1)):
+        band = np.zeros((size, size), bool)
+        for k in range(180):
+            band[y0 + k, x0 + s * k: x0 + s * k + 4] = True
+        np_bin[band] = 1
+        nt[band] = 2
+        hv[0][band] = ((xx - xx[band].mean()) / 90.0)[band]
+        hv[1][band] = ((yy - yy[band].mean()) / 90.0)[band]
+    # a chain of 14 touching discs of radius 12 -> one blob of ~6,000 px with 14 markers
+    for k in range(14):
+        cy, cx = 460, 40 + 22 * k
+        disc = (yy - cy) ** 2 + (xx - cx) ** 2 <= 12 ** 2
+        np_bin[disc] = 1
+        nt[disc] = 3
+        hv[0][disc] = ((xx - cx) / 12.0)[disc]
+        hv[1][disc] = ((yy - cy) / 12.0)[disc]
+    hv = (hv + rng.normal(0, 0.01, hv.shape)).astype(np.float32)
+    tile = {"np_bin": np_bin.astype(np.uint8), "hv": hv, "nt": nt}
+    labels, rows = _check_against_oracle([tile], 40)
+    assert len(rows[0]) > 100
