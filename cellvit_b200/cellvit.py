@@ -164,6 +164,7 @@ class CellViT(nn.Module):
             L.check(lib.cvb_model_workspace_bytes(self._handle, B, H, W, C.byref(need)), "cvb_model_workspace_bytes")
             if self._ws is None or self._ws.numel() < need.value or self._ws.device != x.device:
                 self._ws = torch.empty(need.value, dtype=torch.uint8, device=x.device)
+                self._graphs = {}  # captured graphs hold the old workspace address
             n_np = self.branches_output["nuclei_binary_map"]
             o_np = torch.empty(B, n_np, H, W, device=x.device)
             o_hv = torch.empty(B, 2, H, W, device=x.device)
