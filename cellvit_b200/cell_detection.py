@@ -125,7 +125,7 @@ class CellSegmentationInference:
 
     @torch.no_grad()
     def _pipeline(self, items, magnification: int = 40, head_override=None, with_tokens: bool = False, host_threads: int = 0,
-                  use_graphs: bool = True):
+                  use_graphs: bool = True, raw: bool = False):
         """Generator over ``items`` = iterable of (batch [B,3,H,W] pinned-host or device tensor, payload); yields
         ``(payload, dicts, cell_tokens)`` per batch, in order, where ``dicts`` are the per-tile instance dicts and
         ``cell_tokens`` (``with_tokens``) one float32 array [n_cells, D] per tile, rows aligned with the dict order.
@@ -136,7 +136,8 @@ class CellSegmentationInference:
         them too. ``head_override`` (dict, or callable(payload) -> dict) replaces head maps before post-processing
         (bench/test hook: random-init networks emit constant maps). ``use_graphs``: the forward of each pipeline slot
         is replayed from a CUDA graph (``CellViT.graph_slot``) whose static input buffer the H2D copy writes directly; a
-        slot's static outputs have been consumed (its batch collected) before the slot is replayed."""
+        slot's static outputs have been consumed (its batch collected) before the slot is replayed. ``raw``: yield
+        ``TileCells`` (flat arrays) instead of per-tile dicts."""
         from concurrent.futures import ThreadPoolExecutor
         from .post_proc_cellvit import DetectionCellPostProcessor
         proc = DetectionCellPostProcessor(nr_types=self.model.num_nuclei_classes, magnification=magnification, gt=False)
@@ -179,7 +180,7 @@ class CellSegmentationInference:
 
             def finish(slot):
                 payload = keep[slot][0]
-                res = proc.collect(slot, pool, with_tokens=with_tokens)
+                res = proc.collect(slot, pool, with_tokens=with_tokens, raw=raw)
                 dicts, toks = res[1], (res[2] if with_tokens else None)
                 keep[slot] = None
                 return payload, dicts, toks
@@ -261,46 +262,58 @@ class CellSegmentationInference:
         cell_dict_wsi, cell_dict_detection, processed_patches = [], [], []
         tokens_all, positions_all, contours_all = [], [], []
         scale, psize = wsi.metadata["downsampling"], wsi.metadata["patch_size"]
-        for metadata, dicts, toks in self._pipeline(loader, wsi.metadata["magnification"], head_override, with_tokens=True):
-            for meta, cells, tok in zip(metadata, dicts, toks):
+        for metadata, tiles, toks in self._pipeline(loader, wsi.metadata["magnification"], head_override, with_tokens=True, raw=True):
+            for meta, tc, tok in zip(metadata, tiles, toks):
                 row, col = meta["row"], meta["col"]
                 processed_patches.append(f"{row}_{col}")
                 x_global = int(row * psize * scale - (row + 0.5) * overlap)      # :343-350 (x follows the tile ROW)
                 y_global = int(col * psize * scale - (col + 0.5) * overlap)
                 offset_global = np.array([x_global, y_global])
-                keep = [k for k, c in enumerate(cells.values()) if c["type"] != background]
-                if not keep:
+                # per-tile vectorised arithmetic on the instance table (the reference does this cell by cell, :352-409)
+                rows = tc.rows[tc.valid]
+                sel = rows["type"] != background
+                if not sel.any():
                     continue
-                all_vals = list(cells.values())
-                vals = [all_vals[k] for k in keep]
-                bboxes = np.stack([v["bbox"] for v in vals])
-                status = cell_status_batch(bboxes, 1024, 64)                      # :372-374 (constants as in the reference)
-                on_edge = (bboxes.reshape(len(vals), -1).max(1) == 1024) | (bboxes.reshape(len(vals), -1).min(1) == 0)
-                for n, cell in enumerate(vals):
-                    centroid_global = cell["centroid"] + np.flip(offset_global)
-                    contour_global = cell["contour"] + np.flip(offset_global)
-                    bbox_global = cell["bbox"] + offset_global
-                    cell_dict = {"bbox": bbox_global.tolist(), "centroid": centroid_global.tolist(), "contour": contour_global.tolist(),
-                                 "type_prob": cell["type_prob"], "type": cell["type"], "patch_coordinates": [row, col],
-                                 "cell_status": int(status[n]), "offset_global": offset_global.tolist()}
+                rows = rows[sel]
+                n_cells = len(rows)
+                flip = np.flip(offset_global)
+                bboxes = np.stack([np.stack([rows["rmin"], rows["cmin"]], 1), np.stack([rows["rmax"], rows["cmax"]], 1)], 1).astype(np.int64)
+                status = cell_status_batch(bboxes, 1024, 64).tolist()                 # :372-374 (constants as in the reference)
+                flat = bboxes.reshape(n_cells, -1)
+                on_edge = ((flat.max(1) == 1024) | (flat.min(1) == 0)).tolist()
+                bbox_g = (bboxes + offset_global).tolist()
+                cent_np = np.stack([rows["cx"], rows["cy"]], 1) + flip
+                cent_g = cent_np.tolist()
+                lens_all = tc.lens
+                pt_sel = np.repeat(sel, lens_all)
+                lens = lens_all[sel].tolist()
+                cont_np = tc.points[pt_sel] + flip
+                cont_list = cont_np.tolist()
+                offs = np.concatenate([[0], np.cumsum(lens)]).tolist()
+                types, probs = rows["type"].tolist(), rows["type_prob"].tolist()
+                off_list = offset_global.tolist()
+                for n in range(n_cells):
+                    cell_dict = {"bbox": bbox_g[n], "centroid": cent_g[n], "contour": cont_list[offs[n]:offs[n + 1]],
+                                 "type_prob": probs[n], "type": types[n], "patch_coordinates": [row, col],
+                                 "cell_status": status[n], "offset_global": list(off_list)}
                     if on_edge[n]:
-                        position = get_cell_position(cell["bbox"], 1024)
+                        position = get_cell_position(bboxes[n], 1024)
                         cell_dict["edge_position"] = True
                         cell_dict["edge_information"] = {"position": position, "edge_patches": get_edge_patch(position, row, col)}
                     else:
                         cell_dict["edge_position"] = False
                     cell_dict_wsi.append(cell_dict)
-                    cell_dict_detection.append({"bbox": cell_dict["bbox"], "centroid": cell_dict["centroid"], "type": cell["type"]})
-                    positions_all.append(torch.Tensor(centroid_global))
-                    contours_all.append(torch.Tensor(contour_global))
-                tokens_all.append(torch.from_numpy(tok[keep]))
+                    cell_dict_detection.append({"bbox": cell_dict["bbox"], "centroid": cell_dict["centroid"], "type": types[n]})
+                positions_all.append(torch.from_numpy(cent_np).to(torch.float32))
+                contours_all.extend(torch.split(torch.from_numpy(cont_np).to(torch.float32), lens))
+                tokens_all.append(torch.from_numpy(tok[tc.valid][sel]))
 
         keep_idx = self.post_process_edge_cells(cell_dict_wsi)
         cell_dict_wsi = [cell_dict_wsi[i] for i in keep_idx]
         cell_dict_detection = [cell_dict_detection[i] for i in keep_idx]
         tokens_cat = torch.cat(tokens_all) if tokens_all else torch.zeros(0, self.model.embed_dim)
-        graph = CellGraphDataWSI(x=tokens_cat[keep_idx], positions=torch.stack([positions_all[i] for i in keep_idx]) if keep_idx
-                                 else torch.zeros(0, 2), contours=[contours_all[i] for i in keep_idx],
+        positions_cat = torch.cat(positions_all) if positions_all else torch.zeros(0, 2)
+        graph = CellGraphDataWSI(x=tokens_cat[keep_idx], positions=positions_cat[keep_idx], contours=[contours_all[i] for i in keep_idx],
                                  metadata={"wsi_metadata": wsi.metadata, "nuclei_types": nuclei_types})
 
         out_wsi = {"wsi_metadata": wsi.metadata, "processed_patches": processed_patches, "type_map": nuclei_types, "cells": cell_dict_wsi}

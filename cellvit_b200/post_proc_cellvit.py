@@ -93,6 +93,45 @@ class _Workspace:
         return h
 
 
+class TileCells:
+    """The cells of one tile as flat arrays (no per-cell Python objects): table ``rows`` (ROW_DTYPE), and the contours of
+    the rows in ``valid`` (>= 3 points, post_proc_cellvit.py:110-113) concatenated in ``points`` [sum(lens), 2] (x, y)
+    with ``lens``. Instances the device could not trace (several 8-connected components, > MAX_PTS points) are resolved
+    with cv2 on the label map, exactly as ``rows_to_dict`` does."""
+
+    def __init__(self, labels, rows, pts, npts, with_types=True):
+        self.rows, self.with_types = rows, with_types
+        npts = np.asarray(npts)
+        flagged = np.nonzero(npts < 0)[0]
+        if len(flagged) == 0:
+            self.valid = np.nonzero(npts >= 3)[0]
+            self.lens = npts[self.valid].astype(np.int64)
+            mask = np.arange(pts.shape[1])[None, :] < self.lens[:, None]
+            self.points = pts[self.valid][mask].astype(np.int32)
+        else:  # rare: per-instance path
+            import cv2
+            valid, lens, chunks = [], [], []
+            for i in range(len(rows)):
+                if npts[i] >= 3:
+                    c = pts[i, :npts[i]].astype(np.int32)
+                elif npts[i] >= 0:
+                    continue
+                else:
+                    r = rows[i]
+                    crop = (labels[r["rmin"]:r["rmax"], r["cmin"]:r["cmax"]] == r["id"]).astype(np.uint8)
+                    c = np.squeeze(cv2.findContours(crop, cv2.RETR_TREE, cv2.CHAIN_APPROX_SIMPLE)[0][0].astype("int32"))
+                    if c.ndim != 2 or c.shape[0] < 3:
+                        continue
+                    c = c + np.array([r["cmin"], r["rmin"]], dtype=np.int32)
+                valid.append(i); lens.append(len(c)); chunks.append(c)
+            self.valid = np.array(valid, dtype=np.int64)
+            self.lens = np.array(lens, dtype=np.int64)
+            self.points = np.concatenate(chunks) if chunks else np.zeros((0, 2), np.int32)
+
+    def __len__(self):
+        return len(self.valid)
+
+
 class DetectionCellPostProcessor:
     def __init__(self, nr_types: int = None, magnification=40, gt: bool = False, max_rows: int = 8192) -> None:
         self.nr_types = nr_types
@@ -176,9 +215,11 @@ class DetectionCellPostProcessor:
                                                 self.max_rows, L.ptr(d["cell_tokens"]), L.stream_ptr()), "cvb_cell_tokens")
             w.copy_to_host(slot, min(table_rows, self.max_rows), B)
 
-    def collect(self, slot: int, pool=None, with_tokens: bool = False):
+    def collect(self, slot: int, pool=None, with_tokens: bool = False, raw: bool = False):
         """Wait for host slot ``slot`` and assemble the per-tile instance dicts (reference layout). Returns
-        (label maps, dicts) -- or (label maps, dicts, cell tokens per tile) when ``with_tokens``."""
+        (label maps, dicts) -- or (label maps, dicts, cell tokens per tile) when ``with_tokens``. ``raw``: instead of dicts,
+        one ``TileCells`` per tile (instance table + device contours as flat arrays) for callers that process a tile's
+        cells vectorised (process_wsi); the token rows then align with the table rows."""
         w = self._wsp
         h = w.host[slot]
         h["event"].synchronize()
@@ -198,6 +239,9 @@ class DetectionCellPostProcessor:
         def one(b):
             n = int(counts[b])
             rows = np.frombuffer(tab[b, :n].tobytes(), dtype=ROW_DTYPE)
+            if raw:
+                kept[b] = None
+                return TileCells(lab[b], rows, pts[b, :n], npts[b, :n], with_types)
             return self.rows_to_dict(lab[b], rows, with_types, pts[b, :n], npts[b, :n], kept[b])
 
         dicts = [one(b) for b in range(len(counts))] if pool is None else list(pool.map(one, range(len(counts))))
@@ -207,7 +251,10 @@ class DetectionCellPostProcessor:
         with torch.cuda.stream(h["stream"]):
             for b in range(len(counts)):
                 t = d["cell_tokens"][b, :int(counts[b])].cpu().numpy()  # exact row count, known only now
-                toks.append(t[kept[b]] if len(kept[b]) else np.zeros((0, t.shape[-1]), np.float32))
+                if kept[b] is None:
+                    toks.append(t)
+                else:
+                    toks.append(t[kept[b]] if len(kept[b]) else np.zeros((0, t.shape[-1]), np.float32))
         return lab, dicts, toks
 
     def _rows(self, w: _Workspace, B: int) -> List[np.ndarray]:

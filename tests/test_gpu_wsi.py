@@ -151,3 +151,32 @@ def test_process_wsi_end_to_end(tmp_path):
     assert (d.min(1) < 1.5).sum() == 0, "near-identical centroids survived the overlap clean-up"
     status = np.array([c["cell_status"] for c in cells["cells"]])
     assert (status == 0).sum() > 0.7 * n and (status != 0).sum() > 20
+
+
+def test_tilecells_equal_instance_dicts():
+    """The flat-array view of a tile's cells (TileCells, used by process_wsi) holds exactly what the per-tile instance
+    dicts hold: same instances in the same order, bbox / centroid / type / contour identical."""
+    from cellvit_b200.cell_detection import CellSegmentationInference
+    ckpt = {"arch": "CellViT256", "config": {"data.num_nuclei_classes": 6, "data.num_tissue_classes": 19, "model.backbone": "default"},
+            "model_state_dict": weights.synth_state_dict("ViT256", 6, 19, seed=3)}
+    inf = CellSegmentationInference(ckpt, gpu=0)
+    B, size = 2, 256
+    nuc = [synth.synthetic_nuclei(size, 45 + 5 * i, seed=90 + i) for i in range(B)]
+    lg = [synth.head_logits_from_maps(n["np_bin"], n["nt"], 6) for n in nuc]
+    override = {"nuclei_binary_map": torch.from_numpy(np.stack([l[0] for l in lg])).cuda(),
+                "nuclei_type_map": torch.from_numpy(np.stack([l[1] for l in lg])).cuda(),
+                "hv_map": torch.from_numpy(np.stack([n["hv"] for n in nuc])).cuda()}
+    tiles = torch.from_numpy(synth.synthetic_tiles(B, size, seed=9)).pin_memory()
+    (_, dicts, toks_d), = list(inf._pipeline([(tiles, None)], 40, head_override=override, with_tokens=True))
+    (_, raws, toks_r), = list(inf._pipeline([(tiles, None)], 40, head_override=override, with_tokens=True, raw=True))
+    for b in range(B):
+        tc, d = raws[b], dicts[b]
+        assert len(tc) == len(d) > 20
+        rows = tc.rows[tc.valid]
+        offs = np.concatenate([[0], np.cumsum(tc.lens)])
+        for n, (inst_id, cell) in enumerate(d.items()):
+            assert rows["id"][n] == inst_id and rows["type"][n] == cell["type"] and rows["type_prob"][n] == cell["type_prob"]
+            assert np.array_equal(cell["bbox"], [[rows["rmin"][n], rows["cmin"][n]], [rows["rmax"][n], rows["cmax"][n]]])
+            assert np.array_equal(cell["centroid"], [rows["cx"][n], rows["cy"][n]])
+            assert np.array_equal(cell["contour"], tc.points[offs[n]:offs[n + 1]])
+        assert np.array_equal(toks_r[b][tc.valid], toks_d[b])
