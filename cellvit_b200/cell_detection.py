@@ -311,7 +311,7 @@ class CellSegmentationInference:
                     cell_dict_wsi.append(cell_dict)
                     cell_dict_detection.append({"bbox": cell_dict["bbox"], "centroid": cell_dict["centroid"], "type": types[n]})
                 positions_all.append(torch.from_numpy(cent_np).to(torch.float32))
-                contours_all.extend(torch.split(torch.from_numpy(cont_np).to(torch.float32), lens))
+                contours_all.extend(torch.from_numpy(cont_np).to(torch.float32).split_with_sizes(lens))  # (Tensor.split is 10x slower)
                 tokens_all.append(torch.from_numpy(tok[tc.valid[sel]]))
             t_records += time.perf_counter() - t_rec0
 
@@ -328,14 +328,14 @@ class CellSegmentationInference:
         out_wsi = {"wsi_metadata": wsi.metadata, "processed_patches": processed_patches, "type_map": nuclei_types, "cells": cell_dict_wsi}
         out_det = {"wsi_metadata": wsi.metadata, "processed_patches": processed_patches, "type_map": nuclei_types, "cells": cell_dict_detection}
         with open(outdir / "cells.json", "w") as f:
-            json.dump(out_wsi, f, indent=json_indent)
+            f.write(json.dumps(out_wsi, indent=json_indent))  # dumps = one-shot C encoder; json.dump streams through Python
         with open(outdir / "cell_detection.json", "w") as f:
-            json.dump(out_det, f, indent=json_indent)
+            f.write(json.dumps(out_det, indent=json_indent))
         if geojson:
             with open(outdir / "cells.geojson", "w") as f:
-                json.dump(self.convert_geojson(cell_dict_wsi, True), f, indent=json_indent)
+                f.write(json.dumps(self.convert_geojson(cell_dict_wsi, True), indent=json_indent))
             with open(outdir / "cell_detection.geojson", "w") as f:
-                json.dump(self.convert_geojson(cell_dict_wsi, False), f, indent=json_indent)
+                f.write(json.dumps(self.convert_geojson(cell_dict_wsi, False), indent=json_indent))
         torch.save(graph, outdir / "cells.pt")
         t_end = time.perf_counter()
         # where the wall clock went (seconds): tile stream (decode + GPU + per-cell records), duplicate removal, export
