@@ -151,6 +151,8 @@ class CellSegmentationInference:
                 self._streams = (torch.cuda.Stream(dev), torch.cuda.Stream(dev))
             s_in, s_post = self._streams
             in_buf, consumed, keep = [None, None], [None, None], [None, None]
+            mean_dev = torch.tensor(self.mean, dtype=torch.float32, device=dev).view(1, 3, 1, 1)
+            std_dev = torch.tensor(self.std, dtype=torch.float32, device=dev).view(1, 3, 1, 1)
 
             def stage(k, patches):
                 """Input of batch k into the device buffer of slot k & 1 (H2D on the copy stream); returns
@@ -166,14 +168,19 @@ class CellSegmentationInference:
                 elif patches.is_cuda:
                     return patches, None, None
                 else:
-                    if in_buf[slot] is None or in_buf[slot].shape != patches.shape or in_buf[slot].dtype != patches.dtype:
-                        in_buf[slot] = torch.empty(patches.shape, dtype=patches.dtype, device=dev)
+                    if in_buf[slot] is None or in_buf[slot].shape != patches.shape:
+                        in_buf[slot] = torch.empty(patches.shape, dtype=torch.float32, device=dev)
                         consumed[slot] = torch.cuda.Event()
                         consumed[slot].record(main)  # the fresh block may still be in use by earlier work on `main`
                     buf = in_buf[slot]
                 s_in.wait_event(consumed[slot])      # the forward that last read this slot has finished
                 with torch.cuda.stream(s_in):
-                    buf.copy_(patches, non_blocking=True)
+                    if patches.dtype == torch.uint8:
+                        # raw tiles: ToTensor + Normalize (:214-227) on the device, same operations in the same order
+                        u8 = patches.to(dev, non_blocking=True)
+                        buf.copy_((u8.to(torch.float32).div(255.0) - mean_dev) / std_dev)
+                    else:
+                        buf.copy_(patches, non_blocking=True)
                     ready = torch.cuda.Event()
                     ready.record(s_in)
                 return buf, ready, gs
@@ -233,7 +240,8 @@ class CellSegmentationInference:
 
     # ------------------------------------------------------------------ WSI level
     def process_wsi(self, wsi, subdir_name: str = None, patch_size: int = 1024, overlap: int = 64, batch_size: int = 8,
-                    geojson: bool = False, num_workers: int = None, head_override=None, json_indent=None) -> dict:
+                    geojson: bool = False, num_workers: int = None, head_override=None, json_indent=None,
+                    uint8_tiles: bool = False) -> dict:
         """cell_detection.py:244-483 -- all tiles of one preprocessed WSI -> ``cells.json``, ``cell_detection.json``
         (+ ``.geojson``) and ``cells.pt`` under ``<patched_slide_path>/cell_detection[/subdir_name]``.
 
@@ -242,14 +250,15 @@ class CellSegmentationInference:
         ``_pipeline``; the duplicate removal of overlapping tiles uses the GPU polygon-overlap kernel (wsi_merge.py).
         Returns the ``cells.json`` dictionary. ``head_override`` is the bench/test hook of ``_pipeline``. ``json_indent``: the
         reference writes ``indent=2`` through ujson; Python's json only uses its C encoder without indentation (10x faster
-        on a slide with 10^5 cells), so the files are written compact unless an indent is asked for -- same content."""
+        on a slide with 10^5 cells), so the files are written compact unless an indent is asked for -- same content.
+        ``uint8_tiles``: ship raw uint8 tiles from the DataLoader workers and normalise on the device (bit-identical)."""
         import json
         import os
         from torch.utils.data import DataLoader
         from .wsi_datamodel import CellGraphDataWSI, InferenceTransform, PatchedWSIInference
         from .wsi_merge import cell_status_batch, get_cell_position, get_edge_patch
 
-        dataset = PatchedWSIInference(wsi, transform=InferenceTransform(self.mean, self.std))
+        dataset = PatchedWSIInference(wsi, transform=InferenceTransform(self.mean, self.std, as_uint8=uint8_tiles))
         if num_workers is None:
             num_workers = int(np.clip(int(3 / 4 * (os.cpu_count() or 16)), 1, 2 * batch_size))
         loader = DataLoader(dataset, batch_size=batch_size, num_workers=num_workers, shuffle=False,

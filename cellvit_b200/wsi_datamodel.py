@@ -104,16 +104,22 @@ class InferenceTransform:
     """``T.Compose([T.ToTensor(), T.Normalize(mean, std)])`` (cell_detection.py:214-227) without torchvision:
     PIL / uint8 HWC -> float32 CHW in [0,1] -> (x - mean) / std. RGBA inputs keep their first three channels."""
 
-    def __init__(self, mean=(0.5, 0.5, 0.5), std=(0.5, 0.5, 0.5)):
+    def __init__(self, mean=(0.5, 0.5, 0.5), std=(0.5, 0.5, 0.5), as_uint8: bool = False):
+        """``as_uint8``: return the raw uint8 CHW tile instead; the tile pipeline then applies the same two operations on
+        the device (bit-identical), which cuts the worker -> main -> pinned -> device traffic per tile from 12.6 MB to 3.1 MB."""
         self.mean = torch.tensor(mean, dtype=torch.float32).view(3, 1, 1)
         self.std = torch.tensor(std, dtype=torch.float32).view(3, 1, 1)
+        self.as_uint8 = as_uint8
 
     def __call__(self, img) -> torch.Tensor:
         a = np.asarray(img)
         if a.ndim == 2:
             a = np.repeat(a[..., None], 3, axis=2)
         a = np.array(a[..., :3])  # writable copy
-        x = torch.from_numpy(a).permute(2, 0, 1).to(torch.float32).div(255.0)
+        x = torch.from_numpy(a).permute(2, 0, 1)
+        if self.as_uint8:
+            return x.contiguous()
+        x = x.to(torch.float32).div(255.0)
         return (x - self.mean) / self.std
 
 

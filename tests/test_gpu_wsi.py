@@ -180,3 +180,30 @@ def test_tilecells_equal_instance_dicts():
             assert np.array_equal(cell["centroid"], [rows["cx"][n], rows["cy"][n]])
             assert np.array_equal(cell["contour"], tc.points[offs[n]:offs[n + 1]])
         assert np.array_equal(toks_r[b][tc.valid], toks_d[b])
+
+
+def test_uint8_tiles_are_normalised_on_the_device_bit_identically():
+    """Raw uint8 tiles (InferenceTransform(as_uint8=True)) through the pipeline give the same network input as the host
+    ToTensor + Normalize: the forward outputs are bit-identical."""
+    from cellvit_b200.cell_detection import CellSegmentationInference
+    from cellvit_b200.wsi_datamodel import InferenceTransform
+    ckpt = {"arch": "CellViT256", "config": {"data.num_nuclei_classes": 6, "data.num_tissue_classes": 19, "model.backbone": "default"},
+            "model_state_dict": weights.synth_state_dict("ViT256", 6, 19, seed=3)}
+    inf = CellSegmentationInference(ckpt, gpu=0)
+    rng = np.random.default_rng(2)
+    imgs = [rng.integers(0, 256, (256, 256, 3), dtype=np.uint8) for _ in range(2)]
+    xf = torch.stack([InferenceTransform()(im) for im in imgs]).pin_memory()
+    xu = torch.stack([InferenceTransform(as_uint8=True)(im) for im in imgs]).pin_memory()
+    assert xu.dtype == torch.uint8 and tuple(xu.shape) == (2, 3, 256, 256)
+    seen = {}
+
+    def grab(tag):
+        def hook(payload):
+            seen[tag] = inf.model.graph_slot((2, 3, 256, 256), True, 0, torch.device("cuda", 0))[1].clone()
+            return None
+        return hook
+
+    list(inf._pipeline([(xf, None)], 40, head_override=grab("f")))
+    list(inf._pipeline([(xu, None)], 40, head_override=grab("u")))
+    assert torch.equal(seen["f"], seen["u"])
+    assert torch.equal(seen["f"].cpu(), xf)

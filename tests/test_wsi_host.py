@@ -178,6 +178,9 @@ def test_wsi_layout_and_dataset(tmp_path):
     assert m["row"] == 1 and m["col"] == 1 and m["name"] == "slideA_1_1.png"
     want = (torch.from_numpy(imgs["slideA_1_1.png"]).permute(2, 0, 1).float() / 255 - 0.5) / 0.5
     assert torch.equal(x, want)
+    xu = InferenceTransform(as_uint8=True)(Image.fromarray(imgs["slideA_1_1.png"]))
+    assert xu.dtype == torch.uint8 and torch.equal(xu, torch.from_numpy(imgs["slideA_1_1.png"]).permute(2, 0, 1))
+    assert torch.equal((xu.float().div(255.0) - 0.5) / 0.5, x)   # what the pipeline does with raw tiles on the device
     xb, mb = ds.collate_batch([ds[0], ds[1]])
     assert tuple(xb.shape) == (2, 3, 32, 32) and [q["col"] for q in mb] == [0, 1]
 
