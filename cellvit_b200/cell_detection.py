@@ -153,6 +153,7 @@ class CellSegmentationInference:
             in_buf, consumed, keep = [None, None], [None, None], [None, None]
             mean_dev = torch.tensor(self.mean, dtype=torch.float32, device=dev).view(1, 3, 1, 1)
             std_dev = torch.tensor(self.std, dtype=torch.float32, device=dev).view(1, 3, 1, 1)
+            c255_dev = torch.tensor(255.0, dtype=torch.float32, device=dev)
 
             def stage(k, patches):
                 """Input of batch k into the device buffer of slot k & 1 (H2D on the copy stream); returns
@@ -178,7 +179,8 @@ class CellSegmentationInference:
                     if patches.dtype == torch.uint8:
                         # raw tiles: ToTensor + Normalize (:214-227) on the device, same operations in the same order
                         u8 = patches.to(dev, non_blocking=True)
-                        buf.copy_((u8.to(torch.float32).div(255.0) - mean_dev) / std_dev)
+                        # (division by a 0-dim TENSOR: torch's CUDA div-by-Python-scalar multiplies by the reciprocal instead)
+                        buf.copy_((u8.to(torch.float32) / c255_dev - mean_dev) / std_dev)
                     else:
                         buf.copy_(patches, non_blocking=True)
                     ready = torch.cuda.Event()
@@ -241,7 +243,7 @@ class CellSegmentationInference:
     # ------------------------------------------------------------------ WSI level
     def process_wsi(self, wsi, subdir_name: str = None, patch_size: int = 1024, overlap: int = 64, batch_size: int = 8,
                     geojson: bool = False, num_workers: int = None, head_override=None, json_indent=None,
-                    uint8_tiles: bool = False) -> dict:
+                    uint8_tiles: bool = True) -> dict:
         """cell_detection.py:244-483 -- all tiles of one preprocessed WSI -> ``cells.json``, ``cell_detection.json``
         (+ ``.geojson``) and ``cells.pt`` under ``<patched_slide_path>/cell_detection[/subdir_name]``.
 

@@ -12,6 +12,7 @@ from cellvit_b200.cellvit import CellViTSAM
 from cellvit_b200.wsi_datamodel import WSI
 
 G = int(sys.argv[1]) if len(sys.argv) > 1 else 4
+U8 = bool(int(sys.argv[2])) if len(sys.argv) > 2 else False   # raw uint8 tiles, normalised on the device
 tile, ov, B = 1024, 64, 4
 root = tempfile.mkdtemp(prefix="wsi_")
 os.makedirs(f"{root}/patches"); os.makedirs(f"{root}/metadata")
@@ -49,11 +50,11 @@ def override(metadata):
             "hv_map": torch.stack([a[2] for a in m])}
 
 wsi = WSI(name="s", patient="p", slide_path=root, patched_slide_path=root)
-inf.process_wsi(wsi, subdir_name="warm", batch_size=B, num_workers=8, head_override=override)   # warm-up (graph capture, workers)
+inf.process_wsi(wsi, subdir_name="warm", batch_size=B, num_workers=8, head_override=override, uint8_tiles=U8)   # warm-up (graph capture, workers)
 torch.cuda.synchronize()
 t0 = time.perf_counter()
-out = inf.process_wsi(wsi, subdir_name="run", batch_size=B, geojson=True, num_workers=8, head_override=override)
+out = inf.process_wsi(wsi, subdir_name="run", batch_size=B, geojson=True, num_workers=8, head_override=override, uint8_tiles=U8)
 torch.cuda.synchronize()
 dt = time.perf_counter() - t0
-print(json.dumps({"tiles": G * G, "cells": len(out["cells"]), "seconds": dt, "tiles_per_s": G * G / dt,
+print(json.dumps({"tiles": G * G, "uint8_tiles": U8, "cells": len(out["cells"]), "seconds": dt, "tiles_per_s": G * G / dt,
                   "phases_s": inf.last_timings, "note": "process_wsi incl. PNG decode, head-override host prep, dedup, JSON/GeoJSON/graph export"}))
