@@ -112,6 +112,25 @@ def test_packing_layouts():
     assert P["pos"].shape == (257, 384) and P["clspos"].shape == (384,)
 
 
+def test_packing_sam_rel_tables():
+    """SAM window blocks: rel-pos tables [27, hd] plus their concatenation (rows 0.. = rel_h, rows 32.. = rel_w) that
+    the tcgen05 window attention uses as one K-major operand; global blocks get tables resized to the token grid."""
+    from cellvit_b200 import packing, weights
+    from cellvit_b200.cellvit import CellViTSAM
+    sd = weights.synth_state_dict("SAM-B", 6, 19, seed=2)
+    cfg = CellViTSAM(None, 6, 19, "SAM-B")._cfg()
+    P = packing.pack_static(sd, cfg)
+    win = [i for i in range(cfg["depth"]) if i not in cfg["global_idx"]][0]
+    rh, rw, cat = P[f"b{win}.relh"], P[f"b{win}.relw"], P[f"b{win}.relcat"]
+    assert tuple(rh.shape) == (27, 64) and tuple(cat.shape) == (64, 64) and cat.dtype == torch.float16
+    assert torch.equal(cat[:27], rh) and torch.equal(cat[32:59], rw)
+    assert cat[27:32].abs().sum() == 0 and cat[59:].abs().sum() == 0
+    assert torch.equal(rh.float(), sd[f"encoder.blocks.{win}.attn.rel_pos_h"].half().float())
+    G = packing.pack_for_size(sd, cfg, 16, 16)
+    g = cfg["global_idx"][0]
+    assert tuple(G[f"b{g}.relh"].shape) == (31, 64) and f"b{g}.relcat" not in P
+
+
 def test_shard_indices_cover_all_tiles_once():
     from cellvit_b200.cell_detection import shard_indices, unflatten_dict
     for n, world in [(10, 1), (10, 3), (7, 8), (10000, 8)]:
