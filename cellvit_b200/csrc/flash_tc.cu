@@ -14,7 +14,8 @@
 //            once the softmax warps have published P_t; QK of tile t+1 is issued before PV of tile t so the tensor
 //            pipe works while tile t is in the softmax.
 //   warp 2   TMEM allocator.   warps 4-7  softmax: one query row per thread (TMEM lane), exact online softmax in
-//            the log2 domain, P written to shared memory as the fp16 K-major A operand of PV (128B swizzle). O accumulates
+//            the log2 domain, P written back over the first 32 columns of its S buffer (packed fp16 pairs) and consumed by
+//            P V as a TMEM A operand (TS-mode UMMA: no shared-memory round trip, no A read per instruction). O accumulates
 //            in TMEM across all key tiles; the softmax reference m only moves when a score exceeds it by more than 2^8
 //            (P stays <= 256 in fp16, sums in fp32 -- mathematically the same softmax), and only then is O rescaled in
 //            place (tcgen05.ld / st) -- after the first tile practically never, so the softmax warps never wait for PV.
@@ -33,6 +34,7 @@ constexpr uint32_t FT_V_BYTES = FT_HD * 128;              // 80 rows (hd) x 64 k
 constexpr int FT_VR = 96;                                 // global kernel: V^T rows per head = 80 + a row of ones (row sums of P
                                                           // come out of the P V MMA as output column 80) + 15 zero rows
 constexpr uint32_t FTG_V_BYTES = FT_VR * 128;
+constexpr bool FT_P_TMEM = true;                          // P V reads P from tensor memory (TS-mode UMMA) instead of shared memory
 constexpr int FT_NG = 2;                                  // query groups (of 128 rows) per CTA
 constexpr float FT_L2E = 1.4426950408889634f;
 
@@ -194,7 +196,10 @@ flash_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 if (ptx::elect_one()) {
                     const uint64_t a0 = desc(sP + gb * Cfg::P_BYTES), b0 = desc(sV + stage * FTG_V_BYTES);
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) ptx::umma_f16(tO(grp), a0 + 2u * k, b0 + 2u * k, idesc_pv, (t | k) != 0 ? 1u : 0u);
+                    for (int k = 0; k < 4; ++k) {
+                        if (FT_P_TMEM) ptx::umma_f16_ts(tO(grp), tS(gb) + 8u * k, b0 + 2u * k, idesc_pv, (t | k) != 0 ? 1u : 0u);
+                        else ptx::umma_f16(tO(grp), a0 + 2u * k, b0 + 2u * k, idesc_pv, (t | k) != 0 ? 1u : 0u);
+                    }
                     ptx::umma_commit(o_full(gb));
                     if (grp == NG - 1) ptx::umma_commit(kv_empty(stage));
                 }
@@ -284,8 +289,13 @@ flash_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 pk[j] = ptx::ex2_f16x2(pack_h2(__uint_as_float(v0[2 * j]) - mref, __uint_as_float(v0[2 * j + 1]) - mref));
                 pk[16 + j] = ptx::ex2_f16x2(pack_h2(__uint_as_float(v1[2 * j]) - mref, __uint_as_float(v1[2 * j + 1]) - mref));
             }
-            // P row (64 keys fp16 = 8 chunks of 16 B) into the K-major SWIZZLE_128B A operand: chunk c -> c ^ (row & 7)
-            {
+            if (FT_P_TMEM) {
+                // P row (32 packed fp16 pairs) over the first 32 columns of this S buffer: the A operand of the TS-mode P V MMA
+                ptx::tmem_st32(tS(gb) + lane_off, pk);
+                ptx::tmem_st_wait();
+                ptx::tc_fence_before();
+            } else {
+                // P row (64 keys fp16 = 8 chunks of 16 B) into the K-major SWIZZLE_128B A operand: chunk c -> c ^ (row & 7)
                 const uint32_t base = sP + gb * Cfg::P_BYTES + p_row;
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
@@ -293,8 +303,8 @@ flash_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[4 * c]), "r"(pk[4 * c + 1]),
                                  "r"(pk[4 * c + 2]), "r"(pk[4 * c + 3]) : "memory");
                 }
+                ptx::fence_proxy_async();  // generic-proxy writes -> visible to the tensor core (async proxy)
             }
-            ptx::fence_proxy_async();  // generic-proxy writes -> visible to the tensor core (async proxy)
             ptx::mbar_arrive(p_full(gb));
         }
         {   // all key tiles accumulated: O / l
