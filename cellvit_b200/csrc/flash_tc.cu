@@ -513,8 +513,8 @@ window_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                 ptx::mbar_wait(p_full(gb), (uint32_t)((t >> 1) & 1));
                 ptx::tc_fence_after();
                 if (ptx::elect_one()) {
-                    const uint64_t a0 = desc(sP + gb * WT_P_BYTES), b0 = desc(sV + stage * FT_V_BYTES);
-                    for (int k = 0; k < ksteps; ++k) ptx::umma_f16(tO(grp), a0 + 2u * k, b0 + 2u * k, idesc(FT_HD), (t | k) != 0 ? 1u : 0u);
+                    const uint64_t b0 = desc(sV + stage * FT_V_BYTES);  // P: TMEM A operand, first columns of the S buffer
+                    for (int k = 0; k < ksteps; ++k) ptx::umma_f16_ts(tO(grp), tS(gb) + 8u * k, b0 + 2u * k, idesc(FT_HD), (t | k) != 0 ? 1u : 0u);
                     ptx::umma_commit(o_full(gb));
                     if (grp == 1) ptx::umma_commit(kv_empty(stage));
                 }
@@ -655,18 +655,17 @@ window_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                 pk[j] = pack_h2(p0, p1);
             }
             l_run += rs;
-            {
-                const uint32_t base = sP + gb * WT_P_BYTES + p_row;
+            // P (packed fp16 pairs) over the first columns of this S buffer: TMEM A operand of the P V MMA
+            if (t == WT_NT - 1) {
+                uint32_t d[16];
 #pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    if (c * 8 < ncol) {
-                        const uint32_t addr = base + (((uint32_t)c ^ sw) << 4);
-                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[4 * c]), "r"(pk[4 * c + 1]),
-                                     "r"(pk[4 * c + 2]), "r"(pk[4 * c + 3]) : "memory");
-                    }
-                }
+                for (int j = 0; j < 16; ++j) d[j] = pk[j];
+                ptx::tmem_st16(tS(gb) + lane_off, d);
+            } else {
+                ptx::tmem_st32(tS(gb) + lane_off, pk);
             }
-            ptx::fence_proxy_async();
+            ptx::tmem_st_wait();
+            ptx::tc_fence_before();
             ptx::mbar_arrive(p_full(gb));
         }
         {
