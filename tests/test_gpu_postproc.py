@@ -238,3 +238,11 @@ def test_flood_paths_thin_and_huge_blobs():
     tile = {"np_bin": np_bin.astype(np.uint8), "hv": hv, "nt": nt}
     labels, rows = _check_against_oracle([tile], 40)
     assert len(rows[0]) > 100
+
+
+def test_full_size_batch_bit_exact():
+    """BASELINE configuration of the post-processing: a batch of four 1024 x 1024 tiles with 700 nuclei each (the bench
+    workload) -- every stage output, label map and instance table bit-exact against the oracle."""
+    tiles = [synth.synthetic_nuclei(1024, 700, seed=s) for s in range(4)]
+    labels, rows = _check_against_oracle(tiles, 40)
+    assert all(len(r) > 600 for r in rows)
