@@ -87,3 +87,64 @@ def test_forward_oracle_matches_reference_modules(ref, arch, size):
     for k in ("tissue_types", "nuclei_binary_map", "hv_map", "nuclei_type_map", "tokens"):
         assert r[k].shape == o[k].shape
         assert (r[k] - o[k]).abs().max().item() <= 2e-6, k
+
+
+def _wsi_cell_list(ref_cd, grid=2, tile=1024, ov=64, seed=17):
+    """Cells of a synthetic slide (grid x grid tiles cut from one synthetic-nuclei canvas, so nuclei in the overlap bands
+    appear in two tiles), as the dict list process_wsi hands to the duplicate removal -- built with the REFERENCE's own
+    per-cell code (cell_detection.py:343-395) on oracle post-processing output."""
+    import numpy as np
+    from cellvit_b200 import synth
+    from oracle import postproc_oracle as po
+    side = grid * (tile - ov) + 2 * ov
+    canvas = synth.synthetic_nuclei(side, int(500 * (side / 1024.0) ** 2), seed=seed)
+    cells = []
+    for row in range(grid):
+        for col in range(grid):
+            y0 = int(col * tile - (col + 0.5) * ov) + ov
+            x0 = int(row * tile - (row + 0.5) * ov) + ov
+            sl = (slice(y0, y0 + tile), slice(x0, x0 + tile))
+            pm = np.concatenate([canvas["nt"][sl][..., None], canvas["np_bin"][sl][..., None],
+                                 canvas["hv"][:, sl[0], sl[1]].transpose(1, 2, 0)], -1).astype(np.float64)
+            _, inst = po.DetectionCellPostProcessor(6, 40).post_process_cell_segmentation(pm)
+            x_global = int(row * tile - (row + 0.5) * ov)
+            y_global = int(col * tile - (col + 0.5) * ov)
+            for cell in inst.values():
+                if cell["type"] == 0:
+                    continue
+                offset_global = np.array([x_global, y_global])
+                d = {"bbox": (cell["bbox"] + offset_global).tolist(), "centroid": (cell["centroid"] + np.flip(offset_global)).tolist(),
+                     "contour": (cell["contour"] + np.flip(offset_global)).tolist(), "type_prob": cell["type_prob"], "type": cell["type"],
+                     "patch_coordinates": [row, col], "cell_status": ref_cd.get_cell_position_marging(cell["bbox"], 1024, 64),
+                     "offset_global": offset_global.tolist()}
+                if np.max(cell["bbox"]) == 1024 or np.min(cell["bbox"]) == 0:
+                    position = ref_cd.get_cell_position(cell["bbox"], 1024)
+                    d["edge_position"] = True
+                    d["edge_information"] = {"position": position, "edge_patches": ref_cd.get_edge_patch(position, row, col)}
+                else:
+                    d["edge_position"] = False
+                cells.append(d)
+    return cells
+
+
+@pytest.mark.parametrize("grid,seed", [(2, 17), (3, 5)])
+def test_cell_post_processor_matches_reference_control_flow(grid, seed):
+    """The reference's own CellPostProcessor (cell_detection.py:600-767, unmodified, shapely stubbed with the repo's polygon
+    geometry) and cellvit_b200.wsi_merge.CellPostProcessor keep exactly the same cells of a synthetic overlapping slide."""
+    import copy
+    import logging
+    from cellvit_b200 import wsi_merge as wm
+    ref_cd = ref_shim.import_reference_cell_detection()
+    cells = _wsi_cell_list(ref_cd, grid=grid, seed=seed)
+    assert sum(c["cell_status"] != 0 for c in cells) > 50 and sum(c["edge_position"] for c in cells) > 5
+    ref_keep = list(ref_cd.CellPostProcessor(copy.deepcopy(cells), logging.getLogger("ref")).post_process_cells().index.values)
+
+    def host_overlap(contours, pairs):
+        import numpy as np
+        area = np.array([wm.polygon_area(c) for c in contours])
+        inter = np.array([wm.polygon_intersection_area(contours[i], contours[j]) for i, j in pairs]) if len(pairs) else np.zeros(0)
+        return area, inter
+
+    mine = wm.CellPostProcessor(cells, overlap_fn=host_overlap).post_process_cells()
+    assert len(ref_keep) < len(cells)            # duplicates were removed
+    assert mine == [int(i) for i in ref_keep]
