@@ -153,6 +153,40 @@ def test_process_wsi_end_to_end(tmp_path):
     assert (status == 0).sum() > 0.7 * n and (status != 0).sum() > 20
 
 
+def test_process_wsi_matches_reference_golden(tmp_path):
+    """The whole GPU path of process_wsi (device post-processing, contour tracing, duplicate removal with the polygon kernel,
+    export) against ``tests/golden/wsi_2x2_cells.json.gz`` -- the cells.json the REFERENCE's own process_wsi wrote for the same
+    synthetic slide and head maps (tools/make_wsi_golden.py, oracle/wsi_fixture.py): same cells, same order, same values."""
+    import gzip
+    import pathlib
+    from cellvit_b200.cell_detection import CellSegmentationInference
+    from cellvit_b200.wsi_datamodel import WSI
+    from oracle import wsi_fixture as wf
+    golden = json.loads(gzip.open(pathlib.Path(__file__).parent / "golden" / "wsi_2x2_cells.json.gz").read())
+    root = tmp_path / "slide"
+    wf.make_slide(root)
+    canvas = wf.make_canvas()
+    ckpt = {"arch": "CellViT256", "config": {"data.num_nuclei_classes": 6, "data.num_tissue_classes": 19, "model.backbone": "default"},
+            "model_state_dict": weights.synth_state_dict("ViT256", 6, 19, seed=3)}
+    inf = CellSegmentationInference(ckpt, gpu=0)
+
+    def override(metadata):
+        maps = [wf.tile_maps(canvas, m["row"] * wf.GRID + m["col"]) for m in metadata]
+        lg = [synth.head_logits_from_maps(m[0], m[1], 6) for m in maps]
+        return {"nuclei_binary_map": torch.from_numpy(np.stack([l[0] for l in lg])).cuda(),
+                "nuclei_type_map": torch.from_numpy(np.stack([l[1] for l in lg])).cuda(),
+                "hv_map": torch.from_numpy(np.ascontiguousarray(np.stack([m[2] for m in maps]))).cuda()}
+
+    wsi = WSI(name="slide", patient="p", slide_path=root, patched_slide_path=root)
+    inf.process_wsi(wsi, subdir_name="g", patch_size=wf.TILE, overlap=wf.OV, batch_size=2, geojson=False, num_workers=0,
+                    head_override=override)
+    cells = json.load(open(root / "cell_detection" / "g" / "cells.json"))
+    assert cells["processed_patches"] == golden["processed_patches"]
+    assert len(cells["cells"]) == len(golden["cells"])
+    for k, (a, b) in enumerate(zip(cells["cells"], golden["cells"])):
+        assert a == b, (k, a, b)
+
+
 def test_tilecells_equal_instance_dicts():
     """The flat-array view of a tile's cells (TileCells, used by process_wsi) holds exactly what the per-tile instance
     dicts hold: same instances in the same order, bbox / centroid / type / contour identical."""
