@@ -243,7 +243,7 @@ class CellSegmentationInference:
     # ------------------------------------------------------------------ WSI level
     def process_wsi(self, wsi, subdir_name: str = None, patch_size: int = 1024, overlap: int = 64, batch_size: int = 8,
                     geojson: bool = False, num_workers: int = None, head_override=None, json_indent=None,
-                    uint8_tiles: bool = True) -> dict:
+                    uint8_tiles: bool = True, shard: Tuple[int, int] = None) -> dict:
         """cell_detection.py:244-483 -- all tiles of one preprocessed WSI -> ``cells.json``, ``cell_detection.json``
         (+ ``.geojson``) and ``cells.pt`` under ``<patched_slide_path>/cell_detection[/subdir_name]``.
 
@@ -253,7 +253,12 @@ class CellSegmentationInference:
         Returns the ``cells.json`` dictionary. ``head_override`` is the bench/test hook of ``_pipeline``. ``json_indent``: the
         reference writes ``indent=2`` through ujson; Python's json only uses its C encoder without indentation (10x faster
         on a slide with 10^5 cells), so the files are written compact unless an indent is asked for -- same content.
-        ``uint8_tiles``: ship raw uint8 tiles from the DataLoader workers and normalise on the device (bit-identical)."""
+        ``uint8_tiles``: ship raw uint8 tiles from the DataLoader workers and normalise on the device (bit-identical).
+
+        Multi-GPU (one process per GPU): with ``torch.distributed`` initialised -- or an explicit ``shard=(rank, world_size)``
+        -- rank r processes tiles r, r + world, ... of the slide (no collective on the tile path), the per-tile cell records
+        are gathered on rank 0 and merged in dataset order, and rank 0 alone runs the cross-tile duplicate removal and
+        writes the files: the output is identical to the single-process run. The other ranks return ``None``."""
         import json
         import os
         from torch.utils.data import DataLoader
@@ -263,8 +268,13 @@ class CellSegmentationInference:
         dataset = PatchedWSIInference(wsi, transform=InferenceTransform(self.mean, self.std, as_uint8=uint8_tiles))
         if num_workers is None:
             num_workers = int(np.clip(int(3 / 4 * (os.cpu_count() or 16)), 1, 2 * batch_size))
-        loader = DataLoader(dataset, batch_size=batch_size, num_workers=num_workers, shuffle=False,
-                            collate_fn=dataset.collate_batch, pin_memory=True)
+        if shard is None:
+            import torch.distributed as dist
+            shard = (dist.get_rank(), dist.get_world_size()) if dist.is_available() and dist.is_initialized() else (0, 1)
+        rank, world = shard
+        my_tiles = shard_indices(len(dataset), rank, world)
+        loader = DataLoader(dataset if world == 1 else torch.utils.data.Subset(dataset, my_tiles), batch_size=batch_size,
+                            num_workers=num_workers, shuffle=False, collate_fn=dataset.collate_batch, pin_memory=True)
         nuclei_types = self.run_conf.get("dataset_config", {}).get("nuclei_types", DEFAULT_NUCLEI_TYPES)
         background = nuclei_types.get("Background", 0)
         outdir = Path(wsi.patched_slide_path) / "cell_detection"
@@ -274,15 +284,15 @@ class CellSegmentationInference:
 
         import time
         t_start = time.perf_counter()
-        cell_dict_wsi, cell_dict_detection, processed_patches = [], [], []
-        tokens_all, positions_all, contours_all = [], [], []
+        bundles = []   # one per tile, in this rank's tile order: (patch id, records, detection records, positions, contours, tokens)
         scale, psize = wsi.metadata["downsampling"], wsi.metadata["patch_size"]
         t_records = 0.0
         for metadata, tiles, toks in self._pipeline(loader, wsi.metadata["magnification"], head_override, with_tokens=True, raw=True):
             t_rec0 = time.perf_counter()
             for meta, tc, tok in zip(metadata, tiles, toks):
                 row, col = meta["row"], meta["col"]
-                processed_patches.append(f"{row}_{col}")
+                bundle = {"patch": f"{row}_{col}", "cells": [], "detection": [], "positions": None, "contours": None, "tokens": None}
+                bundles.append(bundle)
                 x_global = int(row * psize * scale - (row + 0.5) * overlap)      # :343-350 (x follows the tile ROW)
                 y_global = int(col * psize * scale - (col + 0.5) * overlap)
                 offset_global = np.array([x_global, y_global])
@@ -319,13 +329,36 @@ class CellSegmentationInference:
                         cell_dict["edge_information"] = {"position": position, "edge_patches": get_edge_patch(position, row, col)}
                     else:
                         cell_dict["edge_position"] = False
-                    cell_dict_wsi.append(cell_dict)
-                    cell_dict_detection.append({"bbox": cell_dict["bbox"], "centroid": cell_dict["centroid"], "type": types[n]})
-                positions_all.append(torch.from_numpy(cent_np).to(torch.float32))
-                contours_all.extend(torch.from_numpy(cont_np).to(torch.float32).split_with_sizes(lens))  # (Tensor.split is 10x slower)
-                tokens_all.append(torch.from_numpy(tok[tc.valid[sel]]))
+                    bundle["cells"].append(cell_dict)
+                    bundle["detection"].append({"bbox": cell_dict["bbox"], "centroid": cell_dict["centroid"], "type": types[n]})
+                bundle["positions"] = torch.from_numpy(cent_np).to(torch.float32)
+                bundle["contours"] = (torch.from_numpy(cont_np).to(torch.float32), lens)
+                bundle["tokens"] = torch.from_numpy(tok[tc.valid[sel]])
             t_records += time.perf_counter() - t_rec0
 
+        if world > 1:   # gather the per-tile records on rank 0 and restore the dataset order
+            import torch.distributed as dist
+            gathered = [None] * world if rank == 0 else None
+            if str(self.device).startswith("cuda"):   # NCCL stages the pickled records through the current device
+                with torch.cuda.device(torch.device(self.device)):
+                    dist.gather_object(bundles, gathered, dst=0)
+            else:
+                dist.gather_object(bundles, gathered, dst=0)
+            if rank != 0:
+                self.last_timings = {"tiles": time.perf_counter() - t_start, "of_which_cell_records": t_records}
+                return None
+            by_tile = {t: b for r in range(world) for t, b in zip(shard_indices(len(dataset), r, world), gathered[r])}
+            bundles = [by_tile[t] for t in range(len(dataset))]
+        cell_dict_wsi, cell_dict_detection, processed_patches = [], [], []
+        tokens_all, positions_all, contours_all = [], [], []
+        for b in bundles:
+            processed_patches.append(b["patch"])
+            if b["cells"]:
+                cell_dict_wsi.extend(b["cells"])
+                cell_dict_detection.extend(b["detection"])
+                positions_all.append(b["positions"])
+                contours_all.extend(b["contours"][0].split_with_sizes(b["contours"][1]))  # (Tensor.split is 10x slower)
+                tokens_all.append(b["tokens"])
         t_tiles = time.perf_counter()
         keep_idx = self.post_process_edge_cells(cell_dict_wsi)
         t_dedup = time.perf_counter()

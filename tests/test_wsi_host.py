@@ -197,3 +197,46 @@ def test_convert_geojson_layout():
     det = CellSegmentationInference.convert_geojson(cells, False)
     assert det[0]["geometry"] == {"type": "MultiPoint", "coordinates": [[11.0, 10.0]]}
     assert det[1]["properties"]["classification"]["color"] == [34, 221, 77]
+
+
+_GLOO_WSI = r"""
+import gzip, json, pathlib, sys, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, sys.argv[1] + "/tests")
+from oracle import wsi_fixture as wf
+from wsi_host_harness import run_host_process_wsi
+dist.init_process_group("gloo")
+rank = dist.get_rank()
+root = pathlib.Path(sys.argv[2])
+out_dir, out = run_host_process_wsi(root, wf.make_canvas(), subdir="sharded")     # shard taken from torch.distributed
+dist.barrier()
+if rank == 0:
+    golden = json.loads(gzip.open(sys.argv[1] + "/tests/golden/wsi_2x2_cells.json.gz").read())
+    cells = json.load(open(out_dir / "cells.json"))
+    assert cells["processed_patches"] == golden["processed_patches"] and cells["cells"] == golden["cells"]
+    assert out["cells"] == golden["cells"]
+    graph = torch.load(out_dir / "cells.pt", weights_only=False)
+    assert graph.x.shape[0] == len(golden["cells"]) == len(graph.contours)
+    assert graph.positions.tolist() == [[float(torch.tensor(v, dtype=torch.float32)) for v in c["centroid"]] for c in golden["cells"]]
+else:
+    assert out is None
+dist.destroy_process_group()
+print("ok", rank)
+"""
+
+
+def test_process_wsi_sharded_over_two_ranks_equals_reference_golden(tmp_path):
+    """world_size 2 (gloo): each rank processes every second tile of the synthetic slide, rank 0 gathers the records, removes
+    the cross-tile duplicates and writes the files -- identical to the reference's single-process output (the golden)."""
+    import subprocess
+    import sys
+    from oracle import wsi_fixture as wf
+    root = tmp_path / "slide"
+    wf.make_slide(root)
+    script = tmp_path / "gloo_wsi.py"
+    script.write_text(_GLOO_WSI)
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29617", str(script), repo, str(root)], capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert r.stdout.count("ok") == 2
