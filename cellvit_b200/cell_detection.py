@@ -259,10 +259,25 @@ class CellSegmentationInference:
         -- rank r processes tiles r, r + world, ... of the slide (no collective on the tile path), the per-tile cell records
         are gathered on rank 0 and merged in dataset order, and rank 0 alone runs the cross-tile duplicate removal and
         writes the files: the output is identical to the single-process run. The other ranks return ``None``."""
+        import gc
+        # The per-cell records are millions of small acyclic lists / dicts: every container allocation counts towards the
+        # cyclic collector's thresholds and its full passes re-traverse all of them (measured: 4x on the record loop, 2x on
+        # the export). Nothing here creates reference cycles, so the collector is paused for the duration of the call.
+        gc_was_enabled = gc.isenabled()
+        gc.disable()
+        try:
+            return self._process_wsi(wsi, subdir_name, patch_size, overlap, batch_size, geojson, num_workers, head_override,
+                                     json_indent, uint8_tiles, shard)
+        finally:
+            if gc_was_enabled:
+                gc.enable()
+
+    def _process_wsi(self, wsi, subdir_name, patch_size, overlap, batch_size, geojson, num_workers, head_override, json_indent,
+                     uint8_tiles, shard):
         import json
         import os
         from torch.utils.data import DataLoader
-        from .wsi_datamodel import CellGraphDataWSI, InferenceTransform, PatchedWSIInference
+        from .wsi_datamodel import CellGraphDataWSI, InferenceTransform, PatchedWSIInference, SplitTensorList
         from .wsi_merge import cell_status_batch, get_cell_position, get_edge_patch
 
         dataset = PatchedWSIInference(wsi, transform=InferenceTransform(self.mean, self.std, as_uint8=uint8_tiles))
@@ -350,14 +365,15 @@ class CellSegmentationInference:
             by_tile = {t: b for r in range(world) for t, b in zip(shard_indices(len(dataset), r, world), gathered[r])}
             bundles = [by_tile[t] for t in range(len(dataset))]
         cell_dict_wsi, cell_dict_detection, processed_patches = [], [], []
-        tokens_all, positions_all, contours_all = [], [], []
+        tokens_all, positions_all, contour_pts, contour_lens = [], [], [], []
         for b in bundles:
             processed_patches.append(b["patch"])
             if b["cells"]:
                 cell_dict_wsi.extend(b["cells"])
                 cell_dict_detection.extend(b["detection"])
                 positions_all.append(b["positions"])
-                contours_all.extend(b["contours"][0].split_with_sizes(b["contours"][1]))  # (Tensor.split is 10x slower)
+                contour_pts.append(b["contours"][0])
+                contour_lens.extend(b["contours"][1])
                 tokens_all.append(b["tokens"])
         t_tiles = time.perf_counter()
         keep_idx = self.post_process_edge_cells(cell_dict_wsi)
@@ -366,7 +382,15 @@ class CellSegmentationInference:
         cell_dict_detection = [cell_dict_detection[i] for i in keep_idx]
         tokens_cat = torch.cat(tokens_all) if tokens_all else torch.zeros(0, self.model.embed_dim)
         positions_cat = torch.cat(positions_all) if positions_all else torch.zeros(0, 2)
-        graph = CellGraphDataWSI(x=tokens_cat[keep_idx], positions=positions_cat[keep_idx], contours=[contours_all[i] for i in keep_idx],
+        lens_np = np.asarray(contour_lens, dtype=np.int64)
+        keep_np = np.asarray(keep_idx, dtype=np.int64)
+        lens_kept = lens_np[keep_np]
+        # rows of the concatenated contour points that belong to the kept cells, in keep order
+        src_start, dst_start = (np.cumsum(lens_np) - lens_np)[keep_np], np.cumsum(lens_kept) - lens_kept
+        gather = np.repeat(src_start - dst_start, lens_kept) + np.arange(int(lens_kept.sum()), dtype=np.int64)
+        pts_cat = torch.cat(contour_pts) if contour_pts else torch.zeros(0, 2)
+        graph = CellGraphDataWSI(x=tokens_cat[keep_idx], positions=positions_cat[keep_idx],
+                                 contours=SplitTensorList(pts_cat[torch.from_numpy(gather)], lens_kept.tolist()),
                                  metadata={"wsi_metadata": wsi.metadata, "nuclei_types": nuclei_types})
 
         out_wsi = {"wsi_metadata": wsi.metadata, "processed_patches": processed_patches, "type_map": nuclei_types, "cells": cell_dict_wsi}

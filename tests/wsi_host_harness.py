@@ -10,7 +10,8 @@ from oracle import wsi_fixture as wf
 from oracle.wsi_fixture import D, NUCLEI_TYPES, OV, TILE
 
 
-def run_host_process_wsi(root, canvas, subdir="ours", shard=None):
+def make_host_inference(canvas, cache=None):
+    """CellSegmentationInference whose device stage yields oracle cells (``cache``: tile index -> cells, reused across calls)."""
     from cellvit_b200 import wsi_merge as wm
     from cellvit_b200.cell_detection import CellSegmentationInference
     from cellvit_b200.post_proc_cellvit import ROW_DTYPE, TileCells
@@ -18,6 +19,14 @@ def run_host_process_wsi(root, canvas, subdir="ours", shard=None):
     from oracle import postproc_oracle as po
 
     def tile_cells(idx):
+        if cache is not None and idx in cache:
+            return cache[idx]
+        out = _tile_cells(idx)
+        if cache is not None:
+            cache[idx] = out
+        return out
+
+    def _tile_cells(idx):
         np_bin, nt, hv = wf.tile_maps(canvas, idx)
         pm = np.concatenate([nt[..., None], np_bin[..., None], hv.transpose(1, 2, 0)], -1).astype(np.float64)
         _, inst = po.DetectionCellPostProcessor(6, 40).post_process_cell_segmentation(pm)
@@ -55,6 +64,12 @@ def run_host_process_wsi(root, canvas, subdir="ours", shard=None):
     inf.model = types.SimpleNamespace(embed_dim=D)
     inf._pipeline = pipeline
     inf.post_process_edge_cells = lambda cell_list: wm.CellPostProcessor(cell_list, None, None, overlap_fn=host_overlap).post_process_cells()
+    return inf
+
+
+def run_host_process_wsi(root, canvas, subdir="ours", shard=None):
+    from cellvit_b200.wsi_datamodel import WSI
+    inf = make_host_inference(canvas)
     wsi = WSI(name="slide", patient="p", slide_path=root, patched_slide_path=root)
     out = inf.process_wsi(wsi, subdir_name=subdir, patch_size=TILE, overlap=OV, batch_size=2, geojson=True, num_workers=0, shard=shard)
     return root / "cell_detection" / subdir, out
