@@ -177,3 +177,23 @@ def test_world_size_2_gloo_broadcast_and_sharding(tmp_path):
                         "--master-port", "29611", str(script), ROOT], capture_output=True, text=True, env=env, timeout=300)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert r.stdout.count("ok") == 2
+
+
+def test_public_header_is_plain_c(tmp_path):
+    """include/cellvit_b200.h is the drop-in boundary: it must compile as strict C99 (no C++-isms, no CUDA or torch headers) and
+    a C translation unit calling through it must link against the shared library."""
+    from cellvit_b200 import build
+    lib = build.build()
+    src = tmp_path / "boundary.c"
+    src.write_text('#include "cellvit_b200.h"\n#include <stdio.h>\n'
+                   'int main(void) {\n'
+                   '    size_t need = 0;\n'
+                   '    if (cvb_postproc_workspace_bytes(0, 1024, 1024, &need) != CVB_EARG) return 2;   /* no GPU needed */\n'
+                   '    printf("%d %s\\n", cvb_version(), cvb_last_error());\n'
+                   '    return 0;\n}\n')
+    exe = tmp_path / "boundary"
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                        lib, f"-Wl,-rpath,{os.path.dirname(lib)}"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    run = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert run.returncode == 0 and run.stdout.split()[0] == "100", (run.returncode, run.stdout, run.stderr)

@@ -240,3 +240,22 @@ def test_process_wsi_sharded_over_two_ranks_equals_reference_golden(tmp_path):
                         "--master-port", "29617", str(script), repo, str(root)], capture_output=True, text=True, env=env, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert r.stdout.count("ok") == 2
+
+
+def test_process_wsi_on_a_slide_without_cells(tmp_path):
+    """No nucleus anywhere: every export file is still written, with empty cell lists and an empty graph (the reference
+    raises in ``torch.stack([])`` here, cell_detection.py:462; an empty result is the useful behaviour)."""
+    from oracle import wsi_fixture as wf
+    from wsi_host_harness import run_host_process_wsi
+    root = tmp_path / "slide"
+    wf.make_slide(root)
+    side = wf.GRID * (wf.TILE - wf.OV) + 2 * wf.OV
+    canvas = {"np_bin": np.zeros((side, side), np.float32), "nt": np.zeros((side, side), np.float32),
+              "hv": np.zeros((2, side, side), np.float32)}
+    out_dir, out = run_host_process_wsi(root, canvas, subdir="empty")
+    assert out["cells"] == [] and out["processed_patches"] == ["0_0", "0_1", "1_0", "1_1"]
+    for name in ("cells.json", "cell_detection.json", "cells.geojson", "cell_detection.geojson"):
+        data = json.load(open(out_dir / name))
+        assert (data["cells"] if isinstance(data, dict) else data) == []
+    graph = torch.load(out_dir / "cells.pt", weights_only=False)
+    assert graph.x.shape[0] == 0 and graph.positions.shape[0] == 0 and list(graph.contours) == []

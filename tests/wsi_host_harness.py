@@ -32,7 +32,7 @@ def make_host_inference(canvas, cache=None):
         _, inst = po.DetectionCellPostProcessor(6, 40).post_process_cell_segmentation(pm)
         n = len(inst)
         rows = np.zeros(n, ROW_DTYPE)
-        cap = max(len(c["contour"]) for c in inst.values())
+        cap = max([len(c["contour"]) for c in inst.values()], default=1)
         pts, npts = np.zeros((n, cap, 2), np.int16), np.zeros(n, np.int32)
         tokens = wf.tile_tokens(idx)
         pooled = np.zeros((n, D), np.float32)
