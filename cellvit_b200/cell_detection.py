@@ -434,3 +434,22 @@ class CellSegmentationInference:
                                "classification": {"name": TYPE_NUCLEI_DICT[cell_type], "color": COLOR_DICT[cell_type]}},
             })
         return features
+
+
+def check_wsi(wsi, magnification: float = 40.0) -> None:
+    """cell_detection.py:1008-1039 -- refuse a preprocessed slide whose tiling does not fit the network: ``RuntimeError`` if the
+    tile magnification (``metadata["magnification"]``, else ``base_magnification / downsampling``) differs from
+    ``magnification``, or the tiles are not 1024 px with a 64 px overlap. Same messages as the reference."""
+    meta = wsi.metadata
+    if meta["magnification"] is not None:
+        tile_magnification = float(meta["magnification"])
+    else:
+        tile_magnification = float(float(meta["base_magnification"]) / meta["downsampling"])
+    if tile_magnification != magnification:
+        raise RuntimeError("The magnification is not matching to the network input magnification.")
+    if int(meta["patch_size"]) % 256 != 0:
+        raise RuntimeError("The patch-size must be devisible by 256.")
+    if meta["patch_size"] != 1024:
+        raise RuntimeError("The patch-size must be 1024.")
+    if meta["patch_overlap"] != 64:
+        raise RuntimeError("The patch-overlap must be 64")

@@ -148,3 +148,29 @@ def test_cell_post_processor_matches_reference_control_flow(grid, seed):
     mine = wm.CellPostProcessor(cells, overlap_fn=host_overlap).post_process_cells()
     assert len(ref_keep) < len(cells)            # duplicates were removed
     assert mine == [int(i) for i in ref_keep]
+
+
+def test_check_wsi_matches_reference():
+    """check_wsi (cell_detection.py:1008-1039): same accept / RuntimeError(message) decisions as the reference's function."""
+    import types
+    from cellvit_b200.cell_detection import check_wsi
+    ref_cd = ref_shim.import_reference_cell_detection()
+    base = {"magnification": 40, "base_magnification": 40, "downsampling": 1, "patch_size": 1024, "patch_overlap": 64}
+    cases = [({}, 40.0), ({"magnification": None}, 40.0), ({"magnification": None, "downsampling": 2}, 40.0), ({"magnification": 20}, 40.0),
+             ({"magnification": 20}, 20.0), ({"patch_size": 512}, 40.0), ({"patch_size": 1000}, 40.0), ({"patch_size": 2048}, 40.0),
+             ({"patch_overlap": 0}, 40.0), ({"magnification": "40"}, 40.0)]
+
+    def outcome(fn, meta, mag):
+        try:
+            fn(types.SimpleNamespace(metadata=dict(meta)), mag)
+            return None
+        except RuntimeError as e:
+            return str(e)
+
+    seen = set()
+    for delta, mag in cases:
+        meta = dict(base, **delta)
+        got, want = outcome(check_wsi, meta, mag), outcome(ref_cd.check_wsi, meta, mag)
+        assert got == want, (meta, mag, got, want)
+        seen.add(want)
+    assert len(seen) == 5     # accepted + the four distinct refusals
