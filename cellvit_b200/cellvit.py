@@ -229,15 +229,22 @@ class CellViT(nn.Module):
         return torch.Tensor(labels.cpu().numpy()).type(torch.float32), dicts
 
     def generate_instance_nuclei_map(self, instance_maps: torch.Tensor, type_preds: List[dict]) -> torch.Tensor:
-        """cellvit.py:385-414."""
+        """cellvit.py:385-414 -- [B, num_nuclei_classes, H, W] float32: plane ``type`` holds the instance id on the pixels of
+        every instance listed in ``type_preds[b]``; instances without a dict entry stay 0. One id -> type table lookup and
+        one scatter per tile instead of the reference's full-image compare per instance (same result)."""
         batch_size, hh, ww = instance_maps.shape
-        out = torch.zeros((batch_size, hh, ww, self.num_nuclei_classes))
+        out = torch.zeros((batch_size, self.num_nuclei_classes, hh, ww))
         for i in range(batch_size):
-            inst = torch.zeros((hh, ww, self.num_nuclei_classes))
+            lab = instance_maps[i].to("cpu", torch.int64)
+            type_of = torch.full((int(lab.max()) + 2,), -1, dtype=torch.int64)
             for nuclei, spec in type_preds[i].items():
-                inst[:, :, spec["type"]][instance_maps[i] == nuclei] = nuclei
-            out[i] = inst
-        return out.permute(0, 3, 1, 2)
+                if 0 <= int(nuclei) < len(type_of):
+                    type_of[int(nuclei)] = int(spec["type"])
+            plane = type_of[lab.clamp(min=0)]
+            plane[lab < 0] = -1
+            listed = plane >= 0
+            out[i].scatter_(0, plane.clamp(min=0).unsqueeze(0), (lab * listed).to(torch.float32).unsqueeze(0))
+        return out
 
     def freeze_encoder(self):
         """cellvit.py:416-420 (the tissue head stays trainable)."""

@@ -174,3 +174,28 @@ def test_check_wsi_matches_reference():
         assert got == want, (meta, mag, got, want)
         seen.add(want)
     assert len(seen) == 5     # accepted + the four distinct refusals
+
+
+def test_generate_instance_nuclei_map_matches_reference(ref):
+    """F8 (cellvit.py:385-414): the table-lookup + scatter formulation against the reference's per-instance loop, including an
+    instance that is in the label map but not in the dict and a dict entry whose id is absent from the map."""
+    import types
+    from cellvit_b200.cellvit import CellViT
+    ref_cellvit = ref[0]
+    rng = np.random.default_rng(4)
+    B, H, W, C = 2, 96, 80, 6
+    labels = np.zeros((B, H, W), np.int64)
+    dicts = []
+    for b in range(B):
+        ids = [3, 4, 9, 17, 40]
+        for k, i in enumerate(ids):
+            labels[b, 10 + 15 * k: 20 + 15 * k, 5 + 7 * b: 40 + 7 * b] = i
+        d = {np.int32(i): {"type": int(rng.integers(0, C))} for i in ids if i != 9}     # 9: traced contour too short -> not listed
+        d[np.int32(77)] = {"type": 2}                                                     # listed but not present
+        dicts.append(d)
+    lab_t = torch.tensor(labels, dtype=torch.float32)          # calculate_instance_map returns float32 label maps
+    stand_in = types.SimpleNamespace(num_nuclei_classes=C)
+    want = ref_cellvit.CellViT.generate_instance_nuclei_map(stand_in, lab_t, dicts)
+    got = CellViT.generate_instance_nuclei_map(stand_in, lab_t, dicts)
+    assert got.dtype == want.dtype and got.shape == want.shape == (B, C, H, W)
+    assert torch.equal(got, want) and got.sum() > 0
