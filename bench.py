@@ -184,6 +184,16 @@ def run_gpu(args):
     s_post = torch.cuda.Stream(dev)
     main = torch.cuda.current_stream(dev)
 
+    gather = None
+    if world > 1 and args.gather_every > 1:
+        from cellvit_b200.cell_detection import TableGather
+        gather = TableGather(world, B, 1024, 88, args.gather_every, dev)
+
+    def flush_gather():
+        if gather is not None:
+            with torch.cuda.stream(s_post):
+                gather.flush()
+
     def step_device():
         # forward of batch k on the main stream; post-processing of batch k on a second stream once that forward has
         # finished (the dependency of the real pipeline), so it overlaps the forward of batch k+1 -- the same
@@ -201,7 +211,9 @@ def run_gpu(args):
             L.check(lib.cvb_postproc(L.ptr(np_dev), L.ptr(hv_dev), L.ptr(nt_dev), B, TILE, TILE, 6, 40, L.ptr(w.labels), L.ptr(w.table),
                                      L.ptr(w.counts), proc.max_rows, L.ptr(w.ws), C.c_size_t(w.ws.numel()), L.stream_ptr()), "cvb_postproc")
             w.launch_contours(B, TILE, TILE, proc.max_rows)   # per-instance contours on the device (cvb_contours)
-            if world > 1:  # collective C2: all-gather of the per-tile instance tables (counts, then the first 1024 rows)
+            if gather is not None:  # collective C2 staged and exchanged once per --gather-every steps
+                gather.add(w.counts, w.table)
+            elif world > 1:  # collective C2: all-gather of the per-tile instance tables (counts, then the first 1024 rows)
                 cnts = [torch.empty_like(w.counts) for _ in range(world)]
                 dist.all_gather(cnts, w.counts)
                 part = w.table[:, :1024].contiguous()
@@ -232,6 +244,7 @@ def run_gpu(args):
     sampler = ClockSampler(local) if rank == 0 else None
     for _ in range(Wm):
         step_device()
+    flush_gather()
     main.wait_stream(s_post)
     sync_all()
     lib.cvb_launch_count(1)
@@ -239,6 +252,7 @@ def run_gpu(args):
     e0.record()
     for _ in range(K):
         step_device()
+    flush_gather()            # (chunked exchange: the tail of the stream is gathered inside the timed region)
     main.wait_stream(s_post)  # the timed region ends when the last batch's post-processing has finished
     e1.record()
     sync_all()
@@ -307,7 +321,7 @@ def run_gpu(args):
                                    f"post-processing on injected synthetic-nuclei head maps ({N_NUCLEI} nuclei/tile); random-init weights",
                        "l2": "per-step working set (1.4 GB fp16 weights + >10 GB activations) exceeds the 126 MB L2; no explicit flush",
                        "forward_launch": "CUDA graph replay" if args.graphs else "eager",
-                       "parallelism": f"tiles sharded over {world} GPU(s), NCCL weight broadcast" + (", per-step all-gather of instance tables" if world > 1 else "")},
+                       "parallelism": f"tiles sharded over {world} GPU(s), NCCL weight broadcast" + ((", per-step all-gather of instance tables" if args.gather_every <= 1 else f", instance tables all-gathered every {args.gather_every} steps") if world > 1 else "")},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "tiles/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke,
                     "api": "CellSegmentationInference.process_tiles: H2D + forward + softmax + device post-processing + D2H + host dicts (3 streams, 2-deep pipeline)"},
@@ -323,6 +337,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--graphs", type=int, default=1, help="1 (default): the forward is replayed from a CUDA graph, as in the product pipeline; 0: eager launches")
+    ap.add_argument("--gather-every", type=int, default=1, help="N>1 only: exchange the instance tables once per this many steps (TableGather) instead of "
+                    "two all-gathers per step (default 1 = per step; the chunked exchange is not measured yet)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling / quick iteration runs)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup

@@ -82,6 +82,46 @@ def broadcast_weights(model: torch.nn.Module, src: int = 0) -> None:
         o += n
 
 
+class TableGather:
+    """Collective C2 in chunks: the per-tile instance tables of several steps are staged in one device buffer and exchanged
+    with ONE all-gather per ``chunk`` steps (and once more at the end of the stream) instead of two collectives per step --
+    a collective's CTAs spin on SMs until every peer has arrived, and the persistent tile engine needs all of them.
+
+    Layout of one staged step: ``[B, 4 + rows * row_bytes]`` uint8 -- per tile its int32 instance count, then the first
+    ``rows`` table rows. Every rank must call ``add`` / ``flush`` the same number of times."""
+
+    def __init__(self, world: int, B: int, rows: int, row_bytes: int, chunk: int, device):
+        self.world, self.B, self.rows, self.row_bytes, self.chunk = world, B, rows, row_bytes, max(1, int(chunk))
+        self.staged = torch.zeros(self.chunk, B, 4 + rows * row_bytes, dtype=torch.uint8, device=device)
+        self.gathered = torch.zeros(world, self.chunk, B, 4 + rows * row_bytes, dtype=torch.uint8, device=device)
+        self.n = 0
+        self.n_gathered = 0
+        self.collectives = 0
+
+    def add(self, counts: torch.Tensor, table: torch.Tensor) -> None:
+        """``counts`` int32 [B], ``table`` uint8 [B, max_rows, row_bytes] (device); copies are enqueued on the current stream."""
+        slot = self.staged[self.n]
+        slot[:, :4].copy_(counts.view(torch.uint8).view(self.B, 4))
+        slot[:, 4:].copy_(table[:, :self.rows].reshape(self.B, -1))
+        self.n += 1
+        if self.n == self.chunk:
+            self.flush()
+
+    def flush(self) -> None:
+        if self.n == 0:
+            return
+        import torch.distributed as dist
+        dist.all_gather_into_tensor(self.gathered.view(self.world * self.chunk, self.B, -1), self.staged)
+        self.n_gathered, self.n = self.n, 0
+        self.collectives += 1
+
+    def tables(self, rank: int, step: int):
+        """(counts int32 [B], rows uint8 [B, rows, row_bytes]) of ``rank`` for staged step ``step`` of the last exchange."""
+        assert 0 <= step < self.n_gathered
+        g = self.gathered[rank, step]
+        return g[:, :4].contiguous().view(torch.int32).view(self.B), g[:, 4:].view(self.B, self.rows, self.row_bytes)
+
+
 class CellSegmentationInference:
     def __init__(self, model_path: Union[Path, str, dict], gpu: int, enforce_mixed_precision: bool = False) -> None:
         """cell_detection.py:93-115. ``model_path`` may also be an already loaded checkpoint dict."""

@@ -164,6 +164,31 @@ for i in mine:
     counts[i] = 100 + i
 dist.all_reduce(counts)
 assert counts.tolist() == [100 + i for i in range(n_tiles)]
+# chunked exchange of instance tables: 5 steps with a chunk of 4 -> one collective after step 4 and one at the flush
+from cellvit_b200.cell_detection import TableGather
+B, rows, rb = 3, 8, 88
+g = TableGather(world, B, rows, rb, 4, "cpu")
+def fake(r, step):
+    gen = torch.Generator().manual_seed(1000 * r + step)
+    return (torch.randint(0, 9, (B,), generator=gen, dtype=torch.int32),
+            torch.randint(0, 256, (B, 16, rb), generator=gen, dtype=torch.uint8))
+for step in range(5):
+    g.add(*fake(rank, step))
+    if step == 3:
+        assert g.collectives == 1 and g.n_gathered == 4
+        for r in range(world):
+            for k in range(4):
+                c, t = g.tables(r, k)
+                wc, wt = fake(r, k)
+                assert torch.equal(c, wc) and torch.equal(t, wt[:, :rows])
+g.flush()
+assert g.collectives == 2 and g.n_gathered == 1
+for r in range(world):
+    c, t = g.tables(r, 0)
+    wc, wt = fake(r, 4)
+    assert torch.equal(c, wc) and torch.equal(t, wt[:, :rows])
+g.flush()
+assert g.collectives == 2
 dist.destroy_process_group()
 print("ok", rank)
 '''
