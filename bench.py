@@ -39,6 +39,9 @@ TILE = 1024
 BATCH = 4
 N_NUCLEI = 700
 METRIC = "1024x1024 tiles/sec (CellViT-SAM-H inference+postproc)"
+# the workload both arms run (config.workload); the arms differ only in how many tiles make one step
+WORKLOAD = (f"CellViT-{ARCH} inference + HV watershed post-processing on injected synthetic-nuclei head maps ({N_NUCLEI} nuclei/tile), "
+            f"synthetic {TILE}x{TILE} tiles, random-init weights")
 # algorithmic GFLOP per SAM-H tile (shared skip decoders once) and the share that runs in
 # the tile-engine kernel (everything except the attention core QK^T / PV / rel-pos einsums: 28*5.3 + 4*87.2 G).
 GFLOP_PER_TILE = 9816.8
@@ -129,9 +132,9 @@ def run_reference(args):
     v = steps / el
     sample = f"{steps} tile(s) of 1 (steps capped by a {budget:.0f}s budget); forward {tf2:.2f}s + postproc {tp2:.2f}s per tile"
     print(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": v, "unit": "tiles/s", "n_gpus": 0, "steps": steps, "warmup": 1,
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "tiles/s", "n_gpus": args.gpus, "steps": steps, "warmup": 1,
         "ms_per_step": 1000.0 * el / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic", "config": {"workload": f"CellViT-{ARCH} inference + post-processing, 1 synthetic {TILE}x{TILE} tile per step, CPU"},
+        "data": "synthetic", "config": {"workload": WORKLOAD, "batch": "1 tile per step on the host cores (bounded sample, no GPU used)"},
         "cpu_baseline": {"value": v, "unit": "tiles/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "tiles/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}))
 
@@ -317,8 +320,7 @@ def run_gpu(args):
             "metric": METRIC, "value": value, "unit": "tiles/s", "n_gpus": world, "steps": K, "warmup": Wm,
             "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16",
             "data": "synthetic",
-            "config": {"workload": f"CellViT-{ARCH} inference, batch={B} synthetic {TILE}x{TILE} tiles per GPU per step, on-GPU HV watershed "
-                                   f"post-processing on injected synthetic-nuclei head maps ({N_NUCLEI} nuclei/tile); random-init weights",
+            "config": {"workload": WORKLOAD, "batch": f"{B} tiles per GPU per step, post-processing on the GPU",
                        "l2": "per-step working set (1.4 GB fp16 weights + >10 GB activations) exceeds the 126 MB L2; no explicit flush",
                        "forward_launch": "CUDA graph replay" if args.graphs else "eager",
                        "parallelism": f"tiles sharded over {world} GPU(s), NCCL weight broadcast" + ((", per-step all-gather of instance tables" if args.gather_every <= 1 else f", instance tables all-gathered every {args.gather_every} steps") if world > 1 else "")},
