@@ -259,3 +259,22 @@ def test_process_wsi_on_a_slide_without_cells(tmp_path):
         assert (data["cells"] if isinstance(data, dict) else data) == []
     graph = torch.load(out_dir / "cells.pt", weights_only=False)
     assert graph.x.shape[0] == 0 and graph.positions.shape[0] == 0 and list(graph.contours) == []
+
+
+def test_inference_transform_is_bit_identical_to_torchvision():
+    """``InferenceTransform`` == ``T.Compose([T.ToTensor(), T.Normalize(mean, std)])`` (cell_detection.py:214-227) bit for
+    bit, for RGB, RGBA and grayscale PIL inputs and for non-default statistics."""
+    T = pytest.importorskip("torchvision.transforms")
+    from PIL import Image
+    from cellvit_b200.wsi_datamodel import InferenceTransform
+    rng = np.random.default_rng(7)
+    for mean, std in [((0.5, 0.5, 0.5), (0.5, 0.5, 0.5)), ((0.485, 0.456, 0.406), (0.229, 0.224, 0.225))]:
+        want_fn = T.Compose([T.ToTensor(), T.Normalize(mean=mean, std=std)])
+        got_fn = InferenceTransform(mean, std)
+        img = Image.fromarray(rng.integers(0, 256, (64, 48, 3), dtype=np.uint8))
+        assert torch.equal(got_fn(img), want_fn(img))
+        rgba = Image.fromarray(rng.integers(0, 256, (32, 32, 4), dtype=np.uint8), mode="RGBA")
+        assert torch.equal(got_fn(rgba), want_fn(rgba.convert("RGB")))       # the alpha plane is dropped, as PNG tiles are RGB
+    # every uint8 value through both: the float path is ToTensor's x / 255 followed by (x - mean) / std
+    ramp = Image.fromarray(np.arange(256, dtype=np.uint8).reshape(16, 16, 1).repeat(3, 2))
+    assert torch.equal(InferenceTransform()(ramp), T.Compose([T.ToTensor(), T.Normalize((0.5,) * 3, (0.5,) * 3)])(ramp))
