@@ -278,3 +278,33 @@ def test_inference_transform_is_bit_identical_to_torchvision():
     # every uint8 value through both: the float path is ToTensor's x / 255 followed by (x - mean) / std
     ramp = Image.fromarray(np.arange(256, dtype=np.uint8).reshape(16, 16, 1).repeat(3, 2))
     assert torch.equal(InferenceTransform()(ramp), T.Compose([T.ToTensor(), T.Normalize((0.5,) * 3, (0.5,) * 3)])(ramp))
+
+
+def _star_polygon(rng, cx, cy, n, r_lo, r_hi):
+    ang = (np.arange(n) + rng.uniform(0.25, 0.75, n)) * (2 * np.pi / n)   # every angular gap < pi: star-shaped, hence simple
+    rad = rng.uniform(r_lo, r_hi, n)
+    return np.stack([cx + rad * np.cos(ang), cy + rad * np.sin(ang)], 1)
+
+
+def test_polygon_intersection_area_invariants():
+    """Size-independent properties of the overlap predicate on random simple (star-shaped) polygons: symmetry, bounded by
+    both areas, self-intersection = area, translation invariance, orientation independence, disjoint -> 0."""
+    rng = np.random.default_rng(11)
+    for trial in range(60):
+        a = _star_polygon(rng, 50 + rng.uniform(-5, 5), 50 + rng.uniform(-5, 5), int(rng.integers(4, 40)), 4, 20)
+        b = _star_polygon(rng, 50 + rng.uniform(-15, 15), 50 + rng.uniform(-15, 15), int(rng.integers(4, 40)), 4, 20)
+        if trial % 2:   # integer vertices, as contours have
+            a, b = np.round(a), np.round(b)
+            if len(np.unique(a, axis=0)) < 3 or len(np.unique(b, axis=0)) < 3:
+                continue
+        aa, ab = wm.polygon_area(a), wm.polygon_area(b)
+        i_ab, i_ba = wm.polygon_intersection_area(a, b), wm.polygon_intersection_area(b, a)
+        tol = 1e-7 * max(aa, ab, 1.0)
+        assert abs(i_ab - i_ba) <= tol
+        assert -tol <= i_ab <= min(aa, ab) + tol
+        if trial % 2 == 0:      # rounding can make a star polygon self-touching; the even-odd self-overlap is only its area when simple
+            assert abs(wm.polygon_intersection_area(a, a) - aa) <= tol
+        shift = np.array([1000.0, -250.0])
+        assert abs(wm.polygon_intersection_area(a + shift, b + shift) - i_ab) <= 1e-6 * max(aa, ab, 1.0)
+        assert abs(wm.polygon_intersection_area(a[::-1], b) - i_ab) <= tol
+        assert wm.polygon_intersection_area(a, b + np.array([500.0, 0.0])) == 0.0
