@@ -23,13 +23,13 @@ def make_canvas():
     side = GRID * (TILE - OV) + 2 * OV
     return synth.synthetic_nuclei(side, CANVAS_NUCLEI, seed=CANVAS_SEED)
 
-def make_slide(root):
+def make_slide(root, magnification=40, downsampling=1):
     """grid x grid PNG tiles whose red channel at pixel (0, 0) holds the tile index (the stand-in networks key on it)."""
     import yaml
     from PIL import Image
     (root / "patches").mkdir(parents=True)
     (root / "metadata").mkdir()
-    yaml.safe_dump({"magnification": 40, "base_magnification": 40, "downsampling": 1, "patch_size": TILE, "patch_overlap": OV,
+    yaml.safe_dump({"magnification": magnification, "base_magnification": 40, "downsampling": downsampling, "patch_size": TILE, "patch_overlap": OV,
                     "label_map": {"background": 0}}, open(root / "metadata.yaml", "w"))
     entries, rng = [], np.random.default_rng(5)
     for r in range(GRID):

@@ -24,9 +24,10 @@ def _strip_ids(geo):
     return geo
 
 
-def test_process_wsi_files_match_reference(tmp_path):
+@pytest.mark.parametrize("magnification,downsampling", [(40, 1), (20, 2)])
+def test_process_wsi_files_match_reference(tmp_path, magnification, downsampling):
     root = tmp_path / "slide"
-    wf.make_slide(root)
+    wf.make_slide(root, magnification, downsampling)
     canvas = wf.make_canvas()
     ref_dir = wf.run_reference(root, canvas)
     our_dir, _ = run_host_process_wsi(root, canvas)
@@ -42,7 +43,8 @@ def test_process_wsi_files_match_reference(tmp_path):
     import gzip
     import pathlib
     golden = json.loads(gzip.open(pathlib.Path(__file__).parent / "golden" / "wsi_2x2_cells.json.gz").read())
-    assert golden["cells"] == cells, "tests/golden/wsi_2x2_cells.json.gz is stale: rerun tools/make_wsi_golden.py"
+    if (magnification, downsampling) == (40, 1):
+        assert golden["cells"] == cells, "tests/golden/wsi_2x2_cells.json.gz is stale: rerun tools/make_wsi_golden.py"
     assert sum(c["cell_status"] != 0 for c in cells) > 30 and sum(c["edge_position"] for c in cells) >= 1
     for name in ("cells.geojson", "cell_detection.geojson"):
         assert _strip_ids(json.load(open(ref_dir / name))) == _strip_ids(json.load(open(our_dir / name)))

@@ -18,6 +18,8 @@ def make_host_inference(canvas, cache=None):
     from cellvit_b200.wsi_datamodel import WSI
     from oracle import postproc_oracle as po
 
+    mag = [40]
+
     def tile_cells(idx):
         if cache is not None and idx in cache:
             return cache[idx]
@@ -29,7 +31,7 @@ def make_host_inference(canvas, cache=None):
     def _tile_cells(idx):
         np_bin, nt, hv = wf.tile_maps(canvas, idx)
         pm = np.concatenate([nt[..., None], np_bin[..., None], hv.transpose(1, 2, 0)], -1).astype(np.float64)
-        _, inst = po.DetectionCellPostProcessor(6, 40).post_process_cell_segmentation(pm)
+        _, inst = po.DetectionCellPostProcessor(6, mag[0]).post_process_cell_segmentation(pm)
         n = len(inst)
         rows = np.zeros(n, ROW_DTYPE)
         cap = max([len(c["contour"]) for c in inst.values()], default=1)
@@ -47,7 +49,8 @@ def make_host_inference(canvas, cache=None):
         return TileCells(None, rows, pts, npts), pooled
 
     def pipeline(loader, magnification, head_override, with_tokens=False, raw=False, **kw):
-        assert magnification == 40 and with_tokens and raw
+        assert with_tokens and raw
+        mag[0] = magnification
         for patches, metadata in loader:
             assert patches.dtype == torch.uint8          # raw tiles travel; normalisation happens on the device
             out = [tile_cells(int(p[0, 0, 0])) for p in patches]
