@@ -13,6 +13,14 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
+def _free_port() -> str:
+    """A TCP port nobody is listening on right now (the rendezvous of the world-size-2 runs must not collide with other jobs)."""
+    import socket
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return str(s.getsockname()[1])
+
+
 @pytest.fixture(scope="module")
 def lib_path():
     from cellvit_b200 import build
@@ -199,7 +207,7 @@ def test_world_size_2_gloo_broadcast_and_sharding(tmp_path):
     script.write_text(_GLOO)
     env = dict(os.environ, MASTER_ADDR="127.0.0.1")
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
-                        "--master-port", "29611", str(script), ROOT], capture_output=True, text=True, env=env, timeout=300)
+                        "--master-port", _free_port(), str(script), ROOT], capture_output=True, text=True, env=env, timeout=300)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert r.stdout.count("ok") == 2
 

@@ -14,6 +14,14 @@ from cellvit_b200 import wsi_merge as wm
 REF = "/root/reference/cell_segmentation/inference/cell_detection.py"
 
 
+def _free_port() -> str:
+    """A TCP port nobody is listening on right now (the rendezvous of the world-size-2 runs must not collide with other jobs)."""
+    import socket
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return str(s.getsockname()[1])
+
+
 def _reference_functions():
     """The three pure position helpers of the reference, compiled from its source in place (nothing is copied)."""
     tree = ast.parse(open(REF).read())
@@ -237,7 +245,7 @@ def test_process_wsi_sharded_over_two_ranks_equals_reference_golden(tmp_path):
     repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     env = dict(os.environ, MASTER_ADDR="127.0.0.1")
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
-                        "--master-port", "29617", str(script), repo, str(root)], capture_output=True, text=True, env=env, timeout=600)
+                        "--master-port", _free_port(), str(script), repo, str(root)], capture_output=True, text=True, env=env, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert r.stdout.count("ok") == 2
 
