@@ -1029,6 +1029,289 @@ window_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     if (warp == 2) ptx::tmem_dealloc(tmem_base, 512);
 }
 
+// ------------------------------------------------------------------------------------------ windowed attention, third design
+// EXPERIMENTAL -- written after the GPU budget of round 1 was spent: it compiles for sm_100a but has NOT been run yet (variant
+// 3 of cvb_set_window_tc_variant, off by default; tests/test_gpu_forward.py covers it only with CVB_EXPERIMENTAL=1).
+//
+// A window item is treated like ONE key tile of flash_tc_kernel. The scores leave the tensor core fully biased:
+//     S = [Q | Gsel] [K | Sel]^T    (5 + 2 k-steps of one UMMA 128 x 208 x 16 per query group)
+// with Gsel = [rel_h(q, kh) | rel_w(q, kw)] / scale from the pre-pass window_qg_kernel (attention.cu; its 64-column row also
+// carries Q[.][64..79], so one shared-memory box serves the fifth Q k-step and both bias k-steps) and Sel the constant 0/1
+// selection matrix (Sel[k][kh(k)] = Sel[k][14 + kw(k)] = 1), resident in shared memory. The softmax threads (one query row each)
+// make two passes over their S row in tensor memory -- running maximum, then P = 2^((s - m) scale log2 e) as packed fp16 pairs
+// (ex2.approx.f16x2) stored back IN PLACE in ascending key order: the packed chunk c (columns 16c..16c+15) lies below the
+// score chunk c (columns 32c..32c+31) that produced it -- so ~64 registers are live and no bias arithmetic is left in the
+// loop. P V is a TS-mode UMMA (A = P from tensor memory) over V^T with a ones row (row sums = output column 80); O goes to
+// columns 128..223 of the group's 256 (the score columns there are dead by then, P sits in 0..103). Shared memory is single-buffered (190 KB): Q /
+// QG / K are released as soon as both S MMAs have completed, V^T after the second P V, and the producer refills them for the
+// next item while this item's softmax and P V run.
+constexpr int W3_VR = 96;                                        // V^T rows per head: 80 + ones + 15 zero rows
+constexpr uint32_t W3_QB = FT_BQ * 128;                          // one 128-row box (16 KB)
+constexpr uint32_t W3_KB = WT_VLD * 128;                         // one 208-row box (26 KB)
+constexpr uint32_t W3_VB = W3_VR * 128;                          // one V^T box: 96 rows x 64 keys
+constexpr uint32_t W3_SMEM = 1024 + 4 * W3_QB + 3 * W3_KB + 4 * W3_VB + 512;
+constexpr uint32_t W3_O_COL = 128;                              // O columns of a group: 128..223 (32-column aligned, as in the second design)
+
+// v rows of window `item` [196, 3*D] -> vt [(head*96 + d)][item*208 + key]; row 80 = ones (keys < 196), rows 81..95 and keys
+// 196..207 zero
+__global__ void __launch_bounds__(256)
+v_transpose_win96_kernel(const __half* __restrict__ qkv, int heads, int n_items, __half* __restrict__ vt) {
+    __shared__ __half tile[WT_VLD][FT_HD + 2];
+    const int item = blockIdx.x, head = blockIdx.y;
+    const int D = heads * FT_HD;
+    const __half* src = qkv + (long long)item * WT_S * 3 * D + 2 * D + head * FT_HD;
+    for (int i = threadIdx.x; i < WT_VLD * (FT_HD / 8); i += 256) {
+        const int r = i / (FT_HD / 8), c = i - r * (FT_HD / 8);
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (r < WT_S) v = *reinterpret_cast<const uint4*>(src + (long long)r * 3 * D + c * 8);
+        const __half* h = reinterpret_cast<const __half*>(&v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) tile[r][c * 8 + j] = h[j];
+    }
+    __syncthreads();
+    const long long ld = (long long)n_items * WT_VLD;
+    __half* dst = vt + (long long)head * W3_VR * ld + (long long)item * WT_VLD;
+    for (int i = threadIdx.x; i < W3_VR * (WT_VLD / 2); i += 256) {
+        const int d = i / (WT_VLD / 2), kp = i - d * (WT_VLD / 2);
+        __half2 v = __floats2half2_rn(0.f, 0.f);
+        if (d < FT_HD) v = __halves2half2(tile[2 * kp][d], tile[2 * kp + 1][d]);
+        else if (d == FT_HD && 2 * kp < WT_S) v = __floats2half2_rn(1.f, 1.f);   // 196 is even: a pair is valid or padding as a whole
+        *reinterpret_cast<__half2*>(dst + (long long)d * ld + 2 * kp) = v;
+    }
+}
+
+// sel fp16 [208][64]: row k (a key of the 14 x 14 window) has ones at columns kh(k) and 14 + kw(k)
+__global__ void window_sel_kernel(__half* __restrict__ sel) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= WT_VLD * 64) return;
+    const int k = i >> 6, c = i & 63;
+    const int kh = k / WT_G, kw = k - kh * WT_G;
+    sel[i] = __float2half((k < WT_S && (c == kh || c == WT_G + kw)) ? 1.0f : 0.0f);
+}
+
+__global__ void __launch_bounds__(WT_THREADS, 1)
+window_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmQG,
+                  const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmK16,
+                  const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmSel, int heads, int n_items,
+                  float scale, __half* __restrict__ out) {
+    extern __shared__ uint8_t ft_smem_raw[];
+    const uint32_t smem_base = (ptx::smem_u32(ft_smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem_gen = ft_smem_raw + (smem_base - ptx::smem_u32(ft_smem_raw));
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
+    const int D = heads * FT_HD;
+    const int n_work = n_items * heads;
+
+    const uint32_t sQ0 = smem_base;               // [group] Q columns 0..63
+    const uint32_t sQG = sQ0 + 2 * W3_QB;          // [group] Q columns 64..79 | Gsel | 0
+    const uint32_t sK0 = sQG + 2 * W3_QB;          // K columns 0..63, 208 rows
+    const uint32_t sKt = sK0 + W3_KB;              // K columns 16..79 (the last k-step reads its columns 48..63)
+    const uint32_t sSel = sKt + W3_KB;
+    const uint32_t sV = sSel + W3_KB;              // 4 boxes of 64 keys
+    const uint32_t bar = sV + 4 * W3_VB;
+    const uint32_t sel_full = bar, qk_full = bar + 8, qk_free = bar + 16, v_full = bar + 24, v_free = bar + 32;
+    auto s_full = [&](int g) { return bar + 8u * (5 + g); };
+    auto p_full = [&](int g) { return bar + 8u * (7 + g); };
+    auto o_full = [&](int g) { return bar + 8u * (9 + g); };
+    auto o_free = [&](int g) { return bar + 8u * (11 + g); };
+    const uint32_t tmem_slot = bar + 8u * 13;
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tmap(&tmQ); ptx::prefetch_tmap(&tmQG); ptx::prefetch_tmap(&tmK); ptx::prefetch_tmap(&tmK16);
+        ptx::prefetch_tmap(&tmV); ptx::prefetch_tmap(&tmSel);
+    }
+    if (warp == 1 && lane == 0) {
+        ptx::mbar_init(sel_full, 1); ptx::mbar_init(qk_full, 1); ptx::mbar_init(qk_free, 1); ptx::mbar_init(v_full, 1);
+        ptx::mbar_init(v_free, 1);
+        for (int g = 0; g < 2; ++g) {
+            ptx::mbar_init(s_full(g), 1); ptx::mbar_init(p_full(g), 128); ptx::mbar_init(o_full(g), 1); ptx::mbar_init(o_free(g), 128);
+        }
+        ptx::fence_barrier_init();
+    }
+    if (warp == 2) {
+        ptx::tmem_alloc(tmem_slot, 512);
+        ptx::tmem_relinquish();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
+    auto tS = [&](int g) { return tmem_base + (uint32_t)(g * 256); };
+    auto tO = [&](int g) { return tmem_base + (uint32_t)(g * 256) + W3_O_COL; };
+
+    if (warp == 0) {
+        // ===================================================== TMA producer
+        if (ptx::elect_one()) {
+            ptx::mbar_expect_tx(sel_full, W3_KB);
+            ptx::tma_load_2d(sSel, &tmSel, sel_full, 0, 0);
+        }
+        int it = 0;
+        for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++it) {
+            const int item = w / heads, head = w - item * heads;
+            const int row0 = item * WT_S;
+            const uint32_t par = (uint32_t)(it & 1);
+            ptx::mbar_wait(qk_free, par ^ 1u);     // both S MMAs of the previous item have completed
+            if (ptx::elect_one()) {
+                ptx::mbar_expect_tx(qk_full, 4 * W3_QB + 2 * W3_KB);
+#pragma unroll
+                for (int g = 0; g < 2; ++g) {
+                    ptx::tma_load_2d(sQ0 + g * W3_QB, &tmQ, qk_full, head * FT_HD, row0 + g * FT_BQ);
+                    ptx::tma_load_2d(sQG + g * W3_QB, &tmQG, qk_full, head * 64, row0 + g * FT_BQ);
+                }
+#pragma unroll
+                for (int t = 0; t < 3; ++t) {
+                    ptx::tma_load_2d(sK0 + t * 8192, &tmK, qk_full, D + head * FT_HD, row0 + t * 64);
+                    ptx::tma_load_2d(sKt + t * 8192, &tmK, qk_full, D + head * FT_HD + 16, row0 + t * 64);
+                }
+                ptx::tma_load_2d(sK0 + 3 * 8192, &tmK16, qk_full, D + head * FT_HD, row0 + 192);
+                ptx::tma_load_2d(sKt + 3 * 8192, &tmK16, qk_full, D + head * FT_HD + 16, row0 + 192);
+            }
+            ptx::mbar_wait(v_free, par ^ 1u);      // both P V of the previous item have completed
+            if (ptx::elect_one()) {
+                ptx::mbar_expect_tx(v_full, 4 * W3_VB);
+#pragma unroll
+                for (int t = 0; t < 4; ++t) ptx::tma_load_2d(sV + t * W3_VB, &tmV, v_full, item * WT_VLD + t * FT_BK, head * W3_VR);
+            }
+        }
+    } else if (warp == 1) {
+        // ===================================================== MMA issuer
+        auto idesc = [](int n) { return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(FT_BQ >> 4) << 24); };
+        const uint64_t desc_hi = (2ull << 61) | (1ull << 46) | ((uint64_t)(1024 >> 4) << 32);  // SWIZZLE_128B, SBO 1024
+        auto desc = [&](uint32_t addr) { return desc_hi | (uint64_t)((addr >> 4) & 0x3FFF); };
+        ptx::mbar_wait(sel_full, 0);
+        int it = 0;
+        for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++it) {
+            const uint32_t par = (uint32_t)(it & 1);
+            ptx::mbar_wait(qk_full, par);
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+                ptx::mbar_wait(o_free(g), par ^ 1u);   // the previous item's O (same TMEM columns) has been read out
+                ptx::tc_fence_after();
+                if (ptx::elect_one()) {
+                    const uint64_t a0 = desc(sQ0 + g * W3_QB), aq = desc(sQG + g * W3_QB);
+                    const uint64_t b0 = desc(sK0), bt = desc(sKt), bs = desc(sSel);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) ptx::umma_f16(tS(g), a0 + 2u * k, b0 + 2u * k, idesc(WT_VLD), k != 0 ? 1u : 0u);
+                    ptx::umma_f16(tS(g), aq, bt + 6u, idesc(WT_VLD), 1u);           // Q / K columns 64..79
+                    ptx::umma_f16(tS(g), aq + 2u, bs, idesc(WT_VLD), 1u);           // + Gsel Sel^T (two k-steps of 16 bias columns)
+                    ptx::umma_f16(tS(g), aq + 4u, bs + 2u, idesc(WT_VLD), 1u);
+                    ptx::umma_commit(s_full(g));
+                    if (g == 1) ptx::umma_commit(qk_free);
+                }
+                __syncwarp();
+            }
+            ptx::mbar_wait(v_full, par);
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+                ptx::mbar_wait(p_full(g), par);
+                ptx::tc_fence_after();
+                if (ptx::elect_one()) {
+#pragma unroll
+                    for (int k = 0; k < WT_VLD / 16; ++k)   // 13 k-steps of 16 keys; P chunk k = 8 packed TMEM columns
+                        ptx::umma_f16_ts(tO(g), tS(g) + 8u * k, desc(sV + (uint32_t)(k >> 2) * W3_VB) + 2u * (k & 3), idesc(W3_VR),
+                                         k != 0 ? 1u : 0u);
+                    ptx::umma_commit(o_full(g));
+                    if (g == 1) ptx::umma_commit(v_free);
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================================================== softmax / output: one query row per thread
+        const int grp = (warp - 4) >> 2, quad = warp & 3, r = quad * 32 + lane;
+        const int qi = grp * FT_BQ + r;
+        const bool row_ok = qi < WT_S;
+        const bool warp_ok = grp * FT_BQ + quad * 32 < WT_S;   // warps whose 32 rows are all padding only keep the barrier counts
+        const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
+        const float sl2 = scale * FT_L2E;
+        auto fl = [](uint32_t u) { return __uint_as_float(u); };
+        int it = 0;
+        for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++it) {
+            const int item = w / heads, head = w - item * heads;
+            const uint32_t par = (uint32_t)(it & 1);
+            // (every thread waits and arrives, also in the all-padding warps: an arrival that ran ahead of its phase would
+            //  be counted towards the previous one)
+            ptx::mbar_wait(s_full(grp), par);
+            if (warp_ok) {
+                ptx::tc_fence_after();
+                const uint32_t ts = tS(grp) + lane_off;
+                // pass 1: exact row maximum over the 196 keys (raw accumulator units)
+                float mx = -INFINITY;
+#pragma unroll 1
+                for (int c = 0; c < 6; ++c) {
+                    uint32_t v[32];
+                    ptx::tmem_ld32(ts + 32u * c, v);
+                    ptx::tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; j += 2) mx = fmaxf(mx, fmaxf(fl(v[j]), fl(v[j + 1])));
+                }
+                {
+                    uint32_t v[16];
+                    ptx::tmem_ld16(ts + 192u, v);
+                    ptx::tmem_ld_wait();
+                    mx = fmaxf(mx, fmaxf(fmaxf(fl(v[0]), fl(v[1])), fmaxf(fl(v[2]), fl(v[3]))));   // keys 192..195; 196..207 are padding
+                }
+                const float mneg = -mx * sl2;
+                // pass 2: P in place, ascending key order
+#pragma unroll 1
+                for (int c = 0; c < 6; ++c) {
+                    uint32_t v[32], pk[16];
+                    ptx::tmem_ld32(ts + 32u * c, v);
+                    ptx::tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        pk[j] = ptx::ex2_f16x2(pack_h2(fmaf(fl(v[2 * j]), sl2, mneg), fmaf(fl(v[2 * j + 1]), sl2, mneg)));
+                    ptx::tmem_st16(ts + 16u * c, pk);
+                }
+                {
+                    uint32_t v[16], pk[16];
+                    ptx::tmem_ld16(ts + 192u, v);
+                    ptx::tmem_ld_wait();
+                    pk[0] = ptx::ex2_f16x2(pack_h2(fmaf(fl(v[0]), sl2, mneg), fmaf(fl(v[1]), sl2, mneg)));
+                    pk[1] = ptx::ex2_f16x2(pack_h2(fmaf(fl(v[2]), sl2, mneg), fmaf(fl(v[3]), sl2, mneg)));
+#pragma unroll
+                    for (int j = 2; j < 16; ++j) pk[j] = 0u;       // keys 196..207: weight 0 (columns 104..111 are unused padding)
+                    ptx::tmem_st16(ts + 96u, pk);
+                }
+                ptx::tmem_st_wait();
+                ptx::tc_fence_before();
+            }
+            ptx::mbar_arrive(p_full(grp));
+            ptx::mbar_wait(o_full(grp), par);
+            if (warp_ok) {
+                ptx::tc_fence_after();
+                const uint32_t to = tO(grp) + lane_off;
+                float inv;
+                {
+                    uint32_t d[16];
+                    ptx::tmem_ld16(to + (uint32_t)FT_HD, d);   // output column 80 = sum of the row's (fp16-rounded) weights
+                    ptx::tmem_ld_wait();
+                    inv = 1.0f / fl(d[0]);
+                }
+                __half* dst = out + ((long long)item * WT_S + qi) * D + head * FT_HD;
+                auto f = [&](uint32_t u) { return __uint_as_float(u) * inv; };
+#pragma unroll 1
+                for (int c0 = 0; c0 < FT_HD; c0 += 16) {
+                    uint32_t d[16];
+                    ptx::tmem_ld16(to + (uint32_t)c0, d);
+                    ptx::tmem_ld_wait();
+                    if (row_ok) {
+#pragma unroll
+                        for (int i = 0; i < 16; i += 8)
+                            *reinterpret_cast<uint4*>(dst + c0 + i) = make_uint4(pack_h2(f(d[i]), f(d[i + 1])), pack_h2(f(d[i + 2]), f(d[i + 3])),
+                                                                                 pack_h2(f(d[i + 4]), f(d[i + 5])), pack_h2(f(d[i + 6]), f(d[i + 7])));
+                    }
+                }
+                ptx::tc_fence_before();
+            }
+            ptx::mbar_arrive(o_free(grp));
+        }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    if (warp == 2) ptx::tmem_dealloc(tmem_base, 512);
+}
+
 PFN_cuTensorMapEncodeTiled_v12000 ft_encode_fn() {
     static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
     if (!fn) {
@@ -1106,14 +1389,21 @@ int op_attention_tc(const __half* qkv, int Gb, int S, int heads, int hd, float s
 // ------------------------------------------------------------------------------------------ windows: host side
 bool op_window_attention_tc_supported(int S, int hd, int gh, int gw) { return hd == FT_HD && S == WT_S && gh == WT_G && gw == WT_G; }
 
+static size_t w3_vt_bytes(int n_items, int heads) { return align_up((size_t)heads * W3_VR * n_items * WT_VLD * 2, 1024); }
+static size_t w3_qg_bytes(int n_items, int heads) { return align_up((size_t)n_items * WT_S * heads * 64 * 2, 1024); }
+
 size_t op_window_attention_tc_workspace_bytes(int n_items, int heads) {
-    return align_up((size_t)heads * FT_HD * n_items * WT_VLD * 2, 1024) + 1024;
+    // variants 1 / 2: V^T (80 rows per head); variant 3: V^T (96 rows per head) + QG + Sel
+    const size_t v12 = align_up((size_t)heads * FT_HD * n_items * WT_VLD * 2, 1024) + 1024;
+    const size_t v3 = w3_vt_bytes(n_items, heads) + w3_qg_bytes(n_items, heads) + align_up((size_t)W3_KB, 1024) + 1024;
+    return v12 > v3 ? v12 : v3;
 }
 
 // 1: four-key-tile loop (window_tc_kernel, 128 us per SAM-H block at B = 4), 2: single-shot N = 208 (window_tc2_kernel, 152 us:
 // one thread per 196-score row is ~1,800 serial instructions per pair, and only 8 softmax warps fit beside the TMEM budget)
 static int g_window_tc_variant = 1;
-extern "C" __attribute__((visibility("default"))) void cvb_set_window_tc_variant(int v) { g_window_tc_variant = v == 2 ? 2 : 1; }
+// 3: scores fully biased by the tensor core, softmax in place in tensor memory (window_tc3_kernel) -- EXPERIMENTAL, never run yet
+extern "C" __attribute__((visibility("default"))) void cvb_set_window_tc_variant(int v) { g_window_tc_variant = (v == 2 || v == 3) ? v : 1; }
 
 int op_window_attention_tc(const __half* qkv, int n_items, int heads, int hd, float scale, const __half* relcat, __half* out,
                            void* workspace, size_t ws_bytes, cudaStream_t stream) {
@@ -1128,7 +1418,31 @@ int op_window_attention_tc(const __half* qkv, int n_items, int heads, int hd, fl
     if (!((configured >> cfg_dev) & 1ull)) {
         CVB_CUDA(cudaFuncSetAttribute(window_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WT_SMEM));
         CVB_CUDA(cudaFuncSetAttribute(window_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)W2_SMEM));
+        CVB_CUDA(cudaFuncSetAttribute(window_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)W3_SMEM));
         configured |= 1ull << cfg_dev;
+    }
+    if (g_window_tc_variant == 3) {
+        __half* vt96 = reinterpret_cast<__half*>(workspace);
+        __half* qg = reinterpret_cast<__half*>(reinterpret_cast<uint8_t*>(workspace) + w3_vt_bytes(n_items, heads));
+        __half* sel = reinterpret_cast<__half*>(reinterpret_cast<uint8_t*>(qg) + w3_qg_bytes(n_items, heads));
+        v_transpose_win96_kernel<<<dim3(n_items, heads), 256, 0, stream>>>(qkv, heads, n_items, vt96);
+        window_sel_kernel<<<(WT_VLD * 64 + 255) / 256, 256, 0, stream>>>(sel);
+        cvb_note_launches(2);
+        CVB_TRY(op_window_qg(qkv, n_items, WT_S, heads, hd, scale, relcat, relcat + 32 * FT_HD, WT_G, WT_G, qg, stream));
+        CUtensorMap tq, tqg, tk, tk16, tv, ts;
+        const uint64_t rows = (uint64_t)n_items * WT_S;
+        CVB_TRY(ft_tmap_2d(&tq, qkv, (uint64_t)3 * D, rows, (uint64_t)3 * D * 2, 64, FT_BQ));
+        CVB_TRY(ft_tmap_2d(&tqg, qg, (uint64_t)heads * 64, rows, (uint64_t)heads * 64 * 2, 64, FT_BQ));
+        CVB_TRY(ft_tmap_2d(&tk, qkv, (uint64_t)3 * D, rows, (uint64_t)3 * D * 2, 64, FT_BK));
+        CVB_TRY(ft_tmap_2d(&tk16, qkv, (uint64_t)3 * D, rows, (uint64_t)3 * D * 2, 64, 16));
+        CVB_TRY(ft_tmap_2d(&tv, vt96, (uint64_t)n_items * WT_VLD, (uint64_t)heads * W3_VR, (uint64_t)n_items * WT_VLD * 2, 64, W3_VR));
+        CVB_TRY(ft_tmap_2d(&ts, sel, 64, WT_VLD, 64 * 2, 64, WT_VLD));
+        const int n_work3 = n_items * heads;
+        const int grid3 = n_work3 < cvb_num_sms() ? n_work3 : cvb_num_sms();
+        window_tc3_kernel<<<grid3, WT_THREADS, W3_SMEM, stream>>>(tq, tqg, tk, tk16, tv, ts, heads, n_items, scale, out);
+        cvb_note_launches(1);
+        CVB_CUDA(cudaGetLastError());
+        return CVB_OK;
     }
     v_transpose_win_kernel<<<dim3(n_items, heads), 256, 0, stream>>>(qkv, heads, n_items, vt);
     CUtensorMap tq, tk, tv, tr;

@@ -67,6 +67,11 @@ int op_attention(const __half* qkv, int Gb, int S, int heads, int hd, float scal
 int op_relpos_tables(const __half* qkv, int Gb, int S, int heads, int hd, const __half* Rh, const __half* Rw, int gh, int gw,
                      __half* bias_h, __half* bias_w, cudaStream_t stream);
 
+// Pre-pass of the third tcgen05 window design (EXPERIMENTAL): qg fp16 [(Gb*S) rows][heads][64] =
+// [Q[.][64..79] | rel_h(q, kh) / scale (14) | rel_w(q, kw) / scale (14) | 0], see window_qg_kernel.
+int op_window_qg(const __half* qkv, int Gb, int S, int heads, int hd, float scale, const __half* Rh, const __half* Rw, int gh, int gw,
+                 __half* qg, cudaStream_t stream);
+
 // --- flash_tc.cu ------------------------------------------------------------------------------------
 // tcgen05 version of op_attention for the SAM global-attention shape (head dim 80, 64-wide token grid, S % 128 == 0,
 // rel-pos tables present). `workspace` (1024-byte aligned, op_attention_tc_workspace_bytes) holds V^T and the two

@@ -2,6 +2,7 @@
 (oracle/forward_oracle.py, pinned to the reference modules). Tolerance on NP/HV/NT head maps: 1e-3 abs
 (BASELINE.json north_star)."""
 import ctypes as C
+import os
 import math
 
 import pytest
@@ -185,9 +186,15 @@ def test_forward_sam_h_1024_attention_tc_vs_mma_sync():
             assert err <= tol, (k, err)
 
 
-@pytest.mark.parametrize("n_items,heads,variant", [(3, 2, 1), (25, 4, 1), (3, 2, 2), (25, 4, 2), (160, 16, 2)])
+_EXPERIMENTAL = pytest.mark.skipif(os.environ.get("CVB_EXPERIMENTAL") != "1",
+                                   reason="window_tc3_kernel was written without a GPU at hand and has not been run yet; CVB_EXPERIMENTAL=1 enables it")
+
+
+@pytest.mark.parametrize("n_items,heads,variant", [(3, 2, 1), (25, 4, 1), (3, 2, 2), (25, 4, 2), (160, 16, 2),
+                                                   pytest.param(1, 1, 3, marks=_EXPERIMENTAL), pytest.param(3, 2, 3, marks=_EXPERIMENTAL),
+                                                   pytest.param(25, 4, 3, marks=_EXPERIMENTAL), pytest.param(160, 16, 3, marks=_EXPERIMENTAL)])
 def test_window_attention_tc_matches_torch(n_items, heads, variant):
-    """tcgen05 window attention (flash_tc.cu, both kernel designs): 14 x 14 windows, head dim 80, rel-pos bias computed
+    """tcgen05 window attention (flash_tc.cu, the kernel designs): 14 x 14 windows, head dim 80, rel-pos bias computed
     in the kernel; 160 x 16 pairs exercise the persistent loop (several pairs per CTA)."""
     L.lib().cvb_set_window_tc_variant(variant)
     g = torch.Generator(device="cuda").manual_seed(13)
