@@ -1,6 +1,7 @@
 """CPU-side checks: the C-ABI library exports every declared symbol, the module mirrors keep the reference
 state_dict surface and error behaviour, packing shapes, sharding logic (incl. a world-size-2 gloo run)."""
 import ctypes
+import math
 import os
 import re
 import subprocess
@@ -230,3 +231,53 @@ def test_public_header_is_plain_c(tmp_path):
     assert r.returncode == 0, r.stderr
     run = subprocess.run([str(exe)], capture_output=True, text=True)
     assert run.returncode == 0 and run.stdout.split()[0] == "100", (run.returncode, run.stdout, run.stderr)
+
+
+def test_window_tc3_operand_layout_reproduces_the_reference_attention():
+    """The experimental third window-attention design (flash_tc.cu: window_tc3_kernel) computes S = [Q | Gsel] [K | Sel]^T with
+    the operand layouts its pre-pass kernels write. This restates those layouts in torch on the CPU -- QG row = [Q[64:80] |
+    rel_h(q, kh) / scale | rel_w(q, kw) / scale | 0] with the kernels' scatter index kk = qpos + g - 1 - j, Sel[k] = ones at kh(k)
+    and 14 + kw(k), keys padded to 208, V^T with a ones row -- and checks the result against attention with the decomposed
+    relative position bias (image_encoder.py:354-392). It pins the design, not the CUDA code (which has not been run yet)."""
+    torch.manual_seed(0)
+    g, hd, S, SP = 14, 80, 196, 208
+    scale = hd ** -0.5
+    q, k, v = torch.randn(S, hd), torch.randn(S, hd), torch.randn(S, hd)
+    Rh, Rw = torch.randn(2 * g - 1, hd) * 0.2, torch.randn(2 * g - 1, hd) * 0.2
+    # reference: softmax(scale q k^T + rel_h + rel_w) v, rel from the UNSCALED q
+    idx = (torch.arange(g)[:, None] - torch.arange(g)[None, :]) + g - 1
+    rq = q.view(g, g, hd)
+    rel_h = torch.einsum("hwc,hkc->hwk", rq, Rh[idx])
+    rel_w = torch.einsum("hwc,wkc->hwk", rq, Rw[idx])
+    attn = ((q * scale) @ k.T).view(g, g, g, g) + rel_h[..., :, None] + rel_w[..., None, :]
+    want = attn.view(S, S).softmax(-1) @ v
+    # pre-pass layouts
+    G_h, G_w = q @ Rh.T, q @ Rw.T                                   # G = Q T^T, [S, 27]
+    qg = torch.zeros(S, 64)
+    qg[:, :16] = q[:, 64:80]
+    for t in range(S):
+        qh, qw = divmod(t, g)
+        for j in range(2 * g - 1):
+            kk = qh + g - 1 - j
+            if 0 <= kk < g:
+                qg[t, 16 + kk] = G_h[t, j] / scale
+            kk = qw + g - 1 - j
+            if 0 <= kk < g:
+                qg[t, 16 + g + kk] = G_w[t, j] / scale
+    sel = torch.zeros(SP, 64)
+    for key in range(S):
+        kh, kw = divmod(key, g)
+        sel[key, kh] = 1.0
+        sel[key, g + kw] = 1.0
+    kp = torch.zeros(SP, hd); kp[:S] = k
+    vt = torch.zeros(96, SP); vt[:hd, :S] = v.T; vt[hd, :S] = 1.0
+    # the kernel's seven k-steps: Q[0:64] K[0:64], Q[64:80] (QG cols 0..15) K[64:80], Gsel (QG cols 16..47) Sel (cols 0..31)
+    s_acc = q[:, :64] @ kp[:, :64].T + qg[:, :16] @ kp[:, 64:80].T + qg[:, 16:48] @ sel[:, :32].T
+    assert (qg[:, 44:] == 0).all() and (sel[:, 28:] == 0).all()
+    sl2 = scale * math.log2(math.e)
+    m = s_acc[:, :S].max(1, keepdim=True).values
+    p = torch.exp2((s_acc - m) * sl2)
+    p[:, S:] = 0.0                                                   # keys 196..207: weight 0
+    o = p @ vt.T                                                     # [S, 96]; column 80 = row sums
+    got = o[:, :hd] / o[:, hd:hd + 1]
+    assert torch.allclose(got, want, rtol=1e-4, atol=1e-5), (got - want).abs().max()
