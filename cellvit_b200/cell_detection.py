@@ -80,6 +80,8 @@ def broadcast_weights(model: torch.nn.Module, src: int = 0) -> None:
         n = t.numel()
         t.copy_(flat[o:o + n].view_as(t))
         o += n
+    if hasattr(model, "invalidate_packed"):   # the copies above go through ``.data`` and leave Tensor._version unchanged
+        model.invalidate_packed()
 
 
 class TableGather:

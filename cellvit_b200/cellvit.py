@@ -85,7 +85,8 @@ class CellViT(nn.Module):
         _build_tree(self, spec, seed=int(torch.initial_seed() & 0xFFFF))
         self._handle = None
         self._packed = {}        # name -> device tensor (kept alive for the C side)
-        self._packed_key = None  # (device, param versions)
+        self._packed_key = None  # (device, pack epoch, hash of the per-tensor (address, version) pairs)
+        self._pack_epoch = 0
         self._size_key = None
         self._ws = None
         self._graphs = {}        # forward_graphed: (shape, tokens, slot, device) -> (graph, static input, static outputs)
@@ -119,14 +120,10 @@ class CellViT(nn.Module):
 
     def _ensure_packed(self, device, h, w):
         self._ensure_handle()
-        ver = ptr = 0
-        for t in self.parameters():
-            ver += t._version
-            ptr ^= t.data_ptr()
-        for t in self.buffers():
-            ver += t._version
-            ptr ^= t.data_ptr()
-        key = (str(device), ver, ptr)
+        # one (address, version) pair per tensor: sums / xors of them can collide, and an in-place write through ``.data``
+        # does not bump the version at all -- callers that do that (``broadcast_weights``) call ``invalidate_packed()``
+        key = (str(device), self._pack_epoch,
+               hash(tuple((t.data_ptr(), t._version) for t in list(self.parameters()) + list(self.buffers()))))
         if key != self._packed_key:  # weights were (re)loaded, updated in place or moved: repack once
             sd_dev = {k: v.to(device) for k, v in self.state_dict().items()}
             self._register(packing.pack_static(sd_dev, self._cfg()))
@@ -138,6 +135,21 @@ class CellViT(nn.Module):
             self._register(packing.pack_for_size(sd_dev, self._cfg(), h, w))
             self._size_key = (h, w)
             self._graphs = {}
+
+    def invalidate_packed(self) -> None:
+        """Force a repack of the kernel-layout weights (and drop captured CUDA graphs) at the next forward: call after
+        writing parameters through ``.data`` or any other route that leaves ``Tensor._version`` unchanged."""
+        self._pack_epoch += 1
+
+    def _load_from_state_dict(self, *args, **kwargs):
+        self._pack_epoch += 1
+        return super()._load_from_state_dict(*args, **kwargs)
+
+    def set_engine_option(self, name: str, value: int) -> None:
+        """Per-model engine option (``cvb_model_set_option``), e.g. ``("attention_tc", 0)`` to run the mma.sync attention
+        kernels instead of the tcgen05 ones. Captured CUDA graphs are dropped."""
+        L.check(L.lib().cvb_model_set_option(self._ensure_handle(), name.encode(), int(value)), "cvb_model_set_option")
+        self._graphs = {}
 
     def __del__(self):
         try:

@@ -635,97 +635,6 @@ window_attn_kernel(const __half* __restrict__ qkv, int S, int heads, float scale
     }
 }
 
-// ------------------------------------------------------------------------------------------ pre-pass of window_tc3_kernel
-// (flash_tc.cu, third tcgen05 window design, EXPERIMENTAL: written without access to a GPU, not yet run)
-// qg[(item*S + t)][head][64] fp16 = [ Q[t][64..79] (16) | rel_h(t, kh = 0..13) / scale (14) | rel_w(t, kw = 0..13) / scale (14) |
-// zeros (20) ]: the second A-operand box of S = [Q | Gsel] [K | Sel]^T, i.e. the same Gsel row window_attn_kernel builds in
-// shared memory (G = Q T^T on the MMA path, scattered with kk = qpos + g - 1 - j), written to global memory once per call.
-constexpr int QG_LD = 72;  // staging row stride (halves): 144 B, 16-byte aligned rows
-
-template <int HD>
-__global__ void __launch_bounds__(WA_THREADS)
-window_qg_kernel(const __half* __restrict__ qkv, int S, int heads, float scale, const __half* __restrict__ Rh,
-                 const __half* __restrict__ Rw, int gh, int gw, __half* __restrict__ qg) {
-    constexpr int LD = HD + 8, KSTEPS = HD / 16, CH = HD / 8;
-    static_assert(HD == 80, "the QG layout assumes a 64 + 16 column split of the head dimension");
-    __shared__ __align__(16) __half th[32 * LD];
-    __shared__ __align__(16) __half tw[32 * LD];
-    __shared__ __align__(16) __half stage[WA_WARPS][16 * QG_LD];
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int g = blockIdx.x, bp = g / heads, head = g - bp * heads;
-    const int D = heads * HD;
-    const long long row_stride = 3LL * D;
-    const __half* q_base = qkv + (long long)bp * S * row_stride + head * HD;
-    const int Lh = 2 * gh - 1, Lw = 2 * gw - 1;
-    for (int i = tid; i < 32 * CH; i += WA_THREADS) {
-        const int r = i / CH, c = i - r * CH;
-        ptx::cp_async16(ptx::smem_u32(th + r * LD + c * 8), Rh + (long long)(r < Lh ? r : 0) * HD + c * 8, r < Lh);
-        ptx::cp_async16(ptx::smem_u32(tw + r * LD + c * 8), Rw + (long long)(r < Lw ? r : 0) * HD + c * 8, r < Lw);
-    }
-    ptx::cp_async_commit();
-    for (int i = tid; i < WA_WARPS * 16 * QG_LD; i += WA_THREADS) (&stage[0][0])[i] = __float2half(0.0f);  // columns 44..63 stay zero
-    ptx::cp_async_wait<0>();
-    __syncthreads();
-    const float inv_scale = 1.0f / scale, inv_gw = 1.0f / (float)gw;
-    const int n_mt = (S + 15) >> 4;
-    __half* st = stage[warp];
-    const int rl = lane >> 2;
-    for (int mt = warp; mt < n_mt; mt += WA_WARPS) {
-        const int q0 = mt * 16;
-        uint32_t q_frag[KSTEPS][4];
-        {
-            const int r0 = q0 + rl, r1 = r0 + 8;
-            const __half* p0 = q_base + (long long)min(r0, S - 1) * row_stride + 2 * (lane & 3);
-            const __half* p1 = q_base + (long long)min(r1, S - 1) * row_stride + 2 * (lane & 3);
-#pragma unroll
-            for (int ks = 0; ks < KSTEPS; ++ks) {
-                q_frag[ks][0] = r0 < S ? *reinterpret_cast<const uint32_t*>(p0 + ks * 16) : 0u;
-                q_frag[ks][1] = r1 < S ? *reinterpret_cast<const uint32_t*>(p1 + ks * 16) : 0u;
-                q_frag[ks][2] = r0 < S ? *reinterpret_cast<const uint32_t*>(p0 + ks * 16 + 8) : 0u;
-                q_frag[ks][3] = r1 < S ? *reinterpret_cast<const uint32_t*>(p1 + ks * 16 + 8) : 0u;
-            }
-        }
-        // Q[.][64..79]: the last k-step's A fragment is exactly that 16 x 16 block
-        *reinterpret_cast<uint32_t*>(st + rl * QG_LD + 2 * (lane & 3)) = q_frag[KSTEPS - 1][0];
-        *reinterpret_cast<uint32_t*>(st + (rl + 8) * QG_LD + 2 * (lane & 3)) = q_frag[KSTEPS - 1][1];
-        *reinterpret_cast<uint32_t*>(st + rl * QG_LD + 8 + 2 * (lane & 3)) = q_frag[KSTEPS - 1][2];
-        *reinterpret_cast<uint32_t*>(st + (rl + 8) * QG_LD + 8 + 2 * (lane & 3)) = q_frag[KSTEPS - 1][3];
-        float s_acc[8][4];
-#pragma unroll
-        for (int tbl = 0; tbl < 2; ++tbl) {
-            const int L = tbl == 0 ? Lh : Lw, gdim = tbl == 0 ? gh : gw, col0 = 16 + (tbl == 0 ? 0 : gh);
-            fa_qk<HD>(tbl == 0 ? th : tw, q_frag, s_acc, lane, (L + 15) >> 4);
-#pragma unroll
-            for (int hrow = 0; hrow < 2; ++hrow) {
-                const int t = q0 + rl + 8 * hrow;
-                if (t < S) {
-                    const int qh = (int)(((float)t + 0.5f) * inv_gw);
-                    const int qpos = tbl == 0 ? qh : t - qh * gw;
-#pragma unroll
-                    for (int nt = 0; nt < 4; ++nt)
-#pragma unroll
-                        for (int e = 0; e < 2; ++e) {
-                            const int j = nt * 8 + 2 * (lane & 3) + e;
-                            const int kk = qpos + gdim - 1 - j;
-                            if (kk >= 0 && kk < gdim && j < L)
-                                st[(rl + 8 * hrow) * QG_LD + col0 + kk] = __float2half(s_acc[nt][2 * hrow + e] * inv_scale);
-                        }
-                }
-            }
-        }
-        __syncwarp();
-        // 16 rows x 128 B, coalesced
-#pragma unroll
-        for (int i = lane; i < 16 * 8; i += 32) {
-            const int row = i >> 3, c = i & 7;
-            if (q0 + row < S)
-                *reinterpret_cast<uint4*>(qg + (((long long)bp * S + q0 + row) * heads + head) * 64 + c * 8) =
-                    *reinterpret_cast<const uint4*>(st + row * QG_LD + c * 8);
-        }
-        __syncwarp();
-    }
-}
-
 template <int HD>
 int launch_window(const __half* qkv, int Gb, int S, int heads, float scale, const __half* Rh, const __half* Rw, int gh, int gw,
                   __half* out, cudaStream_t stream) {
@@ -794,15 +703,4 @@ int op_attention(const __half* qkv, int Gb, int S, int heads, int hd, float scal
                             : launch_flash<64, false>(qkv, Gb, S, heads, scale, Rh, Rw, gh, gw, out, stream);
     cvb_set_error("attention: head dim %d not supported (64 or 80)", hd);
     return CVB_ESHAPE;
-}
-
-int op_window_qg(const __half* qkv, int Gb, int S, int heads, int hd, float scale, const __half* Rh, const __half* Rw, int gh, int gw,
-                 __half* qg, cudaStream_t stream) {
-    CVB_CHECK(qkv && Rh && Rw && qg && Gb > 0 && heads > 0, CVB_EARG, "window_qg: null operand");
-    CVB_CHECK(hd == 80 && gh + gw <= 28 && 2 * gh - 1 <= 32 && 2 * gw - 1 <= 32 && gh * gw == S, CVB_ESHAPE,
-              "window_qg: needs head dim 80 and a window grid of at most 14 x 14");
-    window_qg_kernel<80><<<Gb * heads, WA_THREADS, 0, stream>>>(qkv, S, heads, scale, Rh, Rw, gh, gw, qg);
-    cvb_note_launches(1);
-    CVB_CUDA(cudaGetLastError());
-    return CVB_OK;
 }

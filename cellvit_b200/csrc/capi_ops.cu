@@ -42,15 +42,10 @@ CVB_API int cvb_op_attention_tc(const void* qkv, int Gb, int S, int heads, int h
                            workspace, ws_bytes, (cudaStream_t)stream);
 }
 
-CVB_API int cvb_op_window_attention_tc_workspace_bytes(int n_items, int heads, size_t* out) {
-    CVB_CHECK(out != nullptr && n_items > 0 && heads > 0, CVB_EARG, "cvb_op_window_attention_tc_workspace_bytes: bad arguments");
-    *out = op_window_attention_tc_workspace_bytes(n_items, heads);
-    return CVB_OK;
-}
 CVB_API int cvb_op_window_attention_tc(const void* qkv, int n_items, int heads, int hd, float scale, const void* relcat, void* out,
-                                       void* workspace, size_t ws_bytes, void* stream) {
-    return op_window_attention_tc((const __half*)qkv, n_items, heads, hd, scale, (const __half*)relcat, (__half*)out, workspace,
-                                  ws_bytes, (cudaStream_t)stream);
+                                       void* stream) {
+    return op_window_attention_tc((const __half*)qkv, n_items, heads, hd, scale, (const __half*)relcat, (__half*)out,
+                                  (cudaStream_t)stream);
 }
 
 CVB_API int cvb_op_patch_im2col(const float* x, int B, int H, int W, int P, void* out, void* stream) {

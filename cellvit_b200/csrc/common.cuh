@@ -47,6 +47,9 @@ static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; 
 int cvb_num_sms();
 int cvb_current_device();
 void cvb_note_launches(int n);
+// 2-D fp16 tensor map, 128B swizzle, zero fill outside the tensor (core.cu); `tm` is a CUtensorMap*
+int cvb_tmap_2d_f16(void* tm, const void* base, uint64_t cols, uint64_t rows, uint64_t row_stride_bytes, uint32_t box_cols,
+                    uint32_t box_rows);
 
 #ifdef __CUDACC__
 // ---------------------------------------------------------------- device-side PTX wrappers

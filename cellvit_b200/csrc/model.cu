@@ -21,12 +21,11 @@
 struct cvb_model {
     cvb_model_desc d;
     std::unordered_map<std::string, const void*> params;
+    // option "attention_tc" (cvb_model_set_option): bit 0 = tcgen05 kernel for the global-attention blocks (flash_tc.cu), bit 1 =
+    // tcgen05 kernel for the 14 x 14 windows (window_tc.cu). Both on by default; 0 selects the mma.sync kernels of
+    // attention.cu (kept as the independent implementation the parity tests compare against).
+    int attn_tc_mode = 3;
 };
-
-// cvb_set_attention_tc(mode): bit 0 = tcgen05 kernel for the global-attention blocks (default on), bit 1 = tcgen05 kernel for
-// the 14 x 14 windows (default off: measured on B200 it only ties the mma.sync window kernel -- 128 + 28 us for V^T against
-// 157 us per block -- because a window has just four key tiles and the Q K^T -> softmax -> P V latency chain is exposed).
-static int g_attn_tc_mode = 1;
 
 namespace {
 
@@ -144,13 +143,11 @@ int forward_impl(cvb_model& m, const float* x, int B, int H, int W, float* o_np,
 
     __half* ybuf = A.alloc<__half>(rows_max * D);
     // global-attention blocks of SAM-H run on the tcgen05 attention kernel (needs V^T + bias tables scratch)
-    const bool attn_tc = sam && (g_attn_tc_mode & 1) && op_attention_tc_supported(Tx, hd, reinterpret_cast<const __half*>(1), h, w);
-    const bool win_tc = sam && (g_attn_tc_mode & 2) && ws > 0 && op_window_attention_tc_supported(ws * ws, hd, ws, ws);
-    size_t attn_ws_bytes = attn_tc ? op_attention_tc_workspace_bytes(B, Tx, heads) : 0;
-    if (win_tc && op_window_attention_tc_workspace_bytes(B * g * g, heads) > attn_ws_bytes)
-        attn_ws_bytes = op_window_attention_tc_workspace_bytes(B * g * g, heads);
+    const bool attn_tc = sam && (m.attn_tc_mode & 1) && op_attention_tc_supported(Tx, hd, reinterpret_cast<const __half*>(1), h, w);
+    const bool win_tc = sam && (m.attn_tc_mode & 2) && ws > 0 && op_window_attention_tc_supported(ws * ws, hd, ws, ws);
+    const size_t attn_ws_bytes = attn_tc ? op_attention_tc_workspace_bytes(B, Tx, heads) : 0;
     uint8_t* attn_ws = nullptr;
-    if (attn_tc || win_tc) {
+    if (attn_tc) {
         attn_ws = A.alloc<uint8_t>(attn_ws_bytes + 1024);
         attn_ws = reinterpret_cast<uint8_t*>(((uintptr_t)attn_ws + 1023) & ~(uintptr_t)1023);
     }
@@ -173,7 +170,7 @@ int forward_impl(cvb_model& m, const float* x, int B, int H, int W, float* o_np,
         const __half* tw = sam ? f.P<__half>(p + ".relw") : nullptr;
         if (f.live()) {
             if (attn_tc && !win) f.chk(op_attention_tc(qkv, Gb, S, heads, hd, scale, th, tw, gh, gw, att, attn_ws, attn_ws_bytes, st));
-            else if (win_tc && win) f.chk(op_window_attention_tc(qkv, Gb, heads, hd, scale, f.P<__half>(p + ".relcat"), att, attn_ws, attn_ws_bytes, st));
+            else if (win_tc && win) f.chk(op_window_attention_tc(qkv, Gb, heads, hd, scale, f.P<__half>(p + ".relcat"), att, st));
             else f.chk(op_attention(qkv, Gb, S, heads, hd, scale, th, tw, gh, gw, att, st));
         }
         {
@@ -349,4 +346,13 @@ CVB_API int cvb_forward(cvb_model* m, const float* x, int B, int H, int W, float
 
 CVB_API void cvb_model_destroy(cvb_model* m) { delete m; }
 
-CVB_API void cvb_set_attention_tc(int mode) { g_attn_tc_mode = mode; }
+CVB_API int cvb_model_set_option(cvb_model* m, const char* name, int value) {
+    CVB_CHECK(m && name, CVB_EARG, "cvb_model_set_option: null argument");
+    if (std::string(name) == "attention_tc") {
+        CVB_CHECK(value >= 0 && value <= 3, CVB_EARG, "cvb_model_set_option: attention_tc must be in 0..3");
+        m->attn_tc_mode = value;
+        return CVB_OK;
+    }
+    cvb_set_error("cvb_model_set_option: unknown option '%s'", name);
+    return CVB_EARG;
+}

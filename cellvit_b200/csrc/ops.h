@@ -67,11 +67,6 @@ int op_attention(const __half* qkv, int Gb, int S, int heads, int hd, float scal
 int op_relpos_tables(const __half* qkv, int Gb, int S, int heads, int hd, const __half* Rh, const __half* Rw, int gh, int gw,
                      __half* bias_h, __half* bias_w, cudaStream_t stream);
 
-// Pre-pass of the third tcgen05 window design (EXPERIMENTAL): qg fp16 [(Gb*S) rows][heads][64] =
-// [Q[.][64..79] | rel_h(q, kh) / scale (14) | rel_w(q, kw) / scale (14) | 0], see window_qg_kernel.
-int op_window_qg(const __half* qkv, int Gb, int S, int heads, int hd, float scale, const __half* Rh, const __half* Rw, int gh, int gw,
-                 __half* qg, cudaStream_t stream);
-
 // --- flash_tc.cu ------------------------------------------------------------------------------------
 // tcgen05 version of op_attention for the SAM global-attention shape (head dim 80, 64-wide token grid, S % 128 == 0,
 // rel-pos tables present). `workspace` (1024-byte aligned, op_attention_tc_workspace_bytes) holds V^T and the two
@@ -81,9 +76,10 @@ size_t op_attention_tc_workspace_bytes(int Gb, int S, int heads);
 int op_attention_tc(const __half* qkv, int Gb, int S, int heads, int hd, float scale, const __half* Rh, const __half* Rw, int gh,
                     int gw, __half* out, void* workspace, size_t ws_bytes, cudaStream_t stream);
 
-// tcgen05 attention for the 14 x 14 SAM windows (196 tokens, head dim 80). qkv fp16 [n_items*196, 3*D] in window order,
-// relcat fp16 [64, 80] = rel_h table rows at 0.., rel_w table rows at 32.. (packing.py), out fp16 [n_items*196, D].
+// --- window_tc.cu -----------------------------------------------------------------------------------
+// tcgen05 attention for the 14 x 14 SAM windows (196 tokens, head dim 80), one kernel without pre-passes or workspace.
+// qkv fp16 [n_items*196, 3*D] in window order, relcat fp16 [64, 80] = rel_h table rows at 0.., rel_w table rows at 32..
+// (packing.py), out fp16 [n_items*196, D].
 bool op_window_attention_tc_supported(int S, int hd, int gh, int gw);
-size_t op_window_attention_tc_workspace_bytes(int n_items, int heads);
 int op_window_attention_tc(const __half* qkv, int n_items, int heads, int hd, float scale, const __half* relcat, __half* out,
-                           void* workspace, size_t ws_bytes, cudaStream_t stream);
+                           cudaStream_t stream);

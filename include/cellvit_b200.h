@@ -57,6 +57,9 @@ typedef struct {
 
 int cvb_model_create(const cvb_model_desc* desc, cvb_model** out);
 void cvb_model_destroy(cvb_model* m);
+/* Per-handle options (no process-global state). "attention_tc": bit 0 = tcgen05 kernel for the global-attention blocks,
+ * bit 1 = tcgen05 kernel for the 14 x 14 windows (default 3 = both); 0 = the mma.sync kernels (parity-test reference). */
+int cvb_model_set_option(cvb_model* m, const char* name, int value);
 
 /* Registers one packed parameter tensor (device pointer; the caller keeps it alive). Names and layouts are
  * listed in DESIGN.md ("packed parameter table"); cellvit_b200/packing.py produces them from a reference
@@ -149,12 +152,11 @@ int cvb_op_attention(const void* qkv, int Gb, int S, int heads, int hd, float sc
 int cvb_op_attention_tc_workspace_bytes(int Gb, int S, int heads, size_t* out);
 int cvb_op_attention_tc(const void* qkv, int Gb, int S, int heads, int hd, float scale, const void* Rh, const void* Rw,
                         int gh, int gw, void* out, void* workspace, size_t ws_bytes, void* stream);
-/* tcgen05 attention for the 14 x 14 SAM windows: qkv fp16 [n_items*196, 3*D] in window order, relcat fp16 [64, 80]
- * (rel_h table rows at 0.., rel_w table rows at 32..), out fp16 [n_items*196, D]. */
-int cvb_op_window_attention_tc_workspace_bytes(int n_items, int heads, size_t* out);
+/* tcgen05 attention for the 14 x 14 SAM windows (window_tc.cu; image_encoder.py:235-260 on window_partition'ed tokens):
+ * qkv fp16 [n_items*196, 3*D] in window order, relcat fp16 [64, 80] (rel_h table rows at 0.., rel_w table rows at 32..),
+ * out fp16 [n_items*196, D]. One kernel, no workspace. */
 int cvb_op_window_attention_tc(const void* qkv, int n_items, int heads, int hd, float scale, const void* relcat, void* out,
-                               void* workspace, size_t ws_bytes, void* stream);
-void cvb_set_window_tc_variant(int v); /* 1 (default): four-key-tile loop, 2: single-shot N = 208 kernel */
+                               void* stream);
 int cvb_op_patch_im2col(const float* x, int B, int H, int W, int P, void* out, void* stream);
 int cvb_op_stem_conv(const float* x, int B, int H, int W, const float* w, const float* scale, const float* shift,
                      void* out, int cpad, void* stream);

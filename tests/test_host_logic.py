@@ -233,12 +233,13 @@ def test_public_header_is_plain_c(tmp_path):
     assert run.returncode == 0 and run.stdout.split()[0] == "100", (run.returncode, run.stdout, run.stderr)
 
 
-def test_window_tc3_operand_layout_reproduces_the_reference_attention():
-    """The experimental third window-attention design (flash_tc.cu: window_tc3_kernel) computes S = [Q | Gsel] [K | Sel]^T with
-    the operand layouts its pre-pass kernels write. This restates those layouts in torch on the CPU -- QG row = [Q[64:80] |
-    rel_h(q, kh) / scale | rel_w(q, kw) / scale | 0] with the kernels' scatter index kk = qpos + g - 1 - j, Sel[k] = ones at kh(k)
-    and 14 + kw(k), keys padded to 208, V^T with a ones row -- and checks the result against attention with the decomposed
-    relative position bias (image_encoder.py:354-392). It pins the design, not the CUDA code (which has not been run yet)."""
+def test_window_tc_operand_layout_reproduces_the_reference_attention():
+    """The tcgen05 window-attention kernel (csrc/window_tc.cu) computes S = [Q | Gsel] [K | Sel]^T, where a softmax thread
+    builds its Gsel half from the G = Q Rcat^T row with a register barrel shifter. This restates that data flow in torch on
+    the CPU -- in[i] = G[26 - i] / scale packed in pairs, shift s = 13 - qpos applied as 8 / 4 / 2 / 1 stages on packed
+    registers, QG row = [Q[64:80] | Gsel_h (14) 0 0 | Gsel_w (14) 0 0 | unused], Sel[k] = ones at kh(k) and 16 + kw(k), keys
+    padded to 208, the key split 96 / 112 of the two threads of a row with a shared maximum, row sums from a ones operand --
+    and checks the result against attention with the decomposed relative position bias (image_encoder.py:354-392)."""
     torch.manual_seed(0)
     g, hd, S, SP = 14, 80, 196, 208
     scale = hd ** -0.5
@@ -251,33 +252,39 @@ def test_window_tc3_operand_layout_reproduces_the_reference_attention():
     rel_w = torch.einsum("hwc,wkc->hwk", rq, Rw[idx])
     attn = ((q * scale) @ k.T).view(g, g, g, g) + rel_h[..., :, None] + rel_w[..., None, :]
     want = attn.view(S, S).softmax(-1) @ v
-    # pre-pass layouts
-    G_h, G_w = q @ Rh.T, q @ Rw.T                                   # G = Q T^T, [S, 27]
+    relcat = torch.zeros(64, hd); relcat[:27] = Rh; relcat[32:59] = Rw
+    G = q @ relcat.T                                                 # the G MMA: [S, 64]
+
+    def barrel14(p, s):
+        """p: 15 'registers' of (lo, hi) pairs; returns 7 registers holding in[s .. s + 13] (the kernel's barrel14)."""
+        t1 = [p[min(i + 4, 14)] if s & 8 else p[i] for i in range(11)]
+        t2 = [t1[i + 2] if s & 4 else t1[i] for i in range(9)]
+        t3 = [t2[i + 1] if s & 2 else t2[i] for i in range(8)]
+        return [(t3[i][1], t3[i + 1][0]) if s & 1 else t3[i] for i in range(7)]
+
     qg = torch.zeros(S, 64)
     qg[:, :16] = q[:, 64:80]
     for t in range(S):
         qh, qw = divmod(t, g)
-        for j in range(2 * g - 1):
-            kk = qh + g - 1 - j
-            if 0 <= kk < g:
-                qg[t, 16 + kk] = G_h[t, j] / scale
-            kk = qw + g - 1 - j
-            if 0 <= kk < g:
-                qg[t, 16 + g + kk] = G_w[t, j] / scale
+        for half, qpos in ((0, qh), (1, qw)):
+            gv = (G[t, 32 * half:32 * half + 32] / scale).tolist()
+            p = [(gv[26 - 2 * i], gv[25 - 2 * i]) for i in range(13)] + [(gv[0], 0.0), (0.0, 0.0)]
+            o7 = barrel14(p, 13 - qpos)
+            vals = [x for pair in o7 for x in pair] + [0.0, 0.0]
+            qg[t, 16 + 16 * half:32 + 16 * half] = torch.tensor(vals)
     sel = torch.zeros(SP, 64)
     for key in range(S):
         kh, kw = divmod(key, g)
         sel[key, kh] = 1.0
-        sel[key, g + kw] = 1.0
+        sel[key, 16 + kw] = 1.0
     kp = torch.zeros(SP, hd); kp[:S] = k
-    vt = torch.zeros(96, SP); vt[:hd, :S] = v.T; vt[hd, :S] = 1.0
+    vp = torch.zeros(SP, hd); vp[:S] = v
+    ones = torch.zeros(SP); ones[:S] = 1.0
     # the kernel's seven k-steps: Q[0:64] K[0:64], Q[64:80] (QG cols 0..15) K[64:80], Gsel (QG cols 16..47) Sel (cols 0..31)
     s_acc = q[:, :64] @ kp[:, :64].T + qg[:, :16] @ kp[:, 64:80].T + qg[:, 16:48] @ sel[:, :32].T
-    assert (qg[:, 44:] == 0).all() and (sel[:, 28:] == 0).all()
     sl2 = scale * math.log2(math.e)
-    m = s_acc[:, :S].max(1, keepdim=True).values
+    m = torch.maximum(s_acc[:, :96].max(1, keepdim=True).values, s_acc[:, 96:S].max(1, keepdim=True).values)
     p = torch.exp2((s_acc - m) * sl2)
     p[:, S:] = 0.0                                                   # keys 196..207: weight 0
-    o = p @ vt.T                                                     # [S, 96]; column 80 = row sums
-    got = o[:, :hd] / o[:, hd:hd + 1]
+    got = (p @ vp) / (p @ ones)[:, None]
     assert torch.allclose(got, want, rtol=1e-4, atol=1e-5), (got - want).abs().max()

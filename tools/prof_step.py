@@ -4,10 +4,9 @@ from cellvit_b200.cellvit import CellViTSAM
 from cellvit_b200.post_proc_cellvit import DetectionCellPostProcessor
 from cellvit_b200 import synth
 from cellvit_b200 import _lib as _L
-if len(sys.argv) > 1: _L.lib().cvb_set_attention_tc(int(sys.argv[1]))   # attention mode bits (see csrc/model.cu)
-if len(sys.argv) > 2: _L.lib().cvb_set_window_tc_variant(int(sys.argv[2]))
 torch.manual_seed(0)
 m = CellViTSAM(None, 6, 19, "SAM-H").eval().cuda()
+if len(sys.argv) > 1: m.set_engine_option("attention_tc", int(sys.argv[1]))   # attention mode bits (see csrc/model.cu)
 x = torch.from_numpy(synth.synthetic_tiles(4, 1024, seed=1)).cuda()
 nuc = [synth.synthetic_nuclei(1024, 700, seed=i) for i in range(4)]
 lg = [synth.head_logits_from_maps(n["np_bin"], n["nt"], 6) for n in nuc]
