@@ -40,6 +40,17 @@ constexpr int W_KA = 96;                   // keys of the first half (6 k-steps)
 
 __device__ __forceinline__ uint32_t sel_b32(bool c, uint32_t a, uint32_t b) { return c ? a : b; }
 
+// Two softmax weights 2^((s - m) scale log2 e) as one packed fp16 pair for the P V MMA. `ex2.approx.f16x2` is two MUFU ops plus a
+// conversion (F2FP) and a PRMT on this chip and the F2FP shares the MUFU's issue queue, which made the exponential pass
+// queue-bound. Here: fp32 MUFU of the argument rebiased by -112 (mneg carries it), so the result 2^(y - 112) has the fp16
+// exponent in the fp32 exponent field and (bits + 0x1000) >> 13 IS the fp16 encoding (round half up). The caller scales the weights by
+// 2^8 (maximum = 256, row sums stay in fp32): fp32 MUFU flushes below 2^-126, i.e. weights below 2^-22 of the maximum, where fp16
+// denormals of an unscaled weight would still have carried the collective mass of a peaked row's tail (measured: 2x the error) -- integer ops on the ALU / FMA pipes instead of a second queue slot.
+__device__ __forceinline__ uint32_t exp_pair(float s0, float s1, float sl2, float mneg) {
+    const uint32_t b0 = __float_as_uint(ptx::ex2(fmaf(s0, sl2, mneg))), b1 = __float_as_uint(ptx::ex2(fmaf(s1, sl2, mneg)));
+    return ((b0 + 0x1000u) >> 13) | (((b1 + 0x1000u) << 3) & 0xFFFF0000u);
+}
+
 // in[i] (i = 0..27, fp16 pairs in p[0..13], p[14] = 0) -> out[k] = in[s + k], k = 0..13 (7 packed registers), 0 <= s <= 13
 __device__ __forceinline__ void barrel14(const uint32_t (&p)[15], int s, uint32_t (&out)[7]) {
     uint32_t t1[11], t2[9], t3[8];
@@ -58,13 +69,15 @@ __device__ __forceinline__ void barrel14(const uint32_t (&p)[15], int s, uint32_
 __global__ void __launch_bounds__(W_THREADS, 1)
 window_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                  const __grid_constant__ CUtensorMap tmK16, const __grid_constant__ CUtensorMap tmR, int heads, int n_items,
-                 float scale, __half* __restrict__ out) {
+                 float scale, __half* __restrict__ out, long long* __restrict__ trace) {
     extern __shared__ uint8_t w_smem_raw[];
     const uint32_t smem_base = (ptx::smem_u32(w_smem_raw) + 1023u) & ~1023u;
     uint8_t* smem_gen = w_smem_raw + (smem_base - ptx::smem_u32(w_smem_raw));
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
     const int D = heads * W_HD;
     const int n_work = n_items * heads;
+    // debug timeline (tools/trace_window.py): CTA 0 stamps clock64() per event for its first 8 items
+#define W_TR(ev) do { if (trace != nullptr && blockIdx.x == 0 && it < 8 && lane == 0) trace[it * 64 + (ev)] = clock64(); } while (0)
 
     const uint32_t sQ0 = smem_base;              // [group] Q columns 0..63
     const uint32_t sQG = sQ0 + 2 * W_QB;          // [group] Q columns 64..79 (TMA) | Gsel_h 14 + 2 | Gsel_w 14 + 2 (threads) | unused
@@ -84,7 +97,6 @@ window_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     auto s_full = [&](int g) { return bar + 8u * (9 + g); };
     auto p_full = [&](int g) { return bar + 8u * (11 + g); };
     auto o_full = [&](int g) { return bar + 8u * (13 + g); };
-    auto o_free = [&](int g) { return bar + 8u * (15 + g); };
     const uint32_t tmem_slot = bar + 8u * 17;
 
     if (warp == 0 && lane == 0) {
@@ -95,7 +107,7 @@ window_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         ptx::mbar_init(v_full, 1); ptx::mbar_init(v_free, 2);
         for (int g = 0; g < 2; ++g) {
             ptx::mbar_init(g_full(g), 1); ptx::mbar_init(qg_ready(g), 256); ptx::mbar_init(s_full(g), 1);
-            ptx::mbar_init(p_full(g), 256); ptx::mbar_init(o_full(g), 1); ptx::mbar_init(o_free(g), 256);
+            ptx::mbar_init(p_full(g), 256); ptx::mbar_init(o_full(g), 1);
         }
         ptx::fence_barrier_init();
     }
@@ -153,6 +165,7 @@ window_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
             const int row0 = item * W_S;
             const uint32_t par = (uint32_t)(it & 1);
             ptx::mbar_wait(qk_free, par ^ 1u);     // both groups' S (and G) MMAs of the previous item have completed
+            W_TR(0);
             if (ptx::elect_one()) {
                 ptx::mbar_expect_tx(qk_full, 4 * W_QB + 2 * W_KB);
 #pragma unroll
@@ -169,6 +182,7 @@ window_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                 ptx::tma_load_2d(sKt + 3 * 8192, &tmK16, qk_full, D + head * W_HD + 16, row0 + 192);
             }
             ptx::mbar_wait(v_free, par ^ 1u);      // both groups' P V of the previous item have completed
+            W_TR(1);
             if (ptx::elect_one()) {
                 ptx::mbar_expect_tx(v_full, 2 * W_KB);
 #pragma unroll
@@ -178,6 +192,24 @@ window_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                 }
                 ptx::tma_load_2d(sV0 + 3 * 8192, &tmK16, v_full, 2 * D + head * W_HD, row0 + 192);
                 ptx::tma_load_2d(sV1 + 3 * 8192, &tmK16, v_full, 2 * D + head * W_HD + 64, row0 + 192);
+            }
+            // L2 prefetch of the next item's operands: all CTAs reload at about the same time, and a DRAM-latency burst of
+            // 148 x 168 KB would otherwise sit between this item's S MMAs and the next item's G
+            if (w + (int)gridDim.x < n_work && ptx::elect_one()) {
+                const int w2 = w + (int)gridDim.x, item2 = w2 / heads, head2 = w2 - item2 * heads, r2 = item2 * W_S;
+#pragma unroll
+                for (int g = 0; g < 2; ++g) {
+                    ptx::tma_prefetch_2d(&tmQ, head2 * W_HD, r2 + g * W_BQ);
+                    ptx::tma_prefetch_2d(&tmQ, head2 * W_HD + 64, r2 + g * W_BQ);
+                }
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    const CUtensorMap* tm = t < 3 ? &tmK : &tmK16;
+                    ptx::tma_prefetch_2d(tm, D + head2 * W_HD, r2 + t * 64);
+                    ptx::tma_prefetch_2d(tm, D + head2 * W_HD + 64, r2 + t * 64);
+                    ptx::tma_prefetch_2d(tm, 2 * D + head2 * W_HD, r2 + t * 64);
+                    ptx::tma_prefetch_2d(tm, 2 * D + head2 * W_HD + 64, r2 + t * 64);
+                }
             }
         }
     } else if (warp == 1 || warp == 2) {
@@ -193,13 +225,9 @@ window_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         const uint64_t descv_hi = desc_hi | ((uint64_t)((W_KB >> 4) & 0x3FFF) << 16);
         auto descv = [&](uint32_t addr) { return descv_hi | (uint64_t)((addr >> 4) & 0x3FFF); };
         ptx::mbar_wait(const_full, 0);
-        int it = 0;
-        for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++it) {
-            const uint32_t par = (uint32_t)(it & 1);
-            ptx::mbar_wait(qk_full, par);
-            ptx::mbar_wait(o_free(g), par ^ 1u);   // the previous item's O / l have been read out: the group's columns are free
-            ptx::tc_fence_after();
-            const uint64_t a0 = desc(sQ0 + g * W_QB), aq = desc(sQG + g * W_QB);
+        const uint64_t a0 = desc(sQ0 + g * W_QB), aq = desc(sQG + g * W_QB);
+        // G = Q Rcat^T of the item whose Q has just landed, into the S columns 0..63 of the group
+        auto issue_g = [&]() {
             if (ptx::elect_one()) {
                 const uint64_t r0 = desc(sR0), rt = desc(sRt);
 #pragma unroll
@@ -208,8 +236,20 @@ window_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                 ptx::umma_commit(g_full(g));
             }
             __syncwarp();
-            ptx::mbar_wait(qg_ready(g), par);      // Gsel written (and G read out of the S columns)
+        };
+        int it = 0;
+        if (blockIdx.x < n_work) {
+            ptx::mbar_wait(qk_full, 0);
             ptx::tc_fence_after();
+            W_TR(9 + 8 * g);
+            issue_g();
+        }
+        for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++it) {
+            const uint32_t par = (uint32_t)(it & 1);
+            // Gsel written -- which also means that every thread of the group has read G and the previous item's O / l
+            ptx::mbar_wait(qg_ready(g), par);
+            ptx::tc_fence_after();
+            W_TR(10 + 8 * g);
             if (ptx::elect_one()) {
                 const uint64_t b0 = desc(sK0), bt = desc(sKt), bs = desc(sSel);
 #pragma unroll
@@ -222,8 +262,10 @@ window_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
             }
             __syncwarp();
             ptx::mbar_wait(v_full, par);
+            W_TR(11 + 8 * g);
             ptx::mbar_wait(p_full(g), par);
             ptx::tc_fence_after();
+            W_TR(12 + 8 * g);
             if (ptx::elect_one()) {
 #pragma unroll
                 for (int k = 0; k < W_KP / 16; ++k) {   // 13 k-steps of 16 keys; P chunk = 8 packed TMEM columns
@@ -235,6 +277,16 @@ window_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                 ptx::umma_commit(v_free);
             }
             __syncwarp();
+            if (w + (int)gridDim.x < n_work) {
+                // next item's G while the softmax threads store this item's output: Q of the next item landed long ago (its
+                // load started when this item's S MMAs completed); P V must have finished reading P out of columns 0..47
+                ptx::mbar_wait(qk_full, par ^ 1u);
+                W_TR(8 + 8 * g);
+                ptx::mbar_wait(o_full(g), par);
+                ptx::tc_fence_after();
+                W_TR(13 + 8 * g);
+                issue_g();
+            }
         }
     } else if (warp >= 4) {
         // ===================================================== softmax / output: two threads per query row
@@ -260,7 +312,10 @@ window_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
             const uint32_t par = (uint32_t)(it & 1);
             const uint32_t ts = tS(grp) + lane_off;
             // ---- Gsel: this thread's table half (half 0: rel_h, G columns 0..26; half 1: rel_w, G columns 32..58)
+            const int trb = 24 + 8 * grp + 16 * half;
+            const bool trw = quad == 0;
             ptx::mbar_wait(g_full(grp), par);
+            if (trw) W_TR(trb);
             if (warp_ok) {
                 ptx::tc_fence_after();
                 uint32_t gv[32];
@@ -284,8 +339,10 @@ window_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                 ptx::fence_proxy_async();
             }
             ptx::mbar_arrive(qg_ready(grp));
+            if (trw) W_TR(trb + 1);
             // ---- softmax over this thread's keys
             ptx::mbar_wait(s_full(grp), par);
+            if (trw) W_TR(trb + 2);
             if (warp_ok) {
                 ptx::tc_fence_after();
                 const uint32_t tk = ts + (half == 0 ? 0u : (uint32_t)W_KA);     // first score column of this half
@@ -308,23 +365,23 @@ window_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                 *x_mine = mx;
                 ptx::named_bar_sync(pair_bar, 64);
                 mx = fmaxf(mx, *x_peer);
-                const float mneg = -mx * sl2;
+                if (trw) W_TR(trb + 3);
+                const float mneg = fmaf(-mx, sl2, -104.0f);   // exponent rebias of exp_pair (-112) folded in, and the weights scaled by 2^8
 #pragma unroll 1
                 for (int c = 0; c < 3; ++c) {
                     uint32_t v[32], pk[16];
                     ptx::tmem_ld32(tk + 32u * c, v);
                     ptx::tmem_ld_wait();
 #pragma unroll
-                    for (int j = 0; j < 16; ++j)
-                        pk[j] = ptx::ex2_f16x2(pack_h2(fmaf(fl(v[2 * j]), sl2, mneg), fmaf(fl(v[2 * j + 1]), sl2, mneg)));
+                    for (int j = 0; j < 16; ++j) pk[j] = exp_pair(fl(v[2 * j]), fl(v[2 * j + 1]), sl2, mneg);
                     ptx::tmem_st16(tp + 16u * c, pk);
                 }
                 if (half == 1) {
                     uint32_t v[16], pk[16];
                     ptx::tmem_ld16(tk + 96u, v);
                     ptx::tmem_ld_wait();
-                    pk[0] = ptx::ex2_f16x2(pack_h2(fmaf(fl(v[0]), sl2, mneg), fmaf(fl(v[1]), sl2, mneg)));
-                    pk[1] = ptx::ex2_f16x2(pack_h2(fmaf(fl(v[2]), sl2, mneg), fmaf(fl(v[3]), sl2, mneg)));
+                    pk[0] = exp_pair(fl(v[0]), fl(v[1]), sl2, mneg);
+                    pk[1] = exp_pair(fl(v[2]), fl(v[3]), sl2, mneg);
 #pragma unroll
                     for (int j = 2; j < 16; ++j) pk[j] = 0u;       // keys 196..207: weight 0
                     ptx::tmem_st16(tp + 48u, pk);
@@ -333,8 +390,10 @@ window_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                 ptx::tc_fence_before();
             }
             ptx::mbar_arrive(p_full(grp));
+            if (trw) W_TR(trb + 4);
             // ---- output: half 0 stores head-dim columns 0..47, half 1 columns 48..79
             ptx::mbar_wait(o_full(grp), par);
+            if (trw) W_TR(trb + 5);
             if (warp_ok) {
                 ptx::tc_fence_after();
                 const uint32_t to = ts + W_COL_O;
@@ -347,20 +406,20 @@ window_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                 const float inv = 1.0f / fl(l16[0]);
                 auto f = [&](uint32_t u) { return __uint_as_float(u) * inv; };
                 if (row_ok) {
+                    // each thread owns 96 / 64 contiguous bytes of its row: 32-byte stores (one full sector per request)
                     __half* dst = out + ((long long)item * W_S + qi) * D + head * W_HD + (half == 0 ? 0 : 48);
-#pragma unroll
-                    for (int i = 0; i < 32; i += 8)
-                        *reinterpret_cast<uint4*>(dst + i) = make_uint4(pack_h2(f(d0[i]), f(d0[i + 1])), pack_h2(f(d0[i + 2]), f(d0[i + 3])),
-                                                                        pack_h2(f(d0[i + 4]), f(d0[i + 5])), pack_h2(f(d0[i + 6]), f(d0[i + 7])));
-                    if (half == 0) {
-#pragma unroll
-                        for (int i = 0; i < 16; i += 8)
-                            *reinterpret_cast<uint4*>(dst + 32 + i) = make_uint4(pack_h2(f(d1[i]), f(d1[i + 1])), pack_h2(f(d1[i + 2]), f(d1[i + 3])),
-                                                                                 pack_h2(f(d1[i + 4]), f(d1[i + 5])), pack_h2(f(d1[i + 6]), f(d1[i + 7])));
-                    }
+                    auto st32 = [&](__half* ptr, const uint32_t* d) {
+                        asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(ptr), "r"(pack_h2(f(d[0]), f(d[1]))),
+                                     "r"(pack_h2(f(d[2]), f(d[3]))), "r"(pack_h2(f(d[4]), f(d[5]))), "r"(pack_h2(f(d[6]), f(d[7]))),
+                                     "r"(pack_h2(f(d[8]), f(d[9]))), "r"(pack_h2(f(d[10]), f(d[11]))), "r"(pack_h2(f(d[12]), f(d[13]))),
+                                     "r"(pack_h2(f(d[14]), f(d[15]))) : "memory");
+                    };
+                    st32(dst, d0);
+                    st32(dst + 16, d0 + 16);
+                    if (half == 0) st32(dst + 32, d1);
                 }
             }
-            ptx::mbar_arrive(o_free(grp));
+            if (trw) W_TR(trb + 6);
         }
     }
     ptx::tc_fence_before();
@@ -372,6 +431,8 @@ window_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 }  // namespace
 
 // ------------------------------------------------------------------------------------------ host side
+static long long* g_window_trace = nullptr;   // debug: device buffer of 8 x 64 clock stamps (cellvit_b200_debug.h)
+extern "C" __attribute__((visibility("default"))) void cvb_debug_window_trace(void* dev_buf) { g_window_trace = reinterpret_cast<long long*>(dev_buf); }
 bool op_window_attention_tc_supported(int S, int hd, int gh, int gw) { return hd == W_HD && S == W_S && gh == W_G && gw == W_G; }
 
 int op_window_attention_tc(const __half* qkv, int n_items, int heads, int hd, float scale, const __half* relcat, __half* out,
@@ -393,7 +454,7 @@ int op_window_attention_tc(const __half* qkv, int n_items, int heads, int hd, fl
     CVB_TRY(cvb_tmap_2d_f16(&tr, relcat, (uint64_t)W_HD, 64, (uint64_t)W_HD * 2, 64, 64));
     const int n_work = n_items * heads;
     const int grid = n_work < cvb_num_sms() ? n_work : cvb_num_sms();
-    window_tc_kernel<<<grid, W_THREADS, W_SMEM, stream>>>(tq, tk, tk16, tr, heads, n_items, scale, out);
+    window_tc_kernel<<<grid, W_THREADS, W_SMEM, stream>>>(tq, tk, tk16, tr, heads, n_items, scale, out, g_window_trace);
     cvb_note_launches(1);
     CVB_CUDA(cudaGetLastError());
     return CVB_OK;

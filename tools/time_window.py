@@ -62,3 +62,16 @@ for i in range(30):
     ts.append(a.elapsed_time(b) * 1e3)
 ts = sorted(ts[5:])
 print(f"variant {variant} items {n_items}: max err {err:.2e} finite {finite} median {ts[len(ts) // 2]:.1f} us min {ts[0]:.1f} us")
+if len(sys.argv) > 4:
+    d = (out[:chk * S].float() - ref).abs()
+    i = int(d.argmax()); r, c = divmod(i, D)
+    print("mean err %.3e; worst at row %d (q %d of item %d) col %d (head %d dim %d): got %.5f want %.5f" % (
+        d.mean().item(), r, r % S, r // S, c, c // hd, c % hd, out[r, c].item(), ref[r, c].item()))
+    print("err by query group: rows<128 %.3e rows>=128 %.3e" % (d.view(chk, S, D)[:, :128].max().item(), d.view(chk, S, D)[:, 128:].max().item()))
+    print("err by col block: <48 %.3e >=48 %.3e" % (d.view(chk * S, heads, hd)[:, :, :48].max().item(), d.view(chk * S, heads, hd)[:, :, 48:].max().item()))
+    # same reference with the bias quantised the way the kernel carries it (fp16 of rel / scale)
+    qh_ = lambda t: (t / scale).half().float() * scale
+    att2 = ((q * scale) @ k.transpose(-1, -2)).view(chk, heads, gh, gw, gh, gw) + qh_(rel_h)[..., :, None] + qh_(rel_w)[..., None, :]
+    ref2 = (att2.view(chk, heads, S, S).softmax(-1) @ v).permute(0, 2, 1, 3).reshape(chk * S, D)
+    d2 = (out[:chk * S].float() - ref2).abs()
+    print("vs the reference with fp16-quantised bias/scale: max %.3e mean %.3e" % (d2.max().item(), d2.mean().item()))
