@@ -1,22 +1,28 @@
 #!/usr/bin/env python
 # -*- coding: utf-8 -*-
-"""Headline benchmark: 1024x1024 tiles/s, CellViT-SAM-H inference + HoVer-Net post-processing (BASELINE.json).
+"""Headline benchmark: 1024x1024 tiles/s, CellViT inference + HoVer-Net post-processing (BASELINE.json).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--arch SAM-H|ViT256] [--batch B]
 
-A step = one batch of B=4 synthetic 1024^2 RGB tiles through the hot path: cvb_forward (SAM-H, random-init
-weights of the reference architecture) + cvb_postproc. Random-init networks emit spatially constant argmax
-maps, so -- as the survey prescribes -- post-processing runs on seeded synthetic-nuclei
-head maps (700 nuclei / tile) that are resident on the device in place of the head outputs; the forward still
-runs in full on the synthetic tiles every step.
+Default workload = BASELINE.json configs[2] (the configuration the metric is quoted on): CellViT-SAM-H, B = 4 synthetic
+1024^2 RGB tiles per GPU per step, on-GPU post-processing. `--arch ViT256` (default batch 8) is configs[1].
 
- value : tiles/s with inputs resident in HBM (forward + device post-processing: label maps + instance tables).
- e2e   : tiles/s through the public Python API (model.forward + softmax + calculate_instance_map incl. host
-         contours/dicts) with HOST buffers: pinned H2D of the tiles and D2H of label maps + tables every step.
- roofline : tile-engine kernel (tc_kernel, tcgen05) -- algorithmic FLOPs / sum of its CUDA-event launch times.
+A step = one batch through the hot path: cvb_forward (random-init weights of the reference architecture) + cvb_postproc
++ cvb_contours. Random-init networks emit spatially constant argmax maps, so -- as the survey
+prescribes -- post-processing runs on seeded synthetic-nuclei head maps (700 nuclei / tile) that are resident on the
+device in place of the head outputs; the forward still runs in full on the synthetic tiles every step.
+
+ value    : tiles/s with inputs resident in HBM (forward + device post-processing: label maps, instance tables, contours;
+            post-processing of batch k overlaps the forward of batch k+1 on a second stream, as in the product pipeline).
+ overlap  : forward-only and post-processing-only step times measured in the same run; loss_ms = ms_per_step - forward_only_ms
+            is what the post-processing costs on top of the forward it hides behind.
+ e2e      : tiles/s through the public Python API (CellSegmentationInference.process_tiles) with HOST buffers: pinned H2D of
+            the tiles and D2H of label maps + tables + contours every step, host dict building included.
+ roofline : tile-engine kernel (tc_kernel / conv_patch_kernel, tcgen05) -- algorithmic FLOPs / sum of its CUDA-event launch
+            times; `postproc` = HBM-bound post-processing kernels against the committed ncu DRAM-byte capture.
  cpu_baseline : the oracle port (oracle/, fp32 torch CPU forward + C post-processing) on the host cores, N=1 only.
 --impl reference : the same oracle port as the reference's CPU path (the reference itself is Python and needs
- /root/reference, which does not exist on the GPU box).
+ /root/reference, which does not exist on the GPU box). It uses no GPU.
 """
 from __future__ import annotations
 
@@ -34,19 +40,24 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-ARCH = "SAM-H"
 TILE = 1024
-BATCH = 4
 N_NUCLEI = 700
-METRIC = "1024x1024 tiles/sec (CellViT-SAM-H inference+postproc)"
-# the workload both arms run (config.workload); the arms differ only in how many tiles make one step
-WORKLOAD = (f"CellViT-{ARCH} inference + HV watershed post-processing on injected synthetic-nuclei head maps ({N_NUCLEI} nuclei/tile), "
+# algorithmic GFLOP per tile (shared skip decoders once) and the share outside the tile-engine kernel
+# (attention core Q K^T / P V / rel-pos einsums: SAM-H 28 windowed blocks x 5.3 + 4 global x 87.2; ViT-S 12 blocks x 25.8)
+ARCHS = {
+    "SAM-H": dict(batch=4, gflop=9816.8, gflop_attn=28 * 5.3 + 4 * 87.2, name="CellViT-SAM-H"),
+    "ViT256": dict(batch=8, gflop=3378.9, gflop_attn=12 * 25.8, name="CellViT-256"),
+}
+
+
+def metric_name(arch):
+    return f"1024x1024 tiles/sec ({ARCHS[arch]['name']} inference+postproc)"
+
+
+def workload_name(arch):
+    # the workload both arms run (config.workload); the arms differ only in how many tiles make one step
+    return (f"{ARCHS[arch]['name']} inference + HV watershed post-processing on injected synthetic-nuclei head maps ({N_NUCLEI} nuclei/tile), "
             f"synthetic {TILE}x{TILE} tiles, random-init weights")
-# algorithmic GFLOP per SAM-H tile (shared skip decoders once) and the share that runs in
-# the tile-engine kernel (everything except the attention core QK^T / PV / rel-pos einsums: 28*5.3 + 4*87.2 G).
-GFLOP_PER_TILE = 9816.8
-GFLOP_ATTENTION_CORE = 28 * 5.3 + 4 * 87.2
-GFLOP_TC_PER_TILE = GFLOP_PER_TILE - GFLOP_ATTENTION_CORE
 
 
 def _peaks():
@@ -79,35 +90,34 @@ class ClockSampler:
         self.f.flush()
         rows = [l.strip().split(", ") for l in open(self.f.name) if l.strip()]
         os.unlink(self.f.name)
-        sm, mx, reasons = [], [], set()
+        sm, mx, pw, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in rows:
             try:
-                sm.append(float(r[0])); mx.append(float(r[1]))
+                sm.append(float(r[0])); mx.append(float(r[1])); pw.append(float(r[2]))
                 for n, v in zip(names, r[3:7]):
                     if v.strip().lower().startswith("active"):
                         reasons.add(n)
             except Exception:
                 continue
-        # under load = upper half of the samples by power is not available per row reliably; use the median of all samples
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "power_w": float(np.median(pw)) if pw else None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
 # ------------------------------------------------------------------------------------------------ CPU legs (oracle)
-def cpu_tile_seconds(threads: int, tiles: int = 1):
+def cpu_tile_seconds(arch: str, threads: int, tiles: int = 1):
     """Oracle port on the host: fp32 torch forward (all threads) + C post-processing (1 thread), per 1024^2 tile."""
     import torch
     from cellvit_b200 import synth, weights
     from oracle import forward_oracle, postproc_oracle as po
     torch.set_num_threads(threads)
-    sd = weights.synth_state_dict(ARCH, 6, 19, seed=0)
+    sd = weights.synth_state_dict(arch, 6, 19, seed=0)
     nuc = synth.synthetic_nuclei(TILE, N_NUCLEI, 0)
     t_f = t_p = 0.0
     for i in range(tiles):
         x = torch.from_numpy(synth.synthetic_tiles(1, TILE, seed=i))
         t0 = time.perf_counter()
-        forward_oracle.cellvit_forward(sd, x, ARCH, retrieve_tokens=True)
+        forward_oracle.cellvit_forward(sd, x, arch, retrieve_tokens=True)
         t1 = time.perf_counter()
         pm = np.concatenate([nuc["nt"][..., None], nuc["np_bin"][..., None], nuc["hv"].transpose(1, 2, 0)], -1).astype(np.float64)
         po.DetectionCellPostProcessor(6, 40).post_process_cell_segmentation(pm)
@@ -123,18 +133,20 @@ def run_reference(args):
         return
     cores = os.cpu_count() or 1
     budget = 150.0
-    tf, tp = cpu_tile_seconds(cores, 1)            # also the warm-up
+    tf, tp = cpu_tile_seconds(args.arch, cores, 1)            # also the warm-up
     per = tf + tp
     steps = max(1, min(args.steps, int(budget // per)))
     t0 = time.perf_counter()
-    tf2, tp2 = cpu_tile_seconds(cores, steps)
+    tf2, tp2 = cpu_tile_seconds(args.arch, cores, steps)
     el = time.perf_counter() - t0
     v = steps / el
     sample = f"{steps} tile(s) of 1 (steps capped by a {budget:.0f}s budget); forward {tf2:.2f}s + postproc {tp2:.2f}s per tile"
     print(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": v, "unit": "tiles/s", "n_gpus": args.gpus, "steps": steps, "warmup": 1,
+        "impl": "reference", "metric": metric_name(args.arch), "value": v, "unit": "tiles/s", "n_gpus": args.gpus, "gpus_used": 0,
+        "steps": steps, "warmup": 1,
         "ms_per_step": 1000.0 * el / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic", "config": {"workload": WORKLOAD, "batch": "1 tile per step on the host cores (bounded sample, no GPU used)"},
+        "data": "synthetic", "config": {"workload": workload_name(args.arch),
+                                        "batch": "1 tile per step on the host cores (bounded sample; CPU port of the reference, no GPU used)"},
         "cpu_baseline": {"value": v, "unit": "tiles/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "tiles/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}))
 
@@ -145,8 +157,8 @@ def run_gpu(args):
     import torch.distributed as dist
     from cellvit_b200 import _lib as L
     from cellvit_b200 import synth
-    from cellvit_b200.cellvit import CellViTSAM
-    from cellvit_b200.post_proc_cellvit import DetectionCellPostProcessor
+    from cellvit_b200.cellvit import CellViT256, CellViTSAM
+    from cellvit_b200.post_proc_cellvit import MAX_PTS, ROWS_COPIED, DetectionCellPostProcessor
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -159,19 +171,24 @@ def run_gpu(args):
         dist.init_process_group("nccl", device_id=dev)
     lib = L.lib()
     lib.cvb_launch_count.restype = C.c_longlong
-    B, K, Wm = BATCH, args.steps, args.warmup
+    arch = args.arch
+    cfg = ARCHS[arch]
+    B, K, Wm = args.batch or cfg["batch"], args.steps, args.warmup
+    gflop_tc = cfg["gflop"] - cfg["gflop_attn"]
 
-    # ---- model: weights created on rank 0 only, broadcast once over NCCL (collective C1)
+    # ---- model: every rank builds the architecture, rank 0's weights are broadcast once over NCCL (collective C1)
     torch.manual_seed(0)
-    model = CellViTSAM(None, 6, 19, ARCH).eval().to(dev)
+    model = (CellViTSAM(None, 6, 19, arch) if arch != "ViT256" else CellViT256(None, 6, 19)).eval().to(dev)
     if world > 1:
         with torch.no_grad():
-            flat = torch.cat([p.detach().reshape(-1).float() for p in list(model.parameters()) + [b for b in model.buffers() if b.dtype.is_floating_point]])
+            tensors = list(model.parameters()) + [b for b in model.buffers() if b.dtype.is_floating_point]
+            flat = torch.cat([p.detach().reshape(-1).float() for p in tensors])
             dist.broadcast(flat, 0)
             o = 0
-            for t in list(model.parameters()) + [b for b in model.buffers() if b.dtype.is_floating_point]:
+            for t in tensors:
                 n = t.numel(); t.copy_(flat[o:o + n].view_as(t)); o += n
             del flat
+        model.invalidate_packed()
     proc = DetectionCellPostProcessor(nr_types=6, magnification=40)
 
     # ---- inputs: rank r owns tiles r, r+world, ... of the synthetic stream (weak scaling: B tiles per rank per step)
@@ -182,8 +199,8 @@ def run_gpu(args):
     np_dev = torch.from_numpy(np.stack([l[0] for l in logits])).to(dev)
     nt_dev = torch.from_numpy(np.stack([l[1] for l in logits])).to(dev)
     hv_dev = torch.from_numpy(np.stack([n["hv"] for n in nuc])).to(dev)
-    lab_host = torch.empty(B, TILE, TILE, dtype=torch.int32).pin_memory()
 
+    # post-processing on a default (= lowest) priority stream; the forward graph's kernels carry high priority (cellvit.py)
     s_post = torch.cuda.Stream(dev)
     main = torch.cuda.current_stream(dev)
 
@@ -197,39 +214,49 @@ def run_gpu(args):
             with torch.cuda.stream(s_post):
                 gather.flush()
 
-    def step_device():
-        # forward of batch k on the main stream; post-processing of batch k on a second stream once that forward has
-        # finished (the dependency of the real pipeline), so it overlaps the forward of batch k+1 -- the same
-        # structure as CellSegmentationInference.process_tiles
+    def forward_once():
         with torch.no_grad():
             if args.graphs:
                 model.forward_graphed(x_dev, retrieve_tokens=True, slot=0)
             else:
                 model(x_dev, retrieve_tokens=True)
+
+    def post_once(exchange=True):
+        w = proc._workspace(B, TILE, TILE, dev)
+        L.check(lib.cvb_postproc(L.ptr(np_dev), L.ptr(hv_dev), L.ptr(nt_dev), B, TILE, TILE, 6, 40, L.ptr(w.labels), L.ptr(w.table),
+                                 L.ptr(w.counts), proc.max_rows, L.ptr(w.ws), C.c_size_t(w.ws.numel()), L.stream_ptr()), "cvb_postproc")
+        w.launch_contours(B, TILE, TILE, proc.max_rows)   # per-instance contours on the device (cvb_contours)
+        if not exchange:
+            return
+        if gather is not None:  # collective C2 staged and exchanged once per --gather-every steps
+            gather.add(w.counts, w.table)
+        elif world > 1:  # collective C2 per step: all-gather of the per-tile instance tables (counts, then the first 1024 rows)
+            cnts = [torch.empty_like(w.counts) for _ in range(world)]
+            dist.all_gather(cnts, w.counts)
+            part = w.table[:, :1024].contiguous()
+            tabs = [torch.empty_like(part) for _ in range(world)]
+            dist.all_gather(tabs, part)
+
+    def step_device():
+        # forward of batch k on the main stream; post-processing of batch k on a second stream once that forward has
+        # finished (the dependency of the real pipeline), so it overlaps the forward of batch k+1 -- the same
+        # structure as CellSegmentationInference.process_tiles
+        forward_once()
+        if args.no_post:
+            return
         fwd_done = torch.cuda.Event()
         fwd_done.record(main)
         s_post.wait_event(fwd_done)
         with torch.cuda.stream(s_post):
-            w = proc._workspace(B, TILE, TILE, dev)
-            L.check(lib.cvb_postproc(L.ptr(np_dev), L.ptr(hv_dev), L.ptr(nt_dev), B, TILE, TILE, 6, 40, L.ptr(w.labels), L.ptr(w.table),
-                                     L.ptr(w.counts), proc.max_rows, L.ptr(w.ws), C.c_size_t(w.ws.numel()), L.stream_ptr()), "cvb_postproc")
-            w.launch_contours(B, TILE, TILE, proc.max_rows)   # per-instance contours on the device (cvb_contours)
-            if gather is not None:  # collective C2 staged and exchanged once per --gather-every steps
-                gather.add(w.counts, w.table)
-            elif world > 1:  # collective C2: all-gather of the per-tile instance tables (counts, then the first 1024 rows)
-                cnts = [torch.empty_like(w.counts) for _ in range(world)]
-                dist.all_gather(cnts, w.counts)
-                part = w.table[:, :1024].contiguous()
-                tabs = [torch.empty_like(part) for _ in range(world)]
-                dist.all_gather(tabs, part)
+            post_once()
 
     from cellvit_b200.cell_detection import CellSegmentationInference
     inf = CellSegmentationInference.from_model(model, local)
     override = {"nuclei_binary_map": np_dev, "hv_map": hv_dev, "nuclei_type_map": nt_dev}  # injected synthetic nuclei
 
     def run_e2e(n_batches):
-        # public API: pinned-host tiles in, per-tile instance dicts out (H2D, forward, softmax, device post-processing,
-        # D2H of label maps + tables, host contours/dicts; host work of batch k overlaps device work of batch k+1)
+        # public API: pinned-host tiles in, per-tile instance dicts out (H2D, forward, device post-processing,
+        # D2H of label maps + tables + contours, host dicts; host work of batch k overlaps device work of batch k+1)
         res = inf.process_tiles([tiles_host] * n_batches, magnification=40, head_override=override, use_graphs=bool(args.graphs))
         return sum(len(d) for d in res[-1])
 
@@ -238,6 +265,19 @@ def run_gpu(args):
         if world > 1:
             dist.barrier()
             torch.cuda.synchronize()
+
+    def timed(fn, n, flush=None):
+        """n calls of fn between two events on the main stream (the post stream is joined before the second one)."""
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(n):
+            fn()
+        if flush is not None:
+            flush()
+        main.wait_stream(s_post)
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b)
 
     # launches of one forward (a graph replay does not pass through the launch counter)
     lib.cvb_launch_count(1)
@@ -267,26 +307,64 @@ def run_gpu(args):
     ms_total = float(ms.item())
     value = world * B * K / (ms_total / 1000.0)
 
+    # ---- what the overlap costs: the same step without post-processing, and the post-processing alone (rank-local; max over ranks)
+    Ko = max(3, min(K, 10))
+    ov = None
+    if not args.no_post:
+        sync_all()
+        f_ms = timed(forward_once, Ko) / Ko
+
+        def post_alone():
+            with torch.cuda.stream(s_post):
+                post_once(exchange=False)
+        p_ms = timed(post_alone, Ko) / Ko
+        c_ms = None
+        if world > 1:
+            def exch():
+                with torch.cuda.stream(s_post):
+                    w = proc._workspace(B, TILE, TILE, dev)
+                    if gather is not None:
+                        gather.add(w.counts, w.table)
+                    else:
+                        cnts = [torch.empty_like(w.counts) for _ in range(world)]
+                        dist.all_gather(cnts, w.counts)
+                        part = w.table[:, :1024].contiguous()
+                        tabs = [torch.empty_like(part) for _ in range(world)]
+                        dist.all_gather(tabs, part)
+            sync_all()
+            n_ex = max(Ko, args.gather_every * 2)
+            c_ms = timed(exch, n_ex, flush_gather) / n_ex
+            t3 = torch.tensor([f_ms, p_ms, c_ms], device=dev)
+            dist.all_reduce(t3, op=dist.ReduceOp.MAX)
+            f_ms, p_ms, c_ms = (float(v) for v in t3.tolist())
+        ov = {"forward_only_ms": f_ms, "post_only_ms": p_ms, "loss_ms": ms_total / K - f_ms, "steps": Ko,
+              "collective_ms_per_step": c_ms,
+              "collective": None if world == 1 else ("ncclAllGather of the staged instance tables once per %d steps (TableGather)" % args.gather_every
+                                                     if gather is not None else "two ncclAllGather per step (counts, then 1024 table rows)")}
+
     # ---- e2e through the Python API with host buffers
-    n_cells = run_e2e(2)
-    sync_all()
-    Ke = max(2, min(K, 20))
-    t0 = time.perf_counter()
-    n_cells = run_e2e(Ke)
-    torch.cuda.synchronize()
-    te = torch.tensor([time.perf_counter() - t0], device=dev)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = world * B * Ke / float(te.item())
-    h2d = tiles_host.numel() * 4
-    d2h = B * TILE * TILE * 4 + B * 4 + B * 2048 * 88
+    e2e = None
+    if not args.no_post:
+        run_e2e(2)
+        sync_all()
+        Ke = max(2, min(K, 20))
+        t0 = time.perf_counter()
+        run_e2e(Ke)
+        torch.cuda.synchronize()
+        te = torch.tensor([time.perf_counter() - t0], device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        rows = min(ROWS_COPIED, proc.max_rows)
+        e2e = {"value": world * B * Ke / float(te.item()), "unit": "tiles/s", "h2d_bytes_per_step": tiles_host.numel() * 4,
+               # label maps + counts + per tile the eagerly copied rows of the instance table, contour points and point counts
+               "d2h_bytes_per_step": B * TILE * TILE * 4 + B * 4 + B * rows * (88 + MAX_PTS * 2 * 2 + 4), "steps": Ke,
+               "api": "CellSegmentationInference.process_tiles: H2D + forward + device post-processing + contours + D2H + host dicts (3 streams, 2-deep pipeline)"}
 
     # ---- roofline leg: per-launch CUDA-event timing of the tile-engine kernel over Kp more steps (not under a profiler)
     roof = None
     cpu_base = None
     if rank == 0:
         Kp = max(1, min(K, 3))
-        L.check(lib.cvb_tc_profile_begin(4096), "cvb_tc_profile_begin")
         tc_ms, tc_n, tc_fl = C.c_double(), C.c_int(), C.c_double()
         tot_ms, tot_n, tot_fl = 0.0, 0, 0.0
         for _ in range(Kp):
@@ -295,38 +373,44 @@ def run_gpu(args):
                 model(x_dev, retrieve_tokens=True)
             L.check(lib.cvb_tc_profile_end(C.byref(tc_ms), C.byref(tc_n), C.byref(tc_fl)), "cvb_tc_profile_end")
             tot_ms += tc_ms.value; tot_n += tc_n.value; tot_fl += tc_fl.value
-        peak, _, how = _peaks()
-        achieved = GFLOP_TC_PER_TILE * B * Kp / (tot_ms / 1000.0) / 1000.0  # TFLOP/s
+        peak, hbm, how = _peaks()
+        achieved = gflop_tc * B * Kp / (tot_ms / 1000.0) / 1000.0  # TFLOP/s
         traffic, traffic_src = None, None
         tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
-        if os.path.exists(tpath):  # DRAM bytes per tile-engine launch from the committed ncu pass of this same step
+        if arch == "SAM-H" and B == 4 and os.path.exists(tpath):  # DRAM bytes per tile-engine launch from the committed ncu pass of this same step
             tj = json.load(open(tpath))
             traffic, traffic_src = tj.get("dram_bytes_per_launch"), "profiles/r1_traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum, mean over the step's tile-engine launches)"
-        roof = {"bound": "tensor", "kernel": "tc_kernel (tcgen05 GEMM / implicit-GEMM conv)", "achieved": achieved, "peak": peak,
+        roof = {"bound": "tensor", "kernel": "tc_kernel / conv_patch_kernel (tcgen05 GEMM / implicit-GEMM conv)", "achieved": achieved, "peak": peak,
                 "unit": "TFLOP/s", "frac": achieved / peak, "peak_source": how, "traffic": traffic, "traffic_unit": "bytes/launch",
                 "traffic_source": traffic_src,
                 "launches_per_step": tot_n // Kp, "kernel_ms_per_step": tot_ms / Kp,
-                "executed_tflop_per_step": tot_fl / Kp / 1e12, "algorithmic_tflop_per_step": GFLOP_TC_PER_TILE * B / 1000.0,
-                "share_of_step": (tot_ms / Kp) / (ms_total / K)}
+                "executed_tflop_per_step": tot_fl / Kp / 1e12, "algorithmic_tflop_per_step": gflop_tc * B / 1000.0,
+                "share_of_step": (tot_ms / Kp) / (ms_total / K),
+                "whole_step_frac": (cfg["gflop"] * B / (ms_total / K)) / peak}  # all algorithmic FLOPs of the step / step time / peak
+        ppath = os.path.join(ROOT, "profiles", "r2_postproc_traffic.json")
+        if os.path.exists(ppath):  # HBM-bound post-processing kernels: committed ncu capture (tools/ncu_table.py) of cvb_postproc at this shape
+            roof["postproc"] = json.load(open(ppath))
         if world == 1 and not args.no_cpu:
             cores = os.cpu_count() or 1
-            tf, tp = cpu_tile_seconds(cores, 1)
+            tf, tp = cpu_tile_seconds(arch, cores, 1)
             cpu_base = {"value": 1.0 / (tf + tp), "unit": "tiles/s", "cores": cores, "kind": "port",
                         "sample": f"1 tile: oracle fp32 forward {tf:.2f}s ({cores} threads) + C post-processing {tp:.2f}s (1 thread)"}
     if world > 1:
         dist.barrier()
     if rank == 0:
+        par = f"tiles sharded over {world} GPU(s), NCCL weight broadcast"
+        if world > 1:
+            par += (", per-step all-gather of instance tables" if gather is None else f", instance tables all-gathered every {args.gather_every} steps")
         print(json.dumps({
-            "metric": METRIC, "value": value, "unit": "tiles/s", "n_gpus": world, "steps": K, "warmup": Wm,
+            "metric": metric_name(arch), "value": value, "unit": "tiles/s", "n_gpus": world, "steps": K, "warmup": Wm,
             "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16",
             "data": "synthetic",
-            "config": {"workload": WORKLOAD, "batch": f"{B} tiles per GPU per step, post-processing on the GPU",
-                       "l2": "per-step working set (1.4 GB fp16 weights + >10 GB activations) exceeds the 126 MB L2; no explicit flush",
-                       "forward_launch": "CUDA graph replay" if args.graphs else "eager",
-                       "parallelism": f"tiles sharded over {world} GPU(s), NCCL weight broadcast" + ((", per-step all-gather of instance tables" if args.gather_every <= 1 else f", instance tables all-gathered every {args.gather_every} steps") if world > 1 else "")},
-            "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": "tiles/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke,
-                    "api": "CellSegmentationInference.process_tiles: H2D + forward + softmax + device post-processing + D2H + host dicts (3 streams, 2-deep pipeline)"},
+            "config": {"workload": workload_name(arch),
+                       "batch": f"{B} tiles per GPU per step" + (", forward only (--no-post)" if args.no_post else ", post-processing on the GPU"),
+                       "l2": "per-step working set (fp16 weights + >10 GB activations) exceeds the 126 MB L2; no explicit flush",
+                       "forward_launch": "CUDA graph replay (kernel nodes at high stream priority)" if args.graphs else "eager",
+                       "parallelism": par},
+            "clocks": clocks, "timed_region_s": ms_total / 1000.0, "overlap": ov, "e2e": e2e,
             "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu_base}))
     if world > 1:
         dist.destroy_process_group()
@@ -338,9 +422,12 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--arch", default="SAM-H", choices=sorted(ARCHS), help="SAM-H (default; BASELINE configs[2]) or ViT256 (configs[1], batch 8)")
+    ap.add_argument("--batch", type=int, default=0, help="tiles per GPU per step (default: 4 for SAM-H, 8 for ViT256)")
     ap.add_argument("--graphs", type=int, default=1, help="1 (default): the forward is replayed from a CUDA graph, as in the product pipeline; 0: eager launches")
-    ap.add_argument("--gather-every", type=int, default=1, help="N>1 only: exchange the instance tables once per this many steps (TableGather) instead of "
-                    "two all-gathers per step (default 1 = per step; the chunked exchange is not measured yet)")
+    ap.add_argument("--gather-every", type=int, default=8, help="N>1 only: exchange the instance tables once per this many steps (TableGather, default 8); "
+                    "1 = two all-gathers per step")
+    ap.add_argument("--no-post", action="store_true", help="forward only: no post-processing, no e2e leg (quantifies what the post-processing costs)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling / quick iteration runs)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup

@@ -172,7 +172,7 @@ class CellSegmentationInference:
         ``(payload, dicts, cell_tokens)`` per batch, in order, where ``dicts`` are the per-tile instance dicts and
         ``cell_tokens`` (``with_tokens``) one float32 array [n_cells, D] per tile, rows aligned with the dict order.
 
-        Three streams keep the device busy: the H2D copy of batch k+1 (copy stream) and the softmax (:500-505) +
+        Three streams keep the device busy: the H2D copy of batch k+1 (copy stream) and the
         device post-processing (+ cell-token pooling) + D2H of batch k (post stream) run beside the forward of batch
         k+1 (the caller's stream); the host part (dict building, post_proc_cellvit.py:96-151) of batch k overlaps
         them too. ``head_override`` (dict, or callable(payload) -> dict) replaces head maps before post-processing
@@ -208,8 +208,8 @@ class CellSegmentationInference:
                     if consumed[slot] is None:
                         consumed[slot] = torch.cuda.Event()
                         consumed[slot].record(main)
-                elif patches.is_cuda:
-                    return patches, None, None
+                elif patches.is_cuda and patches.dtype != torch.uint8:
+                    return patches, None, None   # already normalised, produced on `main`: the forward reads it in stream order
                 else:
                     if in_buf[slot] is None or in_buf[slot].shape != patches.shape:
                         in_buf[slot] = torch.empty(patches.shape, dtype=torch.float32, device=dev)
@@ -217,6 +217,13 @@ class CellSegmentationInference:
                         consumed[slot].record(main)  # the fresh block may still be in use by earlier work on `main`
                     buf = in_buf[slot]
                 s_in.wait_event(consumed[slot])      # the forward that last read this slot has finished
+                if patches.is_cuda:
+                    # a device batch may have been produced lazily on the caller's stream (e.g. a generator that normalises
+                    # tiles on the GPU): its producer kernels are queued on `main`, so the copy stream has to wait for them
+                    produced = torch.cuda.Event()
+                    produced.record(main)
+                    s_in.wait_event(produced)
+                    patches.record_stream(s_in)
                 with torch.cuda.stream(s_in):
                     if patches.dtype == torch.uint8:
                         # raw tiles: ToTensor + Normalize (:214-227) on the device, same operations in the same order
@@ -263,11 +270,12 @@ class CellSegmentationInference:
                     pending = None
                 s_post.wait_event(fwd_done)
                 with torch.cuda.stream(s_post):
-                    np_map = F.softmax(predictions["nuclei_binary_map"], dim=1)
-                    nt_map = F.softmax(predictions["nuclei_type_map"], dim=1)
-                    proc.launch_float(np_map, predictions["hv_map"], nt_map, slot=slot,
+                    # The reference soft-maxes NP / NT first (:500-505) and then only takes their arg-max (cellvit.py:369-375);
+                    # softmax is monotonic, so the arg-max of the logits is the same map -- 270 MB of traffic per batch saved.
+                    # (Callers that want the probabilities use get_cell_predictions_with_tokens, which keeps the softmax.)
+                    proc.launch_float(predictions["nuclei_binary_map"], predictions["hv_map"], predictions["nuclei_type_map"], slot=slot,
                                       tokens=predictions["tokens"] if with_tokens else None, patch_size=self.model.patch_size)
-                keep[slot] = (payload, predictions, np_map, nt_map)  # alive until the D2H event of this batch has completed
+                keep[slot] = (payload, predictions)  # alive until the D2H event of this batch has completed
                 if pending is not None:
                     yield finish(pending)
                 pending = slot

@@ -89,6 +89,7 @@ class CellViT(nn.Module):
         self._pack_epoch = 0
         self._size_key = None
         self._ws = None
+        self._capture_stream = None
         self._graphs = {}        # forward_graphed: (shape, tokens, slot, device) -> (graph, static input, static outputs)
 
     # ------------------------------------------------------------------ engine plumbing
@@ -226,7 +227,12 @@ class CellViT(nn.Module):
                     self.forward(static_x, retrieve_tokens)  # eager warm-up: sizes the workspace, sets kernel attributes
                     torch.cuda.synchronize(dev)
                     graph = torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(graph):
+                    # Captured on a HIGH-priority stream: kernel nodes keep the priority of the stream they were captured on,
+                    # so the forward's CTAs are placed before those of the post-processing stream (default = lowest
+                    # priority) whenever both have work pending -- the post-processing fills what the forward leaves free
+                    if self._capture_stream is None or self._capture_stream.device != dev:
+                        self._capture_stream = torch.cuda.Stream(dev, priority=-1)
+                    with torch.cuda.graph(graph, stream=self._capture_stream):
                         out = self.forward(static_x, retrieve_tokens)
                 g = self._graphs[key] = (graph, static_x, out)
         return g
