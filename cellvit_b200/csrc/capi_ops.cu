@@ -43,8 +43,8 @@ CVB_API int cvb_op_attention_tc(const void* qkv, int Gb, int S, int heads, int h
 }
 
 CVB_API int cvb_op_window_attention_tc(const void* qkv, int n_items, int heads, int hd, float scale, const void* relcat, void* out,
-                                       void* stream) {
-    return op_window_attention_tc((const __half*)qkv, n_items, heads, hd, scale, (const __half*)relcat, (__half*)out,
+                                       int* sched_counter, void* stream) {
+    return op_window_attention_tc((const __half*)qkv, n_items, heads, hd, scale, (const __half*)relcat, (__half*)out, sched_counter,
                                   (cudaStream_t)stream);
 }
 

@@ -232,6 +232,148 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t cta_r
         ::"r"(bar), "r"(cta_rank)
         : "memory");
 }
+// cluster-scope release / acquire variants (dynamic tile scheduler: a 4-byte tile index travels with the barrier)
+__device__ __forceinline__ void mbar_arrive_release_cluster(uint32_t bar) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote_release(uint32_t bar, uint32_t cta_rank) {
+    asm volatile(
+        "{\n\t.reg .b32 ra;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
+        ::"r"(bar), "r"(cta_rank)
+        : "memory");
+}
+__device__ __forceinline__ void st_shared_remote_u32(uint32_t addr, uint32_t cta_rank, uint32_t v) {
+    asm volatile(
+        "{\n\t.reg .b32 ra;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+        "st.shared::cluster.u32 [ra], %2;\n\t}"
+        ::"r"(addr), "r"(cta_rank), "r"(v)
+        : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_acq_cluster(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_acq_cluster(uint32_t bar, uint32_t parity) {
+    if (mbar_try_wait_acq_cluster(bar, parity)) return;
+    long long t0 = clock64();
+    while (!mbar_try_wait_acq_cluster(bar, parity)) {
+        if (clock64() - t0 > 4000000000LL) {
+            printf("cellvit_b200: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
+            __trap();
+        }
+    }
+}
+__device__ __forceinline__ void st_shared_u32(uint32_t addr, uint32_t v) {
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_shared_u32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
+
+// ---- dynamic tile scheduler of the persistent kernels. One warp claims tile indices from a global counter (zeroed by the
+// host before the launch) and publishes them through a ring of SCHED_DEPTH slots in shared memory; every other role of the
+// CTA (or CTA pair) consumes the same sequence. A persistent kernel whose CTA i walks tiles i, i + grid, ... takes twice as
+// long as soon as ONE of its CTAs starts late -- which is what happens whenever a CTA of the concurrent post-processing
+// stream occupies an SM at the kernel boundary; with claimed tiles the late CTA simply finds less work.
+constexpr int SCHED_DEPTH = 4;
+constexpr int SCHED_BYTES = 2 * SCHED_DEPTH * (8 + 8 + 4) + 8 + 8;
+struct SchedRing {
+    // shared-memory addresses: full[SCHED_DEPTH], empty[SCHED_DEPTH] barriers, the `go` barrier, int tile[SCHED_DEPTH], and the
+    // same again (lfull, lempty, ltile) for the peer CTA's local copy of the sequence in CTA-pair mode
+    uint32_t full, empty, go, tile, lfull, lempty, ltile;
+    __device__ __forceinline__ void carve(uint32_t base) {
+        full = base; empty = base + 8u * SCHED_DEPTH; go = base + 16u * SCHED_DEPTH; tile = go + 8u;
+        lfull = tile + 4u * SCHED_DEPTH; lempty = lfull + 8u * SCHED_DEPTH; ltile = lempty + 8u * SCHED_DEPTH;
+    }
+    // one thread, before the CTA-wide barrier. consumers = consumer WARPS of this CTA (one elected arrival each);
+    // pair: one more arrival per slot from the peer CTA's relay warp
+    __device__ __forceinline__ void init(int consumers, bool pair) {
+        for (int s = 0; s < SCHED_DEPTH; ++s) {
+            mbar_init(full + 8u * s, 1); mbar_init(empty + 8u * s, (uint32_t)(consumers + (pair ? 1 : 0)));
+            mbar_init(lfull + 8u * s, 1); mbar_init(lempty + 8u * s, (uint32_t)consumers);
+        }
+        mbar_init(go, 1);
+    }
+    // producer warp of the leader CTA (all lanes): claims until the counter runs out; publishes -1 as the terminator.
+    // Everything the role warps of a CTA touch stays at CTA scope: a cluster-scope acquire on every wait costs several
+    // hundred cycles per tile and role (measured: +7..15 % on the kernels' duration). In CTA-pair mode the index travels to
+    // the peer CTA once per tile (remote store + cluster-scope release), where an otherwise idle warp relays it (relay()).
+    template <bool PAIR>
+    __device__ __forceinline__ void produce(int* counter, int n_tiles) {
+        const int lane = threadIdx.x & 31;
+        for (int k = 0;; ++k) {
+            const int slot = k & (SCHED_DEPTH - 1);
+            const uint32_t eph = (uint32_t)(((k / SCHED_DEPTH) & 1) ^ 1);
+            if (PAIR) mbar_wait_acq_cluster(empty + 8u * slot, eph); else mbar_wait(empty + 8u * slot, eph);
+            // claim tile k only once the leading consumer (the load warp) has STARTED tile k - 1: a CTA never holds more than one
+            // claimed-but-unstarted tile, so the tail of the kernel balances like the static lists do, and the claim's
+            // round trip to L2 still has a whole tile to complete
+            if (k >= 1) mbar_wait(go, (uint32_t)((k - 1) & 1));
+            int t = 0;
+            if (lane == 0) t = atomicAdd(counter, 1);
+            t = __shfl_sync(0xffffffffu, t, 0);
+            if (t >= n_tiles) t = -1;
+            if (lane == 0) {
+                st_shared_u32(tile + 4u * slot, (uint32_t)t);
+                mbar_arrive(full + 8u * slot);
+                if (PAIR) {
+                    st_shared_remote_u32(tile + 4u * slot, 1, (uint32_t)t);
+                    mbar_arrive_remote_release(full + 8u * slot, 1);
+                }
+            }
+            __syncwarp();
+            if (t < 0) break;
+        }
+    }
+    // peer CTA of a pair (all lanes of one idle warp): receives the leader's sequence at cluster scope, frees the leader's slot,
+    // and republishes it to the peer's own role warps at CTA scope
+    __device__ __forceinline__ void relay() {
+        const int lane = threadIdx.x & 31;
+        for (int k = 0;; ++k) {
+            const int slot = k & (SCHED_DEPTH - 1);
+            const uint32_t ph = (uint32_t)((k / SCHED_DEPTH) & 1);
+            mbar_wait_acq_cluster(full + 8u * slot, ph);
+            const int t = (int)ld_shared_u32(tile + 4u * slot);
+            __syncwarp();
+            mbar_wait(lempty + 8u * slot, ph ^ 1u);
+            if (lane == 0) {
+                mbar_arrive_remote_release(empty + 8u * slot, 0);
+                st_shared_u32(ltile + 4u * slot, (uint32_t)t);
+                mbar_arrive(lfull + 8u * slot);
+            }
+            __syncwarp();
+            if (t < 0) break;
+        }
+    }
+    // role warp (all lanes): k-th tile of the sequence, -1 when the work is exhausted. `leads`: this is the load warp of
+    // the leader CTA, whose progress paces the claims (see produce)
+    __device__ __forceinline__ int consume(int k, uint32_t rank, bool leads) {
+        const int slot = k & (SCHED_DEPTH - 1);
+        const uint32_t ph = (uint32_t)((k / SCHED_DEPTH) & 1);
+        const uint32_t f = rank == 0 ? full : lfull, e = rank == 0 ? empty : lempty, tl = rank == 0 ? tile : ltile;
+        mbar_wait(f + 8u * slot, ph);
+        const int t = (int)ld_shared_u32(tl + 4u * slot);
+        __syncwarp();
+        if (elect_one()) {
+            mbar_arrive(e + 8u * slot);
+            if (leads) mbar_arrive(go);
+        }
+        return t;
+    }
+};
+
 __device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1) {
     asm volatile(
         "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"

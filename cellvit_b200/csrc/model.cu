@@ -25,6 +25,9 @@ struct cvb_model {
     // tcgen05 kernel for the 14 x 14 windows (window_tc.cu). Both on by default; 0 selects the mma.sync kernels of
     // attention.cu (kept as the independent implementation the parity tests compare against).
     int attn_tc_mode = 3;
+    // option "dynamic_tiles": 1 (default) = the persistent kernels (tile engine, window attention) claim their tiles from a
+    // per-launch counter (SchedRing, common.cuh) instead of walking a static list; 0 = static lists (ablation)
+    int dynamic_tiles = 1;
 };
 
 namespace {
@@ -48,6 +51,12 @@ struct Fwd {
     cudaStream_t st;
     int rc = CVB_OK;
     std::string missing;
+    // per-launch tile counters of the persistent kernels: one int each, zeroed by ONE memset at the start of the forward
+    static constexpr int N_COUNTERS = 1024;
+    int* counters = nullptr;
+    int n_counters = 0;
+    int* next_counter() { return (counters && m.dynamic_tiles && n_counters < N_COUNTERS) ? counters + n_counters++ : nullptr; }
+    TcEpilogue with_counter(const TcEpilogue& e) { TcEpilogue c = e; c.sched_counter = next_counter(); return c; }
 
     template <class T>
     const T* P(const std::string& name) {
@@ -68,7 +77,7 @@ struct Fwd {
 
     void gemm(const __half* a, int M, int K, const std::string& w, int N, const TcEpilogue& e) {
         const __half* wp = P<__half>(w);
-        if (live()) chk(tc_gemm(a, M, K, K, wp, N, K, tc_pick_block_n(N), e, st));
+        if (live()) chk(tc_gemm(a, M, K, K, wp, N, K, tc_pick_block_n(N), with_counter(e), st));
     }
 
     // Conv3x3 + folded BN + ReLU over (src0 || src1), NHWC fp16 -> NHWC fp16 [NB,H,W,N]
@@ -78,7 +87,7 @@ struct Fwd {
         e.kind = TC_EPI_F16; e.act = TC_ACT_RELU; e.out = out; e.ldc = N;
         e.scale = P<float>(name + ".scale"); e.shift = P<float>(name + ".shift");
         const __half* wp = P<__half>(name + ".w");
-        if (live()) chk(tc_conv3x3(s0, C0, s1, C1, NB, H, W, wp, N, tc_pick_block_n(N), e, st));
+        if (live()) chk(tc_conv3x3(s0, C0, s1, C1, NB, H, W, wp, N, tc_pick_block_n(N), with_counter(e), st));
         return out;
     }
     // ConvTranspose2d k2 s2 (+bias): [NB,hin,win,Cin] -> [NB,2hin,2win,Cout]
@@ -88,7 +97,7 @@ struct Fwd {
         e.kind = TC_EPI_CONVT; e.out = out; e.ldc = Cout; e.shift = P<float>(name + ".b");
         e.ct_cout = Cout; e.ct_hin = hin; e.ct_win = win;
         const __half* wp = P<__half>(name + ".w");
-        if (live()) chk(tc_gemm(src, NB * hin * win, Cin, Cin, wp, 4 * Cout, Cin, tc_pick_block_n(4 * Cout), e, st));
+        if (live()) chk(tc_gemm(src, NB * hin * win, Cin, Cin, wp, 4 * Cout, Cin, tc_pick_block_n(4 * Cout), with_counter(e), st));
         return out;
     }
     // Deconv2DBlock (utils.py:46-86): ConvT -> Conv3x3 -> BN -> ReLU
@@ -110,6 +119,8 @@ int forward_impl(cvb_model& m, const float* x, int B, int H, int W, float* o_np,
     const int skip = sam ? 0 : 1;
     const float scale = 1.0f / sqrtf((float)hd);
     const bool live = !A.dry;
+    f.counters = A.alloc<int>(Fwd::N_COUNTERS);
+    if (live) CVB_CUDA(cudaMemsetAsync(f.counters, 0, Fwd::N_COUNTERS * sizeof(int), st));
 
     // ------------------------------------------------------------------ patch embedding (+bias +pos)
     __half* a0 = A.alloc<__half>((size_t)B * T * 768);
@@ -170,7 +181,7 @@ int forward_impl(cvb_model& m, const float* x, int B, int H, int W, float* o_np,
         const __half* tw = sam ? f.P<__half>(p + ".relw") : nullptr;
         if (f.live()) {
             if (attn_tc && !win) f.chk(op_attention_tc(qkv, Gb, S, heads, hd, scale, th, tw, gh, gw, att, attn_ws, attn_ws_bytes, st));
-            else if (win_tc && win) f.chk(op_window_attention_tc(qkv, Gb, heads, hd, scale, f.P<__half>(p + ".relcat"), att, st));
+            else if (win_tc && win) f.chk(op_window_attention_tc(qkv, Gb, heads, hd, scale, f.P<__half>(p + ".relcat"), att, f.next_counter(), st));
             else f.chk(op_attention(qkv, Gb, S, heads, hd, scale, th, tw, gh, gw, att, st));
         }
         {
@@ -220,7 +231,7 @@ int forward_impl(cvb_model& m, const float* x, int B, int H, int W, float* o_np,
         if (f.live()) f.chk(op_layernorm_f16(n0, g1, b1, 1e-6f, B * T, 256, n1, 0, B, h, w, 0, 0, st));
         e.out = n2;
         const __half* w2 = f.P<__half>("neck.2.w");
-        if (f.live()) f.chk(tc_conv3x3(n1, 256, nullptr, 0, B, h, w, w2, 256, 256, e, st));
+        if (f.live()) f.chk(tc_conv3x3(n1, 256, nullptr, 0, B, h, w, w2, 256, 256, f.with_counter(e), st));
         const float* g3 = f.P<float>("neck.3.w");
         const float* b3 = f.P<float>("neck.3.b");
         const float* cw = f.P<float>("cls.w");
@@ -277,7 +288,7 @@ int forward_impl(cvb_model& m, const float* x, int B, int H, int W, float* o_np,
         e.head_w = f.P<float>(n + ".head.w"); e.head_b = f.P<float>(n + ".head.b");
         e.head_nc = br.nc; e.head_hw = H * W; e.head_out = br.out;
         const __half* wp = f.P<__half>(n + ".d0.1.w");
-        if (f.live() && br.out) f.chk(tc_conv3x3(b, 64, nullptr, 0, B, H, W, wp, 64, 64, e, st));
+        if (f.live() && br.out) f.chk(tc_conv3x3(b, 64, nullptr, 0, B, H, W, wp, 64, 64, f.with_counter(e), st));
     }
     (void)pad64;
     return f.rc;
@@ -351,6 +362,10 @@ CVB_API int cvb_model_set_option(cvb_model* m, const char* name, int value) {
     if (std::string(name) == "attention_tc") {
         CVB_CHECK(value >= 0 && value <= 3, CVB_EARG, "cvb_model_set_option: attention_tc must be in 0..3");
         m->attn_tc_mode = value;
+        return CVB_OK;
+    }
+    if (std::string(name) == "dynamic_tiles") {
+        m->dynamic_tiles = value != 0;
         return CVB_OK;
     }
     cvb_set_error("cvb_model_set_option: unknown option '%s'", name);

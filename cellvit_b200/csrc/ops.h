@@ -81,5 +81,6 @@ int op_attention_tc(const __half* qkv, int Gb, int S, int heads, int hd, float s
 // qkv fp16 [n_items*196, 3*D] in window order, relcat fp16 [64, 80] = rel_h table rows at 0.., rel_w table rows at 32..
 // (packing.py), out fp16 [n_items*196, D].
 bool op_window_attention_tc_supported(int S, int hd, int gh, int gw);
+// sched_counter: optional device int, zero at launch: the (window, head) items are then claimed dynamically (SchedRing).
 int op_window_attention_tc(const __half* qkv, int n_items, int heads, int hd, float scale, const __half* relcat, __half* out,
-                           cudaStream_t stream);
+                           int* sched_counter, cudaStream_t stream);

@@ -536,80 +536,77 @@ struct Heap {
     }
 };
 
-// 4-ary heap of packed 16-byte entries in shared memory (one LDS.128 per entry, four independent child loads per
-// level, depth log4 n). Any correct priority queue gives the same flood because (value, age, index) is a strict
-// total order; the array has 4 slack entries so that the child loads never need a bounds check.
-// Entries are two 64-bit integers: k = order-preserving image of the fp64 value (with -0.0 folded onto +0.0, as the
-// floating-point comparison does), ai = age << 32 | index -- so "less" is two integer compares instead of a chain of
-// fp64 ones.
-struct __align__(16) HItem { unsigned long long k, ai; };
-__device__ __forceinline__ unsigned long long f64_order_key(double v) {
-    const long long b = __double_as_longlong(v + 0.0);
-    return b < 0 ? ~(unsigned long long)b : ((unsigned long long)b | 0x8000000000000000ull);
-}
-__device__ __forceinline__ HItem make_item(double v, int age, int idx) {
-    HItem it;
-    it.k = f64_order_key(v);
-    it.ai = ((unsigned long long)(unsigned)age << 32) | (unsigned)idx;
-    return it;
-}
-__device__ __forceinline__ bool it_less(const HItem& a, const HItem& b) { return a.k < b.k || (a.k == b.k && a.ai < b.ai); }
-struct Heap4 {
-    HItem* a;
+// ---- fast path of the flood: rank transform + packed 32-bit keys.
+// The flood only ever COMPARES dist values, so a blob's fp64 values are replaced by their rank among the blob's pixels
+// (rank = number of strictly smaller values: equal values keep equal ranks, so ties still fall through to age and index).
+// A heap entry then is ONE 32-bit integer  rank << 22 | age << 12 | cell  (blob <= 1023 pixels: rank, age < 1024; bounding box
+// + apron <= 4096 cells) and the strict total order (value, age, index) is a single unsigned compare. The heap is 4-ary with
+// node k stored at h[k + 3], so the four children of a node are one aligned LDS.128; vacated slots hold 0xFFFFFFFF, which no
+// key reaches, so the sift needs no bounds checks. Per blob: heap 4 KB + ranks (u16) + labels (i32) of the staged bounding
+// box = 21 KB -- small enough for a flood CTA to be resident BESIDE a tile-engine CTA (~196 KB of an SM's 228 KB), which is
+// what lets the post-processing stream overlap the forward at all: a CTA that does not fit waits for a kernel boundary,
+// occupies the SM alone, and the statically scheduled persistent GEMM that follows runs that SM's tiles late.
+constexpr int FL_MAXN = 1023;                 // pixels per blob on the fast path
+constexpr int FL_HC = FL_MAXN + 1 + 8;        // heap array entries (node k at [k + 3], 4 slack entries)
+constexpr int FL_RC = 2816;                   // staged cells (bounding box + 1-pixel apron)
+constexpr int FL_SMEM = FL_HC * 4 + FL_RC * 4 + FL_RC * 2;   // 21,024 B
+constexpr uint32_t FL_SENT = 0xFFFFFFFFu;
+
+struct RankHeap {
+    uint32_t* h;  // node k at h[k + 3]
     int n;
-    __device__ __forceinline__ void sift_down(int i, HItem x) {
+    __device__ __forceinline__ void sift_down(int i, uint32_t x) {
         for (;;) {
             const int c = 4 * i + 1;
             if (c >= n) break;
-            HItem best = a[c];
-            const HItem t1 = a[c + 1], t2 = a[c + 2], t3 = a[c + 3];
-            int bi = c;
-            if (c + 1 < n && it_less(t1, best)) { best = t1; bi = c + 1; }
-            if (c + 2 < n && it_less(t2, best)) { best = t2; bi = c + 2; }
-            if (c + 3 < n && it_less(t3, best)) { best = t3; bi = c + 3; }
-            if (!it_less(best, x)) break;
-            a[i] = best;
-            i = bi;
+            const uint4 ch = *reinterpret_cast<const uint4*>(h + c + 3);
+            const uint32_t m = min(min(ch.x, ch.y), min(ch.z, ch.w));
+            if (m >= x) break;
+            const int bi = ch.x == m ? 0 : (ch.y == m ? 1 : (ch.z == m ? 2 : 3));
+            h[i + 3] = m;
+            i = c + bi;
         }
-        a[i] = x;
+        h[i + 3] = x;
     }
-    __device__ __forceinline__ void push(HItem x) {
+    __device__ __forceinline__ void push(uint32_t x) {
         int i = n++;
         while (i > 0) {
             const int par = (i - 1) >> 2;
-            const HItem pv = a[par];
-            if (!it_less(x, pv)) break;
-            a[i] = pv;
+            const uint32_t pv = h[par + 3];
+            if (x >= pv) break;
+            h[i + 3] = pv;
             i = par;
         }
-        a[i] = x;
+        h[i + 3] = x;
     }
-    __device__ __forceinline__ HItem pop() {
-        const HItem top = a[0];
+    __device__ __forceinline__ uint32_t pop() {
+        const uint32_t top = h[3];
         --n;
-        if (n > 0) sift_down(0, a[n]);
+        const uint32_t x = h[n + 3];
+        h[n + 3] = FL_SENT;
+        if (n > 0) sift_down(0, x);
         return top;
     }
 };
 
-// One warp per blob. Seeds = marker pixels that still have an unlabelled mask neighbour (interior seeds pop as
-// no-ops and never change `age`, so leaving them out does not change the result). Heap in shared memory when
-// the blob fits (cap_entries), else in the blob's slice of the global scratch arrays.
+// One warp per blob, blobs taken largest class first from the size-class queues. Seeds = marker pixels that still have an
+// unlabelled mask neighbour (interior seeds pop as no-ops and never change `age`, so leaving them out does not change the
+// result). Blobs above the fast path's limits run the same flood with a binary heap of (fp64 value, age, index) in global
+// scratch, one L2 round trip per pop.
 __global__ void __launch_bounds__(32)
-watershed_kernel(const int* __restrict__ queue_base, int qstride, int* __restrict__ qmeta, int cls_begin, int cls_end, const int* __restrict__ cnt,
+watershed_kernel(const int* __restrict__ queue_base, int qstride, int* __restrict__ qmeta, const int* __restrict__ cnt,
                  const int* __restrict__ off, const int* __restrict__ blobpix, const uint8_t* __restrict__ blb, const int* __restrict__ marker,
-                 const double* __restrict__ dist, Dims d, int cap_entries, int rcap, double* __restrict__ gkey, int2* __restrict__ gpay,
-                 int* labels_) {
-    // shared memory: [heap: (cap_entries + 4) x 16 B][region dist: rcap x 8 B][region labels: rcap x 4 B]
+                 const double* __restrict__ dist, Dims d, double* __restrict__ gkey, int2* __restrict__ gpay, int* labels_) {
+    // shared memory: [heap u32 x FL_HC][labels i32 x FL_RC (aliased by the blob's fp64 values while they are ranked)][ranks u16 x FL_RC]
     extern __shared__ __align__(16) uint8_t ws_smem[];
     volatile int* labels = labels_;
-    double* skey = reinterpret_cast<double*>(ws_smem);
-    int2* spay = reinterpret_cast<int2*>(ws_smem + (size_t)cap_entries * 8);
-    HItem* sheap = reinterpret_cast<HItem*>(ws_smem);
-    double* sdist = reinterpret_cast<double*>(ws_smem + (size_t)(cap_entries + 4) * 16);
-    int* slab = reinterpret_cast<int*>(ws_smem + (size_t)(cap_entries + 4) * 16 + (size_t)rcap * 8);
+    uint32_t* sheap = reinterpret_cast<uint32_t*>(ws_smem);
+    int* slab = reinterpret_cast<int*>(ws_smem + (size_t)FL_HC * 4);
+    double* svals = reinterpret_cast<double*>(slab);
+    uint16_t* srank = reinterpret_cast<uint16_t*>(ws_smem + (size_t)FL_HC * 4 + (size_t)FL_RC * 4);
+    static_assert((FL_HC * 4) % 16 == 0 && FL_MAXN * 8 <= FL_RC * 4, "flood shared-memory layout");
     const int lane = threadIdx.x;
-    for (int cls = cls_begin; cls < cls_end; ++cls) {
+    for (int cls = 0; cls < NQ_CLASSES; ++cls) {
     const int qn = qmeta[cls];
     const int* queue = queue_base + (long long)cls * qstride;
     int* qhead = qmeta + 8 + cls;
@@ -627,11 +624,10 @@ watershed_kernel(const int* __restrict__ queue_base, int qstride, int* __restric
         const int* mk = marker + base;
         const double* ds = dist + base;
         volatile int* out = labels + base;
-        // ---- fast path: the blob's bounding box (+1 pixel apron) is staged into shared memory -- mask and label
-        // folded into one int (-1 = outside the mask), dist as fp64 -- and lane 0 runs the serial priority flood
-        // entirely out of shared memory (~0.3 us per pop instead of ~2 us through L2). Local raster indices order
-        // like the global ones, so the (value, age, index) total order is unchanged.
-        {
+        // ---- fast path: the blob's bounding box (+1 pixel apron) is staged into shared memory and lane 0 runs the serial
+        // priority flood entirely out of shared memory. Local raster indices order like the global ones, so the
+        // (value, age, index) total order is unchanged.
+        if (n <= FL_MAXN) {
             int y0 = d.H, y1 = -1, x0 = d.W, x1 = -1;
             for (int i = lane; i < n; i += 32) {
                 const int p = list[i];
@@ -647,23 +643,40 @@ watershed_kernel(const int* __restrict__ queue_base, int qstride, int* __restric
             }
             const int rw = x1 - x0 + 3, rh = y1 - y0 + 3;
             const long long cells_ll = (long long)rw * rh;
-            if (n <= cap_entries && cells_ll <= (long long)rcap) {
+            if (cells_ll <= (long long)FL_RC) {
                 const int cells = (int)cells_ll;
                 int* gout = labels_ + base;
-                // only this blob's pixels enter the region (via its pixel list): everything else, including pixels of
-                // other blobs inside the bounding box and the whole apron, is "outside the mask"
+                auto cell_of = [&](int p) { const int y = p / d.W, x = p - y * d.W; return (y - y0 + 1) * rw + (x - x0 + 1); };
+                // (1) rank transform: vals[i] = dist of the i-th blob pixel; rank = number of strictly smaller values
+                for (int i = lane; i < n; i += 32) svals[i] = ds[list[i]];
+                for (int i = lane; i < FL_HC; i += 32) sheap[i] = FL_SENT;
+                __syncwarp();
+                for (int i0 = lane; i0 < n; i0 += 128) {   // four pixels per lane per sweep over the values
+                    const int i1 = i0 + 32, i2 = i0 + 64, i3 = i0 + 96;
+                    const double v0 = svals[i0], v1 = svals[i1 < n ? i1 : i0], v2 = svals[i2 < n ? i2 : i0], v3 = svals[i3 < n ? i3 : i0];
+                    int r0 = 0, r1 = 0, r2 = 0, r3 = 0;
+                    for (int j = 0; j < n; ++j) {
+                        const double vj = svals[j];
+                        r0 += vj < v0; r1 += vj < v1; r2 += vj < v2; r3 += vj < v3;
+                    }
+                    srank[cell_of(list[i0])] = (uint16_t)r0;
+                    if (i1 < n) srank[cell_of(list[i1])] = (uint16_t)r1;
+                    if (i2 < n) srank[cell_of(list[i2])] = (uint16_t)r2;
+                    if (i3 < n) srank[cell_of(list[i3])] = (uint16_t)r3;
+                }
+                __syncwarp();
+                // (2) labels of the region: only this blob's pixels enter (via its pixel list); everything else, including
+                // pixels of other blobs inside the bounding box and the whole apron, is "outside the mask" (-1)
                 for (int c = lane; c < cells; c += 32) slab[c] = -1;
                 __syncwarp();
                 for (int i = lane; i < n; i += 32) {
                     const int p = list[i];
-                    const int y = p / d.W, x = p - y * d.W;
-                    const int c = (y - y0 + 1) * rw + (x - x0 + 1);
-                    slab[c] = gout[p];
-                    sdist[c] = ds[p];
+                    slab[cell_of(p)] = gout[p];
                 }
                 __syncwarp();
-                Heap4 hq;
-                hq.a = sheap;
+                // (3) seeds
+                RankHeap hq;
+                hq.h = sheap;
                 int n_seed = 0;
                 for (int c0 = 0; c0 < cells; c0 += 32) {
                     const int c = c0 + lane;
@@ -671,17 +684,17 @@ watershed_kernel(const int* __restrict__ queue_base, int qstride, int* __restric
                     if (c < cells && slab[c] > 0)  // labelled cells are never on the apron, so the four neighbours exist
                         is_seed = slab[c - rw] == 0 || slab[c - 1] == 0 || slab[c + 1] == 0 || slab[c + rw] == 0;
                     const uint32_t bits = __ballot_sync(0xffffffffu, is_seed);
-                    if (is_seed) sheap[n_seed + __popc(bits & ((1u << lane) - 1u))] = make_item(sdist[c], 0, c);
+                    if (is_seed) sheap[3 + n_seed + __popc(bits & ((1u << lane) - 1u))] = ((uint32_t)srank[c] << 22) | (uint32_t)c;
                     n_seed += __popc(bits);
                 }
                 __syncwarp();
+                // (4) serial priority flood
                 if (lane == 0) {
                     hq.n = n_seed;
-                    for (int i = (n_seed - 2) / 4; i >= 0 && n_seed > 1; --i) hq.sift_down(i, sheap[i]);  // Floyd heapify
-                    int age = 0;
+                    for (int i = (n_seed - 2) / 4; i >= 0 && n_seed > 1; --i) hq.sift_down(i, sheap[i + 3]);  // Floyd heapify
+                    uint32_t age = 0;
                     while (hq.n > 0) {
-                        const HItem t = hq.pop();
-                        const int c = (int)(unsigned)t.ai;
+                        const int c = (int)(hq.pop() & 0xFFFu);
                         const int lab = slab[c];
                         const int qs[4] = {c - rw, c - 1, c + 1, c + rw};  // up, left, right, down
 #pragma unroll
@@ -690,7 +703,7 @@ watershed_kernel(const int* __restrict__ queue_base, int qstride, int* __restric
                             if (slab[q] == 0) {
                                 ++age;
                                 slab[q] = lab;  // labelled at push time
-                                hq.push(make_item(sdist[q], age, q));
+                                hq.push(((uint32_t)srank[q] << 22) | (age << 12) | (uint32_t)q);
                             }
                         }
                     }
@@ -698,8 +711,7 @@ watershed_kernel(const int* __restrict__ queue_base, int qstride, int* __restric
                 __syncwarp();
                 for (int i = lane; i < n; i += 32) {
                     const int p = list[i];
-                    const int y = p / d.W, x = p - y * d.W;
-                    const int lab = slab[(y - y0 + 1) * rw + (x - x0 + 1)];
+                    const int lab = slab[cell_of(p)];
                     if (lab > 0 && gout[p] == 0) gout[p] = lab;  // pixels this flood labelled
                 }
                 __syncwarp();
@@ -707,8 +719,8 @@ watershed_kernel(const int* __restrict__ queue_base, int qstride, int* __restric
             }
         }
         Heap hp;
-        if (n <= cap_entries) { hp.key = skey; hp.pay = spay; }
-        else { hp.key = gkey + base + off[base + root]; hp.pay = gpay + base + off[base + root]; }
+        hp.key = gkey + base + off[base + root];
+        hp.pay = gpay + base + off[base + root];
         hp.n = 0;
         // ---- collect boundary seeds (any order: the heap order is a strict total order)
         int n_seed = 0;
@@ -1002,27 +1014,6 @@ struct Ws {
     int cap;
     size_t bytes;
 };
-// Flood kernel shared-memory budgets: heap entries (16 B each) + staged bounding-box cells (12 B each). Blobs that exceed
-// either fall back to the global-memory path of the same kernel.
-constexpr int SMALL_CAP = 1024, SMALL_RCAP = 2304;    // 44 KB -> 5 CTAs per SM
-constexpr int LARGE_CAP = 2560, LARGE_RCAP = 7168;    // 127 KB -> leaves room for two SMALL CTAs beside it
-
-// side stream + events for the forked LARGE flood launch (one set per host thread and device)
-struct Fork { cudaStream_t side; cudaEvent_t fork, join; int dev; };
-Fork* get_fork() {
-    thread_local std::vector<Fork> forks;
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
-    for (Fork& f : forks) if (f.dev == dev) return &f;
-    Fork f{};
-    f.dev = dev;
-    if (cudaStreamCreateWithFlags(&f.side, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
-    if (cudaEventCreateWithFlags(&f.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
-    if (cudaEventCreateWithFlags(&f.join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
-    forks.push_back(f);
-    return &forks.back();
-}
-
 Ws carve(void* base, int B, int H, int W) {
     Ws w{};
     Carve c{reinterpret_cast<uint8_t*>(base), 0};
@@ -1128,30 +1119,12 @@ int run_pipeline(const Ws& w, const float* hv, Dims d, int n_types, int object_s
     CVB_CUDA(cudaMemsetAsync(w.fill1, 0, BN * 4, st));
     CVB_CUDA(cudaMemsetAsync(w.qmeta, 0, 16 * 4, st));
     blob_scatter_kernel<<<g, 256, 0, st>>>(w.L1, w.blb, w.off1, d, w.fill1, w.blobpix);
-    blob_queue_kernel<<<g, 256, 0, st>>>(w.L1, w.cnt1, d, 10, SMALL_CAP, w.qmeta, w.queue, w.qstride);
+    blob_queue_kernel<<<g, 256, 0, st>>>(w.L1, w.cnt1, d, 10, FL_MAXN, w.qmeta, w.queue, w.qstride);
     {
-        static unsigned long long configured = 0;  // one bit per device: function attributes are per device
-    const int cfg_dev = cvb_current_device();
-        if (!((configured >> cfg_dev) & 1ull)) {
-            CVB_CUDA(cudaFuncSetAttribute(watershed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (LARGE_CAP + 4) * 16 + LARGE_RCAP * 12));
-            configured |= 1ull << cfg_dev;
-        }
-        const int sms = cvb_num_sms();
-        const size_t smem_s = (size_t)(SMALL_CAP + 4) * 16 + (size_t)SMALL_RCAP * 12;
-        const size_t smem_l = (size_t)(LARGE_CAP + 4) * 16 + (size_t)LARGE_RCAP * 12;
-        // The two launches are independent (disjoint blobs): the LARGE one (few long floods, one CTA per SM) runs on a
-        // forked side stream while the SMALL one fills the rest of the chip. Fork/join with events, so the sequence
-        // stays capturable and the caller's stream sees one ordered unit of work.
-        Fork* fk = get_fork();
-        CVB_CHECK(fk != nullptr, CVB_ECUDA, "cvb_postproc: could not create the side stream");
-        CVB_CUDA(cudaEventRecord(fk->fork, st));
-        CVB_CUDA(cudaStreamWaitEvent(fk->side, fk->fork, 0));
-        watershed_kernel<<<sms, 32, smem_l, fk->side>>>(w.queue, w.qstride, w.qmeta, 0, 1, w.cnt1, w.off1, w.blobpix, w.blb, w.marker,
-                                                        w.dist, d, LARGE_CAP, LARGE_RCAP, w.gkey, w.gpay, labels);
-        CVB_CUDA(cudaEventRecord(fk->join, fk->side));
-        watershed_kernel<<<sms * 5, 32, smem_s, st>>>(w.queue, w.qstride, w.qmeta, 1, NQ_CLASSES, w.cnt1, w.off1, w.blobpix, w.blb,
-                                                      w.marker, w.dist, d, SMALL_CAP, SMALL_RCAP, w.gkey, w.gpay, labels);
-        CVB_CUDA(cudaStreamWaitEvent(st, fk->join, 0));
+        // one launch, blobs largest class first; 21 KB of shared memory per single-warp CTA (see RankHeap): resident beside a
+        // tile-engine CTA, up to ten per SM when the chip is free
+        watershed_kernel<<<cvb_num_sms() * 6, 32, FL_SMEM, st>>>(w.queue, w.qstride, w.qmeta, w.cnt1, w.off1, w.blobpix, w.blb, w.marker,
+                                                                 w.dist, d, w.gkey, w.gpay, labels);
     }
     // ---- P8/P9
     if (table && counts) {
@@ -1160,7 +1133,7 @@ int run_pipeline(const Ws& w, const float* hv, Dims d, int n_types, int object_s
         table_accum_kernel<<<g, 256, 0, st>>>(labels, have_types ? w.tmap : nullptr, d, w.cap, w.acc, w.status, w.status + d.B + 16);
         table_finalize_kernel<<<d.B, 256, 0, st>>>(w.acc, w.cap, w.status + d.B + 16, have_types ? n_types : 0, max_rows, table, counts);
     }
-    cvb_note_launches(17 + ((table && counts) ? 3 : 0));
+    cvb_note_launches(16 + ((table && counts) ? 3 : 0));
     if (dbg_blb) CVB_CUDA(cudaMemcpyAsync(dbg_blb, w.blb, BN, cudaMemcpyDeviceToDevice, st));
     if (dbg_dist) CVB_CUDA(cudaMemcpyAsync(dbg_dist, w.dist, BN * 8, cudaMemcpyDeviceToDevice, st));
     if (dbg_marker) CVB_CUDA(cudaMemcpyAsync(dbg_marker, w.marker, BN * 4, cudaMemcpyDeviceToDevice, st));

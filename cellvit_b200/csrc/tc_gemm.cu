@@ -377,6 +377,16 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUte
     const uint32_t tmem_slot = bar_base + 8u * (2 * MAX_STAGES + 4);
     const uint32_t aux_off = (bar_base - smem_base) + 8u * (2 * MAX_STAGES + 4) + 16u;
     float* head_w_s = reinterpret_cast<float*>(smem_gen + aux_off);  // [8*64] + [8]
+    // dynamic tile scheduler (common.cuh): warp 2 of the leader CTA claims tiles, the 11 (+10 in the peer CTA) other role
+    // warps consume the same sequence; without a counter every role walks the static list tile0, tile0 + tile_step, ...
+    ptx::SchedRing sched;
+    sched.carve(smem_base + aux_off + HEAD_S_BYTES);
+    const bool dyn = p.epi.sched_counter != nullptr;
+    auto next_tile = [&](int k) -> int {
+        if (dyn) return sched.consume(k, rank, warp == 0 && rank == 0);
+        const int t = tile0 + k * tile_step;
+        return t < p.n_tiles ? t : -1;
+    };
 
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tmap(&tmA0);
@@ -392,6 +402,7 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUte
             ptx::mbar_init(tfull_bar(s), 1);
             ptx::mbar_init(tempty_bar(s), (PAIR ? 2 : 1) * (NUM_THREADS - 128));
         }
+        sched.init(rank == 0 ? 11 : 10, PAIR);   // role warps of this CTA: 0, 3, 4..11 and, in the leader, the MMA warp
         ptx::fence_barrier_init();
     }
     if (warp == 2) {
@@ -416,7 +427,9 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUte
         int stage = 0;
         uint32_t phase = 0;
         const uint32_t tx_bytes = (PAIR ? 2u : 1u) * (is_a ? (uint32_t)A_STAGE_BYTES : b_stage_bytes);
-        for (int tile = tile0; tile < p.n_tiles; tile += tile_step) {
+        for (int kt = 0;; ++kt) {
+            const int tile = next_tile(kt);
+            if (tile < 0) break;
             const int mt = tile / p.n_tiles_n, nt = tile - mt * p.n_tiles_n;
             const int m0 = mt * TILE_M + (int)rank * BLOCK_M, n0 = nt * p.block_n + (int)rank * b_rows;
             int img = 0, y0 = 0, x0 = 0;
@@ -476,8 +489,8 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUte
         const uint64_t desc_hi = (2ull << 61) | (1ull << 46) | ((uint64_t)(1024 >> 4) << 32);
         int stage = 0;
         uint32_t phase = 0;
-        int it = 0;
-        for (int tile = tile0; tile < p.n_tiles; tile += tile_step, ++it) {
+        for (int it = 0;; ++it) {
+            if (next_tile(it) < 0) break;
             const int as = it & 1;
             const uint32_t aphase = (it >> 1) & 1;
             ptx::mbar_wait(tempty_bar(as), aphase ^ 1u);
@@ -515,13 +528,14 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUte
         const int r = quad * 32 + lane;
         const int n_chunks = p.block_n / 32;  // block_n % 32 == 0 enforced on the host
         const int last_c = n_chunks - 1 - (((n_chunks - 1) & 1) != half ? 1 : 0);  // last chunk of this warp (may be < 0)
-        int it = 0;
         auto release_tmem = [&](int as_) {
             ptx::tc_fence_before();
             if (PAIR) ptx::mbar_arrive_cluster(tempty_bar(as_), 0);
             else ptx::mbar_arrive(tempty_bar(as_));
         };
-        for (int tile = tile0; tile < p.n_tiles; tile += tile_step, ++it) {
+        for (int it = 0;; ++it) {
+            const int tile = next_tile(it);
+            if (tile < 0) break;
             const int as = it & 1;
             const uint32_t aphase = (it >> 1) & 1;
             const int mt = tile / p.n_tiles_n, nt = tile - mt * p.n_tiles_n;
@@ -533,6 +547,9 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUte
 
             epilogue_tile(e, t_addr, m, row_ok, n0, n_chunks, half, last_c, head_w_s, true, [&]() { release_tmem(as); });
         }
+    } else if (warp == 2 && dyn) {
+        if (rank == 0) sched.produce<PAIR>(p.epi.sched_counter, p.n_tiles);
+        else sched.relay();
     }
 
     ptx::tc_fence_before();
@@ -589,6 +606,14 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     const uint32_t tmem_slot = bar_base + 8u * (8 + 2 * CP_MAX_BSTAGES);
     const uint32_t aux_off = (tmem_slot - smem_base) + 16u;
     float* head_w_s = reinterpret_cast<float*>(smem_gen + aux_off);
+    ptx::SchedRing sched;   // dynamic tile scheduler, as in tc_kernel (producer: warp 2)
+    sched.carve(smem_base + aux_off + HEAD_S_BYTES);
+    const bool dyn = p.epi.sched_counter != nullptr;
+    auto next_tile = [&](int k) -> int {
+        if (dyn) return sched.consume(k, 0, warp == 0);
+        const int t = (int)blockIdx.x + k * (int)gridDim.x;
+        return t < p.n_tiles ? t : -1;
+    };
 
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tmap(&tmA0);
@@ -606,6 +631,7 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
             ptx::mbar_init(bfull(s), 1);
             ptx::mbar_init(bempty(s), 1);
         }
+        sched.init(11, false);
         ptx::fence_barrier_init();
     }
     if (warp == 2) {
@@ -633,7 +659,9 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
         // ===================================================== patch producer (whole warp in the loop, one lane issues)
         int ps = 0;
         uint32_t pphase = 0;
-        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        for (int kt = 0;; ++kt) {
+            const int tile = next_tile(kt);
+            if (tile < 0) break;
             int img, y0, x0;
             tile_origin(tile, img, y0, x0);
             for (int c = 0; c < p.chunks; ++c) {
@@ -654,8 +682,9 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
         // ===================================================== weight producer: one [N x 64] tile per (chunk, tap)
         int bs = 0;
         uint32_t bphase = 0;
-        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-            if (p.resident && tile != (int)blockIdx.x) break;  // resident weights: one pass fills every slot for good
+        for (int kt = 0;; ++kt) {
+            if (next_tile(kt) < 0) break;
+            if (p.resident && kt > 0) continue;  // resident weights: one pass fills every slot for good (the tile sequence is still consumed)
             for (int c = 0; c < p.chunks; ++c) {
                 for (int tap = 0; tap < 9; ++tap) {
                     ptx::mbar_wait(bempty(bs), bphase ^ 1u);
@@ -671,9 +700,10 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
         // ===================================================== MMA issuer (whole warp in the loop, one lane issues)
         const uint32_t idesc = (1u << 4) | ((uint32_t)(p.N >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
         const uint64_t desc_hi = (2ull << 61) | (1ull << 46) | ((uint64_t)(1024 >> 4) << 32);
-        int ps = 0, bs = 0, it = 0;
+        int ps = 0, bs = 0;
         uint32_t pphase = 0, bphase = 0;
-        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+        for (int it = 0;; ++it) {
+            if (next_tile(it) < 0) break;
             const int as = it & 1;
             ptx::mbar_wait(tempty(as), ((it >> 1) & 1) ^ 1u);
             ptx::tc_fence_after();
@@ -712,8 +742,9 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
         const int quad = warp & 3, half = (warp - 4) >> 2;
         const int n_chunks = p.N / 32;
         const int last_c = n_chunks - 1 - (((n_chunks - 1) & 1) != half ? 1 : 0);
-        int it = 0;
-        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+        for (int it = 0;; ++it) {
+            const int tile = next_tile(it);
+            if (tile < 0) break;
             const int as = it & 1;
             int img, y0, x0;
             tile_origin(tile, img, y0, x0);
@@ -729,6 +760,8 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
                 });
             }
         }
+    } else if (warp == 2 && dyn) {
+        sched.produce<false>(p.epi.sched_counter, p.n_tiles);
     }
     ptx::tc_fence_before();
     __syncthreads();
@@ -810,7 +843,7 @@ int launch(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, T
     p.tmem_cols = cols;
     // 1024 B alignment slack + stages + barriers/tmem slot + head weights; always > half an SM so that
     // one CTA (and one 512-column TMEM allocation) lives on an SM at a time.
-    size_t smem = 1024 + (size_t)stages * (A_STAGE_BYTES + b_stage) + 8 * (2 * MAX_STAGES + 4) + 16 + HEAD_S_BYTES;
+    size_t smem = 1024 + (size_t)stages * (A_STAGE_BYTES + b_stage) + 8 * (2 * MAX_STAGES + 4) + 16 + HEAD_S_BYTES + ptx::SCHED_BYTES;
     if (smem < 120 * 1024) smem = 120 * 1024;
     static unsigned long long configured = 0;  // one bit per device: function attributes are per device
     const int cfg_dev = cvb_current_device();
@@ -913,7 +946,7 @@ static int conv_patch_launch(const __half* src0, int C0, const __half* src1, int
     p.tiles_x = W / BLOCK_M; p.tiles_y = H / CP_R; p.n_tiles = NB * p.tiles_x * p.tiles_y;
     p.epi = epi;
     const int b_stage = N * BLOCK_K * 2;
-    const int fixed = 1024 + 2 * CP_PATCH_BYTES + 8 * (8 + 2 * CP_MAX_BSTAGES) + 16 + HEAD_S_BYTES;
+    const int fixed = 1024 + 2 * CP_PATCH_BYTES + 8 * (8 + 2 * CP_MAX_BSTAGES) + 16 + HEAD_S_BYTES + ptx::SCHED_BYTES;
     int bst = (226 * 1024 - fixed) / b_stage;
     if (bst > CP_MAX_BSTAGES) bst = CP_MAX_BSTAGES;
     CVB_CHECK(bst >= 3, CVB_ESHAPE, "conv_patch: not enough shared memory for the weight ring (N=%d)", N);

@@ -36,6 +36,7 @@ struct TcEpilogue {
     int head_nc;
     int head_hw;                           // HEAD: H*W of one image
     float* head_out;                       // HEAD: [NB, nc, H, W]
+    int* sched_counter;                    // optional: device int, ZERO at launch -> tiles are claimed dynamically (SchedRing, common.cuh)
 };
 
 // C[M,N] = A[M,K] * W[N,K]^T.  A fp16 row-major (lda elements), W fp16 row-major [N, ldw] (K-major).

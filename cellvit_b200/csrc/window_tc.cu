@@ -34,7 +34,7 @@ constexpr uint32_t W_KB = W_KP * 128;      // one 208-row x 64-column box
 constexpr uint32_t W_RB = 64 * 128;        // rel-pos table box (64 rows)
 constexpr uint32_t W_ONES = 4 * 16 * 128;  // ones operand: 4 key blocks x 16 rows x 128 B
 constexpr int W_THREADS = 640;             // warps: 0 TMA, 1 issuer group 0, 2 TMEM alloc + issuer group 1, 3 idle, 4..19 softmax
-constexpr uint32_t W_SMEM = 1024 + 4 * W_QB + 5 * W_KB + 2 * W_RB + W_ONES + 2 * 2 * 128 * 4 + 256;
+constexpr uint32_t W_SMEM = 1024 + 4 * W_QB + 5 * W_KB + 2 * W_RB + W_ONES + 2 * 2 * 128 * 4 + 384;
 constexpr uint32_t W_COL_PB = 96, W_COL_O = 160, W_COL_L = 240;
 constexpr int W_KA = 96;                   // keys of the first half (6 k-steps); the second half has 112 (7 k-steps, 100 valid)
 
@@ -69,7 +69,7 @@ __device__ __forceinline__ void barrel14(const uint32_t (&p)[15], int s, uint32_
 __global__ void __launch_bounds__(W_THREADS, 1)
 window_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                  const __grid_constant__ CUtensorMap tmK16, const __grid_constant__ CUtensorMap tmR, int heads, int n_items,
-                 float scale, __half* __restrict__ out, long long* __restrict__ trace) {
+                 float scale, __half* __restrict__ out, int* __restrict__ sched_counter, long long* __restrict__ trace) {
     extern __shared__ uint8_t w_smem_raw[];
     const uint32_t smem_base = (ptx::smem_u32(w_smem_raw) + 1023u) & ~1023u;
     uint8_t* smem_gen = w_smem_raw + (smem_base - ptx::smem_u32(w_smem_raw));
@@ -98,6 +98,15 @@ window_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     auto p_full = [&](int g) { return bar + 8u * (11 + g); };
     auto o_full = [&](int g) { return bar + 8u * (13 + g); };
     const uint32_t tmem_slot = bar + 8u * 17;
+    // item sequence: claimed dynamically by warp 3 (SchedRing, common.cuh) when a counter is given, else blockIdx.x, + gridDim.x, ...
+    ptx::SchedRing sched;
+    sched.carve(bar + 8u * 18);
+    const bool dyn = sched_counter != nullptr;
+    auto next_item = [&](int k) -> int {
+        if (dyn) return sched.consume(k, 0, warp == 0);
+        const int t = (int)blockIdx.x + k * (int)gridDim.x;
+        return t < n_work ? t : -1;
+    };
 
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tmap(&tmQ); ptx::prefetch_tmap(&tmK); ptx::prefetch_tmap(&tmK16); ptx::prefetch_tmap(&tmR);
@@ -109,6 +118,7 @@ window_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
             ptx::mbar_init(g_full(g), 1); ptx::mbar_init(qg_ready(g), 256); ptx::mbar_init(s_full(g), 1);
             ptx::mbar_init(p_full(g), 256); ptx::mbar_init(o_full(g), 1);
         }
+        sched.init(19, false);   // consumers: TMA warp, two issuer warps, sixteen softmax warps
         ptx::fence_barrier_init();
     }
     if (warp == 2) {
@@ -159,8 +169,9 @@ window_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
             ptx::tma_load_2d(sR0, &tmR, const_full, 0, 0);
             ptx::tma_load_2d(sRt, &tmR, const_full, 16, 0);
         }
-        int it = 0;
-        for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++it) {
+        int w = next_item(0);
+        for (int it = 0; w >= 0; ++it) {
+            const int w_next = next_item(it + 1);
             const int item = w / heads, head = w - item * heads;
             const int row0 = item * W_S;
             const uint32_t par = (uint32_t)(it & 1);
@@ -195,8 +206,8 @@ window_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
             }
             // L2 prefetch of the next item's operands: all CTAs reload at about the same time, and a DRAM-latency burst of
             // 148 x 168 KB would otherwise sit between this item's S MMAs and the next item's G
-            if (w + (int)gridDim.x < n_work && ptx::elect_one()) {
-                const int w2 = w + (int)gridDim.x, item2 = w2 / heads, head2 = w2 - item2 * heads, r2 = item2 * W_S;
+            if (w_next >= 0 && ptx::elect_one()) {
+                const int w2 = w_next, item2 = w2 / heads, head2 = w2 - item2 * heads, r2 = item2 * W_S;
 #pragma unroll
                 for (int g = 0; g < 2; ++g) {
                     ptx::tma_prefetch_2d(&tmQ, head2 * W_HD, r2 + g * W_BQ);
@@ -211,6 +222,7 @@ window_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                     ptx::tma_prefetch_2d(tm, 2 * D + head2 * W_HD + 64, r2 + t * 64);
                 }
             }
+            w = w_next;
         }
     } else if (warp == 1 || warp == 2) {
         // ===================================================== MMA issuer of query group g
@@ -237,14 +249,16 @@ window_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
             }
             __syncwarp();
         };
-        int it = 0;
-        if (blockIdx.x < n_work) {
+        int w = next_item(0);
+        if (w >= 0) {
+            const int it = 0;
             ptx::mbar_wait(qk_full, 0);
             ptx::tc_fence_after();
             W_TR(9 + 8 * g);
             issue_g();
         }
-        for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++it) {
+        for (int it = 0; w >= 0; ++it) {
+            const int w_next = next_item(it + 1);
             const uint32_t par = (uint32_t)(it & 1);
             // Gsel written -- which also means that every thread of the group has read G and the previous item's O / l
             ptx::mbar_wait(qg_ready(g), par);
@@ -277,7 +291,7 @@ window_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                 ptx::umma_commit(v_free);
             }
             __syncwarp();
-            if (w + (int)gridDim.x < n_work) {
+            if (w_next >= 0) {
                 // next item's G while the softmax threads store this item's output: Q of the next item landed long ago (its
                 // load started when this item's S MMAs completed); P V must have finished reading P out of columns 0..47
                 ptx::mbar_wait(qk_full, par ^ 1u);
@@ -287,7 +301,10 @@ window_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                 W_TR(13 + 8 * g);
                 issue_g();
             }
+            w = w_next;
         }
+    } else if (warp == 3) {
+        if (dyn) sched.produce<false>(sched_counter, n_work);
     } else if (warp >= 4) {
         // ===================================================== softmax / output: two threads per query row
         const int idx = warp - 4, quad = warp & 3, grp = (idx >> 2) & 1, half = idx >> 3;
@@ -306,8 +323,9 @@ window_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         const float* x_peer = xch + (grp * 2 + (half ^ 1)) * 128 + r;
         const int pair_bar = 1 + grp * 4 + quad;
         auto fl = [](uint32_t u) { return __uint_as_float(u); };
-        int it = 0;
-        for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++it) {
+        for (int it = 0;; ++it) {
+            const int w = next_item(it);
+            if (w < 0) break;
             const int item = w / heads, head = w - item * heads;
             const uint32_t par = (uint32_t)(it & 1);
             const uint32_t ts = tS(grp) + lane_off;
@@ -436,7 +454,7 @@ extern "C" __attribute__((visibility("default"))) void cvb_debug_window_trace(vo
 bool op_window_attention_tc_supported(int S, int hd, int gh, int gw) { return hd == W_HD && S == W_S && gh == W_G && gw == W_G; }
 
 int op_window_attention_tc(const __half* qkv, int n_items, int heads, int hd, float scale, const __half* relcat, __half* out,
-                           cudaStream_t stream) {
+                           int* sched_counter, cudaStream_t stream) {
     CVB_CHECK(qkv && out && relcat, CVB_EARG, "window_attention_tc: null operand");
     CVB_CHECK(hd == W_HD && n_items > 0 && heads > 0, CVB_ESHAPE, "window_attention_tc: needs head dim 80");
     const int D = heads * hd;
@@ -454,7 +472,7 @@ int op_window_attention_tc(const __half* qkv, int n_items, int heads, int hd, fl
     CVB_TRY(cvb_tmap_2d_f16(&tr, relcat, (uint64_t)W_HD, 64, (uint64_t)W_HD * 2, 64, 64));
     const int n_work = n_items * heads;
     const int grid = n_work < cvb_num_sms() ? n_work : cvb_num_sms();
-    window_tc_kernel<<<grid, W_THREADS, W_SMEM, stream>>>(tq, tk, tk16, tr, heads, n_items, scale, out, g_window_trace);
+    window_tc_kernel<<<grid, W_THREADS, W_SMEM, stream>>>(tq, tk, tk16, tr, heads, n_items, scale, out, sched_counter, g_window_trace);
     cvb_note_launches(1);
     CVB_CUDA(cudaGetLastError());
     return CVB_OK;

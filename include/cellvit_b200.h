@@ -154,9 +154,10 @@ int cvb_op_attention_tc(const void* qkv, int Gb, int S, int heads, int hd, float
                         int gh, int gw, void* out, void* workspace, size_t ws_bytes, void* stream);
 /* tcgen05 attention for the 14 x 14 SAM windows (window_tc.cu; image_encoder.py:235-260 on window_partition'ed tokens):
  * qkv fp16 [n_items*196, 3*D] in window order, relcat fp16 [64, 80] (rel_h table rows at 0.., rel_w table rows at 32..),
- * out fp16 [n_items*196, D]. One kernel, no workspace. */
+ * out fp16 [n_items*196, D]. One kernel, no workspace. sched_counter (nullable): device int that is ZERO at launch; the
+ * persistent CTAs then claim their (window, head) items from it instead of walking a static list. */
 int cvb_op_window_attention_tc(const void* qkv, int n_items, int heads, int hd, float scale, const void* relcat, void* out,
-                               void* stream);
+                               int32_t* sched_counter, void* stream);
 int cvb_op_patch_im2col(const float* x, int B, int H, int W, int P, void* out, void* stream);
 int cvb_op_stem_conv(const float* x, int B, int H, int W, const float* w, const float* scale, const float* shift,
                      void* out, int cpad, void* stream);

@@ -186,8 +186,9 @@ def test_forward_sam_h_1024_attention_tc_vs_mma_sync():
             assert err <= tol, (k, err)
 
 
-@pytest.mark.parametrize("n_items,heads,zero_bias", [(1, 1, True), (1, 1, False), (3, 2, False), (25, 4, False), (160, 16, False)])
-def test_window_attention_tc_matches_torch(n_items, heads, zero_bias):
+@pytest.mark.parametrize("n_items,heads,zero_bias,dynamic", [(1, 1, True, False), (1, 1, False, False), (3, 2, False, True), (25, 4, False, False),
+                                                             (160, 16, False, False), (160, 16, False, True)])
+def test_window_attention_tc_matches_torch(n_items, heads, zero_bias, dynamic):
     """tcgen05 window attention (window_tc.cu): 14 x 14 windows, head dim 80, rel-pos bias produced in the kernel, V read
     in place as an MN-major operand; 160 x 16 pairs exercise the persistent loop (several pairs per CTA). The zero-bias
     case isolates the Q K^T / softmax / P V path from the rel-pos path."""
@@ -205,8 +206,9 @@ def test_window_attention_tc_matches_torch(n_items, heads, zero_bias):
     relcat[32:59] = Rw
     out = torch.full((n_items * S, D), float("nan"), device="cuda", dtype=torch.half)
     scale = hd ** -0.5
+    ctr = torch.zeros(1, dtype=torch.int32, device="cuda")   # dynamic: items claimed from a zeroed counter (SchedRing)
     L.check(L.lib().cvb_op_window_attention_tc(L.ptr(qkv), n_items, heads, hd, C.c_float(scale), L.ptr(relcat), L.ptr(out),
-                                               L.stream_ptr()), "window_tc")
+                                               L.ptr(ctr) if dynamic else None, L.stream_ptr()), "window_tc")
     torch.cuda.synchronize()
     ref = _ref_attention(qkv, n_items, S, heads, hd, scale, Rh.float(), Rw.float(), gh, gw)
     assert torch.isfinite(out.float()).all()

@@ -30,10 +30,14 @@ def _model(arch, sd):
     return m.cuda().eval()
 
 
-def _scaled_heads(arch, seed, x, target=10.0):
+def _scaled_heads(arch, seed, x, target=10.0, smooth_upsampling=False):
     """Synthetic weights whose 1x1 heads are rescaled so that every head map spans roughly +-target (random-init logits are
     <= 0.15, which hides relative errors: SURVEY.md section 7.3-2). The factor comes from the fp32 oracle's own head outputs."""
     sd = weights.synth_state_dict(arch, 6, 19, seed=seed)
+    if smooth_upsampling:   # random 2x2 transposed convolutions emit a pixel-scale checkerboard: make them nearest-neighbour-like
+        for k, v in sd.items():
+            if v.ndim == 4 and tuple(v.shape[-2:]) == (2, 2):
+                sd[k] = v[:, :, :1, :1].expand_as(v).contiguous()
     ref = forward_oracle.cellvit_forward(sd, x, arch, retrieve_tokens=False)
     for branch, key in zip(HEADS, ("nuclei_binary_map", "hv_map", "nuclei_type_map")):
         w, b = f"{branch}_decoder.decoder0_header.2.weight", f"{branch}_decoder.decoder0_header.2.bias"
@@ -101,14 +105,20 @@ def test_forward_sam_h_batch4_1024_matches_oracle_on_device():
         assert err <= 1e-3, (k, err)
 
 
-def test_postprocessing_of_the_models_own_head_maps_matches_oracle():
-    """Heads rescaled to magnitude ~10 with zero-mean channels give spatially varying arg-max maps (many small components): the
-    device post-processing consumes the forward's own output buffers (fused head epilogue -> prep_float_kernel hand-off) and must
-    equal the oracle's post-processing of the very same maps copied to the host."""
+@pytest.mark.parametrize("seed", [12, 16, 18])
+def test_postprocessing_of_the_models_own_head_maps_matches_oracle(seed):
+    """The device post-processing consumes the forward's own output buffers (fused head epilogue -> prep_float_kernel hand-off) and
+    must equal the oracle's post-processing of the very same maps copied to the host. Random-init networks emit degenerate maps
+    (SURVEY.md 8d), so the network is made to produce nuclei-like ones: a tile with nuclei-sized blobs, nearest-neighbour-like
+    transposed convolutions (no checkerboard), heads rescaled to |logit| ~ 10 with zero-mean channels. The seeds are ones for
+    which the CPU oracle's own maps give ~20 instances per tile (most random HV heads leave no marker at all)."""
     from cellvit_b200.post_proc_cellvit import DetectionCellPostProcessor
-    arch, size, B = "ViT256", 256, 2
-    x = torch.from_numpy(synth.synthetic_tiles(B, size, seed=21))
-    sd = _scaled_heads(arch, 7, x)
+    arch, size, B = "ViT256", 256, 1
+    x = torch.from_numpy(synth.synthetic_tiles(B, size, seed=21)) * 0.02
+    mask = torch.from_numpy(synth.synthetic_nuclei(size, 30, seed=60)["np_bin"].astype(np.float32))
+    mask = F.avg_pool2d(mask[None, None], 5, 1, 2)[0, 0]
+    x[0] += torch.stack([1.4 * mask - 0.6, 0.9 * mask - 0.4, -1.1 * mask + 0.5])
+    sd = _scaled_heads(arch, seed, x, smooth_upsampling=True)
     m = _model(arch, sd)
     with torch.no_grad():
         out = m(x.cuda(), retrieve_tokens=True)
@@ -118,19 +128,17 @@ def test_postprocessing_of_the_models_own_head_maps_matches_oracle():
     np_bin = out["nuclei_binary_map"].argmax(1).cpu().numpy().astype(np.uint8)
     nt = out["nuclei_type_map"].argmax(1).cpu().numpy()
     hv = out["hv_map"].cpu().numpy()
-    n_fg = 0
     for b in range(B):
-        assert 0.02 < np_bin[b].mean() < 0.98, "degenerate NP map: the test needs spatially varying head outputs"
         pm = np.concatenate([nt[b][..., None], np_bin[b][..., None], hv[b].transpose(1, 2, 0)], -1).astype(np.float64)
         olab, odict = po.DetectionCellPostProcessor(6, 40).post_process_cell_segmentation(pm)
+        print("seed", seed, "foreground", float(np_bin[b].mean()), "instances", len(odict))
+        assert len(odict) >= 5, "the construction no longer gives a non-degenerate instance map"
         assert np.array_equal(labels[b], olab)
         assert sorted(dicts[b]) == sorted(odict)
         for k, ov in odict.items():
             gv = dicts[b][k]
             assert np.array_equal(gv["bbox"], ov["bbox"]) and np.array_equal(gv["centroid"], ov["centroid"])
             assert np.array_equal(gv["contour"], ov["contour"]) and gv["type"] == ov["type"] and gv["type_prob"] == ov["type_prob"]
-        n_fg += len(odict)
-    assert n_fg > 0
 
 
 def test_pipeline_accepts_lazy_device_batches_and_uint8_device_tiles():

@@ -222,3 +222,25 @@ def test_patch_resident_conv_matches_kblock_conv_and_reference(C0, C1, N, H, W):
     for o in outs:
         assert (o.permute(0, 3, 1, 2).float() - ref).abs().max().item() < tol
     assert (outs[0].float() - outs[1].float()).abs().max().item() < 2 * tol
+
+
+@pytest.mark.parametrize("M,K,N,bn", [(4096 * 4, 1280, 3840, 256), (19600, 1280, 1280, 256), (513, 5120, 1280, 256), (300, 128, 64, 64)])
+def test_gemm_dynamic_tile_scheduler_is_bit_identical(M, K, N, bn):
+    """Tiles claimed from a zeroed per-launch counter (SchedRing: single-CTA and CTA-pair mode) give exactly the result of the
+    static tile lists, and the counter ends at tiles + one terminator claim per claiming warp."""
+    g = torch.Generator(device="cuda").manual_seed(5)
+    A = (torch.randn(M, K, device="cuda", generator=g) * 0.5).half()
+    W = (torch.randn(N, K, device="cuda", generator=g) * 0.05).half()
+    shift = torch.randn(N, device="cuda", generator=g) * 0.1
+    outs = []
+    for dynamic in (False, True, True):
+        out = torch.full((M, N), float("nan"), device="cuda", dtype=torch.half)
+        ctr = torch.zeros(1, dtype=torch.int32, device="cuda")
+        epi = L.TcEpilogue(kind=L.EPI_F16, act=0, shift=shift.data_ptr(), out=out.data_ptr(), ldc=N,
+                           sched_counter=ctr.data_ptr() if dynamic else None)
+        _gemm(A, W, epi, bn)
+        outs.append(out)
+        if dynamic:
+            assert int(ctr.item()) > 0
+    assert torch.isfinite(outs[0].float()).all()
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])

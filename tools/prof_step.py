@@ -6,7 +6,9 @@ from cellvit_b200 import synth
 from cellvit_b200 import _lib as _L
 torch.manual_seed(0)
 m = CellViTSAM(None, 6, 19, "SAM-H").eval().cuda()
-if len(sys.argv) > 1: m.set_engine_option("attention_tc", int(sys.argv[1]))   # attention mode bits (see csrc/model.cu)
+import os
+if len(sys.argv) > 1: m.set_engine_option("attention_tc", int(sys.argv[1]))
+if os.environ.get("CVB_DYN") is not None: m.set_engine_option("dynamic_tiles", int(os.environ["CVB_DYN"]))   # attention mode bits (see csrc/model.cu)
 x = torch.from_numpy(synth.synthetic_tiles(4, 1024, seed=1)).cuda()
 nuc = [synth.synthetic_nuclei(1024, 700, seed=i) for i in range(4)]
 lg = [synth.head_logits_from_maps(n["np_bin"], n["nt"], 6) for n in nuc]

@@ -1,6 +1,6 @@
 """Times one window-attention implementation at the BASELINE shape (SAM-H, B = 4: 100 windows x 16 heads, 196 tokens,
 head dim 80) with CUDA events, and checks it against the torch expression of image_encoder.py:235-260,354-392.
-usage: python tools/time_window.py <variant>     0 = mma.sync window kernel, 1 = tcgen05 kernel (window_tc.cu); optional third argument `zero` = zero rel-pos tables"""
+usage: python tools/time_window.py <variant>     0 = mma.sync window kernel, 1 = tcgen05 kernel (window_tc.cu), 2 = the same with dynamic item scheduling; optional third argument `zero` = zero rel-pos tables"""
 import ctypes as C
 import sys
 
@@ -23,6 +23,7 @@ relcat[32:59] = Rw
 out = torch.full((n_items * S, D), float("nan"), device="cuda", dtype=torch.half)
 scale = hd ** -0.5
 lib = L.lib()
+ctr = torch.zeros(1, dtype=torch.int32, device="cuda")
 if len(sys.argv) > 3 and sys.argv[3] == "zero":
     relcat.zero_(); Rh.zero_(); Rw.zero_()
 
@@ -32,8 +33,10 @@ def run():
         L.check(lib.cvb_op_attention(L.ptr(qkv), n_items, S, heads, hd, C.c_float(scale), L.ptr(Rh), L.ptr(Rw), gh, gw, L.ptr(out),
                                      L.stream_ptr()), "attention")
     else:
+        if variant == 2:   # dynamic item scheduling
+            ctr.zero_()
         L.check(lib.cvb_op_window_attention_tc(L.ptr(qkv), n_items, heads, hd, C.c_float(scale), L.ptr(relcat), L.ptr(out),
-                                               L.stream_ptr()), "window_tc")
+                                               L.ptr(ctr) if variant == 2 else None, L.stream_ptr()), "window_tc")
 
 
 run()

@@ -13,7 +13,7 @@ relcat = (torch.randn(64, hd, device="cuda", generator=g) * 0.2).half()
 out = torch.empty(n_items * S, D, device="cuda", dtype=torch.half)
 lib = L.lib()
 def run():
-    L.check(lib.cvb_op_window_attention_tc(L.ptr(qkv), n_items, heads, hd, C.c_float(hd ** -0.5), L.ptr(relcat), L.ptr(out), L.stream_ptr()), "w")
+    L.check(lib.cvb_op_window_attention_tc(L.ptr(qkv), n_items, heads, hd, C.c_float(hd ** -0.5), L.ptr(relcat), L.ptr(out), None, L.stream_ptr()), "w")
 for _ in range(3): run()
 torch.cuda.synchronize()
 tr = torch.zeros(8 * 64, dtype=torch.int64, device="cuda")
