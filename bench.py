@@ -171,6 +171,10 @@ def run_gpu(args):
         dist.init_process_group("nccl", device_id=dev)
     lib = L.lib()
     lib.cvb_launch_count.restype = C.c_longlong
+    if os.environ.get("CVB_SKIP_FLOOD") == "1":   # timing experiment: how much of the overlap loss the flood kernels cause
+        lib.cvb_debug_postproc_skip_flood(1)
+    if os.environ.get("CVB_POST_CTAS"):
+        lib.cvb_debug_postproc_max_ctas(int(os.environ["CVB_POST_CTAS"]))
     arch = args.arch
     cfg = ARCHS[arch]
     B, K, Wm = args.batch or cfg["batch"], args.steps, args.warmup
@@ -395,6 +399,28 @@ def run_gpu(args):
             tf, tp = cpu_tile_seconds(arch, cores, 1)
             cpu_base = {"value": 1.0 / (tf + tp), "unit": "tiles/s", "cores": cores, "kind": "port",
                         "sample": f"1 tile: oracle fp32 forward {tf:.2f}s ({cores} threads) + C post-processing {tp:.2f}s (1 thread)"}
+            # informative second baseline: how the reference itself runs on a GPU box (cell_detection.py:306-323): eager PyTorch
+            # forward under fp16 autocast on the GPU, then the per-tile post-processing on ONE host thread, strictly in sequence
+            try:
+                from cellvit_b200 import weights
+                from oracle import forward_oracle
+                del model
+                torch.cuda.empty_cache()
+                sd_dev = {k: v.to(dev) for k, v in weights.synth_state_dict(arch, 6, 19, seed=0).items()}
+                n_t = 4
+                with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):
+                    forward_oracle.cellvit_forward(sd_dev, x_dev[:1], arch, retrieve_tokens=True)
+                    torch.cuda.synchronize()
+                    t0 = time.perf_counter()
+                    for i in range(n_t):
+                        forward_oracle.cellvit_forward(sd_dev, x_dev[i % B:i % B + 1], arch, retrieve_tokens=True)
+                    torch.cuda.synchronize()
+                    t_fwd = (time.perf_counter() - t0) / n_t
+                cpu_base["gpu_eager"] = {"value": 1.0 / (t_fwd + tp), "unit": "tiles/s", "kind": "port",
+                                         "sample": f"oracle forward in eager PyTorch on this GPU under fp16 autocast {t_fwd * 1e3:.0f} ms/tile "
+                                                   f"+ C post-processing on one host thread {tp:.2f}s/tile, sequential (the reference's own GPU mode)"}
+            except Exception as ex:   # informative only
+                cpu_base["gpu_eager"] = {"unavailable": repr(ex)[:200]}
     if world > 1:
         dist.barrier()
     if rank == 0:

@@ -536,6 +536,62 @@ struct Heap {
     }
 };
 
+// 4-ary heap of packed 16-byte entries in shared memory (one LDS.128 per entry, four independent child loads per
+// level, depth log4 n). Any correct priority queue gives the same flood because (value, age, index) is a strict
+// total order; the array has 4 slack entries so that the child loads never need a bounds check.
+// Entries are two 64-bit integers: k = order-preserving image of the fp64 value (with -0.0 folded onto +0.0, as the
+// floating-point comparison does), ai = age << 32 | index -- so "less" is two integer compares instead of a chain of
+// fp64 ones.
+struct __align__(16) HItem { unsigned long long k, ai; };
+__device__ __forceinline__ unsigned long long f64_order_key(double v) {
+    const long long b = __double_as_longlong(v + 0.0);
+    return b < 0 ? ~(unsigned long long)b : ((unsigned long long)b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ HItem make_item(double v, int age, int idx) {
+    HItem it;
+    it.k = f64_order_key(v);
+    it.ai = ((unsigned long long)(unsigned)age << 32) | (unsigned)idx;
+    return it;
+}
+__device__ __forceinline__ bool it_less(const HItem& a, const HItem& b) { return a.k < b.k || (a.k == b.k && a.ai < b.ai); }
+struct Heap4 {
+    HItem* a;
+    int n;
+    __device__ __forceinline__ void sift_down(int i, HItem x) {
+        for (;;) {
+            const int c = 4 * i + 1;
+            if (c >= n) break;
+            HItem best = a[c];
+            const HItem t1 = a[c + 1], t2 = a[c + 2], t3 = a[c + 3];
+            int bi = c;
+            if (c + 1 < n && it_less(t1, best)) { best = t1; bi = c + 1; }
+            if (c + 2 < n && it_less(t2, best)) { best = t2; bi = c + 2; }
+            if (c + 3 < n && it_less(t3, best)) { best = t3; bi = c + 3; }
+            if (!it_less(best, x)) break;
+            a[i] = best;
+            i = bi;
+        }
+        a[i] = x;
+    }
+    __device__ __forceinline__ void push(HItem x) {
+        int i = n++;
+        while (i > 0) {
+            const int par = (i - 1) >> 2;
+            const HItem pv = a[par];
+            if (!it_less(x, pv)) break;
+            a[i] = pv;
+            i = par;
+        }
+        a[i] = x;
+    }
+    __device__ __forceinline__ HItem pop() {
+        const HItem top = a[0];
+        --n;
+        if (n > 0) sift_down(0, a[n]);
+        return top;
+    }
+};
+
 // ---- fast path of the flood: rank transform + packed 32-bit keys.
 // The flood only ever COMPARES dist values, so a blob's fp64 values are replaced by their rank among the blob's pixels
 // (rank = number of strictly smaller values: equal values keep equal ranks, so ties still fall through to age and index).
@@ -548,8 +604,9 @@ struct Heap {
 // occupies the SM alone, and the statically scheduled persistent GEMM that follows runs that SM's tiles late.
 constexpr int FL_MAXN = 1023;                 // pixels per blob on the fast path
 constexpr int FL_HC = FL_MAXN + 1 + 8;        // heap array entries (node k at [k + 3], 4 slack entries)
-constexpr int FL_RC = 2816;                   // staged cells (bounding box + 1-pixel apron)
-constexpr int FL_SMEM = FL_HC * 4 + FL_RC * 4 + FL_RC * 2;   // 21,024 B
+constexpr int FL_RC = 4096;                   // staged cells (bounding box + 1-pixel apron): the key's 12-bit cell field
+constexpr int FL_SMEM = FL_HC * 4 + FL_RC * 4 + FL_RC * 2;   // 28,704 B
+constexpr int Q_DEFER = NQ_CLASSES;           // extra queue: blobs of classes 1..5 whose bounding box exceeds FL_RC cells
 constexpr uint32_t FL_SENT = 0xFFFFFFFFu;
 
 struct RankHeap {
@@ -594,10 +651,11 @@ struct RankHeap {
 // result). Blobs above the fast path's limits run the same flood with a binary heap of (fp64 value, age, index) in global
 // scratch, one L2 round trip per pop.
 __global__ void __launch_bounds__(32)
-watershed_kernel(const int* __restrict__ queue_base, int qstride, int* __restrict__ qmeta, const int* __restrict__ cnt,
+watershed_kernel(const int* __restrict__ queue_base, int qstride, int* __restrict__ qmeta, int cls_begin, int cls_end, const int* __restrict__ cnt,
                  const int* __restrict__ off, const int* __restrict__ blobpix, const uint8_t* __restrict__ blb, const int* __restrict__ marker,
-                 const double* __restrict__ dist, Dims d, double* __restrict__ gkey, int2* __restrict__ gpay, int* labels_) {
-    // shared memory: [heap u32 x FL_HC][labels i32 x FL_RC (aliased by the blob's fp64 values while they are ranked)][ranks u16 x FL_RC]
+                 const double* __restrict__ dist, Dims d, int cap_entries, int rcap, double* __restrict__ gkey, int2* __restrict__ gpay, int* labels_) {
+    // cap_entries > 0 selects the LARGE layout [heap: (cap_entries + 4) x 16 B][region dist: rcap x 8 B][region labels: rcap x 4 B]
+    // (blobs above the rank path's limits, fp64 values and 16-byte heap entries); else: [heap u32 x FL_HC][labels i32 x FL_RC (aliased by the blob's fp64 values while they are ranked)][ranks u16 x FL_RC]
     extern __shared__ __align__(16) uint8_t ws_smem[];
     volatile int* labels = labels_;
     uint32_t* sheap = reinterpret_cast<uint32_t*>(ws_smem);
@@ -606,7 +664,7 @@ watershed_kernel(const int* __restrict__ queue_base, int qstride, int* __restric
     uint16_t* srank = reinterpret_cast<uint16_t*>(ws_smem + (size_t)FL_HC * 4 + (size_t)FL_RC * 4);
     static_assert((FL_HC * 4) % 16 == 0 && FL_MAXN * 8 <= FL_RC * 4, "flood shared-memory layout");
     const int lane = threadIdx.x;
-    for (int cls = 0; cls < NQ_CLASSES; ++cls) {
+    for (int cls = cls_begin; cls < cls_end; ++cls) {
     const int qn = qmeta[cls];
     const int* queue = queue_base + (long long)cls * qstride;
     int* qhead = qmeta + 8 + cls;
@@ -627,7 +685,7 @@ watershed_kernel(const int* __restrict__ queue_base, int qstride, int* __restric
         // ---- fast path: the blob's bounding box (+1 pixel apron) is staged into shared memory and lane 0 runs the serial
         // priority flood entirely out of shared memory. Local raster indices order like the global ones, so the
         // (value, age, index) total order is unchanged.
-        if (n <= FL_MAXN) {
+        if (cap_entries == 0 && n <= FL_MAXN) {
             int y0 = d.H, y1 = -1, x0 = d.W, x1 = -1;
             for (int i = lane; i < n; i += 32) {
                 const int p = list[i];
@@ -717,6 +775,92 @@ watershed_kernel(const int* __restrict__ queue_base, int qstride, int* __restric
                 __syncwarp();
                 continue;
             }
+        }
+        if (cap_entries == 0) {
+            // few pixels but a bounding box beyond the rank path's region (a thin diagonal chain of nuclei): hand the blob to the
+            // LARGE-layout launch that follows instead of flooding it through L2 (2 us per pop: one such blob took 1.5 ms)
+            if (lane == 0) const_cast<int*>(queue_base)[(long long)Q_DEFER * qstride + atomicAdd(&qmeta[Q_DEFER], 1)] = gi;
+            continue;
+        }
+        {
+            HItem* lheap = reinterpret_cast<HItem*>(ws_smem);
+            double* ldist = reinterpret_cast<double*>(ws_smem + (size_t)(cap_entries + 4) * 16);
+            int* llab = reinterpret_cast<int*>(ws_smem + (size_t)(cap_entries + 4) * 16 + (size_t)rcap * 8);
+        {
+            int y0 = d.H, y1 = -1, x0 = d.W, x1 = -1;
+            for (int i = lane; i < n; i += 32) {
+                const int p = list[i];
+                const int y = p / d.W, x = p - y * d.W;
+                y0 = min(y0, y); y1 = max(y1, y); x0 = min(x0, x); x1 = max(x1, x);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                y0 = min(y0, __shfl_xor_sync(0xffffffffu, y0, o));
+                y1 = max(y1, __shfl_xor_sync(0xffffffffu, y1, o));
+                x0 = min(x0, __shfl_xor_sync(0xffffffffu, x0, o));
+                x1 = max(x1, __shfl_xor_sync(0xffffffffu, x1, o));
+            }
+            const int rw = x1 - x0 + 3, rh = y1 - y0 + 3;
+            const long long cells_ll = (long long)rw * rh;
+            if (n <= cap_entries && cells_ll <= (long long)rcap) {
+                const int cells = (int)cells_ll;
+                int* gout = labels_ + base;
+                // only this blob's pixels enter the region (via its pixel list): everything else, including pixels of
+                // other blobs inside the bounding box and the whole apron, is "outside the mask"
+                for (int c = lane; c < cells; c += 32) llab[c] = -1;
+                __syncwarp();
+                for (int i = lane; i < n; i += 32) {
+                    const int p = list[i];
+                    const int y = p / d.W, x = p - y * d.W;
+                    const int c = (y - y0 + 1) * rw + (x - x0 + 1);
+                    llab[c] = gout[p];
+                    ldist[c] = ds[p];
+                }
+                __syncwarp();
+                Heap4 hq;
+                hq.a = lheap;
+                int n_seed = 0;
+                for (int c0 = 0; c0 < cells; c0 += 32) {
+                    const int c = c0 + lane;
+                    bool is_seed = false;
+                    if (c < cells && llab[c] > 0)  // labelled cells are never on the apron, so the four neighbours exist
+                        is_seed = llab[c - rw] == 0 || llab[c - 1] == 0 || llab[c + 1] == 0 || llab[c + rw] == 0;
+                    const uint32_t bits = __ballot_sync(0xffffffffu, is_seed);
+                    if (is_seed) lheap[n_seed + __popc(bits & ((1u << lane) - 1u))] = make_item(ldist[c], 0, c);
+                    n_seed += __popc(bits);
+                }
+                __syncwarp();
+                if (lane == 0) {
+                    hq.n = n_seed;
+                    for (int i = (n_seed - 2) / 4; i >= 0 && n_seed > 1; --i) hq.sift_down(i, lheap[i]);  // Floyd heapify
+                    int age = 0;
+                    while (hq.n > 0) {
+                        const HItem t = hq.pop();
+                        const int c = (int)(unsigned)t.ai;
+                        const int lab = llab[c];
+                        const int qs[4] = {c - rw, c - 1, c + 1, c + rw};  // up, left, right, down
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const int q = qs[k];
+                            if (llab[q] == 0) {
+                                ++age;
+                                llab[q] = lab;  // labelled at push time
+                                hq.push(make_item(ldist[q], age, q));
+                            }
+                        }
+                    }
+                }
+                __syncwarp();
+                for (int i = lane; i < n; i += 32) {
+                    const int p = list[i];
+                    const int y = p / d.W, x = p - y * d.W;
+                    const int lab = llab[(y - y0 + 1) * rw + (x - x0 + 1)];
+                    if (lab > 0 && gout[p] == 0) gout[p] = lab;  // pixels this flood labelled
+                }
+                __syncwarp();
+                continue;
+            }
+        }
         }
         Heap hp;
         hp.key = gkey + base + off[base + root];
@@ -808,28 +952,46 @@ __global__ void table_init_kernel(Acc* acc, long long n, int H, int W) {
 }
 __global__ void table_accum_kernel(const int* __restrict__ labels, const uint8_t* __restrict__ tmap, Dims d, int cap, Acc* __restrict__ acc,
                                    int* __restrict__ status, int* __restrict__ maxid) {
+    // Warp-aggregated: the 32 pixels of a warp are consecutive in one image row (H * W and the stride are multiples of 32) and
+    // carry one or two distinct labels, so each group of equal labels is reduced inside the warp (match_any + redux) and its
+    // leader issues ONE set of atomics -- the per-pixel version spent its time in ~8 contended atomics per foreground pixel.
     const long long total = (long long)d.B * d.N;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int l = labels[i];
-        const int b = (int)(i / d.N), p = (int)(i - (long long)b * d.N);
-        if (l == 0) {  // only "is there any background" matters (the np.unique(...)[1:] quirk)
+    const int lane = threadIdx.x & 31;
+    const long long n_iter = (total + (long long)gridDim.x * blockDim.x - 1) / ((long long)gridDim.x * blockDim.x);
+    for (long long it = 0; it < n_iter; ++it) {
+        const long long i = it * (long long)gridDim.x * blockDim.x + blockIdx.x * (long long)blockDim.x + threadIdx.x;
+        const bool in = i < total;
+        const int l = in ? labels[i] : 0;
+        const int b = in ? (int)(i / d.N) : 0, p = in ? (int)(i - (long long)b * d.N) : 0;
+        if (in && l == 0) {  // only "is there any background" matters (the np.unique(...)[1:] quirk)
             if (acc[(long long)b * cap].area == 0) acc[(long long)b * cap].area = 1;
-            continue;
         }
-        if (l >= cap) { atomicOr(&status[b], 1); continue; }
-        if (l > maxid[b]) atomicMax(&maxid[b], l);  // bounds the id range table_finalize_kernel scans
-        Acc* a = acc + (long long)b * cap + l;
+        if (in && l >= cap) atomicOr(&status[b], 1);
+        const bool fg = in && l > 0 && l < cap;
+        const uint32_t act = __ballot_sync(0xffffffffu, fg);
+        if (!fg) continue;
         const int y = p / d.W, x = p - y * d.W;
-        atomicAdd(&a->area, 1);
-        atomicAdd(&a->sx, (unsigned long long)x);
-        atomicAdd(&a->sy, (unsigned long long)y);
-        if (y < a->rmin) atomicMin(&a->rmin, y);
-        if (y > a->rmax) atomicMax(&a->rmax, y);
-        if (x < a->cmin) atomicMin(&a->cmin, x);
-        if (x > a->cmax) atomicMax(&a->cmax, x);
+        const int t = tmap ? (int)tmap[i] : 8;
+        // (b, label) identifies the instance; lanes of one warp can straddle two tiles only if N % 32 != 0 -- keyed anyway
+        const uint32_t grp = __match_any_sync(act, (unsigned long long)b << 32 | (unsigned)l);
+        const int cnt = __popc(grp);
+        const int sx = __reduce_add_sync(grp, x), sy = __reduce_add_sync(grp, y);
+        const int xmin = __reduce_min_sync(grp, x), xmax = __reduce_max_sync(grp, x);
+        const int ymin = __reduce_min_sync(grp, y), ymax = __reduce_max_sync(grp, y);
+        Acc* a = acc + (long long)b * cap + l;
+        if (lane == __ffs(grp) - 1) {
+            if (l > maxid[b]) atomicMax(&maxid[b], l);  // bounds the id range table_finalize_kernel scans
+            atomicAdd(&a->area, cnt);
+            atomicAdd(&a->sx, (unsigned long long)sx);
+            atomicAdd(&a->sy, (unsigned long long)sy);
+            if (ymin < a->rmin) atomicMin(&a->rmin, ymin);
+            if (ymax > a->rmax) atomicMax(&a->rmax, ymax);
+            if (xmin < a->cmin) atomicMin(&a->cmin, xmin);
+            if (xmax > a->cmax) atomicMax(&a->cmax, xmax);
+        }
         if (tmap) {
-            const int t = tmap[i];
-            if (t < 8) atomicAdd(&a->hist[t], 1);
+            const uint32_t g2 = __match_any_sync(grp, t);   // lanes of this instance with the same class
+            if (t < 8 && lane == __ffs(g2) - 1) atomicAdd(&a->hist[t], __popc(g2));
         }
     }
 }
@@ -937,7 +1099,7 @@ __global__ void contour_kernel(const int* __restrict__ labels, const cvb_inst_ro
     if (row >= n) return;
     const cvb_inst_row r = table[(long long)b * max_rows + row];
     int* out_n = npts + (long long)b * max_rows + row;
-    if (r.id >= cap || ncomp[(long long)b * cap + r.id] != 1) { *out_n = -1; return; }
+    if (r.id >= cap || (ncomp != nullptr && ncomp[(long long)b * cap + r.id] != 1)) { *out_n = -1; return; }
     const int* lt = labels + (long long)b * d.N;
     short2* out = pts + ((long long)b * max_rows + row) * max_pts;
     const int id = r.id, W = d.W, H = d.H;
@@ -1014,6 +1176,27 @@ struct Ws {
     int cap;
     size_t bytes;
 };
+// LARGE layout of the flood kernel: 4096 heap entries (16 B) + 11,264 staged cells (12 B) = 200 KB, one CTA per SM
+constexpr int FL_LARGE_CAP = 4096, FL_LARGE_RCAP = 11264;
+constexpr int FL_LARGE_SMEM = (FL_LARGE_CAP + 4) * 16 + FL_LARGE_RCAP * 12;
+int g_debug_skip_flood = 0;
+
+// side stream + events for the forked flood launch of the big blobs (one set per host thread and device)
+struct Fork { cudaStream_t side; cudaEvent_t fork, join; int dev; };
+Fork* get_fork() {
+    thread_local std::vector<Fork> forks;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+    for (Fork& f : forks) if (f.dev == dev) return &f;
+    Fork f{};
+    f.dev = dev;
+    if (cudaStreamCreateWithFlags(&f.side, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&f.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&f.join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    forks.push_back(f);
+    return &forks.back();
+}
+
 Ws carve(void* base, int B, int H, int W) {
     Ws w{};
     Carve c{reinterpret_cast<uint8_t*>(base), 0};
@@ -1026,7 +1209,7 @@ Ws carve(void* base, int B, int H, int W) {
     w.Lx = c.take<int>(BN); w.cntx = c.take<int>(BN); w.flagx = c.take<int>(BN); w.rankx = c.take<int>(BN); w.marker = c.take<int>(BN);
     w.bsum = c.take<int>((size_t)B * nb + 256);
     w.qstride = (int)(BN / 8 + 64);
-    w.queue = c.take<int>((size_t)NQ_CLASSES * w.qstride);
+    w.queue = c.take<int>((size_t)(NQ_CLASSES + 1) * w.qstride);
     w.qmeta = c.take<int>(16); w.status = c.take<int>(2 * B + 32);  // status[B + 16] | maxid[B]
     w.mm = c.take<uint32_t>((size_t)B * 4 + 16); w.mm64 = c.take<unsigned long long>((size_t)B * 4 + 16);
     w.sob = c.take<double>(BN * 2); w.dist0 = c.take<double>(BN); w.dist = c.take<double>(BN);
@@ -1036,9 +1219,10 @@ Ws carve(void* base, int B, int H, int W) {
     return w;
 }
 
+int g_post_max_ctas = 0;   // 0: up to 32 CTAs per SM (debug knob, cellvit_b200_debug.h)
 int grid1d(long long n, int block = 256) {
     long long g = (n + block - 1) / block;
-    const long long cap = (long long)cvb_num_sms() * 32;
+    const long long cap = g_post_max_ctas > 0 ? g_post_max_ctas : (long long)cvb_num_sms() * 32;
     return (int)(g < 1 ? 1 : (g > cap ? cap : g));
 }
 
@@ -1080,7 +1264,7 @@ int run_pipeline(const Ws& w, const float* hv, Dims d, int n_types, int object_s
         CVB_CUDA(cudaMemsetAsync(w.mm64, 0, (size_t)d.B * 4 * 8, st));
         CVB_CUDA(cudaMemset2DAsync(w.mm64, 16, 0xFF, 8, (size_t)d.B * 2, st));
     }
-    minmax_f32_kernel<<<dim3(32, d.B * 2), 256, 0, st>>>(hv, d, w.mm);
+    minmax_f32_kernel<<<dim3(148, d.B * 2), 256, 0, st>>>(hv, d, w.mm);
     SobelTaps taps;
     sobel_taps_host(ksize, &taps);
     {
@@ -1121,11 +1305,36 @@ int run_pipeline(const Ws& w, const float* hv, Dims d, int n_types, int object_s
     blob_scatter_kernel<<<g, 256, 0, st>>>(w.L1, w.blb, w.off1, d, w.fill1, w.blobpix);
     blob_queue_kernel<<<g, 256, 0, st>>>(w.L1, w.cnt1, d, 10, FL_MAXN, w.qmeta, w.queue, w.qstride);
     {
-        // one launch, blobs largest class first; 21 KB of shared memory per single-warp CTA (see RankHeap): resident beside a
-        // tile-engine CTA, up to ten per SM when the chip is free
-        watershed_kernel<<<cvb_num_sms() * 6, 32, FL_SMEM, st>>>(w.queue, w.qstride, w.qmeta, w.cnt1, w.off1, w.blobpix, w.blb, w.marker,
-                                                                 w.dist, d, w.gkey, w.gpay, labels);
+        // Two launches of single-warp CTAs (disjoint blobs, so they run concurrently; fork / join with events keeps the sequence
+        // capturable and ordered on the caller's stream):
+        //   class 0 (more than 1023 pixels, ~5 % of the blobs, 15 % of the pixels): fp64 values and 16-byte heap entries of the
+        //             staged bounding box in 200 KB of shared memory, one CTA per SM (~0.35 us per pop; a flood through L2 costs
+        //             2 us per pop, and the largest blob of a tile IS the duration of the post-processing)
+        //   classes 1..5: rank-transformed flood, 21 KB per CTA
+        {
+            static unsigned long long configured = 0;  // one bit per device: function attributes are per device
+            const int cfg_dev = cvb_current_device();
+            if (!((configured >> cfg_dev) & 1ull)) {
+                CVB_CUDA(cudaFuncSetAttribute(watershed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FL_LARGE_SMEM));
+                configured |= 1ull << cfg_dev;
+            }
+        }
+        Fork* fk = get_fork();
+        CVB_CHECK(fk != nullptr, CVB_ECUDA, "cvb_postproc: could not create the side stream");
+        if (g_debug_skip_flood) goto after_flood;   // timing experiments only (cellvit_b200_debug.h): label maps are then incomplete
+        CVB_CUDA(cudaEventRecord(fk->fork, st));
+        CVB_CUDA(cudaStreamWaitEvent(fk->side, fk->fork, 0));
+        watershed_kernel<<<cvb_num_sms(), 32, FL_LARGE_SMEM, fk->side>>>(w.queue, w.qstride, w.qmeta, 0, 1, w.cnt1, w.off1, w.blobpix, w.blb, w.marker,
+                                                                        w.dist, d, FL_LARGE_CAP, FL_LARGE_RCAP, w.gkey, w.gpay, labels);
+        CVB_CUDA(cudaEventRecord(fk->join, fk->side));
+        watershed_kernel<<<cvb_num_sms() * 6, 32, FL_SMEM, st>>>(w.queue, w.qstride, w.qmeta, 1, NQ_CLASSES, w.cnt1, w.off1, w.blobpix, w.blb,
+                                                                 w.marker, w.dist, d, 0, 0, w.gkey, w.gpay, labels);
+        CVB_CUDA(cudaStreamWaitEvent(st, fk->join, 0));
+        // deferred blobs of the rank launch (usually none: the launch then costs a few microseconds)
+        watershed_kernel<<<cvb_num_sms(), 32, FL_LARGE_SMEM, st>>>(w.queue, w.qstride, w.qmeta, Q_DEFER, Q_DEFER + 1, w.cnt1, w.off1, w.blobpix, w.blb,
+                                                                   w.marker, w.dist, d, FL_LARGE_CAP, FL_LARGE_RCAP, w.gkey, w.gpay, labels);
     }
+after_flood:
     // ---- P8/P9
     if (table && counts) {
         CVB_CUDA(cudaMemsetAsync(w.status, 0, (size_t)(2 * d.B + 16) * 4, st));  // status[B+16] and maxid[B]
@@ -1133,7 +1342,7 @@ int run_pipeline(const Ws& w, const float* hv, Dims d, int n_types, int object_s
         table_accum_kernel<<<g, 256, 0, st>>>(labels, have_types ? w.tmap : nullptr, d, w.cap, w.acc, w.status, w.status + d.B + 16);
         table_finalize_kernel<<<d.B, 256, 0, st>>>(w.acc, w.cap, w.status + d.B + 16, have_types ? n_types : 0, max_rows, table, counts);
     }
-    cvb_note_launches(16 + ((table && counts) ? 3 : 0));
+    cvb_note_launches(18 + ((table && counts) ? 3 : 0));
     if (dbg_blb) CVB_CUDA(cudaMemcpyAsync(dbg_blb, w.blb, BN, cudaMemcpyDeviceToDevice, st));
     if (dbg_dist) CVB_CUDA(cudaMemcpyAsync(dbg_dist, w.dist, BN * 8, cudaMemcpyDeviceToDevice, st));
     if (dbg_marker) CVB_CUDA(cudaMemcpyAsync(dbg_marker, w.marker, BN * 4, cudaMemcpyDeviceToDevice, st));
@@ -1179,6 +1388,9 @@ int check_common(int B, int H, int W, int ksize, int max_rows, const void* ws, s
 }  // namespace
 
 #define CVB_API extern "C" __attribute__((visibility("default")))
+
+CVB_API void cvb_debug_postproc_skip_flood(int on) { g_debug_skip_flood = on; }
+CVB_API void cvb_debug_postproc_max_ctas(int n) { g_post_max_ctas = n; }
 
 CVB_API int cvb_postproc_workspace_bytes(int B, int H, int W, size_t* out) {
     CVB_CHECK(out && B > 0 && H > 0 && W > 0, CVB_EARG, "cvb_postproc_workspace_bytes: bad arguments");
@@ -1236,13 +1448,23 @@ CVB_API int cvb_contours_workspace_bytes(int B, int H, int W, size_t* out) {
 // must be resolved on the host (several 8-connected components, or more than max_pts points).
 CVB_API int cvb_contours(const int32_t* labels, const cvb_inst_row* table, const int32_t* counts, int B, int H, int W, int max_rows,
                          int max_pts, int16_t* pts, int32_t* npts, void* workspace, size_t ws_bytes, void* stream) {
-    CVB_CHECK(labels && table && counts && pts && npts && workspace, CVB_EARG, "cvb_contours: null argument");
+    CVB_CHECK(labels && table && counts && pts && npts, CVB_EARG, "cvb_contours: null argument");
     CVB_CHECK(H < 32768 && W < 32768 && max_rows > 0 && max_pts > 0, CVB_ESHAPE, "cvb_contours: bad shape");
+    const Dims d{B, H, W, H * W};
+    const int cap = H * W / 8 + 16;
+    if (workspace == nullptr) {
+        // the caller vouches that every id is ONE 8-connected component -- true for label maps written by cvb_postproc: a marker
+        // is a 4-connected component and the flood only ever labels 4-neighbours of labelled pixels -- so the 8-connected
+        // labelling that finds multi-component ids (a quarter of the contour stage's time) is skipped
+        contour_kernel<<<dim3((max_rows + 63) / 64, B), 64, 0, (cudaStream_t)stream>>>(labels, table, counts, nullptr, d, cap, max_rows, max_pts,
+                                                                                     reinterpret_cast<short2*>(pts), npts);
+        cvb_note_launches(1);
+        CVB_CUDA(cudaGetLastError());
+        return CVB_OK;
+    }
     size_t need = 0;
     CVB_TRY(cvb_contours_workspace_bytes(B, H, W, &need));
     CVB_CHECK(ws_bytes >= need && ((uintptr_t)workspace & 255) == 0, CVB_EWORKSPACE, "cvb_contours: workspace %zu < %zu or unaligned", ws_bytes, need);
-    const Dims d{B, H, W, H * W};
-    const int cap = H * W / 8 + 16;
     int* L = reinterpret_cast<int*>(workspace);
     int* ncomp = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(workspace) + align_up((size_t)B * d.N * 4, 256));
     cudaStream_t st = (cudaStream_t)stream;

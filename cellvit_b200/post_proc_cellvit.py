@@ -67,10 +67,14 @@ class _Workspace:
                           npts=torch.empty(B, max_rows, dtype=torch.int32).pin_memory(),
                           counts=torch.empty(B, dtype=torch.int32).pin_memory(), event=None) for _ in range(self.N_SLOTS)]
 
-    def launch_contours(self, B, H, W, max_rows, slot=0):
+    def launch_contours(self, B, H, W, max_rows, slot=0, connected=True):
+        """``connected``: the slot's label map was written by cvb_postproc, whose instances are 4-connected by construction
+        (markers are connected components, the flood labels 4-neighbours only): the 8-connected multi-component check of
+        cvb_contours is skipped (workspace = NULL)."""
         d = self.dev[slot]
         L.check(L.lib().cvb_contours(L.ptr(d["labels"]), L.ptr(d["table"]), L.ptr(d["counts"]), B, H, W, max_rows, MAX_PTS,
-                                     L.ptr(d["pts"]), L.ptr(d["npts"]), L.ptr(self.cws), C.c_size_t(self.cws.numel()), L.stream_ptr()),
+                                     L.ptr(d["pts"]), L.ptr(d["npts"]), None if connected else L.ptr(self.cws),
+                                     C.c_size_t(0 if connected else self.cws.numel()), L.stream_ptr()),
                 "cvb_contours")
 
     def copy_to_host(self, slot, n_rows, B=None):

@@ -111,7 +111,9 @@ int cvb_postproc_maps(const uint8_t* np_bin, const float* hv, const int32_t* typ
 /* Contours: replaces  cv2.findContours(inst_map, RETR_TREE, CHAIN_APPROX_SIMPLE)[0][0]  per instance
  * (post_proc_cellvit.py:106-125) for the instances in table[b, :counts[b]]. pts int16 (x,y) [B,max_rows,max_pts] in
  * tile coordinates; npts int32 [B,max_rows] = number of points, or -1 when the host must resolve the instance with
- * cv2 (more than one 8-connected component -- cv2 then lists the last one first -- or more than max_pts points). */
+ * cv2 (more than one 8-connected component -- cv2 then lists the last one first -- or more than max_pts points).
+ * workspace == NULL: the caller vouches that every id is one 8-connected component (true for the label maps cvb_postproc
+ * writes: markers are 4-connected components and the flood labels 4-neighbours only); the multi-component check is skipped. */
 int cvb_contours_workspace_bytes(int B, int H, int W, size_t* out);
 int cvb_contours(const int32_t* labels, const cvb_inst_row* table, const int32_t* counts, int B, int H, int W, int max_rows,
                  int max_pts, int16_t* pts, int32_t* npts, void* workspace, size_t ws_bytes, void* stream);
