@@ -153,12 +153,12 @@ int forward_impl(cvb_model& m, const float* x, int B, int H, int W, float* o_np,
     for (int k = 0; k < 4; ++k) z[k] = A.alloc<__half>((size_t)B * T * D);
 
     __half* ybuf = A.alloc<__half>(rows_max * D);
-    // global-attention blocks of SAM-H run on the tcgen05 attention kernel (needs V^T + bias tables scratch)
-    const bool attn_tc = sam && (m.attn_tc_mode & 1) && op_attention_tc_supported(Tx, hd, reinterpret_cast<const __half*>(1), h, w);
+    // global attention (SAM's four global blocks, every block of ViT-S) runs on the tcgen05 attention kernel
+    const bool attn_tc = (m.attn_tc_mode & 1) && op_attention_tc_supported(Tx, hd, sam ? reinterpret_cast<const __half*>(1) : nullptr, h, w);
     const bool win_tc = sam && (m.attn_tc_mode & 2) && ws > 0 && op_window_attention_tc_supported(ws * ws, hd, ws, ws);
-    const size_t attn_ws_bytes = attn_tc ? op_attention_tc_workspace_bytes(B, Tx, heads) : 0;
+    const size_t attn_ws_bytes = (attn_tc && sam) ? op_attention_tc_workspace_bytes(B, Tx, heads) : 0;   // rel-pos bias tables
     uint8_t* attn_ws = nullptr;
-    if (attn_tc) {
+    if (attn_tc && sam) {
         attn_ws = A.alloc<uint8_t>(attn_ws_bytes + 1024);
         attn_ws = reinterpret_cast<uint8_t*>(((uintptr_t)attn_ws + 1023) & ~(uintptr_t)1023);
     }

@@ -165,6 +165,29 @@ def test_attention_tc_matches_torch(Gb, heads):
     assert (out.float() - out2.float()).abs().max().item() < 8e-3  # two fp16-output kernels, each within 4e-3 of the fp32 reference
 
 
+@pytest.mark.parametrize("Gb,S,heads", [(2, 257, 6), (2, 4097, 6), (3, 1025, 2), (1, 64, 1)])
+def test_attention_tc_vit_no_bias_ragged_lengths(Gb, S, heads):
+    """tcgen05 attention for the ViT-S shape of CellViT-256 (flash_tc.cu): head dim 64, no bias, sequence lengths that are not
+    multiples of the 64-key tile (cls token: S = 4097 at 1024^2, 257 at 256^2) -- the keys past S in the last tile belong to the
+    NEXT image's rows and must get weight 0, query rows past S must not be stored (the buffer is NaN-filled past the last row)."""
+    g = torch.Generator(device="cuda").manual_seed(17)
+    hd = 64
+    D = heads * hd
+    qkv = (torch.randn(Gb * S, 3 * D, device="cuda", generator=g)).half()
+    guard = 300   # rows after the last image: must stay untouched
+    out = torch.full((Gb * S + guard, D), float("nan"), device="cuda", dtype=torch.half)
+    scale = hd ** -0.5
+    L.check(L.lib().cvb_op_attention_tc(L.ptr(qkv), Gb, S, heads, hd, C.c_float(scale), None, None, 1, S, L.ptr(out),
+                                        None, C.c_size_t(0), L.stream_ptr()), "attention_tc")
+    torch.cuda.synchronize()
+    assert torch.isnan(out[Gb * S:].float()).all(), "rows past the last query were written"
+    ref = _ref_attention(qkv, Gb, S, heads, hd, scale)
+    got = out[:Gb * S].float()
+    assert torch.isfinite(got).all()
+    err = (got - ref).abs().max().item()
+    assert err < 4e-3, err
+
+
 def test_forward_sam_h_1024_attention_tc_vs_mma_sync():
     """Full SAM-H forward on a 1024^2 tile: the tcgen05 attention kernels (default) against the mma.sync kernels."""
     from cellvit_b200.cellvit import CellViTSAM
