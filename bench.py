@@ -297,8 +297,34 @@ def run_gpu(args):
     lib.cvb_launch_count(1)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(K):
-        step_device()
+    steps_done = K
+    if args.dynamic_queue and world > 1:
+        # C4 mode: the K * world batches of the stream sit in ONE queue (a counter in the c10d store of the rendezvous); a rank
+        # takes the next batch whenever its host loop is free, so a rank that falls behind (larger blobs, lower clocks) simply
+        # processes fewer batches. Every rank enqueues at most 2 steps ahead of its GPU, as the product pipeline does.
+        store = dist.distributed_c10d._get_default_store()
+        total = K * world
+        steps_done = 0
+        inflight = []
+        while int(store.add("cvb_bench_next_batch", 1)) <= total:
+            step_device()
+            steps_done += 1
+            ev = torch.cuda.Event()
+            ev.record(main)
+            inflight.append(ev)
+            if len(inflight) > 2:
+                inflight.pop(0).synchronize()
+        # the staged-table exchange needs the same number of add() calls on every rank: pad with empty steps
+        if gather is not None:
+            n_max = torch.tensor([steps_done], device=dev)
+            dist.all_reduce(n_max, op=dist.ReduceOp.MAX)
+            with torch.cuda.stream(s_post):
+                w = proc._workspace(B, TILE, TILE, dev)
+                for _ in range(int(n_max.item()) - steps_done):
+                    gather.add(w.counts, w.table)
+    else:
+        for _ in range(K):
+            step_device()
     flush_gather()            # (chunked exchange: the tail of the stream is gathered inside the timed region)
     main.wait_stream(s_post)  # the timed region ends when the last batch's post-processing has finished
     e1.record()
@@ -309,7 +335,11 @@ def run_gpu(args):
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_total = float(ms.item())
-    value = world * B * K / (ms_total / 1000.0)
+    done = torch.tensor([steps_done], device=dev)
+    if world > 1:
+        dist.all_reduce(done)
+    total_steps = int(done.item())                    # == K * world (static shards: K per rank)
+    value = B * total_steps / (ms_total / 1000.0)
 
     # ---- what the overlap costs: the same step without post-processing, and the post-processing alone (rank-local; max over ranks)
     Ko = max(3, min(K, 10))
@@ -436,7 +466,9 @@ def run_gpu(args):
                        "l2": "per-step working set (fp16 weights + >10 GB activations) exceeds the 126 MB L2; no explicit flush",
                        "forward_launch": "CUDA graph replay (kernel nodes at high stream priority)" if args.graphs else "eager",
                        "parallelism": par},
-            "clocks": clocks, "timed_region_s": ms_total / 1000.0, "overlap": ov, "e2e": e2e,
+            "clocks": clocks, "timed_region_s": ms_total / 1000.0, "tiles_processed": B * total_steps,
+            "queue": "dynamic (one batch counter in the c10d store)" if (args.dynamic_queue and world > 1) else "static round-robin shards",
+            "overlap": ov, "e2e": e2e,
             "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu_base}))
     if world > 1:
         dist.destroy_process_group()
@@ -453,6 +485,8 @@ def main():
     ap.add_argument("--graphs", type=int, default=1, help="1 (default): the forward is replayed from a CUDA graph, as in the product pipeline; 0: eager launches")
     ap.add_argument("--gather-every", type=int, default=8, help="N>1 only: exchange the instance tables once per this many steps (TableGather, default 8); "
                     "1 = two all-gathers per step")
+    ap.add_argument("--dynamic-queue", action="store_true", help="N>1 only (BASELINE configs[3]): the steps * N batches are handed out from one queue "
+                    "instead of static round-robin shards; ms_per_step is then the job time / steps")
     ap.add_argument("--no-post", action="store_true", help="forward only: no post-processing, no e2e leg (quantifies what the post-processing costs)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling / quick iteration runs)")
     args = ap.parse_args()

@@ -472,6 +472,19 @@ __device__ __forceinline__ float gelu_erf_fast(float x) {
     return fmaf(-(z * 0.70710678118654752440f), y, fmaxf(x, 0.0f));
 }
 
+// Two softmax weights as one packed fp16 pair for a P V MMA: returns (fp16(2^(y0 + 112)), fp16(2^(y1 + 112))) for arguments that the
+// caller has ALREADY rebiased by -112 (y <= -97, i.e. weights up to 2^15). `ex2.approx.f16x2` is two MUFU ops plus a conversion
+// (F2FP) and a PRMT on this chip, and the F2FP shares the MUFU's issue queue, which made the exponential passes of the
+// attention kernels queue-bound. Here: fp32 MUFU, whose result 2^(y) has the fp16 exponent in the fp32 exponent field, so
+// (bits + 0x1000) >> 13 IS the fp16 encoding (round half up) -- integer ops on the ALU / FMA pipes instead of a third queue
+// slot. fp32 MUFU flushes below 2^-126, i.e. weights below 2^-14: callers scale their weights by 2^8 (maximum 256, sums in
+// fp32) so that the flush threshold is 2^-22 of the maximum -- fp16 denormals of unscaled weights would still have carried the
+// collective mass of a peaked row's tail (measured: 2x the error without the scaling).
+__device__ __forceinline__ uint32_t exp2_pair_f16(float y0, float y1) {
+    const uint32_t b0 = __float_as_uint(ptx::ex2(y0)), b1 = __float_as_uint(ptx::ex2(y1));
+    return ((b0 + 0x1000u) >> 13) | (((b1 + 0x1000u) << 3) & 0xFFFF0000u);
+}
+
 __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
     __half2 h = __floats2half2_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&h);

@@ -296,15 +296,16 @@ flash_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 ptx::tc_fence_before();
             }
             if (move) m_ref = cand;
-            const float mref = m_ref - bh;
-            // P = 2^(t - m) straight in fp16 pairs (they are rounded to fp16 for the MMA anyway, and the fp16 rounding of the
-            // exponent only matters for weights that are negligible). The row sum is not accumulated here: the ones operand
-            // makes it output column HD of the P V pass, from exactly these rounded weights.
+            // + the exponent rebias of exp2_pair_f16, - 6: the row's largest weight lies in [2^6, 2^14], so the fp32 flush of the
+            // MUFU (weights below 2^-14) only drops what is below 2^-20 of it
+            const float mref = m_ref - bh + (112.0f - 6.0f);
+            // P = 2^(t - m) as packed fp16 pairs (fp32 MUFU + integer packing, common.cuh). The row sum is not accumulated here: the ones operand makes it output column HD of the P V
+            // pass, from exactly these rounded weights.
             uint32_t pk[32];
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
-                pk[j] = ptx::ex2_f16x2(pack_h2(__uint_as_float(v0[2 * j]) - mref, __uint_as_float(v0[2 * j + 1]) - mref));
-                pk[16 + j] = ptx::ex2_f16x2(pack_h2(__uint_as_float(v1[2 * j]) - mref, __uint_as_float(v1[2 * j + 1]) - mref));
+                pk[j] = exp2_pair_f16(__uint_as_float(v0[2 * j]) - mref, __uint_as_float(v0[2 * j + 1]) - mref);
+                pk[16 + j] = exp2_pair_f16(__uint_as_float(v1[2 * j]) - mref, __uint_as_float(v1[2 * j + 1]) - mref);
             }
             // P row (32 packed fp16 pairs) over the first 32 columns of this S buffer: the A operand of the TS-mode P V MMA
             ptx::tmem_st32(tS(gb) + lane_off, pk);

@@ -40,17 +40,6 @@ constexpr int W_KA = 96;                   // keys of the first half (6 k-steps)
 
 __device__ __forceinline__ uint32_t sel_b32(bool c, uint32_t a, uint32_t b) { return c ? a : b; }
 
-// Two softmax weights 2^((s - m) scale log2 e) as one packed fp16 pair for the P V MMA. `ex2.approx.f16x2` is two MUFU ops plus a
-// conversion (F2FP) and a PRMT on this chip and the F2FP shares the MUFU's issue queue, which made the exponential pass
-// queue-bound. Here: fp32 MUFU of the argument rebiased by -112 (mneg carries it), so the result 2^(y - 112) has the fp16
-// exponent in the fp32 exponent field and (bits + 0x1000) >> 13 IS the fp16 encoding (round half up). The caller scales the weights by
-// 2^8 (maximum = 256, row sums stay in fp32): fp32 MUFU flushes below 2^-126, i.e. weights below 2^-22 of the maximum, where fp16
-// denormals of an unscaled weight would still have carried the collective mass of a peaked row's tail (measured: 2x the error) -- integer ops on the ALU / FMA pipes instead of a second queue slot.
-__device__ __forceinline__ uint32_t exp_pair(float s0, float s1, float sl2, float mneg) {
-    const uint32_t b0 = __float_as_uint(ptx::ex2(fmaf(s0, sl2, mneg))), b1 = __float_as_uint(ptx::ex2(fmaf(s1, sl2, mneg)));
-    return ((b0 + 0x1000u) >> 13) | (((b1 + 0x1000u) << 3) & 0xFFFF0000u);
-}
-
 // in[i] (i = 0..27, fp16 pairs in p[0..13], p[14] = 0) -> out[k] = in[s + k], k = 0..13 (7 packed registers), 0 <= s <= 13
 __device__ __forceinline__ void barrel14(const uint32_t (&p)[15], int s, uint32_t (&out)[7]) {
     uint32_t t1[11], t2[9], t3[8];
@@ -384,22 +373,22 @@ window_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                 ptx::named_bar_sync(pair_bar, 64);
                 mx = fmaxf(mx, *x_peer);
                 if (trw) W_TR(trb + 3);
-                const float mneg = fmaf(-mx, sl2, -104.0f);   // exponent rebias of exp_pair (-112) folded in, and the weights scaled by 2^8
+                const float mneg = fmaf(-mx, sl2, -104.0f);   // exponent rebias of exp2_pair_f16 (-112) folded in, and the weights scaled by 2^8
 #pragma unroll 1
                 for (int c = 0; c < 3; ++c) {
                     uint32_t v[32], pk[16];
                     ptx::tmem_ld32(tk + 32u * c, v);
                     ptx::tmem_ld_wait();
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) pk[j] = exp_pair(fl(v[2 * j]), fl(v[2 * j + 1]), sl2, mneg);
+                    for (int j = 0; j < 16; ++j) pk[j] = exp2_pair_f16(fmaf(fl(v[2 * j]), sl2, mneg), fmaf(fl(v[2 * j + 1]), sl2, mneg));
                     ptx::tmem_st16(tp + 16u * c, pk);
                 }
                 if (half == 1) {
                     uint32_t v[16], pk[16];
                     ptx::tmem_ld16(tk + 96u, v);
                     ptx::tmem_ld_wait();
-                    pk[0] = exp_pair(fl(v[0]), fl(v[1]), sl2, mneg);
-                    pk[1] = exp_pair(fl(v[2]), fl(v[3]), sl2, mneg);
+                    pk[0] = exp2_pair_f16(fmaf(fl(v[0]), sl2, mneg), fmaf(fl(v[1]), sl2, mneg));
+                    pk[1] = exp2_pair_f16(fmaf(fl(v[2]), sl2, mneg), fmaf(fl(v[3]), sl2, mneg));
 #pragma unroll
                     for (int j = 2; j < 16; ++j) pk[j] = 0u;       // keys 196..207: weight 0
                     ptx::tmem_st16(tp + 48u, pk);

@@ -45,6 +45,22 @@ def test_c_abi_exports_every_declared_symbol(lib_path):
     assert L.cvb_model_create(None, None) == -1 and b"null" in L.cvb_last_error()
 
 
+def test_every_exported_symbol_is_declared_in_a_header(lib_path):
+    """No undeclared exports: the dynamic symbol table of libcellvit_b200.so holds exactly the cvb_* functions that
+    include/cellvit_b200.h (the boundary) and include/cellvit_b200_debug.h (test / profiling hooks) declare; both compile as C99."""
+    def declared(name):
+        h = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", name)).read(), flags=re.S)
+        return set(re.findall(r"\b(cvb_[a-z0-9_]+)\s*\(", h))
+    api, dbg = declared("cellvit_b200.h"), declared("cellvit_b200_debug.h")
+    assert not (api & dbg)
+    out = subprocess.run(["nm", "-D", "--defined-only", lib_path], capture_output=True, text=True, check=True).stdout
+    exported = {l.split()[-1] for l in out.splitlines() if l.split() and l.split()[-1].startswith("cvb_")}
+    assert exported == api | dbg, (sorted(exported - api - dbg), sorted((api | dbg) - exported))
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-x", "c",
+                        os.path.join(ROOT, "include", "cellvit_b200_debug.h")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+
+
 def test_model_desc_validation_and_shape_errors(lib_path):
     from cellvit_b200.cellvit import CellViT256, ModelDesc
     L = ctypes.CDLL(lib_path)
