@@ -306,7 +306,10 @@ def run_gpu(args):
         total = K * world
         steps_done = 0
         inflight = []
+        slow = float(os.environ.get("CVB_SLOW_RANK_MS", "0")) / 1e3 if rank == world - 1 else 0.0   # test hook: a straggling rank
         while int(store.add("cvb_bench_next_batch", 1)) <= total:
+            if slow:
+                time.sleep(slow)
             step_device()
             steps_done += 1
             ev = torch.cuda.Event()
@@ -314,13 +317,16 @@ def run_gpu(args):
             inflight.append(ev)
             if len(inflight) > 2:
                 inflight.pop(0).synchronize()
-        # the staged-table exchange needs the same number of add() calls on every rank: pad with empty steps
+        # the staged-table exchange needs the same number of add() calls on every rank: pad with empty steps. The ranks agree on
+        # the maximum through the STORE, not through a collective: an NCCL call here would be ordered differently against the
+        # pending chunk all-gathers on a rank that ran more steps (collectives of one communicator must be issued in the same
+        # order everywhere -- an all-reduce at this point deadlocked the first 8-GPU run)
         if gather is not None:
-            n_max = torch.tensor([steps_done], device=dev)
-            dist.all_reduce(n_max, op=dist.ReduceOp.MAX)
+            store.set(f"cvb_bench_steps_{rank}", str(steps_done))
+            n_max = max(int(store.get(f"cvb_bench_steps_{r}")) for r in range(world))
             with torch.cuda.stream(s_post):
                 w = proc._workspace(B, TILE, TILE, dev)
-                for _ in range(int(n_max.item()) - steps_done):
+                for _ in range(n_max - steps_done):
                     gather.add(w.counts, w.table)
     else:
         for _ in range(K):

@@ -49,6 +49,9 @@ def model_from_checkpoint(checkpoint: dict) -> Union[CellViT, CellViT256, CellVi
     run_conf = unflatten_dict(checkpoint["config"], ".")
     arch = checkpoint["arch"]
     implemented = ["CellViT", "CellViT256", "CellViTSAM"]
+    if arch in ("CellViTShared", "CellViT256Shared", "CellViTSAMShared"):
+        raise NotImplementedError(f"{arch}: the shared-decoder variants of the reference's get_model (cell_detection.py:131-211) are not built "
+                                  f"in cellvit_b200; supported architectures: {implemented}")
     if arch not in implemented:
         raise NotImplementedError(f"Unknown model type. Please select one of {implemented}")
     data, mconf = run_conf["data"], run_conf.get("model", {})
