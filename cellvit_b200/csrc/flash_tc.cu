@@ -17,7 +17,8 @@
 //   warp 1   MMA issuer: S[t&1] = Q K_t^T (fp32 in TMEM), then O += P_t V_t and l += P_t 1 (row sums from the very fp16
 //            weights, via a constant ones operand) once the softmax warps have published P_t; QK of tile t+1 is issued
 //            before PV of tile t so the tensor pipe works while tile t is in the softmax.
-//   warp 2   TMEM allocator.   warps 4-11  softmax: one query row per thread (TMEM lane), exact online softmax in
+//   warp 2   TMEM allocator.   warps 4-19  softmax: TWO threads per query row (TMEM lane; each takes 32 of a tile's 64 key
+//            columns, the tile maximum is exchanged through shared memory + a 64-thread named barrier), exact online softmax in
 //            the log2 domain, P written back over the first 32 columns of its S buffer (packed fp16 pairs) and consumed by
 //            P V as a TMEM A operand (TS-mode UMMA: no shared-memory round trip, no A read per instruction). O accumulates
 //            in TMEM across all key tiles; the softmax reference m only moves when a score exceeds it by more than 2^8
@@ -38,15 +39,16 @@ constexpr float FT_L2E = 1.4426950408889634f;
 constexpr uint32_t FT_ONES_BYTES = 16 * 128;              // ones operand of the row-sum MMA: 16 rows x 64 keys, row 0 = 1
 
 // NG query groups of 128 rows per CTA share every K / V tile; each group has its own S double buffer, O accumulator
-// and four softmax warps (NG = 2: 8 softmax warps, two per scheduler).
+// and eight softmax warps (NG = 2: 16 softmax warps, four per scheduler).
 template <int NG, int HD>
 struct FtCfg {
     static constexpr int BOXES = HD > 64 ? 2 : 1;          // 64-column boxes per Q / K / V row block
-    static constexpr int THREADS = 128 + NG * 128;
+    static constexpr int THREADS = 128 + NG * 256;          // 4 control warps + 8 softmax warps per query group (two threads per row)
     static constexpr uint32_t Q_BYTES = NG * BOXES * FT_BQ * 128;
     static constexpr uint32_t K_BYTES = BOXES * FT_BK * 128;
     static constexpr uint32_t V_BYTES = BOXES * FT_BK * 128;
-    static constexpr uint32_t SMEM = 1024 + Q_BYTES + FT_STAGES * (K_BYTES + V_BYTES) + FT_ONES_BYTES + 512;
+    static constexpr uint32_t X_BYTES = NG * 2 * 128 * 4;   // tile-maximum exchange between the two threads of a row
+    static constexpr uint32_t SMEM = 1024 + Q_BYTES + FT_STAGES * (K_BYTES + V_BYTES) + FT_ONES_BYTES + X_BYTES + 512;
     static constexpr uint32_t O_STRIDE = 96;               // TMEM columns per group's O: HD output columns, then the row sum
 };
 
@@ -71,7 +73,8 @@ flash_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const uint32_t sK = sQ + Cfg::Q_BYTES;
     const uint32_t sV = sK + FT_STAGES * Cfg::K_BYTES;
     const uint32_t sOnes = sV + FT_STAGES * Cfg::V_BYTES;
-    const uint32_t bar = sOnes + FT_ONES_BYTES;
+    const uint32_t sX = sOnes + FT_ONES_BYTES;
+    const uint32_t bar = sX + Cfg::X_BYTES;
     // barriers (8 B each); per-group ones are indexed by gb = group * 2 + buffer
     const uint32_t q_full = bar;
     auto kv_full = [&](int st) { return bar + 8u * (1 + st); };
@@ -91,8 +94,8 @@ flash_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         for (int st = 0; st < FT_STAGES; ++st) { ptx::mbar_init(kv_full(st), 1); ptx::mbar_init(kv_empty(st), 1); }
         for (int gb = 0; gb < 2 * NG; ++gb) {
             ptx::mbar_init(s_full(gb), 1);
-            ptx::mbar_init(s_empty(gb), 128);
-            ptx::mbar_init(p_full(gb), 128);
+            ptx::mbar_init(s_empty(gb), 256);
+            ptx::mbar_init(p_full(gb), 256);
             ptx::mbar_init(o_full(gb), 1);
         }
         ptx::fence_barrier_init();
@@ -207,21 +210,28 @@ flash_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             issue_pv(t);
         }
     } else if (warp >= 4) {
-        // ===================================================== softmax / output: one query row per thread
-        const int grp = (warp - 4) >> 2, quad = warp & 3, r = quad * 32 + lane;
+        // ===================================================== softmax / output: TWO threads per query row (column-split)
+        // warps 4 .. 4 + 8 NG - 1: idx = warp - 4 -> half = idx / (4 NG) takes key columns 32 half .. 32 half + 31 of every tile,
+        // grp = (idx / 4) % NG, TMEM lane quadrant = warp & 3. One thread per row ran at 40 % issue utilisation (2 warps per
+        // scheduler, ~390 dependent instructions per tile); two threads per row halve the chain and double the warps.
+        const int idx = warp - 4, quad = warp & 3, grp = (idx >> 2) % NG, half = idx / (4 * NG), r = quad * 32 + lane;
         const int qrow = q0 + grp * FT_BQ + r;                         // query index inside the image
         const bool row_ok = qrow < S;
         const long long row = (long long)ghd * S + (row_ok ? qrow : S - 1);
         const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
         const float sl2 = scale * FT_L2E;
-        // rel_w[q, 0..63] (log2 domain) packed as 32 half2 registers
-        uint32_t bw[BIAS ? 32 : 1];
+        float* xch = reinterpret_cast<float*>(smem_gen + (sX - smem_base));
+        float* x_mine = xch + (grp * 2 + half) * 128 + r;
+        const float* x_peer = xch + (grp * 2 + (half ^ 1)) * 128 + r;
+        const int pair_bar = 1 + grp * 4 + quad;
+        // rel_w[q, 32 half .. 32 half + 31] (log2 domain) packed as 16 half2 registers
+        uint32_t bw[BIAS ? 16 : 1];
         const __half* bh_row = nullptr;
         unsigned short bh_raw = 0;
         if (BIAS) {
-            const uint4* p = reinterpret_cast<const uint4*>(bias_w + row * 64);
+            const uint4* p = reinterpret_cast<const uint4*>(bias_w + row * 64 + 32 * half);
 #pragma unroll
-            for (int i = 0; i < (BIAS ? 8 : 0); ++i) {
+            for (int i = 0; i < (BIAS ? 4 : 0); ++i) {
                 const uint4 v = __ldg(p + i);
                 bw[4 * i] = v.x; bw[4 * i + 1] = v.y; bw[4 * i + 2] = v.z; bw[4 * i + 3] = v.w;
             }
@@ -240,51 +250,49 @@ flash_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             }
             ptx::mbar_wait(s_full(gb), (uint32_t)((t >> 1) & 1));
             ptx::tc_fence_after();
-            uint32_t v0[32], v1[32];
-            ptx::tmem_ld32(tS(gb) + lane_off, v0);
-            ptx::tmem_ld32(tS(gb) + lane_off + 32u, v1);
+            uint32_t v0[32];
+            ptx::tmem_ld32(tS(gb) + lane_off + 32u * half, v0);
             ptx::tmem_ld_wait();
             ptx::tc_fence_before();
-            ptx::mbar_arrive(s_empty(gb));
-            // scores in the log2 domain (without the per-tile scalar bh), and their maximum
+            // scores in the log2 domain (without the per-tile scalar bh)
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
-                float a0, a1, c0, c1;
+                float a0, a1;
                 if (BIAS) {
-                    const float2 w0 = __half22float2(*reinterpret_cast<const __half2*>(&bw[j]));
-                    const float2 w1 = __half22float2(*reinterpret_cast<const __half2*>(&bw[BIAS ? 16 + j : 0]));
+                    const float2 w0 = __half22float2(*reinterpret_cast<const __half2*>(&bw[BIAS ? j : 0]));
                     a0 = fmaf(__uint_as_float(v0[2 * j]), sl2, w0.x); a1 = fmaf(__uint_as_float(v0[2 * j + 1]), sl2, w0.y);
-                    c0 = fmaf(__uint_as_float(v1[2 * j]), sl2, w1.x); c1 = fmaf(__uint_as_float(v1[2 * j + 1]), sl2, w1.y);
                 } else {
                     a0 = __uint_as_float(v0[2 * j]) * sl2; a1 = __uint_as_float(v0[2 * j + 1]) * sl2;
-                    c0 = __uint_as_float(v1[2 * j]) * sl2; c1 = __uint_as_float(v1[2 * j + 1]) * sl2;
                 }
                 v0[2 * j] = __float_as_uint(a0); v0[2 * j + 1] = __float_as_uint(a1);
-                v1[2 * j] = __float_as_uint(c0); v1[2 * j + 1] = __float_as_uint(c1);
             }
             if (t == n_t - 1 && S - t * FT_BK < FT_BK) {
                 // ragged last tile: keys past the end of the sequence are the next image's rows -> weight 0
-                const int valid = S - t * FT_BK;
+                const int valid = S - t * FT_BK - 32 * half;
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
+                for (int j = 0; j < 32; ++j)
                     if (j >= valid) v0[j] = __float_as_uint(-INFINITY);
-                    if (32 + j >= valid) v1[j] = __float_as_uint(-INFINITY);
-                }
             }
             float mx = -INFINITY;
 #pragma unroll
-            for (int j = 0; j < 32; j += 2)
-                mx = fmaxf(mx, fmaxf(fmaxf(__uint_as_float(v0[j]), __uint_as_float(v0[j + 1])), fmaxf(__uint_as_float(v1[j]), __uint_as_float(v1[j + 1]))));
+            for (int j = 0; j < 32; j += 2) mx = fmaxf(mx, fmaxf(__uint_as_float(v0[j]), __uint_as_float(v0[j + 1])));
+            // the two threads of a row agree on the tile maximum (and thereby on every decision below); the barrier also orders
+            // BOTH threads' score loads before either one's P store, which lands in the partner's score columns
+            *x_mine = mx;
+            ptx::named_bar_sync(pair_bar, 64);
+            mx = fmaxf(mx, *x_peer);
+            ptx::mbar_arrive(s_empty(gb));
             // lazy reference update: move m only when this tile exceeds it by more than 8 (a factor 256)
             const float cand = mx + bh;
             const bool move = cand > m_ref + 8.0f;  // always true on the first tile (m_ref = -inf)
             if (__any_sync(0xffffffffu, move) && t > 0) {
-                // rare: rescale the accumulated O (TMEM) and l of the rows that moved; all PV issued so far must be done
+                // rare: rescale the accumulated O (TMEM) and l of the rows that moved (each thread of the pair its half of the
+                // columns); all PV issued so far must be done
                 const float alpha = move ? ptx::ex2(m_ref - cand) : 1.0f;
                 ptx::mbar_wait(o_full(grp * 2 + ((t - 1) & 1)), (uint32_t)(((t - 1) >> 1) & 1));
                 ptx::tc_fence_after();
 #pragma unroll 1
-                for (int c0 = 0; c0 < (int)Cfg::O_STRIDE; c0 += 16) {  // HD output columns + the row-sum column
+                for (int c0 = 48 * half; c0 < 48 * half + 48; c0 += 16) {  // HD output columns + the row-sum column: 96 in all
                     uint32_t d[16];
                     ptx::tmem_ld16(tO(grp) + lane_off + (uint32_t)c0, d);
                     ptx::tmem_ld_wait();
@@ -299,21 +307,18 @@ flash_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             // + the exponent rebias of exp2_pair_f16, - 6: the row's largest weight lies in [2^6, 2^14], so the fp32 flush of the
             // MUFU (weights below 2^-14) only drops what is below 2^-20 of it
             const float mref = m_ref - bh + (112.0f - 6.0f);
-            // P = 2^(t - m) as packed fp16 pairs (fp32 MUFU + integer packing, common.cuh). The row sum is not accumulated here: the ones operand makes it output column HD of the P V
-            // pass, from exactly these rounded weights.
-            uint32_t pk[32];
+            // P = 2^(t - m) as packed fp16 pairs (fp32 MUFU + integer packing, common.cuh). The row sum is not accumulated here:
+            // the ones operand makes it output column HD of the P V pass, from exactly these rounded weights.
+            uint32_t pk[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                pk[j] = exp2_pair_f16(__uint_as_float(v0[2 * j]) - mref, __uint_as_float(v0[2 * j + 1]) - mref);
-                pk[16 + j] = exp2_pair_f16(__uint_as_float(v1[2 * j]) - mref, __uint_as_float(v1[2 * j + 1]) - mref);
-            }
-            // P row (32 packed fp16 pairs) over the first 32 columns of this S buffer: the A operand of the TS-mode P V MMA
-            ptx::tmem_st32(tS(gb) + lane_off, pk);
+            for (int j = 0; j < 16; ++j) pk[j] = exp2_pair_f16(__uint_as_float(v0[2 * j]) - mref, __uint_as_float(v0[2 * j + 1]) - mref);
+            // P row (2 x 16 packed fp16 pairs) over the first 32 columns of this S buffer: the A operand of the TS-mode P V MMA
+            ptx::tmem_st16(tS(gb) + lane_off + 16u * half, pk);
             ptx::tmem_st_wait();
             ptx::tc_fence_before();
             ptx::mbar_arrive(p_full(gb));
         }
-        {   // all key tiles accumulated: O / l
+        {   // all key tiles accumulated: O / l -- half 0 stores head-dim columns [0, HD/2 rounded to 16), half 1 the rest
             ptx::mbar_wait(o_full(grp * 2 + ((n_t - 1) & 1)), (uint32_t)(((n_t - 1) >> 1) & 1));
             ptx::tc_fence_after();
             float inv;
@@ -325,8 +330,10 @@ flash_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             }
             __half* dst = out + ((long long)g * S + (row_ok ? qrow : 0)) * D + head * HD;
             auto f = [&](uint32_t u) { return __uint_as_float(u) * inv; };
+            constexpr int SPLIT = HD == 80 ? 48 : 32;
+            const int c_begin = half == 0 ? 0 : SPLIT, c_end = half == 0 ? SPLIT : HD;
 #pragma unroll 1
-            for (int c0 = 0; c0 < HD; c0 += 16) {
+            for (int c0 = c_begin; c0 < c_end; c0 += 16) {
                 uint32_t d[16];
                 ptx::tmem_ld16(tO(grp) + lane_off + (uint32_t)c0, d);
                 ptx::tmem_ld_wait();

@@ -58,7 +58,7 @@ __device__ __forceinline__ void barrel14(const uint32_t (&p)[15], int s, uint32_
 __global__ void __launch_bounds__(W_THREADS, 1)
 window_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                  const __grid_constant__ CUtensorMap tmK16, const __grid_constant__ CUtensorMap tmR, int heads, int n_items,
-                 float scale, __half* __restrict__ out, int* __restrict__ sched_counter, long long* __restrict__ trace) {
+                 float scale, __half* __restrict__ out, int* __restrict__ sched_counter, int skew_clocks, long long* __restrict__ trace) {
     extern __shared__ uint8_t w_smem_raw[];
     const uint32_t smem_base = (ptx::smem_u32(w_smem_raw) + 1023u) & ~1023u;
     uint8_t* smem_gen = w_smem_raw + (smem_base - ptx::smem_u32(w_smem_raw));
@@ -251,6 +251,14 @@ window_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
             const uint32_t par = (uint32_t)(it & 1);
             // Gsel written -- which also means that every thread of the group has read G and the previous item's O / l
             ptx::mbar_wait(qg_ready(g), par);
+            if (g == 1 && it == 0 && skew_clocks > 0) {
+                // Put the two query groups in ANTI-PHASE, once: left alone they run in lockstep (same barriers, same item), so both
+                // are in the MUFU-bound exponential pass at the same time (3.3 k clocks instead of 1.7 k) while the tensor pipe
+                // idles, and then both wait for their MMAs. Nothing re-synchronises them afterwards: the shared gates (K / Q reload
+                // after both S MMAs, V reload after both P V) have several thousand clocks of slack.
+                const long long t0 = clock64();
+                while (clock64() - t0 < (long long)skew_clocks) {}
+            }
             ptx::tc_fence_after();
             W_TR(10 + 8 * g);
             if (ptx::elect_one()) {
@@ -438,7 +446,9 @@ window_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 }  // namespace
 
 // ------------------------------------------------------------------------------------------ host side
+static int g_window_skew = 3000;               // clocks by which query group 1 trails group 0 (window_tc_kernel); debug setter below
 static long long* g_window_trace = nullptr;   // debug: device buffer of 8 x 64 clock stamps (cellvit_b200_debug.h)
+extern "C" __attribute__((visibility("default"))) void cvb_debug_window_skew(int clocks) { g_window_skew = clocks; }
 extern "C" __attribute__((visibility("default"))) void cvb_debug_window_trace(void* dev_buf) { g_window_trace = reinterpret_cast<long long*>(dev_buf); }
 bool op_window_attention_tc_supported(int S, int hd, int gh, int gw) { return hd == W_HD && S == W_S && gh == W_G && gw == W_G; }
 
@@ -461,7 +471,7 @@ int op_window_attention_tc(const __half* qkv, int n_items, int heads, int hd, fl
     CVB_TRY(cvb_tmap_2d_f16(&tr, relcat, (uint64_t)W_HD, 64, (uint64_t)W_HD * 2, 64, 64));
     const int n_work = n_items * heads;
     const int grid = n_work < cvb_num_sms() ? n_work : cvb_num_sms();
-    window_tc_kernel<<<grid, W_THREADS, W_SMEM, stream>>>(tq, tk, tk16, tr, heads, n_items, scale, out, sched_counter, g_window_trace);
+    window_tc_kernel<<<grid, W_THREADS, W_SMEM, stream>>>(tq, tk, tk16, tr, heads, n_items, scale, out, sched_counter, g_window_skew, g_window_trace);
     cvb_note_launches(1);
     CVB_CUDA(cudaGetLastError());
     return CVB_OK;

@@ -36,6 +36,8 @@ void cvb_debug_postproc_max_ctas(int n);
 
 /* Clock-stamp timeline of window_tc_kernel (tools/trace_window.py): dev_buf = 8 x 64 int64 on the device, or NULL to stop. */
 void cvb_debug_window_trace(void* dev_buf);
+/* Clocks by which query group 1 of window_tc_kernel is delayed once, to run the two groups in anti-phase (default 3000; 0 = lockstep). */
+void cvb_debug_window_skew(int clocks);
 
 #ifdef __cplusplus
 }

@@ -23,6 +23,9 @@ relcat[32:59] = Rw
 out = torch.full((n_items * S, D), float("nan"), device="cuda", dtype=torch.half)
 scale = hd ** -0.5
 lib = L.lib()
+import os
+if os.environ.get("CVB_WSKEW") is not None:
+    lib.cvb_debug_window_skew(int(os.environ["CVB_WSKEW"]))
 ctr = torch.zeros(1, dtype=torch.int32, device="cuda")
 if len(sys.argv) > 3 and sys.argv[3] == "zero":
     relcat.zero_(); Rh.zero_(); Rw.zero_()

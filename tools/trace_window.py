@@ -12,6 +12,9 @@ qkv = torch.randn(n_items * S, 3 * D, device="cuda", generator=g).half()
 relcat = (torch.randn(64, hd, device="cuda", generator=g) * 0.2).half()
 out = torch.empty(n_items * S, D, device="cuda", dtype=torch.half)
 lib = L.lib()
+import os
+if os.environ.get("CVB_WSKEW") is not None:
+    lib.cvb_debug_window_skew(int(os.environ["CVB_WSKEW"]))
 def run():
     L.check(lib.cvb_op_window_attention_tc(L.ptr(qkv), n_items, heads, hd, C.c_float(hd ** -0.5), L.ptr(relcat), L.ptr(out), None, L.stream_ptr()), "w")
 for _ in range(3): run()
