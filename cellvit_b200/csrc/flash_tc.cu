@@ -14,7 +14,7 @@
 //            the last k-step out of a second box shifted by 16 columns, so only the K-major 128B-swizzle layout is used for
 //            Q and K. V is NOT transposed: the TMA box [64 keys][64 head-dim columns] of the qkv rows is the canonical
 //            MN-major 128B-swizzled B operand (8 keys x 64 columns per atom; head dim 80: a second box LBO bytes further on).
-//   warp 1   MMA issuer: S[t&1] = Q K_t^T (fp32 in TMEM), then O += P_t V_t and l += P_t 1 (row sums from the very fp16
+//   warps 1, 3   MMA issuers, one per query group: S[t&1] = Q K_t^T (fp32 in TMEM), then O += P_t V_t and l += P_t 1 (row sums from the very fp16
 //            weights, via a constant ones operand) once the softmax warps have published P_t; QK of tile t+1 is issued
 //            before PV of tile t so the tensor pipe works while tile t is in the softmax.
 //   warp 2   TMEM allocator.   warps 4-19  softmax: TWO threads per query row (TMEM lane; each takes 32 of a tile's 64 key
@@ -91,7 +91,7 @@ flash_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     }
     if (warp == 1 && lane == 0) {
         ptx::mbar_init(q_full, 1);
-        for (int st = 0; st < FT_STAGES; ++st) { ptx::mbar_init(kv_full(st), 1); ptx::mbar_init(kv_empty(st), 1); }
+        for (int st = 0; st < FT_STAGES; ++st) { ptx::mbar_init(kv_full(st), 1); ptx::mbar_init(kv_empty(st), NG); }   // one P V commit per group's issuer
         for (int gb = 0; gb < 2 * NG; ++gb) {
             ptx::mbar_init(s_full(gb), 1);
             ptx::mbar_init(s_empty(gb), 256);
@@ -148,8 +148,11 @@ flash_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             }
             if (++stage == FT_STAGES) { stage = 0; phase ^= 1u; }
         }
-    } else if (warp == 1) {
-        // ===================================================== MMA issuer
+    } else if (warp == 1 || (warp == 3 && NG == 2)) {
+        // ===================================================== MMA issuers: one warp per query group (warp 1: group 0, warp 3: group 1).
+        // With ONE issuer the in-order waits of the two groups' barriers (s_empty, p_full) serialised them; each group is now
+        // its own pipeline, the tensor pipe interleaves them.
+        const int grp = warp == 1 ? 0 : 1;
         // instruction descriptors: D=f32, A=B=f16; N>>3 @17, M>>4 @24; bit 16: B is MN-major (V read in place)
         const uint32_t idesc_qk = (1u << 4) | ((uint32_t)(FT_BK >> 3) << 17) | ((uint32_t)(FT_BQ >> 4) << 24);
         const uint32_t idesc_pv = (1u << 4) | (1u << 16) | ((uint32_t)(HD >> 3) << 17) | ((uint32_t)(FT_BQ >> 4) << 24);
@@ -161,48 +164,40 @@ flash_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         auto descv = [&](uint32_t addr) { return descv_hi | (uint64_t)((addr >> 4) & 0x3FFF); };
         ptx::mbar_wait(q_full, 0);
         ptx::tc_fence_after();
+        const uint32_t q = sQ + grp * Cfg::BOXES * FT_BQ * 128;
         auto issue_qk = [&](int t) {
-            const int stage = t % FT_STAGES, b = t & 1;
+            const int stage = t % FT_STAGES, gb = grp * 2 + (t & 1);
             ptx::mbar_wait(kv_full(stage), (uint32_t)((t / FT_STAGES) & 1));
+            ptx::mbar_wait(s_empty(gb), (uint32_t)(((t >> 1) & 1) ^ 1));
+            ptx::tc_fence_after();
+            if (ptx::elect_one()) {
+                const uint64_t a0 = desc(q), b0 = desc(sK + stage * Cfg::K_BYTES);
 #pragma unroll
-            for (int grp = 0; grp < NG; ++grp) {
-                const int gb = grp * 2 + b;
-                ptx::mbar_wait(s_empty(gb), (uint32_t)(((t >> 1) & 1) ^ 1));
-                ptx::tc_fence_after();
-                if (ptx::elect_one()) {
-                    const uint32_t q = sQ + grp * Cfg::BOXES * FT_BQ * 128;
-                    const uint64_t a0 = desc(q), b0 = desc(sK + stage * Cfg::K_BYTES);
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) ptx::umma_f16(tS(gb), a0 + 2u * k, b0 + 2u * k, idesc_qk, k != 0 ? 1u : 0u);
-                    if (KS == 5) {  // hd columns 64-79 = columns 48-63 of the second (shifted) box
-                        const uint64_t a1 = desc(q + FT_BQ * 128), b1 = desc(sK + stage * Cfg::K_BYTES + FT_BK * 128);
-                        ptx::umma_f16(tS(gb), a1 + 6u, b1 + 6u, idesc_qk, 1u);
-                    }
-                    ptx::umma_commit(s_full(gb));
+                for (int k = 0; k < 4; ++k) ptx::umma_f16(tS(gb), a0 + 2u * k, b0 + 2u * k, idesc_qk, k != 0 ? 1u : 0u);
+                if (KS == 5) {  // hd columns 64-79 = columns 48-63 of the second (shifted) box
+                    const uint64_t a1 = desc(q + FT_BQ * 128), b1 = desc(sK + stage * Cfg::K_BYTES + FT_BK * 128);
+                    ptx::umma_f16(tS(gb), a1 + 6u, b1 + 6u, idesc_qk, 1u);
                 }
-                __syncwarp();
+                ptx::umma_commit(s_full(gb));
             }
+            __syncwarp();
         };
         auto issue_pv = [&](int t) {
-            const int stage = t % FT_STAGES, b = t & 1;
+            const int stage = t % FT_STAGES, gb = grp * 2 + (t & 1);
+            ptx::mbar_wait(p_full(gb), (uint32_t)((t >> 1) & 1));
+            ptx::tc_fence_after();
+            if (ptx::elect_one()) {
+                const uint32_t v = sV + stage * Cfg::V_BYTES;
+                const uint64_t ones = desc(sOnes);
 #pragma unroll
-            for (int grp = 0; grp < NG; ++grp) {
-                const int gb = grp * 2 + b;
-                ptx::mbar_wait(p_full(gb), (uint32_t)((t >> 1) & 1));
-                ptx::tc_fence_after();
-                if (ptx::elect_one()) {
-                    const uint32_t v = sV + stage * Cfg::V_BYTES;
-                    const uint64_t ones = desc(sOnes);
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {  // 16 keys per k-step: 2 KB of V rows; P chunk = 8 packed TMEM columns
-                        ptx::umma_f16_ts(tO(grp), tS(gb) + 8u * k, descv(v + (uint32_t)k * 2048u), idesc_pv, (t | k) != 0 ? 1u : 0u);
-                        ptx::umma_f16_ts(tO(grp) + HD, tS(gb) + 8u * k, ones + 2u * k, idesc_l, (t | k) != 0 ? 1u : 0u);
-                    }
-                    ptx::umma_commit(o_full(gb));
-                    if (grp == NG - 1) ptx::umma_commit(kv_empty(stage));
+                for (int k = 0; k < 4; ++k) {  // 16 keys per k-step: 2 KB of V rows; P chunk = 8 packed TMEM columns
+                    ptx::umma_f16_ts(tO(grp), tS(gb) + 8u * k, descv(v + (uint32_t)k * 2048u), idesc_pv, (t | k) != 0 ? 1u : 0u);
+                    ptx::umma_f16_ts(tO(grp) + HD, tS(gb) + 8u * k, ones + 2u * k, idesc_l, (t | k) != 0 ? 1u : 0u);
                 }
-                __syncwarp();
+                ptx::umma_commit(o_full(gb));
+                ptx::umma_commit(kv_empty(stage));
             }
+            __syncwarp();
         };
         issue_qk(0);
         for (int t = 0; t < n_t; ++t) {
