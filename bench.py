@@ -173,6 +173,8 @@ def run_gpu(args):
     lib.cvb_launch_count.restype = C.c_longlong
     if os.environ.get("CVB_SKIP_FLOOD") == "1":   # timing experiment: how much of the overlap loss the flood kernels cause
         lib.cvb_debug_postproc_skip_flood(1)
+    if os.environ.get("CVB_FLOOD_LARGE_CTAS"):
+        lib.cvb_debug_flood_large_ctas(int(os.environ["CVB_FLOOD_LARGE_CTAS"]))
     if os.environ.get("CVB_POST_CTAS"):
         lib.cvb_debug_postproc_max_ctas(int(os.environ["CVB_POST_CTAS"]))
     arch = args.arch

@@ -1180,6 +1180,7 @@ struct Ws {
 constexpr int FL_LARGE_CAP = 4096, FL_LARGE_RCAP = 11264;
 constexpr int FL_LARGE_SMEM = (FL_LARGE_CAP + 4) * 16 + FL_LARGE_RCAP * 12;
 int g_debug_skip_flood = 0;
+int g_flood_large_ctas = 0;   // 0: one CTA per SM (debug knob: fewer CTAs hold fewer SMs, each for longer)
 
 // side stream + events for the forked flood launch of the big blobs (one set per host thread and device)
 struct Fork { cudaStream_t side; cudaEvent_t fork, join; int dev; };
@@ -1324,7 +1325,7 @@ int run_pipeline(const Ws& w, const float* hv, Dims d, int n_types, int object_s
         if (g_debug_skip_flood) goto after_flood;   // timing experiments only (cellvit_b200_debug.h): label maps are then incomplete
         CVB_CUDA(cudaEventRecord(fk->fork, st));
         CVB_CUDA(cudaStreamWaitEvent(fk->side, fk->fork, 0));
-        watershed_kernel<<<cvb_num_sms(), 32, FL_LARGE_SMEM, fk->side>>>(w.queue, w.qstride, w.qmeta, 0, 1, w.cnt1, w.off1, w.blobpix, w.blb, w.marker,
+        watershed_kernel<<<g_flood_large_ctas > 0 ? g_flood_large_ctas : cvb_num_sms(), 32, FL_LARGE_SMEM, fk->side>>>(w.queue, w.qstride, w.qmeta, 0, 1, w.cnt1, w.off1, w.blobpix, w.blb, w.marker,
                                                                         w.dist, d, FL_LARGE_CAP, FL_LARGE_RCAP, w.gkey, w.gpay, labels);
         CVB_CUDA(cudaEventRecord(fk->join, fk->side));
         watershed_kernel<<<cvb_num_sms() * 6, 32, FL_SMEM, st>>>(w.queue, w.qstride, w.qmeta, 1, NQ_CLASSES, w.cnt1, w.off1, w.blobpix, w.blb,
@@ -1391,6 +1392,7 @@ int check_common(int B, int H, int W, int ksize, int max_rows, const void* ws, s
 
 CVB_API void cvb_debug_postproc_skip_flood(int on) { g_debug_skip_flood = on; }
 CVB_API void cvb_debug_postproc_max_ctas(int n) { g_post_max_ctas = n; }
+CVB_API void cvb_debug_flood_large_ctas(int n) { g_flood_large_ctas = n; }
 
 CVB_API int cvb_postproc_workspace_bytes(int B, int H, int W, size_t* out) {
     CVB_CHECK(out && B > 0 && H > 0 && W > 0, CVB_EARG, "cvb_postproc_workspace_bytes: bad arguments");

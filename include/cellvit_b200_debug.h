@@ -33,6 +33,8 @@ void cvb_tc_set_l2_prefetch(int k);
  * are then incomplete), cap the grid of the map kernels. */
 void cvb_debug_postproc_skip_flood(int on);
 void cvb_debug_postproc_max_ctas(int n);
+/* Grid of the big-blob flood launch (200 KB of shared memory per CTA; 0 = one CTA per SM). */
+void cvb_debug_flood_large_ctas(int n);
 
 /* Clock-stamp timeline of window_tc_kernel (tools/trace_window.py): dev_buf = 8 x 64 int64 on the device, or NULL to stop. */
 void cvb_debug_window_trace(void* dev_buf);

@@ -72,3 +72,66 @@ def test_watershed_tie_break_is_immaterial_on_nuclei_tiles():
     want = po.watershed(dist, markers=marker, mask=mask)
     assert np.array_equal(ws.flood(dist, marker, mask, "total"), want)
     assert (ws.flood(dist, marker, mask, "reverse") != want).any()
+
+
+def test_rank_transformed_flood_equals_the_oracle_flood():
+    """The GPU flood's fast path (csrc/postproc.cu, RankHeap) replaces a blob's fp64 `dist` values by their rank among the blob's
+    pixels and orders the heap by ONE integer rank << 22 | age << 12 | cell. Restated here in Python -- per 4-connected blob of
+    the mask: bounding box + 1-pixel apron, ranks = number of strictly smaller values (ties keep equal ranks), boundary seeds
+    only, labels at push time, neighbours up / left / right / down -- it must give exactly the labels of the oracle's flood
+    with (value, age, index) ordering, including on a tile with deliberately tied values."""
+    import heapq
+    from scipy import ndimage
+    from cellvit_b200 import synth
+    from oracle import postproc_oracle as po
+
+    def rank_flood(dist, marker, mask):
+        out = marker.copy()
+        lab, n = ndimage.label(mask)   # 4-connectivity
+        for b in range(1, n + 1):
+            ys, xs = np.nonzero(lab == b)
+            y0, x0 = ys.min(), xs.min()
+            rh, rw = ys.max() - y0 + 3, xs.max() - x0 + 3
+            vals = dist[ys, xs]
+            assert len(vals) <= 1023 and rh * rw <= 4096          # the fast path's limits (FL_MAXN, FL_RC)
+            order = np.sort(vals)
+            ranks = np.searchsorted(order, vals, side="left")   # number of strictly smaller values
+            cell = (ys - y0 + 1) * rw + (xs - x0 + 1)
+            slab = np.full(rh * rw, -1, np.int64)
+            srank = np.zeros(rh * rw, np.int64)
+            slab[cell] = out[ys, xs]
+            srank[cell] = ranks
+            heap = []
+            for c in np.nonzero(slab > 0)[0]:
+                if (slab[[c - rw, c - 1, c + 1, c + rw]] == 0).any():
+                    heap.append((int(srank[c]) << 22) | int(c))
+            heapq.heapify(heap)
+            age = 0
+            while heap:
+                c = heapq.heappop(heap) & 0xFFF
+                for q in (c - rw, c - 1, c + 1, c + rw):
+                    if slab[q] == 0:
+                        age += 1
+                        slab[q] = slab[c]
+                        heapq.heappush(heap, (int(srank[q]) << 22) | (age << 12) | int(q))
+            assert age < 1024
+            out[ys, xs] = slab[cell]
+        return out
+
+    for seed, quantise in ((3, False), (4, True)):
+        t = synth.synthetic_nuclei(256, 45, seed)
+        inter = po.proc_np_hv(t["np_bin"], t["hv"], 40, want_intermediates=True)
+        labels, st = inter if isinstance(inter, tuple) else (inter, None)
+        blb, dist, marker = st["blb"], st["dist"].copy(), st["marker"]
+        if quantise:
+            dist = np.round(dist * 8) / 8          # many exact ties: age and index decide
+        want = po.watershed(dist, marker, blb)
+        small = np.zeros_like(blb)
+        lab, n = ndimage.label(blb)
+        for b in range(1, n + 1):                   # keep the blobs the fast path takes (the others use the fp64 layout)
+            ys, xs = np.nonzero(lab == b)
+            if len(ys) <= 1023 and (ys.max() - ys.min() + 3) * (xs.max() - xs.min() + 3) <= 4096:
+                small[ys, xs] = 1
+        assert small.sum() > 0.5 * blb.sum()
+        got = rank_flood(dist, marker * small, small)
+        assert np.array_equal(got[small > 0], want[small > 0])
