@@ -205,6 +205,10 @@ def run_gpu(args):
     np_dev = torch.from_numpy(np.stack([l[0] for l in logits])).to(dev)
     nt_dev = torch.from_numpy(np.stack([l[1] for l in logits])).to(dev)
     hv_dev = torch.from_numpy(np.stack([n["hv"] for n in nuc])).to(dev)
+    # what the fused head epilogue hands to the post-processing in the product pipeline: uint8 arg-max planes (K12 fusion); here
+    # derived once from the injected logits, the forward below still writes its own planes every step
+    np_arg_dev = (np_dev[:, 1] > np_dev[:, 0]).to(torch.uint8).contiguous()
+    nt_arg_dev = nt_dev.argmax(1).to(torch.uint8).contiguous()
 
     # post-processing on a default (= lowest) priority stream; the forward graph's kernels carry high priority (cellvit.py)
     s_post = torch.cuda.Stream(dev)
@@ -223,14 +227,14 @@ def run_gpu(args):
     def forward_once():
         with torch.no_grad():
             if args.graphs:
-                model.forward_graphed(x_dev, retrieve_tokens=True, slot=0)
+                model.forward_graphed(x_dev, retrieve_tokens=True, slot=0, argmax_maps=True)
             else:
-                model(x_dev, retrieve_tokens=True)
+                model(x_dev, retrieve_tokens=True, argmax_maps=True)
 
     def post_once(exchange=True):
         w = proc._workspace(B, TILE, TILE, dev)
-        L.check(lib.cvb_postproc(L.ptr(np_dev), L.ptr(hv_dev), L.ptr(nt_dev), B, TILE, TILE, 6, 40, L.ptr(w.labels), L.ptr(w.table),
-                                 L.ptr(w.counts), proc.max_rows, L.ptr(w.ws), C.c_size_t(w.ws.numel()), L.stream_ptr()), "cvb_postproc")
+        L.check(lib.cvb_postproc_argmax(L.ptr(np_arg_dev), L.ptr(hv_dev), L.ptr(nt_arg_dev), B, TILE, TILE, 6, 40, L.ptr(w.labels), L.ptr(w.table),
+                                        L.ptr(w.counts), proc.max_rows, L.ptr(w.ws), C.c_size_t(w.ws.numel()), L.stream_ptr()), "cvb_postproc_argmax")
         w.launch_contours(B, TILE, TILE, proc.max_rows)   # per-instance contours on the device (cvb_contours)
         if not exchange:
             return
@@ -258,7 +262,7 @@ def run_gpu(args):
 
     from cellvit_b200.cell_detection import CellSegmentationInference
     inf = CellSegmentationInference.from_model(model, local)
-    override = {"nuclei_binary_map": np_dev, "hv_map": hv_dev, "nuclei_type_map": nt_dev}  # injected synthetic nuclei
+    override = {"nuclei_binary_argmax": np_arg_dev, "hv_map": hv_dev, "nuclei_type_argmax": nt_arg_dev}  # injected synthetic nuclei
 
     def run_e2e(n_batches):
         # public API: pinned-host tiles in, per-tile instance dicts out (H2D, forward, device post-processing,

@@ -29,7 +29,7 @@ class TcEpilogue(C.Structure):
         ("win_size", C.c_int), ("win_grid", C.c_int), ("tok_h", C.c_int), ("tok_w", C.c_int),
         ("ct_cout", C.c_int), ("ct_hin", C.c_int), ("ct_win", C.c_int),
         ("head_w", C.c_void_p), ("head_b", C.c_void_p), ("head_nc", C.c_int), ("head_hw", C.c_int),
-        ("head_out", C.c_void_p), ("sched_counter", C.c_void_p),
+        ("head_out", C.c_void_p), ("head_argmax", C.c_void_p), ("head_argmax_nc", C.c_int), ("sched_counter", C.c_void_p),
     ]
 
 

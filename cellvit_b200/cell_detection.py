@@ -206,7 +206,7 @@ class CellSegmentationInference:
                 slot = k & 1
                 gs = None
                 if use_graphs:
-                    gs = self.model.graph_slot(tuple(patches.shape), True, slot, dev)
+                    gs = self.model.graph_slot(tuple(patches.shape), True, slot, dev, argmax_maps=True)
                     buf = gs[1]
                     if consumed[slot] is None:
                         consumed[slot] = torch.cuda.Event()
@@ -259,7 +259,7 @@ class CellSegmentationInference:
                     gs[0].replay()
                     predictions = dict(gs[2])
                 else:
-                    predictions = self.model.forward(x, retrieve_tokens=True)
+                    predictions = self.model.forward(x, retrieve_tokens=True, argmax_maps=True)
                 ov = head_override(payload) if callable(head_override) else head_override
                 if ov:  # (before the event: an override may enqueue device work of its own on this stream)
                     predictions.update(ov)
@@ -276,8 +276,15 @@ class CellSegmentationInference:
                     # The reference soft-maxes NP / NT first (:500-505) and then only takes their arg-max (cellvit.py:369-375);
                     # softmax is monotonic, so the arg-max of the logits is the same map -- 270 MB of traffic per batch saved.
                     # (Callers that want the probabilities use get_cell_predictions_with_tokens, which keeps the softmax.)
-                    proc.launch_float(predictions["nuclei_binary_map"], predictions["hv_map"], predictions["nuclei_type_map"], slot=slot,
-                                      tokens=predictions["tokens"] if with_tokens else None, patch_size=self.model.patch_size)
+                    # K12 fusion: the head epilogue already wrote the uint8 arg-max planes -> no pass over the 8 logit channels.
+                    # An override of the float maps (test / bench hook) that brings no planes of its own takes the float entry.
+                    tok = predictions["tokens"] if with_tokens else None
+                    if ov and ("nuclei_binary_map" in ov or "nuclei_type_map" in ov) and "nuclei_binary_argmax" not in ov:
+                        proc.launch_float(predictions["nuclei_binary_map"], predictions["hv_map"], predictions["nuclei_type_map"], slot=slot,
+                                          tokens=tok, patch_size=self.model.patch_size)
+                    else:
+                        proc.launch_argmax(predictions["nuclei_binary_argmax"], predictions["hv_map"], predictions["nuclei_type_argmax"],
+                                           slot=slot, tokens=tok, patch_size=self.model.patch_size)
                 keep[slot] = (payload, predictions)  # alive until the D2H event of this batch has completed
                 if pending is not None:
                     yield finish(pending)

@@ -160,8 +160,10 @@ class CellViT(nn.Module):
             pass
 
     # ------------------------------------------------------------------ reference API
-    def forward(self, x: torch.Tensor, retrieve_tokens: bool = False) -> dict:
-        """cellvit.py:153-210 / :586-644. Raw logits, fp32, on x.device."""
+    def forward(self, x: torch.Tensor, retrieve_tokens: bool = False, argmax_maps: bool = False) -> dict:
+        """cellvit.py:153-210 / :586-644. Raw logits, fp32, on x.device. ``argmax_maps`` (not in the reference): also return
+        ``nuclei_binary_argmax`` / ``nuclei_type_argmax`` uint8 [B,H,W], the arg-max planes the post-processing consumes,
+        written by the fused head epilogue (``cvb_forward_argmax``)."""
         assert x.shape[-2] % self.patch_size == 0, "Input images must be divisible by the patch size"
         assert x.shape[-1] % self.patch_size == 0, "Input images must be divisible by the patch size"
         if not x.is_cuda:
@@ -184,9 +186,18 @@ class CellViT(nn.Module):
             o_nt = torch.empty(B, self.num_nuclei_classes, H, W, device=x.device)
             o_ti = torch.empty(B, self.num_tissue_classes, device=x.device)
             o_tok = torch.empty(B, self.embed_dim, h, w, device=x.device) if retrieve_tokens else None
-            L.check(lib.cvb_forward(self._handle, L.ptr(x), B, H, W, L.ptr(o_np), L.ptr(o_hv), L.ptr(o_nt), L.ptr(o_ti),
-                                    L.ptr(o_tok), L.ptr(self._ws), C.c_size_t(self._ws.numel()), L.stream_ptr()), "cvb_forward")
+            if argmax_maps:
+                a_np = torch.empty(B, H, W, dtype=torch.uint8, device=x.device)
+                a_nt = torch.empty(B, H, W, dtype=torch.uint8, device=x.device)
+                L.check(lib.cvb_forward_argmax(self._handle, L.ptr(x), B, H, W, L.ptr(o_np), L.ptr(o_hv), L.ptr(o_nt), L.ptr(o_ti),
+                                               L.ptr(o_tok), L.ptr(a_np), L.ptr(a_nt), L.ptr(self._ws), C.c_size_t(self._ws.numel()),
+                                               L.stream_ptr()), "cvb_forward_argmax")
+            else:
+                L.check(lib.cvb_forward(self._handle, L.ptr(x), B, H, W, L.ptr(o_np), L.ptr(o_hv), L.ptr(o_nt), L.ptr(o_ti),
+                                        L.ptr(o_tok), L.ptr(self._ws), C.c_size_t(self._ws.numel()), L.stream_ptr()), "cvb_forward")
         out = {"tissue_types": o_ti}
+        if argmax_maps:
+            out["nuclei_binary_argmax"], out["nuclei_type_argmax"] = a_np, a_nt
         if self.regression_loss:
             out["nuclei_binary_map"], out["regression_map"] = o_np[:, :2], o_np[:, 2:]
         else:
@@ -197,7 +208,7 @@ class CellViT(nn.Module):
             out["tokens"] = o_tok
         return out
 
-    def forward_graphed(self, x: torch.Tensor, retrieve_tokens: bool = True, slot: int = 0) -> dict:
+    def forward_graphed(self, x: torch.Tensor, retrieve_tokens: bool = True, slot: int = 0, argmax_maps: bool = False) -> dict:
         """``forward`` replayed from a CUDA graph (one per input shape and ``slot``): the ~290 launches of a SAM-H forward
         become one graph launch, which removes the 2 us of idle time at every kernel boundary. The returned tensors are
         STATIC: the next call with the same ``slot`` overwrites them (the tile pipeline alternates two slots and has
@@ -208,23 +219,23 @@ class CellViT(nn.Module):
         dev = x.device if x.is_cuda else next(self.parameters()).device
         if dev.type != "cuda":
             raise RuntimeError("cellvit_b200 has no CPU path: move the model to a CUDA device")
-        graph, static_x, out = self.graph_slot(tuple(x.shape), retrieve_tokens, slot, dev)
+        graph, static_x, out = self.graph_slot(tuple(x.shape), retrieve_tokens, slot, dev, argmax_maps)
         static_x.copy_(x, non_blocking=True)
         graph.replay()
         return out
 
-    def graph_slot(self, shape, retrieve_tokens: bool, slot: int, dev):
+    def graph_slot(self, shape, retrieve_tokens: bool, slot: int, dev, argmax_maps: bool = False):
         """(CUDA graph, static input tensor, static output dict) of ``forward`` for one input shape and pipeline slot;
         captured on first use. Repacking the weights (new checkpoint, other tile size) drops all captured graphs."""
         B, _, H, W = shape
         with torch.cuda.device(dev):
             self._ensure_packed(dev, H // 16, W // 16)
-            key = (tuple(shape), bool(retrieve_tokens), int(slot), str(dev))
+            key = (tuple(shape), bool(retrieve_tokens), int(slot), str(dev), bool(argmax_maps))
             g = self._graphs.get(key)
             if g is None:
                 static_x = torch.zeros(tuple(shape), dtype=torch.float32, device=dev)
                 with torch.no_grad():
-                    self.forward(static_x, retrieve_tokens)  # eager warm-up: sizes the workspace, sets kernel attributes
+                    self.forward(static_x, retrieve_tokens, argmax_maps)  # eager warm-up: sizes the workspace, sets kernel attributes
                     torch.cuda.synchronize(dev)
                     graph = torch.cuda.CUDAGraph()
                     # Captured on a HIGH-priority stream: kernel nodes keep the priority of the stream they were captured on,
@@ -233,7 +244,7 @@ class CellViT(nn.Module):
                     if self._capture_stream is None or self._capture_stream.device != dev:
                         self._capture_stream = torch.cuda.Stream(dev, priority=-1)
                     with torch.cuda.graph(graph, stream=self._capture_stream):
-                        out = self.forward(static_x, retrieve_tokens)
+                        out = self.forward(static_x, retrieve_tokens, argmax_maps)
                 g = self._graphs[key] = (graph, static_x, out)
         return g
 

@@ -110,7 +110,7 @@ struct Fwd {
 int pad64(int c) { return (c + 63) / 64 * 64; }
 
 int forward_impl(cvb_model& m, const float* x, int B, int H, int W, float* o_np, float* o_hv, float* o_nt, float* o_tissue,
-                 float* o_tokens, Arena& A, cudaStream_t st) {
+                 float* o_tokens, uint8_t* o_np_arg, uint8_t* o_nt_arg, Arena& A, cudaStream_t st) {
     const cvb_model_desc& d = m.d;
     Fwd f{m, A, st};
     const int h = H / 16, w = W / 16, T = h * w, D = d.embed_dim, heads = d.num_heads, hd = D / heads;
@@ -264,8 +264,10 @@ int forward_impl(cvb_model& m, const float* x, int B, int H, int W, float* o_np,
     __half* s3 = f.deconv_block(z[2], D, B, h, w, "decoder3.0", bt);
 
     // ------------------------------------------------------------------ three upsampling branches (cellvit.py:212-244)
-    struct Br { const char* name; float* out; int nc; };
-    const Br branches[3] = {{"np", o_np, d.n_np_out}, {"hv", o_hv, 2}, {"nt", o_nt, d.n_nt}};
+    // arg: optional u8 arg-max plane of the branch (K12 fusion), over the first arg_nc classes (NP: the binary map's two, also when
+    // the regression channels are present)
+    struct Br { const char* name; float* out; int nc; uint8_t* arg; int arg_nc; };
+    const Br branches[3] = {{"np", o_np, d.n_np_out, o_np_arg, 2}, {"hv", o_hv, 2, nullptr, 0}, {"nt", o_nt, d.n_nt, o_nt_arg, d.n_nt}};
     const size_t mark = A.off;
     for (const Br& br : branches) {
         A.off = mark;  // branch activations reuse the same arena region (stream order serialises the branches)
@@ -286,7 +288,7 @@ int forward_impl(cvb_model& m, const float* x, int B, int H, int W, float* o_np,
         e.kind = TC_EPI_HEAD;
         e.scale = f.P<float>(n + ".d0.1.scale"); e.shift = f.P<float>(n + ".d0.1.shift");
         e.head_w = f.P<float>(n + ".head.w"); e.head_b = f.P<float>(n + ".head.b");
-        e.head_nc = br.nc; e.head_hw = H * W; e.head_out = br.out;
+        e.head_nc = br.nc; e.head_hw = H * W; e.head_out = br.out; e.head_argmax = br.arg; e.head_argmax_nc = br.arg_nc;
         const __half* wp = f.P<__half>(n + ".d0.1.w");
         if (f.live() && br.out) f.chk(tc_conv3x3(b, 64, nullptr, 0, B, H, W, wp, 64, 64, f.with_counter(e), st));
     }
@@ -336,15 +338,15 @@ CVB_API int cvb_model_workspace_bytes(cvb_model* m, int B, int H, int W, size_t*
     Arena A{nullptr, 0, 0, true};
     size_t peak = 0;
     // the branch loop rewinds the arena; track the peak by running the dry pass and taking the max offset
-    forward_impl(*m, nullptr, B, H, W, nullptr, nullptr, nullptr, nullptr, nullptr, A, nullptr);
+    forward_impl(*m, nullptr, B, H, W, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, A, nullptr);
     peak = A.off;
     // branch region is re-used three times; all three are the same size except the head, so A.off is the peak
     *out = peak + 4096;
     return CVB_OK;
 }
 
-CVB_API int cvb_forward(cvb_model* m, const float* x, int B, int H, int W, float* np_logits, float* hv, float* nt_logits,
-                        float* tissue, float* tokens, void* workspace, size_t ws_bytes, void* stream) {
+static int forward_checked(cvb_model* m, const float* x, int B, int H, int W, float* np_logits, float* hv, float* nt_logits,
+                           float* tissue, float* tokens, uint8_t* np_argmax, uint8_t* nt_argmax, void* workspace, size_t ws_bytes, void* stream) {
     CVB_TRY(check_shape(m, B, H, W));
     CVB_CHECK(x && workspace, CVB_EARG, "cvb_forward: null input or workspace");
     size_t need = 0;
@@ -352,7 +354,19 @@ CVB_API int cvb_forward(cvb_model* m, const float* x, int B, int H, int W, float
     CVB_CHECK(ws_bytes >= need, CVB_EWORKSPACE, "cvb_forward: workspace %zu < required %zu bytes", ws_bytes, need);
     CVB_CHECK(((uintptr_t)workspace & 255) == 0, CVB_EARG, "cvb_forward: workspace must be 256-byte aligned");
     Arena A{reinterpret_cast<uint8_t*>(workspace), 0, ws_bytes, false};
-    return forward_impl(*m, x, B, H, W, np_logits, hv, nt_logits, tissue, tokens, A, (cudaStream_t)stream);
+    return forward_impl(*m, x, B, H, W, np_logits, hv, nt_logits, tissue, tokens, np_argmax, nt_argmax, A, (cudaStream_t)stream);
+}
+
+CVB_API int cvb_forward(cvb_model* m, const float* x, int B, int H, int W, float* np_logits, float* hv, float* nt_logits,
+                        float* tissue, float* tokens, void* workspace, size_t ws_bytes, void* stream) {
+    return forward_checked(m, x, B, H, W, np_logits, hv, nt_logits, tissue, tokens, nullptr, nullptr, workspace, ws_bytes, stream);
+}
+
+CVB_API int cvb_forward_argmax(cvb_model* m, const float* x, int B, int H, int W, float* np_logits, float* hv, float* nt_logits,
+                               float* tissue, float* tokens, uint8_t* np_argmax, uint8_t* nt_argmax, void* workspace, size_t ws_bytes,
+                               void* stream) {
+    CVB_CHECK(np_logits && nt_logits, CVB_EARG, "cvb_forward_argmax: the arg-max planes come out of the NP / NT heads, which need their logit outputs");
+    return forward_checked(m, x, B, H, W, np_logits, hv, nt_logits, tissue, tokens, np_argmax, nt_argmax, workspace, ws_bytes, stream);
 }
 
 CVB_API void cvb_model_destroy(cvb_model* m) { delete m; }

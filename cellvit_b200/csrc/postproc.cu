@@ -1421,6 +1421,27 @@ CVB_API int cvb_postproc(const float* np_map, const float* hv, const float* nt_m
                         nullptr, st);
 }
 
+CVB_API int cvb_postproc_argmax(const uint8_t* np_argmax, const float* hv, const uint8_t* nt_argmax, int B, int H, int W, int n_types,
+                                int magnification, int32_t* labels, cvb_inst_row* table, int32_t* counts, int max_rows, void* workspace,
+                                size_t ws_bytes, void* stream) {
+    CVB_CHECK(np_argmax && hv && labels, CVB_EARG, "cvb_postproc_argmax: null map");
+    int object_size, ksize;
+    if (magnification == 40) { object_size = 10; ksize = 21; }
+    else if (magnification == 20) { object_size = 3; ksize = 11; }
+    else { cvb_set_error("Unknown magnification"); return CVB_EARG; }
+    CVB_CHECK(nt_argmax == nullptr || (n_types >= 1 && n_types <= 8), CVB_ESHAPE, "cvb_postproc_argmax: n_types must be in 1..8");
+    size_t need = 0;
+    CVB_TRY(cvb_postproc_workspace_bytes(B, H, W, &need));
+    CVB_TRY(check_common(B, H, W, ksize, max_rows, workspace, ws_bytes, need));
+    Ws w = carve(workspace, B, H, W);
+    // the caller's planes are used in place (read-only): no preparation pass, 1 B/px instead of 4 * (2 + n_types) B/px
+    w.npbin = const_cast<uint8_t*>(np_argmax);
+    if (nt_argmax) w.tmap = const_cast<uint8_t*>(nt_argmax);
+    const Dims d{B, H, W, H * W};
+    return run_pipeline(w, hv, d, n_types, object_size, ksize, nt_argmax != nullptr, labels, table, counts, max_rows, nullptr, nullptr,
+                        nullptr, (cudaStream_t)stream);
+}
+
 CVB_API int cvb_postproc_maps(const uint8_t* np_bin, const float* hv, const int32_t* type_map, int B, int H, int W, int n_types,
                               int object_size, int ksize, int32_t* labels, cvb_inst_row* table, int32_t* counts, int max_rows,
                               uint8_t* dbg_blb, double* dbg_dist, int32_t* dbg_marker, void* workspace, size_t ws_bytes,

@@ -206,8 +206,20 @@ __device__ __forceinline__ void epilogue_tile(const TcEpilogue& e, uint32_t t_ad
         if (half == 0 && row_ok) {
             const int img = m / e.head_hw, pix = m - img * e.head_hw;
 #pragma unroll
-            for (int k = 0; k < 8; ++k)
-                if (k < nc) e.head_out[((size_t)img * nc + k) * e.head_hw + pix] = hs[k] + part[k * 128 + prow] + hb[k];
+            for (int k = 0; k < 8; ++k) {
+                hs[k] = hs[k] + part[k * 128 + prow] + hb[k];
+                if (k < nc) e.head_out[((size_t)img * nc + k) * e.head_hw + pix] = hs[k];
+            }
+            if (e.head_argmax != nullptr) {
+                // the arg-max plane the post-processing consumes (cellvit.py:369-375: torch.argmax of the soft-maxed map = arg-max
+                // of the logits, first maximum wins), written here so that cvb_postproc_argmax reads 1 B/px instead of 4 nc B/px
+                int best = 0;
+                float bv = hs[0];
+#pragma unroll
+                for (int k = 1; k < 8; ++k)
+                    if (k < e.head_argmax_nc && hs[k] > bv) { bv = hs[k]; best = k; }
+                e.head_argmax[(size_t)img * e.head_hw + pix] = (uint8_t)best;
+            }
         }
         ptx::named_bar_sync(bar_id, 64);  // part[] may be overwritten by the next tile only after it was read
         return;

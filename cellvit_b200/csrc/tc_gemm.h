@@ -36,6 +36,8 @@ struct TcEpilogue {
     int head_nc;
     int head_hw;                           // HEAD: H*W of one image
     float* head_out;                       // HEAD: [NB, nc, H, W]
+    uint8_t* head_argmax;                  // HEAD, optional: [NB, H, W] arg-max over the first head_argmax_nc classes (first maximum wins)
+    int head_argmax_nc;
     int* sched_counter;                    // optional: device int, ZERO at launch -> tiles are claimed dynamically (SchedRing, common.cuh)
 };
 

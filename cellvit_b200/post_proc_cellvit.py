@@ -219,6 +219,30 @@ class DetectionCellPostProcessor:
                                                 self.max_rows, L.ptr(d["cell_tokens"]), L.stream_ptr()), "cvb_cell_tokens")
             w.copy_to_host(slot, min(table_rows, self.max_rows), B)
 
+    def launch_argmax(self, np_argmax: torch.Tensor, hv: torch.Tensor, nt_argmax: torch.Tensor, slot: int, table_rows: int = ROWS_COPIED,
+                      tokens: torch.Tensor = None, patch_size: int = 16):
+        """``launch_float`` for the arg-max planes of ``CellViT.forward(..., argmax_maps=True)`` (uint8 [B,H,W], CUDA): the
+        planes are consumed in place by ``cvb_postproc_argmax`` -- no preparation pass over the 8 logit channels."""
+        B, H, W = np_argmax.shape
+        assert np_argmax.dtype == torch.uint8 and np_argmax.is_contiguous() and hv.is_contiguous()
+        with torch.cuda.device(np_argmax.device):
+            w = self._workspace(B, H, W, np_argmax.device)
+            d = w.dev[slot]
+            nt = nt_argmax if self.nr_types is not None else None
+            assert nt is None or (nt.dtype == torch.uint8 and nt.is_contiguous())
+            L.check(L.lib().cvb_postproc_argmax(L.ptr(np_argmax), L.ptr(hv), L.ptr(nt), B, H, W, 0 if nt is None else int(self.nr_types),
+                                                int(self.magnification), L.ptr(d["labels"]), L.ptr(d["table"]), L.ptr(d["counts"]),
+                                                self.max_rows, L.ptr(w.ws), C.c_size_t(w.ws.numel()), L.stream_ptr()), "cvb_postproc_argmax")
+            w.launch_contours(B, H, W, self.max_rows, slot)
+            if tokens is not None:
+                tokens = tokens.contiguous().float()
+                D, th, tw = tokens.shape[1:]
+                if d.get("cell_tokens") is None or d["cell_tokens"].shape[-1] != D:
+                    d["cell_tokens"] = torch.empty(B, self.max_rows, D, dtype=torch.float32, device=np_argmax.device)
+                L.check(L.lib().cvb_cell_tokens(L.ptr(tokens), L.ptr(d["table"]), L.ptr(d["counts"]), B, D, th, tw, int(patch_size),
+                                                self.max_rows, L.ptr(d["cell_tokens"]), L.stream_ptr()), "cvb_cell_tokens")
+            w.copy_to_host(slot, min(table_rows, self.max_rows), B)
+
     def collect(self, slot: int, pool=None, with_tokens: bool = False, raw: bool = False):
         """Wait for host slot ``slot`` and assemble the per-tile instance dicts (reference layout). Returns
         (label maps, dicts) -- or (label maps, dicts, cell tokens per tile) when ``with_tokens``. ``raw``: instead of dicts,

@@ -73,6 +73,13 @@ int cvb_model_workspace_bytes(cvb_model* m, int B, int H, int W, size_t* out);
  * tokens [B,embed_dim,H/16,W/16] (nullable; the z4 skip, retrieve_tokens=True). H == W in {256, 512, 1024}. */
 int cvb_forward(cvb_model* m, const float* x, int B, int H, int W, float* np_logits, float* hv, float* nt_logits,
                 float* tissue, float* tokens, void* workspace, size_t ws_bytes, void* stream);
+/* The same forward that ALSO writes the arg-max planes the post-processing consumes (K12 fusion): np_argmax /
+ * nt_argmax uint8 [B,H,W] (nullable) = torch.argmax over the two binary-map channels / the n_nt type channels, first maximum
+ * wins (cellvit.py:369-375 takes the arg-max of the soft-maxed maps: same plane). Written by the fused head epilogue at no
+ * extra pass; feed them to cvb_postproc_argmax. */
+int cvb_forward_argmax(cvb_model* m, const float* x, int B, int H, int W, float* np_logits, float* hv, float* nt_logits,
+                       float* tissue, float* tokens, uint8_t* np_argmax, uint8_t* nt_argmax, void* workspace, size_t ws_bytes,
+                       void* stream);
 
 /* ------------------------------------------------------------------------------------------------ post-processing
  * Replaces  DetectionCellPostProcessor.post_process_cell_segmentation  (cell_segmentation/utils/post_proc_cellvit.py:67-249)
@@ -98,6 +105,12 @@ int cvb_postproc_workspace_bytes(int B, int H, int W, size_t* out);
 int cvb_postproc(const float* np_map, const float* hv, const float* nt_map, int B, int H, int W, int n_types,
                  int magnification, int32_t* labels, cvb_inst_row* table, int32_t* counts, int max_rows,
                  void* workspace, size_t ws_bytes, void* stream);
+
+/* cvb_postproc on arg-max planes (uint8 [B,H,W], e.g. from cvb_forward_argmax): np_argmax != 0 = nucleus, nt_argmax = class
+ * (nullable). The planes are read in place, no preparation pass: 14 B/px of compulsory input instead of 44 B/px. */
+int cvb_postproc_argmax(const uint8_t* np_argmax, const float* hv, const uint8_t* nt_argmax, int B, int H, int W, int n_types,
+                        int magnification, int32_t* labels, cvb_inst_row* table, int32_t* counts, int max_rows, void* workspace,
+                        size_t ws_bytes, void* stream);
 
 /* Same, from already arg-maxed maps: np_bin uint8 [B,H,W] (0/1), type_map int32 [B,H,W] (nullable). Optional
  * debug outputs (nullable) expose the stage results the parity tests compare with the oracle:

@@ -128,10 +128,22 @@ def test_postprocessing_of_the_models_own_head_maps_matches_oracle(seed):
     np_bin = out["nuclei_binary_map"].argmax(1).cpu().numpy().astype(np.uint8)
     nt = out["nuclei_type_map"].argmax(1).cpu().numpy()
     hv = out["hv_map"].cpu().numpy()
+    # the product pipeline (K12 fusion): arg-max planes written by the head epilogue, consumed in place by cvb_postproc_argmax
+    with torch.no_grad():
+        out2 = m(x.cuda(), retrieve_tokens=True, argmax_maps=True)
+    assert torch.equal(out2["nuclei_binary_argmax"], out2["nuclei_binary_map"].argmax(1).to(torch.uint8))
+    assert torch.equal(out2["nuclei_type_argmax"], out2["nuclei_type_map"].argmax(1).to(torch.uint8))
+    assert torch.equal(out2["nuclei_binary_map"], out["nuclei_binary_map"]) and torch.equal(out2["hv_map"], out["hv_map"])
+    from cellvit_b200.cell_detection import CellSegmentationInference
+    inf = CellSegmentationInference.from_model(m, 0)
+    piped = [d for _, d, _ in inf._pipeline([(x.pin_memory(), None)], 40, use_graphs=True)]
     for b in range(B):
         pm = np.concatenate([nt[b][..., None], np_bin[b][..., None], hv[b].transpose(1, 2, 0)], -1).astype(np.float64)
         olab, odict = po.DetectionCellPostProcessor(6, 40).post_process_cell_segmentation(pm)
         print("seed", seed, "foreground", float(np_bin[b].mean()), "instances", len(odict))
+        assert sorted(piped[0][b]) == sorted(odict)
+        for k, ov in odict.items():
+            assert np.array_equal(piped[0][b][k]["contour"], ov["contour"]) and piped[0][b][k]["type"] == ov["type"]
         assert len(odict) >= 5, "the construction no longer gives a non-degenerate instance map"
         assert np.array_equal(labels[b], olab)
         assert sorted(dicts[b]) == sorted(odict)

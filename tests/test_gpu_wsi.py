@@ -233,7 +233,7 @@ def test_uint8_tiles_are_normalised_on_the_device_bit_identically():
 
     def grab(tag):
         def hook(payload):
-            seen[tag] = inf.model.graph_slot((2, 3, 256, 256), True, 0, torch.device("cuda", 0))[1].clone()
+            seen[tag] = inf.model.graph_slot((2, 3, 256, 256), True, 0, torch.device("cuda", 0), argmax_maps=True)[1].clone()
             return None
         return hook
 
