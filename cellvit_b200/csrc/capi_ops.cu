@@ -57,4 +57,12 @@ CVB_API int cvb_op_stem_conv(const float* x, int B, int H, int W, const float* w
     return op_stem_conv(x, B, H, W, w, scale, shift, (__half*)out, cpad, (cudaStream_t)stream);
 }
 
+CVB_API int cvb_op_copy_planes(const void* src, int sH, int sW, void* dst, int dH, int dW, long long planes, int elem_bytes, void* stream) {
+    return op_copy_planes(src, sH, sW, dst, dH, dW, planes, elem_bytes, (cudaStream_t)stream);
+}
+
+CVB_API int cvb_op_zero_margin(void* buf, long long planes, int H, int W, int bytes_per_px, int vH, int vW, void* stream) {
+    return op_zero_margin(buf, planes, H, W, bytes_per_px, vH, vW, (cudaStream_t)stream);
+}
+
 CVB_API int cvb_tc_epilogue_bytes(void) { return (int)sizeof(TcEpilogue); }

@@ -28,6 +28,10 @@ struct cvb_model {
     // option "dynamic_tiles": 1 (default) = the persistent kernels (tile engine, window attention) claim their tiles from a
     // per-launch counter (SchedRing, common.cuh) instead of walking a static list; 0 = static lists (ablation)
     int dynamic_tiles = 1;
+    // option "square_canvas": tiles whose token grid is not a native grid of the tile engine run their decoder on a zero-extended
+    // canvas (see forward_impl). 0 (default) = each dimension extended on its own (a 272 x 400 tile runs on 512 x 512, a 208 x 1024
+    // tile on 256 x 1024); 1 = both dimensions extended to the larger canvas edge (ablation / fallback)
+    int square_canvas = 0;
 };
 
 namespace {
@@ -36,11 +40,13 @@ struct Arena {
     uint8_t* base;
     size_t off, cap;
     bool dry;
+    size_t peak = 0;  // the branch loop rewinds `off`: the workspace requirement is the high-water mark
     template <class T>
     T* alloc(size_t n) {
         off = align_up(off, 256);
         T* p = reinterpret_cast<T*>(base + off);
         off += n * sizeof(T);
+        if (off > peak) peak = off;
         return p;
     }
 };
@@ -57,6 +63,14 @@ struct Fwd {
     int n_counters = 0;
     int* next_counter() { return (counters && m.dynamic_tiles && n_counters < N_COUNTERS) ? counters + n_counters++ : nullptr; }
     TcEpilogue with_counter(const TcEpilogue& e) { TcEpilogue c = e; c.sched_counter = next_counter(); return c; }
+    // canvas mode (forward_impl): the decoder runs on hc x wc token canvases of which the top-left h x w tokens are real
+    bool canvas = false;
+    int h = 0, w = 0, hc = 0, wc = 0;
+    // re-zero the canvas margin of an NHWC fp16 layer [NB,H,W,C] (H = s * hc): the next 3x3 convolution must see zeros beyond
+    // the real image border, and conv (+shift, ReLU) / ConvT (+bias) outputs are not zero there
+    void mask(__half* buf, int NB, int H, int W, int C) {
+        if (canvas && live()) chk(op_zero_margin(buf, NB, H, W, C * 2, h * (H / hc), w * (W / wc), st));
+    }
 
     template <class T>
     const T* P(const std::string& name) {
@@ -88,6 +102,7 @@ struct Fwd {
         e.scale = P<float>(name + ".scale"); e.shift = P<float>(name + ".shift");
         const __half* wp = P<__half>(name + ".w");
         if (live()) chk(tc_conv3x3(s0, C0, s1, C1, NB, H, W, wp, N, tc_pick_block_n(N), with_counter(e), st));
+        mask(out, NB, H, W, N);
         return out;
     }
     // ConvTranspose2d k2 s2 (+bias): [NB,hin,win,Cin] -> [NB,2hin,2win,Cout]
@@ -98,6 +113,7 @@ struct Fwd {
         e.ct_cout = Cout; e.ct_hin = hin; e.ct_win = win;
         const __half* wp = P<__half>(name + ".w");
         if (live()) chk(tc_gemm(src, NB * hin * win, Cin, Cin, wp, 4 * Cout, Cin, tc_pick_block_n(4 * Cout), with_counter(e), st));
+        mask(out, NB, 2 * hin, 2 * win, Cout);
         return out;
     }
     // Deconv2DBlock (utils.py:46-86): ConvT -> Conv3x3 -> BN -> ReLU
@@ -109,6 +125,9 @@ struct Fwd {
 
 int pad64(int c) { return (c + 63) / 64 * 64; }
 
+// Native token grids of the tile engine's decoder tilings (128-pixel blocks at every level): 16, 32 or 64 tokens per edge.
+int canvas_tokens(int t) { return t <= 16 ? 16 : (t <= 32 ? 32 : 64); }
+
 int forward_impl(cvb_model& m, const float* x, int B, int H, int W, float* o_np, float* o_hv, float* o_nt, float* o_tissue,
                  float* o_tokens, uint8_t* o_np_arg, uint8_t* o_nt_arg, Arena& A, cudaStream_t st) {
     const cvb_model_desc& d = m.d;
@@ -119,6 +138,15 @@ int forward_impl(cvb_model& m, const float* x, int B, int H, int W, float* o_np,
     const int skip = sam ? 0 : 1;
     const float scale = 1.0f / sqrtf((float)hd);
     const bool live = !A.dry;
+    // Any H, W divisible by 16 (cellvit.py:170-175, 603-608). The encoder runs on the real h x w token grid. The decoder's
+    // tilings want 16 / 32 / 64 tokens per edge: other grids run the decoder on the next larger canvas, the real tokens /
+    // pixels top-left and zeros elsewhere, with the margin re-zeroed after every layer -- inside the real region every
+    // convolution then sees exactly the zero padding of the real border, so the cropped result is the reference's.
+    int hc = canvas_tokens(h), wc = canvas_tokens(w);
+    if (m.square_canvas) hc = wc = (hc > wc ? hc : wc);
+    const bool canvas = hc != h || wc != w;
+    const int Hc = 16 * hc, Wc = 16 * wc, Tc = hc * wc;
+    f.canvas = canvas; f.h = h; f.w = w; f.hc = hc; f.wc = wc;
     f.counters = A.alloc<int>(Fwd::N_COUNTERS);
     if (live) CVB_CUDA(cudaMemsetAsync(f.counters, 0, Fwd::N_COUNTERS * sizeof(int), st));
 
@@ -150,7 +178,8 @@ int forward_impl(cvb_model& m, const float* x, int B, int H, int W, float* o_np,
     __half* att = A.alloc<__half>(rows_max * D);
     __half* hid = A.alloc<__half>((size_t)B * Tx * 4 * D);
     __half* z[4];
-    for (int k = 0; k < 4; ++k) z[k] = A.alloc<__half>((size_t)B * T * D);
+    for (int k = 0; k < 4; ++k) z[k] = A.alloc<__half>((size_t)B * Tc * D);
+    __half* zt = canvas ? A.alloc<__half>((size_t)B * T * D) : nullptr;  // compact skip tokens before they are embedded
 
     __half* ybuf = A.alloc<__half>(rows_max * D);
     // global attention (SAM's four global blocks, every block of ViT-S) runs on the tcgen05 attention kernel
@@ -210,7 +239,8 @@ int forward_impl(cvb_model& m, const float* x, int B, int H, int W, float* o_np,
         }
         for (int k = 0; k < 4; ++k)
             if (d.extract[k] == i + 1) {
-                if (f.live()) f.chk(op_cast_rows_f16(xs, B, Tx, skip, D, z[k], st));
+                if (f.live()) f.chk(op_cast_rows_f16(xs, B, Tx, skip, D, canvas ? zt : z[k], st));
+                if (canvas && f.live()) f.chk(op_copy_planes(zt, h, w * (D / 8), z[k], hc, wc * (D / 8), B, 16, st));
                 if (k == 3 && o_tokens && f.live()) f.chk(op_tokens_nchw(xs, B, Tx, skip, D, o_tokens, st));
             }
     }
@@ -229,9 +259,20 @@ int forward_impl(cvb_model& m, const float* x, int B, int H, int W, float* o_np,
         const float* g1 = f.P<float>("neck.1.w");
         const float* b1 = f.P<float>("neck.1.b");
         if (f.live()) f.chk(op_layernorm_f16(n0, g1, b1, 1e-6f, B * T, 256, n1, 0, B, h, w, 0, 0, st));
-        e.out = n2;
         const __half* w2 = f.P<__half>("neck.2.w");
-        if (f.live()) f.chk(tc_conv3x3(n1, 256, nullptr, 0, B, h, w, w2, 256, 256, f.with_counter(e), st));
+        if (!canvas) {
+            e.out = n2;
+            if (f.live()) f.chk(tc_conv3x3(n1, 256, nullptr, 0, B, h, w, w2, 256, 256, f.with_counter(e), st));
+        } else {
+            __half* n1c = A.alloc<__half>((size_t)B * Tc * 256);
+            float* n2c = A.alloc<float>((size_t)B * Tc * 256);
+            e.out = n2c;
+            if (f.live()) {
+                f.chk(op_copy_planes(n1, h, w * 32, n1c, hc, wc * 32, B, 16, st));
+                f.chk(tc_conv3x3(n1c, 256, nullptr, 0, B, hc, wc, w2, 256, 256, f.with_counter(e), st));
+                f.chk(op_copy_planes(n2c, hc, wc * 64, n2, h, w * 64, B, 16, st));
+            }
+        }
         const float* g3 = f.P<float>("neck.3.w");
         const float* b3 = f.P<float>("neck.3.b");
         const float* cw = f.P<float>("cls.w");
@@ -248,20 +289,24 @@ int forward_impl(cvb_model& m, const float* x, int B, int H, int W, float* o_np,
 
     // ------------------------------------------------------------------ shared skip decoders (cellvit.py:116-131)
     const int s11 = d.skip11, s12 = d.skip12, bt = d.bott_pad;
-    __half* st0 = A.alloc<__half>((size_t)B * H * W * 64);
+    // from here on every layer lives on the canvas (hc x wc tokens = Hc x Wc pixels; == h, w, H, W for the native grids)
+    __half* st0 = A.alloc<__half>((size_t)B * Hc * Wc * 64);
     {
         const float* sw = f.P<float>("decoder0.0.w");
         const float* sc = f.P<float>("decoder0.0.scale");
         const float* sh = f.P<float>("decoder0.0.shift");
-        if (f.live()) f.chk(op_stem_conv(x, B, H, W, sw, sc, sh, st0, 64, st));
+        // the stem stencil pads at the real border itself: run it on the real tile, then embed its output
+        __half* st0r = canvas ? A.alloc<__half>((size_t)B * H * W * 64) : st0;
+        if (f.live()) f.chk(op_stem_conv(x, B, H, W, sw, sc, sh, st0r, 64, st));
+        if (canvas && f.live()) f.chk(op_copy_planes(st0r, H, W * 8, st0, Hc, Wc * 8, B, 16, st));
     }
-    __half* s0 = f.conv_bn_relu(st0, 64, nullptr, 0, B, H, W, "decoder0.1", 64);
-    __half* s1 = f.deconv_block(z[0], D, B, h, w, "decoder1.0", s11);
-    s1 = f.deconv_block(s1, s11, B, 2 * h, 2 * w, "decoder1.1", s12);
-    s1 = f.deconv_block(s1, s12, B, 4 * h, 4 * w, "decoder1.2", 128);
-    __half* s2 = f.deconv_block(z[1], D, B, h, w, "decoder2.0", s11);
-    s2 = f.deconv_block(s2, s11, B, 2 * h, 2 * w, "decoder2.1", 256);
-    __half* s3 = f.deconv_block(z[2], D, B, h, w, "decoder3.0", bt);
+    __half* s0 = f.conv_bn_relu(st0, 64, nullptr, 0, B, Hc, Wc, "decoder0.1", 64);
+    __half* s1 = f.deconv_block(z[0], D, B, hc, wc, "decoder1.0", s11);
+    s1 = f.deconv_block(s1, s11, B, 2 * hc, 2 * wc, "decoder1.1", s12);
+    s1 = f.deconv_block(s1, s12, B, 4 * hc, 4 * wc, "decoder1.2", 128);
+    __half* s2 = f.deconv_block(z[1], D, B, hc, wc, "decoder2.0", s11);
+    s2 = f.deconv_block(s2, s11, B, 2 * hc, 2 * wc, "decoder2.1", 256);
+    __half* s3 = f.deconv_block(z[2], D, B, hc, wc, "decoder3.0", bt);
 
     // ------------------------------------------------------------------ three upsampling branches (cellvit.py:212-244)
     // arg: optional u8 arg-max plane of the branch (K12 fusion), over the first arg_nc classes (NP: the binary map's two, also when
@@ -272,25 +317,39 @@ int forward_impl(cvb_model& m, const float* x, int B, int H, int W, float* o_np,
     for (const Br& br : branches) {
         A.off = mark;  // branch activations reuse the same arena region (stream order serialises the branches)
         const std::string n = br.name;
-        __half* b = f.conv_t(z[3], D, B, h, w, n + ".bottleneck", bt);
-        b = f.conv_bn_relu(s3, bt, b, bt, B, 2 * h, 2 * w, n + ".d3.0", bt);
-        b = f.conv_bn_relu(b, bt, nullptr, 0, B, 2 * h, 2 * w, n + ".d3.1", bt);
-        b = f.conv_bn_relu(b, bt, nullptr, 0, B, 2 * h, 2 * w, n + ".d3.2", bt);
-        b = f.conv_t(b, bt, B, 2 * h, 2 * w, n + ".d3.ct", 256);
-        b = f.conv_bn_relu(s2, 256, b, 256, B, 4 * h, 4 * w, n + ".d2.0", 256);
-        b = f.conv_bn_relu(b, 256, nullptr, 0, B, 4 * h, 4 * w, n + ".d2.1", 256);
-        b = f.conv_t(b, 256, B, 4 * h, 4 * w, n + ".d2.ct", 128);
-        b = f.conv_bn_relu(s1, 128, b, 128, B, 8 * h, 8 * w, n + ".d1.0", 128);
-        b = f.conv_bn_relu(b, 128, nullptr, 0, B, 8 * h, 8 * w, n + ".d1.1", 128);
-        b = f.conv_t(b, 128, B, 8 * h, 8 * w, n + ".d1.ct", 64);
-        b = f.conv_bn_relu(s0, 64, b, 64, B, H, W, n + ".d0.0", 64);
+        __half* b = f.conv_t(z[3], D, B, hc, wc, n + ".bottleneck", bt);
+        b = f.conv_bn_relu(s3, bt, b, bt, B, 2 * hc, 2 * wc, n + ".d3.0", bt);
+        b = f.conv_bn_relu(b, bt, nullptr, 0, B, 2 * hc, 2 * wc, n + ".d3.1", bt);
+        b = f.conv_bn_relu(b, bt, nullptr, 0, B, 2 * hc, 2 * wc, n + ".d3.2", bt);
+        b = f.conv_t(b, bt, B, 2 * hc, 2 * wc, n + ".d3.ct", 256);
+        b = f.conv_bn_relu(s2, 256, b, 256, B, 4 * hc, 4 * wc, n + ".d2.0", 256);
+        b = f.conv_bn_relu(b, 256, nullptr, 0, B, 4 * hc, 4 * wc, n + ".d2.1", 256);
+        b = f.conv_t(b, 256, B, 4 * hc, 4 * wc, n + ".d2.ct", 128);
+        b = f.conv_bn_relu(s1, 128, b, 128, B, 8 * hc, 8 * wc, n + ".d1.0", 128);
+        b = f.conv_bn_relu(b, 128, nullptr, 0, B, 8 * hc, 8 * wc, n + ".d1.1", 128);
+        b = f.conv_t(b, 128, B, 8 * hc, 8 * wc, n + ".d1.ct", 64);
+        b = f.conv_bn_relu(s0, 64, b, 64, B, Hc, Wc, n + ".d0.0", 64);
+        // canvas mode: the fused head writes canvas-sized planes, which are cropped to the caller's [.., H, W] outputs
+        float* head_out = br.out;
+        uint8_t* head_arg = br.arg;
+        if (canvas) {
+            head_out = A.alloc<float>((size_t)B * br.nc * Hc * Wc);
+            head_arg = A.alloc<uint8_t>((size_t)B * Hc * Wc);
+            if (!br.arg) head_arg = nullptr;
+        }
         TcEpilogue e = Fwd::epi0();
         e.kind = TC_EPI_HEAD;
         e.scale = f.P<float>(n + ".d0.1.scale"); e.shift = f.P<float>(n + ".d0.1.shift");
         e.head_w = f.P<float>(n + ".head.w"); e.head_b = f.P<float>(n + ".head.b");
-        e.head_nc = br.nc; e.head_hw = H * W; e.head_out = br.out; e.head_argmax = br.arg; e.head_argmax_nc = br.arg_nc;
+        e.head_nc = br.nc; e.head_hw = Hc * Wc; e.head_out = head_out; e.head_argmax = head_arg; e.head_argmax_nc = br.arg_nc;
         const __half* wp = f.P<__half>(n + ".d0.1.w");
-        if (f.live() && br.out) f.chk(tc_conv3x3(b, 64, nullptr, 0, B, H, W, wp, 64, 64, f.with_counter(e), st));
+        if (f.live() && br.out) {
+            f.chk(tc_conv3x3(b, 64, nullptr, 0, B, Hc, Wc, wp, 64, 64, f.with_counter(e), st));
+            if (canvas) {
+                f.chk(op_copy_planes(head_out, Hc, Wc, br.out, H, W, (long long)B * br.nc, 4, st));
+                if (br.arg) f.chk(op_copy_planes(head_arg, Hc, Wc, br.arg, H, W, B, 1, st));
+            }
+        }
     }
     (void)pad64;
     return f.rc;
@@ -326,9 +385,9 @@ CVB_API int cvb_model_set_param(cvb_model* m, const char* name, const void* dev_
 static int check_shape(const cvb_model* m, int B, int H, int W) {
     CVB_CHECK(m != nullptr && B > 0, CVB_EARG, "cvb_forward: null model or empty batch");
     CVB_CHECK(H % 16 == 0 && W % 16 == 0 && H > 0 && W > 0, CVB_ESHAPE, "Input images must be divisible by the patch size (%dx%d)", H, W);
-    CVB_CHECK(H == W, CVB_ESHAPE, "cvb_forward: only square tiles are supported (%dx%d)", H, W);
-    CVB_CHECK(H == 256 || H == 512 || H == 1024, CVB_ESHAPE,
-              "cvb_forward: tile edge %d not supported by the 128-pixel conv tiling (256, 512 or 1024)", H);
+    CVB_CHECK(H <= 1024 && W <= 1024, CVB_ESHAPE, "cvb_forward: tile %dx%d exceeds the 1024-pixel edge the engine is sized for", H, W);
+    // SAM adds pos_embed[:, :h, :h, :] to the [B,h,w,D] tokens (utils.py:222-224): that only broadcasts for square token grids
+    CVB_CHECK(!m->d.sam || H == W, CVB_ESHAPE, "cvb_forward: the SAM encoders take square tiles only (%dx%d)", H, W);
     return CVB_OK;
 }
 
@@ -336,11 +395,8 @@ CVB_API int cvb_model_workspace_bytes(cvb_model* m, int B, int H, int W, size_t*
     CVB_CHECK(out != nullptr, CVB_EARG, "cvb_model_workspace_bytes: null out");
     CVB_TRY(check_shape(m, B, H, W));
     Arena A{nullptr, 0, 0, true};
-    size_t peak = 0;
-    // the branch loop rewinds the arena; track the peak by running the dry pass and taking the max offset
     forward_impl(*m, nullptr, B, H, W, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, A, nullptr);
-    peak = A.off;
-    // branch region is re-used three times; all three are the same size except the head, so A.off is the peak
+    const size_t peak = A.peak;
     *out = peak + 4096;
     return CVB_OK;
 }
@@ -380,6 +436,10 @@ CVB_API int cvb_model_set_option(cvb_model* m, const char* name, int value) {
     }
     if (std::string(name) == "dynamic_tiles") {
         m->dynamic_tiles = value != 0;
+        return CVB_OK;
+    }
+    if (std::string(name) == "square_canvas") {
+        m->square_canvas = value != 0;
         return CVB_OK;
     }
     cvb_set_error("cvb_model_set_option: unknown option '%s'", name);

@@ -44,6 +44,13 @@ int op_tokens_nchw(const float* x, int B, int T_src, int skip, int D, float* out
 int op_stem_conv(const float* x, int B, int H, int W, const float* w, const float* scale, const float* shift,
                  __half* out, int cpad, cudaStream_t stream);
 
+// Canvas helpers (model.cu: tiles whose token grid is not a native grid of the tile engine run the decoder on a
+// zero-extended canvas). copy_planes: dst[p][y][x] = (y < sH && x < sW) ? src[p][y][x] : 0 over `planes` planes of
+// elements of 1, 4 or 16 bytes (crop when dst is smaller, zero-extending embed when larger).
+// zero_margin: zero every pixel with y >= vH or x >= vW of NHWC planes [planes][H][W][bytes_per_px].
+int op_copy_planes(const void* src, int sH, int sW, void* dst, int dH, int dW, long long planes, int elem_bytes, cudaStream_t stream);
+int op_zero_margin(void* buf, long long planes, int H, int W, int bytes_per_px, int vH, int vW, cudaStream_t stream);
+
 // SAM neck tail (image_encoder.py:110-113, utils.py:230-233, cellvit.py:613): per image LayerNorm2d over C of
 // y [B, T, C] fp32, mean over T, then Linear(C -> n_out). out [B, n_out] fp32.
 int op_ln_mean_linear(const float* y, int B, int T, int C, const float* gamma, const float* beta, float eps,

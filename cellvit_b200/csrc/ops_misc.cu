@@ -368,6 +368,44 @@ int grid_for(long long work_items, int block) {
     return (int)(g < 1 ? 1 : (g > cap ? cap : g));
 }
 
+
+// ------------------------------------------------------------------------------------------ canvas helpers
+// Tiles whose token grid is not one of the tile engine's native grids run their decoder on a zero-extended canvas
+// (model.cu): planes are embedded top-left into the canvas, every layer's margin is re-zeroed (so that the next 3x3
+// convolution sees the zero padding of the real image border), and the head outputs are cropped back.
+template <class T> __device__ __forceinline__ T zero_of() { return T(0); }
+template <> __device__ __forceinline__ uint4 zero_of<uint4>() { return make_uint4(0, 0, 0, 0); }
+
+// dst[p][y][x] = (y < sH && x < sW) ? src[p][y][x] : 0   for y < dH, x < dW  (crop when dst is smaller, zero-extend when larger)
+template <class T>
+__global__ void copy_planes_kernel(const T* __restrict__ src, int sH, int sW, T* __restrict__ dst, int dH, int dW, long long total) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int x = (int)(i % dW);
+        const long long r = i / dW;
+        const int y = (int)(r % dH);
+        const long long p = r / dH;
+        T v = zero_of<T>();
+        if (y < sH && x < sW) v = src[(p * sH + y) * sW + x];
+        dst[i] = v;
+    }
+}
+
+// zero the pixels (y >= vH or x >= vW) of NHWC planes [planes][H][W][vec] (vec = 16-byte units per pixel)
+__global__ void zero_margin_kernel(uint4* __restrict__ buf, long long planes, int H, int W, int vec, int vH, int vW) {
+    const long long right = (long long)vH * (W - vW), per_plane = right + (long long)(H - vH) * W;
+    const long long total = planes * per_plane * vec;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int v = (int)(i % vec);
+        long long r = i / vec;
+        const long long p = r / per_plane;
+        r -= p * per_plane;
+        int y, x;
+        if (r < right) { y = (int)(r / (W - vW)); x = vW + (int)(r % (W - vW)); }
+        else { r -= right; y = vH + (int)(r / W); x = (int)(r % W); }
+        buf[((p * H + y) * W + x) * vec + v] = make_uint4(0, 0, 0, 0);
+    }
+}
+
 }  // namespace
 
 int op_patch_im2col(const float* x, int B, int H, int W, int P, __half* out, cudaStream_t stream) {
@@ -416,6 +454,39 @@ int op_tokens_nchw(const float* x, int B, int T_src, int skip, int D, float* out
     CVB_CHECK(x && out && T_src > skip, CVB_EARG, "tokens_nchw: bad arguments");
     dim3 grid(cdiv(T_src - skip, 32), cdiv(D, 32), B), block(32, 8);
     tokens_nchw_kernel<<<grid, block, 0, stream>>>(x, T_src, skip, D, out);
+    cvb_note_launches(1);
+    CVB_CUDA(cudaGetLastError());
+    return CVB_OK;
+}
+
+
+int op_copy_planes(const void* src, int sH, int sW, void* dst, int dH, int dW, long long planes, int elem_bytes, cudaStream_t stream) {
+    CVB_CHECK(src && dst && sH > 0 && sW > 0 && dH > 0 && dW > 0 && planes > 0, CVB_EARG, "copy_planes: bad arguments");
+    const long long total = planes * dH * dW;
+    const int grid = grid_for(total, 256);
+    if (elem_bytes == 16) {
+        CVB_CHECK((((uintptr_t)src | (uintptr_t)dst) & 15) == 0, CVB_EARG, "copy_planes: 16-byte elements need 16-byte alignment");
+        copy_planes_kernel<uint4><<<grid, 256, 0, stream>>>((const uint4*)src, sH, sW, (uint4*)dst, dH, dW, total);
+    } else if (elem_bytes == 4) {
+        copy_planes_kernel<float><<<grid, 256, 0, stream>>>((const float*)src, sH, sW, (float*)dst, dH, dW, total);
+    } else if (elem_bytes == 1) {
+        copy_planes_kernel<uint8_t><<<grid, 256, 0, stream>>>((const uint8_t*)src, sH, sW, (uint8_t*)dst, dH, dW, total);
+    } else {
+        cvb_set_error("copy_planes: element size %d not supported (1, 4, 16)", elem_bytes);
+        return CVB_EARG;
+    }
+    cvb_note_launches(1);
+    CVB_CUDA(cudaGetLastError());
+    return CVB_OK;
+}
+
+int op_zero_margin(void* buf, long long planes, int H, int W, int bytes_per_px, int vH, int vW, cudaStream_t stream) {
+    CVB_CHECK(buf && planes > 0 && bytes_per_px > 0 && bytes_per_px % 16 == 0 && vH > 0 && vW > 0 && vH <= H && vW <= W &&
+                  (((uintptr_t)buf) & 15) == 0, CVB_EARG, "zero_margin: bad arguments");
+    const long long per_plane = (long long)vH * (W - vW) + (long long)(H - vH) * W;
+    if (per_plane == 0) return CVB_OK;
+    const int vec = bytes_per_px / 16;
+    zero_margin_kernel<<<grid_for(planes * per_plane * vec, 256), 256, 0, stream>>>((uint4*)buf, planes, H, W, vec, vH, vW);
     cvb_note_launches(1);
     CVB_CUDA(cudaGetLastError());
     return CVB_OK;

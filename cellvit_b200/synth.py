@@ -16,10 +16,11 @@ from __future__ import annotations
 import numpy as np
 
 
-def synthetic_tiles(batch: int, size: int = 1024, seed: int = 0) -> np.ndarray:
-    """[B,3,size,size] float32 in [-1,1] from seeded uniform uint8 RGB."""
+def synthetic_tiles(batch: int, size=1024, seed: int = 0) -> np.ndarray:
+    """[B,3,H,W] float32 in [-1,1] from seeded uniform uint8 RGB; ``size`` = edge of a square tile or ``(H, W)``."""
     rng = np.random.default_rng(seed)
-    u8 = rng.integers(0, 256, size=(batch, size, size, 3), dtype=np.uint8)
+    hh, ww = (size, size) if isinstance(size, int) else size
+    u8 = rng.integers(0, 256, size=(batch, hh, ww, 3), dtype=np.uint8)
     x = u8.astype(np.float32) / np.float32(255.0)
     x = (x - np.float32(0.5)) / np.float32(0.5)
     return np.ascontiguousarray(x.transpose(0, 3, 1, 2))

@@ -58,7 +58,9 @@ typedef struct {
 int cvb_model_create(const cvb_model_desc* desc, cvb_model** out);
 void cvb_model_destroy(cvb_model* m);
 /* Per-handle options (no process-global state). "attention_tc": bit 0 = tcgen05 kernel for the global-attention blocks,
- * bit 1 = tcgen05 kernel for the 14 x 14 windows (default 3 = both); 0 = the mma.sync kernels (parity-test reference). */
+ * bit 1 = tcgen05 kernel for the 14 x 14 windows (default 3 = both); 0 = the mma.sync kernels (parity-test reference).
+ * "dynamic_tiles": 1 (default) = persistent kernels claim tiles from a per-launch counter, 0 = static tile lists.
+ * "square_canvas": 0 (default) = a non-native tile size extends each decoder dimension to its own canvas, 1 = to a square one. */
 int cvb_model_set_option(cvb_model* m, const char* name, int value);
 
 /* Registers one packed parameter tensor (device pointer; the caller keeps it alive). Names and layouts are
@@ -70,7 +72,12 @@ int cvb_model_workspace_bytes(cvb_model* m, int B, int H, int W, size_t* out);
 
 /* x [B,3,H,W] fp32 (already normalised, cell_detection.py:214-227). Outputs are raw logits, fp32 NCHW:
  * np_logits [B,n_np_out,H,W], hv [B,2,H,W], nt_logits [B,n_nt,H,W], tissue [B,n_tissue],
- * tokens [B,embed_dim,H/16,W/16] (nullable; the z4 skip, retrieve_tokens=True). H == W in {256, 512, 1024}. */
+ * tokens [B,embed_dim,H/16,W/16] (nullable; the z4 skip, retrieve_tokens=True).
+ * Shapes: any H, W divisible by 16 up to 1024 (cellvit.py:170-175, 603-608; CVB_ESHAPE otherwise), non-square included for the
+ * ViT-S encoder; the SAM encoders take square tiles only, as in the reference (its pos_embed slice, utils.py:222-224, only
+ * broadcasts for square token grids). Token grids of 16 / 32 / 64 per edge (256 / 512 / 1024 pixels) are the tile engine's
+ * native decoder tilings; any other size runs the encoder on its real token grid and the decoder on the next larger
+ * zero-extended canvas, cropped on output -- same results, the cost of the canvas size. */
 int cvb_forward(cvb_model* m, const float* x, int B, int H, int W, float* np_logits, float* hv, float* nt_logits,
                 float* tissue, float* tokens, void* workspace, size_t ws_bytes, void* stream);
 /* The same forward that ALSO writes the arg-max planes the post-processing consumes (K12 fusion): np_argmax /
@@ -174,6 +181,11 @@ int cvb_op_attention_tc(const void* qkv, int Gb, int S, int heads, int hd, float
 int cvb_op_window_attention_tc(const void* qkv, int n_items, int heads, int hd, float scale, const void* relcat, void* out,
                                int32_t* sched_counter, void* stream);
 int cvb_op_patch_im2col(const float* x, int B, int H, int W, int P, void* out, void* stream);
+/* Canvas helpers of cvb_forward for non-native tile sizes. copy_planes: dst[p][y][x] = (y < sH && x < sW) ? src[p][y][x] : 0 for
+ * y < dH, x < dW over `planes` planes of elements of 1, 4 or 16 bytes (a crop when dst is smaller, a zero-extending embed when
+ * larger). zero_margin: zero the pixels with y >= vH or x >= vW of NHWC planes [planes][H][W][bytes_per_px] (multiple of 16). */
+int cvb_op_copy_planes(const void* src, int sH, int sW, void* dst, int dH, int dW, long long planes, int elem_bytes, void* stream);
+int cvb_op_zero_margin(void* buf, long long planes, int H, int W, int bytes_per_px, int vH, int vW, void* stream);
 int cvb_op_stem_conv(const float* x, int B, int H, int W, const float* w, const float* scale, const float* shift,
                      void* out, int cpad, void* stream);
 

@@ -71,7 +71,19 @@ def test_model_desc_validation_and_shape_errors(lib_path):
     assert L.cvb_model_workspace_bytes(h, 1, 256, 256, ctypes.byref(need)) == 0 and need.value > 0
     assert L.cvb_model_workspace_bytes(h, 1, 250, 250, ctypes.byref(need)) == -2     # not divisible by 16
     assert b"divisible by the patch size" in L.cvb_last_error()
-    assert L.cvb_model_workspace_bytes(h, 1, 320, 320, ctypes.byref(need)) == -2     # unsupported tile edge
+    small = need.value
+    assert L.cvb_model_workspace_bytes(h, 1, 320, 320, ctypes.byref(need)) == 0      # any multiple of 16: decoder on a 512 canvas
+    canvas = need.value
+    assert L.cvb_model_workspace_bytes(h, 1, 512, 512, ctypes.byref(need)) == 0 and small < need.value < canvas
+    assert L.cvb_model_workspace_bytes(h, 1, 208, 1024, ctypes.byref(need)) == 0     # non-square (ViT-S only)
+    assert L.cvb_model_workspace_bytes(h, 1, 1040, 256, ctypes.byref(need)) == -2    # beyond the 1024-pixel edge
+    assert b"1024" in L.cvb_last_error()
+    from cellvit_b200.cellvit import CellViTSAM
+    ms = CellViTSAM(None, 6, 19, "SAM-B")
+    hs = ms._ensure_handle()
+    assert L.cvb_model_workspace_bytes(hs, 1, 400, 400, ctypes.byref(need)) == 0
+    assert L.cvb_model_workspace_bytes(hs, 1, 256, 512, ctypes.byref(need)) == -2    # SAM: square token grids only (utils.py:222-224)
+    assert b"square" in L.cvb_last_error()
     bad = ModelDesc(sam=0, embed_dim=100, depth=1, num_heads=3)
     out = ctypes.c_void_p()
     assert L.cvb_model_create(ctypes.byref(bad), ctypes.byref(out)) != 0
