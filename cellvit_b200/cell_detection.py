@@ -303,16 +303,20 @@ class CellSegmentationInference:
     # ------------------------------------------------------------------ WSI level
     def process_wsi(self, wsi, subdir_name: str = None, patch_size: int = 1024, overlap: int = 64, batch_size: int = 8,
                     geojson: bool = False, num_workers: int = None, head_override=None, json_indent=None,
-                    uint8_tiles: bool = True, shard: Tuple[int, int] = None) -> dict:
+                    uint8_tiles: bool = True, shard: Tuple[int, int] = None):
         """cell_detection.py:244-483 -- all tiles of one preprocessed WSI -> ``cells.json``, ``cell_detection.json``
         (+ ``.geojson``) and ``cells.pt`` under ``<patched_slide_path>/cell_detection[/subdir_name]``.
 
         Same per-cell records as the reference (global bbox / centroid / contour, ``cell_status``, edge information,
         mean cell token). The forward, post-processing, contour tracing and token pooling run on the GPU through
         ``_pipeline``; the duplicate removal of overlapping tiles uses the GPU polygon-overlap kernel (wsi_merge.py).
-        Returns the ``cells.json`` dictionary. ``head_override`` is the bench/test hook of ``_pipeline``. ``json_indent``: the
-        reference writes ``indent=2`` through ujson; Python's json only uses its C encoder without indentation (10x faster
-        on a slide with 10^5 cells), so the files are written compact unless an indent is asked for -- same content.
+        The cells of the slide are kept as columns (``wsi_records.CellColumns``), never as per-cell Python objects: the
+        per-tile record arithmetic is vectorised, the duplicate removal reads the columns, and the JSON / GeoJSON files are
+        streamed from them by the native writer ``cvb_export_json`` (byte-identical to ``json.dumps`` of the reference's
+        record dicts). Returns the ``cells.json`` dictionary as a read-only mapping whose ``"cells"`` list of per-cell dicts
+        is only built when it is read (``.columns`` holds the arrays). ``head_override`` is the bench/test hook of
+        ``_pipeline``. ``json_indent``: the reference writes ``indent=2`` through ujson; ``None`` (default) writes the same
+        content compact (a third of the bytes), ``json_indent=2`` gives the reference's layout.
         ``uint8_tiles``: ship raw uint8 tiles from the DataLoader workers and normalise on the device (bit-identical).
 
         Multi-GPU (one process per GPU): with ``torch.distributed`` initialised -- or an explicit ``shard=(rank, world_size)``
@@ -334,11 +338,9 @@ class CellSegmentationInference:
 
     def _process_wsi(self, wsi, subdir_name, patch_size, overlap, batch_size, geojson, num_workers, head_override, json_indent,
                      uint8_tiles, shard):
-        import json
         import os
         from torch.utils.data import DataLoader
-        from .wsi_datamodel import CellGraphDataWSI, InferenceTransform, PatchedWSIInference, SplitTensorList
-        from .wsi_merge import cell_status_batch, get_cell_position, get_edge_patch
+        from .wsi_datamodel import CellGraphDataWSI, InferenceTransform, PatchedWSIInference, SplitTensorList, save_cell_graph
 
         dataset = PatchedWSIInference(wsi, transform=InferenceTransform(self.mean, self.std, as_uint8=uint8_tiles))
         if num_workers is None:
@@ -358,63 +360,26 @@ class CellSegmentationInference:
         outdir.mkdir(exist_ok=True, parents=True)
 
         import time
+        from .wsi_records import CellColumns, LazyCellsJson, write_cells_json, write_geojson
         t_start = time.perf_counter()
-        bundles = []   # one per tile, in this rank's tile order: (patch id, records, detection records, positions, contours, tokens)
+        bundles = []   # one per tile, in this rank's tile order: (patch id, CellColumns of the tile or None)
         scale, psize = wsi.metadata["downsampling"], wsi.metadata["patch_size"]
         t_records = 0.0
         for metadata, tiles, toks in self._pipeline(loader, wsi.metadata["magnification"], head_override, with_tokens=True, raw=True):
             t_rec0 = time.perf_counter()
             for meta, tc, tok in zip(metadata, tiles, toks):
                 row, col = meta["row"], meta["col"]
-                bundle = {"patch": f"{row}_{col}", "cells": [], "detection": [], "positions": None, "contours": None, "tokens": None}
-                bundles.append(bundle)
                 x_global = int(row * psize * scale - (row + 0.5) * overlap)      # :343-350 (x follows the tile ROW)
                 y_global = int(col * psize * scale - (col + 0.5) * overlap)
-                offset_global = np.array([x_global, y_global])
-                # per-tile vectorised arithmetic on the instance table (the reference does this cell by cell, :352-409)
-                rows = tc.rows[tc.valid]
-                sel = rows["type"] != background
-                if not sel.any():
-                    continue
-                rows = rows[sel]
-                n_cells = len(rows)
-                flip = np.flip(offset_global)
-                bboxes = np.stack([np.stack([rows["rmin"], rows["cmin"]], 1), np.stack([rows["rmax"], rows["cmax"]], 1)], 1).astype(np.int64)
-                status = cell_status_batch(bboxes, 1024, 64).tolist()                 # :372-374 (constants as in the reference)
-                flat = bboxes.reshape(n_cells, -1)
-                on_edge = ((flat.max(1) == 1024) | (flat.min(1) == 0)).tolist()
-                bbox_g = (bboxes + offset_global).tolist()
-                cent_np = np.stack([rows["cx"], rows["cy"]], 1) + flip
-                cent_g = cent_np.tolist()
-                lens_all = tc.lens
-                pt_sel = np.repeat(sel, lens_all)
-                lens = lens_all[sel].tolist()
-                cont_np = tc.points[pt_sel] + flip
-                cont_list = cont_np.tolist()
-                offs = np.concatenate([[0], np.cumsum(lens)]).tolist()
-                types, probs = rows["type"].tolist(), rows["type_prob"].tolist()
-                off_list = offset_global.tolist()
-                for n in range(n_cells):
-                    cell_dict = {"bbox": bbox_g[n], "centroid": cent_g[n], "contour": cont_list[offs[n]:offs[n + 1]],
-                                 "type_prob": probs[n], "type": types[n], "patch_coordinates": [row, col],
-                                 "cell_status": status[n], "offset_global": list(off_list)}
-                    if on_edge[n]:
-                        position = get_cell_position(bboxes[n], 1024)
-                        cell_dict["edge_position"] = True
-                        cell_dict["edge_information"] = {"position": position, "edge_patches": get_edge_patch(position, row, col)}
-                    else:
-                        cell_dict["edge_position"] = False
-                    bundle["cells"].append(cell_dict)
-                    bundle["detection"].append({"bbox": cell_dict["bbox"], "centroid": cell_dict["centroid"], "type": types[n]})
-                bundle["positions"] = torch.from_numpy(cent_np).to(torch.float32)
-                bundle["contours"] = (torch.from_numpy(cont_np).to(torch.float32), lens)
-                bundle["tokens"] = torch.from_numpy(tok[tc.valid[sel]])
+                # the per-cell records of the tile (:352-409) as columns: vectorised arithmetic on the instance table, no
+                # per-cell Python objects (constants 1024 / 64 as in the reference, :372-378)
+                bundles.append((f"{row}_{col}", CellColumns.from_tile(tc, tok, row, col, np.array([x_global, y_global]), background, 1024, 64)))
             t_records += time.perf_counter() - t_rec0
 
-        if world > 1:   # gather the per-tile records on rank 0 and restore the dataset order
+        if world > 1:   # gather the per-tile columns on rank 0 and restore the dataset order
             import torch.distributed as dist
             gathered = [None] * world if rank == 0 else None
-            if str(self.device).startswith("cuda"):   # NCCL stages the pickled records through the current device
+            if str(self.device).startswith("cuda"):   # NCCL stages the pickled arrays through the current device
                 with torch.cuda.device(torch.device(self.device)):
                     dist.gather_object(bundles, gathered, dst=0)
             else:
@@ -424,55 +389,33 @@ class CellSegmentationInference:
                 return None
             by_tile = {t: b for r in range(world) for t, b in zip(shard_indices(len(dataset), r, world), gathered[r])}
             bundles = [by_tile[t] for t in range(len(dataset))]
-        cell_dict_wsi, cell_dict_detection, processed_patches = [], [], []
-        tokens_all, positions_all, contour_pts, contour_lens = [], [], [], []
-        for b in bundles:
-            processed_patches.append(b["patch"])
-            if b["cells"]:
-                cell_dict_wsi.extend(b["cells"])
-                cell_dict_detection.extend(b["detection"])
-                positions_all.append(b["positions"])
-                contour_pts.append(b["contours"][0])
-                contour_lens.extend(b["contours"][1])
-                tokens_all.append(b["tokens"])
+        processed_patches = [b[0] for b in bundles]
+        cols = CellColumns.concat([b[1] for b in bundles], token_dim=self.model.embed_dim)
         t_tiles = time.perf_counter()
-        keep_idx = self.post_process_edge_cells(cell_dict_wsi)
+        keep_idx = self.post_process_edge_cells(cols)
         t_dedup = time.perf_counter()
-        cell_dict_wsi = [cell_dict_wsi[i] for i in keep_idx]
-        cell_dict_detection = [cell_dict_detection[i] for i in keep_idx]
-        tokens_cat = torch.cat(tokens_all) if tokens_all else torch.zeros(0, self.model.embed_dim)
-        positions_cat = torch.cat(positions_all) if positions_all else torch.zeros(0, 2)
-        lens_np = np.asarray(contour_lens, dtype=np.int64)
-        keep_np = np.asarray(keep_idx, dtype=np.int64)
-        lens_kept = lens_np[keep_np]
-        # rows of the concatenated contour points that belong to the kept cells, in keep order
-        src_start, dst_start = (np.cumsum(lens_np) - lens_np)[keep_np], np.cumsum(lens_kept) - lens_kept
-        gather = np.repeat(src_start - dst_start, lens_kept) + np.arange(int(lens_kept.sum()), dtype=np.int64)
-        pts_cat = torch.cat(contour_pts) if contour_pts else torch.zeros(0, 2)
-        graph = CellGraphDataWSI(x=tokens_cat[keep_idx], positions=positions_cat[keep_idx],
-                                 contours=SplitTensorList(pts_cat[torch.from_numpy(gather)], lens_kept.tolist()),
+        kept = cols.take(keep_idx)
+        graph = CellGraphDataWSI(x=torch.from_numpy(kept.tokens), positions=torch.from_numpy(kept.centroid).to(torch.float32),
+                                 contours=SplitTensorList(torch.from_numpy(kept.contour_pts).to(torch.float32), np.diff(kept.contour_off).tolist()),
                                  metadata={"wsi_metadata": wsi.metadata, "nuclei_types": nuclei_types})
 
-        out_wsi = {"wsi_metadata": wsi.metadata, "processed_patches": processed_patches, "type_map": nuclei_types, "cells": cell_dict_wsi}
-        out_det = {"wsi_metadata": wsi.metadata, "processed_patches": processed_patches, "type_map": nuclei_types, "cells": cell_dict_detection}
-        with open(outdir / "cells.json", "w") as f:
-            f.write(json.dumps(out_wsi, indent=json_indent))  # dumps = one-shot C encoder; json.dump streams through Python
-        with open(outdir / "cell_detection.json", "w") as f:
-            f.write(json.dumps(out_det, indent=json_indent))
+        # cells.json / cell_detection.json (:438-463) and the GeoJSON pair (:443-447, 457-461) streamed from the columns
+        header = {"wsi_metadata": wsi.metadata, "processed_patches": processed_patches, "type_map": nuclei_types}
+        write_cells_json(kept, outdir / "cells.json", header, detection=False, indent=json_indent)
+        write_cells_json(kept, outdir / "cell_detection.json", header, detection=True, indent=json_indent)
         if geojson:
-            with open(outdir / "cells.geojson", "w") as f:
-                f.write(json.dumps(self.convert_geojson(cell_dict_wsi, True), indent=json_indent))
-            with open(outdir / "cell_detection.geojson", "w") as f:
-                f.write(json.dumps(self.convert_geojson(cell_dict_wsi, False), indent=json_indent))
-        torch.save(graph, outdir / "cells.pt")
+            write_geojson(kept, outdir / "cells.geojson", True, TYPE_NUCLEI_DICT, COLOR_DICT, indent=json_indent)
+            write_geojson(kept, outdir / "cell_detection.geojson", False, TYPE_NUCLEI_DICT, COLOR_DICT, indent=json_indent)
+        save_cell_graph(graph, outdir / "cells.pt")
         t_end = time.perf_counter()
         # where the wall clock went (seconds): tile stream (decode + GPU + per-cell records), duplicate removal, export
         self.last_timings = {"tiles": t_tiles - t_start, "of_which_cell_records": t_records, "dedup": t_dedup - t_tiles,
                              "export": t_end - t_dedup}
-        return out_wsi
+        return LazyCellsJson(header, kept)
 
-    def post_process_edge_cells(self, cell_list: List[dict]) -> List[int]:
-        """cell_detection.py:516-536 -- indices of the cells to keep after the overlap clean-up."""
+    def post_process_edge_cells(self, cell_list) -> List[int]:
+        """cell_detection.py:516-536 -- indices of the cells to keep after the overlap clean-up. ``cell_list``: the reference's
+        list of per-cell dicts, or the columnar store of the slide (``wsi_records.CellColumns``)."""
         from .wsi_merge import CellPostProcessor
         return CellPostProcessor(cell_list, None, torch.device(self.device)).post_process_cells()
 

@@ -158,3 +158,18 @@ class GraphDataWSI:
 @dataclass
 class CellGraphDataWSI(GraphDataWSI):
     contours: List[torch.Tensor]
+
+
+def save_cell_graph(graph: CellGraphDataWSI, path) -> None:
+    """``torch.save(graph, cells.pt)`` (cell_detection.py:462-468) with the class recorded under the REFERENCE's module path
+    (``cell_segmentation.datasets.cell_graph_datamodel.CellGraphDataWSI``): a reference-side ``torch.load`` returns the
+    reference's own dataclass, with the fields x / positions / contours / metadata it expects."""
+    from . import _graph_pickle
+    torch.save(graph, path, pickle_module=_graph_pickle)
+
+
+def load_cell_graph(path, map_location="cpu"):
+    """Reads a ``cells.pt`` written by this package or by the reference: the reference's dataclass where it is importable, this
+    package's ``CellGraphDataWSI`` (same fields) otherwise."""
+    from . import _graph_pickle
+    return torch.load(path, map_location=map_location, pickle_module=_graph_pickle, weights_only=False)

@@ -186,14 +186,20 @@ def overlap_areas(contours: List[np.ndarray], pairs: np.ndarray, device=None) ->
 
 class CellPostProcessor:
     """cell_detection.py:600-767. ``cell_list`` entries need: contour, cell_status, edge_position, edge_information
-    (for edge cells), patch_coordinates [row, col]. ``post_process_cells`` returns the sorted indices to keep."""
+    (for edge cells), patch_coordinates [row, col] -- or ``cell_list`` is the columnar store of the slide
+    (``wsi_records.CellColumns``), which holds the same information without per-cell objects.
+    ``post_process_cells`` returns the sorted indices to keep."""
 
-    def __init__(self, cell_list: List[dict], logger=None, device=None, overlap_fn=None) -> None:
+    def __init__(self, cell_list, logger=None, device=None, overlap_fn=None) -> None:
         self.logger = logger
-        self.cells = cell_list
         self.device = device
         self.overlap_fn = overlap_fn or overlap_areas
-        status = np.array([c["cell_status"] for c in cell_list], dtype=np.int64) if cell_list else np.zeros(0, np.int64)
+        self.cols = cell_list if hasattr(cell_list, "contour_off") else None
+        self.cells = None if self.cols is not None else cell_list
+        if self.cols is not None:
+            status = self.cols.status
+        else:
+            status = np.array([c["cell_status"] for c in cell_list], dtype=np.int64) if cell_list else np.zeros(0, np.int64)
         self.mid_idx = np.nonzero(status == 0)[0]
         self.margin_idx = np.nonzero(status != 0)[0]
 
@@ -211,6 +217,13 @@ class CellPostProcessor:
     def _clean_edge_cells(self) -> List[int]:
         """:640-672 -- margin cells that do not touch the border, plus border cells whose (first) neighbour tile has no
         margin cell at all (i.e. was not processed / is empty there)."""
+        if self.cols is not None:
+            c = self.cols
+            existing = set(map(tuple, c.patch[self.margin_idx].tolist()))
+            edge = c.edge[self.margin_idx] != 0
+            keep = self.margin_idx[~edge].tolist()
+            keep += [int(i) for i in self.margin_idx[edge] if c.first_edge_patch(int(i)) not in existing]
+            return sorted(keep)
         existing = {tuple(self.cells[i]["patch_coordinates"]) for i in self.margin_idx}
         keep = []
         for i in self.margin_idx:
@@ -226,7 +239,10 @@ class CellPostProcessor:
         > 1 % of either area) is replaced by the largest of those partners, partners are consumed."""
         if len(cleaned) < 2:
             return list(cleaned)
-        contours = [np.asarray(self.cells[i]["contour"], dtype=np.float64).reshape(-1, 2) for i in cleaned]
+        if self.cols is not None:
+            contours = [self.cols.contour(i).astype(np.float64) for i in cleaned]
+        else:
+            contours = [np.asarray(self.cells[i]["contour"], dtype=np.float64).reshape(-1, 2) for i in cleaned]
         boxes = np.array([[c[:, 0].min(), c[:, 1].min(), c[:, 0].max(), c[:, 1].max()] if len(c) else [0, 0, -1, -1] for c in contours])
         pairs = envelope_pairs(boxes)
         area, inter = self.overlap_fn(contours, pairs, self.device) if self.overlap_fn is overlap_areas else self.overlap_fn(contours, pairs)

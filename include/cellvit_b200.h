@@ -155,6 +155,42 @@ int cvb_cell_tokens(const float* tokens, const cvb_inst_row* table, const int32_
 int cvb_polygon_overlap(const double* pts_xy, const int32_t* poly_off, int n_poly, const int32_t* pairs, int n_pairs,
                         double* poly_area, double* inter_area, void* stream);
 
+/* ------------------------------------------------------------------------------------------------ WSI-level export (host only)
+ * Replaces the per-cell record dicts and json dumps of process_wsi (cell_segmentation/inference/cell_detection.py:352-409 records,
+ * :438-475 cells.json / cell_detection.json / *.geojson, :538-597 convert_geojson): the cells of a slide live in columns (HOST
+ * pointers, global WSI coordinates) and the files are streamed from them. Format = Python's json.dumps(obj, indent) byte for byte
+ * (floats as float.__repr__); indent < 0 = compact. */
+typedef struct cvb_cell_columns {
+    long long n;                /* cells                                                                              */
+    const int64_t* bbox;        /* [n,2,2] [[rmin,cmin],[rmax,cmax]] + global offset (:357-358)                        */
+    const double* centroid;     /* [n,2]                                                        (:359)                */
+    const int64_t* contour_pts; /* [contour_off[n],2] (x, y) of all contours                    (:360)                */
+    const int64_t* contour_off; /* [n+1]                                                                              */
+    const double* type_prob;    /* [n]                                                                                */
+    const int64_t* type;        /* [n]                                                                                */
+    const int64_t* patch;       /* [n,2] tile (row, col)                                        (:366)                */
+    const int64_t* status;      /* [n] cell_status 0..8                                         (:372-374)            */
+    const int64_t* offset;      /* [n,2] offset_global of the tile                              (:343-350)            */
+    const uint8_t* edge;        /* [n] edge_position                                            (:376-392)            */
+    const int8_t* position;     /* [n,4] [top, right, down, left] border flags (read for edge cells; edge_patches follow
+                                   from them and the tile coordinates, :877-902)                                     */
+} cvb_cell_columns;
+enum { CVB_JSON_CELLS = 0,      /* full records of cells.json                                                         */
+       CVB_JSON_DETECTION = 1,  /* {"bbox", "centroid", "type"} records of cell_detection.json                        */
+       CVB_JSON_POLYGONS = 2,   /* GeoJSON MultiPolygon coordinates: [[closed ring]] per cell   (:569-575)            */
+       CVB_JSON_POINTS = 3 };   /* GeoJSON MultiPoint coordinates: centroids                                          */
+/* One array rendered from the columns over the cells idx[0..n_idx), between two caller-rendered strings: the file is the
+ * concatenation of head + array + tail over all sections. depth = nesting depth of the array (for indented output). */
+typedef struct cvb_json_section {
+    const char* head;
+    const char* tail;
+    const int64_t* idx;
+    long long n_idx;
+    int kind;
+    int depth;
+} cvb_json_section;
+int cvb_export_json(const char* path, const cvb_cell_columns* cols, const cvb_json_section* sections, int n_sections, int indent);
+
 /* ------------------------------------------------------------------------------------------------ operator level
  * The individual device operators, exposed for unit parity tests and for callers that want to compose them.
  * cvb_tc_epilogue mirrors TcEpilogue in cellvit_b200/csrc/tc_gemm.h (see that header for field semantics). */

@@ -49,6 +49,10 @@ def import_reference(watershed_fn=None):
         cellvit = importlib.import_module("models.segmentation.cell_segmentation.cellvit")
         post = importlib.import_module("cell_segmentation.utils.post_proc_cellvit")
     warnings.warn = saved_warn
+    if watershed_fn is not None:
+        # the module binds `watershed` by name at import time (post_proc_cellvit.py:20): rebind it, so that a module that was
+        # already imported with another flood (another test module ran first) calls the one asked for here
+        post.watershed = watershed_fn
     return cellvit, post
 
 

@@ -8,6 +8,7 @@ import torch
 
 from cellvit_b200 import synth, weights
 from cellvit_b200 import wsi_merge as wm
+from cellvit_b200.wsi_datamodel import load_cell_graph
 
 pytestmark = pytest.mark.gpu
 
@@ -133,7 +134,7 @@ def test_process_wsi_end_to_end(tmp_path):
         assert (outdir / f).exists(), f
     cells = json.load(open(outdir / "cells.json"))
     assert cells["processed_patches"] == ["0_0", "0_1", "1_0", "1_1"] and len(cells["cells"]) == len(out["cells"]) > 1000
-    graph = torch.load(outdir / "cells.pt", weights_only=False)
+    graph = load_cell_graph(outdir / "cells.pt")
     n = len(cells["cells"])
     assert tuple(graph.x.shape) == (n, 384) and tuple(graph.positions.shape) == (n, 2) and len(graph.contours) == n
     assert torch.isfinite(graph.x).all()

@@ -10,6 +10,7 @@ import pytest
 import torch
 
 from cellvit_b200 import wsi_merge as wm
+from cellvit_b200.wsi_datamodel import load_cell_graph
 
 REF = "/root/reference/cell_segmentation/inference/cell_detection.py"
 
@@ -212,6 +213,7 @@ import gzip, json, pathlib, sys, torch, torch.distributed as dist
 sys.path.insert(0, sys.argv[1]); sys.path.insert(0, sys.argv[1] + "/tests")
 from oracle import wsi_fixture as wf
 from wsi_host_harness import run_host_process_wsi
+from cellvit_b200.wsi_datamodel import load_cell_graph
 dist.init_process_group("gloo")
 rank = dist.get_rank()
 root = pathlib.Path(sys.argv[2])
@@ -222,7 +224,7 @@ if rank == 0:
     cells = json.load(open(out_dir / "cells.json"))
     assert cells["processed_patches"] == golden["processed_patches"] and cells["cells"] == golden["cells"]
     assert out["cells"] == golden["cells"]
-    graph = torch.load(out_dir / "cells.pt", weights_only=False)
+    graph = load_cell_graph(out_dir / "cells.pt")
     assert graph.x.shape[0] == len(golden["cells"]) == len(graph.contours)
     assert graph.positions.tolist() == [[float(torch.tensor(v, dtype=torch.float32)) for v in c["centroid"]] for c in golden["cells"]]
 else:
@@ -265,7 +267,7 @@ def test_process_wsi_on_a_slide_without_cells(tmp_path):
     for name in ("cells.json", "cell_detection.json", "cells.geojson", "cell_detection.geojson"):
         data = json.load(open(out_dir / name))
         assert (data["cells"] if isinstance(data, dict) else data) == []
-    graph = torch.load(out_dir / "cells.pt", weights_only=False)
+    graph = load_cell_graph(out_dir / "cells.pt")
     assert graph.x.shape[0] == 0 and graph.positions.shape[0] == 0 and list(graph.contours) == []
 
 

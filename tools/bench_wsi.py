@@ -77,7 +77,7 @@ out = inf.process_wsi(wsi, subdir_name="run", batch_size=B, geojson=True, num_wo
 torch.cuda.synchronize()
 dt = time.perf_counter() - t0
 if rank == 0:
-    print(json.dumps({"tiles": G * G, "n_gpus": world, "uint8_tiles": U8, "cells": len(out["cells"]), "seconds": dt, "tiles_per_s": G * G / dt,
+    print(json.dumps({"tiles": G * G, "n_gpus": world, "uint8_tiles": U8, "cells": len(out.columns), "seconds": dt, "tiles_per_s": G * G / dt,
                       "phases_s": inf.last_timings, "note": "process_wsi incl. PNG decode, head-override host prep, dedup, JSON/GeoJSON/graph export"}))
 if world > 1:
     dist.barrier()
