@@ -16,7 +16,7 @@ _LIB = None
 # enums of csrc/tc_gemm.h
 EPI_F16, EPI_RES_F32, EPI_CONVT, EPI_HEAD = 0, 1, 2, 3
 ACT_NONE, ACT_RELU, ACT_GELU = 0, 1, 2
-ROW_IDENTITY, ROW_SEQ, ROW_WINDOW = 0, 1, 2
+ROW_IDENTITY, ROW_SEQ, ROW_WINDOW, ROW_TO_WINDOW = 0, 1, 2, 3
 
 
 class TcEpilogue(C.Structure):

@@ -32,6 +32,11 @@ struct cvb_model {
     // canvas (see forward_impl). 0 (default) = each dimension extended on its own (a 272 x 400 tile runs on 512 x 512, a 208 x 1024
     // tile on 256 x 1024); 1 = both dimensions extended to the larger canvas edge (ablation / fallback)
     int square_canvas = 0;
+    // option "window_pad_skip": 1 (default) = the QKV GEMM of a windowed block runs over the real tokens only (LayerNorm in raster
+    // order, rows scattered into window order by the epilogue, the padding rows filled with the bias they would compute to);
+    // 0 = the GEMM runs over all window-partitioned rows incl. the zero padding (16 % more rows on a 64 x 64 grid; ablation).
+    // Bit-identical results.
+    int window_pad_skip = 1;
 };
 
 namespace {
@@ -199,11 +204,17 @@ int forward_impl(cvb_model& m, const float* x, int B, int H, int W, float* o_np,
         const int rows = win ? B * Tw : B * Tx;
         const float* n1w = f.P<float>(p + ".n1.w");
         const float* n1b = f.P<float>(p + ".n1.b");
-        if (f.live()) f.chk(op_layernorm_f16(xs, n1w, n1b, 1e-6f, rows, D, ln, win ? 1 : 0, B, h, w, ws, g, st));
+        // Windowed blocks pad the token grid to a multiple of 14 AFTER norm1 (image_encoder.py:180-184): the padding rows of the
+        // QKV input are zeros, so their QKV rows equal the bias. The GEMM therefore runs over the B*T real tokens in raster order
+        // and its epilogue scatters them to their window-partitioned rows; the padding rows are filled with the bias.
+        const bool pad_skip = win && m.window_pad_skip && Tw != T;
+        if (f.live()) f.chk(op_layernorm_f16(xs, n1w, n1b, 1e-6f, pad_skip ? B * Tx : rows, D, ln, (win && !pad_skip) ? 1 : 0, B, h, w, ws, g, st));
         {
             TcEpilogue e = Fwd::epi0();
             e.kind = TC_EPI_F16; e.out = qkv; e.ldc = 3 * D; e.shift = f.P<float>(p + ".qkv.b");
-            f.gemm(ln, rows, D, p + ".qkv.w", 3 * D, e);
+            if (pad_skip) { e.row_map = TC_ROW_TO_WINDOW; e.win_size = ws; e.win_grid = g; e.tok_h = h; e.tok_w = w; }
+            f.gemm(ln, pad_skip ? B * Tx : rows, D, p + ".qkv.w", 3 * D, e);
+            if (pad_skip && f.live()) f.chk(op_window_pad_fill(qkv, e.shift, B, 3 * D, h, w, ws, g, st));
         }
         const int Gb = win ? B * g * g : B, S = win ? ws * ws : Tx, gh = win ? ws : h, gw = win ? ws : w;
         const __half* th = sam ? f.P<__half>(p + ".relh") : nullptr;
@@ -440,6 +451,10 @@ CVB_API int cvb_model_set_option(cvb_model* m, const char* name, int value) {
     }
     if (std::string(name) == "square_canvas") {
         m->square_canvas = value != 0;
+        return CVB_OK;
+    }
+    if (std::string(name) == "window_pad_skip") {
+        m->window_pad_skip = value != 0;
         return CVB_OK;
     }
     cvb_set_error("cvb_model_set_option: unknown option '%s'", name);

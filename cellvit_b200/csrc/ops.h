@@ -44,6 +44,11 @@ int op_tokens_nchw(const float* x, int B, int T_src, int skip, int D, float* out
 int op_stem_conv(const float* x, int B, int H, int W, const float* w, const float* scale, const float* shift,
                  __half* out, int cpad, cudaStream_t stream);
 
+// Padding rows of a window-partitioned fp16 matrix [B*g*g*ws*ws, N] <- bias (fp32 [N], rounded to fp16): the value a Linear layer
+// has on the all-zero rows the reference pads with after norm1 (image_encoder.py:180-184), so that the QKV GEMM of a windowed
+// block only runs over the real tokens (TC_ROW_TO_WINDOW scatters its rows into window order). Real rows are not touched.
+int op_window_pad_fill(__half* out, const float* bias, int B, int N, int tok_h, int tok_w, int ws, int g, cudaStream_t stream);
+
 // Canvas helpers (model.cu: tiles whose token grid is not a native grid of the tile engine run the decoder on a
 // zero-extended canvas). copy_planes: dst[p][y][x] = (y < sH && x < sW) ? src[p][y][x] : 0 over `planes` planes of
 // elements of 1, 4 or 16 bytes (crop when dst is smaller, zero-extending embed when larger).

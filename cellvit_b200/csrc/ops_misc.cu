@@ -369,6 +369,26 @@ int grid_for(long long work_items, int block) {
 }
 
 
+// Rows of a window-partitioned fp16 matrix [B, g*g windows, ws*ws tokens][N] that are PADDING (token outside the tok_h x tok_w
+// grid) <- the per-column constant `bias`: what a Linear layer gives for the all-zero rows that the reference pads with
+// AFTER norm1 (image_encoder.py:180-184, 263-288) -- so the GEMM itself only has to run over the real tokens.
+__global__ void __launch_bounds__(256)
+window_pad_fill_kernel(__half* __restrict__ out, const float* __restrict__ bias, int rows, int N, int tok_h, int tok_w, int ws, int g) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= rows) return;
+    const int per_img = g * g * ws * ws;
+    const int rem = warp % per_img;
+    const int win = rem / (ws * ws), t = rem - win * ws * ws;
+    const int y = (win / g) * ws + t / ws, x = (win % g) * ws + t % ws;
+    if (y < tok_h && x < tok_w) return;
+    __half* o = out + (long long)warp * N;
+    for (int i = lane * 8; i < N; i += 256) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(bias + i));
+        const float4 d = __ldg(reinterpret_cast<const float4*>(bias + i + 4));
+        *reinterpret_cast<uint4*>(o + i) = make_uint4(pack_h2(a.x, a.y), pack_h2(a.z, a.w), pack_h2(d.x, d.y), pack_h2(d.z, d.w));
+    }
+}
+
 // ------------------------------------------------------------------------------------------ canvas helpers
 // Tiles whose token grid is not one of the tile engine's native grids run their decoder on a zero-extended canvas
 // (model.cu): planes are embedded top-left into the canvas, every layer's margin is re-zeroed (so that the next 3x3
@@ -459,6 +479,17 @@ int op_tokens_nchw(const float* x, int B, int T_src, int skip, int D, float* out
     return CVB_OK;
 }
 
+
+int op_window_pad_fill(__half* out, const float* bias, int B, int N, int tok_h, int tok_w, int ws, int g, cudaStream_t stream) {
+    CVB_CHECK(out && bias && B > 0 && N % 8 == 0 && ws > 0 && g > 0 && (((uintptr_t)out | (uintptr_t)bias) & 15) == 0, CVB_EARG,
+              "window_pad_fill: bad arguments");
+    if (g * ws == tok_h && g * ws == tok_w) return CVB_OK;  // no padding
+    const int rows = B * g * g * ws * ws;
+    window_pad_fill_kernel<<<cdiv(rows, 8), 256, 0, stream>>>(out, bias, rows, N, tok_h, tok_w, ws, g);
+    cvb_note_launches(1);
+    CVB_CUDA(cudaGetLastError());
+    return CVB_OK;
+}
 
 int op_copy_planes(const void* src, int sH, int sW, void* dst, int dH, int dW, long long planes, int elem_bytes, cudaStream_t stream) {
     CVB_CHECK(src && dst && sH > 0 && sW > 0 && dH > 0 && dW > 0 && planes > 0, CVB_EARG, "copy_planes: bad arguments");

@@ -60,9 +60,17 @@ __device__ __forceinline__ void head_smem_fill(float* hs, const TcEpilogue& e, i
 __device__ __forceinline__ int map_out_row(const TcEpilogue& e, int m) {
     if (e.row_map == TC_ROW_IDENTITY) return m;
     if (e.row_map == TC_ROW_SEQ) return m + (m / e.row_seq) * e.row_pad + e.row_off;
-    // TC_ROW_WINDOW (image_encoder.py:291-318 window_unpartition)
     const int ws = e.win_size, g = e.win_grid;
     const int per_img = g * g * ws * ws;
+    if (e.row_map == TC_ROW_TO_WINDOW) {  // image_encoder.py:263-288 window_partition of raster row m
+        const int hw = e.tok_h * e.tok_w;
+        const int b = m / hw;
+        const int rem = m - b * hw;
+        const int y = rem / e.tok_w, x = rem - y * e.tok_w;
+        const int wy = y / ws, wx = x / ws;
+        return b * per_img + (wy * g + wx) * ws * ws + (y - wy * ws) * ws + (x - wx * ws);
+    }
+    // TC_ROW_WINDOW (image_encoder.py:291-318 window_unpartition)
     const int b = m / per_img;
     int rem = m - b * per_img;
     const int win = rem / (ws * ws);
@@ -819,7 +827,7 @@ int check_epilogue(const TcEpilogue& e, int N, int block_n) {
         CVB_CHECK(N == 64 && block_n == 64 && e.head_nc >= 1 && e.head_nc <= 8 && e.head_out && e.head_w && e.head_b &&
                       e.scale && e.shift,
                   CVB_ESHAPE, "tc: HEAD epilogue needs N == 64, 1..8 classes, scale and shift");
-    if (e.row_map == TC_ROW_WINDOW)
+    if (e.row_map == TC_ROW_WINDOW || e.row_map == TC_ROW_TO_WINDOW)
         CVB_CHECK(e.win_size > 0 && e.win_grid > 0 && e.tok_h > 0 && e.tok_w > 0, CVB_EARG, "tc: bad window map");
     if (e.row_map == TC_ROW_SEQ) CVB_CHECK(e.row_seq > 0, CVB_EARG, "tc: bad seq map");
     return CVB_OK;

@@ -13,6 +13,8 @@ enum TcRowMap {
     TC_ROW_IDENTITY = 0,
     TC_ROW_SEQ = 1,     // out row = m + (m / row_seq) * row_pad + row_off          (ViT-256 cls-token slot)
     TC_ROW_WINDOW = 2,  // m indexes window-partitioned tokens; out row = (b,y,x) raster, padded tokens dropped
+    TC_ROW_TO_WINDOW = 3,  // m indexes (b,y,x) raster tokens; out row = their window-partitioned position (window_partition,
+                           // image_encoder.py:263-288) -- the padded rows in between are not touched
 };
 
 // Plain-old-data: mirrored field by field by ctypes in tests (cellvit_b200/_lib.py).
@@ -29,7 +31,7 @@ struct TcEpilogue {
     int res_off;
     int row_map;         // TcRowMap
     int row_seq, row_pad, row_off;
-    int win_size, win_grid, tok_h, tok_w;  // TC_ROW_WINDOW: window edge, windows per side, token grid
+    int win_size, win_grid, tok_h, tok_w;  // TC_ROW_WINDOW / TC_ROW_TO_WINDOW: window edge, windows per side, token grid
     int ct_cout, ct_hin, ct_win;           // CONVT geometry (input grid)
     const float* head_w;                   // HEAD: [nc, 64]
     const float* head_b;                   // HEAD: [nc]

@@ -170,3 +170,20 @@ def test_process_tiles_on_a_non_native_tile_size_matches_oracle():
                 assert np.array_equal(gv["bbox"], ov["bbox"]) and np.array_equal(gv["centroid"], ov["centroid"])
                 assert np.array_equal(gv["contour"], ov["contour"]) and gv["type"] == ov["type"] and gv["type_prob"] == ov["type_prob"]
             assert toks[b].shape == (len(odict), 384)
+
+
+@pytest.mark.parametrize("arch,size", [("SAM-B", 256), ("SAM-H", 400)])
+def test_window_pad_skip_gives_the_same_forward(arch, size):
+    """The QKV GEMM of the windowed blocks runs over the real tokens only (rows scattered into window order by the epilogue,
+    padding rows = bias): same maps as running it over the zero-padded window-partitioned rows (image_encoder.py:180-184)."""
+    sd, m = _model(arch)
+    x = torch.from_numpy(synth.synthetic_tiles(2, size, seed=4)).cuda()
+    with torch.no_grad():
+        a = m(x, retrieve_tokens=True)
+        m.set_engine_option("window_pad_skip", 0)
+        b = m(x, retrieve_tokens=True)
+    torch.cuda.synchronize()
+    for k in ("nuclei_binary_map", "hv_map", "nuclei_type_map", "tissue_types", "tokens"):
+        d = (a[k] - b[k]).abs().max().item()
+        print(k, "max abs difference", d, "bit-equal", torch.equal(a[k], b[k]))
+        assert d <= 1e-5 * max(1.0, b[k].abs().max().item()), (k, d)
