@@ -32,10 +32,10 @@ struct cvb_model {
     // canvas (see forward_impl). 0 (default) = each dimension extended on its own (a 272 x 400 tile runs on 512 x 512, a 208 x 1024
     // tile on 256 x 1024); 1 = both dimensions extended to the larger canvas edge (ablation / fallback)
     int square_canvas = 0;
-    // option "window_pad_skip": 1 (default) = the QKV GEMM of a windowed block runs over the real tokens only (LayerNorm in raster
-    // order, rows scattered into window order by the epilogue, the padding rows filled with the bias they would compute to);
-    // 0 = the GEMM runs over all window-partitioned rows incl. the zero padding (16 % more rows on a 64 x 64 grid; ablation).
-    // Bit-identical results.
+    // option "window_pad_skip": 1 (default) = the QKV and attn-out GEMMs of a windowed block run over the real tokens only (QKV:
+    // LayerNorm in raster order, rows scattered into window order by the epilogue, the padding rows filled with the bias they would
+    // compute to; attn-out: the tcgen05 window attention writes its output un-partitioned); 0 = both GEMMs run over all
+    // window-partitioned rows incl. the zero padding (16 % more rows on a 64 x 64 grid; ablation). Same results.
     int window_pad_skip = 1;
 };
 
@@ -216,12 +216,16 @@ int forward_impl(cvb_model& m, const float* x, int B, int H, int W, float* o_np,
             f.gemm(ln, pad_skip ? B * Tx : rows, D, p + ".qkv.w", 3 * D, e);
             if (pad_skip && f.live()) f.chk(op_window_pad_fill(qkv, e.shift, B, 3 * D, h, w, ws, g, st));
         }
+        // ... and the tcgen05 window attention writes its output un-partitioned (raster order, padding rows dropped), so that the
+        // attn-out projection runs over the real tokens only as well
+        const bool att_raster = pad_skip && win_tc;
         const int Gb = win ? B * g * g : B, S = win ? ws * ws : Tx, gh = win ? ws : h, gw = win ? ws : w;
         const __half* th = sam ? f.P<__half>(p + ".relh") : nullptr;
         const __half* tw = sam ? f.P<__half>(p + ".relw") : nullptr;
         if (f.live()) {
             if (attn_tc && !win) f.chk(op_attention_tc(qkv, Gb, S, heads, hd, scale, th, tw, gh, gw, att, attn_ws, attn_ws_bytes, st));
-            else if (win_tc && win) f.chk(op_window_attention_tc(qkv, Gb, heads, hd, scale, f.P<__half>(p + ".relcat"), att, f.next_counter(), st));
+            else if (win_tc && win) f.chk(op_window_attention_tc(qkv, Gb, heads, hd, scale, f.P<__half>(p + ".relcat"), att, f.next_counter(), st,
+                                                                 att_raster ? g : 0, h, w));
             else f.chk(op_attention(qkv, Gb, S, heads, hd, scale, th, tw, gh, gw, att, st));
         }
         {
@@ -230,12 +234,12 @@ int forward_impl(cvb_model& m, const float* x, int B, int H, int W, float* o_np,
             // the main loop (131 -> 69 us per launch), unlike lin2 (K = 5120) which keeps the fp32 residual epilogue.
             TcEpilogue e = Fwd::epi0();
             e.kind = TC_EPI_F16; e.out = ybuf; e.ldc = D; e.shift = f.P<float>(p + ".proj.b");
-            f.gemm(att, rows, D, p + ".proj.w", D, e);
+            f.gemm(att, att_raster ? B * Tx : rows, D, p + ".proj.w", D, e);
         }
         const float* n2w = f.P<float>(p + ".n2.w");
         const float* n2b = f.P<float>(p + ".n2.b");
         {
-            LnFuse lf{ybuf, win ? 1 : 0, xs, nullptr, 0, Tx, 1};
+            LnFuse lf{ybuf, (win && !att_raster) ? 1 : 0, xs, nullptr, 0, Tx, 1};
             if (f.live()) f.chk(op_residual_ln(xs, lf, n2w, n2b, 1e-6f, B * Tx, D, ln, 0, B, h, w, ws, g, st));
         }
         {

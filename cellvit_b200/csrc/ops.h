@@ -94,5 +94,7 @@ int op_attention_tc(const __half* qkv, int Gb, int S, int heads, int hd, float s
 // (packing.py), out fp16 [n_items*196, D].
 bool op_window_attention_tc_supported(int S, int hd, int gh, int gw);
 // sched_counter: optional device int, zero at launch: the (window, head) items are then claimed dynamically (SchedRing).
+// un_g > 0: the output is written UN-PARTITIONED (window_unpartition, image_encoder.py:291-318): out fp16 [B*un_h*un_w, D] in raster
+// token order for un_g x un_g windows per image over an un_h x un_w token grid, rows of padding tokens dropped.
 int op_window_attention_tc(const __half* qkv, int n_items, int heads, int hd, float scale, const __half* relcat, __half* out,
-                           int* sched_counter, cudaStream_t stream);
+                           int* sched_counter, cudaStream_t stream, int un_g = 0, int un_h = 0, int un_w = 0);

@@ -58,7 +58,8 @@ __device__ __forceinline__ void barrel14(const uint32_t (&p)[15], int s, uint32_
 __global__ void __launch_bounds__(W_THREADS, 1)
 window_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                  const __grid_constant__ CUtensorMap tmK16, const __grid_constant__ CUtensorMap tmR, int heads, int n_items,
-                 float scale, __half* __restrict__ out, int* __restrict__ sched_counter, int skew_clocks, long long* __restrict__ trace) {
+                 float scale, __half* __restrict__ out, int* __restrict__ sched_counter, int skew_clocks, long long* __restrict__ trace,
+                 int un_g, int un_h, int un_w) {
     extern __shared__ uint8_t w_smem_raw[];
     const uint32_t smem_base = (ptx::smem_u32(w_smem_raw) + 1023u) & ~1023u;
     uint8_t* smem_gen = w_smem_raw + (smem_base - ptx::smem_u32(w_smem_raw));
@@ -420,9 +421,19 @@ window_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                 ptx::tc_fence_before();
                 const float inv = 1.0f / fl(l16[0]);
                 auto f = [&](uint32_t u) { return __uint_as_float(u) * inv; };
-                if (row_ok) {
+                // output row: window order (item, token), or -- un_g > 0 -- the token's raster row in the un_h x un_w grid of its
+                // image (window_unpartition, image_encoder.py:291-318), padding tokens dropped
+                long long orow = (long long)item * W_S + qi;
+                bool st_ok = row_ok;
+                if (un_g > 0) {
+                    const int per = un_g * un_g, b = item / per, wi = item - b * per;
+                    const int y = (wi / un_g) * W_G + qi / W_G, x = (wi % un_g) * W_G + qi % W_G;
+                    st_ok = row_ok && y < un_h && x < un_w;
+                    orow = ((long long)b * un_h + y) * un_w + x;
+                }
+                if (st_ok) {
                     // each thread owns 96 / 64 contiguous bytes of its row: 32-byte stores (one full sector per request)
-                    __half* dst = out + ((long long)item * W_S + qi) * D + head * W_HD + (half == 0 ? 0 : 48);
+                    __half* dst = out + orow * D + head * W_HD + (half == 0 ? 0 : 48);
                     auto st32 = [&](__half* ptr, const uint32_t* d) {
                         asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(ptr), "r"(pack_h2(f(d[0]), f(d[1]))),
                                      "r"(pack_h2(f(d[2]), f(d[3]))), "r"(pack_h2(f(d[4]), f(d[5]))), "r"(pack_h2(f(d[6]), f(d[7]))),
@@ -453,8 +464,10 @@ extern "C" __attribute__((visibility("default"))) void cvb_debug_window_trace(vo
 bool op_window_attention_tc_supported(int S, int hd, int gh, int gw) { return hd == W_HD && S == W_S && gh == W_G && gw == W_G; }
 
 int op_window_attention_tc(const __half* qkv, int n_items, int heads, int hd, float scale, const __half* relcat, __half* out,
-                           int* sched_counter, cudaStream_t stream) {
+                           int* sched_counter, cudaStream_t stream, int un_g, int un_h, int un_w) {
     CVB_CHECK(qkv && out && relcat, CVB_EARG, "window_attention_tc: null operand");
+    CVB_CHECK(un_g == 0 || (un_g > 0 && n_items % (un_g * un_g) == 0 && un_h > 0 && un_w > 0 && un_h <= un_g * W_G && un_w <= un_g * W_G),
+              CVB_EARG, "window_attention_tc: bad un-partition geometry");
     CVB_CHECK(hd == W_HD && n_items > 0 && heads > 0, CVB_ESHAPE, "window_attention_tc: needs head dim 80");
     const int D = heads * hd;
     static unsigned long long configured = 0;  // one bit per device: function attributes are per device
@@ -471,7 +484,7 @@ int op_window_attention_tc(const __half* qkv, int n_items, int heads, int hd, fl
     CVB_TRY(cvb_tmap_2d_f16(&tr, relcat, (uint64_t)W_HD, 64, (uint64_t)W_HD * 2, 64, 64));
     const int n_work = n_items * heads;
     const int grid = n_work < cvb_num_sms() ? n_work : cvb_num_sms();
-    window_tc_kernel<<<grid, W_THREADS, W_SMEM, stream>>>(tq, tk, tk16, tr, heads, n_items, scale, out, sched_counter, g_window_skew, g_window_trace);
+    window_tc_kernel<<<grid, W_THREADS, W_SMEM, stream>>>(tq, tk, tk16, tr, heads, n_items, scale, out, sched_counter, g_window_skew, g_window_trace, un_g, un_h, un_w);
     cvb_note_launches(1);
     CVB_CUDA(cudaGetLastError());
     return CVB_OK;
