@@ -44,29 +44,32 @@ def shard_indices(n_tiles: int, rank: int, world_size: int) -> List[int]:
     return list(range(rank, n_tiles, world_size))
 
 
-def model_from_checkpoint(checkpoint: dict) -> Union[CellViT, CellViT256, CellViTSAM]:
-    """cell_detection.py:131-211: ``{"arch", "config" (flattened), "model_state_dict"}`` -> eval-mode model."""
+def model_from_checkpoint(checkpoint: dict):
+    """cell_detection.py:131-211: ``{"arch", "config" (flattened), "model_state_dict"}`` -> eval-mode model. All six
+    architectures of the reference's ``__get_model``. (There, a ``CellViT256Shared`` checkpoint dies with ``UnboundLocalError``
+    because of a misspelt name test at :192; here it loads.)"""
+    from .cellvit import CellViT256Shared, CellViTSAMShared, CellViTShared
     run_conf = unflatten_dict(checkpoint["config"], ".")
     arch = checkpoint["arch"]
-    implemented = ["CellViT", "CellViT256", "CellViTSAM"]
-    if arch in ("CellViTShared", "CellViT256Shared", "CellViTSAMShared"):
-        raise NotImplementedError(f"{arch}: the shared-decoder variants of the reference's get_model (cell_detection.py:131-211) are not built "
-                                  f"in cellvit_b200; supported architectures: {implemented}")
+    implemented = ["CellViT", "CellViTShared", "CellViT256", "CellViT256Shared", "CellViTSAM", "CellViTSAMShared"]
     if arch not in implemented:
         raise NotImplementedError(f"Unknown model type. Please select one of {implemented}")
     data, mconf = run_conf["data"], run_conf.get("model", {})
-    if arch == "CellViT":
-        model = CellViT(num_nuclei_classes=data["num_nuclei_classes"], num_tissue_classes=data["num_tissue_classes"],
-                        embed_dim=mconf["embed_dim"], input_channels=mconf.get("input_channels", 3), depth=mconf["depth"],
-                        num_heads=mconf["num_heads"], extract_layers=mconf["extract_layers"],
-                        regression_loss=mconf.get("regression_loss", False))
-    elif arch == "CellViT256":
-        model = CellViT256(model256_path=None, num_nuclei_classes=data["num_nuclei_classes"],
-                           num_tissue_classes=data["num_tissue_classes"], regression_loss=mconf.get("regression_loss", False))
+    if arch in ("CellViT", "CellViTShared"):
+        cls = CellViT if arch == "CellViT" else CellViTShared
+        model = cls(num_nuclei_classes=data["num_nuclei_classes"], num_tissue_classes=data["num_tissue_classes"],
+                    embed_dim=mconf["embed_dim"], input_channels=mconf.get("input_channels", 3), depth=mconf["depth"],
+                    num_heads=mconf["num_heads"], extract_layers=mconf["extract_layers"],
+                    regression_loss=mconf.get("regression_loss", False))
+    elif arch in ("CellViT256", "CellViT256Shared"):
+        cls = CellViT256 if arch == "CellViT256" else CellViT256Shared
+        model = cls(model256_path=None, num_nuclei_classes=data["num_nuclei_classes"],
+                    num_tissue_classes=data["num_tissue_classes"], regression_loss=mconf.get("regression_loss", False))
     else:
-        model = CellViTSAM(model_path=None, num_nuclei_classes=data["num_nuclei_classes"],
-                           num_tissue_classes=data["num_tissue_classes"], vit_structure=mconf["backbone"],
-                           regression_loss=mconf.get("regression_loss", False))
+        cls = CellViTSAM if arch == "CellViTSAM" else CellViTSAMShared
+        model = cls(model_path=None, num_nuclei_classes=data["num_nuclei_classes"],
+                    num_tissue_classes=data["num_tissue_classes"], vit_structure=mconf["backbone"],
+                    regression_loss=mconf.get("regression_loss", False))
     model.load_state_dict(checkpoint["model_state_dict"])
     model.eval()
     return model, run_conf

@@ -27,7 +27,7 @@ class ModelDesc(C.Structure):
     _fields_ = [("sam", C.c_int), ("embed_dim", C.c_int), ("depth", C.c_int), ("num_heads", C.c_int),
                 ("window_size", C.c_int), ("n_global", C.c_int), ("global_idx", C.c_int * 8), ("extract", C.c_int * 4),
                 ("n_np_out", C.c_int), ("n_nt", C.c_int), ("n_tissue", C.c_int), ("skip11", C.c_int), ("skip12", C.c_int),
-                ("bott_pad", C.c_int)]
+                ("bott_pad", C.c_int), ("shared_decoder", C.c_int)]
 
 
 class _Node(nn.Module):
@@ -55,7 +55,7 @@ class CellViT(nn.Module):
     def __init__(self, num_nuclei_classes: int, num_tissue_classes: int, embed_dim: int, input_channels: int,
                  depth: int, num_heads: int, extract_layers: List, mlp_ratio: float = 4, qkv_bias: bool = True,
                  drop_rate: float = 0, attn_drop_rate: float = 0, drop_path_rate: float = 0,
-                 regression_loss: bool = False, _arch: str = "ViT256"):
+                 regression_loss: bool = False, _arch: str = "ViT256", _shared: bool = False):
         super().__init__()
         assert len(extract_layers) == 4, "Please provide 4 layers for skip connections"
         if input_channels != 3 or mlp_ratio != 4 or not qkv_bias:
@@ -78,10 +78,11 @@ class CellViT(nn.Module):
         self.branches_output = {"nuclei_binary_map": 2 + (2 if regression_loss else 0), "hv_map": 2,
                                 "nuclei_type_maps": num_nuclei_classes}
         self._arch = _arch
+        self._shared = bool(_shared)   # the *Shared variants (cellvit_shared.py): one decoder trunk, three 1x1 heads
         self._sam = _arch != "ViT256"
         self._global_idx = tuple(weights.SAM_CFG[_arch]["global_idx"]) if self._sam else ()
         spec = weights.state_spec(_arch, num_nuclei_classes, num_tissue_classes, regression_loss,
-                                  embed_dim=embed_dim, depth=depth, num_heads=num_heads)
+                                  embed_dim=embed_dim, depth=depth, num_heads=num_heads, shared=self._shared)
         _build_tree(self, spec, seed=int(torch.initial_seed() & 0xFFFF))
         self._handle = None
         self._packed = {}        # name -> device tensor (kept alive for the C side)
@@ -95,7 +96,8 @@ class CellViT(nn.Module):
     # ------------------------------------------------------------------ engine plumbing
     def _cfg(self):
         return dict(sam=self._sam, embed_dim=self.embed_dim, depth=self.depth, num_heads=self.num_heads, window=14,
-                    global_idx=self._global_idx, skip11=self.skip_dim_11, skip12=self.skip_dim_12, bott=self.bottleneck_dim)
+                    global_idx=self._global_idx, skip11=self.skip_dim_11, skip12=self.skip_dim_12, bott=self.bottleneck_dim,
+                    shared=self._shared)
 
     def _ensure_handle(self):
         if self._handle is None:
@@ -103,7 +105,7 @@ class CellViT(nn.Module):
                           window_size=14 if self._sam else 0, n_global=len(self._global_idx),
                           n_np_out=self.branches_output["nuclei_binary_map"], n_nt=self.num_nuclei_classes,
                           n_tissue=self.num_tissue_classes, skip11=self.skip_dim_11, skip12=self.skip_dim_12,
-                          bott_pad=packing.pad64(self.bottleneck_dim))
+                          bott_pad=packing.pad64(self.bottleneck_dim), shared_decoder=int(self._shared))
             for i, g in enumerate(self._global_idx):
                 d.global_idx[i] = g
             for i, e in enumerate(self.extract_layers):
@@ -330,3 +332,43 @@ class CellViTSAM(CellViT):
         own = self._modules["encoder"].state_dict()
         msg = self._modules["encoder"].load_state_dict({k: v for k, v in state_dict.items() if k in own}, strict=False)
         print(f"Loading checkpoint: {msg}")
+
+
+class CellViTShared(CellViT):
+    """cellvit_shared.py:23-331 -- CellViT with ONE shared upsampling trunk (``decoder.*``) and a 1x1 convolution per output
+    (``nuclei_binary_map_decoder``, ``hv_map_decoder``, ``nuclei_type_maps_decoder``) on its 64-channel feature map."""
+
+    def __init__(self, num_nuclei_classes: int, num_tissue_classes: int, embed_dim: int, input_channels: int, depth: int,
+                 num_heads: int, extract_layers: List, mlp_ratio: float = 4, qkv_bias: bool = True, drop_rate: float = 0,
+                 attn_drop_rate: float = 0, drop_path_rate: float = 0, regression_loss: bool = False, _arch: str = "ViT256"):
+        super().__init__(num_nuclei_classes, num_tissue_classes, embed_dim, input_channels, depth, num_heads, extract_layers,
+                         mlp_ratio, qkv_bias, drop_rate, attn_drop_rate, drop_path_rate, regression_loss, _arch=_arch, _shared=True)
+
+
+class CellViT256Shared(CellViTShared):
+    """cellvit_shared.py:333-393."""
+
+    def __init__(self, model256_path, num_nuclei_classes: int, num_tissue_classes: int, drop_rate: float = 0,
+                 attn_drop_rate: float = 0, drop_path_rate: float = 0, regression_loss: bool = False):
+        self.model256_path = model256_path
+        super().__init__(num_nuclei_classes, num_tissue_classes, 384, 3, 12, 6, [3, 6, 9, 12], 4, True, drop_rate, attn_drop_rate,
+                         drop_path_rate, regression_loss, _arch="ViT256")
+
+    load_pretrained_encoder = CellViT256.load_pretrained_encoder
+
+
+class CellViTSAMShared(CellViTShared):
+    """cellvit_shared.py:396-560."""
+
+    def __init__(self, model_path, num_nuclei_classes: int, num_tissue_classes: int, vit_structure, drop_rate: float = 0,
+                 regression_loss: bool = False):
+        if vit_structure.upper() not in weights.SAM_CFG:
+            raise NotImplementedError("Unknown ViT-SAM backbone structure")
+        cfg = weights.SAM_CFG[vit_structure.upper()]
+        self.model_path = model_path
+        super().__init__(num_nuclei_classes, num_tissue_classes, cfg["embed_dim"], 3, cfg["depth"], cfg["num_heads"],
+                         list(cfg["extract"]), 4, True, drop_rate, 0, 0, regression_loss, _arch=vit_structure.upper())
+        self.prompt_embed_dim = 256
+        self.encoder_global_attn_indexes = list(cfg["global_idx"])
+
+    load_pretrained_encoder = CellViTSAM.load_pretrained_encoder

@@ -328,10 +328,21 @@ int forward_impl(cvb_model& m, const float* x, int B, int H, int W, float* o_np,
     // the regression channels are present)
     struct Br { const char* name; float* out; int nc; uint8_t* arg; int arg_nc; };
     const Br branches[3] = {{"np", o_np, d.n_np_out, o_np_arg, 2}, {"hv", o_hv, 2, nullptr, 0}, {"nt", o_nt, d.n_nt, o_nt_arg, d.n_nt}};
+    // CellViT: one upsampling trunk per output. The *Shared variants (cellvit_shared.py:147-231): ONE trunk ("dec") whose 64-channel
+    // feature map feeds three 1x1 heads -- here the last trunk convolution (decoder0_header.1) runs once per head with that head
+    // fused into its epilogue, so the feature map is never written (the same launches as a CellViT branch tail).
+    const bool shared = d.shared_decoder != 0;
+    const int n_trunks = shared ? 1 : 3;
     const size_t mark = A.off;
-    for (const Br& br : branches) {
-        A.off = mark;  // branch activations reuse the same arena region (stream order serialises the branches)
-        const std::string n = br.name;
+    for (int t = 0; t < n_trunks; ++t) {
+        A.off = mark;  // trunk activations reuse the same arena region (stream order serialises the trunks)
+        const std::string n = shared ? "dec" : branches[t].name;
+        // a trunk none of whose outputs is asked for is not launched; its allocations still happen (the dry pass that sizes the
+        // workspace and the live pass must agree), which is what a temporarily "dry" arena does
+        bool wanted = false;
+        for (int k = 0; k < 3; ++k) wanted |= (shared || k == t) && branches[k].out != nullptr;
+        const bool saved_dry = A.dry;
+        if (!wanted) A.dry = true;
         __half* b = f.conv_t(z[3], D, B, hc, wc, n + ".bottleneck", bt);
         b = f.conv_bn_relu(s3, bt, b, bt, B, 2 * hc, 2 * wc, n + ".d3.0", bt);
         b = f.conv_bn_relu(b, bt, nullptr, 0, B, 2 * hc, 2 * wc, n + ".d3.1", bt);
@@ -344,25 +355,30 @@ int forward_impl(cvb_model& m, const float* x, int B, int H, int W, float* o_np,
         b = f.conv_bn_relu(b, 128, nullptr, 0, B, 8 * hc, 8 * wc, n + ".d1.1", 128);
         b = f.conv_t(b, 128, B, 8 * hc, 8 * wc, n + ".d1.ct", 64);
         b = f.conv_bn_relu(s0, 64, b, 64, B, Hc, Wc, n + ".d0.0", 64);
-        // canvas mode: the fused head writes canvas-sized planes, which are cropped to the caller's [.., H, W] outputs
-        float* head_out = br.out;
-        uint8_t* head_arg = br.arg;
-        if (canvas) {
-            head_out = A.alloc<float>((size_t)B * br.nc * Hc * Wc);
-            head_arg = A.alloc<uint8_t>((size_t)B * Hc * Wc);
-            if (!br.arg) head_arg = nullptr;
-        }
-        TcEpilogue e = Fwd::epi0();
-        e.kind = TC_EPI_HEAD;
-        e.scale = f.P<float>(n + ".d0.1.scale"); e.shift = f.P<float>(n + ".d0.1.shift");
-        e.head_w = f.P<float>(n + ".head.w"); e.head_b = f.P<float>(n + ".head.b");
-        e.head_nc = br.nc; e.head_hw = Hc * Wc; e.head_out = head_out; e.head_argmax = head_arg; e.head_argmax_nc = br.arg_nc;
-        const __half* wp = f.P<__half>(n + ".d0.1.w");
-        if (f.live() && br.out) {
-            f.chk(tc_conv3x3(b, 64, nullptr, 0, B, Hc, Wc, wp, 64, 64, f.with_counter(e), st));
+        A.dry = saved_dry;
+        for (int k = 0; k < 3; ++k) {
+            if (!shared && k != t) continue;
+            const Br& br = branches[k];
+            // canvas mode: the fused head writes canvas-sized planes, which are cropped to the caller's [.., H, W] outputs
+            float* head_out = br.out;
+            uint8_t* head_arg = br.arg;
             if (canvas) {
-                f.chk(op_copy_planes(head_out, Hc, Wc, br.out, H, W, (long long)B * br.nc, 4, st));
-                if (br.arg) f.chk(op_copy_planes(head_arg, Hc, Wc, br.arg, H, W, B, 1, st));
+                head_out = A.alloc<float>((size_t)B * br.nc * Hc * Wc);
+                head_arg = A.alloc<uint8_t>((size_t)B * Hc * Wc);
+                if (!br.arg) head_arg = nullptr;
+            }
+            TcEpilogue e = Fwd::epi0();
+            e.kind = TC_EPI_HEAD;
+            e.scale = f.P<float>(n + ".d0.1.scale"); e.shift = f.P<float>(n + ".d0.1.shift");
+            e.head_w = f.P<float>(std::string(br.name) + ".head.w"); e.head_b = f.P<float>(std::string(br.name) + ".head.b");
+            e.head_nc = br.nc; e.head_hw = Hc * Wc; e.head_out = head_out; e.head_argmax = head_arg; e.head_argmax_nc = br.arg_nc;
+            const __half* wp = f.P<__half>(n + ".d0.1.w");
+            if (f.live() && br.out) {
+                f.chk(tc_conv3x3(b, 64, nullptr, 0, B, Hc, Wc, wp, 64, 64, f.with_counter(e), st));
+                if (canvas) {
+                    f.chk(op_copy_planes(head_out, Hc, Wc, br.out, H, W, (long long)B * br.nc, 4, st));
+                    if (br.arg) f.chk(op_copy_planes(head_arg, Hc, Wc, br.arg, H, W, B, 1, st));
+                }
             }
         }
     }

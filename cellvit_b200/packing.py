@@ -88,7 +88,7 @@ def vit_pos(pos_embed, h, w, dim):
 
 
 def pack_static(sd, cfg):
-    """Size-independent tensors. cfg: dict(sam, embed_dim, depth, num_heads, window, global_idx, skip11, skip12, bott)."""
+    """Size-independent tensors. cfg: dict(sam, embed_dim, depth, num_heads, window, global_idx, skip11, skip12, bott[, shared])."""
     D, depth, sam = cfg["embed_dim"], cfg["depth"], cfg["sam"]
     bott, bt = cfg["bott"], pad64(cfg["bott"])
     s11, s12 = cfg["skip11"], cfg["skip12"]
@@ -130,16 +130,22 @@ def pack_static(sd, cfg):
         P[name + ".conv.w"] = pack_conv3x3(sd[ref + ".block.1.weight"].float(), [(cout, pad64(cout))], pad64(cout))
         P[name + ".conv.scale"], P[name + ".conv.shift"] = fold_bn(sd, ref + ".block.1", ref + ".block.2", pad64(cout))
 
-    P["decoder0.0.w"] = _f(sd["decoder0.0.block.0.weight"].reshape(32, 27))
-    P["decoder0.0.scale"], P["decoder0.0.shift"] = fold_bn(sd, "decoder0.0.block.0", "decoder0.0.block.1", 32)
-    conv_block("decoder0.1", "decoder0.1", [(32, 64)], 64)
-    deconv_block("decoder1.0", "decoder1.0", D, s11)
-    deconv_block("decoder1.1", "decoder1.1", s11, s12)
-    deconv_block("decoder1.2", "decoder1.2", s12, 128)
-    deconv_block("decoder2.0", "decoder2.0", D, s11)
-    deconv_block("decoder2.1", "decoder2.1", s11, 256)
-    deconv_block("decoder3.0", "decoder3.0", D, bott)
-    for n, ref in BRANCHES.items():
+    # reference module names of the four skip decoders and of the upsampling trunks: CellViT keeps the skips at the top level and
+    # one trunk per output (cellvit.py:116-151); the *Shared variants keep everything under ``decoder`` with ONE trunk and a
+    # 1x1 head per output (cellvit_shared.py:113-145, 231-330)
+    shared = bool(cfg.get("shared"))
+    sk = [f"decoder.decoder{k}_skip" for k in range(4)] if shared else [f"decoder{k}" for k in range(4)]
+    P["decoder0.0.w"] = _f(sd[sk[0] + ".0.block.0.weight"].reshape(32, 27))
+    P["decoder0.0.scale"], P["decoder0.0.shift"] = fold_bn(sd, sk[0] + ".0.block.0", sk[0] + ".0.block.1", 32)
+    conv_block(sk[0] + ".1", "decoder0.1", [(32, 64)], 64)
+    deconv_block(sk[1] + ".0", "decoder1.0", D, s11)
+    deconv_block(sk[1] + ".1", "decoder1.1", s11, s12)
+    deconv_block(sk[1] + ".2", "decoder1.2", s12, 128)
+    deconv_block(sk[2] + ".0", "decoder2.0", D, s11)
+    deconv_block(sk[2] + ".1", "decoder2.1", s11, 256)
+    deconv_block(sk[3] + ".0", "decoder3.0", D, bott)
+    trunks = {"dec": "decoder"} if shared else BRANCHES
+    for n, ref in trunks.items():
         def ct(src, dst, cin, cout):
             P[f"{n}.{dst}.w"], P[f"{n}.{dst}.b"] = pack_conv_t(sd[f"{ref}.{src}.weight"].float(), sd[f"{ref}.{src}.bias"].float(),
                                                                pad64(cin), pad64(cout))
@@ -156,9 +162,11 @@ def pack_static(sd, cfg):
         ct("decoder1_upsampler.2", "d1.ct", 128, 64)
         conv_block(f"{ref}.decoder0_header.0", f"{n}.d0.0", [(64, 64), (64, 64)], 64)
         conv_block(f"{ref}.decoder0_header.1", f"{n}.d0.1", [(64, 64)], 64)
-        hw = sd[f"{ref}.decoder0_header.2.weight"]
+    for n, ref in BRANCHES.items():   # the 1x1 heads
+        key = ref if shared else f"{ref}.decoder0_header.2"
+        hw = sd[key + ".weight"]
         P[f"{n}.head.w"] = _f(hw.reshape(hw.shape[0], 64))
-        P[f"{n}.head.b"] = _f(sd[f"{ref}.decoder0_header.2.bias"])
+        P[f"{n}.head.b"] = _f(sd[key + ".bias"])
     return P
 
 

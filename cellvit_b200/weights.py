@@ -39,9 +39,10 @@ def decoder_dims(embed_dim: int):
 
 
 def state_spec(arch: str, num_nuclei_classes: int, num_tissue_classes: int, regression_loss: bool = False,
-               embed_dim=None, depth=None, num_heads=None):
+               embed_dim=None, depth=None, num_heads=None, shared: bool = False):
     """OrderedDict key -> (shape, kind); kind in {w_lin, w_conv, w_convT, bias, ln_w, ln_b, bn_w, bn_b,
-    bn_mean, bn_var, bn_nbt, pos, cls, relpos}."""
+    bn_mean, bn_var, bn_nbt, pos, cls, relpos}. ``shared``: the ``*Shared`` variants (cellvit_shared.py:113-145, 231-330) --
+    ONE decoder trunk under ``decoder.*`` and a 1x1 convolution per output on its 64-channel feature map."""
     cfg = arch_config(arch)
     D = embed_dim or cfg["embed_dim"]
     depth = depth or cfg["depth"]
@@ -118,17 +119,20 @@ def state_spec(arch: str, num_nuclei_classes: int, num_tissue_classes: int, regr
             lin("encoder.head", D, num_tissue_classes)
 
     s11, s12, bd = decoder_dims(D)
-    conv_block("decoder0.0", 3, 32)
-    conv_block("decoder0.1", 32, 64)
-    deconv_block("decoder1.0", D, s11)
-    deconv_block("decoder1.1", s11, s12)
-    deconv_block("decoder1.2", s12, 128)
-    deconv_block("decoder2.0", D, s11)
-    deconv_block("decoder2.1", s11, 256)
-    deconv_block("decoder3.0", D, bd)
     nb_out = 2 + (2 if regression_loss else 0)
-    for name, ncls in (("nuclei_binary_map_decoder", nb_out), ("hv_map_decoder", 2),
-                       ("nuclei_type_maps_decoder", num_nuclei_classes)):
+    heads = (("nuclei_binary_map_decoder", nb_out), ("hv_map_decoder", 2), ("nuclei_type_maps_decoder", num_nuclei_classes))
+
+    def skips(names):
+        conv_block(names[0] + ".0", 3, 32)
+        conv_block(names[0] + ".1", 32, 64)
+        deconv_block(names[1] + ".0", D, s11)
+        deconv_block(names[1] + ".1", s11, s12)
+        deconv_block(names[1] + ".2", s12, 128)
+        deconv_block(names[2] + ".0", D, s11)
+        deconv_block(names[2] + ".1", s11, 256)
+        deconv_block(names[3] + ".0", D, bd)
+
+    def upsampling(name, ncls):
         convT(f"{name}.bottleneck_upsampler", D, bd)
         conv_block(f"{name}.decoder3_upsampler.0", 2 * bd, bd)
         conv_block(f"{name}.decoder3_upsampler.1", bd, bd)
@@ -142,7 +146,18 @@ def state_spec(arch: str, num_nuclei_classes: int, num_tissue_classes: int, regr
         convT(f"{name}.decoder1_upsampler.2", 128, 64)
         conv_block(f"{name}.decoder0_header.0", 128, 64)
         conv_block(f"{name}.decoder0_header.1", 64, 64)
-        conv(f"{name}.decoder0_header.2", 64, ncls, 1)
+        if ncls:
+            conv(f"{name}.decoder0_header.2", 64, ncls, 1)
+
+    if shared:
+        skips([f"decoder.decoder{k}_skip" for k in range(4)])
+        upsampling("decoder", 0)
+        for name, ncls in heads:
+            conv(name, 64, ncls, 1)
+    else:
+        skips([f"decoder{k}" for k in range(4)])
+        for name, ncls in heads:
+            upsampling(name, ncls)
     if cfg["sam"] and num_tissue_classes > 0:
         lin("classifier_head", 256, num_tissue_classes)
     return S
@@ -179,6 +194,6 @@ def synth_tensor(key: str, shape, kind: str, seed: int = 0) -> torch.Tensor:
 
 
 def synth_state_dict(arch: str, num_nuclei_classes: int = 6, num_tissue_classes: int = 19, seed: int = 0,
-                     regression_loss: bool = False) -> "OrderedDict[str, torch.Tensor]":
-    spec = state_spec(arch, num_nuclei_classes, num_tissue_classes, regression_loss)
+                     regression_loss: bool = False, shared: bool = False) -> "OrderedDict[str, torch.Tensor]":
+    spec = state_spec(arch, num_nuclei_classes, num_tissue_classes, regression_loss, shared=shared)
     return OrderedDict((k, synth_tensor(k, shp, kind, seed)) for k, (shp, kind) in spec.items())

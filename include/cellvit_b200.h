@@ -53,6 +53,8 @@ typedef struct {
     int n_tissue;       /* num_tissue_classes                                                                 */
     int skip11, skip12; /* decoder widths (cellvit.py:106-113)                                                */
     int bott_pad;       /* bottleneck width padded to a multiple of 64 (312 -> 320 for ViT-256)               */
+    int shared_decoder; /* 1: the *Shared variants (cellvit_shared.py:147-231): ONE upsampling trunk (parameters "dec.*")
+                           and a 1x1 head per output on its 64-channel feature map; 0: three branches            */
 } cvb_model_desc;
 
 int cvb_model_create(const cvb_model_desc* desc, cvb_model** out);

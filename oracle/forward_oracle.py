@@ -164,8 +164,9 @@ def _deconv_block(x, sd, p):  # Deconv2DBlock, utils.py:46-86
     return F.relu(_bn(F.conv2d(x, sd[p + ".block.1.weight"], sd[p + ".block.1.bias"], padding=1), sd, p + ".block.2"))
 
 
-def _branch(sd, name, z4, s3, s2, s1, s0):
-    """cellvit.py:212-244 with the shared skips s0..s3 precomputed."""
+def _branch(sd, name, z4, s3, s2, s1, s0, head=True):
+    """cellvit.py:212-244 with the shared skips s0..s3 precomputed. ``head=False``: stop at the 64-channel feature map
+    (the trunk of the ``*Shared`` variants, cellvit_shared.py:199-231)."""
     b = F.conv_transpose2d(z4, sd[f"{name}.bottleneck_upsampler.weight"], sd[f"{name}.bottleneck_upsampler.bias"], stride=2)
     b = torch.cat([s3, b], dim=1)
     for i in range(3):
@@ -179,6 +180,8 @@ def _branch(sd, name, z4, s3, s2, s1, s0):
     b = torch.cat([s0, b], dim=1)
     for i in range(2):
         b = _conv_block(b, sd, f"{name}.decoder0_header.{i}")
+    if not head:
+        return b
     return F.conv2d(b, sd[f"{name}.decoder0_header.2.weight"], sd[f"{name}.decoder0_header.2.bias"])
 
 
@@ -194,19 +197,27 @@ def cellvit_forward(sd, x, arch: str, retrieve_tokens: bool = False, regression_
         feat, z = sam_encoder(sd, x, SAM_CFG[arch])
         out["tissue_types"] = _lin(feat, sd, "classifier_head")
     z1, z2, z3, z4 = z
-    s0 = _conv_block(_conv_block(x, sd, "decoder0.0"), sd, "decoder0.1")
+    shared = "decoder.bottleneck_upsampler.weight" in sd   # the *Shared variants: one trunk, three 1x1 heads (cellvit_shared.py:147-197)
+    sk = [f"decoder.decoder{k}_skip" for k in range(4)] if shared else [f"decoder{k}" for k in range(4)]
+    s0 = _conv_block(_conv_block(x, sd, sk[0] + ".0"), sd, sk[0] + ".1")
     s1 = z1
     for i in range(3):
-        s1 = _deconv_block(s1, sd, f"decoder1.{i}")
-    s2 = _deconv_block(_deconv_block(z2, sd, "decoder2.0"), sd, "decoder2.1")
-    s3 = _deconv_block(z3, sd, "decoder3.0")
-    nb = _branch(sd, "nuclei_binary_map_decoder", z4, s3, s2, s1, s0)
+        s1 = _deconv_block(s1, sd, f"{sk[1]}.{i}")
+    s2 = _deconv_block(_deconv_block(z2, sd, sk[2] + ".0"), sd, sk[2] + ".1")
+    s3 = _deconv_block(z3, sd, sk[3] + ".0")
+    if shared:
+        up = _branch(sd, "decoder", z4, s3, s2, s1, s0, head=False)
+        nb = F.conv2d(up, sd["nuclei_binary_map_decoder.weight"], sd["nuclei_binary_map_decoder.bias"])
+        out["hv_map"] = F.conv2d(up, sd["hv_map_decoder.weight"], sd["hv_map_decoder.bias"])
+        out["nuclei_type_map"] = F.conv2d(up, sd["nuclei_type_maps_decoder.weight"], sd["nuclei_type_maps_decoder.bias"])
+    else:
+        nb = _branch(sd, "nuclei_binary_map_decoder", z4, s3, s2, s1, s0)
+        out["hv_map"] = _branch(sd, "hv_map_decoder", z4, s3, s2, s1, s0)
+        out["nuclei_type_map"] = _branch(sd, "nuclei_type_maps_decoder", z4, s3, s2, s1, s0)
     if regression_loss:
         out["nuclei_binary_map"], out["regression_map"] = nb[:, :2], nb[:, 2:]
     else:
         out["nuclei_binary_map"] = nb
-    out["hv_map"] = _branch(sd, "hv_map_decoder", z4, s3, s2, s1, s0)
-    out["nuclei_type_map"] = _branch(sd, "nuclei_type_maps_decoder", z4, s3, s2, s1, s0)
     if retrieve_tokens:
         out["tokens"] = z4
     return out

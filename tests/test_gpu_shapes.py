@@ -187,3 +187,28 @@ def test_window_pad_skip_gives_the_same_forward(arch, size):
         d = (a[k] - b[k]).abs().max().item()
         print(k, "max abs difference", d, "bit-equal", torch.equal(a[k], b[k]))
         assert d <= 1e-5 * max(1.0, b[k].abs().max().item()), (k, d)
+
+
+@pytest.mark.parametrize("arch,size,B,regression", [("ViT256", 256, 2, False), ("SAM-B", 256, 1, True), ("ViT256", (272, 400), 1, True)])
+def test_shared_decoder_variants_match_oracle(arch, size, B, regression):
+    """CellViT256Shared / CellViTSAMShared (cellvit_shared.py:147-231): one upsampling trunk, three 1x1 heads -- against the fp32
+    oracle (pinned to the reference's Shared modules in tests/test_oracle_vs_reference.py), native and canvas tile sizes."""
+    from cellvit_b200.cellvit import CellViT256Shared, CellViTSAMShared
+    sd = weights.synth_state_dict(arch, 6, 19, seed=3, regression_loss=regression, shared=True)
+    m = CellViT256Shared(None, 6, 19, regression_loss=regression) if arch == "ViT256" else CellViTSAMShared(None, 6, 19, arch, regression_loss=regression)
+    m.load_state_dict(sd, strict=True)
+    m = m.cuda().eval()
+    x = torch.from_numpy(synth.synthetic_tiles(B, size, seed=5))
+    from oracle import forward_oracle
+    sd_dev = {k: v.cuda() for k, v in sd.items()}
+    refs = [forward_oracle.cellvit_forward(sd_dev, x[b:b + 1].cuda(), arch, retrieve_tokens=True, regression_loss=regression) for b in range(B)]
+    ref = {k: torch.cat([r[k] for r in refs]).cpu() for k in refs[0]}
+    with torch.no_grad():
+        out = m(x.cuda(), retrieve_tokens=True, argmax_maps=True)
+    torch.cuda.synchronize()
+    assert ("regression_map" in out) == regression
+    if regression:
+        assert (out["regression_map"].cpu() - ref["regression_map"]).abs().max().item() <= TOL
+    _check(out, {k: v for k, v in ref.items() if k != "regression_map"})
+    assert torch.equal(out["nuclei_type_argmax"].long(), out["nuclei_type_map"].argmax(1))
+    assert torch.equal(out["nuclei_binary_argmax"].long(), out["nuclei_binary_map"][:, :2].argmax(1))

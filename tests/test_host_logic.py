@@ -316,3 +316,34 @@ def test_window_tc_operand_layout_reproduces_the_reference_attention():
     p[:, S:] = 0.0                                                   # keys 196..207: weight 0
     got = (p @ vp) / (p @ ones)[:, None]
     assert torch.allclose(got, want, rtol=1e-4, atol=1e-5), (got - want).abs().max()
+
+
+@pytest.mark.parametrize("arch", ["ViT256", "SAM-B"])
+def test_shared_decoder_variants_surface(arch, lib_path):
+    """The ``*Shared`` variants (cellvit_shared.py): reference constructor signatures, the reference's state_dict keys in its
+    order (weights.state_spec(shared=True) is pinned against the reference modules in tests/test_oracle_vs_reference.py), a
+    third of the decoder workspace, and model_from_checkpoint accepts the arch names of the reference's __get_model."""
+    from cellvit_b200 import weights
+    from cellvit_b200.cell_detection import model_from_checkpoint
+    from cellvit_b200.cellvit import CellViT256, CellViT256Shared, CellViTSAM, CellViTSAMShared, CellViTShared
+    m = CellViT256Shared(None, 6, 19) if arch == "ViT256" else CellViTSAMShared(None, 6, 19, arch, regression_loss=True)
+    assert isinstance(m, CellViTShared)
+    sd = weights.synth_state_dict(arch, 6, 19, seed=1, regression_loss=arch != "ViT256", shared=True)
+    assert list(m.state_dict().keys()) == list(sd.keys())
+    m.load_state_dict(sd, strict=True)
+    assert m.branches_output == {"nuclei_binary_map": 2 if arch == "ViT256" else 4, "hv_map": 2, "nuclei_type_maps": 6}
+    assert any(k.startswith("decoder.decoder3_upsampler.") for k in sd) and "nuclei_binary_map_decoder.weight" in sd
+    ckpt = {"arch": "CellViT256Shared" if arch == "ViT256" else "CellViTSAMShared",
+            "config": {"data.num_nuclei_classes": 6, "data.num_tissue_classes": 19, "model.backbone": arch if arch != "ViT256" else "default",
+                       "model.regression_loss": arch != "ViT256"},
+            "model_state_dict": sd}
+    loaded, _ = model_from_checkpoint(ckpt)
+    assert type(loaded).__name__ == ckpt["arch"] and not loaded.training
+    full = CellViT256(None, 6, 19) if arch == "ViT256" else CellViTSAM(None, 6, 19, arch)
+    L = ctypes.CDLL(lib_path)
+    a, b = ctypes.c_size_t(), ctypes.c_size_t()
+    assert L.cvb_model_workspace_bytes(m._ensure_handle(), 2, 256, 256, ctypes.byref(a)) == 0
+    assert L.cvb_model_workspace_bytes(full._ensure_handle(), 2, 256, 256, ctypes.byref(b)) == 0
+    assert 0 < a.value <= b.value
+    with pytest.raises(NotImplementedError):
+        model_from_checkpoint(dict(ckpt, arch="CellViTUnknown"))

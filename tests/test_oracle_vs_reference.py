@@ -89,6 +89,29 @@ def test_forward_oracle_matches_reference_modules(ref, arch, size):
         assert (r[k] - o[k]).abs().max().item() <= 2e-6, k
 
 
+@pytest.mark.parametrize("arch,size,regression", [("ViT256", 64, False), ("SAM-B", 64, True)])
+def test_forward_oracle_matches_reference_shared_modules(ref, arch, size, regression):
+    """The ``*Shared`` variants (cellvit_shared.py): one decoder trunk + a 1x1 head per output. Pins ``weights.state_spec(shared=True)``
+    (strict load into the reference modules, same key ORDER) and the oracle's shared path against the reference forward."""
+    import importlib
+    shared = importlib.import_module("models.segmentation.cell_segmentation.cellvit_shared")
+    torch.manual_seed(0)
+    m = shared.CellViT256Shared(None, 6, 19, regression_loss=regression) if arch == "ViT256" else \
+        shared.CellViTSAMShared(None, 6, 19, arch, regression_loss=regression)
+    m.eval()
+    sd = weights.synth_state_dict(arch, 6, 19, seed=3, regression_loss=regression, shared=True)
+    assert list(m.state_dict().keys()) == list(sd.keys())
+    m.load_state_dict(sd, strict=True)
+    x = torch.from_numpy(synth.synthetic_tiles(1, size, seed=5))
+    with torch.no_grad():
+        r = m(x, retrieve_tokens=True)
+    o = forward_oracle.cellvit_forward(dict(sd), x, arch, retrieve_tokens=True, regression_loss=regression)
+    assert sorted(r) == sorted(o)
+    for k in r:
+        assert r[k].shape == o[k].shape
+        assert (r[k] - o[k]).abs().max().item() <= 2e-6, k
+
+
 def _wsi_cell_list(ref_cd, grid=2, tile=1024, ov=64, seed=17):
     """Cells of a synthetic slide (grid x grid tiles cut from one synthetic-nuclei canvas, so nuclei in the overlap bands
     appear in two tiles), as the dict list process_wsi hands to the duplicate removal -- built with the REFERENCE's own
