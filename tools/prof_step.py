@@ -18,5 +18,13 @@ npd = torch.from_numpy(np.stack([l[0] for l in lg])).cuda(); ntd = torch.from_nu
 hvd = torch.from_numpy(np.stack([n["hv"] for n in nuc])).cuda()
 p = DetectionCellPostProcessor(6, 40)
 with torch.no_grad():
-    m(x, retrieve_tokens=True); p.run_float(npd, hvd, ntd)
+    if os.environ.get("CVB_POST", "float") == "argmax":
+        # the product pipeline's path (K12): the head epilogue writes the uint8 arg-max planes, cvb_postproc_argmax consumes planes
+        # (here: the planes of the injected synthetic-nuclei maps), contours and cell tokens follow
+        out = m(x, retrieve_tokens=True, argmax_maps=True)
+        p.launch_argmax(npd.argmax(1).to(torch.uint8), hvd, ntd.argmax(1).to(torch.uint8), slot=0, tokens=out["tokens"], patch_size=16)
+        torch.cuda.synchronize()
+        p.collect(0, None, with_tokens=True)
+    else:
+        m(x, retrieve_tokens=True); p.run_float(npd, hvd, ntd)
 torch.cuda.synchronize()
