@@ -433,9 +433,13 @@ def run_gpu(args):
                 "executed_tflop_per_step": tot_fl / Kp / 1e12, "algorithmic_tflop_per_step": gflop_tc * B / 1000.0,
                 "share_of_step": (tot_ms / Kp) / (ms_total / K),
                 "whole_step_frac": (cfg["gflop"] * B / (ms_total / K)) / peak}  # all algorithmic FLOPs of the step / step time / peak
-        ppath = os.path.join(ROOT, "profiles", "r2_postproc_traffic.json")
-        if os.path.exists(ppath):  # HBM-bound post-processing kernels: committed ncu capture (tools/ncu_table.py) of cvb_postproc at this shape
-            roof["postproc"] = json.load(open(ppath))
+        # HBM-bound post-processing kernels: committed ncu captures at this shape (tools/postproc_traffic.py). The arg-max entry
+        # (cvb_postproc_argmax, what this bench and the product pipeline run) first, the float entry's older capture as fallback.
+        for pname in ("r2_postproc_traffic_k12.json", "r2_postproc_traffic.json"):
+            ppath = os.path.join(ROOT, "profiles", pname)
+            if os.path.exists(ppath):
+                roof["postproc"] = json.load(open(ppath))
+                break
         if world == 1 and not args.no_cpu:
             cores = os.cpu_count() or 1
             tf, tp = cpu_tile_seconds(arch, cores, 1)
