@@ -373,19 +373,27 @@ int grid_for(long long work_items, int block) {
 // grid) <- the per-column constant `bias`: what a Linear layer gives for the all-zero rows that the reference pads with
 // AFTER norm1 (image_encoder.py:180-184, 263-288) -- so the GEMM itself only has to run over the real tokens.
 __global__ void __launch_bounds__(256)
-window_pad_fill_kernel(__half* __restrict__ out, const float* __restrict__ bias, int rows, int N, int tok_h, int tok_w, int ws, int g) {
+window_pad_fill_kernel(__half* __restrict__ out, const float* __restrict__ bias, int B, int N, int tok_h, int tok_w, int ws, int g) {
+    // one warp per (padding token, 1024-column chunk): the padding tokens of an image are enumerated directly -- the strip right
+    // of the real grid, then the rows below it -- instead of testing every window-partitioned row (one row in six is padding)
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (warp >= rows) return;
-    const int per_img = g * g * ws * ws;
-    const int rem = warp % per_img;
-    const int win = rem / (ws * ws), t = rem - win * ws * ws;
-    const int y = (win / g) * ws + t / ws, x = (win % g) * ws + t % ws;
-    if (y < tok_h && x < tok_w) return;
-    __half* o = out + (long long)warp * N;
-    for (int i = lane * 8; i < N; i += 256) {
-        const float4 a = __ldg(reinterpret_cast<const float4*>(bias + i));
-        const float4 d = __ldg(reinterpret_cast<const float4*>(bias + i + 4));
-        *reinterpret_cast<uint4*>(o + i) = make_uint4(pack_h2(a.x, a.y), pack_h2(a.z, a.w), pack_h2(d.x, d.y), pack_h2(d.z, d.w));
+    const int P = g * ws;                                    // padded grid edge
+    const int right = tok_h * (P - tok_w), per_img = right + (P - tok_h) * P;
+    const int chunks = (N + 1023) >> 10;
+    if (warp >= B * per_img * chunks) return;
+    const int chunk = warp % chunks, r = warp / chunks;
+    const int b = r / per_img, i = r - b * per_img;
+    int y, x;
+    if (i < right) { y = i / (P - tok_w); x = tok_w + i % (P - tok_w); }
+    else { const int j = i - right; y = tok_h + j / P; x = j % P; }
+    const int wy = y / ws, wx = x / ws;
+    const long long row = (long long)b * P * P + (wy * g + wx) * ws * ws + (y - wy * ws) * ws + (x - wx * ws);
+    __half* o = out + row * N;
+    const int end = min(N, (chunk + 1) << 10);
+    for (int c = (chunk << 10) + lane * 8; c < end; c += 256) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(bias + c));
+        const float4 d = __ldg(reinterpret_cast<const float4*>(bias + c + 4));
+        *reinterpret_cast<uint4*>(o + c) = make_uint4(pack_h2(a.x, a.y), pack_h2(a.z, a.w), pack_h2(d.x, d.y), pack_h2(d.z, d.w));
     }
 }
 
@@ -484,8 +492,10 @@ int op_window_pad_fill(__half* out, const float* bias, int B, int N, int tok_h, 
     CVB_CHECK(out && bias && B > 0 && N % 8 == 0 && ws > 0 && g > 0 && (((uintptr_t)out | (uintptr_t)bias) & 15) == 0, CVB_EARG,
               "window_pad_fill: bad arguments");
     if (g * ws == tok_h && g * ws == tok_w) return CVB_OK;  // no padding
-    const int rows = B * g * g * ws * ws;
-    window_pad_fill_kernel<<<cdiv(rows, 8), 256, 0, stream>>>(out, bias, rows, N, tok_h, tok_w, ws, g);
+    const int P = g * ws;
+    CVB_CHECK(tok_h <= P && tok_w <= P, CVB_EARG, "window_pad_fill: token grid larger than the window grid");
+    const long long warps = (long long)B * ((long long)tok_h * (P - tok_w) + (long long)(P - tok_h) * P) * ((N + 1023) / 1024);
+    window_pad_fill_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, stream>>>(out, bias, B, N, tok_h, tok_w, ws, g);
     cvb_note_launches(1);
     CVB_CUDA(cudaGetLastError());
     return CVB_OK;
