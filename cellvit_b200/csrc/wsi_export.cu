@@ -191,6 +191,13 @@ void detection_record(JsonOut& o, const cvb_cell_columns& c, long long i) {
 extern "C" __attribute__((visibility("default")))
 int cvb_export_json(const char* path, const cvb_cell_columns* cols, const cvb_json_section* sections, int n_sections, int indent) {
     CVB_CHECK(path && cols && (sections || n_sections == 0) && n_sections >= 0, CVB_EARG, "cvb_export_json: null argument");
+    CVB_CHECK(cols->n >= 0 && (cols->n == 0 || (cols->bbox && cols->centroid && cols->contour_off && cols->type_prob && cols->type &&
+                                                cols->patch && cols->status && cols->offset && cols->edge && cols->position)),
+              CVB_EARG, "cvb_export_json: null column");
+    for (long long i = 0; i < cols->n; ++i)
+        CVB_CHECK(cols->contour_off[i] >= 0 && cols->contour_off[i] <= cols->contour_off[i + 1], CVB_EARG,
+                  "cvb_export_json: contour offsets must be non-negative and non-decreasing (cell %lld)", i);
+    CVB_CHECK(cols->n == 0 || cols->contour_off[cols->n] == 0 || cols->contour_pts != nullptr, CVB_EARG, "cvb_export_json: null contour points");
     for (int s = 0; s < n_sections; ++s) {
         const cvb_json_section& sec = sections[s];
         CVB_CHECK(sec.kind >= CVB_JSON_CELLS && sec.kind <= CVB_JSON_POINTS && sec.n_idx >= 0 && (sec.idx || sec.n_idx == 0), CVB_EARG,

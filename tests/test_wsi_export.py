@@ -177,3 +177,16 @@ def test_cells_pt_names_the_reference_dataclass(tmp_path):
         r = subprocess.run([sys.executable, str(script), str(tmp_path / "cells.pt"), "/root/reference"], capture_output=True, text=True,
                            cwd=str(tmp_path), timeout=300)
         assert r.returncode == 0 and "ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_export_rejects_malformed_columns(tmp_path):
+    """The native writer validates what it is about to index: cell indices, contour offsets, the output path."""
+    from cellvit_b200 import _lib as L
+    cols = _random_columns(10, seed=4)
+    with pytest.raises(L.CvbError, match="out of range"):
+        cols.export_json(tmp_path / "a.json", [("", "", np.array([0, 10]), 0, 1)])
+    with pytest.raises(L.CvbError, match="cannot open"):
+        cols.export_json(tmp_path / "no_such_dir" / "a.json", [("", "", None, 0, 1)])
+    cols.contour_off[3] = cols.contour_off[4] + 5
+    with pytest.raises(L.CvbError, match="non-decreasing"):
+        cols.export_json(tmp_path / "a.json", [("", "", None, 0, 1)])
