@@ -347,3 +347,45 @@ def test_shared_decoder_variants_surface(arch, lib_path):
     assert 0 < a.value <= b.value
     with pytest.raises(NotImplementedError):
         model_from_checkpoint(dict(ckpt, arch="CellViTUnknown"))
+
+
+@pytest.mark.parametrize("B,h,w,ws", [(2, 64, 64, 14), (1, 16, 16, 14), (2, 25, 25, 14), (1, 13, 13, 14), (1, 28, 28, 14), (3, 5, 9, 4)])
+def test_window_partition_index_maps_restated(B, h, w, ws):
+    """CPU restatement of the index arithmetic the windowed blocks rely on (csrc/tc_gemm.cu map_out_row, csrc/ops_misc.cu
+    window_pad_fill_kernel, csrc/window_tc.cu un-partitioned store) against torch's window_partition (image_encoder.py:263-288):
+    the raster -> window-order row map (TC_ROW_TO_WINDOW) hits exactly the rows that hold real tokens, the padding-token
+    enumeration of the fill kernel hits exactly the other rows, and the window -> raster map (TC_ROW_WINDOW / un_g) inverts it."""
+    import torch.nn.functional as F
+    g = max((h + ws - 1) // ws, (w + ws - 1) // ws)
+    P = g * ws
+    tok = torch.arange(1, B * h * w + 1, dtype=torch.float32).view(B, h, w, 1)            # token ids in raster order, 0 = padding
+    padded = F.pad(tok, (0, 0, 0, P - w, 0, P - h))
+    win = padded.view(B, g, ws, g, ws, 1).permute(0, 1, 3, 2, 4, 5).reshape(-1).long().numpy()   # window_partition, flattened rows
+
+    def to_window(m):   # TC_ROW_TO_WINDOW
+        b, rem = divmod(m, h * w)
+        y, x = divmod(rem, w)
+        wy, wx = y // ws, x // ws
+        return b * P * P + (wy * g + wx) * ws * ws + (y - wy * ws) * ws + (x - wx * ws)
+
+    def to_raster(r):   # TC_ROW_WINDOW and the un-partitioned store of window_tc_kernel: -1 = padding token
+        b, rem = divmod(r, P * P)
+        wi, t = divmod(rem, ws * ws)
+        y, x = (wi // g) * ws + t // ws, (wi % g) * ws + t % ws
+        return (b * h + y) * w + x if (y < h and x < w) else -1
+
+    real_rows = [to_window(m) for m in range(B * h * w)]
+    assert [int(win[r]) for r in real_rows] == list(range(1, B * h * w + 1))
+    right, per_img = h * (P - w), h * (P - w) + (P - h) * P
+    pad_rows = []
+    for r in range(B * per_img):                              # window_pad_fill_kernel's enumeration
+        b, i = divmod(r, per_img)
+        if i < right:
+            y, x = i // (P - w), w + i % (P - w)
+        else:
+            y, x = h + (i - right) // P, (i - right) % P
+        wy, wx = y // ws, x // ws
+        pad_rows.append(b * P * P + (wy * g + wx) * ws * ws + (y - wy * ws) * ws + (x - wx * ws))
+    assert len(set(pad_rows)) == len(pad_rows) and sorted(pad_rows) == [r for r in range(len(win)) if win[r] == 0]
+    assert sorted(real_rows + pad_rows) == list(range(len(win)))
+    assert [to_raster(r) for r in range(len(win))] == [int(v) - 1 for v in win]
