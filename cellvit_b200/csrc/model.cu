@@ -229,9 +229,9 @@ int forward_impl(cvb_model& m, const float* x, int B, int H, int W, float* o_np,
             else f.chk(op_attention(qkv, Gb, S, heads, hd, scale, th, tw, gh, gw, att, st));
         }
         {
-            // attn-out projection writes fp16 y (+bias) in window order; the residual add x += unpartition(y) is fused
-            // into norm2 below (coalesced) -- with K = 1280 a scattered fp32 read-modify-write epilogue is slower than
-            // the main loop (131 -> 69 us per launch), unlike lin2 (K = 5120) which keeps the fp32 residual epilogue.
+            // attn-out projection writes fp16 y (+bias) in the row order of `att` (raster, or window order on the mma.sync /
+            // no-pad-skip paths); the residual add x += y is fused into norm2 below (coalesced) -- with K = 1280 a scattered fp32
+            // read-modify-write epilogue is slower than the main loop (131 -> 69 us), unlike lin2 (K = 5120) which keeps it.
             TcEpilogue e = Fwd::epi0();
             e.kind = TC_EPI_F16; e.out = ybuf; e.ldc = D; e.shift = f.P<float>(p + ".proj.b");
             f.gemm(att, att_raster ? B * Tx : rows, D, p + ".proj.w", D, e);
