@@ -172,7 +172,7 @@ def test_process_tiles_on_a_non_native_tile_size_matches_oracle():
             assert toks[b].shape == (len(odict), 384)
 
 
-@pytest.mark.parametrize("arch,size", [("SAM-B", 256), ("SAM-H", 400)])
+@pytest.mark.parametrize("arch,size", [("SAM-B", 256), ("SAM-H", 400), ("SAM-B", 1024)])
 def test_window_pad_skip_gives_the_same_forward(arch, size):
     """The QKV GEMM of the windowed blocks runs over the real tokens only (rows scattered into window order by the epilogue,
     padding rows = bias): same maps as running it over the zero-padded window-partitioned rows (image_encoder.py:180-184)."""
