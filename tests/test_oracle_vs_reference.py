@@ -69,7 +69,10 @@ def test_postproc_degenerate_tiles(ref):
     assert np.array_equal(lab, olab) and sorted(dct) == sorted(odct)
 
 
-@pytest.mark.parametrize("arch,size", [("ViT256", 64), ("SAM-B", 64)])
+# non-square and non-native tile sizes too (cellvit.py:170-175 takes any multiple of 16): the GPU shape tests (tests/test_gpu_shapes.py)
+# compare the engine with the oracle at such sizes, this pins the oracle itself there -- bicubic position-embedding resize on a
+# non-square grid (vits_histo.py:377-402), windows larger than the token grid and grids that need padding (image_encoder.py:263-288)
+@pytest.mark.parametrize("arch,size", [("ViT256", 64), ("SAM-B", 64), ("ViT256", (48, 80)), ("ViT256", (112, 32)), ("SAM-B", 80), ("SAM-B", 240)])
 def test_forward_oracle_matches_reference_modules(ref, arch, size):
     cellvit, _, _ = ref
     torch.manual_seed(0)
