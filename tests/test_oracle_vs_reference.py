@@ -27,11 +27,14 @@ def _pred_map(d):
     return np.concatenate([d["nt"][..., None], d["np_bin"][..., None], d["hv"].transpose(1, 2, 0)], -1).astype(np.float64)
 
 
-@pytest.mark.parametrize("size,n,seed,mag,noise", [(256, 40, 0, 40, 0.0), (256, 60, 1, 20, 0.0), (512, 170, 2, 40, 0.02),
-                                                   (320, 80, 3, 40, 0.05)])
-def test_postproc_stages_match_reference(ref, size, n, seed, mag, noise):
+@pytest.mark.parametrize("size,n,seed,mag,noise,crop", [(256, 40, 0, 40, 0.0, None), (256, 60, 1, 20, 0.0, None), (512, 170, 2, 40, 0.02, None),
+                                                        (320, 80, 3, 40, 0.05, None), (400, 120, 4, 40, 0.02, (272, 400)),
+                                                        (400, 120, 5, 20, 0.0, (399, 173))])
+def test_postproc_stages_match_reference(ref, size, n, seed, mag, noise, crop):
     _, post, cap = ref
     d = synth.synthetic_nuclei(size, n, seed, noise=noise)
+    if crop:   # non-square (and odd-sized) maps: nuclei cut by the new border included
+        d = {k: np.ascontiguousarray(v[..., :crop[0], :crop[1]]) for k, v in d.items()}
     proc = post.DetectionCellPostProcessor(nr_types=6, magnification=mag, gt=False)
     ref_lab, ref_dict = proc.post_process_cell_segmentation(_pred_map(d))
     lab, inter = po.proc_np_hv(d["np_bin"], d["hv"], mag, want_intermediates=True)
