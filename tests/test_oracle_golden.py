@@ -135,3 +135,73 @@ def test_rank_transformed_flood_equals_the_oracle_flood():
         assert small.sum() > 0.5 * blb.sum()
         got = rank_flood(dist, marker * small, small)
         assert np.array_equal(got[small > 0], want[small > 0])
+
+
+def test_canvas_decoder_restatement_equals_direct_decoder():
+    """CPU restatement of the canvas scheme of csrc/model.cu (tile sizes that are not native to the decoder tilings): embed the skip
+    tokens / the stem output top-left into a larger zero canvas, re-zero the margin after EVERY decoder layer, crop the head
+    outputs -- and the result equals the decoder evaluated directly on the real size (oracle/forward_oracle.py), because inside
+    the real region every 3x3 convolution then sees exactly the zero padding of the real border. Without the re-zeroing it does
+    not (folded-BN shift + ReLU and ConvT bias make the margin non-zero), which the test also shows."""
+    import torch
+    import torch.nn.functional as F
+    from cellvit_b200 import synth, weights
+    from oracle import forward_oracle as fo
+    torch.manual_seed(0)
+    arch, (H, W), (Hc, Wc) = "ViT256", (48, 80), (64, 96)
+    h, w, hc, wc = H // 16, W // 16, Hc // 16, Wc // 16
+    sd = weights.synth_state_dict(arch, 6, 19, seed=3)
+    x = torch.from_numpy(synth.synthetic_tiles(1, (H, W), seed=5))
+    ref = fo.cellvit_forward(sd, x, arch)
+    _, z = fo.vit256_encoder(sd, x, fo.VIT256_CFG)
+
+    def run(mask_margins):
+        def embed(t, s):   # [B,C,s*h,s*w] -> zero canvas [B,C,s*hc,s*wc]
+            return F.pad(t, (0, s * (wc - w), 0, s * (hc - h)))
+
+        def mask(t):       # zero everything outside the real region of a layer at scale s = t.height / hc
+            if not mask_margins:
+                return t
+            s = t.shape[-2] // hc
+            m = torch.zeros_like(t)
+            m[..., : s * h, : s * w] = 1
+            return t * m
+
+        conv = lambda t, p: mask(fo._conv_block(t, sd, p))
+        convt = lambda t, p: mask(F.conv_transpose2d(t, sd[p + ".weight"], sd[p + ".bias"], stride=2))
+        def deconv(t, p):   # Deconv2DBlock = ConvT -> Conv3x3 -> BN -> ReLU, margin re-zeroed after the ConvT as well
+            u = mask(F.conv_transpose2d(t, sd[p + ".block.0.weight"], sd[p + ".block.0.bias"], stride=2))
+            return mask(F.relu(fo._bn(F.conv2d(u, sd[p + ".block.1.weight"], sd[p + ".block.1.bias"], padding=1), sd, p + ".block.2")))
+
+        z1, z2, z3, z4 = (embed(t, 1) for t in z)
+        s0 = conv(embed(fo._conv_block(x, sd, "decoder0.0"), 16), "decoder0.1")   # the stem pads at the real border itself
+        s1 = z1
+        for i in range(3):
+            s1 = deconv(s1, f"decoder1.{i}")
+        s2 = deconv(deconv(z2, "decoder2.0"), "decoder2.1")
+        s3 = deconv(z3, "decoder3.0")
+        out = {}
+        for key, name in (("nuclei_binary_map", "nuclei_binary_map_decoder"), ("hv_map", "hv_map_decoder"),
+                          ("nuclei_type_map", "nuclei_type_maps_decoder")):
+            b = convt(z4, f"{name}.bottleneck_upsampler")
+            b = torch.cat([s3, b], 1)
+            for i in range(3):
+                b = conv(b, f"{name}.decoder3_upsampler.{i}")
+            b = convt(b, f"{name}.decoder3_upsampler.3")
+            for lvl, s in (("decoder2_upsampler", s2), ("decoder1_upsampler", s1)):
+                b = torch.cat([s, b], 1)
+                for i in range(2):
+                    b = conv(b, f"{name}.{lvl}.{i}")
+                b = convt(b, f"{name}.{lvl}.2")
+            b = torch.cat([s0, b], 1)
+            for i in range(2):
+                b = conv(b, f"{name}.decoder0_header.{i}")
+            out[key] = F.conv2d(b, sd[f"{name}.decoder0_header.2.weight"], sd[f"{name}.decoder0_header.2.bias"])[..., :H, :W]
+        return out
+
+    with torch.no_grad():
+        good, bad = run(True), run(False)
+    for k in ("nuclei_binary_map", "hv_map", "nuclei_type_map"):
+        assert good[k].shape == ref[k].shape
+        assert (good[k] - ref[k]).abs().max().item() <= 1e-5, k
+    assert max((bad[k] - ref[k]).abs().max().item() for k in bad) > 1e-3     # the margin DOES leak without the re-zeroing
