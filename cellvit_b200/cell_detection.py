@@ -414,6 +414,11 @@ class CellSegmentationInference:
         # where the wall clock went (seconds): tile stream (decode + GPU + per-cell records), duplicate removal, export
         self.last_timings = {"tiles": t_tiles - t_start, "of_which_cell_records": t_records, "dedup": t_dedup - t_tiles,
                              "export": t_end - t_dedup}
+        # the per-type cell counts the reference logs at the end of process_wsi (:470-478: value_counts("type") with the type names)
+        inverse = {v: k for k, v in nuclei_types.items()}
+        ids, counts = np.unique(kept.type, return_counts=True)
+        self.last_stats = {"cells_before_cleaning": len(cols), "cells": len(kept),
+                           "per_type": {inverse.get(int(t), int(t)): int(c) for t, c in sorted(zip(ids, counts), key=lambda tc: -tc[1])}}
         return LazyCellsJson(header, kept)
 
     def post_process_edge_cells(self, cell_list) -> List[int]:

@@ -318,3 +318,22 @@ def test_polygon_intersection_area_invariants():
         assert abs(wm.polygon_intersection_area(a + shift, b + shift) - i_ab) <= 1e-6 * max(aa, ab, 1.0)
         assert abs(wm.polygon_intersection_area(a[::-1], b) - i_ab) <= tol
         assert wm.polygon_intersection_area(a, b + np.array([500.0, 0.0])) == 0.0
+
+
+def test_process_wsi_reports_cell_counts_per_type(tmp_path):
+    """``last_stats`` = what the reference logs at the end of process_wsi (cell_detection.py:470-478): cells before / after the
+    clean-up and the count per nucleus type name; consistent with the written cells.json."""
+    from collections import Counter
+    from oracle import wsi_fixture as wf
+    from wsi_host_harness import make_host_inference
+    from cellvit_b200.wsi_datamodel import WSI
+    root = tmp_path / "slide"
+    wf.make_slide(root)
+    inf = make_host_inference(wf.make_canvas())
+    wsi = WSI(name="slide", patient="p", slide_path=root, patched_slide_path=root)
+    out = inf.process_wsi(wsi, subdir_name="s", patch_size=wf.TILE, overlap=wf.OV, batch_size=2, num_workers=0)
+    cells = json.load(open(root / "cell_detection" / "s" / "cells.json"))["cells"]
+    names = {v: k for k, v in wf.NUCLEI_TYPES.items()}
+    assert inf.last_stats["cells"] == len(cells) == len(out.columns) < inf.last_stats["cells_before_cleaning"]
+    assert inf.last_stats["per_type"] == dict(Counter(names[c["type"]] for c in cells))
+    assert list(inf.last_stats["per_type"].values()) == sorted(inf.last_stats["per_type"].values(), reverse=True)
