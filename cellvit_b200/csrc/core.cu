@@ -62,6 +62,6 @@ __attribute__((visibility("default"))) long long cvb_launch_count(int reset) {
     if (reset) g_launches = 0;
     return v;
 }
-__attribute__((visibility("default"))) int cvb_version(void) { return 100; }
+__attribute__((visibility("default"))) int cvb_version(void) { return 200; }  // 200: round-2 ABI (cvb_model_desc.shared_decoder, arg-max entries, export)
 __attribute__((visibility("default"))) const char* cvb_last_error(void) { return g_err; }
 }

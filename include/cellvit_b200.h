@@ -30,7 +30,7 @@ extern "C" {
 #define CVB_EWORKSPACE -4  /* workspace too small                                                           */
 #define CVB_EOVERFLOW -5   /* instance table overflow: counts[] holds the number of rows that were needed  */
 
-int cvb_version(void);
+int cvb_version(void);        /* 200 = this header (100: round 1, before cvb_model_desc.shared_decoder / the arg-max and export entries) */
 const char* cvb_last_error(void);
 
 /* ------------------------------------------------------------------------------------------------ forward
