@@ -36,7 +36,7 @@ def test_c_abi_exports_every_declared_symbol(lib_path):
     L = ctypes.CDLL(lib_path)
     missing = [n for n in names if not hasattr(L, n)]
     assert not missing, missing
-    assert L.cvb_version() >= 100
+    assert L.cvb_version() == 200
     # argument validation that needs no GPU
     L.cvb_last_error.restype = ctypes.c_char_p
     need = ctypes.c_size_t()
@@ -258,7 +258,7 @@ def test_public_header_is_plain_c(tmp_path):
                         lib, f"-Wl,-rpath,{os.path.dirname(lib)}"], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     run = subprocess.run([str(exe)], capture_output=True, text=True)
-    assert run.returncode == 0 and run.stdout.split()[0] == "100", (run.returncode, run.stdout, run.stderr)
+    assert run.returncode == 0 and run.stdout.split()[0] == "200", (run.returncode, run.stdout, run.stderr)
 
 
 def test_window_tc_operand_layout_reproduces_the_reference_attention():
