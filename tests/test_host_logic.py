@@ -252,13 +252,31 @@ def test_public_header_is_plain_c(tmp_path):
                    '    size_t need = 0;\n'
                    '    if (cvb_postproc_workspace_bytes(0, 1024, 1024, &need) != CVB_EARG) return 2;   /* no GPU needed */\n'
                    '    printf("%d %s\\n", cvb_version(), cvb_last_error());\n'
+                   '    /* the WSI export entry point from plain C: two cells, one on the tile border */\n'
+                   '    {\n'
+                   '        int64_t bbox[8] = {0, 5, 9, 12, 40, 41, 50, 52}, pts[12] = {5, 0, 12, 0, 12, 9, 41, 40, 52, 40, 52, 50}, off[3] = {0, 3, 6};\n'
+                   '        double cen[4] = {8.5, 4.25, 46.0, 45.0}, prob[2] = {0.75, 1.0};\n'
+                   '        int64_t type[2] = {1, 2}, patch[4] = {0, 1, 0, 1}, status[2] = {2, 0}, offs[4] = {-32, 928, -32, 928};\n'
+                   '        uint8_t edge[2] = {1, 0};\n'
+                   '        int8_t pos[8] = {1, 0, 0, 0, 0, 0, 0, 0};\n'
+                   '        cvb_cell_columns c = {2, bbox, cen, pts, off, prob, type, patch, status, offs, edge, pos};\n'
+                   '        int64_t idx[2] = {0, 1};\n'
+                   '        cvb_json_section s = {"{\\"cells\\": ", "}", idx, 2, CVB_JSON_CELLS, 1};\n'
+                   '        if (cvb_export_json("cells.json", &c, &s, 1, -1) != CVB_OK) return 3;\n'
+                   '    }\n'
                    '    return 0;\n}\n')
     exe = tmp_path / "boundary"
     r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
                         lib, f"-Wl,-rpath,{os.path.dirname(lib)}"], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
-    run = subprocess.run([str(exe)], capture_output=True, text=True)
+    run = subprocess.run([str(exe)], capture_output=True, text=True, cwd=str(tmp_path))
     assert run.returncode == 0 and run.stdout.split()[0] == "200", (run.returncode, run.stdout, run.stderr)
+    import json
+    cells = json.load(open(tmp_path / "cells.json"))["cells"]
+    assert cells[0] == {"bbox": [[0, 5], [9, 12]], "centroid": [8.5, 4.25], "contour": [[5, 0], [12, 0], [12, 9]], "type_prob": 0.75, "type": 1,
+                        "patch_coordinates": [0, 1], "cell_status": 2, "offset_global": [-32, 928], "edge_position": True,
+                        "edge_information": {"position": [1, 0, 0, 0], "edge_patches": [[-1, 1]]}}
+    assert cells[1]["edge_position"] is False and "edge_information" not in cells[1] and cells[1]["centroid"] == [46.0, 45.0]
 
 
 def test_window_tc_operand_layout_reproduces_the_reference_attention():
