@@ -138,21 +138,51 @@ def envelope_pairs(boxes: np.ndarray, cell: float = 128.0) -> np.ndarray:
     keys, ids = np.concatenate(keys), np.concatenate(ids)
     order = np.lexsort((ids, keys))
     keys, ids = keys[order], ids[order]
-    starts = np.nonzero(np.r_[True, keys[1:] != keys[:-1]])[0]
-    ends = np.r_[starts[1:], len(keys)]
+    # all (i < j) pairs inside each run of equal keys, without a Python loop over the runs: element k pairs with element k + d of
+    # the sorted arrays for d = 1, 2, ... while both lie in the same run (runs are short: a grid cell holds a handful of boxes)
     out = []
-    for s, e in zip(starts, ends):
-        if e - s < 2:
-            continue
-        m = ids[s:e]
-        i, j = np.triu_indices(len(m), 1)
-        out.append(np.stack([m[i], m[j]], 1))
+    d = 1
+    while d < len(keys):
+        same = keys[d:] == keys[:-d]
+        if not same.any():
+            break
+        out.append(np.stack([ids[:-d][same], ids[d:][same]], 1))     # ids ascend inside a run, so column 0 < column 1
+        d += 1
     if not out:
         return np.zeros((0, 2), np.int32)
     p = np.unique(np.concatenate(out), axis=0)
     bi, bj = b[p[:, 0]], b[p[:, 1]]
     keep = (bi[:, 0] <= bj[:, 2]) & (bj[:, 0] <= bi[:, 2]) & (bi[:, 1] <= bj[:, 3]) & (bj[:, 1] <= bi[:, 3])
     return p[keep].astype(np.int32)
+
+
+class _ContourList:
+    """Read-only sequence of contours [k_i, 2] stored as ONE array + offsets (what the columnar cell store holds): element access
+    is a slice, and ``overlap_areas`` ships ``flat`` / ``offsets`` to the device as they are instead of re-concatenating."""
+
+    def __init__(self, flat: np.ndarray, offsets: np.ndarray):
+        self.flat, self.offsets = flat, offsets
+
+    def __len__(self):
+        return len(self.offsets) - 1
+
+    def __getitem__(self, i):
+        if i < 0:
+            i += len(self)
+        return self.flat[self.offsets[i]:self.offsets[i + 1]]
+
+    def __iter__(self):
+        return (self[i] for i in range(len(self)))
+
+
+def flatten_contours(contours) -> Tuple[np.ndarray, np.ndarray]:
+    """(offsets int32 [n+1], points fp64 [sum k_i, 2]) of a list of contours or of a ``_ContourList`` (which is already flat)."""
+    if isinstance(contours, _ContourList):
+        return contours.offsets.astype(np.int32), np.ascontiguousarray(contours.flat, dtype=np.float64).reshape(-1, 2)
+    off = np.zeros(len(contours) + 1, np.int32)
+    off[1:] = np.cumsum([len(c) for c in contours])
+    pts = np.concatenate([np.asarray(c, dtype=np.float64).reshape(-1, 2) for c in contours]) if off[-1] else np.zeros((0, 2))
+    return off, pts
 
 
 def overlap_areas(contours: List[np.ndarray], pairs: np.ndarray, device=None) -> Tuple[np.ndarray, np.ndarray]:
@@ -164,9 +194,7 @@ def overlap_areas(contours: List[np.ndarray], pairs: np.ndarray, device=None) ->
     n = len(contours)
     if n == 0:
         return np.zeros(0), np.zeros(0)
-    off = np.zeros(n + 1, np.int32)
-    off[1:] = np.cumsum([len(c) for c in contours])
-    pts = np.concatenate([np.asarray(c, dtype=np.float64).reshape(-1, 2) for c in contours]) if off[-1] else np.zeros((0, 2))
+    off, pts = flatten_contours(contours)
     with torch.cuda.device(device):
         d_pts = torch.from_numpy(np.ascontiguousarray(pts)).to(device)
         d_off = torch.from_numpy(off).to(device)
@@ -240,10 +268,23 @@ class CellPostProcessor:
         if len(cleaned) < 2:
             return list(cleaned)
         if self.cols is not None:
-            contours = [self.cols.contour(i).astype(np.float64) for i in cleaned]
+            # contours and their envelopes straight from the columns: one gather + four segmented reductions
+            idx = np.asarray(cleaned, dtype=np.int64)
+            off = self.cols.contour_off
+            lens = (off[1:] - off[:-1])[idx]
+            seg = np.zeros(len(idx) + 1, np.int64)
+            np.cumsum(lens, out=seg[1:])
+            flat = self.cols.contour_pts[np.repeat(off[:-1][idx] - seg[:-1], lens) + np.arange(int(seg[-1]), dtype=np.int64)].astype(np.float64)
+            contours = _ContourList(flat, seg)
+            boxes = np.tile(np.array([0.0, 0.0, -1.0, -1.0]), (len(idx), 1))
+            ne = lens > 0
+            if ne.any():
+                st = seg[:-1][ne]   # (reduceat needs non-empty segments: a start index repeated for an empty one would read its neighbour)
+                boxes[ne] = np.stack([np.minimum.reduceat(flat[:, 0], st), np.minimum.reduceat(flat[:, 1], st),
+                                      np.maximum.reduceat(flat[:, 0], st), np.maximum.reduceat(flat[:, 1], st)], 1)
         else:
             contours = [np.asarray(self.cells[i]["contour"], dtype=np.float64).reshape(-1, 2) for i in cleaned]
-        boxes = np.array([[c[:, 0].min(), c[:, 1].min(), c[:, 0].max(), c[:, 1].max()] if len(c) else [0, 0, -1, -1] for c in contours])
+            boxes = np.array([[c[:, 0].min(), c[:, 1].min(), c[:, 0].max(), c[:, 1].max()] if len(c) else [0, 0, -1, -1] for c in contours])
         pairs = envelope_pairs(boxes)
         area, inter = self.overlap_fn(contours, pairs, self.device) if self.overlap_fn is overlap_areas else self.overlap_fn(contours, pairs)
         with np.errstate(divide="ignore", invalid="ignore"):
@@ -252,7 +293,11 @@ class CellPostProcessor:
         for (i, j) in pairs[strong]:
             nbrs.setdefault(int(i), []).append(int(j))
             nbrs.setdefault(int(j), []).append(int(i))
-        alive = list(range(len(cleaned)))  # local ids, ascending == ascending cell index
+        # Cells without any strong partner take no part in the loop below: they are never consumed (only partners are) and always
+        # keep themselves, in every round -- so the rounds only walk the cells that have partners (a few per cent of a slide).
+        isolated = np.ones(len(cleaned), bool)
+        isolated[pairs[strong].ravel()] = False
+        alive = sorted(nbrs)               # local ids, ascending == ascending cell index
         for iteration in range(20):
             alive_set = set(alive)
             merged, iterated, overlaps = deque(), set(), 0
@@ -272,4 +317,6 @@ class CellPostProcessor:
                 self._log("Found all overlapping cells")
                 break
             alive = sorted(set(merged))
-        return [cleaned[k] for k in alive]
+        keep = isolated
+        keep[alive] = True
+        return [cleaned[k] for k in np.nonzero(keep)[0]]

@@ -337,3 +337,20 @@ def test_process_wsi_reports_cell_counts_per_type(tmp_path):
     assert inf.last_stats["cells"] == len(cells) == len(out.columns) < inf.last_stats["cells_before_cleaning"]
     assert inf.last_stats["per_type"] == dict(Counter(names[c["type"]] for c in cells))
     assert list(inf.last_stats["per_type"].values()) == sorted(inf.last_stats["per_type"].values(), reverse=True)
+
+
+def test_contour_list_is_a_flat_view_of_the_contours():
+    """``_ContourList`` (what the duplicate removal builds from the columnar store) behaves like the list of per-cell arrays and
+    flattens to the same (offsets, points) the device call takes."""
+    rng = np.random.default_rng(0)
+    lens = [3, 7, 4, 12]
+    parts = [rng.integers(0, 100, (k, 2)).astype(np.float64) for k in lens]
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    cl = wm._ContourList(np.concatenate(parts), off)
+    assert len(cl) == 4 and all(np.array_equal(a, b) for a, b in zip(cl, parts))
+    assert np.array_equal(cl[-1], parts[-1]) and np.array_equal(cl[np.int32(1)], parts[1])
+    o1, p1 = wm.flatten_contours(cl)
+    o2, p2 = wm.flatten_contours(parts)
+    assert o1.dtype == o2.dtype == np.int32 and np.array_equal(o1, o2) and np.array_equal(p1, p2) and p1.flags.c_contiguous
+    o3, p3 = wm.flatten_contours([])
+    assert o3.tolist() == [0] and p3.shape == (0, 2)
