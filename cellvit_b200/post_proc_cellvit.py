@@ -301,18 +301,20 @@ class DetectionCellPostProcessor:
         Without device contours, or for instances the device flagged (npts < 0), the contour comes from cv2.
         ``kept`` (optional list) receives the table row index of every instance that made it into the dict."""
         out = {}
-        ids, rmin_, cmin_, rmax_, cmax_ = (rows[k].tolist() for k in ("id", "rmin", "cmin", "rmax", "cmax"))
-        cx, cy, tp, ty = rows["cx"].tolist(), rows["cy"].tolist(), rows["type_prob"].tolist(), rows["type"].tolist()
+        ids, tp, ty = rows["id"].astype(np.int32), rows["type_prob"].tolist(), rows["type"].tolist()
+        # bbox / centroid arrays of all instances at once; the dict entries are rows of them (no per-instance array construction)
+        bbox_all = np.stack([np.stack([rows["rmin"], rows["cmin"]], 1), np.stack([rows["rmax"], rows["cmax"]], 1)], 1).astype(np.int64)
+        cent_all = np.stack([rows["cx"], rows["cy"]], 1)
         nn = npts.tolist() if npts is not None else None
-        pts32 = pts.astype(np.int32) if pts is not None else None
+        pts32 = pts.astype(np.int32) if pts is not None else None   # a private copy: the entries below are views of its rows
         for i, inst_id in enumerate(ids):
-            rmin, cmin, rmax, cmax = rmin_[i], cmin_[i], rmax_[i], cmax_[i]
             if nn is not None and nn[i] >= 0:
                 if nn[i] < 3:
                     continue  # "< 3 points dont make a contour" (post_proc_cellvit.py:110-113)
-                contour = pts32[i, :nn[i]].copy()
+                contour = pts32[i, :nn[i]]
             else:
                 import cv2
+                (rmin, cmin), (rmax, cmax) = bbox_all[i].tolist()
                 crop = (labels[rmin:rmax, cmin:cmax] == inst_id).astype(np.uint8)
                 cnts = cv2.findContours(crop, cv2.RETR_TREE, cv2.CHAIN_APPROX_SIMPLE)
                 contour = np.squeeze(cnts[0][0].astype("int32"))
@@ -322,9 +324,9 @@ class DetectionCellPostProcessor:
                 contour[:, 1] += rmin
             if kept is not None:
                 kept.append(i)
-            out[np.int32(inst_id)] = {
-                "bbox": np.array([[rmin, cmin], [rmax, cmax]]),
-                "centroid": np.array([cx[i], cy[i]]),
+            out[inst_id] = {
+                "bbox": bbox_all[i],
+                "centroid": cent_all[i],
                 "contour": contour,
                 "type_prob": tp[i] if with_types else None,
                 "type": ty[i] if with_types else None,

@@ -205,3 +205,41 @@ def test_canvas_decoder_restatement_equals_direct_decoder():
         assert good[k].shape == ref[k].shape
         assert (good[k] - ref[k]).abs().max().item() <= 1e-5, k
     assert max((bad[k] - ref[k]).abs().max().item() for k in bad) > 1e-3     # the margin DOES leak without the re-zeroing
+
+
+def test_product_rows_to_dict_is_the_oracles_on_the_host():
+    """``DetectionCellPostProcessor.rows_to_dict`` (host side of the product: instance table (+ device contours) -> the
+    reference's per-tile dict, post_proc_cellvit.py:96-151) against the oracle's dict builder on the same oracle table: the cv2
+    contour path, the device-contour path (contours handed in as padded point rows), instances below 3 points dropped, key and
+    value types as the reference has them (np.int32 keys, int64 bbox, float64 centroid, int32 contour)."""
+    from cellvit_b200.post_proc_cellvit import MAX_PTS, ROW_DTYPE, DetectionCellPostProcessor
+    d = synth.synthetic_nuclei(256, 45, seed=11)
+    lab = po.proc_np_hv(d["np_bin"], d["hv"], 40)
+    orows = po.instance_table(lab, d["nt"], 6)
+    want = po.rows_to_dict(lab, orows)
+    rows = np.zeros(len(orows), ROW_DTYPE)
+    for f in ROW_DTYPE.names:
+        rows[f] = orows[f]
+
+    def same(got):
+        assert list(got) == list(want) and all(type(k) is np.int32 for k in got)
+        for k, w in want.items():
+            g = got[k]
+            for f in ("bbox", "centroid", "contour"):
+                assert g[f].dtype == w[f].dtype and np.array_equal(g[f], w[f]), (k, f)
+            assert g["type"] == w["type"] and g["type_prob"] == w["type_prob"]
+
+    same(DetectionCellPostProcessor.rows_to_dict(lab, rows))                                  # contours traced by cv2 on the host
+    pts = np.zeros((len(rows), MAX_PTS, 2), np.int16)
+    npts = np.zeros(len(rows), np.int32)                                                      # 0 points: dropped (as the < 3 rule says)
+    for i, r in enumerate(rows):
+        c = want.get(np.int32(r["id"]))
+        if c is not None:
+            npts[i] = len(c["contour"])
+            pts[i, :npts[i]] = c["contour"]
+    kept = []
+    same(DetectionCellPostProcessor.rows_to_dict(None, rows, True, pts, npts, kept))          # contours delivered by the device
+    assert [int(rows[i]["id"]) for i in kept] == [int(k) for k in want]
+    flagged = npts.copy()
+    flagged[::3] = -1                                                                         # device could not trace: cv2 fallback
+    same(DetectionCellPostProcessor.rows_to_dict(lab, rows, True, pts, flagged))
