@@ -306,12 +306,17 @@ class DetectionCellPostProcessor:
         bbox_all = np.stack([np.stack([rows["rmin"], rows["cmin"]], 1), np.stack([rows["rmax"], rows["cmax"]], 1)], 1).astype(np.int64)
         cent_all = np.stack([rows["cx"], rows["cy"]], 1)
         nn = npts.tolist() if npts is not None else None
-        pts32 = pts.astype(np.int32) if pts is not None else None   # a private copy: the entries below are views of its rows
+        if pts is not None:
+            # the device's padded point rows -> ONE compact int32 array of all contour points of the tile (a private copy of the
+            # pinned buffer); the dict entries below are slices of it
+            lens = np.clip(np.asarray(npts), 0, None)
+            flat = pts[np.arange(pts.shape[1])[None, :] < lens[:, None]].astype(np.int32)
+            offs = np.concatenate([[0], np.cumsum(lens)]).tolist()
         for i, inst_id in enumerate(ids):
             if nn is not None and nn[i] >= 0:
                 if nn[i] < 3:
                     continue  # "< 3 points dont make a contour" (post_proc_cellvit.py:110-113)
-                contour = pts32[i, :nn[i]]
+                contour = flat[offs[i]:offs[i + 1]]
             else:
                 import cv2
                 (rmin, cmin), (rmax, cmax) = bbox_all[i].tolist()
