@@ -104,8 +104,8 @@ def test_forward_matches_oracle(arch, size, B):
     assert errs["tokens"] <= 2e-2 * max(1.0, ref["tokens"].abs().max().item()), errs
 
 
-# ("ViT256", 8) = BASELINE config C2 (batch 8 x 1024^2); SAM-H at the C3 batch of 4: tests/test_gpu_parity_hardening.py
-@pytest.mark.parametrize("arch,B", [("SAM-H", 2), ("ViT256", 2), ("ViT256", 8)])
+# SAM-H at the C3 batch of 4: tests/test_gpu_parity_hardening.py; CellViT-256 at the C2 batch of 8: tests/test_gpu_x_c2_batch.py
+@pytest.mark.parametrize("arch,B", [("SAM-H", 2), ("ViT256", 2)])
 def test_forward_full_size_1024_matches_oracle_on_device(arch, B):
     """BASELINE.json's full tile size. The fp32 oracle (oracle/forward_oracle.py, plain torch ops) is evaluated on
     the GPU in fp32 with TF32 off -- at 1024^2 it needs ~40 s per SAM-H tile on CPU."""
