@@ -422,10 +422,13 @@ def run_gpu(args):
         peak, hbm, how = _peaks()
         achieved = gflop_tc * B * Kp / (tot_ms / 1000.0) / 1000.0  # TFLOP/s
         traffic, traffic_src = None, None
-        tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
-        if arch == "SAM-H" and B == 4 and os.path.exists(tpath):  # DRAM bytes per tile-engine launch from the committed ncu pass of this same step
-            tj = json.load(open(tpath))
-            traffic, traffic_src = tj.get("dram_bytes_per_launch"), "profiles/r1_traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum, mean over the step's tile-engine launches)"
+        for tname in ("r2_traffic.json", "r1_traffic.json"):   # the newest committed ncu pass of this same step (tile-engine launches)
+            tpath = os.path.join(ROOT, "profiles", tname)
+            if arch == "SAM-H" and B == 4 and os.path.exists(tpath):  # DRAM bytes per tile-engine launch
+                tj = json.load(open(tpath))
+                traffic = tj.get("dram_bytes_per_launch")
+                traffic_src = f"profiles/{tname} (ncu dram__bytes_read.sum + dram__bytes_write.sum, mean over the step's {tj.get('launches')} tile-engine launches)"
+                break
         roof = {"bound": "tensor", "kernel": "tc_kernel / conv_patch_kernel (tcgen05 GEMM / implicit-GEMM conv)", "achieved": achieved, "peak": peak,
                 "unit": "TFLOP/s", "frac": achieved / peak, "peak_source": how, "traffic": traffic, "traffic_unit": "bytes/launch",
                 "traffic_source": traffic_src,
