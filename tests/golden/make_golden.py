@@ -8,6 +8,8 @@ Fixtures (all derived from seeds, so only outputs are stored):
                      post_proc_cellvit.py:247) and the instance table fields (bbox, centroid, type, type_prob).
                      NOTE: the flood itself (P7) is the oracle restatement -- parity unpinned for that stage.
   forward_<arch>.npz : reference nn.Module forward on synthetic_tiles with weights.synth_state_dict(arch, seed=3)
+  forward_<tag>.npz  : the same for a non-square tile (48 x 80) and for the *Shared modules (cellvit_shared.py), params =
+                       [H, W, tile seed, weight seed, shared, regression_loss]
 """
 import os
 import sys
@@ -23,6 +25,9 @@ from oracle import postproc_oracle as po, ref_shim  # noqa: E402
 HERE = os.path.dirname(os.path.abspath(__file__))
 POSTPROC_CASES = [(128, 14, 0, 40, 0.0), (128, 20, 1, 20, 0.0), (192, 30, 2, 40, 0.03), (256, 48, 3, 40, 0.0)]
 FORWARD_CASES = [("ViT256", 64, 5), ("SAM-B", 64, 5)]
+# (file tag, arch, tile size, shared-decoder variant, regression_loss): non-square / non-native tile sizes and the *Shared modules
+FORWARD_CASES_EXTRA = [("ViT256_48x80", "ViT256", (48, 80), False, False), ("ViT256_shared", "ViT256", 64, True, False),
+                       ("SAM-B_shared_80", "SAM-B", 80, True, True)]
 
 
 def main():
@@ -54,6 +59,20 @@ def main():
             r = m(x, retrieve_tokens=True)
         np.savez_compressed(os.path.join(HERE, f"forward_{arch}.npz"), params=np.array([size, seed, 3], np.int64),
                             **{k: v.numpy() for k, v in r.items()})
+    import importlib
+    shared_mod = importlib.import_module("models.segmentation.cell_segmentation.cellvit_shared")
+    for tag, arch, size, shared, regression in FORWARD_CASES_EXTRA:
+        mod = shared_mod if shared else cellvit
+        cls = {("ViT256", False): "CellViT256", ("ViT256", True): "CellViT256Shared", ("SAM-B", False): "CellViTSAM", ("SAM-B", True): "CellViTSAMShared"}
+        ctor = getattr(mod, cls[(arch, shared)])
+        m = (ctor(None, 6, 19, regression_loss=regression) if arch == "ViT256" else ctor(None, 6, 19, arch, regression_loss=regression)).eval()
+        m.load_state_dict(weights.synth_state_dict(arch, 6, 19, seed=3, regression_loss=regression, shared=shared), strict=True)
+        x = torch.from_numpy(synth.synthetic_tiles(1, size, seed=5))
+        with torch.no_grad():
+            r = m(x, retrieve_tokens=True)
+        hw = (size, size) if isinstance(size, int) else size
+        np.savez_compressed(os.path.join(HERE, f"forward_{tag}.npz"), params=np.array([hw[0], hw[1], 5, 3, int(shared), int(regression)], np.int64),
+                            arch=np.array(arch), **{k: v.numpy() for k, v in r.items()})
 
 
 if __name__ == "__main__":

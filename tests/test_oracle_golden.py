@@ -45,6 +45,22 @@ def test_forward_oracle_vs_golden(arch):
         assert np.abs(o[k].numpy() - g[k]).max() <= 5e-6, k
 
 
+@pytest.mark.parametrize("tag", ["ViT256_48x80", "ViT256_shared", "SAM-B_shared_80"])
+def test_forward_oracle_vs_golden_shapes_and_shared_variants(tag):
+    """Fixtures made by the reference's own modules (tests/golden/make_golden.py): a non-square tile (cellvit.py:170-175) and the
+    ``*Shared`` variants (cellvit_shared.py), incl. the regression head split."""
+    g = np.load(os.path.join(GOLD, f"forward_{tag}.npz"))
+    H, W, seed, wseed, shared, regression = (int(v) for v in g["params"])
+    arch = str(g["arch"])
+    sd = weights.synth_state_dict(arch, 6, 19, seed=wseed, regression_loss=bool(regression), shared=bool(shared))
+    x = torch.from_numpy(synth.synthetic_tiles(1, (H, W), seed=seed))
+    o = forward_oracle.cellvit_forward(sd, x, arch, retrieve_tokens=True, regression_loss=bool(regression))
+    keys = ["tissue_types", "nuclei_binary_map", "hv_map", "nuclei_type_map", "tokens"] + (["regression_map"] if regression else [])
+    assert sorted(k for k in g.files if k not in ("params", "arch")) == sorted(keys)
+    for k in keys:
+        assert o[k].shape == g[k].shape and np.abs(o[k].numpy() - g[k]).max() <= 5e-6, k
+
+
 def test_watershed_tie_break_is_immaterial_on_nuclei_tiles():
     """The one unpinned choice of the P7 restatement -- how exact (value, age) ties between marker seeds are ordered -- does
     not change a single label on synthetic-nuclei tiles: an independent pure-Python flood gives the C oracle's labels under
